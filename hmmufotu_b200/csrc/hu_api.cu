@@ -1,0 +1,520 @@
+// C ABI: batch workspace, host-side band planning, staging, stage drivers and result read-back.
+#include "hu_batch.cuh"
+#include <string.h>
+#include <ctype.h>
+#include <utility>
+
+namespace hu {
+
+#define HU_TRY(x) do { int rc_ = (x); if (rc_ != HU_OK) return rc_; } while (0)
+
+template <typename T>
+static int balloc(hu_batch* b, T** p, size_t n) {
+	void* q = NULL;
+	cudaError_t e = cudaMalloc(&q, std::max<size_t>(n, 1) * sizeof(T));
+	if (e != cudaSuccess) {
+		setError("cudaMalloc of %zu bytes failed: %s", n * sizeof(T), cudaGetErrorString(e));
+		return HU_ERR_NOMEM;
+	}
+	b->allocs.push_back(q);
+	*p = (T*) q;
+	return HU_OK;
+}
+template <typename T>
+static int palloc(hu_batch* b, T** p, size_t n) {
+	void* q = NULL;
+	cudaError_t e = cudaMallocHost(&q, std::max<size_t>(n, 1) * sizeof(T));
+	if (e != cudaSuccess) {
+		setError("cudaMallocHost of %zu bytes failed: %s", n * sizeof(T), cudaGetErrorString(e));
+		return HU_ERR_NOMEM;
+	}
+	b->pinned.push_back(q);
+	*p = (T*) q;
+	return HU_OK;
+}
+
+// Band of one sequence as a chain of boxes (src/BandedHMMP7.cpp:794-881).  Returns false when the
+// ViterbiAlignPaths do not chain monotonically (the reference would sweep overlapping boxes in place).
+static bool planBand(int N, int K, const hu_vpath* vp, int nPaths, VPlan* plan) {
+	const double kMinGapFrac = 0.2; // src/BandedHMMP7.h
+	plan->nReg = 0;
+	for (int p = 0; p < nPaths; ++p) {
+		const hu_vpath& v = vp[p];
+		if (!(v.start >= 1 && v.start <= v.end && v.end <= K && v.from >= 1 && v.from <= v.to && v.to <= N && v.nIns >= 0 && v.nDel >= 0)) return false;
+		if (p > 0 && !(v.start >= vp[p - 1].end && v.from >= vp[p - 1].to)) return false;
+	}
+	int n = 0;
+	for (int p = 0; p < nPaths; ++p) {
+		const hu_vpath& v = vp[p];
+		int upQLen = p == 0 ? v.from - 1 : v.from - vp[p - 1].to;
+		if (upQLen < 0) upQLen = 0;
+		int up_start = p == 0 ? (int) (v.start - upQLen * (1 + kMinGapFrac)) : vp[p - 1].end;
+		if (up_start < 1) up_start = 1;
+		int up_from = p == 0 ? (int) (v.from - upQLen * (1 + kMinGapFrac)) : vp[p - 1].to;
+		if (up_from < 1) up_from = 1;
+		VRegion r;
+		memset(&r, 0, sizeof r);
+		r.j0 = up_start; r.j1 = v.start; r.i0 = up_from; r.i1 = v.from; r.useB = 1;
+		plan->reg[n++] = r;
+		memset(&r, 0, sizeof r);
+		r.j0 = v.start; r.j1 = v.end; r.i0 = v.from; r.i1 = v.to; r.useB = 1;
+		r.strip = 1; r.pStart = v.start; r.pFrom = v.from; r.nIns = v.nIns; r.nDel = v.nDel;
+		plan->reg[n++] = r;
+	}
+	const hu_vpath& last = vp[nPaths - 1];
+	const int downQLen = N - last.to;
+	int down_end = (int) (last.end + downQLen * (1 + kMinGapFrac));
+	int down_to = (int) (last.to + downQLen * (1 + kMinGapFrac));
+	if (down_end > K) down_end = K;
+	if (down_to > N) down_to = N;
+	VRegion r;
+	memset(&r, 0, sizeof r);
+	r.j0 = last.end; r.j1 = down_end; r.i0 = last.to; r.i1 = down_to; r.useB = 0;
+	plan->reg[n++] = r;
+	plan->nReg = n;
+	return true;
+}
+
+__global__ void windowsKernel(int n, const hu_align_row* __restrict__ merged, int* __restrict__ winStart, int* __restrict__ winEnd) {
+	const int r = blockIdx.x * blockDim.x + threadIdx.x;
+	if (r >= n) return;
+	const hu_align_row a = merged[r];
+	const bool bad = a.flags & (HU_ALIGN_INVALID | HU_ALIGN_CHIMERA);
+	winStart[r] = bad ? -1 : a.csStart - 1; // src/hmmufotu.cpp:645
+	winEnd[r] = bad ? -1 : a.csEnd - 1;
+}
+
+static void buildEqualPerm(int* perm) {
+	// the permutation std::sort(rbegin, rend, cmp) applies to n equal keys depends on n only; run the very
+	// call the reference makes (src/hmmufotu.cpp:730) on tagged elements and record what lands first
+	struct Cmp { static bool lt(const std::pair<double, int>& a, const std::pair<double, int>& b) { return a.first < b.first; } };
+	perm[0] = 0;
+	for (int n = 1; n <= HU_MAX_SEED; ++n) {
+		std::vector<std::pair<double, int> > v(n);
+		for (int i = 0; i < n; ++i) v[i] = std::make_pair(1.0, i);
+		std::sort(v.rbegin(), v.rend(), Cmp::lt);
+		perm[n] = v[0].second;
+	}
+}
+
+} // namespace hu
+
+using namespace hu;
+
+extern "C" {
+
+void* hu_host_alloc(size_t bytes) {
+	void* q = NULL;
+	if (cudaMallocHost(&q, bytes ? bytes : 1) != cudaSuccess) {
+		setError("cudaMallocHost of %zu bytes failed", bytes);
+		cudaGetLastError();
+		return NULL;
+	}
+	return q;
+}
+void hu_host_free(void* p) {
+	if (p) cudaFreeHost(p);
+}
+
+void hu_sep_params_default(hu_sep_params* p) {
+	p->maxNSeed = 50;
+	p->useTrueLoglik = 0;
+	p->maxDiff = INFINITY;
+	p->maxHeight = INFINITY;
+	p->maxError = 20;
+	p->equalSortPerm = NULL;
+}
+
+int hu_batch_create(hu_batch** out, hu_db* db, int32_t maxReads, int32_t maxSeqLen, int32_t paired) {
+	if (!out || !db || maxReads < 1 || maxSeqLen < 1) { setError("hu_batch_create: bad arguments"); return HU_ERR_ARG; }
+	HU_CUDA(cudaSetDevice(db->device));
+	hu_batch* b = new hu_batch();
+	memset(&b->vit, 0, sizeof b->vit);
+	memset(&b->seed, 0, sizeof b->seed);
+	memset(&b->stats, 0, sizeof b->stats);
+	b->db = db; b->maxReads = maxReads; b->maxSeqLen = maxSeqLen; b->paired = paired ? 1 : 0;
+	b->maxSeq = maxReads * (paired ? 2 : 1);
+	b->nReads = b->nSeq = 0; b->launches = 0;
+	b->dPtrs = NULL; b->ptrsCap = 0; b->placeSlab = NULL;
+	*out = b;
+	HU_CUDA(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
+	for (int i = 0; i < 16; ++i) HU_CUDA(cudaEventCreate(&b->ev[i]));
+	const int K = db->hmm.K, L = db->hmm.L;
+	const TreeDev& t = db->tree;
+	b->codesCap = (long long) b->maxSeq * maxSeqLen;
+	HU_TRY(balloc(b, &b->dCodes, (size_t) b->codesCap));
+	HU_TRY(balloc(b, &b->dPlans, (size_t) b->maxSeq));
+	b->tracesCap = (long long) b->maxSeq * (maxSeqLen + K + 4);
+	HU_TRY(balloc(b, &b->dTraces, (size_t) b->tracesCap));
+	HU_TRY(balloc(b, &b->vit.aligned, (size_t) b->maxSeq * L));
+	HU_TRY(balloc(b, &b->vit.rows, (size_t) b->maxSeq));
+	HU_TRY(balloc(b, &b->merged, (size_t) maxReads));
+	HU_TRY(balloc(b, &b->vit.fullCount, 2));
+	b->vit.fullCursor = b->vit.fullCount + 1;
+	HU_TRY(balloc(b, &b->vit.fullList, (size_t) b->maxSeq));
+	int sms = 0;
+	HU_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, db->device));
+	// Viterbi CTA shape: as many warps as the per-warp shared memory allows
+	int wpb = HU_VIT_WARPS;
+	const size_t perWarp = ((size_t) (maxSeqLen + 15) / 16 * 16 + (size_t) 3 * (maxSeqLen + 2) * 8 + 8 * 24 + 5 * sizeof(VRegion) + 16 + 15) / 16 * 16;
+	while (wpb > 1 && perWarp * wpb > 200 * 1024) wpb >>= 1;
+	if (perWarp > 200 * 1024) { setError("maxSeqLen %d too long for the Viterbi shared-memory layout", maxSeqLen); return HU_ERR_ARG; }
+	b->vit.warpsPerBlock = wpb;
+	b->vit.maxLen = maxSeqLen;
+	b->fullSlots = std::min(sms * 2 * wpb, std::max(wpb, (b->maxSeq + wpb - 1) / wpb * wpb));
+	b->vit.fullSlabWords = (size_t) K * ((maxSeqLen + 7) / 8);
+	HU_TRY(balloc(b, &b->vit.fullPtrs, b->vit.fullSlabWords * b->fullSlots));
+	HU_TRY(balloc(b, &b->winStart, (size_t) maxReads));
+	HU_TRY(balloc(b, &b->winEnd, (size_t) maxReads));
+	const int nReadsPad = (maxReads + HU_SCAN_READS - 1) / HU_SCAN_READS * HU_SCAN_READS;
+	HU_TRY(balloc(b, &b->seed.rplanes, (size_t) t.nWords * nReadsPad * 4));
+	HU_TRY(balloc(b, &b->seed.rValid, (size_t) nReadsPad));
+	HU_TRY(balloc(b, &b->seed.keys, (size_t) maxReads * t.scanPitch));
+	HU_TRY(balloc(b, &b->seed.seedIds, (size_t) maxReads * HU_MAX_SEED));
+	HU_TRY(balloc(b, &b->seed.nSeeds, (size_t) maxReads));
+	HU_TRY(balloc(b, &b->est, (size_t) maxReads * HU_MAX_SEED));
+	HU_TRY(balloc(b, &b->places, (size_t) maxReads * HU_MAX_SEED));
+	HU_TRY(balloc(b, &b->order, (size_t) maxReads * HU_MAX_SEED));
+	HU_TRY(balloc(b, &b->nKept, (size_t) maxReads));
+	HU_TRY(balloc(b, &b->best, (size_t) maxReads));
+	HU_TRY(balloc(b, &b->equalPerm, (size_t) HU_MAX_SEED + 1));
+	HU_TRY(balloc(b, &b->workCount, 4));
+	HU_CUDA(cudaMemset(b->seed.nSeeds, 0, (size_t) maxReads * sizeof(int)));
+	HU_CUDA(cudaMemset(b->nKept, 0, (size_t) maxReads * sizeof(int)));
+	int perm[HU_MAX_SEED + 1];
+	buildEqualPerm(perm);
+	HU_CUDA(cudaMemcpy(b->equalPerm, perm, sizeof perm, cudaMemcpyHostToDevice));
+	HU_TRY(palloc(b, &b->hPlansPinned, (size_t) b->maxSeq));
+	return HU_OK;
+}
+
+int hu_batch_destroy(hu_batch* b) {
+	if (!b) return HU_OK;
+	cudaSetDevice(b->db->device);
+	cudaStreamSynchronize(b->stream);
+	for (size_t i = 0; i < b->allocs.size(); ++i) cudaFree(b->allocs[i]);
+	for (size_t i = 0; i < b->pinned.size(); ++i) cudaFreeHost(b->pinned[i]);
+	if (b->dPtrs) cudaFree(b->dPtrs);
+	for (int i = 0; i < 16; ++i) cudaEventDestroy(b->ev[i]);
+	cudaStreamDestroy(b->stream);
+	delete b;
+	return HU_OK;
+}
+
+int hu_batch_upload(hu_batch* b, const hu_read_batch* rb) {
+	if (!b || !rb || rb->nReads < 1 || rb->nReads > b->maxReads) { setError("hu_batch_upload: bad batch size"); return HU_ERR_ARG; }
+	if ((rb->paired != 0) != (b->paired != 0)) { setError("hu_batch_upload: pairedness differs from the workspace"); return HU_ERR_ARG; }
+	HU_CUDA(cudaSetDevice(b->db->device));
+	const int nSeq = rb->nReads * (rb->paired ? 2 : 1);
+	const int K = b->db->hmm.K;
+	const long long nCodes = rb->offsets[nSeq] - rb->offsets[0];
+	if (nCodes > b->codesCap) { setError("hu_batch_upload: %lld bases exceed the workspace capacity %lld", nCodes, b->codesCap); return HU_ERR_ARG; }
+	long long ptrWords = 0, traceOff = 0;
+	VPlan* plans = b->hPlansPinned;
+	b->hTraceOff.resize(nSeq + 1);
+	for (int s = 0; s < nSeq; ++s) {
+		VPlan& p = plans[s];
+		memset(&p, 0, sizeof p);
+		const long long len = rb->offsets[s + 1] - rb->offsets[s];
+		if (len < 1 || len > b->maxSeqLen) { setError("hu_batch_upload: sequence %d has length %lld (workspace maxSeqLen %d)", s, len, b->maxSeqLen); return HU_ERR_ARG; }
+		p.N = (int) len;
+		p.codeOff = rb->offsets[s] - rb->offsets[0];
+		p.traceOff = traceOff;
+		b->hTraceOff[s] = traceOff;
+		traceOff += len + K + 4;
+		const int np = rb->nPaths ? rb->nPaths[s] : 0;
+		if (np < 0 || np > 2) { setError("hu_batch_upload: nPaths[%d] = %d", s, np); return HU_ERR_ARG; }
+		if (np == 0) p.flags = HU_ALIGN_NOSEED;
+		else if (!planBand(p.N, K, rb->vpaths + (size_t) s * 2, np, &p)) { p.nReg = 0; p.flags = HU_ALIGN_NOSEED | HU_ALIGN_IRREGULAR; }
+		for (int r = 0; r < p.nReg; ++r) {
+			VRegion& R = p.reg[r];
+			R.rowWords = (R.i1 - R.i0 + 1 + 7) / 8;
+			R.ptrOff = ptrWords;
+			ptrWords += (long long) R.rowWords * (R.j1 - R.j0 + 1);
+		}
+	}
+	b->hTraceOff[nSeq] = traceOff;
+	if (ptrWords > b->ptrsCap) { // grow the back-pointer buffer (synchronous; only when a batch needs more than any before)
+		HU_CUDA(cudaStreamSynchronize(b->stream));
+		if (b->dPtrs) cudaFree(b->dPtrs);
+		b->ptrsCap = ptrWords + ptrWords / 4 + 1024;
+		void* q = NULL;
+		cudaError_t e = cudaMalloc(&q, (size_t) b->ptrsCap * sizeof(uint32_t));
+		if (e != cudaSuccess) { b->dPtrs = NULL; b->ptrsCap = 0; setError("cudaMalloc of the back-pointer buffer (%lld words) failed", ptrWords); return HU_ERR_NOMEM; }
+		b->dPtrs = (uint32_t*) q;
+	}
+	b->nReads = rb->nReads; b->nSeq = nSeq;
+	HU_CUDA(cudaMemcpyAsync(b->dCodes, rb->codes + rb->offsets[0], (size_t) nCodes, cudaMemcpyHostToDevice, b->stream));
+	HU_CUDA(cudaMemcpyAsync(b->dPlans, plans, (size_t) nSeq * sizeof(VPlan), cudaMemcpyHostToDevice, b->stream));
+	b->vit.plans = b->dPlans; b->vit.codes = b->dCodes; b->vit.ptrs = b->dPtrs; b->vit.traces = b->dTraces;
+	b->launches = 0;
+	b->h2dBytes = nCodes + (long long) nSeq * sizeof(VPlan);
+	return HU_OK;
+}
+
+int hu_batch_set_aligned(hu_batch* b, int32_t n, const int8_t* codes, const int32_t* start, const int32_t* end) {
+	if (!b || n < 1 || n > b->maxReads || !codes || !start || !end) { setError("hu_batch_set_aligned: bad arguments"); return HU_ERR_ARG; }
+	HU_CUDA(cudaSetDevice(b->db->device));
+	const int L = b->db->hmm.L;
+	b->nReads = b->nSeq = n;
+	HU_CUDA(cudaMemcpyAsync(b->vit.aligned, codes, (size_t) n * L, cudaMemcpyHostToDevice, b->stream));
+	HU_CUDA(cudaMemcpyAsync(b->winStart, start, (size_t) n * sizeof(int), cudaMemcpyHostToDevice, b->stream));
+	HU_CUDA(cudaMemcpyAsync(b->winEnd, end, (size_t) n * sizeof(int), cudaMemcpyHostToDevice, b->stream));
+	b->launches = 0;
+	b->h2dBytes = (long long) n * L + 8LL * n;
+	return HU_OK;
+}
+
+int hu_align_batch(hu_batch* b, int mode) {
+	if (!b || b->nSeq < 1 || !b->vit.plans) { setError("hu_align_batch: no reads uploaded"); return HU_ERR_STATE; }
+	HU_CUDA(cudaSetDevice(b->db->device));
+	HU_CUDA(cudaEventRecord(b->ev[0], b->stream));
+	HU_TRY(launchViterbi(b, mode));
+	windowsKernel<<<(b->nReads + 127) / 128, 128, 0, b->stream>>>(b->nReads, b->merged, b->winStart, b->winEnd);
+	b->launches += 1;
+	HU_CUDA(cudaEventRecord(b->ev[1], b->stream));
+	return HU_OK;
+}
+
+int hu_seed_batch(hu_batch* b, const hu_sep_params* p) {
+	if (!b || !p || b->nReads < 1) { setError("hu_seed_batch: empty batch"); return HU_ERR_STATE; }
+	HU_CUDA(cudaSetDevice(b->db->device));
+	return launchSeed(b, p);
+}
+int hu_estimate_batch(hu_batch* b, const hu_sep_params* p) {
+	if (!b || !p || b->nReads < 1) { setError("hu_estimate_batch: empty batch"); return HU_ERR_STATE; }
+	HU_CUDA(cudaSetDevice(b->db->device));
+	return launchEstimate(b, p);
+}
+int hu_place_batch(hu_batch* b, const hu_sep_params* p) {
+	if (!b || !p || b->nReads < 1) { setError("hu_place_batch: empty batch"); return HU_ERR_STATE; }
+	HU_CUDA(cudaSetDevice(b->db->device));
+	return launchPlace(b, p);
+}
+int hu_finalize_batch(hu_batch* b, const hu_sep_params* p) {
+	if (!b || !p || b->nReads < 1) { setError("hu_finalize_batch: empty batch"); return HU_ERR_STATE; }
+	HU_CUDA(cudaSetDevice(b->db->device));
+	if (p->equalSortPerm) HU_CUDA(cudaMemcpyAsync(b->equalPerm, p->equalSortPerm, (HU_MAX_SEED + 1) * sizeof(int), cudaMemcpyHostToDevice, b->stream));
+	return launchFinalize(b, p);
+}
+int hu_assign_batch(hu_batch* b, int mode, const hu_sep_params* p) {
+	HU_TRY(hu_align_batch(b, mode));
+	HU_TRY(hu_seed_batch(b, p));
+	HU_TRY(hu_estimate_batch(b, p));
+	HU_TRY(hu_place_batch(b, p));
+	return hu_finalize_batch(b, p);
+}
+int hu_batch_sync(hu_batch* b) {
+	if (!b) return HU_ERR_ARG;
+	HU_CUDA(cudaSetDevice(b->db->device));
+	HU_CUDA(cudaStreamSynchronize(b->stream));
+	return HU_OK;
+}
+
+int hu_batch_get_align(hu_batch* b, hu_align_row* rows, char* traces, int64_t traceCap, int64_t* traceOff) {
+	if (!b || !rows) return HU_ERR_ARG;
+	HU_CUDA(cudaSetDevice(b->db->device));
+	HU_CUDA(cudaMemcpyAsync(rows, b->vit.rows, (size_t) b->nSeq * sizeof(hu_align_row), cudaMemcpyDeviceToHost, b->stream));
+	HU_CUDA(cudaStreamSynchronize(b->stream));
+	if (traces && traceOff) {
+		// device traces are stored end-to-start in fixed slots; hand them back packed and start-to-end
+		std::vector<char> raw((size_t) b->hTraceOff[b->nSeq]);
+		HU_CUDA(cudaMemcpy(raw.data(), b->dTraces, raw.size(), cudaMemcpyDeviceToHost));
+		int64_t o = 0;
+		for (int s = 0; s < b->nSeq; ++s) {
+			traceOff[s] = o;
+			const int n = rows[s].traceLen;
+			if (o + n + 1 > traceCap) { setError("hu_batch_get_align: trace buffer too small"); return HU_ERR_ARG; }
+			const char* src = raw.data() + b->hTraceOff[s];
+			for (int i = 0; i < n; ++i) traces[o + i] = src[n - 1 - i];
+			traces[o + n] = 0;
+			o += n + 1;
+		}
+		traceOff[b->nSeq] = o;
+	}
+	return HU_OK;
+}
+
+#define HU_GET(dst, src, count)                                                                                   \
+	do {                                                                                                          \
+		if (dst) HU_CUDA(cudaMemcpyAsync(dst, src, (size_t) (count) * sizeof(*(dst)), cudaMemcpyDeviceToHost, b->stream)); \
+	} while (0)
+
+int hu_batch_get_merged(hu_batch* b, hu_align_row* rows) {
+	if (!b) return HU_ERR_ARG;
+	HU_CUDA(cudaSetDevice(b->db->device));
+	HU_GET(rows, b->merged, b->nReads);
+	HU_CUDA(cudaStreamSynchronize(b->stream));
+	return HU_OK;
+}
+int hu_batch_get_aligned_codes(hu_batch* b, int8_t* codes) {
+	if (!b) return HU_ERR_ARG;
+	HU_CUDA(cudaSetDevice(b->db->device));
+	HU_GET(codes, b->vit.aligned, (size_t) b->nReads * b->db->hmm.L);
+	HU_CUDA(cudaStreamSynchronize(b->stream));
+	return HU_OK;
+}
+int hu_batch_get_seeds(hu_batch* b, int32_t* nSeeds, int32_t* ids, double* dist) {
+	if (!b) return HU_ERR_ARG;
+	HU_CUDA(cudaSetDevice(b->db->device));
+	std::vector<int> n(b->nReads), all((size_t) b->nReads * HU_MAX_SEED);
+	HU_CUDA(cudaMemcpyAsync(n.data(), b->seed.nSeeds, n.size() * sizeof(int), cudaMemcpyDeviceToHost, b->stream));
+	HU_CUDA(cudaMemcpyAsync(all.data(), b->seed.seedIds, all.size() * sizeof(int), cudaMemcpyDeviceToHost, b->stream));
+	std::vector<hu_place_row> est;
+	if (dist) {
+		est.resize((size_t) b->nReads * HU_MAX_SEED);
+		HU_CUDA(cudaMemcpyAsync(est.data(), b->est, est.size() * sizeof(hu_place_row), cudaMemcpyDeviceToHost, b->stream));
+	}
+	HU_CUDA(cudaStreamSynchronize(b->stream));
+	const int mx = b->seed.maxNSeed;
+	for (int r = 0; r < b->nReads; ++r) {
+		if (nSeeds) nSeeds[r] = n[r];
+		for (int s = 0; s < mx; ++s) {
+			if (ids) ids[(size_t) r * mx + s] = s < n[r] ? all[(size_t) r * HU_MAX_SEED + s] : -1;
+			if (dist) dist[(size_t) r * mx + s] = s < n[r] ? est[(size_t) r * HU_MAX_SEED + s].dist : NAN; // valid after hu_estimate_batch
+		}
+	}
+	return HU_OK;
+}
+static int getRows(hu_batch* b, const hu_place_row* src, bool ordered, int32_t* nKept, hu_place_row* rows) {
+	HU_CUDA(cudaSetDevice(b->db->device));
+	std::vector<int> n(b->nReads), ord((size_t) b->nReads * HU_MAX_SEED);
+	std::vector<hu_place_row> all((size_t) b->nReads * HU_MAX_SEED);
+	HU_CUDA(cudaMemcpyAsync(n.data(), b->nKept, n.size() * sizeof(int), cudaMemcpyDeviceToHost, b->stream));
+	HU_CUDA(cudaMemcpyAsync(ord.data(), b->order, ord.size() * sizeof(int), cudaMemcpyDeviceToHost, b->stream));
+	HU_CUDA(cudaMemcpyAsync(all.data(), src, all.size() * sizeof(hu_place_row), cudaMemcpyDeviceToHost, b->stream));
+	HU_CUDA(cudaStreamSynchronize(b->stream));
+	const int mx = b->seed.maxNSeed;
+	for (int r = 0; r < b->nReads; ++r) {
+		if (nKept) nKept[r] = n[r];
+		for (int i = 0; i < n[r] && rows; ++i)
+			rows[(size_t) r * mx + i] = all[(size_t) r * HU_MAX_SEED + (ordered ? ord[(size_t) r * HU_MAX_SEED + i] : i)];
+	}
+	return HU_OK;
+}
+int hu_batch_get_estimates(hu_batch* b, int32_t* nKept, hu_place_row* rows) {
+	if (!b) return HU_ERR_ARG;
+	return getRows(b, b->est, true, nKept, rows);
+}
+int hu_batch_get_places(hu_batch* b, int32_t* nKept, hu_place_row* rows) {
+	if (!b) return HU_ERR_ARG;
+	return getRows(b, b->places, false, nKept, rows);
+}
+int hu_batch_get_best(hu_batch* b, hu_place_row* rows) {
+	if (!b || !rows) return HU_ERR_ARG;
+	HU_CUDA(cudaSetDevice(b->db->device));
+	HU_GET(rows, b->best, b->nReads);
+	HU_CUDA(cudaStreamSynchronize(b->stream));
+	return HU_OK;
+}
+
+int hu_batch_stage_ms(hu_batch* b, float ms[8]) {
+	if (!b || !ms) return HU_ERR_ARG;
+	HU_CUDA(cudaSetDevice(b->db->device));
+	HU_CUDA(cudaStreamSynchronize(b->stream));
+	static const int from[6] = {0, 2, 3, 4, 5, 6}, to[6] = {1, 3, 4, 5, 6, 7};
+	for (int i = 0; i < 8; ++i) ms[i] = 0;
+	for (int i = 0; i < 6; ++i)
+		if (cudaEventElapsedTime(&ms[i], b->ev[from[i]], b->ev[to[i]]) != cudaSuccess) { ms[i] = -1; cudaGetLastError(); }
+	return HU_OK;
+}
+
+int hu_batch_get_stats(hu_batch* b, hu_batch_stats* s) {
+	if (!b || !s) return HU_ERR_ARG;
+	HU_CUDA(cudaSetDevice(b->db->device));
+	memset(s, 0, sizeof *s);
+	std::vector<hu_align_row> rows(b->nSeq);
+	std::vector<int> ws(b->nReads), we(b->nReads), ns(b->nReads), nk(b->nReads);
+	HU_CUDA(cudaStreamSynchronize(b->stream));
+	if (b->vit.plans) HU_CUDA(cudaMemcpy(rows.data(), b->vit.rows, rows.size() * sizeof(hu_align_row), cudaMemcpyDeviceToHost));
+	HU_CUDA(cudaMemcpy(ws.data(), b->winStart, ws.size() * sizeof(int), cudaMemcpyDeviceToHost));
+	HU_CUDA(cudaMemcpy(we.data(), b->winEnd, we.size() * sizeof(int), cudaMemcpyDeviceToHost));
+	HU_CUDA(cudaMemcpy(ns.data(), b->seed.nSeeds, ns.size() * sizeof(int), cudaMemcpyDeviceToHost));
+	HU_CUDA(cudaMemcpy(nk.data(), b->nKept, nk.size() * sizeof(int), cudaMemcpyDeviceToHost));
+	if (b->vit.plans)
+		for (int i = 0; i < b->nSeq; ++i) s->cells += rows[i].cells;
+	const long long nodes = b->db->tree.nNodes - 1;
+	for (int r = 0; r < b->nReads; ++r) {
+		if (ws[r] < 0) continue;
+		const long long W = we[r] - ws[r] + 1;
+		s->seedPairs += nodes;
+		s->seedBytes += nodes * W + W;
+		s->estItems += ns[r];
+		s->estBytes += 65 * W * ns[r];
+		s->placeItems += nk[r];
+		s->placeBytes += 64 * W * nk[r];
+	}
+	s->launches = b->launches;
+	return HU_OK;
+}
+
+// buildGlobalAlign (src/BandedHMMP7.cpp:1008-1081) with getPaddingSeq (cpp:1137-1186), on the host.
+int hu_trace_to_align(const hu_hmm_params* hmm, const char* read, int32_t readLen, const hu_align_row* row,
+		const char* trace, char* align) {
+	if (!hmm || !read || !row || !trace || !align) { setError("hu_trace_to_align: NULL argument"); return HU_ERR_ARG; }
+	const int L = hmm->L;
+	const int* p2cs = hmm->p2cs;
+	std::string out;
+	out.reserve(L);
+	const std::string seq(read, readLen);
+	const std::string seqN = seq.substr(0, row->seqStart - 1);
+	const std::string seqC = row->seqEnd < readLen ? seq.substr(row->seqEnd) : std::string();
+	const int csStart = row->csStart, csEnd = row->csEnd;
+	int j = 0, k = 0;
+	std::string insert;
+	const int tl = row->traceLen;
+	for (int t = 0; t < tl; ++t) {
+		switch (trace[t]) {
+		case 'B': { // right-justified N-terminal remainder
+			const int len = csStart - 1, n = (int) seqN.size();
+			if (n == 0) out.append(len, '.');
+			else if (n >= len) out.append(seqN, n - len, len);
+			else { out.append(len - n, '.'); out.append(seqN); }
+			j = row->seqStart; k = row->hmmStart;
+			break;
+		}
+		case 'M':
+			if (k > 1 && t > 1 && p2cs[k] - p2cs[k - 1] > 1) {
+				const int len = p2cs[k] - p2cs[k - 1] - 1, n = (int) insert.size();
+				if (n == 0) out.append(len, '-');
+				else if (n >= len) { // both halves of a too-long insert
+					out.append(insert, 0, len / 2);
+					out.append(insert, n - (len - len / 2), len - len / 2);
+				} else { // literal: the head of the insert is written on both sides of the fill
+					out.append(insert, 0, n / 2);
+					out.append(len - n, '-');
+					out.append(insert, 0, n - n / 2);
+				}
+			}
+			insert.clear();
+			out.push_back(seq.at(j - 1));
+			j++; k++;
+			break;
+		case 'I':
+			insert.clear();
+			while (t < tl && trace[t] == 'I') { insert.push_back((char) tolower(seq.at(j - 1))); j++; t++; }
+			t--;
+			break;
+		case 'D':
+			if (k > 1 && p2cs[k] - p2cs[k - 1] > 1) out.append(p2cs[k] - p2cs[k - 1] - 1, '-');
+			out.push_back('-');
+			k++;
+			break;
+		case 'E': { // left-justified C-terminal remainder
+			const int len = L - csEnd, n = (int) seqC.size();
+			if (n == 0) out.append(len, '.');
+			else if (n >= len) out.append(seqC, 0, len);
+			else { out.append(seqC); out.append(len - n, '.'); }
+			break;
+		}
+		default:
+			setError("hu_trace_to_align: bad trace state '%c'", trace[t]);
+			return HU_ERR_ARG;
+		}
+	}
+	if ((int) out.size() != L) { setError("hu_trace_to_align: aligned length %zu != L %d", out.size(), L); return HU_ERR_STATE; }
+	memcpy(align, out.data(), L);
+	return HU_OK;
+}
+
+} // extern "C"

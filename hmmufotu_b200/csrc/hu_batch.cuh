@@ -1,0 +1,108 @@
+// Batch workspace shared by the stage kernels (K1 Viterbi, K2 seed scan/select, K3 estimate, K4 place).
+#pragma once
+#include "hu_internal.cuh"
+
+#define HU_CODE_GAP (-2) // '-' in an aligned string (DegenAlphabet gap code, src/DegenAlphabet.cpp:43-64)
+#define HU_CODE_PAD (-3) // '.' padding outside the aligned region; any negative code is a gap to the SEP stages
+#define HU_VIT_WARPS 8   // max warps (= sequences) per Viterbi CTA
+#define HU_SCAN_TILE 512 // node slots per seed-scan CTA
+#define HU_SCAN_READS 8  // reads per seed-scan CTA
+
+namespace hu {
+
+struct VRegion {
+	int j0, j1, i0, i1;          // box: profile columns j0..j1, read rows i0..i1 (1-based, inclusive)
+	int strip, pStart, pFrom, nIns, nDel; // seed strip: only cells with -nDel <= (i-pFrom)-(j-pStart) <= nIns
+	int useB;                    // begin-state entry allowed (false in the downstream box)
+	int rowWords;                // back-pointer words per column = ceil(rows / 8)
+	int pad;
+	long long ptrOff;            // word offset of this box in the back-pointer buffer
+};
+struct VPlan {
+	int N, nReg, flags, pad;
+	long long codeOff, traceOff;
+	VRegion reg[5];
+};
+struct VitArgs {
+	int nSeq, maxLen, warpsPerBlock, pad;
+	const VPlan* plans;
+	const int8_t* codes;
+	uint32_t* ptrs;
+	char* traces;
+	int8_t* aligned;     // [nSeq][L]
+	hu_align_row* rows;  // [nSeq]
+	int* fullCount;      // [0] number of queued sequences, [1] cursor
+	int* fullCursor;
+	int* fullList;
+	uint32_t* fullPtrs;
+	size_t fullSlabWords;
+	double cNN, cNB, cEC, cCC;
+};
+
+struct SeedArgs {
+	int nReads, maxNSeed;
+	double maxDiff, maxHeight;
+	const int8_t* aligned;  // [nReads][L]
+	const int* winStart;    // 0-based inclusive window per read; winStart < 0: read is not placed
+	const int* winEnd;
+	uint32_t* rplanes;      // [nWords][nReadsPad][4]: hi, lo, valid, 0
+	int nReadsPad;
+	int* rValid;            // popcount of the valid plane per read
+	unsigned long long* keys; // [nReads][scanPitch]: (floor(d * 2^31 / N) << 32) | node id
+	int* seedIds;           // [nReads][HU_MAX_SEED]
+	int* nSeeds;            // [nReads]
+};
+
+} // namespace hu
+
+struct hu_batch {
+	hu_db* db;
+	cudaStream_t stream;
+	cudaEvent_t ev[16];
+	int maxReads, maxSeqLen, paired, maxSeq;
+	int nReads, nSeq;
+	long long launches;
+	// ---- K1 ----
+	hu::VitArgs vit;
+	int8_t* dCodes;
+	long long codesCap;
+	hu::VPlan* dPlans;
+	uint32_t* dPtrs;
+	long long ptrsCap;
+	char* dTraces;
+	long long tracesCap;
+	int fullSlots;
+	hu_align_row* merged;  // [maxReads]
+	std::vector<hu::VPlan> hPlans;
+	std::vector<long long> hTraceOff;
+	// ---- SEP ----
+	int* winStart;
+	int* winEnd;
+	hu::SeedArgs seed;
+	hu_place_row* est;     // [maxReads][HU_MAX_SEED] estimateSeq results, seed order
+	int* order;            // [maxReads][HU_MAX_SEED] filterPlacements order (indices into est)
+	int* nKept;            // [maxReads]
+	hu_place_row* places;  // [maxReads][HU_MAX_SEED] placeSeq results, filter order
+	hu_place_row* best;    // [maxReads]
+	int* equalPerm;        // [HU_MAX_SEED+1]
+	int* workItems;        // compacted (read, slot) lists for K3/K4
+	int* workCount;
+	double* placeSlab;     // global rho slabs for windows wider than the shared-memory capacity
+	long long h2dBytes;
+	// stats
+	hu_batch_stats stats;
+	int maxW;              // widest window of the current batch (host-side bound for shared memory sizing)
+	std::vector<void*> allocs;
+	std::vector<void*> pinned;
+	// pinned staging
+	int8_t* hCodes;
+	hu::VPlan* hPlansPinned;
+};
+
+namespace hu {
+int launchViterbi(hu_batch* b, int mode);
+int launchSeed(hu_batch* b, const hu_sep_params* p);
+int launchEstimate(hu_batch* b, const hu_sep_params* p);
+int launchPlace(hu_batch* b, const hu_sep_params* p);
+int launchFinalize(hu_batch* b, const hu_sep_params* p);
+} // namespace hu

@@ -1,0 +1,497 @@
+// Database replica on one device: profile tables, tree, node sequences (+ bit planes for the seed
+// scan), substitution model and the 4 x csLen conditional-likelihood messages of every directed edge.
+// Mirrors what hmmufotu loads from <db>.hmm / <db>.ptu (src/hmmufotu.cpp:457-494) and, when the
+// messages are not supplied, what hmmufotu-build computes by re-rooting at every node
+// (src/hmmufotu-build.cpp:455-459, src/PhyloTreeUnrooted.cpp:320-374).
+#include "hu_internal.cuh"
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+#include <algorithm>
+#include <cmath>
+
+namespace hu {
+
+static thread_local char g_err[512] = "";
+void setError(const char* fmt, ...) {
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(g_err, sizeof g_err, fmt, ap);
+	va_end(ap);
+}
+
+// ---------------------------------------------------------------- model (host) ----
+// Symmetric 4x4 eigen-solver (cyclic Jacobi rotations).  The reference calls Eigen::EigenSolver on
+// the trace-scaled Q (src/GTR.cpp:124-145); P(t) does not depend on the eigenvector basis.
+static void symEig4(double a[4][4], double w[4], double v[4][4]) {
+	for (int i = 0; i < 4; ++i)
+		for (int j = 0; j < 4; ++j) v[i][j] = i == j;
+	for (int sweep = 0; sweep < 100; ++sweep) {
+		double off = 0;
+		for (int i = 0; i < 4; ++i)
+			for (int j = i + 1; j < 4; ++j) off += fabs(a[i][j]);
+		if (off < 1e-290) break;
+		for (int p = 0; p < 3; ++p)
+			for (int q = p + 1; q < 4; ++q) {
+				if (a[p][q] == 0.0) continue;
+				const double tau = (a[q][q] - a[p][p]) / (2.0 * a[p][q]);
+				const double t = (tau >= 0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+				const double c = 1.0 / sqrt(1.0 + t * t), s = t * c;
+				for (int k = 0; k < 4; ++k) { // A <- A J
+					const double x = a[k][p], y = a[k][q];
+					a[k][p] = c * x - s * y;
+					a[k][q] = s * x + c * y;
+				}
+				for (int k = 0; k < 4; ++k) { // A <- J^T A
+					const double x = a[p][k], y = a[q][k];
+					a[p][k] = c * x - s * y;
+					a[q][k] = s * x + c * y;
+				}
+				for (int k = 0; k < 4; ++k) {
+					const double x = v[k][p], y = v[k][q];
+					v[k][p] = c * x - s * y;
+					v[k][q] = s * x + c * y;
+				}
+			}
+	}
+	for (int i = 0; i < 4; ++i) w[i] = a[i][i];
+}
+
+int buildModel(const hu_model_desc* d, Model* m) {
+	memset(m, 0, sizeof *m);
+	m->type = d->type;
+	m->dgK = d->dgK;
+	if (d->type < HU_GTR || d->type > HU_JC69) { setError("unknown substitution model type %d", d->type); return HU_ERR_ARG; }
+	if (d->dgK < 0 || d->dgK > HU_MAX_DG) { setError("discrete Gamma K=%d out of range", d->dgK); return HU_ERR_ARG; }
+	for (int i = 0; i < 4; ++i) m->pi[i] = d->pi[i];
+	m->kr = d->kr; m->ky = d->ky; m->kappa = d->kappa; m->beta = d->beta;
+	if (d->type == HU_K80) { // src/K80.h:97-100
+		m->beta = 1.0 / (2.0 * d->kappa);
+		for (int i = 0; i < 4; ++i) m->pi[i] = 0.25;
+	}
+	if (d->type == HU_JC69)
+		for (int i = 0; i < 4; ++i) m->pi[i] = 0.25;
+	for (int i = 0; i < 4; ++i) m->logPi[i] = log(m->pi[i]);
+	for (int k = 0; k < d->dgK; ++k) m->dgR[k] = d->dgRates[k];
+	if (d->type == HU_GTR) {
+		// Q = R * diag(pi), diagonal = -row sum, scaled so that -trace(Q) = 1 (src/DNASubModel.cpp:123-126)
+		double Q[4][4];
+		for (int i = 0; i < 4; ++i)
+			for (int j = 0; j < 4; ++j) Q[i][j] = i == j ? 0.0 : d->R[i * 4 + j] * m->pi[j];
+		double tr = 0;
+		for (int i = 0; i < 4; ++i) {
+			double rs = 0;
+			for (int j = 0; j < 4; ++j) rs += Q[i][j];
+			Q[i][i] = -rs;
+			tr += Q[i][i];
+		}
+		for (int i = 0; i < 4; ++i)
+			for (int j = 0; j < 4; ++j) Q[i][j] /= -tr;
+		// reversible: S = D^1/2 Q D^-1/2 is symmetric, Q = D^-1/2 W diag(w) W^T D^1/2
+		double S[4][4], W[4][4], w[4], sq[4];
+		for (int i = 0; i < 4; ++i) sq[i] = sqrt(m->pi[i]);
+		for (int i = 0; i < 4; ++i)
+			for (int j = 0; j < 4; ++j) S[i][j] = sq[i] * Q[i][j] / sq[j];
+		for (int i = 0; i < 4; ++i)
+			for (int j = i + 1; j < 4; ++j) S[i][j] = S[j][i] = 0.5 * (S[i][j] + S[j][i]);
+		symEig4(S, w, W);
+		for (int k = 0; k < 4; ++k) m->lambda[k] = w[k];
+		for (int i = 0; i < 4; ++i)
+			for (int k = 0; k < 4; ++k) {
+				m->U[i * 4 + k] = W[i][k] / sq[i];
+				m->Ui[k * 4 + i] = W[i][k] * sq[i];
+			}
+	}
+	return HU_OK;
+}
+
+// ---------------------------------------------------------------- tree evaluation kernels ----
+// per-edge transition matrices for every rate category: PP[node][k][16] = P(blen[node] * rate_k)
+__global__ void edgePrKernel(Model m, const double* __restrict__ blen, int nNodes, int KK, double* __restrict__ PP) {
+	const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+	if (idx >= nNodes * KK) return;
+	const int node = idx / KK, k = idx % KK;
+	double P[16];
+	modelPr(m, blen[node] * (m.dgK ? m.dgR[k] : 1.0), P);
+	for (int i = 0; i < 16; ++i) PP[(size_t) idx * 16 + i] = P[i];
+}
+
+// Upward pass for the nodes of one depth level: up[x] = loglik(x, j) with x's parent as root side.
+__global__ void upLevelKernel(Model m, const int* __restrict__ levelNodes, int nLevel, int csLen,
+		const int* __restrict__ childStart, const int* __restrict__ childList, const int8_t* __restrict__ seq,
+		const double* __restrict__ PP, int KK, double* __restrict__ up, int isRootLevel, double* __restrict__ rootMsg) {
+	const int x = levelNodes[blockIdx.y];
+	const int j = blockIdx.x * blockDim.x + threadIdx.x;
+	if (j >= csLen) return;
+	const int c0 = childStart[x], c1 = childStart[x + 1];
+	double mat[HU_MAX_DG][4];
+	for (int k = 0; k < KK; ++k) mat[k][0] = mat[k][1] = mat[k][2] = mat[k][3] = 0.0;
+	for (int c = c0; c < c1; ++c) {
+		const int ch = childList[c];
+		double v[4], y[4];
+		ld4(up + ((size_t) ch * csLen + j) * 4, v);
+		for (int k = 0; k < KK; ++k) {
+			dpsMat(PP + ((size_t) ch * KK + k) * 16, v, y);
+			for (int i = 0; i < 4; ++i) mat[k][i] += y[i];
+		}
+	}
+	double o[4];
+	const bool leaf = c0 == c1;
+	if (!leaf && m.dgK) rmes(mat, KK, o);
+	else for (int i = 0; i < 4; ++i) o[i] = mat[0][i];
+	if (leaf) {
+		double n[4];
+		leafMsg(m, seq[(size_t) x * csLen + j], n);
+		for (int i = 0; i < 4; ++i) o[i] += n[i];
+	}
+	double* dst = isRootLevel ? rootMsg + (size_t) j * 4 : up + ((size_t) x * csLen + j) * 4;
+	st4(dst, o);
+}
+
+// Downward pass: dn[x] = loglik(parent, j) seen from x (siblings' up messages + the parent's own dn)
+__global__ void dnLevelKernel(Model m, const int* __restrict__ levelNodes, int nLevel, int csLen, int root,
+		const int* __restrict__ parent, const int* __restrict__ childStart, const int* __restrict__ childList,
+		const double* __restrict__ PP, int KK, const double* __restrict__ up, double* __restrict__ dn) {
+	const int x = levelNodes[blockIdx.y];
+	const int j = blockIdx.x * blockDim.x + threadIdx.x;
+	if (j >= csLen) return;
+	const int pa = parent[x];
+	double mat[HU_MAX_DG][4];
+	for (int k = 0; k < KK; ++k) mat[k][0] = mat[k][1] = mat[k][2] = mat[k][3] = 0.0;
+	for (int c = childStart[pa]; c < childStart[pa + 1]; ++c) {
+		const int sib = childList[c];
+		if (sib == x) continue;
+		double v[4], y[4];
+		ld4(up + ((size_t) sib * csLen + j) * 4, v);
+		for (int k = 0; k < KK; ++k) {
+			dpsMat(PP + ((size_t) sib * KK + k) * 16, v, y);
+			for (int i = 0; i < 4; ++i) mat[k][i] += y[i];
+		}
+	}
+	if (pa != root) {
+		double v[4], y[4];
+		ld4(dn + ((size_t) pa * csLen + j) * 4, v);
+		for (int k = 0; k < KK; ++k) {
+			dpsMat(PP + ((size_t) pa * KK + k) * 16, v, y);
+			for (int i = 0; i < 4; ++i) mat[k][i] += y[i];
+		}
+	}
+	const int deg = childStart[pa + 1] - childStart[pa] + (pa == root ? 0 : 1);
+	double o[4];
+	if (deg != 1 && m.dgK) rmes(mat, KK, o);
+	else for (int i = 0; i < 4; ++i) o[i] = mat[0][i];
+	st4(dn + ((size_t) x * csLen + j) * 4, o);
+}
+
+// inferSeq(): arg-max of the upward message for internal nodes (src/PhyloTreeUnrooted.cpp:1085-1093)
+__global__ void inferSeqKernel(int nNodes, int csLen, int root, const int* __restrict__ childStart,
+		const double* __restrict__ up, const double* __restrict__ rootMsg, int8_t* __restrict__ seq) {
+	const int x = blockIdx.y;
+	const int j = blockIdx.x * blockDim.x + threadIdx.x;
+	if (j >= csLen || childStart[x] == childStart[x + 1]) return;
+	double v[4];
+	ld4((x == root ? rootMsg : up + (size_t) x * csLen * 4) + (size_t) j * 4, v);
+	seq[(size_t) x * csLen + j] = (int8_t) argmax4(v);
+}
+
+// node sequences -> bit planes [word][plane][slot] (hi, lo, valid)
+__global__ void packPlanesKernel(const int8_t* __restrict__ seq, int csLen, int nWords, const int* __restrict__ scanNode,
+		int nScan, int scanPitch, uint32_t* __restrict__ planes) {
+	const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+	const int w = blockIdx.y;
+	if (slot >= scanPitch) return;
+	uint32_t hi = 0, lo = 0, va = 0;
+	const int node = slot < nScan ? scanNode[slot] : -1;
+	if (node >= 0) {
+		const int8_t* s = seq + (size_t) node * csLen + w * 32;
+		const int n = min(32, csLen - w * 32);
+		for (int b = 0; b < n; ++b) {
+			const int c = s[b];
+			if (c >= 0) {
+				va |= 1u << b;
+				hi |= (uint32_t) ((c >> 1) & 1) << b;
+				lo |= (uint32_t) (c & 1) << b;
+			}
+		}
+	}
+	planes[((size_t) w * 3 + 0) * scanPitch + slot] = hi;
+	planes[((size_t) w * 3 + 1) * scanPitch + slot] = lo;
+	planes[((size_t) w * 3 + 2) * scanPitch + slot] = va;
+}
+
+template <typename T>
+static int devAlloc(hu_db* db, T** p, size_t n) {
+	void* q = NULL;
+	cudaError_t e = cudaMalloc(&q, std::max<size_t>(n, 1) * sizeof(T));
+	if (e != cudaSuccess) {
+		setError("cudaMalloc of %zu bytes failed: %s", n * sizeof(T), cudaGetErrorString(e));
+		return HU_ERR_NOMEM;
+	}
+	db->allocs.push_back(q);
+	db->bytes += n * sizeof(T);
+	*p = (T*) q;
+	return HU_OK;
+}
+#define HU_TRY(x) do { int rc_ = (x); if (rc_ != HU_OK) return rc_; } while (0)
+
+template <typename T>
+static int upload(hu_db* db, const T** dst, const T* src, size_t n) {
+	T* p;
+	HU_TRY(devAlloc(db, &p, n));
+	HU_CUDA(cudaMemcpy(p, src, n * sizeof(T), cudaMemcpyHostToDevice));
+	*dst = p;
+	return HU_OK;
+}
+
+static int createImpl(hu_db* db, const hu_hmm_params* hp, const hu_tree_desc* td, const hu_model_desc* md) {
+	HU_TRY(buildModel(md, &db->model));
+	// ---- profile: SoA tables with a padded pitch ----
+	const int K = hp->K, Kp = ((K + 1 + 15) / 16) * 16;
+	db->K = K; db->L = hp->L;
+	db->p2cs.assign(hp->p2cs, hp->p2cs + K + 1);
+	std::vector<double> eM((size_t) 4 * Kp, INFINITY), eI((size_t) 4 * Kp, INFINITY), tr((size_t) 7 * Kp, INFINITY), ent(Kp, INFINITY), ext(Kp, INFINITY);
+	static const int tIdx[7] = {0 * 3 + 0, 0 * 3 + 1, 0 * 3 + 2, 1 * 3 + 0, 1 * 3 + 1, 2 * 3 + 0, 2 * 3 + 2};
+	for (int k = 0; k <= K; ++k) {
+		for (int b = 0; b < 4; ++b) {
+			eM[(size_t) b * Kp + k] = hp->eM[(size_t) k * 4 + b];
+			eI[(size_t) b * Kp + k] = hp->eI[(size_t) k * 4 + b];
+		}
+		for (int t = 0; t < 7; ++t) tr[(size_t) t * Kp + k] = hp->T[(size_t) k * 9 + tIdx[t]];
+		ent[k] = hp->entry[k];
+		ext[k] = hp->exit[k];
+	}
+	db->hmm.K = K; db->hmm.L = hp->L; db->hmm.Kp = Kp;
+	HU_TRY(upload(db, &db->hmm.eM, eM.data(), eM.size()));
+	HU_TRY(upload(db, &db->hmm.eI, eI.data(), eI.size()));
+	HU_TRY(upload(db, &db->hmm.tr, tr.data(), tr.size()));
+	HU_TRY(upload(db, &db->hmm.ent, ent.data(), ent.size()));
+	HU_TRY(upload(db, &db->hmm.ext, ext.data(), ext.size()));
+	HU_TRY(upload(db, &db->hmm.p2cs, hp->p2cs, (size_t) K + 1));
+	// ---- tree ----
+	const int n = (int) td->nNodes, csLen = td->csLen;
+	if (td->nNodes <= 1 || td->nNodes > (1 << 30) || csLen <= 0 || csLen > 65535) { setError("bad tree dimensions"); return HU_ERR_ARG; }
+	if (hp->L != csLen) { setError("profile MAXL %d != tree csLen %d", hp->L, csLen); return HU_ERR_ARG; }
+	TreeDev& t = db->tree;
+	t.nNodes = n; t.csLen = csLen; t.root = td->root; t.nWords = (csLen + 31) / 32;
+	HU_TRY(upload(db, &t.parent, td->parent, (size_t) n));
+	HU_TRY(upload(db, &t.blen, td->blen, (size_t) n));
+	HU_TRY(upload(db, &t.height, td->height, (size_t) n));
+	HU_TRY(upload(db, &t.taxon, td->taxon, (size_t) n));
+	db->heightHost.assign(td->height, td->height + n);
+	int8_t* seq;
+	HU_TRY(devAlloc(db, &seq, (size_t) n * csLen));
+	HU_CUDA(cudaMemcpy(seq, td->seq, (size_t) n * csLen, cudaMemcpyHostToDevice));
+	t.seq = seq;
+	double *up, *dn;
+	const size_t msgN = (size_t) n * csLen * 4;
+	HU_TRY(devAlloc(db, &up, msgN));
+	HU_TRY(devAlloc(db, &dn, msgN));
+	t.up = up; t.dn = dn;
+	// children in CSR form (neighbour order = ascending id, as built from a parent vector)
+	std::vector<int> childStart(n + 1, 0), childList(std::max(0, n - 1)), depth(n, -1);
+	for (int x = 0; x < n; ++x)
+		if (td->parent[x] >= 0) childStart[td->parent[x] + 1]++;
+	for (int x = 0; x < n; ++x) childStart[x + 1] += childStart[x];
+	{
+		std::vector<int> fill(childStart.begin(), childStart.end() - 1);
+		for (int x = 0; x < n; ++x)
+			if (td->parent[x] >= 0) childList[fill[td->parent[x]]++] = x;
+	}
+	if ((td->up == NULL) != (td->dn == NULL)) { setError("up and dn must both be given or both be NULL"); return HU_ERR_ARG; }
+	if (td->up) {
+		HU_CUDA(cudaMemcpy(up, td->up, msgN * sizeof(double), cudaMemcpyHostToDevice));
+		HU_CUDA(cudaMemcpy(dn, td->dn, msgN * sizeof(double), cudaMemcpyHostToDevice));
+	} else {
+		// depth levels by breadth-first traversal from the root
+		std::vector<int> order;
+		order.reserve(n);
+		order.push_back(td->root);
+		depth[td->root] = 0;
+		for (size_t h = 0; h < order.size(); ++h) {
+			const int x = order[h];
+			for (int c = childStart[x]; c < childStart[x + 1]; ++c) {
+				depth[childList[c]] = depth[x] + 1;
+				order.push_back(childList[c]);
+			}
+		}
+		if ((int) order.size() != n) { setError("parent vector does not describe a tree rooted at %d", td->root); return HU_ERR_ARG; }
+		const int maxDepth = depth[order.back()];
+		std::vector<int> levelStart(maxDepth + 2, 0);
+		for (int x = 0; x < n; ++x) levelStart[depth[x] + 1]++;
+		for (int d = 0; d <= maxDepth; ++d) levelStart[d + 1] += levelStart[d];
+		int *dChildStart, *dChildList, *dOrder;
+		double *dPP, *dRootMsg;
+		const int KK = std::max(1, db->model.dgK);
+		// scratch (freed below): not part of the replica
+		HU_CUDA(cudaMalloc(&dChildStart, (n + 1) * sizeof(int)));
+		HU_CUDA(cudaMalloc(&dChildList, std::max(1, n - 1) * sizeof(int)));
+		HU_CUDA(cudaMalloc(&dOrder, n * sizeof(int)));
+		HU_CUDA(cudaMalloc(&dPP, (size_t) n * KK * 16 * sizeof(double)));
+		HU_CUDA(cudaMalloc(&dRootMsg, (size_t) csLen * 4 * sizeof(double)));
+		HU_CUDA(cudaMemcpy(dChildStart, childStart.data(), (n + 1) * sizeof(int), cudaMemcpyHostToDevice));
+		HU_CUDA(cudaMemcpy(dChildList, childList.data(), (n - 1) * sizeof(int), cudaMemcpyHostToDevice));
+		HU_CUDA(cudaMemcpy(dOrder, order.data(), n * sizeof(int), cudaMemcpyHostToDevice)); // BFS order is level-sorted
+		edgePrKernel<<<(n * KK + 127) / 128, 128>>>(db->model, t.blen, n, KK, dPP);
+		const int TB = 128;
+		const dim3 gx((csLen + TB - 1) / TB);
+		for (int d = maxDepth; d >= 0; --d) {
+			const int cnt = levelStart[d + 1] - levelStart[d];
+			for (int o = 0; o < cnt; o += 65535) {
+				const int c = std::min(65535, cnt - o);
+				upLevelKernel<<<dim3(gx.x, c), TB>>>(db->model, dOrder + levelStart[d] + o, c, csLen, dChildStart, dChildList, seq, dPP, KK, up, d == 0, dRootMsg);
+			}
+		}
+		if (td->inferInternalSeq)
+			for (int o = 0; o < n; o += 65535) {
+				// grid.y indexes nodes o..o+c-1 through pointer offsets
+				const int c = std::min(65535, n - o);
+				inferSeqKernel<<<dim3(gx.x, c), TB>>>(c, csLen, td->root - o, dChildStart + o, up + (size_t) o * csLen * 4, dRootMsg, seq + (size_t) o * csLen);
+			}
+		for (int d = 1; d <= maxDepth; ++d) {
+			const int cnt = levelStart[d + 1] - levelStart[d];
+			for (int o = 0; o < cnt; o += 65535) {
+				const int c = std::min(65535, cnt - o);
+				dnLevelKernel<<<dim3(gx.x, c), TB>>>(db->model, dOrder + levelStart[d] + o, c, csLen, td->root, t.parent, dChildStart, dChildList, dPP, KK, up, dn);
+			}
+		}
+		HU_CUDA(cudaGetLastError());
+		HU_CUDA(cudaDeviceSynchronize());
+		cudaFree(dChildStart); cudaFree(dChildList); cudaFree(dOrder); cudaFree(dPP); cudaFree(dRootMsg);
+		// the root has no parent edge: keep its rows defined
+		HU_CUDA(cudaMemset(up + (size_t) td->root * csLen * 4, 0, (size_t) csLen * 4 * sizeof(double)));
+		HU_CUDA(cudaMemset(dn + (size_t) td->root * csLen * 4, 0, (size_t) csLen * 4 * sizeof(double)));
+	}
+	// ---- scan order + bit planes (after sequence inference) ----
+	std::vector<int8_t> hseq;
+	const int8_t* hs = td->seq;
+	if (!td->up && td->inferInternalSeq) {
+		hseq.resize((size_t) n * csLen);
+		HU_CUDA(cudaMemcpy(hseq.data(), seq, hseq.size(), cudaMemcpyDeviceToHost));
+		hs = hseq.data();
+	}
+	std::vector<int> gapNodes, fullNodes;
+	for (int x = 0; x < n; ++x) {
+		if (x == td->root) continue;
+		const int8_t* s = hs + (size_t) x * csLen;
+		bool gap = false;
+		for (int j = 0; j < csLen && !gap; ++j) gap = s[j] < 0;
+		(gap ? gapNodes : fullNodes).push_back(x);
+	}
+	// gap block padded to a multiple of the scan tile so that every tile is homogeneous
+	const int TILE = 512;
+	std::vector<int> scanNode;
+	scanNode.insert(scanNode.end(), gapNodes.begin(), gapNodes.end());
+	while (scanNode.size() % TILE) scanNode.push_back(-1);
+	t.nGapSlots = (int) scanNode.size();
+	scanNode.insert(scanNode.end(), fullNodes.begin(), fullNodes.end());
+	t.nScan = (int) scanNode.size();
+	while (scanNode.size() % TILE) scanNode.push_back(-1);
+	t.scanPitch = (int) scanNode.size();
+	// padding slots (inside the gap block and at the tail) carry node -1 and all-zero planes
+	HU_TRY(upload(db, &t.scanNode, scanNode.data(), scanNode.size()));
+	uint32_t* planes;
+	HU_TRY(devAlloc(db, &planes, (size_t) t.nWords * 3 * t.scanPitch));
+	HU_CUDA(cudaMemset(planes, 0, (size_t) t.nWords * 3 * t.scanPitch * sizeof(uint32_t)));
+	{
+		packPlanesKernel<<<dim3((t.scanPitch + 127) / 128, t.nWords), 128>>>(seq, csLen, t.nWords, t.scanNode, t.nScan, t.scanPitch, planes);
+		HU_CUDA(cudaGetLastError());
+		HU_CUDA(cudaDeviceSynchronize());
+	}
+	t.planes = planes;
+	return HU_OK;
+}
+
+} // namespace hu
+
+extern "C" {
+
+const char* hu_last_error(void) { return hu::g_err; }
+const char* hu_version(void) { return "hmmufotu-b200 0.1 (reference HmmUFOtu v1.5.1)"; }
+
+int hu_hmm_finalize(int32_t K, const double* T, double* entry, double* exit_) {
+	if (K < 1 || !T || !entry || !exit_) { hu::setError("hu_hmm_finalize: bad arguments"); return HU_ERR_ARG; }
+	enum { M = 0, I = 1, D = 2 };
+#define TC(k, a, b) T[(size_t) (k) *9 + (a) *3 + (b)]
+	// adjustProfileLocalMode (src/BandedHMMP7.cpp:721-733): uniform entry/exit probabilities
+	std::vector<double> en(K + 1, exp(-TC(0, M, M))), ex(K + 1, exp(-TC(K, M, M)));
+	en[0] = ex[0] = 0;
+	// wingRetract (src/BandedHMMP7.cpp:1083-1120): fold the B->D..D->M and M->D..D->E paths in
+	for (int j = 2; j <= K; ++j) {
+		double cost = 0;
+		cost += TC(0, M, D);
+		for (int i = 1; i < j - 1; ++i) cost += TC(i, D, D);
+		cost += TC(j - 1, D, M);
+		en[j] += exp(-cost);
+		if (en[j] > 1) en[j] = 1;
+	}
+	for (int i = 1; i <= K - 1; ++i) {
+		double cost = 0;
+		cost += TC(i, M, D);
+		for (int j = i + 1; j < K; ++j) cost += TC(j, D, D);
+		cost += TC(K, D, M);
+		ex[i] += exp(-cost);
+		if (ex[i] > 1) ex[i] = 1;
+	}
+#undef TC
+	for (int k = 0; k <= K; ++k) {
+		entry[k] = -log(en[k]);
+		exit_[k] = -log(ex[k]);
+	}
+	return HU_OK;
+}
+
+int hu_model_Pr(const hu_model_desc* d, double v, double* P16) {
+	hu::Model m;
+	int rc = hu::buildModel(d, &m);
+	if (rc != HU_OK) return rc;
+	hu::modelPr(m, v, P16);
+	return HU_OK;
+}
+
+int hu_db_create(hu_db** out, const hu_hmm_params* hmm, const hu_tree_desc* tree, const hu_model_desc* model, int device) {
+	if (!out || !hmm || !tree || !model) { hu::setError("hu_db_create: NULL argument"); return HU_ERR_ARG; }
+	int nDev = 0;
+	cudaError_t e = cudaGetDeviceCount(&nDev);
+	if (e != cudaSuccess || nDev == 0) {
+		hu::setError("no CUDA device available (%s); this library has no CPU fallback", cudaGetErrorString(e));
+		return HU_ERR_CUDA;
+	}
+	HU_CUDA(cudaSetDevice(device));
+	hu_db* db = new hu_db();
+	db->device = device;
+	int rc = hu::createImpl(db, hmm, tree, model);
+	if (rc != HU_OK) {
+		hu_db_destroy(db);
+		return rc;
+	}
+	*out = db;
+	return HU_OK;
+}
+
+int hu_db_destroy(hu_db* db) {
+	if (!db) return HU_OK;
+	cudaSetDevice(db->device);
+	for (size_t i = 0; i < db->allocs.size(); ++i) cudaFree(db->allocs[i]);
+	delete db;
+	return HU_OK;
+}
+
+int hu_db_get_messages(hu_db* db, int64_t node0, int64_t n, double* up, double* dn) {
+	if (!db || node0 < 0 || node0 + n > db->tree.nNodes) { hu::setError("hu_db_get_messages: bad range"); return HU_ERR_ARG; }
+	HU_CUDA(cudaSetDevice(db->device));
+	const size_t per = (size_t) db->tree.csLen * 4;
+	if (up) HU_CUDA(cudaMemcpy(up, db->tree.up + node0 * per, n * per * sizeof(double), cudaMemcpyDeviceToHost));
+	if (dn) HU_CUDA(cudaMemcpy(dn, db->tree.dn + node0 * per, n * per * sizeof(double), cudaMemcpyDeviceToHost));
+	return HU_OK;
+}
+
+int hu_db_get_seq(hu_db* db, int64_t node0, int64_t n, int8_t* seq) {
+	if (!db || node0 < 0 || node0 + n > db->tree.nNodes || !seq) { hu::setError("hu_db_get_seq: bad range"); return HU_ERR_ARG; }
+	HU_CUDA(cudaSetDevice(db->device));
+	HU_CUDA(cudaMemcpy(seq, db->tree.seq + node0 * db->tree.csLen, (size_t) n * db->tree.csLen, cudaMemcpyDeviceToHost));
+	return HU_OK;
+}
+
+int64_t hu_db_bytes(hu_db* db) { return db ? db->bytes : 0; }
+
+} // extern "C"

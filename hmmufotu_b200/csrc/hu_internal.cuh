@@ -1,0 +1,205 @@
+// Internal declarations shared by the kernels and the C ABI (hmmufotu_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+#include <string>
+#include <vector>
+#include <algorithm>
+#include "../../include/hmmufotu_b200.h"
+
+#define HU_HD __host__ __device__ __forceinline__
+
+namespace hu {
+
+// ---------------------------------------------------------------- error plumbing ----
+void setError(const char* fmt, ...);
+#define HU_CUDA(call)                                                                      \
+	do {                                                                                   \
+		cudaError_t e_ = (call);                                                           \
+		if (e_ != cudaSuccess) {                                                           \
+			hu::setError("%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+			return HU_ERR_CUDA;                                                            \
+		}                                                                                  \
+	} while (0)
+
+// ---------------------------------------------------------------- substitution model ----
+// Derived form of hu_model_desc; Pr() runs identically on host and device.
+struct Model {
+	int type;
+	int dgK;
+	double pi[4];
+	double logPi[4];
+	double kr, ky, kappa, beta;
+	double lambda[4];   // GTR: eigenvalues of the trace-scaled Q
+	double U[16], Ui[16]; // GTR: eigenvectors / inverse, row-major
+	double dgR[HU_MAX_DG];
+};
+int buildModel(const hu_model_desc* d, Model* m); // host: eigen-decomposition etc.
+
+// DNASubModel::Pr(v): GTR src/GTR.h:116-121; TN93 src/TN93.h:113-154; HKY85 src/HKY85.h:111-153;
+// F81 src/F81.h:110-118; K80 src/K80.h:109-118; JC69 src/JC69.h:97-101.  Row-major P[i*4+j].
+HU_HD void modelPr(const Model& m, double v, double* P) {
+	switch (m.type) {
+	case HU_GTR: {
+		if (v == 0) {
+			for (int i = 0; i < 16; ++i) P[i] = (i % 5 == 0) ? 1.0 : 0.0;
+			return;
+		}
+		double e[4];
+		for (int k = 0; k < 4; ++k) e[k] = exp(m.lambda[k] * v);
+		for (int i = 0; i < 4; ++i)
+			for (int j = 0; j < 4; ++j) {
+				double s = 0;
+				for (int k = 0; k < 4; ++k) s += m.U[i * 4 + k] * e[k] * m.Ui[k * 4 + j];
+				P[i * 4 + j] = s;
+			}
+		return;
+	}
+	case HU_TN93:
+	case HU_HKY85: {
+		const double kR = m.type == HU_TN93 ? m.kr : m.kappa, kY = m.type == HU_TN93 ? m.ky : m.kappa;
+		const double a = m.pi[0], c = m.pi[1], g = m.pi[2], t = m.pi[3];
+		const double pr = a + g, py = c + t;
+		const double e = exp(-m.beta * v);
+		const double eR = exp(-(1 + pr * (kR - 1)) * m.beta * v);
+		const double eY = exp(-(1 + py * (kY - 1)) * m.beta * v);
+		const double tv = 1 - e;
+		P[0] = (a * (pr + py * e) + g * eR) / pr;  P[1] = c * tv;  P[2] = (g * (pr + py * e) - g * eR) / pr;  P[3] = t * tv;
+		P[4] = a * tv;  P[5] = (c * (py + pr * e) + t * eY) / py;  P[6] = g * tv;  P[7] = (t * (py + pr * e) - t * eY) / py;
+		P[8] = (a * (pr + py * e) - a * eR) / pr;  P[9] = c * tv;  P[10] = (g * (pr + py * e) + a * eR) / pr;  P[11] = t * tv;
+		P[12] = a * tv;  P[13] = (c * (py + pr * e) - c * eY) / py;  P[14] = g * tv;  P[15] = (t * (py + pr * e) + c * eY) / py;
+		if (P[2] < 0) P[2] = 0;
+		if (P[7] < 0) P[7] = 0;
+		if (P[8] < 0) P[8] = 0;
+		if (P[13] < 0) P[13] = 0;
+		return;
+	}
+	case HU_F81: {
+		const double e = exp(-m.beta * v);
+		for (int i = 0; i < 4; ++i)
+			for (int j = 0; j < 4; ++j) P[i * 4 + j] = (i == j ? e : 0.0) + m.pi[j] * (1 - e);
+		return;
+	}
+	case HU_K80: {
+		const double e = exp(-4 * m.beta * v);
+		const double eV = exp(-2 * (1 + m.kappa) * m.beta * v);
+		const double dg = (1.0 + e + 2 * eV) / 4, ti = (1.0 + e - 2 * eV) / 4, tv = (1.0 - e) / 4;
+		for (int i = 0; i < 16; ++i) P[i] = tv;
+		for (int i = 0; i < 4; ++i) P[i * 4 + i] = dg;
+		P[2] = P[8] = P[7] = P[13] = ti;
+		return;
+	}
+	default: { // JC69
+		const double x = exp(-4 * v / 3);
+		const double off = (1 - x) / 4, dg = (1 + 3 * x) / 4;
+		for (int i = 0; i < 16; ++i) P[i] = off;
+		for (int i = 0; i < 4; ++i) P[i * 4 + i] = dg;
+		return;
+	}
+	}
+}
+
+// ---------------------------------------------------------------- scaled log-space primitives ----
+// src/PhyloTreeUnrooted.h:1488-1529.  MIN_LOGLIK_EXP = DBL_MIN_EXP / 2 = -510 (src/PhyloTreeUnrooted.cpp:68).
+#define HU_MIN_LOGLIK_EXP (-510.0)
+
+HU_HD double scaleOf(double mx) { return (mx != -INFINITY && mx < HU_MIN_LOGLIK_EXP) ? HU_MIN_LOGLIK_EXP - mx : 0.0; }
+HU_HD double max4(const double* v) { return fmax(fmax(v[0], v[1]), fmax(v[2], v[3])); }
+HU_HD int argmax4(const double* v) { // maxCoeff(&idx): first strict maximum
+	int b = 0;
+	double m = v[0];
+	if (v[1] > m) { m = v[1]; b = 1; }
+	if (v[2] > m) { m = v[2]; b = 2; }
+	if (v[3] > m) { b = 3; }
+	return b;
+}
+// Y = dot_product_scaled(P, V): Y_i = log(sum_k P_ik exp(V_k + s)) - s
+HU_HD void dpsMat(const double* P, const double* V, double* Y) {
+	const double s = scaleOf(max4(V));
+	const double e0 = exp(V[0] + s), e1 = exp(V[1] + s), e2 = exp(V[2] + s), e3 = exp(V[3] + s);
+	for (int i = 0; i < 4; ++i)
+		Y[i] = log((P[i * 4] * e0 + P[i * 4 + 1] * e1) + (P[i * 4 + 2] * e2 + P[i * 4 + 3] * e3)) - s;
+}
+HU_HD double dpsVec(const double* pi, const double* V) {
+	const double s = scaleOf(max4(V));
+	return log((pi[0] * exp(V[0] + s) + pi[2] * exp(V[2] + s)) + (pi[1] * exp(V[1] + s) + pi[3] * exp(V[3] + s))) - s;
+}
+// leaf message of a base code (src/PhyloTreeUnrooted.h:1431-1437)
+HU_HD void leafMsg(const Model& m, int b, double* Y) {
+	if (b >= 0) {
+		Y[0] = Y[1] = Y[2] = Y[3] = -INFINITY;
+		Y[b] = 0.0;
+	} else
+		for (int k = 0; k < 4; ++k) Y[k] = m.logPi[k];
+}
+
+// row_mean_exp_scaled (src/PhyloTreeUnrooted.h:1521-1529) over KK category columns held in mat[k][4]
+HU_HD void rmes(const double (*mat)[4], int KK, double* Y) {
+	for (int i = 0; i < 4; ++i) {
+		double mx = mat[0][i];
+		for (int k = 1; k < KK; ++k) mx = fmax(mx, mat[k][i]);
+		const double sc = scaleOf(mx);
+		double s = 0;
+		for (int k = 0; k < KK; ++k) s += exp(mat[k][i] + sc);
+		Y[i] = log(s / KK) - sc;
+	}
+}
+
+#ifdef __CUDACC__
+__device__ __forceinline__ void ld4(const double* p, double* v) { // one 4-vector message column, 2 x 128-bit
+	const double2 a = __ldg(reinterpret_cast<const double2*>(p));
+	const double2 b = __ldg(reinterpret_cast<const double2*>(p) + 1);
+	v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+__device__ __forceinline__ void st4(double* p, const double* v) {
+	reinterpret_cast<double2*>(p)[0] = make_double2(v[0], v[1]);
+	reinterpret_cast<double2*>(p)[1] = make_double2(v[2], v[3]);
+}
+#endif
+
+// ---------------------------------------------------------------- device-resident database ----
+struct HmmDev {
+	int K, L, Kp;            // Kp: padded row pitch of the per-column tables (multiple of 16)
+	const double* eM;        // [4][Kp]
+	const double* eI;        // [4][Kp]
+	const double* tr;        // [7][Kp]: MM MI MD IM II DM DD
+	const double* ent;       // [Kp]
+	const double* ext;       // [Kp]
+	const int* p2cs;         // [K+1]
+};
+enum { T_MM = 0, T_MI = 1, T_MD = 2, T_IM = 3, T_II = 4, T_DM = 5, T_DD = 6 };
+
+struct TreeDev {
+	int nNodes, csLen, root;
+	int nWords;              // ceil(csLen / 32)
+	const int* parent;
+	const double* blen;
+	const double* height;
+	const int8_t* seq;       // [nNodes][csLen]
+	const int* taxon;
+	const double* up;        // [nNodes][csLen][4]
+	const double* dn;
+	// bit planes for the seed scan: [word][plane][nodeSlot], nodeSlot = position in scanOrder
+	const uint32_t* planes;
+	int nScan;               // number of scan slots (non-root nodes), padded to scanPitch
+	int scanPitch;
+	const int* scanNode;     // slot -> node id
+	int nGapSlots;           // slots [0, nGapSlots) hold nodes whose sequence has gaps (need the valid plane)
+};
+
+} // namespace hu
+
+struct hu_db {
+	int device;
+	hu::Model model;
+	hu::HmmDev hmm;
+	hu::TreeDev tree;
+	std::vector<void*> allocs;
+	int64_t bytes;
+	// host copies used by the facades / stage planning
+	int K, L;
+	std::vector<int> p2cs;
+	std::vector<double> heightHost;
+	hu_db() : device(0), bytes(0), K(0), L(0) {}
+};

@@ -1,0 +1,341 @@
+// K4: the "Place" stage of SEP -- PTUnrooted::placeSeq on the private 4-node tree {v, u, r, n}
+// (src/PhyloTreeUnrooted.cpp:879-954), i.e. the joint branch-length optimisation (cpp:800-847) built on
+// Felsenstein's single-branch EM (cpp:749-798) and the dGamma-mixed message rebuilds (cpp:320-346),
+// then calcQValues + the final sort (src/HmmUFOtu_main.cpp:182-216, src/hmmufotu.cpp:725-733).
+//
+// One warp per (read, placement), persistent over the item space.  The message windows U, V are streamed
+// from HBM/L2 once per rebuild with 128-bit loads; inside one EM call the per-column terms do not change
+// between iterations (the reference recomputes them every iteration), so they are computed once per call
+// and kept on chip as rho_j = e^{A_j-s_j} / e^{B_j-s_j}: an iteration is then W fused multiply-adds, W
+// divisions and one warp reduction.
+#include "hu_batch.cuh"
+
+namespace hu {
+
+#define HU_PLACE_WARPS 4
+#define HU_PLACE_CAPW 2048 // columns of rho kept in shared memory per warp (16 KB); wider windows use a global slab
+#define HU_BRANCH_EPS 1e-5 // src/PhyloTreeUnrooted.cpp:70
+#define HU_MAX_ITER 100    // src/PhyloTreeUnrooted.cpp:71
+
+struct PlaceArgs {
+	int nReads, maxNSeed, capW, useTrue;
+	double maxHeight;
+	const int8_t* aligned;
+	const int* winStart;
+	const int* winEnd;
+	const hu_place_row* est;
+	const int* order;
+	const int* nKept;
+	hu_place_row* places;
+	int* cursor;
+	double* slab;      // [warp slots][csLen]
+};
+
+struct WarpShared {
+	double P[3][HU_MAX_DG][16]; // P(lu r_k), P(lv r_k), P(ln r_k)
+	double NP[HU_MAX_DG][5][4]; // dot_product_scaled(P(ln r_k), leaf message of base b / gap)
+	double piN[5];              // dot_product_scaled(pi, leaf message)
+};
+
+__device__ __forceinline__ double warpSum(double v) {
+	for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+	return v;
+}
+
+// Felsenstein EM for one branch given rho_j (NaN = column skipped), src/PhyloTreeUnrooted.cpp:749-798
+__device__ double emBranch(const double* __restrict__ rho, int W, int nValid, double wInit, double cap) {
+	const int lane = threadIdx.x & 31;
+	double q0 = exp(-wInit), p0 = 1 - q0;
+	double p = p0, q = q0;
+	for (int it = 0; it < HU_MAX_ITER && p >= 0 && p <= 1; ++it) {
+		double s = 0;
+		// e^B p0 / (e^A q0 + e^B p0) = p0 / (rho q0 + p0)
+		for (int c = lane; c < W; c += 32) {
+			const double rh = rho[c];
+			if (rh == rh) s += p0 / (rh * q0 + p0);
+		}
+		p = warpSum(s) / (double) nValid;
+		q = 1 - p;
+		if (fabs(log(q) - log(q0)) < HU_BRANCH_EPS) break;
+		p0 = p; q0 = q;
+	}
+	double w = -log(q);
+	if (w > cap) w = cap;
+	return w;
+}
+
+__global__ void __launch_bounds__(HU_PLACE_WARPS * 32) placeKernel(PlaceArgs a, TreeDev t, Model m) {
+	extern __shared__ __align__(16) unsigned char smemRaw[];
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	WarpShared* ws = reinterpret_cast<WarpShared*>(smemRaw) + warp;
+	double* rhoS = reinterpret_cast<double*>(smemRaw + sizeof(WarpShared) * HU_PLACE_WARPS) + (size_t) warp * a.capW;
+	const int slot = blockIdx.x * HU_PLACE_WARPS + warp;
+	const int total = a.nReads * a.maxNSeed;
+	const int KK = m.dgK > 0 ? m.dgK : 1;
+	for (;;) {
+		int item = 0;
+		if (lane == 0) item = atomicAdd(a.cursor, 1);
+		item = __shfl_sync(0xffffffffu, item, 0);
+		if (item >= total) return;
+		const int r = item / a.maxNSeed, idx = item % a.maxNSeed;
+		if (a.winStart[r] < 0 || idx >= a.nKept[r]) continue;
+		const hu_place_row e = a.est[(size_t) r * HU_MAX_SEED + a.order[(size_t) r * HU_MAX_SEED + idx]];
+		const int start = e.start, end = e.end, W = end - start + 1;
+		const int c = e.cNode, pN = e.pNode;
+		const double w0 = t.blen[c];
+		const double* U = t.up + ((size_t) c * t.csLen + start) * 4;
+		const double* V = t.dn + ((size_t) c * t.csLen + start) * 4;
+		const int8_t* x = a.aligned + (size_t) r * t.csLen + start;
+		double* rho = W <= a.capW ? rhoS : a.slab + (size_t) slot * t.csLen;
+		double lu = w0 * e.ratio, lv = w0 * (1 - e.ratio), ln = e.wnr; // cpp:906-912
+		__syncwarp();
+		if (lane < 5) {
+			double n[4];
+			leafMsg(m, lane < 4 ? lane : -1, n);
+			ws->piN[lane] = dpsVec(m.pi, n);
+		}
+		double wur0 = lu, wvr0 = lv, wnr0 = ln;
+		const double w0j = wur0 + wvr0;
+		double wur = wur0, wvr = wvr0, wnr = wnr0;
+		int iter = 0;
+		for (iter = 0; iter < HU_MAX_ITER && 0 <= wur && wur <= w0j; ++iter) {
+			// ---- msg(r->n) from u and v, then optimise the n-r branch (cap 1) ----
+			__syncwarp();
+			if (lane < KK) modelPr(m, lu * (m.dgK ? m.dgR[lane] : 1.0), ws->P[0][lane]);
+			else if (lane >= 8 && lane < 8 + KK) modelPr(m, lv * (m.dgK ? m.dgR[lane - 8] : 1.0), ws->P[1][lane - 8]);
+			__syncwarp();
+			int nValid = 0;
+			for (int cI = lane; cI < W; cI += 32) {
+				double uv[4], vv[4], ya[4], yb[4], mat[HU_MAX_DG][4], rn[4];
+				ld4(U + (size_t) cI * 4, uv);
+				ld4(V + (size_t) cI * 4, vv);
+				for (int k = 0; k < KK; ++k) {
+					dpsMat(ws->P[0][k], uv, ya);
+					dpsMat(ws->P[1][k], vv, yb);
+					for (int i = 0; i < 4; ++i) mat[k][i] = ya[i] + yb[i];
+				}
+				if (m.dgK) rmes(mat, KK, rn);
+				else for (int i = 0; i < 4; ++i) rn[i] = mat[0][i];
+				const int b = x[cI];
+				double nm[4], z[4];
+				leafMsg(m, b, nm);
+				for (int i = 0; i < 4; ++i) z[i] = rn[i] + nm[i];
+				const double logA = dpsVec(m.pi, z);
+				const double logB = dpsVec(m.pi, rn) + ws->piN[b >= 0 ? b : 4];
+				double rh = NAN;
+				if (!(isnan(logA) || isnan(logB))) {
+					const double sc = fmax(logA, logB);
+					rh = exp(logA - sc) / exp(logB - sc);
+					nValid++;
+				}
+				rho[cI] = rh;
+			}
+			for (int o = 16; o > 0; o >>= 1) nValid += __shfl_xor_sync(0xffffffffu, nValid, o);
+			__syncwarp();
+			wnr = emBranch(rho, W, nValid, ln, 1.0);
+			ln = wnr;
+			// ---- msg(r->u) from v and n, then optimise the u-r branch (cap w0) ----
+			__syncwarp();
+			if (lane < KK) modelPr(m, ln * (m.dgK ? m.dgR[lane] : 1.0), ws->P[2][lane]);
+			__syncwarp();
+			for (int q = lane; q < KK * 5; q += 32) {
+				const int k = q / 5, b = q % 5;
+				double n[4], y[4];
+				leafMsg(m, b < 4 ? b : -1, n);
+				dpsMat(ws->P[2][k], n, y);
+				for (int i = 0; i < 4; ++i) ws->NP[k][b][i] = y[i];
+			}
+			__syncwarp();
+			nValid = 0;
+			for (int cI = lane; cI < W; cI += 32) {
+				double uv[4], vv[4], yb[4], mat[HU_MAX_DG][4], ru[4];
+				ld4(U + (size_t) cI * 4, uv);
+				ld4(V + (size_t) cI * 4, vv);
+				const int b = x[cI];
+				for (int k = 0; k < KK; ++k) {
+					dpsMat(ws->P[1][k], vv, yb);
+					const double* np = ws->NP[k][b >= 0 ? b : 4];
+					for (int i = 0; i < 4; ++i) mat[k][i] = yb[i] + np[i];
+				}
+				if (m.dgK) rmes(mat, KK, ru);
+				else for (int i = 0; i < 4; ++i) ru[i] = mat[0][i];
+				double z[4];
+				for (int i = 0; i < 4; ++i) z[i] = ru[i] + uv[i];
+				const double logA = dpsVec(m.pi, z);
+				const double logB = dpsVec(m.pi, ru) + dpsVec(m.pi, uv);
+				double rh = NAN;
+				if (!(isnan(logA) || isnan(logB))) {
+					const double sc = fmax(logA, logB);
+					rh = exp(logA - sc) / exp(logB - sc);
+					nValid++;
+				}
+				rho[cI] = rh;
+			}
+			for (int o = 16; o > 0; o >>= 1) nValid += __shfl_xor_sync(0xffffffffu, nValid, o);
+			__syncwarp();
+			wur = emBranch(rho, W, nValid, lu, w0j);
+			lu = wur;
+			wvr = w0j - wur;
+			lv = wvr; // msg(r->v) is rebuilt by the reference but never read afterwards
+			if (fabs(wur - wur0) < HU_BRANCH_EPS && fabs(wnr - wnr0) < HU_BRANCH_EPS) { // ::abs resolves to the double overload here
+				iter++;
+				break;
+			}
+			wur0 = wur; wvr0 = wvr; wnr0 = wnr;
+		}
+		// ---- intended root log-likelihood: sum_j log(pi . exp(loglik(r, j))) ----
+		__syncwarp();
+		if (lane < KK) modelPr(m, lu * (m.dgK ? m.dgR[lane] : 1.0), ws->P[0][lane]);
+		else if (lane >= 8 && lane < 8 + KK) modelPr(m, lv * (m.dgK ? m.dgR[lane - 8] : 1.0), ws->P[1][lane - 8]);
+		else if (lane >= 16 && lane < 16 + KK) modelPr(m, ln * (m.dgK ? m.dgR[lane - 16] : 1.0), ws->P[2][lane - 16]);
+		__syncwarp();
+		for (int q = lane; q < KK * 5; q += 32) {
+			const int k = q / 5, b = q % 5;
+			double n[4], y[4];
+			leafMsg(m, b < 4 ? b : -1, n);
+			dpsMat(ws->P[2][k], n, y);
+			for (int i = 0; i < 4; ++i) ws->NP[k][b][i] = y[i];
+		}
+		__syncwarp();
+		double tl = 0;
+		for (int cI = lane; cI < W; cI += 32) {
+			double uv[4], vv[4], ya[4], yb[4], mat[HU_MAX_DG][4], root[4];
+			ld4(U + (size_t) cI * 4, uv);
+			ld4(V + (size_t) cI * 4, vv);
+			const int b = x[cI];
+			for (int k = 0; k < KK; ++k) {
+				dpsMat(ws->P[0][k], uv, ya);
+				dpsMat(ws->P[1][k], vv, yb);
+				const double* np = ws->NP[k][b >= 0 ? b : 4];
+				for (int i = 0; i < 4; ++i) mat[k][i] = (ya[i] + yb[i]) + np[i];
+			}
+			if (m.dgK) rmes(mat, KK, root);
+			else for (int i = 0; i < 4; ++i) root[i] = mat[0][i];
+			tl += dpsVec(m.pi, root);
+		}
+		tl = warpSum(tl);
+		if (lane == 0) {
+			hu_place_row row = e;
+			// literal return value: treeLoglik over a root message of INVALID_LOGLIK = 1
+			const double ones[4] = {1.0, 1.0, 1.0, 1.0};
+			const double c1 = dpsVec(m.pi, ones);
+			double lit = 0;
+			for (int j = 0; j < W; ++j) lit += c1;
+			row.loglik = lit;
+			row.loglikTrue = tl;
+			row.wnr = ln;
+			row.ratio = lu / w0;
+			row.height = t.height[c] + lu;
+			row.aNode = (row.ratio <= 0.5 || t.height[pN] > a.maxHeight) ? c : pN;
+			row.taxon = t.taxon[row.aNode];
+			row.outerIters = iter;
+			a.places[(size_t) r * HU_MAX_SEED + idx] = row;
+		}
+	}
+}
+
+// calcQValues (UNIFORM prior) + sort by qPlace + bestPlace; one thread per read.
+__global__ void finalizeKernel(int nReads, const int* __restrict__ winStart, const int* __restrict__ nKept,
+		hu_place_row* __restrict__ places, int useTrue, const int* __restrict__ equalPerm, hu_place_row* __restrict__ best) {
+	const int r = blockIdx.x * blockDim.x + threadIdx.x;
+	if (r >= nReads) return;
+	const int n = winStart[r] < 0 ? 0 : nKept[r];
+	hu_place_row* pl = places + (size_t) r * HU_MAX_SEED;
+	hu_place_row out;
+	if (n == 0) {
+		out.start = out.end = 0; out.cNode = out.pNode = out.aNode = out.taxon = -1;
+		out.dist = out.wuv = out.ratio = out.wnr = out.loglik = out.loglikTrue = out.estLoglik = 0;
+		out.height = out.annoDist = out.qPlace = out.qTaxon = 0;
+		out.outerIters = 0; out.nPlaces = 0;
+		best[r] = out;
+		return;
+	}
+	const double MAX_Q = 250.0, LOG10 = log(10.0);
+	int tax[HU_MAX_SEED];
+	double taxPP[HU_MAX_SEED];
+	int nTax = 0;
+	double norm = -INFINITY, mx = -INFINITY;
+	for (int i = 0; i < n; ++i) {
+		if (useTrue) pl[i].loglik = pl[i].loglikTrue;
+		const double p = pl[i].loglik + 0.0;
+		mx = fmax(mx, p);
+		int tIdx = -1;
+		for (int k = 0; k < nTax; ++k) if (tax[k] == pl[i].taxon) { tIdx = k; break; }
+		if (tIdx < 0) { tax[nTax] = pl[i].taxon; taxPP[nTax] = p; nTax++; }
+		else { // add_scaled, src/math/Stats.h:233-236
+			const double sc = fmax(taxPP[tIdx], p);
+			taxPP[tIdx] = log(exp(taxPP[tIdx] - sc) + exp(p - sc)) + sc;
+		}
+		const double sc = fmax(norm, p);
+		norm = log(exp(norm - sc) + exp(p - sc)) + sc;
+	}
+	double sum = 0;
+	for (int i = 0; i < n; ++i) sum += exp(pl[i].loglik - mx);
+	bool allEqual = true;
+	double q0 = 0;
+	for (int i = 0; i < n; ++i) {
+		const double pr = exp(pl[i].loglik - mx) / sum;
+		double q = -10.0 * log(1 - pr) / LOG10; // p2q
+		if (q > MAX_Q) q = MAX_Q;
+		pl[i].qPlace = q;
+		if (i == 0) q0 = q;
+		else if (!(q == q0)) allEqual = false;
+		double pt = 0;
+		for (int k = 0; k < nTax; ++k) if (tax[k] == pl[i].taxon) pt = taxPP[k];
+		double qt = -10.0 * log(1 - exp(pt - norm)) / LOG10;
+		if (qt > MAX_Q) qt = MAX_Q;
+		pl[i].qTaxon = qt;
+		pl[i].annoDist = (pl[i].aNode == pl[i].cNode ? pl[i].wuv * pl[i].ratio : (1 - pl[i].ratio) * pl[i].wuv) + pl[i].wnr;
+		pl[i].nPlaces = n;
+	}
+	// std::sort(places.rbegin(), places.rend(), compareByQPlace); bestPlace = places[0]
+	int pick = 0;
+	if (allEqual) pick = equalPerm[n]; // what libstdc++'s introsort leaves first on n equal keys
+	else
+		for (int i = 1; i < n; ++i) if (pl[i].qPlace > pl[pick].qPlace) pick = i;
+	best[r] = pl[pick];
+}
+
+int launchPlace(hu_batch* b, const hu_sep_params* p) {
+	hu_db* db = b->db;
+	PlaceArgs a;
+	a.nReads = b->nReads; a.maxNSeed = p->maxNSeed; a.capW = HU_PLACE_CAPW; a.useTrue = p->useTrueLoglik;
+	a.maxHeight = p->maxHeight;
+	a.aligned = b->vit.aligned; a.winStart = b->winStart; a.winEnd = b->winEnd;
+	a.est = b->est; a.order = b->order; a.nKept = b->nKept; a.places = b->places;
+	a.cursor = b->workCount + 1;
+	int sms = 0;
+	HU_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, db->device));
+	const int ctasPerSm = 3;
+	const int grid = sms * ctasPerSm;
+	const size_t smem = sizeof(WarpShared) * HU_PLACE_WARPS + (size_t) HU_PLACE_WARPS * HU_PLACE_CAPW * sizeof(double);
+	static bool attr = false;
+	if (!attr) {
+		HU_CUDA(cudaFuncSetAttribute(placeKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+		attr = true;
+	}
+	// global slab for windows wider than the shared-memory capacity
+	const size_t slabBytes = (size_t) grid * HU_PLACE_WARPS * db->tree.csLen * sizeof(double);
+	if (!b->placeSlab) {
+		void* q = NULL;
+		HU_CUDA(cudaMalloc(&q, slabBytes));
+		b->allocs.push_back(q);
+		b->placeSlab = (double*) q;
+	}
+	a.slab = b->placeSlab;
+	placeKernel<<<grid, HU_PLACE_WARPS * 32, smem, b->stream>>>(a, db->tree, db->model);
+	HU_CUDA(cudaEventRecord(b->ev[6], b->stream));
+	b->launches += 1;
+	HU_CUDA(cudaGetLastError());
+	return HU_OK;
+}
+
+int launchFinalize(hu_batch* b, const hu_sep_params* p) {
+	finalizeKernel<<<(b->nReads + 63) / 64, 64, 0, b->stream>>>(b->nReads, b->winStart, b->nKept, b->places, p->useTrueLoglik, b->equalPerm, b->best);
+	HU_CUDA(cudaEventRecord(b->ev[7], b->stream));
+	b->launches += 1;
+	HU_CUDA(cudaGetLastError());
+	return HU_OK;
+}
+
+} // namespace hu

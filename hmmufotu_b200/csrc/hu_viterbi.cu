@@ -1,0 +1,524 @@
+// K1: batched banded plan-7 Viterbi, traceback and aligned-code emission.
+//
+// One warp per sequence.  The "band" of the reference is a chain of boxes joined at their corners
+// (upstream rectangle, seed strip, inter-seed rectangle, seed strip, downstream rectangle;
+// src/BandedHMMP7.cpp:782-892).  Each box is swept in 32-column stripes: lane l owns profile column
+// j0+32s+l, rows advance as an anti-diagonal wavefront (row i = i0+t-l at step t), the (i,j-1) and
+// (i-1,j-1) dependencies arrive by warp shuffle, the (i-1,j) dependency stays in registers, and the
+// right-most column of a stripe is handed to the next stripe through shared memory.  All arithmetic is
+// fp64 adds and mins in the reference's operand order, so costs and argmins are bit-identical to it.
+// Instead of the reference's four dense (N+1)x(K+2) matrices, only a 4-bit back-pointer per cell is
+// stored (2 bits M: B/M/I/D, 1 bit I: M/I, 1 bit D: M/D), evaluated with exactly the candidate sets and
+// first-strict-minimum tie rule buildViterbiTrace uses (src/BandedHMMP7.cpp:943-1006, .h:722-788).
+#include "hu_batch.cuh"
+
+namespace hu {
+
+struct Cell { double M, I, D; };
+
+__device__ __forceinline__ double col0M(int i, double cNN, double cNB) {
+	// prepareViterbiScores, src/BandedHMMP7.cpp:735-746: DP_M(i,0) = (i==1 ? 0 : cNN*(i-1)) + cNB, DP_M(0,0) = inf
+	if (i < 1) return INFINITY;
+	return (i == 1 ? 0.0 : cNN * (double) (i - 1)) + cNB;
+}
+
+struct Best { double v; int j, i; };
+__device__ __forceinline__ bool better(double v, int j, int i, const Best& b) {
+	// S.minCoeff(&row,&col): first strict minimum in column-major visiting order
+	return v < b.v || (v == b.v && (j < b.j || (j == b.j && i < b.i)));
+}
+
+struct WarpCtx {
+	const int8_t* x;   // read codes, x[i-1]
+	int N;
+	double cNN, cNB, cEC, cCC;
+	double* bnd;       // shared: [3][bndPitch]
+	int bndPitch;
+	Cell* win;         // shared: 2x2 window around the current chain corner, [a*2+b] = cell (ic-1+a, jc-1+b)
+	Cell* winNew;      // shared: window being captured around the end corner of the running box
+	int ic, jc;        // chain corner of win
+};
+
+// Sweep one box.  Returns the number of cell updates.
+__device__ long long sweepBox(const HmmDev& h, const VRegion& R, bool hasNext, WarpCtx& w, uint32_t* __restrict__ ptrBase, Best& best) {
+	const int lane = threadIdx.x & 31;
+	const int K = h.K, Kp = h.Kp;
+	const int rows = R.i1 - R.i0 + 1, cols = R.j1 - R.j0 + 1;
+	long long cells = 0;
+	// ---- window around the end corner: start from what is known before this box ----
+	if (lane < 4) {
+		const int a = lane >> 1, b = lane & 1;
+		const int ci = R.i1 - 1 + a, cj = R.j1 - 1 + b;
+		Cell c;
+		c.M = c.I = c.D = INFINITY;
+		const int oa = ci - (w.ic - 1), ob = cj - (w.jc - 1);
+		if (oa >= 0 && oa < 2 && ob >= 0 && ob < 2) c = w.win[oa * 2 + ob];
+		else if (cj == 0) { c.M = c.I = col0M(ci, w.cNN, w.cNB); }
+		w.winNew[lane] = c;
+	}
+	// ---- left boundary column (j0-1) for stripe 0 ----
+	for (int r = lane; r <= rows; r += 32) {
+		const int i = R.i0 - 1 + r;
+		Cell c;
+		c.M = c.I = c.D = INFINITY;
+		if (R.j0 - 1 == 0) c.M = c.I = col0M(i, w.cNN, w.cNB);
+		else if (r == 0) c = w.win[0];
+		else if (r == 1) c = w.win[2];
+		w.bnd[r] = c.M; w.bnd[w.bndPitch + r] = c.I; w.bnd[2 * w.bndPitch + r] = c.D;
+	}
+	__syncwarp();
+	const Cell top0 = w.win[1]; // (i0-1, j0)
+	const int nStripes = (cols + 31) / 32;
+	for (int s = 0; s < nStripes; ++s) {
+		const int jb = R.j0 + 32 * s;
+		const int j = jb + lane;
+		const int ncols = min(32, R.j1 - jb + 1);
+		const bool colOn = lane < ncols;
+		const int jj = colOn ? j : R.j1; // clamp for loads
+		// per-column parameters (Tmat_cost[j-1] and [j], emissions, entry, exit)
+		const double tMMp = __ldg(h.tr + T_MM * Kp + jj - 1), tIMp = __ldg(h.tr + T_IM * Kp + jj - 1), tDMp = __ldg(h.tr + T_DM * Kp + jj - 1);
+		const double tMDp = __ldg(h.tr + T_MD * Kp + jj - 1), tDDp = __ldg(h.tr + T_DD * Kp + jj - 1);
+		const double tMI = __ldg(h.tr + T_MI * Kp + jj), tII = __ldg(h.tr + T_II * Kp + jj), tIMj = __ldg(h.tr + T_IM * Kp + jj);
+		const double ent = __ldg(h.ent + jj), ext = __ldg(h.ext + jj);
+		const double eM0 = __ldg(h.eM + jj), eM1 = __ldg(h.eM + Kp + jj), eM2 = __ldg(h.eM + 2 * Kp + jj), eM3 = __ldg(h.eM + 3 * Kp + jj);
+		const double eI0 = __ldg(h.eI + jj), eI1 = __ldg(h.eI + Kp + jj), eI2 = __ldg(h.eI + 2 * Kp + jj), eI3 = __ldg(h.eI + 3 * Kp + jj);
+		const bool dOn = jj > 1 && jj < K;
+		// state: cur = (i-1, j) own column; diag = (i-1, j-1)
+		double curM = INFINITY, curI = INFINITY, curD = INFINITY;
+		if (s == 0 && lane == 0) { curM = top0.M; curI = top0.I; curD = top0.D; }
+		double dgM = INFINITY, dgI = INFINITY, dgD = INFINITY;
+		if (lane == 0) { dgM = w.bnd[0]; dgI = w.bnd[w.bndPitch]; dgD = w.bnd[2 * w.bndPitch]; }
+		uint32_t acc = 0;
+		uint32_t* ptrCol = ptrBase + R.ptrOff + (long long) (jj - R.j0) * R.rowWords;
+		const int steps = rows + ncols - 1;
+		for (int t = 0; t < steps; ++t) {
+			const int i = R.i0 + t - lane;
+			double lM = __shfl_up_sync(0xffffffffu, curM, 1);
+			double lI = __shfl_up_sync(0xffffffffu, curI, 1);
+			double lD = __shfl_up_sync(0xffffffffu, curD, 1);
+			if (lane == 0) {
+				const int r = i - (R.i0 - 1);
+				if (r <= rows) { lM = w.bnd[r]; lI = w.bnd[w.bndPitch + r]; lD = w.bnd[2 * w.bndPitch + r]; }
+				else lM = lI = lD = INFINITY;
+			}
+			const bool on = colOn && i >= R.i0 && i <= R.i1;
+			if (on) {
+				bool pred = true;
+				if (R.strip) {
+					const int d = (i - R.pFrom) - (j - R.pStart);
+					pred = d <= R.nIns && d >= -R.nDel;
+				}
+				double nM = INFINITY, nI = INFINITY, nD = INFINITY;
+				uint32_t code = 0;
+				if (pred) {
+					const int b = w.x[i - 1];
+					const double eM = (b & 2) ? ((b & 1) ? eM3 : eM2) : ((b & 1) ? eM1 : eM0);
+					const double eI = (b & 2) ? ((b & 1) ? eI3 : eI2) : ((b & 1) ? eI1 : eI0);
+					// DP_M: src/BandedHMMP7.cpp:812-819 (useB) / :866-872 (downstream, no B)
+					const double cB = col0M(i, w.cNN, w.cNB) + ent;
+					const double cM = dgM + tMMp, cI = dgI + tIMp, cD = dgD + tDMp;
+					double m3 = fmin(cM, fmin(cI, cD));
+					nM = eM + (R.useB ? fmin(cB, m3) : m3);
+					// trace candidates (src/BandedHMMP7.cpp:962-971): always with B; only B and I at j == 1
+					uint32_t pm = 0;
+					if (j > 1) {
+						double mn = cB;
+						if (cM < mn) { mn = cM; pm = 1; }
+						if (cI < mn) { mn = cI; pm = 2; }
+						if (cD < mn) { pm = 3; }
+					} else
+						pm = (cI < cB) ? 2 : 0;
+					// DP_I: :820-822
+					const double iM = curM + tMI, iI = curI + tII;
+					nI = eI + fmin(iM, iI);
+					const uint32_t pi = iI < iM ? 1 : 0;
+					// DP_D: :823-825 (only 1 < j < K)
+					uint32_t pd = 0;
+					if (dOn) {
+						const double dM = lM + tMDp, dD = lD + tDDp;
+						nD = fmin(dM, dD);
+						pd = dD < dM ? 1 : 0;
+					}
+					code = pm | (pi << 2) | (pd << 3);
+					cells++;
+					// S (src/BandedHMMP7.cpp:883-891); the end corner is recomputed by the next box
+					if (!(hasNext && i == R.i1 && j == R.j1)) {
+						const double rowPen = i < w.N ? w.cCC * (double) (w.N - i) : 0.0;
+						double sv = (nM + ext) + w.cEC;
+						if (i < w.N) sv += rowPen;
+						if (better(sv, j, i, best)) { best.v = sv; best.j = j; best.i = i; }
+						if (j == K) {
+							double s2 = (nI + tIMj) + w.cEC;
+							if (i < w.N) s2 += rowPen;
+							if (better(s2, K + 1, i, best)) { best.v = s2; best.j = K + 1; best.i = i; }
+						}
+					}
+				}
+				acc |= code << (4 * ((i - R.i0) & 7));
+				if (((i - R.i0) & 7) == 7 || i == R.i1) {
+					ptrCol[(i - R.i0) >> 3] = acc;
+					acc = 0;
+				}
+				if (pred && i >= R.i1 - 1 && j >= R.j1 - 1) {
+					Cell c; c.M = nM; c.I = nI; c.D = nD;
+					w.winNew[(i - (R.i1 - 1)) * 2 + (j - (R.j1 - 1))] = c;
+				}
+				if (lane == 31) {
+					const int r = i - (R.i0 - 1);
+					w.bnd[r] = nM; w.bnd[w.bndPitch + r] = nI; w.bnd[2 * w.bndPitch + r] = nD;
+				}
+				curM = nM; curI = nI; curD = nD;
+			}
+			dgM = lM; dgI = lI; dgD = lD;
+		}
+		__syncwarp();
+		if (lane == 0) { w.bnd[0] = INFINITY; w.bnd[w.bndPitch] = INFINITY; w.bnd[2 * w.bndPitch] = INFINITY; }
+		__syncwarp();
+	}
+	// commit the window
+	__syncwarp();
+	if (lane < 4) w.win[lane] = w.winNew[lane];
+	w.ic = R.i1; w.jc = R.j1;
+	__syncwarp();
+	return cells;
+}
+
+__device__ __forceinline__ void initWindow(WarpCtx& w, int i0, int j0) {
+	const int lane = threadIdx.x & 31;
+	if (lane < 4) {
+		const int a = lane >> 1, b = lane & 1;
+		const int ci = i0 - 1 + a, cj = j0 - 1 + b;
+		Cell c;
+		c.M = c.I = c.D = INFINITY;
+		if (cj == 0) c.M = c.I = col0M(ci, w.cNN, w.cNB);
+		w.win[lane] = c;
+	}
+	w.ic = i0; w.jc = j0;
+	__syncwarp();
+}
+
+__device__ __forceinline__ uint32_t ptrAt(const VRegion* regs, int nReg, const uint32_t* __restrict__ ptrBase, int i, int j) {
+	for (int r = nReg - 1; r >= 0; --r) {
+		const VRegion& R = regs[r];
+		if (i >= R.i0 && i <= R.i1 && j >= R.j0 && j <= R.j1) {
+			const uint32_t wv = ptrBase[R.ptrOff + (long long) (j - R.j0) * R.rowWords + ((i - R.i0) >> 3)];
+			return (wv >> (4 * ((i - R.i0) & 7))) & 15u;
+		}
+	}
+	return 0;
+}
+
+// getPaddingSeq(..., JUSTIFIED) of an insert into a gap of Lg columns (src/BandedHMMP7.cpp:1168-1181),
+// written as base codes; the head duplication for short inserts is the reference's literal behaviour.
+__device__ void justifiedPad(int8_t* out, int Lg, const int8_t* ins, int n) {
+	if (n == 0) {
+		for (int c = 0; c < Lg; ++c) out[c] = HU_CODE_GAP;
+		return;
+	}
+	if (n >= Lg) {
+		const int fl = Lg / 2, ce = Lg - fl;
+		for (int c = 0; c < fl; ++c) out[c] = ins[c];
+		for (int c = 0; c < ce; ++c) out[fl + c] = ins[n - ce + c];
+	} else {
+		const int fl = n / 2, ce = n - fl;
+		for (int c = 0; c < fl; ++c) out[c] = ins[c];
+		for (int c = 0; c < Lg - n; ++c) out[fl + c] = HU_CODE_GAP;
+		for (int c = 0; c < ce; ++c) out[fl + Lg - n + c] = ins[c];
+	}
+}
+
+// After the sweeps: S argmin -> traceback -> trace string (reversed) -> aligned codes -> result row.
+__device__ void finishSeq(const HmmDev& h, const VRegion* regs, int nReg, const uint32_t* __restrict__ ptrBase, WarpCtx& w,
+		Best best, long long cells, int flags, const int8_t* __restrict__ gx, char* __restrict__ trace, int8_t* __restrict__ alignedRow,
+		hu_align_row* __restrict__ row) {
+	const int lane = threadIdx.x & 31;
+	if (lane != 0) return;
+	const int K = h.K;
+	row->cells = cells;
+	row->cost = best.v;
+	if (best.v == INFINITY) { // unreachable after the full pass unless the profile forbids the read
+		row->flags = flags | HU_ALIGN_INVALID;
+		row->traceLen = 0;
+		row->seqStart = row->seqEnd = row->hmmStart = row->hmmEnd = row->csStart = row->csEnd = 0;
+		return;
+	}
+	char s = best.j <= K ? 'M' : 'I';
+	int i = best.i, j = best.j <= K ? best.j : K;
+	const int alnEnd = j, alnTo = best.i;
+	int pos = 0;
+	trace[pos++] = 'E';
+	char last = 'E';
+	while (i >= 1 && j >= 0) {
+		trace[pos++] = s;
+		last = s;
+		if (s == 'M') {
+			const uint32_t c = ptrAt(regs, nReg, ptrBase, i, j) & 3u;
+			s = "BMID"[c];
+			i--; j--;
+		} else if (s == 'I') {
+			if (j > 0) {
+				const uint32_t c = (ptrAt(regs, nReg, ptrBase, i, j) >> 2) & 1u;
+				s = c ? 'I' : 'M';
+			} else { // column 0: whichMin(DP_M(i,0)+T[0](M,I), DP_I(i-1,0)+T[0](I,I)) in "BI"
+				const double a = col0M(i, w.cNN, w.cNB) + __ldg(h.tr + T_MI * h.Kp);
+				const double b = col0M(i - 1, w.cNN, w.cNB) + __ldg(h.tr + T_II * h.Kp);
+				s = b < a ? 'I' : 'B';
+			}
+			i--;
+		} else if (s == 'D') {
+			const uint32_t c = (ptrAt(regs, nReg, ptrBase, i, j) >> 3) & 1u;
+			s = c ? 'D' : 'M';
+			j--;
+		} else
+			break;
+	}
+	const int alnStart = j + 1, alnFrom = i + 1;
+	if (last != 'B') trace[pos++] = 'B';
+	const int csStart = __ldg(h.p2cs + alnStart), csEnd = __ldg(h.p2cs + alnEnd);
+	row->seqStart = alnFrom; row->seqEnd = alnTo;
+	row->hmmStart = alnStart; row->hmmEnd = alnEnd;
+	row->csStart = csStart; row->csEnd = csEnd;
+	row->traceLen = pos;
+	const bool valid = 0 < alnFrom && alnFrom <= alnTo && 0 < alnStart && alnStart <= alnEnd && alnEnd <= K &&
+			0 < csStart && csStart <= csEnd && csEnd <= h.L && best.v >= 0;
+	if (!valid) flags |= HU_ALIGN_INVALID;
+	row->flags = flags;
+	if (!valid || !alignedRow) return;
+	// buildGlobalAlign (src/BandedHMMP7.cpp:1008-1081) as codes, inside [csStart, csEnd] only: the pads
+	// outside are '.' whenever the whole read is aligned (always so in GLOBAL mode)
+	int rj = alnFrom, k = alnStart; // 1-based read position / profile position
+	int insFrom = 0, insLen = 0;    // pending insert = x[insFrom-1 .. insFrom+insLen-2]
+	int t = 0;
+	for (int q = pos - 1; q >= 0; --q, ++t) {
+		const char st = trace[q];
+		if (st == 'M') {
+			if (k > 1 && t > 1) {
+				const int g = __ldg(h.p2cs + k) - __ldg(h.p2cs + k - 1) - 1;
+				if (g > 0) justifiedPad(alignedRow + __ldg(h.p2cs + k - 1), g, gx + insFrom - 1, insLen);
+			}
+			insLen = 0;
+			alignedRow[__ldg(h.p2cs + k) - 1] = gx[rj - 1];
+			rj++; k++;
+		} else if (st == 'I') {
+			insFrom = rj;
+			insLen = 0;
+			while (q >= 0 && trace[q] == 'I') { insLen++; rj++; q--; t++; }
+			q++; t--;
+		} else if (st == 'D') {
+			if (k > 1) {
+				const int g = __ldg(h.p2cs + k) - __ldg(h.p2cs + k - 1) - 1;
+				for (int c = 0; c < g; ++c) alignedRow[__ldg(h.p2cs + k - 1) + c] = HU_CODE_GAP;
+			}
+			alignedRow[__ldg(h.p2cs + k) - 1] = HU_CODE_GAP;
+			k++;
+		}
+	}
+}
+
+// smem per warp: codes (maxLen, padded to 8) | bnd 3*(maxLen+2) doubles | win 4 cells | winNew 4 cells | regions
+__host__ __device__ inline size_t viterbiWarpSmem(int maxLen) {
+	const size_t codes = ((size_t) maxLen + 15) / 16 * 16;
+	return codes + (size_t) 3 * (maxLen + 2) * sizeof(double) + 8 * sizeof(Cell) + 5 * sizeof(VRegion) + 16;
+}
+
+struct WarpSmem {
+	int8_t* codes;
+	double* bnd;
+	Cell* win;
+	Cell* winNew;
+	VRegion* regs;
+};
+__device__ __forceinline__ WarpSmem carve(unsigned char* base, int maxLen) {
+	WarpSmem s;
+	const size_t codes = ((size_t) maxLen + 15) / 16 * 16;
+	s.bnd = reinterpret_cast<double*>(base);
+	s.win = reinterpret_cast<Cell*>(s.bnd + 3 * (maxLen + 2));
+	s.winNew = s.win + 4;
+	s.regs = reinterpret_cast<VRegion*>(s.winNew + 4);
+	s.codes = reinterpret_cast<int8_t*>(s.regs + 5);
+	(void) codes;
+	return s;
+}
+
+// Pass 1: the banded plans.  Sequences without a usable plan, or whose band holds no finite path, are
+// queued for pass 2 (src/HmmUFOtu_main.cpp:86-96).
+__global__ void __launch_bounds__(HU_VIT_WARPS * 32) viterbiBandedKernel(HmmDev h, VitArgs a) {
+	extern __shared__ __align__(16) unsigned char smemRaw[];
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int seq = blockIdx.x * a.warpsPerBlock + warp;
+	if (seq >= a.nSeq) return;
+	WarpSmem sm = carve(smemRaw + (size_t) warp * ((viterbiWarpSmem(a.maxLen) + 15) / 16 * 16), a.maxLen);
+	const VPlan& plan = a.plans[seq];
+	const int N = plan.N;
+	const int8_t* gx = a.codes + plan.codeOff;
+	if (plan.nReg == 0) {
+		if (lane == 0) {
+			const int slot = atomicAdd(a.fullCount, 1);
+			a.fullList[slot] = seq;
+			a.rows[seq].flags = plan.flags;
+			a.rows[seq].cells = 0;
+		}
+		return;
+	}
+	for (int i = lane; i < N; i += 32) sm.codes[i] = gx[i];
+	if (lane < plan.nReg) sm.regs[lane] = plan.reg[lane];
+	__syncwarp();
+	WarpCtx w;
+	w.x = sm.codes; w.N = N;
+	w.cNN = a.cNN; w.cNB = a.cNB; w.cEC = a.cEC; w.cCC = a.cCC;
+	w.bnd = sm.bnd; w.bndPitch = a.maxLen + 2;
+	w.win = sm.win; w.winNew = sm.winNew;
+	initWindow(w, sm.regs[0].i0, sm.regs[0].j0);
+	Best best; best.v = INFINITY; best.j = 0x7fffffff; best.i = 0x7fffffff;
+	long long cells = 0;
+	for (int r = 0; r < plan.nReg; ++r) cells += sweepBox(h, sm.regs[r], r + 1 < plan.nReg, w, a.ptrs, best);
+	// warp argmin
+	for (int o = 16; o > 0; o >>= 1) {
+		Best ob;
+		ob.v = __shfl_xor_sync(0xffffffffu, best.v, o);
+		ob.j = __shfl_xor_sync(0xffffffffu, best.j, o);
+		ob.i = __shfl_xor_sync(0xffffffffu, best.i, o);
+		if (better(ob.v, ob.j, ob.i, best)) best = ob;
+		cells += __shfl_xor_sync(0xffffffffu, cells, o);
+	}
+	if (best.v == INFINITY) { // banded version failed
+		if (lane == 0) {
+			const int slot = atomicAdd(a.fullCount, 1);
+			a.fullList[slot] = seq;
+			a.rows[seq].flags = plan.flags | HU_ALIGN_FALLBACK;
+			a.rows[seq].cells = cells;
+		}
+		return;
+	}
+	__syncwarp();
+	int8_t* arow = a.aligned ? a.aligned + (size_t) seq * h.L : NULL;
+	finishSeq(h, sm.regs, plan.nReg, a.ptrs, w, best, cells, plan.flags, gx, a.traces + plan.traceOff, arow, a.rows + seq);
+}
+
+// Pass 2: full Viterbi (src/BandedHMMP7.cpp:748-780) for the queued sequences; persistent warps, each with
+// its own N x K back-pointer slab.
+__global__ void __launch_bounds__(HU_VIT_WARPS * 32) viterbiFullKernel(HmmDev h, VitArgs a) {
+	extern __shared__ __align__(16) unsigned char smemRaw[];
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int slot = blockIdx.x * a.warpsPerBlock + warp;
+	WarpSmem sm = carve(smemRaw + (size_t) warp * ((viterbiWarpSmem(a.maxLen) + 15) / 16 * 16), a.maxLen);
+	const int count = *a.fullCount;
+	uint32_t* slab = a.fullPtrs + (size_t) slot * a.fullSlabWords;
+	for (;;) {
+		int idx = 0;
+		if (lane == 0) idx = atomicAdd(a.fullCursor, 1);
+		idx = __shfl_sync(0xffffffffu, idx, 0);
+		if (idx >= count) return;
+		const int seq = a.fullList[idx];
+		const VPlan& plan = a.plans[seq];
+		const int N = plan.N;
+		const int8_t* gx = a.codes + plan.codeOff;
+		__syncwarp();
+		for (int i = lane; i < N; i += 32) sm.codes[i] = gx[i];
+		if (lane == 0) {
+			VRegion R;
+			R.j0 = 1; R.j1 = h.K; R.i0 = 1; R.i1 = N;
+			R.strip = 0; R.pStart = R.pFrom = R.nIns = R.nDel = 0; R.useB = 1;
+			R.rowWords = (N + 7) / 8;
+			R.ptrOff = 0;
+			sm.regs[0] = R;
+		}
+		__syncwarp();
+		WarpCtx w;
+		w.x = sm.codes; w.N = N;
+		w.cNN = a.cNN; w.cNB = a.cNB; w.cEC = a.cEC; w.cCC = a.cCC;
+		w.bnd = sm.bnd; w.bndPitch = a.maxLen + 2;
+		w.win = sm.win; w.winNew = sm.winNew;
+		initWindow(w, 1, 1);
+		Best best; best.v = INFINITY; best.j = 0x7fffffff; best.i = 0x7fffffff;
+		long long cells = sweepBox(h, sm.regs[0], false, w, slab, best);
+		for (int o = 16; o > 0; o >>= 1) {
+			Best ob;
+			ob.v = __shfl_xor_sync(0xffffffffu, best.v, o);
+			ob.j = __shfl_xor_sync(0xffffffffu, best.j, o);
+			ob.i = __shfl_xor_sync(0xffffffffu, best.i, o);
+			if (better(ob.v, ob.j, ob.i, best)) best = ob;
+			cells += __shfl_xor_sync(0xffffffffu, cells, o);
+		}
+		__syncwarp();
+		int8_t* arow = a.aligned ? a.aligned + (size_t) seq * h.L : NULL;
+		const int flags = a.rows[seq].flags;
+		const long long prior = a.rows[seq].cells;
+		finishSeq(h, sm.regs, 1, slab, w, best, cells + prior, flags, gx, a.traces + plan.traceOff, arow, a.rows + seq);
+		__syncwarp();
+	}
+}
+
+// PE: orientation test (src/hmmufotu.cpp:629-639) and HmmAlignment::merge (src/BandedHMMP7.cpp:1188-1213).
+// Mate rows live at nReads + r.  The forward row becomes the merged row.
+__global__ void mergeMatesKernel(int nReads, int L, const hu_align_row* __restrict__ rows, hu_align_row* __restrict__ merged,
+		int8_t* __restrict__ aligned) {
+	const int r = blockIdx.x;
+	if (r >= nReads) return;
+	const hu_align_row a = rows[r], b = rows[nReads + r];
+	hu_align_row m = a;
+	m.cells = a.cells + b.cells;
+	m.flags = a.flags | (b.flags & (HU_ALIGN_INVALID | HU_ALIGN_FALLBACK));
+	const bool bad = (m.flags & HU_ALIGN_INVALID) || !(a.csStart <= b.csStart && a.csEnd <= b.csEnd);
+	if (bad) {
+		m.flags |= HU_ALIGN_CHIMERA;
+	} else {
+		m.seqStart = min(a.seqStart, b.seqStart); m.seqEnd = max(a.seqEnd, b.seqEnd);
+		m.hmmStart = min(a.hmmStart, b.hmmStart); m.hmmEnd = max(a.hmmEnd, b.hmmEnd);
+		m.csStart = min(a.csStart, b.csStart); m.csEnd = max(a.csEnd, b.csEnd);
+		m.cost = a.cost + b.cost;
+		int8_t* x = aligned + (size_t) r * L;
+		const int8_t* y = aligned + (size_t) (nReads + r) * L;
+		for (int c = b.csStart - 1 + threadIdx.x; c < b.csEnd; c += blockDim.x)
+			if (x[c] == HU_CODE_PAD && y[c] != HU_CODE_PAD) x[c] = y[c];
+	}
+	if (threadIdx.x == 0) merged[r] = m;
+}
+
+__global__ void copyRowsKernel(int n, const hu_align_row* __restrict__ rows, hu_align_row* __restrict__ merged) {
+	const int r = blockIdx.x * blockDim.x + threadIdx.x;
+	if (r < n) merged[r] = rows[r];
+}
+
+int launchViterbi(hu_batch* b, int mode) {
+	hu_db* db = b->db;
+	const HmmDev& h = db->hmm;
+	// setSequenceMode (src/BandedHMMP7.cpp:561-583, src/BandedHMMP7Bg.cpp:33-35)
+	const double Kbg = h.K >= 350 ? h.K : 350;
+	const double term = 1.0 - Kbg / (Kbg + 1.0);
+	double tNN = 0, tCC = 0;
+	switch (mode) {
+	case HU_GLOBAL: tNN = tCC = 0; break;
+	case HU_LOCAL: tNN = tCC = term; break;
+	case HU_NGCL: tNN = 0; tCC = term; break;
+	case HU_CGNL: tNN = term; tCC = 0; break;
+	default: setError("unknown alignment mode %d", mode); return HU_ERR_ARG;
+	}
+	VitArgs a = b->vit;
+	a.cNN = -log(tNN); a.cCC = -log(tCC); a.cNB = -log(1.0 - tNN); a.cEC = -log(1.0);
+	const int nSeq = b->nSeq;
+	a.nSeq = nSeq;
+	const size_t perWarp = (viterbiWarpSmem(a.maxLen) + 15) / 16 * 16;
+	const int wpb = a.warpsPerBlock;
+	const size_t smem = perWarp * wpb;
+	static size_t attrSet = 0;
+	if (smem > attrSet) {
+		HU_CUDA(cudaFuncSetAttribute(viterbiBandedKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+		HU_CUDA(cudaFuncSetAttribute(viterbiFullKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+		attrSet = smem;
+	}
+	HU_CUDA(cudaMemsetAsync(a.fullCount, 0, 2 * sizeof(int), b->stream)); // count + cursor
+	HU_CUDA(cudaMemsetAsync(a.aligned, HU_CODE_PAD & 0xff, (size_t) nSeq * h.L, b->stream));
+	viterbiBandedKernel<<<(nSeq + wpb - 1) / wpb, wpb * 32, smem, b->stream>>>(h, a);
+	viterbiFullKernel<<<b->fullSlots / wpb, wpb * 32, smem, b->stream>>>(h, a);
+	b->launches += 2;
+	if (b->paired) {
+		mergeMatesKernel<<<b->nReads, 128, 0, b->stream>>>(b->nReads, h.L, a.rows, b->merged, a.aligned);
+	} else
+		copyRowsKernel<<<(b->nReads + 127) / 128, 128, 0, b->stream>>>(b->nReads, a.rows, b->merged);
+	b->launches += 1;
+	HU_CUDA(cudaGetLastError());
+	return HU_OK;
+}
+
+} // namespace hu

@@ -1,0 +1,287 @@
+"""Host-side mirror of the reference's per-read interface over the C ABI.
+
+`Database` stands for the (hmm, ptu) pair `hmmufotu` loads (/root/reference/src/hmmufotu.cpp:457-494);
+`Batch` exposes the stages of the per-read pipeline under the reference's names
+(/root/reference/src/HmmUFOtu_main.h:70-113): alignSeq, getSeed, estimateSeq (+filterPlacements), placeSeq,
+calcQValues, batched.  All arithmetic happens in libhmmufotu_b200.so on the GPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+
+from . import _lib
+from ._lib import check
+
+ALIGN_DT = np.dtype([("seqStart", "<i4"), ("seqEnd", "<i4"), ("hmmStart", "<i4"), ("hmmEnd", "<i4"), ("csStart", "<i4"),
+                     ("csEnd", "<i4"), ("flags", "<i4"), ("traceLen", "<i4"), ("cost", "<f8"), ("cells", "<i8")])
+PLACE_DT = np.dtype([("start", "<i4"), ("end", "<i4"), ("cNode", "<i4"), ("pNode", "<i4"), ("aNode", "<i4"), ("taxon", "<i4"),
+                     ("dist", "<f8"), ("wuv", "<f8"), ("ratio", "<f8"), ("wnr", "<f8"), ("loglik", "<f8"),
+                     ("loglikTrue", "<f8"), ("estLoglik", "<f8"), ("height", "<f8"), ("annoDist", "<f8"),
+                     ("qPlace", "<f8"), ("qTaxon", "<f8"), ("outerIters", "<i4"), ("nPlaces", "<i4")])
+assert ALIGN_DT.itemsize == C.sizeof(_lib.AlignRow) and PLACE_DT.itemsize == C.sizeof(_lib.PlaceRow)
+
+
+def _p(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def model_desc(m: Dict, dg_rates=None) -> _lib.ModelDesc:
+    d = _lib.ModelDesc()
+    d.type = int(m["type"])
+    rates = np.zeros(0) if dg_rates is None else np.asarray(dg_rates, dtype=np.float64)
+    d.dgK = int(rates.size)
+    for i in range(4):
+        d.pi[i] = float(m["pi"][i])
+    R = np.asarray(m.get("R", np.zeros((4, 4))), dtype=np.float64).reshape(16)
+    for i in range(16):
+        d.R[i] = float(R[i])
+    d.kr, d.ky, d.kappa, d.beta = float(m["kr"]), float(m["ky"]), float(m["kappa"]), float(m["beta"])
+    for i in range(rates.size):
+        d.dgRates[i] = float(rates[i])
+    return d
+
+
+def model_Pr(m: Dict, v: float) -> np.ndarray:
+    """DNASubModel::Pr(v) through the library (host evaluation of the kernels' code)."""
+    P = np.zeros((4, 4))
+    d = model_desc(m)
+    check(_lib.load().hu_model_Pr(C.byref(d), float(v), _p(P)))
+    return P
+
+
+def hmm_finalize(K: int, T: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+    T = np.ascontiguousarray(T, dtype=np.float64)
+    entry = np.zeros(K + 1)
+    exit_ = np.zeros(K + 1)
+    check(_lib.load().hu_hmm_finalize(K, _p(T), _p(entry), _p(exit_)))
+    return entry, exit_
+
+
+class Database:
+    """One database replica on one GPU."""
+
+    def __init__(self, db, device: int = 0, messages: Optional[Tuple[np.ndarray, np.ndarray]] = None,
+                 infer_internal: bool = True):
+        L = _lib.load()
+        self.src = db
+        self.K, self.L = int(db.K), int(db.cs_len)
+        self.n_nodes = int(db.n_nodes)
+        self._keep = []
+        eM = np.ascontiguousarray(db.eM, dtype=np.float64)
+        eI = np.ascontiguousarray(db.eI, dtype=np.float64)
+        T = np.ascontiguousarray(db.T, dtype=np.float64)
+        p2cs = np.ascontiguousarray(db.p2cs, dtype=np.int32)
+        entry, exit_ = hmm_finalize(self.K, T)
+        self.entry, self.exit = entry, exit_
+        hp = _lib.HmmParams(self.K, self.L, _p(eM), _p(eI), _p(T), _p(entry), _p(exit_), _p(p2cs))
+        self._hmm_arrays = (eM, eI, T, entry, exit_, p2cs)
+        self.hmm_params = hp
+        parent = np.ascontiguousarray(db.parent, dtype=np.int32)
+        blen = np.ascontiguousarray(db.blen, dtype=np.float64)
+        height = np.ascontiguousarray(db.height, dtype=np.float64)
+        seq = np.ascontiguousarray(db.seq, dtype=np.int8)
+        taxon = np.ascontiguousarray(db.taxon, dtype=np.int32)
+        td = _lib.TreeDesc()
+        td.nNodes, td.csLen, td.root = self.n_nodes, self.L, int(db.root)
+        td.parent, td.blen, td.height, td.seq, td.taxon = _p(parent), _p(blen), _p(height), _p(seq), _p(taxon)
+        if messages is not None:
+            up = np.ascontiguousarray(messages[0], dtype=np.float64)
+            dn = np.ascontiguousarray(messages[1], dtype=np.float64)
+            td.up, td.dn = _p(up), _p(dn)
+            td.inferInternalSeq = 0
+        else:
+            td.up = td.dn = None
+            td.inferInternalSeq = int(infer_internal)
+        md = model_desc(db.model, db.dg_rates)
+        h = C.c_void_p()
+        check(L.hu_db_create(C.byref(h), C.byref(hp), C.byref(td), C.byref(md), device))
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            _lib.load().hu_db_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    @property
+    def bytes(self) -> int:
+        return int(_lib.load().hu_db_bytes(self.h))
+
+    def messages(self, node0: int = 0, n: Optional[int] = None):
+        n = self.n_nodes - node0 if n is None else n
+        up = np.zeros((n, self.L, 4))
+        dn = np.zeros((n, self.L, 4))
+        check(_lib.load().hu_db_get_messages(self.h, node0, n, _p(up), _p(dn)))
+        return up, dn
+
+    def seqs(self, node0: int = 0, n: Optional[int] = None) -> np.ndarray:
+        n = self.n_nodes - node0 if n is None else n
+        s = np.zeros((n, self.L), dtype=np.int8)
+        check(_lib.load().hu_db_get_seq(self.h, node0, n, _p(s)))
+        return s
+
+    def trace_to_align(self, read: str, row, trace: str) -> str:
+        """BandedHMMP7::buildGlobalAlign on the host."""
+        ar = _lib.AlignRow()
+        for f, _ in _lib.AlignRow._fields_:
+            setattr(ar, f, row[f].item() if hasattr(row[f], "item") else row[f])
+        out = C.create_string_buffer(self.L)
+        check(_lib.load().hu_trace_to_align(C.byref(self.hmm_params), read.encode(), len(read), C.byref(ar), trace.encode(), out))
+        return out.raw.decode()
+
+
+class SepParams:
+    def __init__(self, max_n_seed: int = 50, max_error: float = 20.0, max_diff: float = np.inf,
+                 max_height: float = np.inf, use_true_loglik: bool = False):
+        p = _lib.SepParams()
+        _lib.load().hu_sep_params_default(C.byref(p))
+        p.maxNSeed, p.maxError, p.maxDiff, p.maxHeight = max_n_seed, max_error, max_diff, max_height
+        p.useTrueLoglik = int(use_true_loglik)
+        self.c = p
+
+
+class Batch:
+    """Device workspace for one batch of reads; stages named after the reference's functions."""
+
+    def __init__(self, database: Database, max_reads: int, max_len: int, paired: bool = False):
+        self.db = database
+        self.max_reads, self.max_len, self.paired = max_reads, max_len, paired
+        h = C.c_void_p()
+        check(_lib.load().hu_batch_create(C.byref(h), database.h, max_reads, max_len, int(paired)))
+        self.h = h
+        self.n = 0
+        self.n_seq = 0
+        self.max_n_seed = 50
+        self._keep = None
+
+    def close(self):
+        if getattr(self, "h", None):
+            _lib.load().hu_batch_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    # ---- staging ----
+    def upload(self, reads, mates=None):
+        """reads (and mates, already reverse-complemented): synth.ReadSet-like with codes/offsets/vpaths/n_paths."""
+        if (mates is not None) != self.paired:
+            raise ValueError("pairedness differs from the workspace")
+        if mates is None:
+            codes, offsets, vp, npth = reads.codes, reads.offsets, reads.vpaths, reads.n_paths
+        else:
+            codes = np.concatenate([reads.codes, mates.codes])
+            offsets = np.concatenate([reads.offsets, mates.offsets[1:] + reads.offsets[-1]])
+            vp = np.concatenate([reads.vpaths, mates.vpaths])
+            npth = np.concatenate([reads.n_paths, mates.n_paths])
+        codes = np.ascontiguousarray(codes, dtype=np.int8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        vp = np.ascontiguousarray(vp, dtype=np.int32)
+        npth = np.ascontiguousarray(npth, dtype=np.int32)
+        self._keep = (codes, offsets, vp, npth)
+        rb = _lib.ReadBatch(reads.n, int(self.paired), _p(codes), _p(offsets), _p(vp), _p(npth))
+        check(_lib.load().hu_batch_upload(self.h, C.byref(rb)))
+        self.n = reads.n
+        self.n_seq = reads.n * (2 if self.paired else 1)
+
+    def set_aligned(self, codes: np.ndarray, start: np.ndarray, end: np.ndarray):
+        codes = np.ascontiguousarray(codes, dtype=np.int8)
+        start = np.ascontiguousarray(start, dtype=np.int32)
+        end = np.ascontiguousarray(end, dtype=np.int32)
+        self._keep = (codes, start, end)
+        check(_lib.load().hu_batch_set_aligned(self.h, codes.shape[0], _p(codes), _p(start), _p(end)))
+        self.n = self.n_seq = codes.shape[0]
+
+    # ---- stages ----
+    def alignSeq(self, mode: int = _lib.GLOBAL):
+        check(_lib.load().hu_align_batch(self.h, mode))
+
+    def getSeed(self, p: SepParams):
+        self.max_n_seed = p.c.maxNSeed
+        check(_lib.load().hu_seed_batch(self.h, C.byref(p.c)))
+
+    def estimateSeq(self, p: SepParams):
+        check(_lib.load().hu_estimate_batch(self.h, C.byref(p.c)))
+
+    def placeSeq(self, p: SepParams):
+        check(_lib.load().hu_place_batch(self.h, C.byref(p.c)))
+
+    def calcQValues(self, p: SepParams):
+        check(_lib.load().hu_finalize_batch(self.h, C.byref(p.c)))
+
+    def assign(self, p: SepParams, mode: int = _lib.GLOBAL):
+        self.max_n_seed = p.c.maxNSeed
+        check(_lib.load().hu_assign_batch(self.h, mode, C.byref(p.c)))
+
+    def sep(self, p: SepParams):
+        self.getSeed(p)
+        self.estimateSeq(p)
+        self.placeSeq(p)
+        self.calcQValues(p)
+
+    def sync(self):
+        check(_lib.load().hu_batch_sync(self.h))
+
+    # ---- results ----
+    def alignments(self, with_traces: bool = True):
+        rows = np.zeros(self.n_seq, dtype=ALIGN_DT)
+        if not with_traces:
+            check(_lib.load().hu_batch_get_align(self.h, _p(rows), None, 0, None))
+            return rows, None
+        cap = int(self.n_seq) * (self.max_len + self.db.K + 8)
+        buf = np.zeros(cap, dtype=np.uint8)
+        off = np.zeros(self.n_seq + 1, dtype=np.int64)
+        check(_lib.load().hu_batch_get_align(self.h, _p(rows), _p(buf), cap, _p(off)))
+        raw = buf.tobytes()
+        traces = [raw[off[i]:off[i] + rows["traceLen"][i]].decode() for i in range(self.n_seq)]
+        return rows, traces
+
+    def merged(self) -> np.ndarray:
+        rows = np.zeros(self.n, dtype=ALIGN_DT)
+        check(_lib.load().hu_batch_get_merged(self.h, _p(rows)))
+        return rows
+
+    def aligned_codes(self) -> np.ndarray:
+        codes = np.zeros((self.n, self.db.L), dtype=np.int8)
+        check(_lib.load().hu_batch_get_aligned_codes(self.h, _p(codes)))
+        return codes
+
+    def seeds(self, with_dist: bool = False):
+        n = np.zeros(self.n, dtype=np.int32)
+        ids = np.zeros((self.n, self.max_n_seed), dtype=np.int32)
+        dist = np.zeros((self.n, self.max_n_seed)) if with_dist else None
+        check(_lib.load().hu_batch_get_seeds(self.h, _p(n), _p(ids), _p(dist)))
+        return n, ids, dist
+
+    def estimates(self):
+        n = np.zeros(self.n, dtype=np.int32)
+        rows = np.zeros((self.n, self.max_n_seed), dtype=PLACE_DT)
+        check(_lib.load().hu_batch_get_estimates(self.h, _p(n), _p(rows)))
+        return n, rows
+
+    def places(self):
+        n = np.zeros(self.n, dtype=np.int32)
+        rows = np.zeros((self.n, self.max_n_seed), dtype=PLACE_DT)
+        check(_lib.load().hu_batch_get_places(self.h, _p(n), _p(rows)))
+        return n, rows
+
+    def best(self) -> np.ndarray:
+        rows = np.zeros(self.n, dtype=PLACE_DT)
+        check(_lib.load().hu_batch_get_best(self.h, _p(rows)))
+        return rows
+
+    def stage_ms(self) -> np.ndarray:
+        ms = np.zeros(8, dtype=np.float32)
+        check(_lib.load().hu_batch_stage_ms(self.h, _p(ms)))
+        return ms
+
+    def stats(self) -> Dict[str, int]:
+        s = _lib.BatchStats()
+        check(_lib.load().hu_batch_get_stats(self.h, C.byref(s)))
+        return {f: int(getattr(s, f)) for f, _ in _lib.BatchStats._fields_}

@@ -1,0 +1,313 @@
+/*
+ * oracle_capi.cpp -- CPU ORACLE (test infrastructure, never shipped): flat C entry points
+ * over oracle.h so that tests/ and bench.py's cpu_baseline / --impl reference leg can drive
+ * the restatement through ctypes.  PARITY UNPINNED, see oracle.h.
+ *
+ * orc_assign() restates the per-read body of /root/reference/src/hmmufotu.cpp:641-733.
+ */
+#include "oracle.h"
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <sstream>
+
+using namespace orc;
+
+namespace {
+struct OrcPlaceRow { /* mirrored by tests/oracle_py.py */
+	int32_t start, end;
+	int64_t c, p, a;
+	double wuv, ratio, wnr, loglik, loglikTrue, height, qPlace, qTaxon, estLoglik;
+	int32_t outerIters, pad;
+};
+
+void fillRow(OrcPlaceRow& r, const Placement& pl, double est) {
+	r.start = pl.start; r.end = pl.end; r.c = pl.c; r.p = pl.p; r.a = pl.a;
+	r.wuv = pl.wuv; r.ratio = pl.ratio; r.wnr = pl.wnr; r.loglik = pl.loglik; r.loglikTrue = pl.loglikTrue;
+	r.height = pl.height; r.qPlace = pl.qPlace; r.qTaxon = pl.qTaxon; r.estLoglik = est;
+	r.outerIters = pl.outerIters; r.pad = 0;
+}
+} // namespace
+
+extern "C" {
+
+/* ------------------------------------------------------------------ HMM ---- */
+void* orc_hmm_from_costs(int K, int L, const double* eM, const double* eI, const double* T, const int* p2cs) {
+	Hmm* h = new Hmm();
+	h->L = L;
+	h->setProfileSize(K);
+	std::copy(eM, eM + (size_t) 4 * (K + 1), h->eM.begin());
+	std::copy(eI, eI + (size_t) 4 * (K + 1), h->eI.begin());
+	std::copy(T, T + (size_t) 9 * (K + 1), h->T.begin());
+	for (int k = 1; k <= K; ++k) {
+		h->p2cs[k] = p2cs[k];
+		h->cs2p[p2cs[k]] = k;
+	}
+	h->finalize();
+	return h;
+}
+
+void* orc_hmm_load(const char* path) {
+	Hmm* h = new Hmm();
+	if (h->loadText(path) != 0) { delete h; return NULL; }
+	return h;
+}
+
+void orc_hmm_free(void* h) { delete (Hmm*) h; }
+void orc_hmm_set_mode(void* h, int mode) { ((Hmm*) h)->setSequenceMode(mode); }
+int orc_hmm_K(void* h) { return ((Hmm*) h)->K; }
+int orc_hmm_L(void* h) { return ((Hmm*) h)->L; }
+
+void orc_hmm_get(void* hp, double* eM, double* eI, double* T, double* entry, double* exit_, int* p2cs, int* cs2p) {
+	Hmm* h = (Hmm*) hp;
+	if (eM) std::copy(h->eM.begin(), h->eM.end(), eM);
+	if (eI) std::copy(h->eI.begin(), h->eI.end(), eI);
+	if (T) std::copy(h->T.begin(), h->T.end(), T);
+	if (entry) std::copy(h->entry.begin(), h->entry.end(), entry);
+	if (exit_) std::copy(h->exit_.begin(), h->exit_.end(), exit_);
+	if (p2cs) std::copy(h->p2cs.begin(), h->p2cs.begin() + h->K + 1, p2cs);
+	if (cs2p) std::copy(h->cs2p.begin(), h->cs2p.begin() + h->L + 1, cs2p);
+}
+
+/* alignSeq after the seed search.  vpaths: nPaths x {start,end,from,to,nIns,nDel}.
+ * coords: {seqStart,seqEnd,hmmStart,hmmEnd,csStart,csEnd}; align: L chars; trace: NUL-terminated.
+ * returns 0, or -1 when the trace buffer is too small */
+int orc_align(void* hp, const char* read, int n, const int* vp, int nPaths, int* coords, double* cost,
+		char* align, char* trace, int traceCap, int* usedFallback, long* cells) {
+	Hmm* h = (Hmm*) hp;
+	std::vector<VPath> paths(nPaths);
+	for (int i = 0; i < nPaths; ++i) {
+		VPath p = {vp[i * 6], vp[i * 6 + 1], vp[i * 6 + 2], vp[i * 6 + 3], vp[i * 6 + 4], vp[i * 6 + 5]};
+		paths[i] = p;
+	}
+	HmmAlignment a = alignWithPaths(*h, std::string(read, n), paths);
+	coords[0] = a.seqStart; coords[1] = a.seqEnd; coords[2] = a.hmmStart; coords[3] = a.hmmEnd;
+	coords[4] = a.csStart; coords[5] = a.csEnd;
+	*cost = a.cost;
+	if (align) memcpy(align, a.align.data(), std::min((size_t) h->L, a.align.size()));
+	if (usedFallback) *usedFallback = a.usedFallback;
+	if (cells) *cells = a.bandCells;
+	if (trace) {
+		if ((int) a.trace.size() + 1 > traceCap) return -1;
+		memcpy(trace, a.trace.c_str(), a.trace.size() + 1);
+	}
+	return a.isValid() ? 0 : 1;
+}
+
+/* PE merge of two aligned strings (src/BandedHMMP7.cpp:1188-1213); coords/cost updated in place */
+void orc_merge(int L, int* coords, double* cost, char* align, const int* ocoords, double ocost, const char* oalign) {
+	HmmAlignment a, b;
+	a.K = b.K = 1; a.L = b.L = L;
+	a.seqStart = coords[0]; a.seqEnd = coords[1]; a.hmmStart = coords[2]; a.hmmEnd = coords[3]; a.csStart = coords[4]; a.csEnd = coords[5];
+	b.seqStart = ocoords[0]; b.seqEnd = ocoords[1]; b.hmmStart = ocoords[2]; b.hmmEnd = ocoords[3]; b.csStart = ocoords[4]; b.csEnd = ocoords[5];
+	a.cost = *cost; b.cost = ocost;
+	a.align.assign(align, L); b.align.assign(oalign, L);
+	a.merge(b);
+	coords[0] = a.seqStart; coords[1] = a.seqEnd; coords[2] = a.hmmStart; coords[3] = a.hmmEnd; coords[4] = a.csStart; coords[5] = a.csEnd;
+	*cost = a.cost;
+	memcpy(align, a.align.data(), L);
+}
+
+/* DigitalSeq of an aligned string (src/DigitalSeq.cpp:41-48); returns length written */
+int orc_digitize(const char* align, int n, int8_t* out) {
+	std::vector<int8_t> v = digitalSeq(std::string(align, n));
+	std::copy(v.begin(), v.end(), out);
+	return (int) v.size();
+}
+
+/* ---------------------------------------------------------------- model ---- */
+void* orc_model_create(int type, const double* pi, const double* R, double kr, double ky, double kappa, double beta) {
+	Model* m = new Model();
+	m->type = type;
+	for (int i = 0; i < 4; ++i) m->pi[i] = pi[i];
+	if (R) for (int i = 0; i < 16; ++i) m->R[i] = R[i];
+	m->kr = kr; m->ky = ky; m->kappa = kappa; m->beta = beta;
+	m->setup();
+	return m;
+}
+void* orc_model_load_text(const char* text) {
+	Model* m = new Model();
+	std::istringstream in(text);
+	if (m->loadText(in) != 0) { delete m; return NULL; }
+	return m;
+}
+void orc_model_free(void* m) { delete (Model*) m; }
+void orc_model_Pr(void* m, double v, double* P) { ((Model*) m)->Pr(v, P); }
+void orc_model_pi(void* m, double* pi) { for (int i = 0; i < 4; ++i) pi[i] = ((Model*) m)->pi[i]; }
+int orc_model_type(void* m) { return ((Model*) m)->type; }
+
+/* ----------------------------------------------------------------- tree ---- */
+struct OrcTree {
+	Tree t;
+	std::vector<std::vector<long> > children;
+	std::vector<double> rootMsg;
+};
+
+void* orc_tree_create(long nNodes, int csLen, long root, const int* parent, const double* blen, const double* height,
+		const int8_t* seq, const int* taxon, void* model, int dgK, const double* dgRates) {
+	OrcTree* o = new OrcTree();
+	Tree& t = o->t;
+	t.nNodes = nNodes; t.csLen = csLen; t.root = root;
+	t.parent.assign(parent, parent + nNodes);
+	t.blen.assign(blen, blen + nNodes);
+	t.height.assign(height, height + nNodes);
+	t.seq.assign(seq, seq + (size_t) nNodes * csLen);
+	t.anno.resize(nNodes);
+	for (long i = 0; i < nNodes; ++i) {
+		char buf[32];
+		snprintf(buf, sizeof buf, "taxon%d", taxon ? taxon[i] : (int) i);
+		t.anno[i] = buf;
+	}
+	t.model = *(Model*) model;
+	t.dg.K = dgK;
+	if (dgK) t.dg.r.assign(dgRates, dgRates + dgK);
+	o->children.resize(nNodes);
+	for (long i = 0; i < nNodes; ++i)
+		if (t.parent[i] >= 0) o->children[t.parent[i]].push_back(i);
+	return o;
+}
+void orc_tree_free(void* o) { delete (OrcTree*) o; }
+
+/* all-roots evaluation; with inferInternal the internal-node sequences (and the root's) are replaced
+ * by the arg-max of their upward message (src/PhyloTreeUnrooted.cpp:1085-1093) */
+void orc_tree_evaluate(void* op, int inferInternal) {
+	OrcTree* o = (OrcTree*) op;
+	Tree& t = o->t;
+	t.evaluateAll(o->children);
+	/* root message: loglik(root, j), src/PhyloTreeUnrooted.cpp:320-346 */
+	const int KK = std::max(t.dg.K, 1);
+	o->rootMsg.assign((size_t) t.csLen * 4, 0.0);
+	std::vector<double> mat((size_t) 4 * KK), PP;
+	for (int j = 0; j < t.csLen; ++j) {
+		std::fill(mat.begin(), mat.end(), 0.0);
+		for (size_t ci = 0; ci < o->children[t.root].size(); ++ci) {
+			long ch = o->children[t.root][ci];
+			for (int k = 0; k < KK; ++k) {
+				double P[16], c[4];
+				t.model.Pr(t.blen[ch] * (t.dg.K ? t.dg.r[k] : 1.0), P);
+				dpsMat(P, t.U(ch) + (size_t) j * 4, c);
+				for (int i = 0; i < 4; ++i) mat[(size_t) k * 4 + i] += c[i];
+			}
+		}
+		double* out = &o->rootMsg[(size_t) j * 4];
+		if (t.dg.K) {
+			for (int i = 0; i < 4; ++i) {
+				double mx = mat[i];
+				for (int k = 1; k < KK; ++k) mx = std::max(mx, mat[(size_t) k * 4 + i]);
+				double sc = (mx != NEG_INF && mx < -510.0) ? -510.0 - mx : 0;
+				double s = ::exp(mat[i] + sc);
+				for (int k = 1; k < KK; ++k) s = s + ::exp(mat[(size_t) k * 4 + i] + sc);
+				out[i] = ::log(s / KK) - sc;
+			}
+		} else
+			for (int i = 0; i < 4; ++i) out[i] = mat[i];
+	}
+	if (inferInternal) {
+		for (long x = 0; x < t.nNodes; ++x) {
+			if (o->children[x].empty()) continue;
+			const double* m = x == t.root ? &o->rootMsg[0] : t.U(x);
+			for (int j = 0; j < t.csLen; ++j) {
+				const double* v = m + (size_t) j * 4;
+				int b = 0;
+				for (int k = 1; k < 4; ++k) if (v[k] > v[b]) b = k;
+				t.seq[(size_t) x * t.csLen + j] = (int8_t) b;
+			}
+		}
+	}
+}
+
+void orc_tree_get(void* op, double* up, double* dn, int8_t* seq) {
+	Tree& t = ((OrcTree*) op)->t;
+	if (up) std::copy(t.up.begin(), t.up.end(), up);
+	if (dn) std::copy(t.dn.begin(), t.dn.end(), dn);
+	if (seq) std::copy(t.seq.begin(), t.seq.end(), seq);
+}
+void orc_tree_set_messages(void* op, const double* up, const double* dn) {
+	Tree& t = ((OrcTree*) op)->t;
+	size_t n = (size_t) t.nNodes * t.csLen * 4;
+	t.up.assign(up, up + n);
+	t.dn.assign(dn, dn + n);
+}
+
+/* getSeed + truncation to maxN (src/HmmUFOtu_main.cpp:127-152, src/hmmufotu.cpp:646-647) */
+int orc_get_seed(void* op, const int8_t* seq, int start, int end, double maxDiff, double maxHeight, int seedOrder, int maxN,
+		long* ids, double* dist) {
+	Tree& t = ((OrcTree*) op)->t;
+	std::vector<PTLoc> s = getSeed(t, seq, start, end, maxDiff, maxHeight, seedOrder);
+	if ((int) s.size() > maxN) s.resize(maxN);
+	for (size_t i = 0; i < s.size(); ++i) { ids[i] = s[i].id; dist[i] = s[i].dist; }
+	return (int) s.size();
+}
+
+long orc_pdist(void* op, long node, const int8_t* seq, int start, int end, long* N) {
+	Tree& t = ((OrcTree*) op)->t;
+	long d = 0;
+	pDist(t.s(node), seq, start, end, &d, N);
+	return d;
+}
+
+void orc_estimate(void* op, const int8_t* seq, int start, int end, long id, double dist, OrcPlaceRow* out) {
+	Tree& t = ((OrcTree*) op)->t;
+	PTLoc loc = {start, end, id, dist};
+	Placement pl = estimateSeq(t, seq, loc);
+	fillRow(*out, pl, pl.loglik);
+}
+
+void orc_place(void* op, const int8_t* seq, OrcPlaceRow* io, double maxHeight) {
+	Tree& t = ((OrcTree*) op)->t;
+	Placement pl;
+	pl.start = io->start; pl.end = io->end; pl.c = io->c; pl.p = io->p; pl.a = io->a;
+	pl.wuv = io->wuv; pl.ratio = io->ratio; pl.wnr = io->wnr; pl.loglik = io->loglik;
+	double est = io->loglik;
+	placeSeq(t, seq, pl, maxHeight);
+	fillRow(*io, pl, est);
+}
+
+/* per-read SEP body, src/hmmufotu.cpp:645-733.  seeds given (from orc_get_seed or the device);
+ * useTrue != 0 substitutes the intended root loglik for the literal constant.
+ * rows: up to nSeeds entries, post-sort order; returns n (number of placements kept); rows[0] is bestPlace */
+int orc_assign(void* op, const int8_t* seq, int start, int end, int nSeeds, const long* ids, const double* dist,
+		double maxError, double maxHeight, int useTrue, OrcPlaceRow* rows) {
+	Tree& t = ((OrcTree*) op)->t;
+	std::vector<Placement> places;
+	for (int i = 0; i < nSeeds; ++i) {
+		PTLoc loc = {start, end, ids[i], dist[i]};
+		places.push_back(estimateSeq(t, seq, loc));
+	}
+	filterPlacements(places, maxError);
+	std::vector<double> est(places.size());
+	for (size_t i = 0; i < places.size(); ++i) {
+		est[i] = places[i].loglik;
+		places[i].outerIters = (int) i; /* temporarily: index into est[] */
+	}
+	std::vector<int> iters(places.size());
+	for (size_t i = 0; i < places.size(); ++i) {
+		int idx = places[i].outerIters;
+		placeSeq(t, seq, places[i], maxHeight);
+		iters[i] = places[i].outerIters;
+		places[i].outerIters = idx;
+		if (useTrue) places[i].loglik = places[i].loglikTrue;
+	}
+	calcQValues(t, places);
+	sortByQPlace(places);
+	for (size_t i = 0; i < places.size(); ++i) {
+		int idx = places[i].outerIters;
+		places[i].outerIters = iters[idx];
+		fillRow(rows[i], places[i], est[idx]);
+	}
+	return (int) places.size();
+}
+
+/* permutation std::sort(rbegin, rend) leaves on an all-equal array of n elements: out[i] = old index now at i */
+void orc_equal_sort_perm(int n, int* out) {
+	std::vector<std::pair<double, int> > v(n);
+	for (int i = 0; i < n; ++i) v[i] = std::make_pair(0.0, i);
+	struct Cmp { static bool lt(const std::pair<double, int>& a, const std::pair<double, int>& b) { return a.first < b.first; } };
+	std::sort(v.rbegin(), v.rend(), Cmp::lt);
+	for (int i = 0; i < n; ++i) out[i] = v[i].second;
+}
+
+int orc_sizeof_place_row() { return (int) sizeof(OrcPlaceRow); }
+
+} // extern "C"

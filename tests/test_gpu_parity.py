@@ -1,0 +1,167 @@
+"""-m gpu: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs."""
+import numpy as np
+import pytest
+
+import oracle_py as O
+from hmmufotu_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-9  # BASELINE.json north_star: placement log-likelihood and branch lengths within 1e-9 relative
+
+
+@pytest.fixture(scope="module")
+def small():
+    from hmmufotu_b200 import engine
+    db = synth.make_db(n_leaves=60, cs_len=700, occupancy=0.85, seed=11)
+    otree = O.OracleTree(db)                      # evaluates messages, infers internal sequences
+    up, dn = otree.messages()
+    db.seq = otree.seqs()
+    ohmm = O.OracleHmm(db)
+    gdb = engine.Database(db, messages=(up, dn))
+    reads = synth.make_reads(db, 300, read_len=200, seed=5, drop_seed_prob=0.05)
+    return dict(db=db, otree=otree, ohmm=ohmm, gdb=gdb, reads=reads, engine=engine)
+
+
+def test_hmm_finalize_matches_oracle(small):
+    p = small["ohmm"].params()
+    assert np.array_equal(p["entry"], small["gdb"].entry)
+    assert np.array_equal(p["exit"], small["gdb"].exit)
+
+
+def test_model_pr(small):
+    from hmmufotu_b200 import engine
+    for t in range(6):
+        m = synth.gg97_model(t)
+        om = O.OracleModel(m)
+        for v in (0.0, 1e-4, 0.03, 0.4, 2.5):
+            np.testing.assert_allclose(engine.model_Pr(m, v), om.Pr(v), rtol=1e-12, atol=1e-15)
+
+
+def test_messages_device_vs_oracle(small):
+    engine = small["engine"]
+    db = small["db"]
+    g2 = engine.Database(db, messages=None, infer_internal=True)
+    up, dn = g2.messages()
+    oup, odn = small["otree"].messages()
+    nonroot = np.arange(db.n_nodes) != db.root
+    for a, b in ((up, oup), (dn, odn)):
+        a, b = a[nonroot], b[nonroot]
+        fin = np.isfinite(b)
+        assert np.array_equal(np.isfinite(a), fin)
+        np.testing.assert_allclose(a[fin], b[fin], rtol=1e-12)
+    assert np.array_equal(g2.seqs(), small["otree"].seqs())
+    g2.close()
+
+
+def _align_oracle(small, i):
+    rs = small["reads"]
+    return small["ohmm"].align(rs.read_str(i), rs.vpaths[i, :rs.n_paths[i]])
+
+
+def test_viterbi_bit_exact(small):
+    engine, rs = small["engine"], small["reads"]
+    b = engine.Batch(small["gdb"], rs.n, 260)
+    b.upload(rs)
+    b.alignSeq()
+    rows, traces = b.alignments()
+    codes = b.aligned_codes()
+    n_fb = 0
+    for i in range(rs.n):
+        o = _align_oracle(small, i)
+        r = rows[i]
+        assert [r["seqStart"], r["seqEnd"], r["hmmStart"], r["hmmEnd"], r["csStart"], r["csEnd"]] == list(o["coords"]), i
+        assert r["cost"] == o["cost"], (i, r["cost"], o["cost"])       # bit-exact fp64
+        assert traces[i] == o["trace"], i
+        assert bool(r["flags"] & 3) == o["fallback"], i
+        assert r["cells"] == o["cells"], i
+        n_fb += o["fallback"]
+        s, e = o["coords"][4] - 1, o["coords"][5] - 1
+        want = O.digitize(o["align"])
+        got = codes[i].copy()
+        got[got < 0] = -2
+        assert np.array_equal(got[s:e + 1], want[s:e + 1]), i
+        assert (got[:s] < 0).all() and (got[e + 1:] < 0).all()
+        assert small["gdb"].trace_to_align(rs.read_str(i), r, traces[i]) == o["align"], i
+    assert n_fb > 0  # the full-Viterbi path was exercised
+    b.close()
+
+
+def _oracle_aligned(small, n):
+    rs = small["reads"]
+    L = small["db"].cs_len
+    codes = np.full((n, L), -2, dtype=np.int8)
+    start = np.zeros(n, dtype=np.int32)
+    end = np.zeros(n, dtype=np.int32)
+    for i in range(n):
+        o = _align_oracle(small, i)
+        codes[i] = O.digitize(o["align"])
+        start[i], end[i] = o["coords"][4] - 1, o["coords"][5] - 1
+    return codes, start, end
+
+
+def test_seed_estimate_place(small):
+    engine, otree = small["engine"], small["otree"]
+    n = 64
+    codes, start, end = _oracle_aligned(small, n)
+    b = engine.Batch(small["gdb"], n, 260)
+    b.set_aligned(codes, start, end)
+    p = engine.SepParams()
+    b.sep(p)
+    ns, ids, dist = b.seeds(with_dist=True)
+    nk, est = b.estimates()
+    nk2, pl = b.places()
+    best = b.best()
+    for i in range(n):
+        oid, odist = otree.get_seed(codes[i], start[i], end[i], 50, order=1)
+        assert ns[i] == len(oid)
+        assert np.array_equal(ids[i, :ns[i]], oid), i
+        assert np.array_equal(dist[i, :ns[i]], odist), i             # exact d/N doubles
+        rows = otree.assign(codes[i], start[i], end[i], oid, odist)    # literal pipeline
+        assert nk[i] == len(rows) == nk2[i]
+        # estimates in filter order == oracle placements sorted by estimated loglik
+        o_sorted = sorted(rows, key=lambda r: -r.estLoglik)
+        for k in range(nk[i]):
+            g, o = est[i, k], o_sorted[k]
+            assert (g["cNode"], g["pNode"]) == (o.c, o.p), (i, k)
+            np.testing.assert_allclose(g["estLoglik"], o.estLoglik, rtol=RTOL)
+            gp = pl[i, k]
+            assert (gp["cNode"], gp["pNode"], gp["aNode"]) == (o.c, o.p, o.a), (i, k)
+            np.testing.assert_allclose([gp["ratio"], gp["wnr"], gp["loglik"], gp["loglikTrue"], gp["height"]],
+                                       [o.ratio, o.wnr, o.loglik, o.loglikTrue, o.height], rtol=RTOL, atol=1e-12)
+            assert gp["outerIters"] == o.outerIters
+        o0 = rows[0]                                                   # bestPlace
+        g0 = best[i]
+        assert (g0["cNode"], g0["pNode"], g0["aNode"]) == (o0.c, o0.p, o0.a), i
+        np.testing.assert_allclose([g0["qPlace"], g0["qTaxon"], g0["ratio"], g0["wnr"]],
+                                   [o0.qPlace, o0.qTaxon, o0.ratio, o0.wnr], rtol=1e-7, atol=1e-9, equal_nan=True)
+    # intended-loglik mode: the chosen edge is the true maximum-likelihood placement
+    p2 = engine.SepParams(use_true_loglik=True)
+    b.calcQValues(p2)
+    best2 = b.best()
+    for i in range(n):
+        oid, odist = otree.get_seed(codes[i], start[i], end[i], 50, order=1)
+        rows = otree.assign(codes[i], start[i], end[i], oid, odist, use_true=True)
+        assert (best2[i]["cNode"], best2[i]["pNode"]) == (rows[0].c, rows[0].p), i
+    b.close()
+
+
+def test_full_pipeline_from_reads(small):
+    engine, rs, otree = small["engine"], small["reads"], small["otree"]
+    n = 48
+    sub = rs.slice(0, n)
+    b = engine.Batch(small["gdb"], n, 260)
+    b.upload(sub)
+    b.assign(engine.SepParams())
+    best = b.best()
+    st = b.stats()
+    assert st["launches"] >= 8 and st["cells"] > 0
+    for i in range(n):
+        o = _align_oracle(small, i)
+        seq = O.digitize(o["align"])
+        s, e = o["coords"][4] - 1, o["coords"][5] - 1
+        oid, odist = otree.get_seed(seq, s, e, 50, order=1)
+        rows = otree.assign(seq, s, e, oid, odist)
+        assert (best[i]["cNode"], best[i]["pNode"], best[i]["aNode"]) == (rows[0].c, rows[0].p, rows[0].a), i
+        assert best[i]["nPlaces"] == len(rows)
+    b.close()
