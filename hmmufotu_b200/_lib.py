@@ -67,7 +67,7 @@ SYMBOLS = ["hu_hmm_finalize", "hu_model_Pr", "hu_db_create", "hu_db_destroy", "h
            "hu_finalize_batch", "hu_assign_batch", "hu_batch_sync", "hu_batch_get_align", "hu_batch_get_merged",
            "hu_batch_get_aligned_codes", "hu_batch_get_seeds", "hu_batch_get_estimates", "hu_batch_get_places",
            "hu_batch_get_best", "hu_batch_stage_ms", "hu_batch_get_stats", "hu_trace_to_align", "hu_last_error",
-           "hu_version", "hu_host_alloc", "hu_host_free"]
+           "hu_version", "hu_host_alloc", "hu_host_free", "hu_batch_mark", "hu_batch_elapsed"]
 
 _LIB = None
 
@@ -114,6 +114,8 @@ def load() -> C.CDLL:
     L.hu_host_alloc.restype = vp
     L.hu_host_alloc.argtypes = [C.c_size_t]
     L.hu_host_free.argtypes = [vp]
+    L.hu_batch_mark.argtypes = [vp, C.c_int]
+    L.hu_batch_elapsed.argtypes = [vp, C.c_int, vp, C.c_int, P(C.c_float)]
     _LIB = L
     return L
 

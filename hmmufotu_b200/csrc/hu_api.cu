@@ -408,6 +408,20 @@ int hu_batch_get_best(hu_batch* b, hu_place_row* rows) {
 	return HU_OK;
 }
 
+int hu_batch_mark(hu_batch* b, int id) {
+	if (!b || id < 0 || id > 7) { setError("hu_batch_mark: bad mark id"); return HU_ERR_ARG; }
+	HU_CUDA(cudaSetDevice(b->db->device));
+	HU_CUDA(cudaEventRecord(b->ev[8 + id], b->stream));
+	return HU_OK;
+}
+int hu_batch_elapsed(hu_batch* from, int idFrom, hu_batch* to, int idTo, float* ms) {
+	if (!from || !to || !ms || idFrom < 0 || idFrom > 7 || idTo < 0 || idTo > 7) { setError("hu_batch_elapsed: bad arguments"); return HU_ERR_ARG; }
+	HU_CUDA(cudaSetDevice(from->db->device));
+	HU_CUDA(cudaEventSynchronize(to->ev[8 + idTo]));
+	HU_CUDA(cudaEventElapsedTime(ms, from->ev[8 + idFrom], to->ev[8 + idTo]));
+	return HU_OK;
+}
+
 int hu_batch_stage_ms(hu_batch* b, float ms[8]) {
 	if (!b || !ms) return HU_ERR_ARG;
 	HU_CUDA(cudaSetDevice(b->db->device));

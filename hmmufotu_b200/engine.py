@@ -60,6 +60,31 @@ def hmm_finalize(K: int, T: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
     return entry, exit_
 
 
+def pinned_empty(shape, dtype) -> np.ndarray:
+    """numpy array over page-locked host memory (cudaMallocHost); freed when the array is collected."""
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape)) * dtype.itemsize
+    L = _lib.load()
+    ptr = L.hu_host_alloc(max(n, 1))
+    if not ptr:
+        raise _lib.HuError("hu_host_alloc failed: " + L.hu_last_error().decode())
+    buf = (C.c_char * max(n, 1)).from_address(ptr)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+    _PINNED[ptr] = buf
+    import weakref
+    weakref.finalize(buf, L.hu_host_free, ptr)
+    return arr
+
+
+_PINNED = {}
+
+
+def pinned_copy(a: np.ndarray) -> np.ndarray:
+    out = pinned_empty(a.shape, a.dtype)
+    out[...] = a
+    return out
+
+
 class Database:
     """One database replica on one GPU."""
 
@@ -275,6 +300,15 @@ class Batch:
         rows = np.zeros(self.n, dtype=PLACE_DT)
         check(_lib.load().hu_batch_get_best(self.h, _p(rows)))
         return rows
+
+    def mark(self, i: int):
+        check(_lib.load().hu_batch_mark(self.h, i))
+
+    def elapsed_ms(self, i: int, other: "Batch", j: int) -> float:
+        """ms from mark i of this workspace to mark j of `other` (waits for the latter)."""
+        ms = C.c_float()
+        check(_lib.load().hu_batch_elapsed(self.h, i, other.h, j, C.byref(ms)))
+        return float(ms.value)
 
     def stage_ms(self) -> np.ndarray:
         ms = np.zeros(8, dtype=np.float32)

@@ -251,18 +251,14 @@ def make_db(n_leaves: int = 125, cs_len: int = 1486, occupancy: float = 0.87, se
     del states
     leaf_ids = np.flatnonzero(is_leaf)
     # per-leaf deletions on occupied columns and sparse insertions elsewhere
-    dele = rng.random((leaf_ids.size, n_occ)) < leaf_del
-    sub = seq[leaf_ids][:, occ_cols]
-    sub[dele] = -2
     tmp = seq[leaf_ids]
-    tmp[:, occ_cols] = sub
+    n_del = rng.binomial(leaf_ids.size * n_occ, leaf_del)
+    tmp[rng.integers(0, leaf_ids.size, n_del), occ_cols[rng.integers(0, n_occ, n_del)]] = -2
     un_cols = np.flatnonzero(~occ)
     if un_cols.size and leaf_ins > 0:
-        ins = rng.random((leaf_ids.size, un_cols.size)) < leaf_ins
-        insb = rng.integers(0, 4, ins.shape).astype(np.int8)
-        cur = tmp[:, un_cols]
-        cur[ins] = insb[ins]
-        tmp[:, un_cols] = cur
+        n_ins = rng.binomial(leaf_ids.size * un_cols.size, leaf_ins)
+        tmp[rng.integers(0, leaf_ids.size, n_ins), un_cols[rng.integers(0, un_cols.size, n_ins)]] = \
+            rng.integers(0, 4, n_ins).astype(np.int8)
     seq[leaf_ids] = tmp
     # internal rows: ungapped placeholder (to be replaced by the arg-max of the upward message)
     internal = np.flatnonzero(~is_leaf)

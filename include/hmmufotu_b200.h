@@ -187,6 +187,11 @@ int hu_batch_get_estimates(hu_batch* b, int32_t* nKept, hu_place_row* rows /* nR
 int hu_batch_get_places(hu_batch* b, int32_t* nKept, hu_place_row* rows /* nReads x maxNSeed */);
 int hu_batch_get_best(hu_batch* b, hu_place_row* rows /* nReads */);
 
+/* user timing marks: record CUDA event `id` (0..7) on the batch stream; elapsed ms between two marks
+ * (possibly of two workspaces of the same device), both of which must have completed */
+int hu_batch_mark(hu_batch* b, int id);
+int hu_batch_elapsed(hu_batch* from, int idFrom, hu_batch* to, int idTo, float* ms);
+
 /* per-stage device time of the last run of each stage (CUDA events on the batch stream), ms:
  * [0] align [1] seed scan [2] seed select [3] estimate [4] place [5] finalize; and work counters */
 int hu_batch_stage_ms(hu_batch* b, float ms[8]);

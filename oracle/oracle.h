@@ -136,7 +136,8 @@ struct Tree {
 	const int8_t* s(long id) const { return &seq[(size_t) id * csLen]; }
 	/* all-roots Felsenstein evaluation (src/hmmufotu-build.cpp:455-459,
 	 * src/PhyloTreeUnrooted.cpp:320-374): fills up/dn from leaf sequences */
-	void evaluateAll(const std::vector<std::vector<long> >& children);
+	/* columns [j0, j1) only (column stripes are independent: one thread each); alloc: (re)size up/dn first */
+	void evaluateAll(const std::vector<std::vector<long> >& children, int j0 = 0, int j1 = -1, bool alloc = true);
 };
 
 struct PTLoc { int start, end; long id; double dist; };      /* src/PhyloTreeUnrooted.h:390-405 */

@@ -11,6 +11,8 @@
 #include <cstdio>
 #include <cstring>
 #include <sstream>
+#include <atomic>
+#include <thread>
 
 using namespace orc;
 
@@ -171,10 +173,26 @@ void orc_tree_free(void* o) { delete (OrcTree*) o; }
 
 /* all-roots evaluation; with inferInternal the internal-node sequences (and the root's) are replaced
  * by the arg-max of their upward message (src/PhyloTreeUnrooted.cpp:1085-1093) */
-void orc_tree_evaluate(void* op, int inferInternal) {
+void orc_tree_evaluate_mt(void* op, int inferInternal, int nThreads);
+void orc_tree_evaluate(void* op, int inferInternal) { orc_tree_evaluate_mt(op, inferInternal, 1); }
+
+void orc_tree_evaluate_mt(void* op, int inferInternal, int nThreads) {
 	OrcTree* o = (OrcTree*) op;
 	Tree& t = o->t;
-	t.evaluateAll(o->children);
+	if (nThreads <= 1)
+		t.evaluateAll(o->children);
+	else { /* column stripes are independent */
+		t.up.assign((size_t) t.nNodes * t.csLen * 4, 0.0);
+		t.dn.assign((size_t) t.nNodes * t.csLen * 4, 0.0);
+		std::vector<std::thread> th;
+		const int per = (t.csLen + nThreads - 1) / nThreads;
+		for (int i = 0; i < nThreads; ++i) {
+			const int j0 = i * per, j1 = std::min(t.csLen, j0 + per);
+			if (j0 >= j1) break;
+			th.push_back(std::thread([&t, o, j0, j1]() { t.evaluateAll(o->children, j0, j1, false); }));
+		}
+		for (size_t i = 0; i < th.size(); ++i) th[i].join();
+	}
 	/* root message: loglik(root, j), src/PhyloTreeUnrooted.cpp:320-346 */
 	const int KK = std::max(t.dg.K, 1);
 	o->rootMsg.assign((size_t) t.csLen * 4, 0.0);
@@ -306,6 +324,58 @@ void orc_equal_sort_perm(int n, int* out) {
 	struct Cmp { static bool lt(const std::pair<double, int>& a, const std::pair<double, int>& b) { return a.first < b.first; } };
 	std::sort(v.rbegin(), v.rend(), Cmp::lt);
 	for (int i = 0; i < n; ++i) out[i] = v[i].second;
+}
+
+/* The per-read body of the reference's task loop (src/hmmufotu.cpp:610-748) for a list of SE reads, one
+ * std::thread per core pulling reads from a shared counter (the reference uses one OpenMP task per read).
+ * The tree may hold a column slice [col0, col0 + csLen) of the consensus; aligned reads are cut to it.
+ * seedOrder 0 = std::sort as in the reference.  out: one best-placement row per read; coords: 6 ints + cost. */
+int orc_run_reads(void* hp, void* op, int nReads, const char* reads, const long* offsets, const int* vpaths, const int* nPaths,
+		int col0, int maxNSeed, double maxError, int seedOrder, int useTrue, int nThreads, OrcPlaceRow* out, int* coords, double* cost) {
+	Hmm* h = (Hmm*) hp;
+	Tree& t = ((OrcTree*) op)->t;
+	std::atomic<int> next(0), bad(0);
+	auto work = [&]() {
+		for (;;) {
+			const int r = next.fetch_add(1);
+			if (r >= nReads) return;
+			std::vector<VPath> paths(nPaths[r]);
+			for (int i = 0; i < nPaths[r]; ++i) {
+				const int* v = vpaths + ((size_t) r * 2 + i) * 6;
+				VPath p = {v[0], v[1], v[2], v[3], v[4], v[5]};
+				paths[i] = p;
+			}
+			HmmAlignment a = alignWithPaths(*h, std::string(reads + offsets[r], offsets[r + 1] - offsets[r]), paths);
+			if (coords) {
+				int* c = coords + (size_t) r * 6;
+				c[0] = a.seqStart; c[1] = a.seqEnd; c[2] = a.hmmStart; c[3] = a.hmmEnd; c[4] = a.csStart; c[5] = a.csEnd;
+			}
+			if (cost) cost[r] = a.cost;
+			std::vector<int8_t> seq = digitalSeq(a.align);
+			const int s = a.csStart - 1 - col0, e = a.csEnd - 1 - col0;
+			if (!a.isValid() || s < 0 || e >= t.csLen) { bad++; memset(&out[r], 0, sizeof(OrcPlaceRow)); out[r].c = -1; continue; }
+			const int8_t* sq = seq.data() + col0;
+			std::vector<PTLoc> seeds = getSeed(t, sq, s, e, INF, INF, seedOrder);
+			if ((int) seeds.size() > maxNSeed) seeds.resize(maxNSeed);
+			std::vector<Placement> places;
+			for (size_t i = 0; i < seeds.size(); ++i) places.push_back(estimateSeq(t, sq, seeds[i]));
+			filterPlacements(places, maxError);
+			for (size_t i = 0; i < places.size(); ++i) {
+				const double est = places[i].loglik;
+				placeSeq(t, sq, places[i], INF);
+				if (useTrue) places[i].loglik = places[i].loglikTrue;
+				places[i].qTaxon = est; /* carried through calcQValues? no: overwritten; kept only for debugging */
+			}
+			calcQValues(t, places);
+			sortByQPlace(places);
+			fillRow(out[r], places[0], 0.0);
+			out[r].pad = (int) places.size();
+		}
+	};
+	std::vector<std::thread> th;
+	for (int i = 0; i < std::max(1, nThreads); ++i) th.push_back(std::thread(work));
+	for (size_t i = 0; i < th.size(); ++i) th[i].join();
+	return bad.load();
 }
 
 int orc_sizeof_place_row() { return (int) sizeof(OrcPlaceRow); }

@@ -484,13 +484,16 @@ void calcQValues(const Tree& t, std::vector<Placement>& places) { /* src/HmmUFOt
 }
 
 /* ------------------------------------------------- all-roots tree evaluation ---- */
-void Tree::evaluateAll(const std::vector<std::vector<long> >& children) {
+void Tree::evaluateAll(const std::vector<std::vector<long> >& children, int j0, int j1, bool alloc) {
 	/* Mathematically what src/hmmufotu-build.cpp:455-459 obtains by re-rooting at every node:
 	 * up[id] = loglik(id, j) rooted above id; dn[id] = loglik(parent, j) rooted at id.
 	 * Summation order over neighbours: children in list order, then the parent. */
 	const int Kd = dg.K, KK = std::max(Kd, 1);
-	up.assign((size_t) nNodes * csLen * 4, 0.0);
-	dn.assign((size_t) nNodes * csLen * 4, 0.0);
+	if (j1 < 0) j1 = csLen;
+	if (alloc) {
+		up.assign((size_t) nNodes * csLen * 4, 0.0);
+		dn.assign((size_t) nNodes * csLen * 4, 0.0);
+	}
 	std::vector<long> order;
 	order.reserve(nNodes);
 	{
@@ -510,7 +513,7 @@ void Tree::evaluateAll(const std::vector<std::vector<long> >& children) {
 		if (x == root) continue;
 		double* out = &up[(size_t) x * csLen * 4];
 		bool leaf = children[x].empty();
-		for (int j = 0; j < csLen; ++j) {
+		for (int j = j0; j < j1; ++j) {
 			std::fill(mat.begin(), mat.end(), 0.0);
 			for (size_t ci = 0; ci < children[x].size(); ++ci) {
 				long ch = children[x][ci];
@@ -533,7 +536,7 @@ void Tree::evaluateAll(const std::vector<std::vector<long> >& children) {
 		long pa = parent[x];
 		double* out = &dn[(size_t) x * csLen * 4];
 		bool paLeafLike = (children[pa].size() + (pa == root ? 0 : 1)) == 1; /* isLeaf(): one neighbour */
-		for (int j = 0; j < csLen; ++j) {
+		for (int j = j0; j < j1; ++j) {
 			std::fill(mat.begin(), mat.end(), 0.0);
 			for (size_t ci = 0; ci < children[pa].size(); ++ci) {
 				long sib = children[pa][ci];

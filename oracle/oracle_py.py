@@ -12,7 +12,7 @@ from typing import List, Optional, Sequence, Tuple
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-ORACLE_DIR = os.path.join(os.path.dirname(_HERE), "oracle")
+ORACLE_DIR = _HERE
 _LIB: Optional[C.CDLL] = None
 
 
@@ -70,6 +70,8 @@ def lib() -> C.CDLL:
         L.orc_place.argtypes = [vp, vp, P(PlaceRow), f64]
         L.orc_assign.argtypes = [vp, vp, i32, i32, i32, vp, vp, f64, f64, i32, P(PlaceRow)]
         L.orc_equal_sort_perm.argtypes = [i32, vp]
+        L.orc_tree_evaluate_mt.argtypes = [vp, i32, i32]
+        L.orc_run_reads.argtypes = [vp, vp, i32, C.c_char_p, vp, vp, vp, i32, i32, f64, i32, i32, i32, P(PlaceRow), vp, vp]
         assert L.orc_sizeof_place_row() == C.sizeof(PlaceRow)
         _LIB = L
     return _LIB
@@ -174,7 +176,7 @@ class OracleModel:
 
 
 class OracleTree:
-    def __init__(self, db, evaluate: bool = True, infer_internal: bool = True):
+    def __init__(self, db, evaluate: bool = True, infer_internal: bool = True, threads: int = 1):
         L = lib()
         self.db = db
         self.model = OracleModel(db.model)
@@ -188,7 +190,7 @@ class OracleTree:
         self.h = L.orc_tree_create(db.n_nodes, db.cs_len, db.root, _p(parent), _p(blen), _p(height), _p(seq), _p(taxon),
                                    self.model.h, int(rates.size), _p(rates) if rates.size else None)
         if evaluate:
-            L.orc_tree_evaluate(self.h, int(infer_internal))
+            L.orc_tree_evaluate_mt(self.h, int(infer_internal), int(threads))
 
     def __del__(self):
         if getattr(self, "h", None):
@@ -236,6 +238,23 @@ class OracleTree:
         s = np.ascontiguousarray(seq, dtype=np.int8)
         n = lib().orc_assign(self.h, _p(s), start, end, ids.size, _p(ids), _p(dist), max_error, max_height, int(use_true), rows)
         return [rows[i] for i in range(n)]
+
+
+def run_reads(hmm: "OracleHmm", tree: "OracleTree", reads, col0: int = 0, max_n_seed: int = 50, max_error: float = 20.0,
+              seed_order: int = 0, use_true: bool = False, threads: int = 1):
+    """The reference's per-read task body for a ReadSet on `threads` host threads.
+    -> (rows: list[PlaceRow], coords int32 [n, 6], cost f64 [n], n_bad)"""
+    n = reads.n
+    text = "".join("ACGT"[c] for c in reads.codes).encode()
+    offsets = np.ascontiguousarray(reads.offsets, dtype=np.int64)
+    vp = np.ascontiguousarray(reads.vpaths, dtype=np.int32)
+    npth = np.ascontiguousarray(reads.n_paths, dtype=np.int32)
+    rows = (PlaceRow * n)()
+    coords = np.zeros((n, 6), dtype=np.int32)
+    cost = np.zeros(n)
+    bad = lib().orc_run_reads(hmm.h, tree.h, n, text, _p(offsets), _p(vp), _p(npth), col0, max_n_seed, max_error,
+                              seed_order, int(use_true), threads, rows, _p(coords), _p(cost))
+    return rows, coords, cost, bad
 
 
 def equal_sort_perm(n: int) -> np.ndarray:
