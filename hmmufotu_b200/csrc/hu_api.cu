@@ -268,6 +268,7 @@ int hu_batch_set_aligned(hu_batch* b, int32_t n, const int8_t* codes, const int3
 int hu_align_batch(hu_batch* b, int mode) {
 	if (!b || b->nSeq < 1 || !b->vit.plans) { setError("hu_align_batch: no reads uploaded"); return HU_ERR_STATE; }
 	HU_CUDA(cudaSetDevice(b->db->device));
+	b->launches = 0;
 	HU_CUDA(cudaEventRecord(b->ev[0], b->stream));
 	HU_TRY(launchViterbi(b, mode));
 	windowsKernel<<<(b->nReads + 127) / 128, 128, 0, b->stream>>>(b->nReads, b->merged, b->winStart, b->winEnd);
