@@ -11,7 +11,7 @@
 namespace hu {
 
 #define HU_EST_THREADS 128
-#define HU_EST_CAPW 2048 // columns of R kept in shared memory (64 KB); wider windows recompute R in pass 2
+#define HU_EST_CAPW 1536 // columns of g kept in shared memory (48 KB); wider windows recompute g in pass 2
 
 struct EstArgs {
 	int nReads, maxNSeed, capW, pad;
@@ -83,57 +83,62 @@ __global__ void __launch_bounds__(HU_EST_THREADS) estimateKernel(EstArgs a, Tree
 		const double* U = t.up + ((size_t) u * t.csLen + start) * 4;
 		const double* V = t.dn + ((size_t) u * t.csLen + start) * 4;
 		const bool store = W <= a.capW;
-		// ---- pass 1: R_j and the unweighted branch-length estimate (cpp:1018-1032) ----
+		// ---- pass 1: g_j = (P(wur) e^U_j) * (P(wvr) e^V_j) (= e^{R_j} up to the column scale) and the
+		//      unweighted branch-length estimate (cpp:1018-1032).  Linear domain, see expNorm().
 		int diff = 0;
+		double sumScale = 0;
 		for (int c = tid; c < W; c += HU_EST_THREADS) {
-			double uv[4], vv[4], ya[4], yb[4], R[4];
+			double uv[4], vv[4], eu[4], ev[4], ya[4], yb[4], g[4];
 			ld4(U + (size_t) c * 4, uv);
 			ld4(V + (size_t) c * 4, vv);
-			dpsMat(sP[0], uv, ya);
-			dpsMat(sP[1], vv, yb);
-			for (int k = 0; k < 4; ++k) R[k] = ya[k] + yb[k];
+			sumScale += expNorm(uv, eu) + expNorm(vv, ev);
+			matVec4(sP[0], eu, ya);
+			matVec4(sP[1], ev, yb);
+			for (int k = 0; k < 4; ++k) g[k] = ya[k] * yb[k];
 			if (store) {
-				reinterpret_cast<double2*>(sR + (size_t) c * 4)[0] = make_double2(R[0], R[1]);
-				reinterpret_cast<double2*>(sR + (size_t) c * 4)[1] = make_double2(R[2], R[3]);
+				reinterpret_cast<double2*>(sR + (size_t) c * 4)[0] = make_double2(g[0], g[1]);
+				reinterpret_cast<double2*>(sR + (size_t) c * 4)[1] = make_double2(g[2], g[3]);
 			}
 			const int b = x[start + c];
-			diff += argmax4(R) != (b >= 0 ? b : piMax);
+			diff += argmax4(g) != (b >= 0 ? b : piMax);
 		}
 		diff = blockSum(diff, redI);
 		const double wnr = (double) diff / (double) W;
-		// ---- N * P(wnr): depends on the read's base only ----
+		// ---- P(wnr) applied to the read's leaf vector: depends on the base only ----
 		if (tid == 0) modelPr(m, wnr, sP[2]);
 		__syncthreads();
 		if (tid < 5) {
 			double n[4], y[4];
-			leafMsg(m, tid < 4 ? tid : -1, n);
-			dpsMat(sP[2], n, y);
+			leafLin(m, tid < 4 ? tid : -1, n);
+			matVec4(sP[2], n, y);
 			for (int k = 0; k < 4; ++k) sNp[tid][k] = y[k];
 		}
 		__syncthreads();
-		// ---- pass 2: treeLoglik(pi, UPr + VPr + NPr) (cpp:872-874) ----
+		// ---- pass 2: treeLoglik(pi, UPr + VPr + NPr) (cpp:872-874) = sum_j log(pi . (g_j * n_j)) + scales ----
 		double ll = 0;
 		for (int c = tid; c < W; c += HU_EST_THREADS) {
-			double R[4];
+			double g[4];
 			if (store) {
 				const double2 p0 = reinterpret_cast<const double2*>(sR + (size_t) c * 4)[0];
 				const double2 p1 = reinterpret_cast<const double2*>(sR + (size_t) c * 4)[1];
-				R[0] = p0.x; R[1] = p0.y; R[2] = p1.x; R[3] = p1.y;
+				g[0] = p0.x; g[1] = p0.y; g[2] = p1.x; g[3] = p1.y;
 			} else {
-				double uv[4], vv[4], ya[4], yb[4];
+				double uv[4], vv[4], eu[4], ev[4], ya[4], yb[4];
 				ld4(U + (size_t) c * 4, uv);
 				ld4(V + (size_t) c * 4, vv);
-				dpsMat(sP[0], uv, ya);
-				dpsMat(sP[1], vv, yb);
-				for (int k = 0; k < 4; ++k) R[k] = ya[k] + yb[k];
+				expNorm(uv, eu);
+				expNorm(vv, ev);
+				matVec4(sP[0], eu, ya);
+				matVec4(sP[1], ev, yb);
+				for (int k = 0; k < 4; ++k) g[k] = ya[k] * yb[k];
 			}
 			const int b = x[start + c];
 			const double* np = sNp[b >= 0 ? b : 4];
 			double z[4];
-			for (int k = 0; k < 4; ++k) z[k] = R[k] + np[k];
-			ll += dpsVec(m.pi, z);
+			for (int k = 0; k < 4; ++k) z[k] = g[k] * np[k];
+			ll += log(dotPi(m, z));
 		}
-		ll = blockSum(ll, redD);
+		ll = blockSum(ll + sumScale, redD);
 		if (tid == 0) {
 			hu_place_row row;
 			row.start = start; row.end = end;
@@ -188,7 +193,7 @@ int launchEstimate(hu_batch* b, const hu_sep_params* p) {
 	int sms = 0;
 	HU_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, db->device));
 	HU_CUDA(cudaMemsetAsync(b->workCount, 0, 4 * sizeof(int), b->stream));
-	const int grid = std::min(sms * 3, b->nReads * p->maxNSeed);
+	const int grid = std::min(sms * 4, b->nReads * p->maxNSeed);
 	estimateKernel<<<grid, HU_EST_THREADS, smem, b->stream>>>(a, db->tree, db->model);
 	filterKernel<<<(b->nReads + 127) / 128, 128, 0, b->stream>>>(b->nReads, b->winStart, a.nSeeds, b->est, p->maxError, b->order, b->nKept);
 	HU_CUDA(cudaEventRecord(b->ev[5], b->stream));

@@ -134,6 +134,32 @@ HU_HD void leafMsg(const Model& m, int b, double* Y) {
 		for (int k = 0; k < 4; ++k) Y[k] = m.logPi[k];
 }
 
+// ---- linear-domain forms used by the estimate / place kernels ----
+// A message column V (log domain) enters every SEP formula only as exp(V + s): dot_product_scaled(P, V)_i =
+// log(sum_k P_ik e^{V_k+s}) - s.  With s = -max(V) (any s gives the same value up to rounding; the reference
+// uses s = 0 unless max(V) < -510) the 4-vector e = exp(V - max V) and the scalar max V carry everything:
+//   exp(dps(P, V)_i) = e^{max V} * (P e)_i.
+// The kernels therefore do their products and sums on e and P e and take one log per column where a
+// log-likelihood is needed, instead of the exp/log round trip per matrix row of the literal code.
+HU_HD double expNorm(const double* V, double* e) {
+	double mx = max4(V);
+	if (mx == -INFINITY) mx = 0.0;
+	for (int k = 0; k < 4; ++k) e[k] = exp(V[k] - mx);
+	return mx;
+}
+HU_HD void matVec4(const double* P, const double* e, double* y) {
+	for (int i = 0; i < 4; ++i) y[i] = (P[i * 4] * e[0] + P[i * 4 + 1] * e[1]) + (P[i * 4 + 2] * e[2] + P[i * 4 + 3] * e[3]);
+}
+// exp of the leaf message of a base code: one-hot, or pi for a gap
+HU_HD void leafLin(const Model& m, int b, double* y) {
+	if (b >= 0) {
+		y[0] = y[1] = y[2] = y[3] = 0.0;
+		y[b] = 1.0;
+	} else
+		for (int k = 0; k < 4; ++k) y[k] = m.pi[k];
+}
+HU_HD double dotPi(const Model& m, const double* g) { return (m.pi[0] * g[0] + m.pi[2] * g[2]) + (m.pi[1] * g[1] + m.pi[3] * g[3]); }
+
 // row_mean_exp_scaled (src/PhyloTreeUnrooted.h:1521-1529) over KK category columns held in mat[k][4]
 HU_HD void rmes(const double (*mat)[4], int KK, double* Y) {
 	for (int i = 0; i < 4; ++i) {

@@ -3,17 +3,21 @@
 // Felsenstein's single-branch EM (cpp:749-798) and the dGamma-mixed message rebuilds (cpp:320-346),
 // then calcQValues + the final sort (src/HmmUFOtu_main.cpp:182-216, src/hmmufotu.cpp:725-733).
 //
-// One warp per (read, placement), persistent over the item space.  The message windows U, V are streamed
-// from HBM/L2 once per rebuild with 128-bit loads; inside one EM call the per-column terms do not change
-// between iterations (the reference recomputes them every iteration), so they are computed once per call
-// and kept on chip as rho_j = e^{A_j-s_j} / e^{B_j-s_j}: an iteration is then W fused multiply-adds, W
-// divisions and one warp reduction.
+// One warp per (read, placement), persistent over the item space.  Everything is done in the linear domain
+// (hu_internal.cuh, expNorm): with e^U_j, e^V_j the max-normalised exponentials of the two stored messages,
+//   msg(r->n)_j ~ mean_k (P(lu r_k) e^U_j) * (P(lv r_k) e^V_j)           (the per-column scales cancel below)
+//   rho_j = e^{A_j - B_j} = pi.(msg * n_j) / ((pi.msg) (pi.n_j))          A, B of cpp:769-770
+// so a message rebuild costs 8 exp + a few dozen FMAs per column and no log, and since rho_j does not change
+// inside one EM call (the reference recomputes A_j, B_j every iteration) an EM iteration is one fused
+// multiply-add and one reciprocal per column plus a warp reduction:  p <- mean_j p0 / (rho_j q0 + p0).
+// Same iterates, same stopping rules, same caps as the reference; the values differ from it only by rounding
+// (checked to 1e-9 relative against the oracle in tests/test_gpu_parity.py).
 #include "hu_batch.cuh"
 
 namespace hu {
 
 #define HU_PLACE_WARPS 4
-#define HU_PLACE_CAPW 2048 // columns of rho kept in shared memory per warp (16 KB); wider windows use a global slab
+#define HU_PLACE_CAPW 1536 // columns of rho kept in shared memory per warp (12 KB); wider windows use a global slab
 #define HU_BRANCH_EPS 1e-5 // src/PhyloTreeUnrooted.cpp:70
 #define HU_MAX_ITER 100    // src/PhyloTreeUnrooted.cpp:71
 
@@ -33,8 +37,7 @@ struct PlaceArgs {
 
 struct WarpShared {
 	double P[3][HU_MAX_DG][16]; // P(lu r_k), P(lv r_k), P(ln r_k)
-	double NP[HU_MAX_DG][5][4]; // dot_product_scaled(P(ln r_k), leaf message of base b / gap)
-	double piN[5];              // dot_product_scaled(pi, leaf message)
+	double NP[HU_MAX_DG][5][4]; // P(ln r_k) applied to the leaf vector of base b / gap (linear)
 };
 
 __device__ __forceinline__ double warpSum(double v) {
@@ -42,23 +45,41 @@ __device__ __forceinline__ double warpSum(double v) {
 	return v;
 }
 
+// 1/x for x >= ~1e-30: single-precision seed + two Newton steps (relative error < 1e-15), no branches
+__device__ __forceinline__ double rcpFast(double x) {
+	double r = (double) __frcp_rn((float) x);
+	r = fma(r, fma(-x, r, 1.0), r);
+	r = fma(r, fma(-x, r, 1.0), r);
+	return r;
+}
+
 // Felsenstein EM for one branch given rho_j (NaN = column skipped), src/PhyloTreeUnrooted.cpp:749-798
-__device__ double emBranch(const double* __restrict__ rho, int W, int nValid, double wInit, double cap) {
+__device__ double emBranch(const double* __restrict__ rho, int W, int nValid, double wInit, double cap, int* itersOut) {
 	const int lane = threadIdx.x & 31;
 	double q0 = exp(-wInit), p0 = 1 - q0;
 	double p = p0, q = q0;
-	for (int it = 0; it < HU_MAX_ITER && p >= 0 && p <= 1; ++it) {
+	int it = 0;
+	for (it = 0; it < HU_MAX_ITER && p >= 0 && p <= 1; ++it) {
 		double s = 0;
-		// e^B p0 / (e^A q0 + e^B p0) = p0 / (rho q0 + p0)
-		for (int c = lane; c < W; c += 32) {
-			const double rh = rho[c];
-			if (rh == rh) s += p0 / (rh * q0 + p0);
+		if (p0 > 1e-30 && q0 >= 0) { // e^B p0 / (e^A q0 + e^B p0) = p0 / (rho q0 + p0)
+			for (int c = lane; c < W; c += 32) {
+				const double rh = rho[c];
+				const double x = fma(rh, q0, p0);
+				const double term = x < 1e300 ? p0 * rcpFast(x) : 0.0;
+				if (rh == rh) s += term;
+			}
+		} else {
+			for (int c = lane; c < W; c += 32) {
+				const double rh = rho[c];
+				if (rh == rh) s += p0 / (rh * q0 + p0);
+			}
 		}
 		p = warpSum(s) / (double) nValid;
 		q = 1 - p;
-		if (fabs(log(q) - log(q0)) < HU_BRANCH_EPS) break;
+		if (fabs(log(q) - log(q0)) < HU_BRANCH_EPS) { it++; break; }
 		p0 = p; q0 = q;
 	}
+	*itersOut += it;
 	double w = -log(q);
 	if (w > cap) w = cap;
 	return w;
@@ -72,6 +93,8 @@ __global__ void __launch_bounds__(HU_PLACE_WARPS * 32) placeKernel(PlaceArgs a, 
 	const int slot = blockIdx.x * HU_PLACE_WARPS + warp;
 	const int total = a.nReads * a.maxNSeed;
 	const int KK = m.dgK > 0 ? m.dgK : 1;
+	double piSq = 0; // pi . pi: (pi . n) for a gap column of the read
+	for (int k = 0; k < 4; ++k) piSq += m.pi[k] * m.pi[k];
 	for (;;) {
 		int item = 0;
 		if (lane == 0) item = atomicAdd(a.cursor, 1);
@@ -88,16 +111,10 @@ __global__ void __launch_bounds__(HU_PLACE_WARPS * 32) placeKernel(PlaceArgs a, 
 		const int8_t* x = a.aligned + (size_t) r * t.csLen + start;
 		double* rho = W <= a.capW ? rhoS : a.slab + (size_t) slot * t.csLen;
 		double lu = w0 * e.ratio, lv = w0 * (1 - e.ratio), ln = e.wnr; // cpp:906-912
-		__syncwarp();
-		if (lane < 5) {
-			double n[4];
-			leafMsg(m, lane < 4 ? lane : -1, n);
-			ws->piN[lane] = dpsVec(m.pi, n);
-		}
 		double wur0 = lu, wvr0 = lv, wnr0 = ln;
 		const double w0j = wur0 + wvr0;
 		double wur = wur0, wvr = wvr0, wnr = wnr0;
-		int iter = 0;
+		int iter = 0, emIters = 0;
 		for (iter = 0; iter < HU_MAX_ITER && 0 <= wur && wur <= w0j; ++iter) {
 			// ---- msg(r->n) from u and v, then optimise the n-r branch (cap 1) ----
 			__syncwarp();
@@ -106,33 +123,27 @@ __global__ void __launch_bounds__(HU_PLACE_WARPS * 32) placeKernel(PlaceArgs a, 
 			__syncwarp();
 			int nValid = 0;
 			for (int cI = lane; cI < W; cI += 32) {
-				double uv[4], vv[4], ya[4], yb[4], mat[HU_MAX_DG][4], rn[4];
+				double uv[4], vv[4], eu[4], ev[4], ya[4], yb[4], g[4] = {0, 0, 0, 0};
 				ld4(U + (size_t) cI * 4, uv);
 				ld4(V + (size_t) cI * 4, vv);
+				expNorm(uv, eu);
+				expNorm(vv, ev);
 				for (int k = 0; k < KK; ++k) {
-					dpsMat(ws->P[0][k], uv, ya);
-					dpsMat(ws->P[1][k], vv, yb);
-					for (int i = 0; i < 4; ++i) mat[k][i] = ya[i] + yb[i];
+					matVec4(ws->P[0][k], eu, ya);
+					matVec4(ws->P[1][k], ev, yb);
+					for (int i = 0; i < 4; ++i) g[i] += ya[i] * yb[i];
 				}
-				if (m.dgK) rmes(mat, KK, rn);
-				else for (int i = 0; i < 4; ++i) rn[i] = mat[0][i];
 				const int b = x[cI];
-				double nm[4], z[4];
-				leafMsg(m, b, nm);
-				for (int i = 0; i < 4; ++i) z[i] = rn[i] + nm[i];
-				const double logA = dpsVec(m.pi, z);
-				const double logB = dpsVec(m.pi, rn) + ws->piN[b >= 0 ? b : 4];
-				double rh = NAN;
-				if (!(isnan(logA) || isnan(logB))) {
-					const double sc = fmax(logA, logB);
-					rh = exp(logA - sc) / exp(logB - sc);
-					nValid++;
-				}
+				// A = log pi.(g n), B = log pi.g + log pi.n; the 1/K of the rate mixture cancels
+				const double num = b >= 0 ? m.pi[b] * g[b] : ((m.pi[0] * m.pi[0] * g[0] + m.pi[2] * m.pi[2] * g[2]) + (m.pi[1] * m.pi[1] * g[1] + m.pi[3] * m.pi[3] * g[3]));
+				const double den = dotPi(m, g) * (b >= 0 ? m.pi[b] : piSq);
+				const double rh = num / den;
+				nValid += rh == rh;
 				rho[cI] = rh;
 			}
 			for (int o = 16; o > 0; o >>= 1) nValid += __shfl_xor_sync(0xffffffffu, nValid, o);
 			__syncwarp();
-			wnr = emBranch(rho, W, nValid, ln, 1.0);
+			wnr = emBranch(rho, W, nValid, ln, 1.0, &emIters);
 			ln = wnr;
 			// ---- msg(r->u) from v and n, then optimise the u-r branch (cap w0) ----
 			__syncwarp();
@@ -141,39 +152,33 @@ __global__ void __launch_bounds__(HU_PLACE_WARPS * 32) placeKernel(PlaceArgs a, 
 			for (int q = lane; q < KK * 5; q += 32) {
 				const int k = q / 5, b = q % 5;
 				double n[4], y[4];
-				leafMsg(m, b < 4 ? b : -1, n);
-				dpsMat(ws->P[2][k], n, y);
+				leafLin(m, b < 4 ? b : -1, n);
+				matVec4(ws->P[2][k], n, y);
 				for (int i = 0; i < 4; ++i) ws->NP[k][b][i] = y[i];
 			}
 			__syncwarp();
 			nValid = 0;
 			for (int cI = lane; cI < W; cI += 32) {
-				double uv[4], vv[4], yb[4], mat[HU_MAX_DG][4], ru[4];
+				double uv[4], vv[4], eu[4], ev[4], yb[4], g[4] = {0, 0, 0, 0};
 				ld4(U + (size_t) cI * 4, uv);
 				ld4(V + (size_t) cI * 4, vv);
+				expNorm(uv, eu);
+				expNorm(vv, ev);
 				const int b = x[cI];
 				for (int k = 0; k < KK; ++k) {
-					dpsMat(ws->P[1][k], vv, yb);
+					matVec4(ws->P[1][k], ev, yb);
 					const double* np = ws->NP[k][b >= 0 ? b : 4];
-					for (int i = 0; i < 4; ++i) mat[k][i] = yb[i] + np[i];
+					for (int i = 0; i < 4; ++i) g[i] += yb[i] * np[i];
 				}
-				if (m.dgK) rmes(mat, KK, ru);
-				else for (int i = 0; i < 4; ++i) ru[i] = mat[0][i];
 				double z[4];
-				for (int i = 0; i < 4; ++i) z[i] = ru[i] + uv[i];
-				const double logA = dpsVec(m.pi, z);
-				const double logB = dpsVec(m.pi, ru) + dpsVec(m.pi, uv);
-				double rh = NAN;
-				if (!(isnan(logA) || isnan(logB))) {
-					const double sc = fmax(logA, logB);
-					rh = exp(logA - sc) / exp(logB - sc);
-					nValid++;
-				}
+				for (int i = 0; i < 4; ++i) z[i] = g[i] * eu[i];
+				const double rh = dotPi(m, z) / (dotPi(m, g) * dotPi(m, eu));
+				nValid += rh == rh;
 				rho[cI] = rh;
 			}
 			for (int o = 16; o > 0; o >>= 1) nValid += __shfl_xor_sync(0xffffffffu, nValid, o);
 			__syncwarp();
-			wur = emBranch(rho, W, nValid, lu, w0j);
+			wur = emBranch(rho, W, nValid, lu, w0j, &emIters);
 			lu = wur;
 			wvr = w0j - wur;
 			lv = wvr; // msg(r->v) is rebuilt by the reference but never read afterwards
@@ -192,26 +197,25 @@ __global__ void __launch_bounds__(HU_PLACE_WARPS * 32) placeKernel(PlaceArgs a, 
 		for (int q = lane; q < KK * 5; q += 32) {
 			const int k = q / 5, b = q % 5;
 			double n[4], y[4];
-			leafMsg(m, b < 4 ? b : -1, n);
-			dpsMat(ws->P[2][k], n, y);
+			leafLin(m, b < 4 ? b : -1, n);
+			matVec4(ws->P[2][k], n, y);
 			for (int i = 0; i < 4; ++i) ws->NP[k][b][i] = y[i];
 		}
 		__syncwarp();
 		double tl = 0;
 		for (int cI = lane; cI < W; cI += 32) {
-			double uv[4], vv[4], ya[4], yb[4], mat[HU_MAX_DG][4], root[4];
+			double uv[4], vv[4], eu[4], ev[4], ya[4], yb[4], g[4] = {0, 0, 0, 0};
 			ld4(U + (size_t) cI * 4, uv);
 			ld4(V + (size_t) cI * 4, vv);
+			const double sc = expNorm(uv, eu) + expNorm(vv, ev);
 			const int b = x[cI];
 			for (int k = 0; k < KK; ++k) {
-				dpsMat(ws->P[0][k], uv, ya);
-				dpsMat(ws->P[1][k], vv, yb);
+				matVec4(ws->P[0][k], eu, ya);
+				matVec4(ws->P[1][k], ev, yb);
 				const double* np = ws->NP[k][b >= 0 ? b : 4];
-				for (int i = 0; i < 4; ++i) mat[k][i] = (ya[i] + yb[i]) + np[i];
+				for (int i = 0; i < 4; ++i) g[i] += (ya[i] * yb[i]) * np[i];
 			}
-			if (m.dgK) rmes(mat, KK, root);
-			else for (int i = 0; i < 4; ++i) root[i] = mat[0][i];
-			tl += dpsVec(m.pi, root);
+			tl += log(dotPi(m, g) / (double) KK) + sc;
 		}
 		tl = warpSum(tl);
 		if (lane == 0) {
@@ -229,6 +233,7 @@ __global__ void __launch_bounds__(HU_PLACE_WARPS * 32) placeKernel(PlaceArgs a, 
 			row.aNode = (row.ratio <= 0.5 || t.height[pN] > a.maxHeight) ? c : pN;
 			row.taxon = t.taxon[row.aNode];
 			row.outerIters = iter;
+			row.nPlaces = emIters; // diagnostic until finalizeKernel overwrites it with the placement count
 			a.places[(size_t) r * HU_MAX_SEED + idx] = row;
 		}
 	}
