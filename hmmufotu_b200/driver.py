@@ -1,0 +1,65 @@
+"""Read-sharding driver: the database is replicated on every GPU, reads are split into contiguous blocks in
+file order (so concatenating the ranks' rows reproduces the order the single-threaded reference writes,
+/root/reference/src/hmmufotu.cpp:603-751), and the only collective is the gather of fixed-size assignment
+rows to rank 0.  One process per GPU; `torch.distributed` (NCCL on GPUs, gloo in the CPU tests) is plumbing.
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional, Tuple
+
+import numpy as np
+
+ROW_DT = np.dtype([("read", "<i8"), ("seqStart", "<i4"), ("seqEnd", "<i4"), ("hmmStart", "<i4"), ("hmmEnd", "<i4"),
+                   ("csStart", "<i4"), ("csEnd", "<i4"), ("flags", "<i4"), ("nPlaces", "<i4"), ("cost", "<f8"),
+                   ("cNode", "<i4"), ("pNode", "<i4"), ("aNode", "<i4"), ("taxon", "<i4"), ("ratio", "<f8"),
+                   ("annoDist", "<f8"), ("loglik", "<f8"), ("qPlace", "<f8"), ("qTaxon", "<f8")])
+
+
+def shard_bounds(n_reads: int, world: int, rank: int) -> Tuple[int, int]:
+    """Contiguous block [lo, hi) of rank `rank`; block sizes differ by at most one, earlier ranks get the extra."""
+    base, extra = divmod(n_reads, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def pack_rows(read0: int, align_rows: np.ndarray, best_rows: np.ndarray) -> np.ndarray:
+    """Fixed-size POD rows (one per read) from the device results of one shard."""
+    out = np.zeros(align_rows.shape[0], dtype=ROW_DT)
+    out["read"] = read0 + np.arange(align_rows.shape[0])
+    for f in ("seqStart", "seqEnd", "hmmStart", "hmmEnd", "csStart", "csEnd", "flags", "cost"):
+        out[f] = align_rows[f]
+    for f in ("nPlaces", "cNode", "pNode", "aNode", "taxon", "ratio", "annoDist", "loglik", "qPlace", "qTaxon"):
+        out[f] = best_rows[f]
+    return out
+
+
+def gather_rows(rows: np.ndarray, n_total: int, world: int, rank: int, device: Optional[str] = None) -> Optional[np.ndarray]:
+    """Gather every rank's rows on rank 0 in read order.  Equal-size padded blocks -> one all_gather."""
+    if world == 1:
+        return rows
+    import torch
+    import torch.distributed as dist
+    per = -(-n_total // world)
+    buf = np.zeros(per, dtype=ROW_DT)
+    buf[:rows.shape[0]] = rows
+    t = torch.from_numpy(buf.view(np.uint8).copy())
+    if device is not None:
+        t = t.to(device)
+    parts = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(parts, t)
+    if rank != 0:
+        return None
+    out = []
+    for r, p in enumerate(parts):
+        lo, hi = shard_bounds(n_total, world, r)
+        out.append(p.cpu().numpy().view(ROW_DT)[:hi - lo])
+    return np.concatenate(out)
+
+
+def assign_reads(reads, process_shard: Callable, world: int = 1, rank: int = 0, device: Optional[str] = None):
+    """Split `reads` over ranks, run `process_shard(sub_reads) -> (align_rows, best_rows)` on this rank's block
+    and gather the rows on rank 0 (None elsewhere)."""
+    lo, hi = shard_bounds(reads.n, world, rank)
+    sub = reads.slice(lo, hi)
+    a, b = process_shard(sub)
+    return gather_rows(pack_rows(lo, a, b), reads.n, world, rank, device)

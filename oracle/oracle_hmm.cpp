@@ -150,7 +150,9 @@ int Hmm::loadText(const std::string& path) { /* src/BandedHMMP7.cpp:100-246 */
 		}
 		std::istringstream iss(line);
 		std::string tag, tmp;
-		if (!line.empty() && !isspace((unsigned char) line[0])) {
+		/* literal: `!isspace(line[0])` also holds for an empty line (line[0] == '\0'), i.e. the line
+		 * remainder left behind by the `in >>` reads of a transition row is a header line with an empty tag */
+		if (line.empty() || !isspace((unsigned char) line[0])) {
 			iss >> tag;
 			if (tag.substr(0, 6) == "HMMER3") {
 				if (tag.length() < 8 || tag[7] < 'f') return -2;
@@ -170,7 +172,7 @@ int Hmm::loadText(const std::string& path) { /* src/BandedHMMP7.cpp:100-246 */
 				std::string val; std::getline(iss, val);
 				size_t b = val.find_first_not_of(" \t");
 				size_t e = val.find_last_not_of(" \t");
-				optTags[tag] = b == std::string::npos ? "" : val.substr(b, e - b + 1);
+				if (!tag.empty()) optTags[tag] = b == std::string::npos ? "" : val.substr(b, e - b + 1);
 			}
 		} else {
 			iss >> tag;
