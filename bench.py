@@ -264,6 +264,9 @@ def main():
         if i + 1 < args.steps:
             e2e_step(i + 1)
         rows, traces, best = e2e_collect(i)
+        if world > 1:  # the one collective of the path: fixed-size assignment rows to rank 0 (NCCL)
+            from hmmufotu_b200 import driver
+            driver.gather_rows(driver.pack_rows(rank * B, rows, best), world * B, world, rank, device="cuda")
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_value = world * B * args.steps / e2e_s
