@@ -167,8 +167,13 @@ int hu_batch_create(hu_batch** out, hu_db* db, int32_t maxReads, int32_t maxSeqL
 	HU_TRY(balloc(b, &b->winStart, (size_t) maxReads));
 	HU_TRY(balloc(b, &b->winEnd, (size_t) maxReads));
 	const int nReadsPad = (maxReads + HU_SCAN_READS - 1) / HU_SCAN_READS * HU_SCAN_READS;
-	HU_TRY(balloc(b, &b->seed.rplanes, (size_t) t.nWords * nReadsPad * 4));
+	HU_TRY(balloc(b, &b->seed.rplanes, (size_t) t.nPWords * nReadsPad * 4));
 	HU_TRY(balloc(b, &b->seed.rValid, (size_t) nReadsPad));
+	HU_TRY(balloc(b, &b->seed.rWordLo, (size_t) nReadsPad));
+	HU_TRY(balloc(b, &b->seed.rWordHi, (size_t) nReadsPad));
+	HU_TRY(balloc(b, &b->seed.nSparse, (size_t) nReadsPad));
+	b->seed.sparseCap = maxSeqLen * (paired ? 2 : 1); // a read cannot have more bases in non-match columns than bases
+	HU_TRY(balloc(b, &b->seed.sparse, (size_t) maxReads * b->seed.sparseCap));
 	HU_TRY(balloc(b, &b->seed.keys, (size_t) maxReads * t.scanPitch));
 	HU_TRY(balloc(b, &b->seed.seedIds, (size_t) maxReads * HU_MAX_SEED));
 	HU_TRY(balloc(b, &b->seed.nSeeds, (size_t) maxReads));

@@ -45,10 +45,15 @@ struct SeedArgs {
 	const int8_t* aligned;  // [nReads][L]
 	const int* winStart;    // 0-based inclusive window per read; winStart < 0: read is not placed
 	const int* winEnd;
-	uint32_t* rplanes;      // [nWords][nReadsPad][4]: hi, lo, valid, 0
+	uint32_t* rplanes;      // [nPWords][nReadsPad][4]: hi, lo, valid, 0 (profile coordinates)
 	int nReadsPad;
 	int* rValid;            // popcount of the valid plane per read
-	unsigned long long* keys; // [nReads][scanPitch]: (floor(d * 2^31 / N) << 32) | node id
+	int* rWordLo;           // first / last profile word with a read base
+	int* rWordHi;
+	int* nSparse;           // read bases in non-match columns: count and (column << 8 | base) list
+	uint32_t* sparse;
+	int sparseCap;
+	uint32_t* keys;         // [nReads][scanPitch]: floor(d * 2^31 / N), 0xFFFFFFFF = excluded
 	int* seedIds;           // [nReads][HU_MAX_SEED]
 	int* nSeeds;            // [nReads]
 };

@@ -194,19 +194,20 @@ __global__ void inferSeqKernel(int nNodes, int csLen, int root, const int* __res
 	seq[(size_t) x * csLen + j] = (int8_t) argmax4(v);
 }
 
-// node sequences -> bit planes [word][plane][slot] (hi, lo, valid)
-__global__ void packPlanesKernel(const int8_t* __restrict__ seq, int csLen, int nWords, const int* __restrict__ scanNode,
-		int nScan, int scanPitch, uint32_t* __restrict__ planes) {
+// node sequences -> bit planes over the match columns, [word][plane][slot] (hi, lo, valid)
+__global__ void packPlanesKernel(const int8_t* __restrict__ seq, int csLen, int K, const int* __restrict__ p2cs,
+		const int* __restrict__ scanNode, int nScan, int scanPitch, uint32_t* __restrict__ planes) {
 	const int slot = blockIdx.x * blockDim.x + threadIdx.x;
 	const int w = blockIdx.y;
 	if (slot >= scanPitch) return;
 	uint32_t hi = 0, lo = 0, va = 0;
 	const int node = slot < nScan ? scanNode[slot] : -1;
 	if (node >= 0) {
-		const int8_t* s = seq + (size_t) node * csLen + w * 32;
-		const int n = min(32, csLen - w * 32);
-		for (int b = 0; b < n; ++b) {
-			const int c = s[b];
+		const int8_t* s = seq + (size_t) node * csLen;
+		for (int b = 0; b < 32; ++b) {
+			const int k = w * 32 + b + 1;
+			if (k > K) break;
+			const int c = s[p2cs[k] - 1];
 			if (c >= 0) {
 				va |= 1u << b;
 				hi |= (uint32_t) ((c >> 1) & 1) << b;
@@ -217,6 +218,23 @@ __global__ void packPlanesKernel(const int8_t* __restrict__ seq, int csLen, int 
 	planes[((size_t) w * 3 + 0) * scanPitch + slot] = hi;
 	planes[((size_t) w * 3 + 1) * scanPitch + slot] = lo;
 	planes[((size_t) w * 3 + 2) * scanPitch + slot] = va;
+}
+
+// seq[node][col] -> seqT[col][slot] (32 x 32 tiles through shared memory)
+__global__ void transposeSeqKernel(const int8_t* __restrict__ seq, int csLen, const int* __restrict__ scanNode, int scanPitch,
+		int8_t* __restrict__ seqT) {
+	__shared__ int8_t tile[32][33];
+	const int slot0 = blockIdx.x * 32, col0 = blockIdx.y * 32;
+	for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+		const int slot = slot0 + r, col = col0 + threadIdx.x;
+		const int node = slot < scanPitch ? scanNode[slot] : -1;
+		tile[r][threadIdx.x] = (node >= 0 && col < csLen) ? seq[(size_t) node * csLen + col] : (int8_t) -2;
+	}
+	__syncthreads();
+	for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+		const int col = col0 + r, slot = slot0 + threadIdx.x;
+		if (col < csLen && slot < scanPitch) seqT[(size_t) col * scanPitch + slot] = tile[threadIdx.x][r];
+	}
 }
 
 template <typename T>
@@ -373,8 +391,8 @@ static int createImpl(hu_db* db, const hu_hmm_params* hp, const hu_tree_desc* td
 	for (int x = 0; x < n; ++x) {
 		if (x == td->root) continue;
 		const int8_t* s = hs + (size_t) x * csLen;
-		bool gap = false;
-		for (int j = 0; j < csLen && !gap; ++j) gap = s[j] < 0;
+		bool gap = false; // a gap in any MATCH column: the node needs the valid plane
+		for (int k = 1; k <= K && !gap; ++k) gap = s[hp->p2cs[k] - 1] < 0;
 		(gap ? gapNodes : fullNodes).push_back(x);
 	}
 	// gap block padded to a multiple of the scan tile so that every tile is homogeneous
@@ -390,14 +408,24 @@ static int createImpl(hu_db* db, const hu_hmm_params* hp, const hu_tree_desc* td
 	// padding slots (inside the gap block and at the tail) carry node -1 and all-zero planes
 	HU_TRY(upload(db, &t.scanNode, scanNode.data(), scanNode.size()));
 	uint32_t* planes;
-	HU_TRY(devAlloc(db, &planes, (size_t) t.nWords * 3 * t.scanPitch));
-	HU_CUDA(cudaMemset(planes, 0, (size_t) t.nWords * 3 * t.scanPitch * sizeof(uint32_t)));
+	t.nPWords = (K + 31) / 32;
+	HU_TRY(devAlloc(db, &planes, (size_t) t.nPWords * 3 * t.scanPitch));
+	int8_t* seqT;
+	HU_TRY(devAlloc(db, &seqT, (size_t) csLen * t.scanPitch));
+	std::vector<int> colK(csLen, 0);
+	for (int k = 1; k <= K; ++k) {
+		if (hp->p2cs[k] < 1 || hp->p2cs[k] > csLen) { setError("profile2CSIdx[%d] = %d outside 1..%d", k, hp->p2cs[k], csLen); return HU_ERR_ARG; }
+		colK[hp->p2cs[k] - 1] = k;
+	}
+	HU_TRY(upload(db, &t.colK, colK.data(), colK.size()));
 	{
-		packPlanesKernel<<<dim3((t.scanPitch + 127) / 128, t.nWords), 128>>>(seq, csLen, t.nWords, t.scanNode, t.nScan, t.scanPitch, planes);
+		packPlanesKernel<<<dim3((t.scanPitch + 127) / 128, t.nPWords), 128>>>(seq, csLen, K, db->hmm.p2cs, t.scanNode, t.nScan, t.scanPitch, planes);
+		transposeSeqKernel<<<dim3(t.scanPitch / 32, (csLen + 31) / 32), dim3(32, 8)>>>(seq, csLen, t.scanNode, t.scanPitch, seqT);
 		HU_CUDA(cudaGetLastError());
 		HU_CUDA(cudaDeviceSynchronize());
 	}
 	t.planes = planes;
+	t.seqT = seqT;
 	return HU_OK;
 }
 

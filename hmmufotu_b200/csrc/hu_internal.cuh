@@ -206,8 +206,12 @@ struct TreeDev {
 	const int* taxon;
 	const double* up;        // [nNodes][csLen][4]
 	const double* dn;
-	// bit planes for the seed scan: [word][plane][nodeSlot], nodeSlot = position in scanOrder
+	// seed scan, in PROFILE coordinates: bit (k-1)%32 of word (k-1)/32 is match column p2cs[k] (k = 1..K);
+	// [word][plane][nodeSlot], planes hi, lo, valid; nodeSlot = position in the scan order
 	const uint32_t* planes;
+	int nPWords;             // ceil(K / 32)
+	const int8_t* seqT;      // [csLen][scanPitch]: node codes transposed into slot order (non-match columns are read)
+	const int* colK;         // [csLen]: profile position of a match column, 0 otherwise
 	int nScan;               // number of scan slots (non-root nodes), padded to scanPitch
 	int scanPitch;
 	const int* scanNode;     // slot -> node id

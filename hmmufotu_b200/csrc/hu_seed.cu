@@ -2,45 +2,81 @@
 // every non-root node (src/HmmUFOtu_main.cpp:127-152, src/SeqUtils.cpp:37-54) and keeps the maxNSeed
 // closest (src/hmmufotu.cpp:646-647).
 //
-// Node sequences are held as three bit planes (hi, lo, valid) of 32 consensus columns per word, slots
-// contiguous per (word, plane), so a CTA streams a 512-slot tile with coalesced 128-bit loads and compares
-// it against 8 reads of the batch kept in shared memory: d = popc(((nh^rh)|(nl^rl)) & nv & rv),
-// N = popc(nv & rv).  Ungapped (inferred, internal-node) sequences skip the valid plane.  The result per
-// (read, node) is the exact order-preserving integer key floor(d*2^31/N) (distinct rationals with
-// denominators < 2^13 differ by more than 2^-26, so the key orders exactly like the reference's doubles),
-// packed with the node id, and a per-read radix select returns the maxNSeed smallest in (dist, id) order.
+// d and N are sums over consensus columns, so the columns are split exactly into
+//   * the K match columns of the profile: an aligned read has nearly all of its bases there.  Node and read
+//     sequences are held as three bit planes (hi, lo, valid) over PROFILE positions, 32 per word, node slots
+//     contiguous per (word, plane): a CTA streams a 512-slot tile with coalesced 128-bit loads against 8 reads
+//     kept in shared memory, d += popc(((nh^rh)|(nl^rl)) & nv & rv), N += popc(nv & rv).  A 250-base read spans
+//     ~9 words instead of the ~43 words its 1 400 consensus columns would take.  Ungapped (inferred,
+//     internal-node) sequences skip the valid plane.
+//   * the non-match columns, where a read only has the few insert bases buildGlobalAlign could place: these are
+//     listed per read and added from a slot-major transposed copy of the node sequences in the scan epilogue.
+// The result per (read, node) is the exact order-preserving integer key floor(d*2^31/N) (distinct rationals
+// with denominators < 2^13 differ by more than 2^-26, so keys order exactly like the reference's doubles);
+// a per-read radix select over (key, node id) returns the maxNSeed smallest in (dist, id) order.
 #include "hu_batch.cuh"
 
 namespace hu {
 
-// aligned codes -> bit planes of the window, [word][read][4]
-__global__ void packReadsKernel(SeedArgs a, int L, int nWords) {
+// aligned codes -> bit planes over profile positions, [word][read][4]; one thread per (word, read)
+__global__ void packReadsKernel(SeedArgs a, int L, int K, const int* __restrict__ p2cs) {
 	const int r = blockIdx.x * blockDim.x + threadIdx.x;
 	const int w = blockIdx.y;
 	if (r >= a.nReadsPad) return;
 	uint32_t hi = 0, lo = 0, va = 0;
 	if (r < a.nReads && a.winStart[r] >= 0) {
 		const int s = a.winStart[r], e = a.winEnd[r];
-		const int c0 = max(w * 32, s), c1 = min(min(w * 32 + 31, e), L - 1);
 		const int8_t* x = a.aligned + (size_t) r * L;
-		for (int c = c0; c <= c1; ++c) {
+		for (int b = 0; b < 32; ++b) {
+			const int k = w * 32 + b + 1;
+			if (k > K) break;
+			const int c = __ldg(p2cs + k) - 1;
+			if (c < s || c > e) continue;
 			const int v = x[c];
 			if (v >= 0) {
-				const int b = c - w * 32;
 				va |= 1u << b;
 				hi |= (uint32_t) ((v >> 1) & 1) << b;
 				lo |= (uint32_t) (v & 1) << b;
 			}
 		}
-		if (va) atomicAdd(a.rValid + r, __popc(va));
+		if (va) {
+			atomicAdd(a.rValid + r, __popc(va));
+			atomicMin(a.rWordLo + r, w);
+			atomicMax(a.rWordHi + r, w);
+		}
 	}
 	reinterpret_cast<uint4*>(a.rplanes)[(size_t) w * a.nReadsPad + r] = make_uint4(hi, lo, va, 0u);
 }
 
-__device__ __forceinline__ unsigned long long makeKey(int d, int N, int node, bool excluded) {
-	uint32_t q = 0xFFFFFFFFu;
-	if (!excluded && N > 0) q = (uint32_t) __double2ll_rd(__ddiv_rn((double) d * 2147483648.0, (double) N));
-	return ((unsigned long long) q << 32) | (uint32_t) (excluded ? 0x7FFFFFFF : node);
+// bases of the read in non-match columns of its window: (column << 8) | base; one warp per read
+__global__ void sparseListKernel(SeedArgs a, int L, const int* __restrict__ colK) {
+	const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+	const int lane = threadIdx.x & 31;
+	if (r >= a.nReads) return;
+	int n = 0;
+	if (a.winStart[r] >= 0) {
+		const int s = a.winStart[r], e = a.winEnd[r];
+		const int8_t* x = a.aligned + (size_t) r * L;
+		uint32_t* out = a.sparse + (size_t) r * a.sparseCap;
+		for (int c0 = s; c0 <= e; c0 += 32) {
+			const int c = c0 + lane;
+			const bool hit = c <= e && x[c] >= 0 && __ldg(colK + c) == 0;
+			const unsigned m = __ballot_sync(0xffffffffu, hit);
+			if (hit) {
+				const int pos = n + __popc(m & ((1u << lane) - 1u));
+				if (pos < a.sparseCap) out[pos] = ((uint32_t) c << 8) | (uint32_t) x[c];
+			}
+			n += __popc(m);
+		}
+	}
+	// more non-match bases than the workspace was sized for (only possible through hu_batch_set_aligned with
+	// rows denser than maxSeqLen): the read is reported unplaced rather than scored on a truncated list
+	if (lane == 0) a.nSparse[r] = n <= a.sparseCap ? n : -1;
+}
+
+__device__ __forceinline__ uint32_t makeKey(int d, int N, bool excluded) {
+	if (excluded || N <= 0) return 0xFFFFFFFFu; // 0/0: the reference's NaN distance; such nodes sort last here
+	return (uint32_t) __double2ll_rd(__ddiv_rn((double) d * 2147483648.0, (double) N));
 }
 
 template <bool GAP>
@@ -53,15 +89,14 @@ __global__ void __launch_bounds__(128) seedScanKernel(SeedArgs a, TreeDev t, int
 	if (threadIdx.x == 0) {
 		int lo = 0x7fffffff, hi = -1;
 		for (int r = r0; r < r0 + HU_SCAN_READS; ++r)
-			if (r < a.nReads && a.winStart[r] >= 0) {
-				lo = min(lo, a.winStart[r] >> 5);
-				hi = max(hi, a.winEnd[r] >> 5);
+			if (r < a.nReads && a.winStart[r] >= 0 && a.rWordHi[r] >= 0) {
+				lo = min(lo, a.rWordLo[r]);
+				hi = max(hi, a.rWordHi[r]);
 			}
 		sLo = lo; sHi = hi;
 	}
 	__syncthreads();
 	const int gLo = sLo, gHi = sHi;
-	if (gHi < 0) return;
 	const uint4* rp = reinterpret_cast<const uint4*>(a.rplanes);
 	for (int i = threadIdx.x; i < (gHi - gLo + 1) * HU_SCAN_READS; i += blockDim.x)
 		sR[i] = rp[(size_t) (gLo + i / HU_SCAN_READS) * a.nReadsPad + r0 + (i % HU_SCAN_READS)];
@@ -105,22 +140,34 @@ __global__ void __launch_bounds__(128) seedScanKernel(SeedArgs a, TreeDev t, int
 	for (int r = 0; r < HU_SCAN_READS; ++r) {
 		const int rr = r0 + r;
 		if (rr >= a.nReads || a.winStart[rr] < 0) continue;
-		const int nv = GAP ? 0 : a.rValid[rr];
-		unsigned long long k[4];
+		int dd[4], nn[4];
 #pragma unroll
-		for (int s = 0; s < 4; ++s) k[s] = makeKey(d[r][s], GAP ? n[r][s] : nv, node[s], excl[s]);
-		ulonglong2* dst = reinterpret_cast<ulonglong2*>(a.keys + (size_t) rr * pitch + slot);
-		dst[0] = make_ulonglong2(k[0], k[1]);
-		dst[1] = make_ulonglong2(k[2], k[3]);
+		for (int s = 0; s < 4; ++s) { dd[s] = d[r][s]; nn[s] = GAP ? n[r][s] : a.rValid[rr]; }
+		// insert bases of the read in non-match columns
+		const int ns = a.nSparse[rr];
+		const uint32_t* sp = a.sparse + (size_t) rr * a.sparseCap;
+		for (int i = 0; i < ns; ++i) {
+			const uint32_t e = __ldg(sp + i);
+			const int rb = (int) (e & 0xff);
+			const char4 nb = *reinterpret_cast<const char4*>(t.seqT + (size_t) (e >> 8) * pitch + slot);
+			const int b4[4] = {nb.x, nb.y, nb.z, nb.w};
+#pragma unroll
+			for (int s = 0; s < 4; ++s)
+				if (b4[s] >= 0) { nn[s]++; dd[s] += b4[s] != rb; }
+		}
+		uint4 k;
+		k.x = makeKey(dd[0], nn[0], excl[0] || ns < 0); k.y = makeKey(dd[1], nn[1], excl[1] || ns < 0);
+		k.z = makeKey(dd[2], nn[2], excl[2] || ns < 0); k.w = makeKey(dd[3], nn[3], excl[3] || ns < 0);
+		*reinterpret_cast<uint4*>(a.keys + (size_t) rr * pitch + slot) = k;
 	}
 }
 
-// ---- per-read selection of the maxNSeed smallest (key, id) ----
+// ---- per-read selection of the maxNSeed smallest (key, node id) ----
 #define HU_SEL_THREADS 256
 #define HU_SEL_CAND 2048
 #define HU_SEL_BINS 2048
 
-__global__ void __launch_bounds__(HU_SEL_THREADS) seedSelectKernel(SeedArgs a, int scanPitch) {
+__global__ void __launch_bounds__(HU_SEL_THREADS) seedSelectKernel(SeedArgs a, int scanPitch, const int* __restrict__ scanNode) {
 	__shared__ unsigned int hist[HU_SEL_BINS];
 	__shared__ unsigned long long cand[HU_SEL_CAND];
 	__shared__ unsigned int sCount, sValid, sDigit, sBelow;
@@ -131,9 +178,10 @@ __global__ void __launch_bounds__(HU_SEL_THREADS) seedSelectKernel(SeedArgs a, i
 		if (tid == 0) a.nSeeds[r] = 0;
 		return;
 	}
-	const unsigned long long* keys = a.keys + (size_t) r * scanPitch;
-	const ulonglong2* keys2 = reinterpret_cast<const ulonglong2*>(keys);
-	const int n2 = scanPitch / 2;
+	const uint4* keys4 = reinterpret_cast<const uint4*>(a.keys + (size_t) r * scanPitch);
+	const int4* node4 = reinterpret_cast<const int4*>(scanNode);
+	const int n4 = scanPitch / 4;
+	// composite value c = (key << 32) | node id, refined 11 bits at a time from the top
 	const int shifts[6] = {53, 42, 31, 20, 9, 0};
 	const int widths[6] = {11, 11, 11, 11, 11, 9};
 	unsigned long long prefixVal = 0, prefixMask = 0; // elements with (c & prefixMask) == prefixVal are undecided
@@ -147,15 +195,18 @@ __global__ void __launch_bounds__(HU_SEL_THREADS) seedSelectKernel(SeedArgs a, i
 		const int sh = shifts[level];
 		const unsigned int dm = (1u << widths[level]) - 1u;
 		unsigned int valid = 0, maxq = 0;
-		for (int i = tid; i < n2; i += HU_SEL_THREADS) {
-			const ulonglong2 kk = keys2[i];
-			const unsigned long long c2[2] = {kk.x, kk.y};
+		for (int i = tid; i < n4; i += HU_SEL_THREADS) {
+			const uint4 kk = keys4[i];
+			const unsigned int q4[4] = {kk.x, kk.y, kk.z, kk.w};
+			int4 nd = make_int4(0, 0, 0, 0);
+			if (sh < 32) nd = __ldg(node4 + i); // node ids only matter once the key bits are exhausted
+			const int n4v[4] = {nd.x, nd.y, nd.z, nd.w};
 #pragma unroll
-			for (int e = 0; e < 2; ++e) {
-				const unsigned long long c = c2[e];
-				const unsigned int q = (unsigned int) (c >> 32);
+			for (int e = 0; e < 4; ++e) {
+				const unsigned int q = q4[e];
 				if (q == 0xFFFFFFFFu) continue;
 				if (level == 0) { valid++; maxq = max(maxq, q); }
+				const unsigned long long c = ((unsigned long long) q << 32) | (unsigned int) n4v[e];
 				if ((c & prefixMask) == prefixVal) atomicAdd(&hist[(unsigned int) (c >> sh) & dm], 1u);
 			}
 		}
@@ -190,10 +241,22 @@ __global__ void __launch_bounds__(HU_SEL_THREADS) seedSelectKernel(SeedArgs a, i
 	// gather everything below the bound (count <= HU_SEL_CAND) and sort it
 	if (tid == 0) sCount = 0;
 	__syncthreads();
-	for (int i = tid; i < n2; i += HU_SEL_THREADS) {
-		const ulonglong2 kk = keys2[i];
-		if (kk.x < bound && (unsigned int) (kk.x >> 32) != 0xFFFFFFFFu) { const unsigned int p = atomicAdd(&sCount, 1u); if (p < HU_SEL_CAND) cand[p] = kk.x; }
-		if (kk.y < bound && (unsigned int) (kk.y >> 32) != 0xFFFFFFFFu) { const unsigned int p = atomicAdd(&sCount, 1u); if (p < HU_SEL_CAND) cand[p] = kk.y; }
+	for (int i = tid; i < n4; i += HU_SEL_THREADS) {
+		const uint4 kk = keys4[i];
+		const unsigned int q4[4] = {kk.x, kk.y, kk.z, kk.w};
+		const unsigned int qb = (unsigned int) (bound >> 32);
+		if (min(min(q4[0], q4[1]), min(q4[2], q4[3])) > qb) continue;
+		const int4 nd = __ldg(node4 + i);
+		const int n4v[4] = {nd.x, nd.y, nd.z, nd.w};
+#pragma unroll
+		for (int e = 0; e < 4; ++e) {
+			if (q4[e] == 0xFFFFFFFFu) continue;
+			const unsigned long long c = ((unsigned long long) q4[e] << 32) | (unsigned int) n4v[e];
+			if (c < bound) {
+				const unsigned int p = atomicAdd(&sCount, 1u);
+				if (p < HU_SEL_CAND) cand[p] = c;
+			}
+		}
 	}
 	__syncthreads();
 	const unsigned int cnt = min(sCount, (unsigned int) HU_SEL_CAND);
@@ -243,24 +306,27 @@ int launchSeed(hu_batch* b, const hu_sep_params* p) {
 	b->seed = a;
 	HU_CUDA(cudaEventRecord(b->ev[2], b->stream));
 	HU_CUDA(cudaMemsetAsync(a.rValid, 0, (size_t) a.nReadsPad * sizeof(int), b->stream));
-	packReadsKernel<<<dim3((a.nReadsPad + 127) / 128, t.nWords), 128, 0, b->stream>>>(a, t.csLen, t.nWords);
+	HU_CUDA(cudaMemsetAsync(a.rWordLo, 0x7f, (size_t) a.nReadsPad * sizeof(int), b->stream));
+	HU_CUDA(cudaMemsetAsync(a.rWordHi, 0xff, (size_t) a.nReadsPad * sizeof(int), b->stream));
+	packReadsKernel<<<dim3((a.nReadsPad + 127) / 128, t.nPWords), 128, 0, b->stream>>>(a, t.csLen, db->hmm.K, db->hmm.p2cs);
+	sparseListKernel<<<(b->nReads + 3) / 4, 128, 0, b->stream>>>(a, t.csLen, t.colK);
 	const int groups = a.nReadsPad / HU_SCAN_READS;
-	const size_t smem = (size_t) t.nWords * HU_SCAN_READS * sizeof(uint4);
+	const size_t smem = (size_t) t.nPWords * HU_SCAN_READS * sizeof(uint4);
 	static bool attr = false;
 	if (!attr) {
 		HU_CUDA(cudaFuncSetAttribute(seedScanKernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
 		HU_CUDA(cudaFuncSetAttribute(seedScanKernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
 		attr = true;
 	}
-	if (smem > 200 * 1024) { setError("consensus too long for the seed-scan read tile (%d words)", t.nWords); return HU_ERR_ARG; }
+	if (smem > 200 * 1024) { setError("profile too long for the seed-scan read tile (%d words)", t.nPWords); return HU_ERR_ARG; }
 	const int gapTiles = t.nGapSlots / HU_SCAN_TILE, allTiles = t.scanPitch / HU_SCAN_TILE;
 	// grid.x (fast) runs over read groups so that consecutive CTAs reuse the same node tile from L2
 	if (gapTiles > 0) seedScanKernel<true><<<dim3(groups, gapTiles), 128, smem, b->stream>>>(a, t, 0);
 	if (allTiles > gapTiles) seedScanKernel<false><<<dim3(groups, allTiles - gapTiles), 128, smem, b->stream>>>(a, t, gapTiles);
 	HU_CUDA(cudaEventRecord(b->ev[3], b->stream));
-	seedSelectKernel<<<b->nReads, HU_SEL_THREADS, 0, b->stream>>>(a, t.scanPitch);
+	seedSelectKernel<<<b->nReads, HU_SEL_THREADS, 0, b->stream>>>(a, t.scanPitch, t.scanNode);
 	HU_CUDA(cudaEventRecord(b->ev[4], b->stream));
-	b->launches += 2 + (gapTiles > 0) + (allTiles > gapTiles);
+	b->launches += 3 + (gapTiles > 0) + (allTiles > gapTiles);
 	HU_CUDA(cudaGetLastError());
 	return HU_OK;
 }
