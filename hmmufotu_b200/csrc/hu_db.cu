@@ -116,10 +116,25 @@ __global__ void edgePrKernel(Model m, const double* __restrict__ blen, int nNode
 	for (int i = 0; i < 16; ++i) PP[(size_t) idx * 16 + i] = P[i];
 }
 
+// Messages live on the device in the linear form of hu_internal.cuh (expNorm): E = exp(V - max V) (4 doubles per
+// column) and the scale max V (1 double per column).  dot_product_scaled(P, V)_i = log((P E)_i) + scale.
+__device__ __forceinline__ void convMsg(const double* P, const double* E, double sc, double* y) {
+	double t[4];
+	matVec4(P, E, t);
+	for (int i = 0; i < 4; ++i) y[i] = log(t[i]) + sc;
+}
+__device__ __forceinline__ void storeMsg(double* E, double* S, size_t idx, const double* o) {
+	double e[4];
+	const double mx = expNorm(o, e);
+	st4(E + idx * 4, e);
+	S[idx] = mx;
+}
+
 // Upward pass for the nodes of one depth level: up[x] = loglik(x, j) with x's parent as root side.
 __global__ void upLevelKernel(Model m, const int* __restrict__ levelNodes, int nLevel, int csLen,
 		const int* __restrict__ childStart, const int* __restrict__ childList, const int8_t* __restrict__ seq,
-		const double* __restrict__ PP, int KK, double* __restrict__ up, int isRootLevel, double* __restrict__ rootMsg) {
+		const double* __restrict__ PP, int KK, double* __restrict__ up, double* __restrict__ upS, int isRootLevel,
+		double* __restrict__ rootMsg) {
 	const int x = levelNodes[blockIdx.y];
 	const int j = blockIdx.x * blockDim.x + threadIdx.x;
 	if (j >= csLen) return;
@@ -129,9 +144,11 @@ __global__ void upLevelKernel(Model m, const int* __restrict__ levelNodes, int n
 	for (int c = c0; c < c1; ++c) {
 		const int ch = childList[c];
 		double v[4], y[4];
-		ld4(up + ((size_t) ch * csLen + j) * 4, v);
+		const size_t idx = (size_t) ch * csLen + j;
+		ld4(up + idx * 4, v);
+		const double sc = upS[idx];
 		for (int k = 0; k < KK; ++k) {
-			dpsMat(PP + ((size_t) ch * KK + k) * 16, v, y);
+			convMsg(PP + ((size_t) ch * KK + k) * 16, v, sc, y);
 			for (int i = 0; i < 4; ++i) mat[k][i] += y[i];
 		}
 	}
@@ -144,14 +161,15 @@ __global__ void upLevelKernel(Model m, const int* __restrict__ levelNodes, int n
 		leafMsg(m, seq[(size_t) x * csLen + j], n);
 		for (int i = 0; i < 4; ++i) o[i] += n[i];
 	}
-	double* dst = isRootLevel ? rootMsg + (size_t) j * 4 : up + ((size_t) x * csLen + j) * 4;
-	st4(dst, o);
+	if (isRootLevel) st4(rootMsg + (size_t) j * 4, o); // log domain: only its arg-max is used (inferSeq)
+	else storeMsg(up, upS, (size_t) x * csLen + j, o);
 }
 
 // Downward pass: dn[x] = loglik(parent, j) seen from x (siblings' up messages + the parent's own dn)
 __global__ void dnLevelKernel(Model m, const int* __restrict__ levelNodes, int nLevel, int csLen, int root,
 		const int* __restrict__ parent, const int* __restrict__ childStart, const int* __restrict__ childList,
-		const double* __restrict__ PP, int KK, const double* __restrict__ up, double* __restrict__ dn) {
+		const double* __restrict__ PP, int KK, const double* __restrict__ up, const double* __restrict__ upS,
+		double* __restrict__ dn, double* __restrict__ dnS) {
 	const int x = levelNodes[blockIdx.y];
 	const int j = blockIdx.x * blockDim.x + threadIdx.x;
 	if (j >= csLen) return;
@@ -162,17 +180,21 @@ __global__ void dnLevelKernel(Model m, const int* __restrict__ levelNodes, int n
 		const int sib = childList[c];
 		if (sib == x) continue;
 		double v[4], y[4];
-		ld4(up + ((size_t) sib * csLen + j) * 4, v);
+		const size_t idx = (size_t) sib * csLen + j;
+		ld4(up + idx * 4, v);
+		const double sc = upS[idx];
 		for (int k = 0; k < KK; ++k) {
-			dpsMat(PP + ((size_t) sib * KK + k) * 16, v, y);
+			convMsg(PP + ((size_t) sib * KK + k) * 16, v, sc, y);
 			for (int i = 0; i < 4; ++i) mat[k][i] += y[i];
 		}
 	}
 	if (pa != root) {
 		double v[4], y[4];
-		ld4(dn + ((size_t) pa * csLen + j) * 4, v);
+		const size_t idx = (size_t) pa * csLen + j;
+		ld4(dn + idx * 4, v);
+		const double sc = dnS[idx];
 		for (int k = 0; k < KK; ++k) {
-			dpsMat(PP + ((size_t) pa * KK + k) * 16, v, y);
+			convMsg(PP + ((size_t) pa * KK + k) * 16, v, sc, y);
 			for (int i = 0; i < 4; ++i) mat[k][i] += y[i];
 		}
 	}
@@ -180,7 +202,26 @@ __global__ void dnLevelKernel(Model m, const int* __restrict__ levelNodes, int n
 	double o[4];
 	if (deg != 1 && m.dgK) rmes(mat, KK, o);
 	else for (int i = 0; i < 4; ++i) o[i] = mat[0][i];
-	st4(dn + ((size_t) x * csLen + j) * 4, o);
+	storeMsg(dn, dnS, (size_t) x * csLen + j, o);
+}
+
+// log-domain messages supplied by the host -> linear form, in place over a staging chunk
+__global__ void toLinearKernel(const double* __restrict__ logMsg, size_t nCols, double* __restrict__ E, double* __restrict__ S) {
+	const size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= nCols) return;
+	double v[4];
+	ld4(logMsg + i * 4, v);
+	storeMsg(E, S, i, v);
+}
+// and back, for hu_db_get_messages: V_k = log(E_k) + scale
+__global__ void toLogKernel(const double* __restrict__ E, const double* __restrict__ S, size_t nCols, double* __restrict__ logMsg) {
+	const size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= nCols) return;
+	double e[4], v[4];
+	ld4(E + i * 4, e);
+	const double sc = S[i];
+	for (int k = 0; k < 4; ++k) v[k] = log(e[k]) + sc;
+	st4(logMsg + i * 4, v);
 }
 
 // inferSeq(): arg-max of the upward message for internal nodes (src/PhyloTreeUnrooted.cpp:1085-1093)
@@ -300,11 +341,13 @@ static int createImpl(hu_db* db, const hu_hmm_params* hp, const hu_tree_desc* td
 	HU_TRY(devAlloc(db, &seq, (size_t) n * csLen));
 	HU_CUDA(cudaMemcpy(seq, td->seq, (size_t) n * csLen, cudaMemcpyHostToDevice));
 	t.seq = seq;
-	double *up, *dn;
+	double *up, *dn, *upS, *dnS;
 	const size_t msgN = (size_t) n * csLen * 4;
 	HU_TRY(devAlloc(db, &up, msgN));
 	HU_TRY(devAlloc(db, &dn, msgN));
-	t.up = up; t.dn = dn;
+	HU_TRY(devAlloc(db, &upS, msgN / 4));
+	HU_TRY(devAlloc(db, &dnS, msgN / 4));
+	t.up = up; t.dn = dn; t.upS = upS; t.dnS = dnS;
 	// children in CSR form (neighbour order = ascending id, as built from a parent vector)
 	std::vector<int> childStart(n + 1, 0), childList(std::max(0, n - 1)), depth(n, -1);
 	for (int x = 0; x < n; ++x)
@@ -317,8 +360,19 @@ static int createImpl(hu_db* db, const hu_hmm_params* hp, const hu_tree_desc* td
 	}
 	if ((td->up == NULL) != (td->dn == NULL)) { setError("up and dn must both be given or both be NULL"); return HU_ERR_ARG; }
 	if (td->up) {
-		HU_CUDA(cudaMemcpy(up, td->up, msgN * sizeof(double), cudaMemcpyHostToDevice));
-		HU_CUDA(cudaMemcpy(dn, td->dn, msgN * sizeof(double), cudaMemcpyHostToDevice));
+		// staged conversion of the .ptu's log-domain messages, 16 M columns (512 MB) at a time
+		const size_t nCols = msgN / 4, chunk = (size_t) 16 << 20;
+		double* stage;
+		HU_CUDA(cudaMalloc(&stage, std::min(chunk, nCols) * 4 * sizeof(double)));
+		for (int dir = 0; dir < 2; ++dir)
+			for (size_t o = 0; o < nCols; o += chunk) {
+				const size_t c = std::min(chunk, nCols - o);
+				HU_CUDA(cudaMemcpy(stage, (dir ? td->dn : td->up) + o * 4, c * 4 * sizeof(double), cudaMemcpyHostToDevice));
+				toLinearKernel<<<(unsigned) ((c + 255) / 256), 256>>>(stage, c, (dir ? dn : up) + o * 4, (dir ? dnS : upS) + o);
+			}
+		HU_CUDA(cudaGetLastError());
+		HU_CUDA(cudaDeviceSynchronize());
+		cudaFree(stage);
 	} else {
 		// depth levels by breadth-first traversal from the root
 		std::vector<int> order;
@@ -356,7 +410,7 @@ static int createImpl(hu_db* db, const hu_hmm_params* hp, const hu_tree_desc* td
 			const int cnt = levelStart[d + 1] - levelStart[d];
 			for (int o = 0; o < cnt; o += 65535) {
 				const int c = std::min(65535, cnt - o);
-				upLevelKernel<<<dim3(gx.x, c), TB>>>(db->model, dOrder + levelStart[d] + o, c, csLen, dChildStart, dChildList, seq, dPP, KK, up, d == 0, dRootMsg);
+				upLevelKernel<<<dim3(gx.x, c), TB>>>(db->model, dOrder + levelStart[d] + o, c, csLen, dChildStart, dChildList, seq, dPP, KK, up, upS, d == 0, dRootMsg);
 			}
 		}
 		if (td->inferInternalSeq)
@@ -369,7 +423,7 @@ static int createImpl(hu_db* db, const hu_hmm_params* hp, const hu_tree_desc* td
 			const int cnt = levelStart[d + 1] - levelStart[d];
 			for (int o = 0; o < cnt; o += 65535) {
 				const int c = std::min(65535, cnt - o);
-				dnLevelKernel<<<dim3(gx.x, c), TB>>>(db->model, dOrder + levelStart[d] + o, c, csLen, td->root, t.parent, dChildStart, dChildList, dPP, KK, up, dn);
+				dnLevelKernel<<<dim3(gx.x, c), TB>>>(db->model, dOrder + levelStart[d] + o, c, csLen, td->root, t.parent, dChildStart, dChildList, dPP, KK, up, upS, dn, dnS);
 			}
 		}
 		HU_CUDA(cudaGetLastError());
@@ -378,6 +432,8 @@ static int createImpl(hu_db* db, const hu_hmm_params* hp, const hu_tree_desc* td
 		// the root has no parent edge: keep its rows defined
 		HU_CUDA(cudaMemset(up + (size_t) td->root * csLen * 4, 0, (size_t) csLen * 4 * sizeof(double)));
 		HU_CUDA(cudaMemset(dn + (size_t) td->root * csLen * 4, 0, (size_t) csLen * 4 * sizeof(double)));
+		HU_CUDA(cudaMemset(upS + (size_t) td->root * csLen, 0, (size_t) csLen * sizeof(double)));
+		HU_CUDA(cudaMemset(dnS + (size_t) td->root * csLen, 0, (size_t) csLen * sizeof(double)));
 	}
 	// ---- scan order + bit planes (after sequence inference) ----
 	std::vector<int8_t> hseq;
@@ -507,9 +563,21 @@ int hu_db_destroy(hu_db* db) {
 int hu_db_get_messages(hu_db* db, int64_t node0, int64_t n, double* up, double* dn) {
 	if (!db || node0 < 0 || node0 + n > db->tree.nNodes) { hu::setError("hu_db_get_messages: bad range"); return HU_ERR_ARG; }
 	HU_CUDA(cudaSetDevice(db->device));
-	const size_t per = (size_t) db->tree.csLen * 4;
-	if (up) HU_CUDA(cudaMemcpy(up, db->tree.up + node0 * per, n * per * sizeof(double), cudaMemcpyDeviceToHost));
-	if (dn) HU_CUDA(cudaMemcpy(dn, db->tree.dn + node0 * per, n * per * sizeof(double), cudaMemcpyDeviceToHost));
+	// the device holds (exp(V - max V), max V); hand back V = log(E) + scale, one node at a time
+	const size_t cols = (size_t) db->tree.csLen;
+	double* stage;
+	HU_CUDA(cudaMalloc(&stage, cols * 4 * sizeof(double)));
+	for (int dir = 0; dir < 2; ++dir) {
+		double* dst = dir ? dn : up;
+		if (!dst) continue;
+		const double* E = dir ? db->tree.dn : db->tree.up;
+		const double* S = dir ? db->tree.dnS : db->tree.upS;
+		for (int64_t x = 0; x < n; ++x) {
+			hu::toLogKernel<<<(unsigned) ((cols + 255) / 256), 256>>>(E + (size_t) (node0 + x) * cols * 4, S + (size_t) (node0 + x) * cols, cols, stage);
+			HU_CUDA(cudaMemcpy(dst + (size_t) x * cols * 4, stage, cols * 4 * sizeof(double), cudaMemcpyDeviceToHost));
+		}
+	}
+	cudaFree(stage);
 	return HU_OK;
 }
 

@@ -82,16 +82,18 @@ __global__ void __launch_bounds__(HU_EST_THREADS) estimateKernel(EstArgs a, Tree
 		__syncthreads();
 		const double* U = t.up + ((size_t) u * t.csLen + start) * 4;
 		const double* V = t.dn + ((size_t) u * t.csLen + start) * 4;
+		const double* US = t.upS + (size_t) u * t.csLen + start;
+		const double* VS = t.dnS + (size_t) u * t.csLen + start;
 		const bool store = W <= a.capW;
 		// ---- pass 1: g_j = (P(wur) e^U_j) * (P(wvr) e^V_j) (= e^{R_j} up to the column scale) and the
 		//      unweighted branch-length estimate (cpp:1018-1032).  Linear domain, see expNorm().
 		int diff = 0;
 		double sumScale = 0;
 		for (int c = tid; c < W; c += HU_EST_THREADS) {
-			double uv[4], vv[4], eu[4], ev[4], ya[4], yb[4], g[4];
-			ld4(U + (size_t) c * 4, uv);
-			ld4(V + (size_t) c * 4, vv);
-			sumScale += expNorm(uv, eu) + expNorm(vv, ev);
+			double eu[4], ev[4], ya[4], yb[4], g[4];
+			ld4(U + (size_t) c * 4, eu);
+			ld4(V + (size_t) c * 4, ev);
+			sumScale += __ldg(US + c) + __ldg(VS + c);
 			matVec4(sP[0], eu, ya);
 			matVec4(sP[1], ev, yb);
 			for (int k = 0; k < 4; ++k) g[k] = ya[k] * yb[k];
@@ -123,11 +125,9 @@ __global__ void __launch_bounds__(HU_EST_THREADS) estimateKernel(EstArgs a, Tree
 				const double2 p1 = reinterpret_cast<const double2*>(sR + (size_t) c * 4)[1];
 				g[0] = p0.x; g[1] = p0.y; g[2] = p1.x; g[3] = p1.y;
 			} else {
-				double uv[4], vv[4], eu[4], ev[4], ya[4], yb[4];
-				ld4(U + (size_t) c * 4, uv);
-				ld4(V + (size_t) c * 4, vv);
-				expNorm(uv, eu);
-				expNorm(vv, ev);
+				double eu[4], ev[4], ya[4], yb[4];
+				ld4(U + (size_t) c * 4, eu);
+				ld4(V + (size_t) c * 4, ev);
 				matVec4(sP[0], eu, ya);
 				matVec4(sP[1], ev, yb);
 				for (int k = 0; k < 4; ++k) g[k] = ya[k] * yb[k];

@@ -204,8 +204,10 @@ struct TreeDev {
 	const double* height;
 	const int8_t* seq;       // [nNodes][csLen]
 	const int* taxon;
-	const double* up;        // [nNodes][csLen][4]
-	const double* dn;
+	const double* up;        // [nNodes][csLen][4]: exp(msg(id -> parent) - scale), max-normalised
+	const double* dn;        //                     exp(msg(parent -> id) - scale)
+	const double* upS;       // [nNodes][csLen]: the scales (max of the log-domain column)
+	const double* dnS;
 	// seed scan, in PROFILE coordinates: bit (k-1)%32 of word (k-1)/32 is match column p2cs[k] (k = 1..K);
 	// [word][plane][nodeSlot], planes hi, lo, valid; nodeSlot = position in the scan order
 	const uint32_t* planes;

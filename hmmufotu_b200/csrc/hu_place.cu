@@ -108,6 +108,8 @@ __global__ void __launch_bounds__(HU_PLACE_WARPS * 32) placeKernel(PlaceArgs a, 
 		const double w0 = t.blen[c];
 		const double* U = t.up + ((size_t) c * t.csLen + start) * 4;
 		const double* V = t.dn + ((size_t) c * t.csLen + start) * 4;
+		const double* US = t.upS + (size_t) c * t.csLen + start;
+		const double* VS = t.dnS + (size_t) c * t.csLen + start;
 		const int8_t* x = a.aligned + (size_t) r * t.csLen + start;
 		double* rho = W <= a.capW ? rhoS : a.slab + (size_t) slot * t.csLen;
 		double lu = w0 * e.ratio, lv = w0 * (1 - e.ratio), ln = e.wnr; // cpp:906-912
@@ -123,11 +125,9 @@ __global__ void __launch_bounds__(HU_PLACE_WARPS * 32) placeKernel(PlaceArgs a, 
 			__syncwarp();
 			int nValid = 0;
 			for (int cI = lane; cI < W; cI += 32) {
-				double uv[4], vv[4], eu[4], ev[4], ya[4], yb[4], g[4] = {0, 0, 0, 0};
-				ld4(U + (size_t) cI * 4, uv);
-				ld4(V + (size_t) cI * 4, vv);
-				expNorm(uv, eu);
-				expNorm(vv, ev);
+				double eu[4], ev[4], ya[4], yb[4], g[4] = {0, 0, 0, 0};
+				ld4(U + (size_t) cI * 4, eu);
+				ld4(V + (size_t) cI * 4, ev);
 				for (int k = 0; k < KK; ++k) {
 					matVec4(ws->P[0][k], eu, ya);
 					matVec4(ws->P[1][k], ev, yb);
@@ -159,11 +159,9 @@ __global__ void __launch_bounds__(HU_PLACE_WARPS * 32) placeKernel(PlaceArgs a, 
 			__syncwarp();
 			nValid = 0;
 			for (int cI = lane; cI < W; cI += 32) {
-				double uv[4], vv[4], eu[4], ev[4], yb[4], g[4] = {0, 0, 0, 0};
-				ld4(U + (size_t) cI * 4, uv);
-				ld4(V + (size_t) cI * 4, vv);
-				expNorm(uv, eu);
-				expNorm(vv, ev);
+				double eu[4], ev[4], yb[4], g[4] = {0, 0, 0, 0};
+				ld4(U + (size_t) cI * 4, eu);
+				ld4(V + (size_t) cI * 4, ev);
 				const int b = x[cI];
 				for (int k = 0; k < KK; ++k) {
 					matVec4(ws->P[1][k], ev, yb);
@@ -204,10 +202,10 @@ __global__ void __launch_bounds__(HU_PLACE_WARPS * 32) placeKernel(PlaceArgs a, 
 		__syncwarp();
 		double tl = 0;
 		for (int cI = lane; cI < W; cI += 32) {
-			double uv[4], vv[4], eu[4], ev[4], ya[4], yb[4], g[4] = {0, 0, 0, 0};
-			ld4(U + (size_t) cI * 4, uv);
-			ld4(V + (size_t) cI * 4, vv);
-			const double sc = expNorm(uv, eu) + expNorm(vv, ev);
+			double eu[4], ev[4], ya[4], yb[4], g[4] = {0, 0, 0, 0};
+			ld4(U + (size_t) cI * 4, eu);
+			ld4(V + (size_t) cI * 4, ev);
+			const double sc = __ldg(US + cI) + __ldg(VS + cI);
 			const int b = x[cI];
 			for (int k = 0; k < KK; ++k) {
 				matVec4(ws->P[0][k], eu, ya);
