@@ -161,7 +161,7 @@ int hu_batch_create(hu_batch** out, hu_db* db, int32_t maxReads, int32_t maxSeqL
 	if (perWarp > 200 * 1024) { setError("maxSeqLen %d too long for the Viterbi shared-memory layout", maxSeqLen); return HU_ERR_ARG; }
 	b->vit.warpsPerBlock = wpb;
 	b->vit.maxLen = maxSeqLen;
-	b->fullSlots = std::min(sms * 2 * wpb, std::max(wpb, (b->maxSeq + wpb - 1) / wpb * wpb));
+	b->fullSlots = std::min(sms * 2, b->maxSeq); // CTAs of the full-matrix pass, one back-pointer slab each
 	b->vit.fullSlabWords = (size_t) K * ((maxSeqLen + 7) / 8);
 	HU_TRY(balloc(b, &b->vit.fullPtrs, b->vit.fullSlabWords * b->fullSlots));
 	HU_TRY(balloc(b, &b->winStart, (size_t) maxReads));

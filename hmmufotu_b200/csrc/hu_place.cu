@@ -45,15 +45,18 @@ __device__ __forceinline__ double warpSum(double v) {
 	return v;
 }
 
-// 1/x for x >= ~1e-30: single-precision seed + two Newton steps (relative error < 1e-15), no branches
+#define HU_RHO_SKIP 1e300 // stands for a skipped column (NaN in the reference's test): its EM term is ~1e-300
+
+// 1/x: hardware fp64 reciprocal approximation (about 2^-20 relative) + one Newton step -> below 1e-12 relative,
+// no branches.  x is rho q0 + p0 with 0 <= rho <= 1e300, 0 < p0, q0 <= 1.
 __device__ __forceinline__ double rcpFast(double x) {
-	double r = (double) __frcp_rn((float) x);
-	r = fma(r, fma(-x, r, 1.0), r);
-	r = fma(r, fma(-x, r, 1.0), r);
-	return r;
+	double r;
+	asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+	return fma(r, fma(-x, r, 1.0), r);
 }
 
-// Felsenstein EM for one branch given rho_j (NaN = column skipped), src/PhyloTreeUnrooted.cpp:749-798
+// Felsenstein EM for one branch given rho_j, src/PhyloTreeUnrooted.cpp:749-798:
+// p <- (1/N) sum_j e^B p0 / (e^A q0 + e^B p0) = (1/N) sum_j p0 / (rho_j q0 + p0)
 __device__ double emBranch(const double* __restrict__ rho, int W, int nValid, double wInit, double cap, int* itersOut) {
 	const int lane = threadIdx.x & 31;
 	double q0 = exp(-wInit), p0 = 1 - q0;
@@ -61,17 +64,19 @@ __device__ double emBranch(const double* __restrict__ rho, int W, int nValid, do
 	int it = 0;
 	for (it = 0; it < HU_MAX_ITER && p >= 0 && p <= 1; ++it) {
 		double s = 0;
-		if (p0 > 1e-30 && q0 >= 0) { // e^B p0 / (e^A q0 + e^B p0) = p0 / (rho q0 + p0)
-			for (int c = lane; c < W; c += 32) {
-				const double rh = rho[c];
-				const double x = fma(rh, q0, p0);
-				const double term = x < 1e300 ? p0 * rcpFast(x) : 0.0;
-				if (rh == rh) s += term;
+		if (p0 > 1e-200 && q0 >= 0) {
+			double s1 = 0; // two accumulators: independent dependency chains
+			int c = lane;
+			for (; c + 32 < W; c += 64) {
+				s = fma(p0, rcpFast(fma(rho[c], q0, p0)), s);
+				s1 = fma(p0, rcpFast(fma(rho[c + 32], q0, p0)), s1);
 			}
-		} else {
+			if (c < W) s = fma(p0, rcpFast(fma(rho[c], q0, p0)), s);
+			s += s1;
+		} else { // degenerate branch length: plain division keeps the reference's NaN / inf behaviour
 			for (int c = lane; c < W; c += 32) {
 				const double rh = rho[c];
-				if (rh == rh) s += p0 / (rh * q0 + p0);
+				if (rh < HU_RHO_SKIP) s += p0 / (rh * q0 + p0);
 			}
 		}
 		p = warpSum(s) / (double) nValid;
@@ -139,7 +144,7 @@ __global__ void __launch_bounds__(HU_PLACE_WARPS * 32) placeKernel(PlaceArgs a, 
 				const double den = dotPi(m, g) * (b >= 0 ? m.pi[b] : piSq);
 				const double rh = num / den;
 				nValid += rh == rh;
-				rho[cI] = rh;
+				rho[cI] = rh == rh ? fmin(rh, HU_RHO_SKIP) : HU_RHO_SKIP;
 			}
 			for (int o = 16; o > 0; o >>= 1) nValid += __shfl_xor_sync(0xffffffffu, nValid, o);
 			__syncwarp();
@@ -172,7 +177,7 @@ __global__ void __launch_bounds__(HU_PLACE_WARPS * 32) placeKernel(PlaceArgs a, 
 				for (int i = 0; i < 4; ++i) z[i] = g[i] * eu[i];
 				const double rh = dotPi(m, z) / (dotPi(m, g) * dotPi(m, eu));
 				nValid += rh == rh;
-				rho[cI] = rh;
+				rho[cI] = rh == rh ? fmin(rh, HU_RHO_SKIP) : HU_RHO_SKIP;
 			}
 			for (int o = 16; o > 0; o >>= 1) nValid += __shfl_xor_sync(0xffffffffu, nValid, o);
 			__syncwarp();

@@ -28,10 +28,82 @@ __device__ __forceinline__ bool better(double v, int j, int i, const Best& b) {
 	return v < b.v || (v == b.v && (j < b.j || (j == b.j && i < b.i)));
 }
 
+// per-column profile parameters held in registers by the lane that owns the column
+struct ColParams {
+	double tMMp, tIMp, tDMp, tMDp, tDDp; // Tmat_cost[j-1](M,M) (I,M) (D,M) (M,D) (D,D)
+	double tMI, tII, tIMj;               // Tmat_cost[j](M,I) (I,I) (I,M)
+	double ent, ext;
+	double eM0, eM1, eM2, eM3, eI0, eI1, eI2, eI3;
+	bool dOn;                            // 1 < j < K
+};
+__device__ __forceinline__ void loadCol(const HmmDev& h, int jj, ColParams& p) {
+	const int Kp = h.Kp;
+	p.tMMp = __ldg(h.tr + T_MM * Kp + jj - 1); p.tIMp = __ldg(h.tr + T_IM * Kp + jj - 1); p.tDMp = __ldg(h.tr + T_DM * Kp + jj - 1);
+	p.tMDp = __ldg(h.tr + T_MD * Kp + jj - 1); p.tDDp = __ldg(h.tr + T_DD * Kp + jj - 1);
+	p.tMI = __ldg(h.tr + T_MI * Kp + jj); p.tII = __ldg(h.tr + T_II * Kp + jj); p.tIMj = __ldg(h.tr + T_IM * Kp + jj);
+	p.ent = __ldg(h.ent + jj); p.ext = __ldg(h.ext + jj);
+	p.eM0 = __ldg(h.eM + jj); p.eM1 = __ldg(h.eM + Kp + jj); p.eM2 = __ldg(h.eM + 2 * Kp + jj); p.eM3 = __ldg(h.eM + 3 * Kp + jj);
+	p.eI0 = __ldg(h.eI + jj); p.eI1 = __ldg(h.eI + Kp + jj); p.eI2 = __ldg(h.eI + 2 * Kp + jj); p.eI3 = __ldg(h.eI + 3 * Kp + jj);
+	p.dOn = jj > 1 && jj < h.K;
+}
+
+struct SeqConst { // per-sequence constants of the special states (setSequenceMode, src/BandedHMMP7.cpp:561-583)
+	int N, K;
+	double cNN, cNB, cEC, cCC;
+	bool sAllRows; // cCC finite: rows i < N can hold the minimum of S (NGCL / LOCAL); GLOBAL: only row N
+};
+
+// One cell (i, j): DP_M / DP_I / DP_D (src/BandedHMMP7.cpp:812-825), its 4-bit back-pointer and the S candidate.
+// diag = (i-1,j-1), up = (i-1,j), left = (i,j-1).  Returns the pointer code.
+__device__ __forceinline__ uint32_t cellUpdate(const ColParams& p, const SeqConst& q, int b, int i, int j, bool useB, bool trackS,
+		double dgM, double dgI, double dgD, double upM, double upI, double lM, double lD,
+		double& nM, double& nI, double& nD, Best& best) {
+	const double eM = (b & 2) ? ((b & 1) ? p.eM3 : p.eM2) : ((b & 1) ? p.eM1 : p.eM0);
+	const double eI = (b & 2) ? ((b & 1) ? p.eI3 : p.eI2) : ((b & 1) ? p.eI1 : p.eI0);
+	// DP_M: useB at :812-819, no B in the downstream box :866-872
+	const double cB = col0M(i, q.cNN, q.cNB) + p.ent;
+	const double cM = dgM + p.tMMp, cI = dgI + p.tIMp, cD = dgD + p.tDMp;
+	const double m3 = fmin(cM, fmin(cI, cD));
+	nM = eM + (useB ? fmin(cB, m3) : m3);
+	// trace candidates (src/BandedHMMP7.cpp:962-971): always with B; only B and I at j == 1
+	uint32_t pm = 0;
+	if (j > 1) {
+		double mn = cB;
+		if (cM < mn) { mn = cM; pm = 1; }
+		if (cI < mn) { mn = cI; pm = 2; }
+		if (cD < mn) { pm = 3; }
+	} else
+		pm = (cI < cB) ? 2 : 0;
+	// DP_I: :820-822
+	const double iM = upM + p.tMI, iI = upI + p.tII;
+	nI = eI + fmin(iM, iI);
+	const uint32_t pi = iI < iM ? 1 : 0;
+	// DP_D: :823-825 (only 1 < j < K)
+	uint32_t pd = 0;
+	nD = INFINITY;
+	if (p.dOn) {
+		const double dM = lM + p.tMDp, dD = lD + p.tDDp;
+		nD = fmin(dM, dD);
+		pd = dD < dM ? 1 : 0;
+	}
+	// S (src/BandedHMMP7.cpp:883-891)
+	if (trackS && (i == q.N || q.sAllRows)) {
+		const double rowPen = i < q.N ? q.cCC * (double) (q.N - i) : 0.0;
+		double sv = (nM + p.ext) + q.cEC;
+		if (i < q.N) sv += rowPen;
+		if (better(sv, j, i, best)) { best.v = sv; best.j = j; best.i = i; }
+		if (j == q.K) {
+			double s2 = (nI + p.tIMj) + q.cEC;
+			if (i < q.N) s2 += rowPen;
+			if (better(s2, q.K + 1, i, best)) { best.v = s2; best.j = q.K + 1; best.i = i; }
+		}
+	}
+	return pm | (pi << 2) | (pd << 3);
+}
+
 struct WarpCtx {
 	const int8_t* x;   // read codes, x[i-1]
-	int N;
-	double cNN, cNB, cEC, cCC;
+	SeqConst q;
 	double* bnd;       // shared: [3][bndPitch]
 	int bndPitch;
 	Cell* win;         // shared: 2x2 window around the current chain corner, [a*2+b] = cell (ic-1+a, jc-1+b)
@@ -42,7 +114,6 @@ struct WarpCtx {
 // Sweep one box.  Returns the number of cell updates.
 __device__ long long sweepBox(const HmmDev& h, const VRegion& R, bool hasNext, WarpCtx& w, uint32_t* __restrict__ ptrBase, Best& best) {
 	const int lane = threadIdx.x & 31;
-	const int K = h.K, Kp = h.Kp;
 	const int rows = R.i1 - R.i0 + 1, cols = R.j1 - R.j0 + 1;
 	long long cells = 0;
 	// ---- window around the end corner: start from what is known before this box ----
@@ -53,7 +124,7 @@ __device__ long long sweepBox(const HmmDev& h, const VRegion& R, bool hasNext, W
 		c.M = c.I = c.D = INFINITY;
 		const int oa = ci - (w.ic - 1), ob = cj - (w.jc - 1);
 		if (oa >= 0 && oa < 2 && ob >= 0 && ob < 2) c = w.win[oa * 2 + ob];
-		else if (cj == 0) { c.M = c.I = col0M(ci, w.cNN, w.cNB); }
+		else if (cj == 0) { c.M = c.I = col0M(ci, w.q.cNN, w.q.cNB); }
 		w.winNew[lane] = c;
 	}
 	// ---- left boundary column (j0-1) for stripe 0 ----
@@ -61,7 +132,7 @@ __device__ long long sweepBox(const HmmDev& h, const VRegion& R, bool hasNext, W
 		const int i = R.i0 - 1 + r;
 		Cell c;
 		c.M = c.I = c.D = INFINITY;
-		if (R.j0 - 1 == 0) c.M = c.I = col0M(i, w.cNN, w.cNB);
+		if (R.j0 - 1 == 0) c.M = c.I = col0M(i, w.q.cNN, w.q.cNB);
 		else if (r == 0) c = w.win[0];
 		else if (r == 1) c = w.win[2];
 		w.bnd[r] = c.M; w.bnd[w.bndPitch + r] = c.I; w.bnd[2 * w.bndPitch + r] = c.D;
@@ -75,14 +146,8 @@ __device__ long long sweepBox(const HmmDev& h, const VRegion& R, bool hasNext, W
 		const int ncols = min(32, R.j1 - jb + 1);
 		const bool colOn = lane < ncols;
 		const int jj = colOn ? j : R.j1; // clamp for loads
-		// per-column parameters (Tmat_cost[j-1] and [j], emissions, entry, exit)
-		const double tMMp = __ldg(h.tr + T_MM * Kp + jj - 1), tIMp = __ldg(h.tr + T_IM * Kp + jj - 1), tDMp = __ldg(h.tr + T_DM * Kp + jj - 1);
-		const double tMDp = __ldg(h.tr + T_MD * Kp + jj - 1), tDDp = __ldg(h.tr + T_DD * Kp + jj - 1);
-		const double tMI = __ldg(h.tr + T_MI * Kp + jj), tII = __ldg(h.tr + T_II * Kp + jj), tIMj = __ldg(h.tr + T_IM * Kp + jj);
-		const double ent = __ldg(h.ent + jj), ext = __ldg(h.ext + jj);
-		const double eM0 = __ldg(h.eM + jj), eM1 = __ldg(h.eM + Kp + jj), eM2 = __ldg(h.eM + 2 * Kp + jj), eM3 = __ldg(h.eM + 3 * Kp + jj);
-		const double eI0 = __ldg(h.eI + jj), eI1 = __ldg(h.eI + Kp + jj), eI2 = __ldg(h.eI + 2 * Kp + jj), eI3 = __ldg(h.eI + 3 * Kp + jj);
-		const bool dOn = jj > 1 && jj < K;
+		ColParams cp;
+		loadCol(h, jj, cp);
 		// state: cur = (i-1, j) own column; diag = (i-1, j-1)
 		double curM = INFINITY, curI = INFINITY, curD = INFINITY;
 		if (s == 0 && lane == 0) { curM = top0.M; curI = top0.I; curD = top0.D; }
@@ -111,48 +176,10 @@ __device__ long long sweepBox(const HmmDev& h, const VRegion& R, bool hasNext, W
 				double nM = INFINITY, nI = INFINITY, nD = INFINITY;
 				uint32_t code = 0;
 				if (pred) {
-					const int b = w.x[i - 1];
-					const double eM = (b & 2) ? ((b & 1) ? eM3 : eM2) : ((b & 1) ? eM1 : eM0);
-					const double eI = (b & 2) ? ((b & 1) ? eI3 : eI2) : ((b & 1) ? eI1 : eI0);
-					// DP_M: src/BandedHMMP7.cpp:812-819 (useB) / :866-872 (downstream, no B)
-					const double cB = col0M(i, w.cNN, w.cNB) + ent;
-					const double cM = dgM + tMMp, cI = dgI + tIMp, cD = dgD + tDMp;
-					double m3 = fmin(cM, fmin(cI, cD));
-					nM = eM + (R.useB ? fmin(cB, m3) : m3);
-					// trace candidates (src/BandedHMMP7.cpp:962-971): always with B; only B and I at j == 1
-					uint32_t pm = 0;
-					if (j > 1) {
-						double mn = cB;
-						if (cM < mn) { mn = cM; pm = 1; }
-						if (cI < mn) { mn = cI; pm = 2; }
-						if (cD < mn) { pm = 3; }
-					} else
-						pm = (cI < cB) ? 2 : 0;
-					// DP_I: :820-822
-					const double iM = curM + tMI, iI = curI + tII;
-					nI = eI + fmin(iM, iI);
-					const uint32_t pi = iI < iM ? 1 : 0;
-					// DP_D: :823-825 (only 1 < j < K)
-					uint32_t pd = 0;
-					if (dOn) {
-						const double dM = lM + tMDp, dD = lD + tDDp;
-						nD = fmin(dM, dD);
-						pd = dD < dM ? 1 : 0;
-					}
-					code = pm | (pi << 2) | (pd << 3);
+					// the end corner is recomputed by the next box: its S candidate is taken there
+					code = cellUpdate(cp, w.q, w.x[i - 1], i, j, R.useB != 0, !(hasNext && i == R.i1 && j == R.j1),
+							dgM, dgI, dgD, curM, curI, lM, lD, nM, nI, nD, best);
 					cells++;
-					// S (src/BandedHMMP7.cpp:883-891); the end corner is recomputed by the next box
-					if (!(hasNext && i == R.i1 && j == R.j1)) {
-						const double rowPen = i < w.N ? w.cCC * (double) (w.N - i) : 0.0;
-						double sv = (nM + ext) + w.cEC;
-						if (i < w.N) sv += rowPen;
-						if (better(sv, j, i, best)) { best.v = sv; best.j = j; best.i = i; }
-						if (j == K) {
-							double s2 = (nI + tIMj) + w.cEC;
-							if (i < w.N) s2 += rowPen;
-							if (better(s2, K + 1, i, best)) { best.v = s2; best.j = K + 1; best.i = i; }
-						}
-					}
 				}
 				acc |= code << (4 * ((i - R.i0) & 7));
 				if (((i - R.i0) & 7) == 7 || i == R.i1) {
@@ -190,7 +217,7 @@ __device__ __forceinline__ void initWindow(WarpCtx& w, int i0, int j0) {
 		const int ci = i0 - 1 + a, cj = j0 - 1 + b;
 		Cell c;
 		c.M = c.I = c.D = INFINITY;
-		if (cj == 0) c.M = c.I = col0M(ci, w.cNN, w.cNB);
+		if (cj == 0) c.M = c.I = col0M(ci, w.q.cNN, w.q.cNB);
 		w.win[lane] = c;
 	}
 	w.ic = i0; w.jc = j0;
@@ -260,8 +287,8 @@ __device__ void finishSeq(const HmmDev& h, const VRegion* regs, int nReg, const 
 				const uint32_t c = (ptrAt(regs, nReg, ptrBase, i, j) >> 2) & 1u;
 				s = c ? 'I' : 'M';
 			} else { // column 0: whichMin(DP_M(i,0)+T[0](M,I), DP_I(i-1,0)+T[0](I,I)) in "BI"
-				const double a = col0M(i, w.cNN, w.cNB) + __ldg(h.tr + T_MI * h.Kp);
-				const double b = col0M(i - 1, w.cNN, w.cNB) + __ldg(h.tr + T_II * h.Kp);
+				const double a = col0M(i, w.q.cNN, w.q.cNB) + __ldg(h.tr + T_MI * h.Kp);
+				const double b = col0M(i - 1, w.q.cNN, w.q.cNB) + __ldg(h.tr + T_II * h.Kp);
 				s = b < a ? 'I' : 'B';
 			}
 			i--;
@@ -364,8 +391,9 @@ __global__ void __launch_bounds__(HU_VIT_WARPS * 32) viterbiBandedKernel(HmmDev 
 	if (lane < plan.nReg) sm.regs[lane] = plan.reg[lane];
 	__syncwarp();
 	WarpCtx w;
-	w.x = sm.codes; w.N = N;
-	w.cNN = a.cNN; w.cNB = a.cNB; w.cEC = a.cEC; w.cCC = a.cCC;
+	w.x = sm.codes;
+	w.q.N = N; w.q.K = h.K; w.q.cNN = a.cNN; w.q.cNB = a.cNB; w.q.cEC = a.cEC; w.q.cCC = a.cCC;
+	w.q.sAllRows = a.cCC < INFINITY;
 	w.bnd = sm.bnd; w.bndPitch = a.maxLen + 2;
 	w.win = sm.win; w.winNew = sm.winNew;
 	initWindow(w, sm.regs[0].i0, sm.regs[0].j0);
@@ -395,43 +423,111 @@ __global__ void __launch_bounds__(HU_VIT_WARPS * 32) viterbiBandedKernel(HmmDev 
 	finishSeq(h, sm.regs, plan.nReg, a.ptrs, w, best, cells, plan.flags, gx, a.traces + plan.traceOff, arow, a.rows + seq);
 }
 
-// Pass 2: full Viterbi (src/BandedHMMP7.cpp:748-780) for the queued sequences; persistent warps, each with
-// its own N x K back-pointer slab.
+// Pass 2: full Viterbi (src/BandedHMMP7.cpp:748-780) for the queued sequences.  One CTA per sequence, persistent:
+// the 32-column stripes of the N x K matrix are dealt round-robin to the warps, which run as a software
+// pipeline -- stripe s+1 trails stripe s by one warp-width of rows, the last column of a stripe travels
+// through a ring of shared-memory buffers, a per-stripe progress counter orders the hand-over.  Same cell
+// code as the banded pass (cellUpdate), so costs and back-pointers are bit-identical to a single-warp sweep.
+__host__ __device__ inline size_t viterbiFullSmem(int maxLen, int nW) {
+	return ((size_t) maxLen + 15) / 16 * 16 + (size_t) nW * 3 * (maxLen + 2) * sizeof(double) + 2048 * sizeof(int) +
+			(size_t) nW * (sizeof(Best) + sizeof(long long)) + sizeof(VRegion) + 64;
+}
+
 __global__ void __launch_bounds__(HU_VIT_WARPS * 32) viterbiFullKernel(HmmDev h, VitArgs a) {
 	extern __shared__ __align__(16) unsigned char smemRaw[];
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	const int slot = blockIdx.x * a.warpsPerBlock + warp;
-	WarpSmem sm = carve(smemRaw + (size_t) warp * ((viterbiWarpSmem(a.maxLen) + 15) / 16 * 16), a.maxLen);
+	const int nW = blockDim.x >> 5;
+	const int pitch = a.maxLen + 2;
+	double* bndAll = reinterpret_cast<double*>(smemRaw);
+	volatile int* progress = reinterpret_cast<volatile int*>(bndAll + (size_t) nW * 3 * pitch);
+	Best* wBest = reinterpret_cast<Best*>(const_cast<int*>(progress) + 2048);
+	long long* wCells = reinterpret_cast<long long*>(wBest + nW);
+	VRegion* reg = reinterpret_cast<VRegion*>(wCells + nW);
+	int* sIdx = reinterpret_cast<int*>(reg + 1);
+	int8_t* codes = reinterpret_cast<int8_t*>(sIdx + 4);
 	const int count = *a.fullCount;
-	uint32_t* slab = a.fullPtrs + (size_t) slot * a.fullSlabWords;
+	uint32_t* slab = a.fullPtrs + (size_t) blockIdx.x * a.fullSlabWords;
+	const int K = h.K;
+	const int nStripes = (K + 31) / 32;
 	for (;;) {
-		int idx = 0;
-		if (lane == 0) idx = atomicAdd(a.fullCursor, 1);
-		idx = __shfl_sync(0xffffffffu, idx, 0);
+		__syncthreads();
+		if (threadIdx.x == 0) *sIdx = atomicAdd(a.fullCursor, 1);
+		__syncthreads();
+		const int idx = *sIdx;
 		if (idx >= count) return;
 		const int seq = a.fullList[idx];
 		const VPlan& plan = a.plans[seq];
 		const int N = plan.N;
 		const int8_t* gx = a.codes + plan.codeOff;
-		__syncwarp();
-		for (int i = lane; i < N; i += 32) sm.codes[i] = gx[i];
-		if (lane == 0) {
+		for (int i = threadIdx.x; i < N; i += blockDim.x) codes[i] = gx[i];
+		for (int i = threadIdx.x; i < nStripes; i += blockDim.x) progress[i] = 0;
+		if (threadIdx.x == 0) {
 			VRegion R;
-			R.j0 = 1; R.j1 = h.K; R.i0 = 1; R.i1 = N;
+			R.j0 = 1; R.j1 = K; R.i0 = 1; R.i1 = N;
 			R.strip = 0; R.pStart = R.pFrom = R.nIns = R.nDel = 0; R.useB = 1;
-			R.rowWords = (N + 7) / 8;
+			R.rowWords = (N + 7) / 8; R.pad = 0;
 			R.ptrOff = 0;
-			sm.regs[0] = R;
+			*reg = R;
 		}
-		__syncwarp();
-		WarpCtx w;
-		w.x = sm.codes; w.N = N;
-		w.cNN = a.cNN; w.cNB = a.cNB; w.cEC = a.cEC; w.cCC = a.cCC;
-		w.bnd = sm.bnd; w.bndPitch = a.maxLen + 2;
-		w.win = sm.win; w.winNew = sm.winNew;
-		initWindow(w, 1, 1);
+		__syncthreads();
+		SeqConst q;
+		q.N = N; q.K = K; q.cNN = a.cNN; q.cNB = a.cNB; q.cEC = a.cEC; q.cCC = a.cCC;
+		q.sAllRows = a.cCC < INFINITY;
+		const int rowWords = (N + 7) / 8;
 		Best best; best.v = INFINITY; best.j = 0x7fffffff; best.i = 0x7fffffff;
-		long long cells = sweepBox(h, sm.regs[0], false, w, slab, best);
+		long long cells = 0;
+		for (int s = warp; s < nStripes; s += nW) {
+			const int jb = 1 + 32 * s;
+			const int j = jb + lane;
+			const int ncols = min(32, K - jb + 1);
+			const bool colOn = lane < ncols;
+			const int jj = colOn ? j : K;
+			ColParams cp;
+			loadCol(h, jj, cp);
+			const double* in = bndAll + (size_t) ((s + nW - 1) % nW) * 3 * pitch; // written by stripe s-1
+			double* out = bndAll + (size_t) (s % nW) * 3 * pitch;
+			double curM = INFINITY, curI = INFINITY, curD = INFINITY; // row 0
+			double dgM = INFINITY, dgI = INFINITY, dgD = INFINITY;    // (0, jb-1)
+			uint32_t acc = 0;
+			uint32_t* ptrCol = slab + (long long) (jj - 1) * rowWords;
+			const int steps = N + ncols - 1;
+			for (int t = 0; t < steps; ++t) {
+				const int i = 1 + t - lane;
+				if (s > 0) { // lane 0 needs row t+1 of the previous stripe's last column
+					const int need = min(t + 1, N);
+					while (progress[s - 1] < need) { }
+					__threadfence_block();
+				}
+				double lM = __shfl_up_sync(0xffffffffu, curM, 1);
+				double lI = __shfl_up_sync(0xffffffffu, curI, 1);
+				double lD = __shfl_up_sync(0xffffffffu, curD, 1);
+				if (lane == 0) {
+					if (i <= N) {
+						if (s == 0) { lM = lI = col0M(i, q.cNN, q.cNB); lD = INFINITY; }
+						else { lM = in[i]; lI = in[pitch + i]; lD = in[2 * pitch + i]; }
+					} else
+						lM = lI = lD = INFINITY;
+				}
+				const bool on = colOn && i >= 1 && i <= N;
+				if (on) {
+					double nM, nI, nD;
+					const uint32_t code = cellUpdate(cp, q, codes[i - 1], i, j, true, true, dgM, dgI, dgD, curM, curI, lM, lD, nM, nI, nD, best);
+					cells++;
+					acc |= code << (4 * ((i - 1) & 7));
+					if (((i - 1) & 7) == 7 || i == N) {
+						ptrCol[(i - 1) >> 3] = acc;
+						acc = 0;
+					}
+					if (lane == 31) {
+						out[i] = nM; out[pitch + i] = nI; out[2 * pitch + i] = nD;
+						__threadfence_block();
+						progress[s] = i;
+					}
+					curM = nM; curI = nI; curD = nD;
+				}
+				dgM = lM; dgI = lI; dgD = lD;
+			}
+		}
 		for (int o = 16; o > 0; o >>= 1) {
 			Best ob;
 			ob.v = __shfl_xor_sync(0xffffffffu, best.v, o);
@@ -440,12 +536,21 @@ __global__ void __launch_bounds__(HU_VIT_WARPS * 32) viterbiFullKernel(HmmDev h,
 			if (better(ob.v, ob.j, ob.i, best)) best = ob;
 			cells += __shfl_xor_sync(0xffffffffu, cells, o);
 		}
-		__syncwarp();
-		int8_t* arow = a.aligned ? a.aligned + (size_t) seq * h.L : NULL;
-		const int flags = a.rows[seq].flags;
-		const long long prior = a.rows[seq].cells;
-		finishSeq(h, sm.regs, 1, slab, w, best, cells + prior, flags, gx, a.traces + plan.traceOff, arow, a.rows + seq);
-		__syncwarp();
+		if (lane == 0) { wBest[warp] = best; wCells[warp] = cells; }
+		__syncthreads();
+		if (warp == 0) {
+			for (int k = 1; k < nW; ++k) {
+				if (better(wBest[k].v, wBest[k].j, wBest[k].i, best)) best = wBest[k];
+				cells += wCells[k];
+			}
+			WarpCtx w;
+			w.x = codes; w.q = q;
+			w.bnd = NULL; w.bndPitch = 0; w.win = NULL; w.winNew = NULL; w.ic = w.jc = 0;
+			int8_t* arow = a.aligned ? a.aligned + (size_t) seq * h.L : NULL;
+			const int flags = a.rows[seq].flags;
+			const long long prior = a.rows[seq].cells;
+			finishSeq(h, reg, 1, slab, w, best, cells + prior, flags, gx, a.traces + plan.traceOff, arow, a.rows + seq);
+		}
 	}
 }
 
@@ -504,13 +609,18 @@ int launchViterbi(hu_batch* b, int mode) {
 	static size_t attrSet = 0;
 	if (smem > attrSet) {
 		HU_CUDA(cudaFuncSetAttribute(viterbiBandedKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-		HU_CUDA(cudaFuncSetAttribute(viterbiFullKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
 		attrSet = smem;
+	}
+	const size_t smemFull = viterbiFullSmem(a.maxLen, wpb);
+	static size_t attrFull = 0;
+	if (smemFull > attrFull) {
+		HU_CUDA(cudaFuncSetAttribute(viterbiFullKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smemFull));
+		attrFull = smemFull;
 	}
 	HU_CUDA(cudaMemsetAsync(a.fullCount, 0, 2 * sizeof(int), b->stream)); // count + cursor
 	HU_CUDA(cudaMemsetAsync(a.aligned, HU_CODE_PAD & 0xff, (size_t) nSeq * h.L, b->stream));
 	viterbiBandedKernel<<<(nSeq + wpb - 1) / wpb, wpb * 32, smem, b->stream>>>(h, a);
-	viterbiFullKernel<<<b->fullSlots / wpb, wpb * 32, smem, b->stream>>>(h, a);
+	viterbiFullKernel<<<b->fullSlots, wpb * 32, smemFull, b->stream>>>(h, a);
 	b->launches += 2;
 	if (b->paired) {
 		mergeMatesKernel<<<b->nReads, 128, 0, b->stream>>>(b->nReads, h.L, a.rows, b->merged, a.aligned);
