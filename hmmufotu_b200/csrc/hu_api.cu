@@ -156,7 +156,7 @@ int hu_batch_create(hu_batch** out, hu_db* db, int32_t maxReads, int32_t maxSeqL
 	HU_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, db->device));
 	// Viterbi CTA shape: as many warps as the per-warp shared memory allows
 	int wpb = HU_VIT_WARPS;
-	const size_t perWarp = ((size_t) (maxSeqLen + 15) / 16 * 16 + (size_t) 3 * (maxSeqLen + 2) * 8 + 8 * 24 + 5 * sizeof(VRegion) + 16 + 15) / 16 * 16;
+	const size_t perWarp = ((size_t) (maxSeqLen + 15) / 16 * 16 + (size_t) 3 * (maxSeqLen + 2) * 8 + 320 * 8 + 8 * 24 + 5 * sizeof(VRegion) + 16 + 15) / 16 * 16;
 	while (wpb > 1 && perWarp * wpb > 200 * 1024) wpb >>= 1;
 	if (perWarp > 200 * 1024) { setError("maxSeqLen %d too long for the Viterbi shared-memory layout", maxSeqLen); return HU_ERR_ARG; }
 	b->vit.warpsPerBlock = wpb;

@@ -51,54 +51,66 @@ struct SeqConst { // per-sequence constants of the special states (setSequenceMo
 	int N, K;
 	double cNN, cNB, cEC, cCC;
 	bool sAllRows; // cCC finite: rows i < N can hold the minimum of S (NGCL / LOCAL); GLOBAL: only row N
+	bool nnInf;    // T_SP(N,N) = 0 (GLOBAL / NGCL): the begin state is reachable from read position 1 only
 };
+__device__ __forceinline__ void setSeqConst(SeqConst& q, int N, int K, double cNN, double cNB, double cEC, double cCC) {
+	q.N = N; q.K = K; q.cNN = cNN; q.cNB = cNB; q.cEC = cEC; q.cCC = cCC;
+	q.sAllRows = cCC < INFINITY;
+	q.nnInf = !(cNN < INFINITY);
+}
+// DP_M(i,0) + entry cost: the B candidate of cell (i, j)
+__device__ __forceinline__ double entryCand(const SeqConst& q, int i, double ent) {
+	if (q.nnInf) return i == 1 ? (0.0 + q.cNB) + ent : INFINITY;
+	return col0M(i, q.cNN, q.cNB) + ent;
+}
+// emission tables of the lane's column in shared memory: [M|I][base 0..3, 4 = outside the band (+inf)][lane]
+__device__ __forceinline__ void storeEmis(double* emis, const ColParams& p, int lane) {
+	emis[0 * 32 + lane] = p.eM0; emis[1 * 32 + lane] = p.eM1; emis[2 * 32 + lane] = p.eM2; emis[3 * 32 + lane] = p.eM3;
+	emis[4 * 32 + lane] = INFINITY;
+	emis[5 * 32 + lane] = p.eI0; emis[6 * 32 + lane] = p.eI1; emis[7 * 32 + lane] = p.eI2; emis[8 * 32 + lane] = p.eI3;
+	emis[9 * 32 + lane] = INFINITY;
+}
 
-// One cell (i, j): DP_M / DP_I / DP_D (src/BandedHMMP7.cpp:812-825), its 4-bit back-pointer and the S candidate.
-// diag = (i-1,j-1), up = (i-1,j), left = (i,j-1).  Returns the pointer code.
-__device__ __forceinline__ uint32_t cellUpdate(const ColParams& p, const SeqConst& q, int b, int i, int j, bool useB, bool trackS,
+// One cell (i, j): DP_M / DP_I / DP_D (src/BandedHMMP7.cpp:812-825) and its 4-bit back-pointer.
+// diag = (i-1,j-1), up = (i-1,j), left = (i,j-1).  eM / eI are the emission costs of the read base (+inf for a
+// cell outside the band, which therefore comes out as +inf like the reference's untouched matrix entries).
+template <bool USE_B>
+__device__ __forceinline__ uint32_t cellUpdate(const ColParams& p, double cB, double eM, double eI, bool first, bool dOk,
 		double dgM, double dgI, double dgD, double upM, double upI, double lM, double lD,
-		double& nM, double& nI, double& nD, Best& best) {
-	const double eM = (b & 2) ? ((b & 1) ? p.eM3 : p.eM2) : ((b & 1) ? p.eM1 : p.eM0);
-	const double eI = (b & 2) ? ((b & 1) ? p.eI3 : p.eI2) : ((b & 1) ? p.eI1 : p.eI0);
-	// DP_M: useB at :812-819, no B in the downstream box :866-872
-	const double cB = col0M(i, q.cNN, q.cNB) + p.ent;
+		double& nM, double& nI, double& nD) {
+	// candidates of DP_M; the trace (src/BandedHMMP7.cpp:962-971) always ranks B too, and only B and I at j == 1
 	const double cM = dgM + p.tMMp, cI = dgI + p.tIMp, cD = dgD + p.tDMp;
-	const double m3 = fmin(cM, fmin(cI, cD));
-	nM = eM + (useB ? fmin(cB, m3) : m3);
-	// trace candidates (src/BandedHMMP7.cpp:962-971): always with B; only B and I at j == 1
+	double mn = cB;
 	uint32_t pm = 0;
-	if (j > 1) {
-		double mn = cB;
-		if (cM < mn) { mn = cM; pm = 1; }
-		if (cI < mn) { mn = cI; pm = 2; }
-		if (cD < mn) { pm = 3; }
-	} else
-		pm = (cI < cB) ? 2 : 0;
+	if (cM < mn) { mn = cM; pm = 1; }
+	if (cI < mn) { mn = cI; pm = 2; }
+	if (cD < mn) { mn = cD; pm = 3; }
+	if (first) pm = (cI < cB) ? 2 : 0;
+	// useB at :812-819; no B in the downstream box :866-872
+	nM = eM + (USE_B ? mn : fmin(cM, fmin(cI, cD)));
 	// DP_I: :820-822
 	const double iM = upM + p.tMI, iI = upI + p.tII;
-	nI = eI + fmin(iM, iI);
-	const uint32_t pi = iI < iM ? 1 : 0;
+	const bool pi = iI < iM;
+	nI = eI + (pi ? iI : iM);
 	// DP_D: :823-825 (only 1 < j < K)
-	uint32_t pd = 0;
-	nD = INFINITY;
-	if (p.dOn) {
-		const double dM = lM + p.tMDp, dD = lD + p.tDDp;
-		nD = fmin(dM, dD);
-		pd = dD < dM ? 1 : 0;
+	const double dM = lM + p.tMDp, dD = lD + p.tDDp;
+	const bool pd = dD < dM;
+	nD = dOk ? (pd ? dD : dM) : INFINITY;
+	return pm | ((uint32_t) pi << 2) | ((uint32_t) (pd && dOk) << 3);
+}
+
+// S(i,j) = DP_M(i,j) + exit(j) (+ the I_K -> E column) + special-state costs (src/BandedHMMP7.cpp:883-891);
+// only rows that can hold a finite S are visited (row N alone when T_SP(C,C) = 0, i.e. GLOBAL)
+__device__ __forceinline__ void cellScore(const ColParams& p, const SeqConst& q, int i, int j, double nM, double nI, Best& best) {
+	const double rowPen = i < q.N ? q.cCC * (double) (q.N - i) : 0.0;
+	double sv = (nM + p.ext) + q.cEC;
+	if (i < q.N) sv += rowPen;
+	if (better(sv, j, i, best)) { best.v = sv; best.j = j; best.i = i; }
+	if (j == q.K) {
+		double s2 = (nI + p.tIMj) + q.cEC;
+		if (i < q.N) s2 += rowPen;
+		if (better(s2, q.K + 1, i, best)) { best.v = s2; best.j = q.K + 1; best.i = i; }
 	}
-	// S (src/BandedHMMP7.cpp:883-891)
-	if (trackS && (i == q.N || q.sAllRows)) {
-		const double rowPen = i < q.N ? q.cCC * (double) (q.N - i) : 0.0;
-		double sv = (nM + p.ext) + q.cEC;
-		if (i < q.N) sv += rowPen;
-		if (better(sv, j, i, best)) { best.v = sv; best.j = j; best.i = i; }
-		if (j == q.K) {
-			double s2 = (nI + p.tIMj) + q.cEC;
-			if (i < q.N) s2 += rowPen;
-			if (better(s2, q.K + 1, i, best)) { best.v = s2; best.j = q.K + 1; best.i = i; }
-		}
-	}
-	return pm | (pi << 2) | (pd << 3);
 }
 
 struct WarpCtx {
@@ -106,14 +118,17 @@ struct WarpCtx {
 	SeqConst q;
 	double* bnd;       // shared: [3][bndPitch]
 	int bndPitch;
+	double* emis;      // shared: [2][5][32] emission tables of the current stripe
 	Cell* win;         // shared: 2x2 window around the current chain corner, [a*2+b] = cell (ic-1+a, jc-1+b)
 	Cell* winNew;      // shared: window being captured around the end corner of the running box
 	int ic, jc;        // chain corner of win
 };
 
 // Sweep one box.  Returns the number of cell updates.
-__device__ long long sweepBox(const HmmDev& h, const VRegion& R, bool hasNext, WarpCtx& w, uint32_t* __restrict__ ptrBase, Best& best) {
+__device__ long long sweepBox(const HmmDev& h, const VRegion& Rsm, bool hasNext, WarpCtx& wsm, uint32_t* __restrict__ ptrBase, Best& best) {
 	const int lane = threadIdx.x & 31;
+	const VRegion R = Rsm; // registers: the box lives in shared memory, which the loop below also writes
+	WarpCtx w = wsm;
 	const int rows = R.i1 - R.i0 + 1, cols = R.j1 - R.j0 + 1;
 	long long cells = 0;
 	// ---- window around the end corner: start from what is known before this box ----
@@ -148,6 +163,9 @@ __device__ long long sweepBox(const HmmDev& h, const VRegion& R, bool hasNext, W
 		const int jj = colOn ? j : R.j1; // clamp for loads
 		ColParams cp;
 		loadCol(h, jj, cp);
+		__syncwarp();
+		storeEmis(w.emis, cp, lane);
+		__syncwarp();
 		// state: cur = (i-1, j) own column; diag = (i-1, j-1)
 		double curM = INFINITY, curI = INFINITY, curD = INFINITY;
 		if (s == 0 && lane == 0) { curM = top0.M; curI = top0.I; curD = top0.D; }
@@ -166,21 +184,25 @@ __device__ long long sweepBox(const HmmDev& h, const VRegion& R, bool hasNext, W
 				if (r <= rows) { lM = w.bnd[r]; lI = w.bnd[w.bndPitch + r]; lD = w.bnd[2 * w.bndPitch + r]; }
 				else lM = lI = lD = INFINITY;
 			}
-			const bool on = colOn && i >= R.i0 && i <= R.i1;
+			const bool on = colOn && (unsigned) (i - R.i0) < (unsigned) rows;
+			bool pred = on;
+			if (R.strip) {
+				const int d = (i - R.pFrom) - (j - R.pStart);
+				pred = on && d <= R.nIns && d >= -R.nDel;
+			}
+			// straight-line cell update: a lane outside the band looks up the +inf emission row, so its cell
+			// comes out +inf like an untouched entry of the reference's matrices
+			const int ic = min(max(i, 1), w.q.N);
+			const int bb = pred ? (int) w.x[ic - 1] : 4;
+			const double eM = w.emis[bb * 32 + lane], eI = w.emis[(5 + bb) * 32 + lane];
+			const double cB = entryCand(w.q, i, cp.ent);
+			double nM, nI, nD;
+			uint32_t code = R.useB ? cellUpdate<true>(cp, cB, eM, eI, j == 1, cp.dOn && pred, dgM, dgI, dgD, curM, curI, lM, lD, nM, nI, nD)
+			                       : cellUpdate<false>(cp, cB, eM, eI, j == 1, cp.dOn && pred, dgM, dgI, dgD, curM, curI, lM, lD, nM, nI, nD);
+			cells += pred;
+			// the end corner is recomputed by the next box: its S candidate is taken there
+			if (pred && (i == w.q.N || w.q.sAllRows) && !(hasNext && i == R.i1 && j == R.j1)) cellScore(cp, w.q, i, j, nM, nI, best);
 			if (on) {
-				bool pred = true;
-				if (R.strip) {
-					const int d = (i - R.pFrom) - (j - R.pStart);
-					pred = d <= R.nIns && d >= -R.nDel;
-				}
-				double nM = INFINITY, nI = INFINITY, nD = INFINITY;
-				uint32_t code = 0;
-				if (pred) {
-					// the end corner is recomputed by the next box: its S candidate is taken there
-					code = cellUpdate(cp, w.q, w.x[i - 1], i, j, R.useB != 0, !(hasNext && i == R.i1 && j == R.j1),
-							dgM, dgI, dgD, curM, curI, lM, lD, nM, nI, nD, best);
-					cells++;
-				}
 				acc |= code << (4 * ((i - R.i0) & 7));
 				if (((i - R.i0) & 7) == 7 || i == R.i1) {
 					ptrCol[(i - R.i0) >> 3] = acc;
@@ -205,7 +227,7 @@ __device__ long long sweepBox(const HmmDev& h, const VRegion& R, bool hasNext, W
 	// commit the window
 	__syncwarp();
 	if (lane < 4) w.win[lane] = w.winNew[lane];
-	w.ic = R.i1; w.jc = R.j1;
+	wsm.ic = R.i1; wsm.jc = R.j1;
 	__syncwarp();
 	return cells;
 }
@@ -345,12 +367,13 @@ __device__ void finishSeq(const HmmDev& h, const VRegion* regs, int nReg, const 
 // smem per warp: codes (maxLen, padded to 8) | bnd 3*(maxLen+2) doubles | win 4 cells | winNew 4 cells | regions
 __host__ __device__ inline size_t viterbiWarpSmem(int maxLen) {
 	const size_t codes = ((size_t) maxLen + 15) / 16 * 16;
-	return codes + (size_t) 3 * (maxLen + 2) * sizeof(double) + 8 * sizeof(Cell) + 5 * sizeof(VRegion) + 16;
+	return codes + (size_t) 3 * (maxLen + 2) * sizeof(double) + 320 * sizeof(double) + 8 * sizeof(Cell) + 5 * sizeof(VRegion) + 16;
 }
 
 struct WarpSmem {
 	int8_t* codes;
 	double* bnd;
+	double* emis;
 	Cell* win;
 	Cell* winNew;
 	VRegion* regs;
@@ -359,7 +382,8 @@ __device__ __forceinline__ WarpSmem carve(unsigned char* base, int maxLen) {
 	WarpSmem s;
 	const size_t codes = ((size_t) maxLen + 15) / 16 * 16;
 	s.bnd = reinterpret_cast<double*>(base);
-	s.win = reinterpret_cast<Cell*>(s.bnd + 3 * (maxLen + 2));
+	s.emis = s.bnd + 3 * (maxLen + 2);
+	s.win = reinterpret_cast<Cell*>(s.emis + 320);
 	s.winNew = s.win + 4;
 	s.regs = reinterpret_cast<VRegion*>(s.winNew + 4);
 	s.codes = reinterpret_cast<int8_t*>(s.regs + 5);
@@ -392,9 +416,8 @@ __global__ void __launch_bounds__(HU_VIT_WARPS * 32) viterbiBandedKernel(HmmDev 
 	__syncwarp();
 	WarpCtx w;
 	w.x = sm.codes;
-	w.q.N = N; w.q.K = h.K; w.q.cNN = a.cNN; w.q.cNB = a.cNB; w.q.cEC = a.cEC; w.q.cCC = a.cCC;
-	w.q.sAllRows = a.cCC < INFINITY;
-	w.bnd = sm.bnd; w.bndPitch = a.maxLen + 2;
+	setSeqConst(w.q, N, h.K, a.cNN, a.cNB, a.cEC, a.cCC);
+	w.bnd = sm.bnd; w.bndPitch = a.maxLen + 2; w.emis = sm.emis;
 	w.win = sm.win; w.winNew = sm.winNew;
 	initWindow(w, sm.regs[0].i0, sm.regs[0].j0);
 	Best best; best.v = INFINITY; best.j = 0x7fffffff; best.i = 0x7fffffff;
@@ -429,7 +452,7 @@ __global__ void __launch_bounds__(HU_VIT_WARPS * 32) viterbiBandedKernel(HmmDev 
 // through a ring of shared-memory buffers, a per-stripe progress counter orders the hand-over.  Same cell
 // code as the banded pass (cellUpdate), so costs and back-pointers are bit-identical to a single-warp sweep.
 __host__ __device__ inline size_t viterbiFullSmem(int maxLen, int nW) {
-	return ((size_t) maxLen + 15) / 16 * 16 + (size_t) nW * 3 * (maxLen + 2) * sizeof(double) + 2048 * sizeof(int) +
+	return ((size_t) maxLen + 15) / 16 * 16 + (size_t) nW * (3 * (maxLen + 2) + 320) * sizeof(double) + 2048 * sizeof(int) +
 			(size_t) nW * (sizeof(Best) + sizeof(long long)) + sizeof(VRegion) + 64;
 }
 
@@ -439,7 +462,8 @@ __global__ void __launch_bounds__(HU_VIT_WARPS * 32) viterbiFullKernel(HmmDev h,
 	const int nW = blockDim.x >> 5;
 	const int pitch = a.maxLen + 2;
 	double* bndAll = reinterpret_cast<double*>(smemRaw);
-	volatile int* progress = reinterpret_cast<volatile int*>(bndAll + (size_t) nW * 3 * pitch);
+	double* emis = bndAll + (size_t) nW * 3 * pitch + (size_t) warp * 320;
+	volatile int* progress = reinterpret_cast<volatile int*>(bndAll + (size_t) nW * (3 * pitch + 320));
 	Best* wBest = reinterpret_cast<Best*>(const_cast<int*>(progress) + 2048);
 	long long* wCells = reinterpret_cast<long long*>(wBest + nW);
 	VRegion* reg = reinterpret_cast<VRegion*>(wCells + nW);
@@ -471,8 +495,7 @@ __global__ void __launch_bounds__(HU_VIT_WARPS * 32) viterbiFullKernel(HmmDev h,
 		}
 		__syncthreads();
 		SeqConst q;
-		q.N = N; q.K = K; q.cNN = a.cNN; q.cNB = a.cNB; q.cEC = a.cEC; q.cCC = a.cCC;
-		q.sAllRows = a.cCC < INFINITY;
+		setSeqConst(q, N, K, a.cNN, a.cNB, a.cEC, a.cCC);
 		const int rowWords = (N + 7) / 8;
 		Best best; best.v = INFINITY; best.j = 0x7fffffff; best.i = 0x7fffffff;
 		long long cells = 0;
@@ -484,6 +507,9 @@ __global__ void __launch_bounds__(HU_VIT_WARPS * 32) viterbiFullKernel(HmmDev h,
 			const int jj = colOn ? j : K;
 			ColParams cp;
 			loadCol(h, jj, cp);
+			__syncwarp();
+			storeEmis(emis, cp, lane);
+			__syncwarp();
 			const double* in = bndAll + (size_t) ((s + nW - 1) % nW) * 3 * pitch; // written by stripe s-1
 			double* out = bndAll + (size_t) (s % nW) * 3 * pitch;
 			double curM = INFINITY, curI = INFINITY, curD = INFINITY; // row 0
@@ -511,7 +537,10 @@ __global__ void __launch_bounds__(HU_VIT_WARPS * 32) viterbiFullKernel(HmmDev h,
 				const bool on = colOn && i >= 1 && i <= N;
 				if (on) {
 					double nM, nI, nD;
-					const uint32_t code = cellUpdate(cp, q, codes[i - 1], i, j, true, true, dgM, dgI, dgD, curM, curI, lM, lD, nM, nI, nD, best);
+					const int bb = codes[i - 1];
+					const uint32_t code = cellUpdate<true>(cp, entryCand(q, i, cp.ent), emis[bb * 32 + lane], emis[(5 + bb) * 32 + lane], j == 1, cp.dOn,
+							dgM, dgI, dgD, curM, curI, lM, lD, nM, nI, nD);
+					if (i == N || q.sAllRows) cellScore(cp, q, i, j, nM, nI, best);
 					cells++;
 					acc |= code << (4 * ((i - 1) & 7));
 					if (((i - 1) & 7) == 7 || i == N) {
@@ -545,7 +574,7 @@ __global__ void __launch_bounds__(HU_VIT_WARPS * 32) viterbiFullKernel(HmmDev h,
 			}
 			WarpCtx w;
 			w.x = codes; w.q = q;
-			w.bnd = NULL; w.bndPitch = 0; w.win = NULL; w.winNew = NULL; w.ic = w.jc = 0;
+			w.bnd = NULL; w.bndPitch = 0; w.emis = NULL; w.win = NULL; w.winNew = NULL; w.ic = w.jc = 0;
 			int8_t* arow = a.aligned ? a.aligned + (size_t) seq * h.L : NULL;
 			const int flags = a.rows[seq].flags;
 			const long long prior = a.rows[seq].cells;
