@@ -15,7 +15,7 @@ namespace hu {
 #define HU_EST_WARPS 8
 
 struct EstArgs {
-	int nReads, maxNSeed, ctaCols, pad1;
+	int nReads, maxNSeed, pad0, pad1;
 	const int8_t* aligned;
 	const int* winStart;
 	const int* winEnd;
@@ -45,7 +45,6 @@ __global__ void __launch_bounds__(HU_EST_WARPS * 32) estimateKernel(EstArgs a, T
 		const int r = item / a.maxNSeed, s = item % a.maxNSeed;
 		if (a.winStart[r] < 0 || s >= a.nSeeds[r]) continue;
 		const int start = a.winStart[r], end = a.winEnd[r], W = end - start + 1;
-		if (W <= a.ctaCols) continue; // the register-resident CTA kernel takes these
 		const int u = a.seedIds[(size_t) r * HU_MAX_SEED + s];
 		const int v = t.parent[u];
 		const int8_t* x = a.aligned + (size_t) r * t.csLen + start;
@@ -134,164 +133,6 @@ __global__ void __launch_bounds__(HU_EST_WARPS * 32) estimateKernel(EstArgs a, T
 	}
 }
 
-// ---- register-resident variant: one CTA (8 warps) per item, windows up to HU_EST_CTA_COLS columns ----
-// Each thread owns up to 7 columns and keeps their g_j in registers between the two passes, so the message
-// windows are read from HBM exactly once (the warp kernel above re-reads them in pass 2, and with ~4 700
-// windows of ~110 KB in flight that second read misses L2).
-#define HU_EST_CTA_THREADS 256
-#define HU_EST_CTA_Q 7
-#define HU_EST_CTA_COLS (HU_EST_CTA_THREADS * HU_EST_CTA_Q)
-
-// P(t) by half a warp: lane l < 16 computes entry (l / 4, l % 4).  GTR only; other models have closed forms
-// that one lane evaluates.  half = 0: lanes 0..15, half = 1: lanes 16..31.
-__device__ __forceinline__ void modelPrHalfWarp(const Model& m, double t, double* P, int lane, int half) {
-	const int l = lane - 16 * half;
-	if (l < 0 || l >= 16) return;
-	if (m.type == HU_GTR) {
-		const int i = l >> 2, j = l & 3;
-		double s = (i == j) ? 1.0 : 0.0;
-		if (t != 0) {
-			s = 0;
-			for (int k = 0; k < 4; ++k) s += m.U[i * 4 + k] * exp(m.lambda[k] * t) * m.Ui[k * 4 + j];
-		}
-		P[l] = s;
-	} else if (l == 0)
-		modelPr(m, t, P);
-}
-
-__device__ __forceinline__ double ctaSumD(double v, double* red, int warp, int lane) {
-	for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-	__syncthreads();
-	if (lane == 0) red[warp] = v;
-	__syncthreads();
-	double s = red[0];
-	for (int w = 1; w < HU_EST_CTA_THREADS / 32; ++w) s += red[w];
-	return s;
-}
-__device__ __forceinline__ unsigned int ctaSumU(unsigned int v, unsigned int* red, int warp, int lane) {
-	for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-	__syncthreads();
-	if (lane == 0) red[warp] = v;
-	__syncthreads();
-	unsigned int s = red[0];
-	for (int w = 1; w < HU_EST_CTA_THREADS / 32; ++w) s += red[w];
-	return s;
-}
-
-__global__ void __launch_bounds__(HU_EST_CTA_THREADS, 2) estimateCtaKernel(EstArgs a, TreeDev t, Model m) {
-	__shared__ EstShared ws;
-	__shared__ double redD[HU_EST_CTA_THREADS / 32];
-	__shared__ unsigned int redU[2][HU_EST_CTA_THREADS / 32];
-	__shared__ int sItem;
-	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-	const int total = a.nReads * a.maxNSeed;
-	int piMax = 0;
-	for (int k = 1; k < 4; ++k) if (m.logPi[k] > m.logPi[piMax]) piMax = k;
-	for (;;) {
-		__syncthreads();
-		if (tid == 0) sItem = atomicAdd(a.cursor + 2, 1);
-		__syncthreads();
-		const int item = sItem;
-		if (item >= total) return;
-		const int r = item / a.maxNSeed, s = item % a.maxNSeed;
-		if (a.winStart[r] < 0 || s >= a.nSeeds[r]) continue;
-		const int start = a.winStart[r], end = a.winEnd[r], W = end - start + 1;
-		if (W > HU_EST_CTA_COLS) continue; // the warp kernel takes wide windows
-		const int u = a.seedIds[(size_t) r * HU_MAX_SEED + s];
-		const int v = t.parent[u];
-		const int8_t* x = a.aligned + (size_t) r * t.csLen + start;
-		const int8_t* su = t.seq + (size_t) u * t.csLen + start;
-		const int8_t* sv = t.seq + (size_t) v * t.csLen + start;
-		const double* U = t.up + ((size_t) u * t.csLen + start) * 4;
-		const double* V = t.dn + ((size_t) u * t.csLen + start) * 4;
-		const double* US = t.upS + (size_t) u * t.csLen + start;
-		const double* VS = t.dnS + (size_t) u * t.csLen + start;
-		// ---- p-distances (byte loads only) while the message lines are prefetched into L2 ----
-		int bq[HU_EST_CTA_Q];
-		unsigned int cu = 0, cv = 0; // (N << 16) | d
-#pragma unroll
-		for (int q = 0; q < HU_EST_CTA_Q; ++q) {
-			const int c = q * HU_EST_CTA_THREADS + tid;
-			bq[q] = -128; // column outside the window
-			if (c < W) {
-				asm volatile("prefetch.global.L2 [%0];" ::"l"(U + (size_t) c * 4));
-				asm volatile("prefetch.global.L2 [%0];" ::"l"(V + (size_t) c * 4));
-				const int b = x[c];
-				bq[q] = b;
-				if (b >= 0) {
-					const int bu = su[c], bv = sv[c];
-					if (bu >= 0) cu += 0x10000u + (bu != b);
-					if (bv >= 0) cv += 0x10000u + (bv != b);
-				}
-			}
-		}
-		cu = ctaSumU(cu, redU[0], warp, lane);
-		cv = ctaSumU(cv, redU[1], warp, lane);
-		const double cDist = (double) (cu & 0xffffu) / (double) (cu >> 16);
-		const double pDist = (double) (cv & 0xffffu) / (double) (cv >> 16);
-		double ratio = cDist / (cDist + pDist);
-		if (isnan(ratio)) ratio = 0.5;
-		const double w0 = t.blen[u];
-		const double wur = w0 * ratio, wvr = w0 - wur;
-		if (warp == 0) {
-			modelPrHalfWarp(m, wur, ws.P[0], lane, 0);
-			modelPrHalfWarp(m, wvr, ws.P[1], lane, 1);
-		}
-		__syncthreads();
-		// ---- pass 1: g_j into registers ----
-		double g[HU_EST_CTA_Q][4];
-		double sumScale = 0;
-		unsigned int diff = 0;
-#pragma unroll
-		for (int q = 0; q < HU_EST_CTA_Q; ++q) {
-			const int c = q * HU_EST_CTA_THREADS + tid;
-			if (c >= W) continue;
-			double eu[4], ev[4], ya[4], yb[4];
-			ld4(U + (size_t) c * 4, eu);
-			ld4(V + (size_t) c * 4, ev);
-			sumScale += __ldg(US + c) + __ldg(VS + c);
-			matVec4(ws.P[0], eu, ya);
-			matVec4(ws.P[1], ev, yb);
-			for (int k = 0; k < 4; ++k) g[q][k] = ya[k] * yb[k];
-			diff += argmax4(g[q]) != (bq[q] >= 0 ? bq[q] : piMax);
-		}
-		diff = ctaSumU(diff, redU[0], warp, lane);
-		const double wnr = (double) diff / (double) W;
-		if (warp == 0) modelPrHalfWarp(m, wnr, ws.P[2], lane, 0);
-		__syncthreads();
-		if (tid < 5) {
-			double n[4], y[4];
-			leafLin(m, tid < 4 ? tid : -1, n);
-			matVec4(ws.P[2], n, y);
-			for (int k = 0; k < 4; ++k) ws.Np[tid][k] = y[k];
-		}
-		__syncthreads();
-		// ---- pass 2 on registers ----
-		double ll = sumScale;
-#pragma unroll
-		for (int q = 0; q < HU_EST_CTA_Q; ++q) {
-			if (bq[q] == -128) continue;
-			const double* np = ws.Np[bq[q] >= 0 ? bq[q] : 4];
-			double z[4];
-			for (int k = 0; k < 4; ++k) z[k] = g[q][k] * np[k];
-			ll += log(dotPi(m, z));
-		}
-		ll = ctaSumD(ll, redD, warp, lane);
-		if (tid == 0) {
-			hu_place_row row;
-			row.start = start; row.end = end;
-			row.cNode = u; row.pNode = v; row.aNode = ratio <= 0.5 ? u : v;
-			row.taxon = t.taxon[row.aNode];
-			row.dist = cDist;
-			row.wuv = w0; row.ratio = ratio; row.wnr = wnr;
-			row.loglik = ll; row.loglikTrue = 0; row.estLoglik = ll;
-			row.height = 0; row.annoDist = 0; row.qPlace = 0; row.qTaxon = 0;
-			row.outerIters = 0; row.nPlaces = 0;
-			a.est[(size_t) r * HU_MAX_SEED + s] = row;
-		}
-	}
-}
-
 // filterPlacements: order by estimated loglik (descending; equal logliks keep seed order) and keep the
 // placements within maxError of the best.
 __global__ void filterKernel(int nReads, const int* __restrict__ winStart, const int* __restrict__ nSeeds,
@@ -318,16 +159,15 @@ __global__ void filterKernel(int nReads, const int* __restrict__ winStart, const
 int launchEstimate(hu_batch* b, const hu_sep_params* p) {
 	hu_db* db = b->db;
 	EstArgs a;
-	a.nReads = b->nReads; a.maxNSeed = p->maxNSeed; a.ctaCols = HU_EST_CTA_COLS; a.pad1 = 0;
+	a.nReads = b->nReads; a.maxNSeed = p->maxNSeed; a.pad0 = a.pad1 = 0;
 	a.aligned = b->vit.aligned; a.winStart = b->winStart; a.winEnd = b->winEnd;
 	a.seedIds = b->seed.seedIds; a.nSeeds = b->seed.nSeeds;
 	a.est = b->est; a.cursor = b->workCount;
 	int sms = 0;
 	HU_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, db->device));
 	HU_CUDA(cudaMemsetAsync(b->workCount, 0, 4 * sizeof(int), b->stream));
-	estimateCtaKernel<<<sms * 2, HU_EST_CTA_THREADS, 0, b->stream>>>(a, db->tree, db->model);
-	estimateKernel<<<sms * 4, HU_EST_WARPS * 32, 0, b->stream>>>(a, db->tree, db->model); // windows wider than HU_EST_CTA_COLS
-	b->launches += 1;
+	const int grid = sms * 4;
+	estimateKernel<<<grid, HU_EST_WARPS * 32, 0, b->stream>>>(a, db->tree, db->model);
 	filterKernel<<<(b->nReads + 127) / 128, 128, 0, b->stream>>>(b->nReads, b->winStart, a.nSeeds, b->est, p->maxError, b->order, b->nKept);
 	HU_CUDA(cudaEventRecord(b->ev[5], b->stream));
 	b->launches += 2;

@@ -40,9 +40,6 @@ struct WarpShared {
 	double NP[HU_MAX_DG][5][4]; // P(ln r_k) applied to the leaf vector of base b / gap (linear)
 };
 
-// one out-of-line copy of the model switch: the kernel body stays small enough for the instruction cache
-__device__ __noinline__ void modelPrNI(const Model& m, double v, double* P) { modelPr(m, v, P); }
-
 __device__ __forceinline__ double warpSum(double v) {
 	for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
 	return v;
@@ -128,8 +125,8 @@ __global__ void __launch_bounds__(HU_PLACE_WARPS * 32) placeKernel(PlaceArgs a, 
 		for (iter = 0; iter < HU_MAX_ITER && 0 <= wur && wur <= w0j; ++iter) {
 			// ---- msg(r->n) from u and v, then optimise the n-r branch (cap 1) ----
 			__syncwarp();
-			if (lane < KK) modelPrNI(m, lu * (m.dgK ? m.dgR[lane] : 1.0), ws->P[0][lane]);
-			else if (lane >= 8 && lane < 8 + KK) modelPrNI(m, lv * (m.dgK ? m.dgR[lane - 8] : 1.0), ws->P[1][lane - 8]);
+			if (lane < KK) modelPr(m, lu * (m.dgK ? m.dgR[lane] : 1.0), ws->P[0][lane]);
+			else if (lane >= 8 && lane < 8 + KK) modelPr(m, lv * (m.dgK ? m.dgR[lane - 8] : 1.0), ws->P[1][lane - 8]);
 			__syncwarp();
 			int nValid = 0;
 			for (int cI = lane; cI < W; cI += 32) {
@@ -155,7 +152,7 @@ __global__ void __launch_bounds__(HU_PLACE_WARPS * 32) placeKernel(PlaceArgs a, 
 			ln = wnr;
 			// ---- msg(r->u) from v and n, then optimise the u-r branch (cap w0) ----
 			__syncwarp();
-			if (lane < KK) modelPrNI(m, ln * (m.dgK ? m.dgR[lane] : 1.0), ws->P[2][lane]);
+			if (lane < KK) modelPr(m, ln * (m.dgK ? m.dgR[lane] : 1.0), ws->P[2][lane]);
 			__syncwarp();
 			for (int q = lane; q < KK * 5; q += 32) {
 				const int k = q / 5, b = q % 5;
@@ -196,9 +193,9 @@ __global__ void __launch_bounds__(HU_PLACE_WARPS * 32) placeKernel(PlaceArgs a, 
 		}
 		// ---- intended root log-likelihood: sum_j log(pi . exp(loglik(r, j))) ----
 		__syncwarp();
-		if (lane < KK) modelPrNI(m, lu * (m.dgK ? m.dgR[lane] : 1.0), ws->P[0][lane]);
-		else if (lane >= 8 && lane < 8 + KK) modelPrNI(m, lv * (m.dgK ? m.dgR[lane - 8] : 1.0), ws->P[1][lane - 8]);
-		else if (lane >= 16 && lane < 16 + KK) modelPrNI(m, ln * (m.dgK ? m.dgR[lane - 16] : 1.0), ws->P[2][lane - 16]);
+		if (lane < KK) modelPr(m, lu * (m.dgK ? m.dgR[lane] : 1.0), ws->P[0][lane]);
+		else if (lane >= 8 && lane < 8 + KK) modelPr(m, lv * (m.dgK ? m.dgR[lane - 8] : 1.0), ws->P[1][lane - 8]);
+		else if (lane >= 16 && lane < 16 + KK) modelPr(m, ln * (m.dgK ? m.dgR[lane - 16] : 1.0), ws->P[2][lane - 16]);
 		__syncwarp();
 		for (int q = lane; q < KK * 5; q += 32) {
 			const int k = q / 5, b = q % 5;
