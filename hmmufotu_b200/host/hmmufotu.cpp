@@ -1,0 +1,329 @@
+// hmmufotu -- taxonomy assignment of 16S reads: banded-HMM alignment + SEP phylogenetic placement on B200 GPUs.
+// Command line, defaults and TSV output follow /root/reference/src/hmmufotu.cpp (options :77-109, defaults
+// :37-57, database loading :445-498, strand pre-test :501-545, read loop :603-751).  The per-read work of the
+// reference's OpenMP tasks is batched through include/hmmufotu_b200.h; the CSFM seed search stays on the
+// host, in file order, so that its rand() stream is the reference's for a given -S.
+#include "hu_host.h"
+
+#include <errno.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+#include <fstream>
+#include <limits>
+#include <sstream>
+
+using namespace std;
+using namespace EGriceLab::HmmUFOtu;
+
+static const double inf = numeric_limits<double>::infinity();
+static const int DEFAULT_READ_STRAND = 0, MIN_STRAND_TEST = 100, MAX_STRAND_TEST = 1000;
+static const double STRAND_CONFIDENCE = 0.9;
+static const int DEFAULT_SEED_LEN = 20, MAX_SEED_LEN = 25, MIN_SEED_LEN = 15, DEFAULT_SEED_REGION = 50;
+
+static void printUsage(const string& prog) {
+	cerr << "Usage:    " << prog << "  <HmmUFOtu-DB> <READ-FILE1> [READ-FILE2] [options]" << endl
+		 << "READ-FILE1  FILE                 : sequence read file for the assembled/forward read" << endl
+		 << "READ-FILE2  FILE                 : sequence read file for the reverse read" << endl
+		 << "Options:    -o  FILE             : write the assignment output to FILE instead of stdout" << endl
+		 << "            -a  FILE             : in addition to the assignment output, write the read alignment in fasta format" << endl
+		 << "            --fmt  STR           : read file format (applied to all read files), supported format: 'fasta', 'fastq'" << endl
+		 << "            -L|--seed-len  INT   : seed length used for banded-Hmm search [" << DEFAULT_SEED_LEN << "]" << endl
+		 << "            -R  INT              : size of 5'/3' seed region for finding seed matches for CSFM-index [" << DEFAULT_SEED_REGION << "]" << endl
+		 << "            --single  FLAG       : assume READ-FILE1 is single-end read instead of assembled read (partial-local HMM setting)" << endl
+		 << "            -s|--strand  INT     : strand of reads/mates, 1 for 1st-strand, 2 for 2nd-strand, 0 for auto-detection [" << DEFAULT_READ_STRAND << "]" << endl
+		 << "            -t|--test  INT       : use first # reads to detect the strandness of input reads/mates [" << MIN_STRAND_TEST << "]" << endl
+		 << "            -i|--ignore  FLAG    : ignore forward/reverse orientation check" << endl
+		 << "            -N  INT              : max # of seed nodes used in the 'Seed' stage of SEP algorithm [50]" << endl
+		 << "            -d|--max-diff  DBL   : max p-dist difference allowed for sub-optimal seeds [inf]" << endl
+		 << "            -H|--max-height  DBL : max height of seed nodes to be used in the SEP algorithm [inf]" << endl
+		 << "            -e|--err  DBL        : max placement error used in the 'Estimate' stage of SEP algorithm [20]" << endl
+		 << "            --true-loglik  FLAG  : report the root log-likelihood of each placement instead of the reference's constant (DESIGN.md 5)" << endl
+		 << "            --chimera-out  FILE  : keep assignment output of chimera reads (bad mate orientation) in FILE" << endl
+		 << "            -S|--seed  INT       : random seed used for CSFM-index seed searches, for debug only" << endl
+		 << "            --gpu  INT           : CUDA device to use [0]" << endl
+		 << "            --batch  INT         : reads per GPU batch [4096]" << endl
+		 << "            --align-only  FLAG   : only align the reads, do not place them" << endl
+		 << "            --check-db  FLAG     : load the database files, print a summary and exit (no GPU needed)" << endl
+		 << "            -v  FLAG             : enable verbose information" << endl
+		 << "            --version            : show program version and exit" << endl
+		 << "            -h|--help            : print this message and exit" << endl;
+}
+
+// CommandOptions (src/util/CommandOptions.cpp:32-52): "-x value" pairs, flags, positional arguments
+struct CommandOptions {
+	vector<string> mainOpts;
+	map<string, string> opts;
+	string cmd;
+	CommandOptions(int argc, char** argv) {
+		for (int i = 0; i < argc; ++i) cmd += string(i ? " " : "") + argv[i];
+		for (int i = 1; i < argc; ++i) {
+			const string a = argv[i];
+			if (a.size() > 1 && a[0] == '-' && !(isdigit((unsigned char) a[1]) || a[1] == '.')) {
+				if (i + 1 < argc && !(strlen(argv[i + 1]) > 1 && argv[i + 1][0] == '-' && !isdigit((unsigned char) argv[i + 1][1]))) opts[a] = argv[++i];
+				else opts[a] = "";
+			} else
+				mainOpts.push_back(a);
+		}
+	}
+	bool hasOpt(const string& o) const { return opts.count(o) != 0; }
+	const char* getOptStr(const string& o) const { return opts.find(o)->second.c_str(); }
+	string get(const string& a, const string& b, const string& dflt) const { return hasOpt(a) ? opts.find(a)->second : hasOpt(b) ? opts.find(b)->second : dflt; }
+};
+
+struct ReadBatchHost { // one batch of (pairs of) reads staged for hu_batch_upload
+	vector<PrimarySeq> fwd, rev;
+	vector<int8_t> codes;
+	vector<int64_t> offsets;
+	vector<hu_vpath> vpaths;
+	vector<int32_t> nPaths;
+};
+
+static void stage(const BandedHMMP7& hmm, const CSFMIndex& csfm, const PrimarySeq& read, int seedLen, int seedRegion,
+		BandedHMMP7::align_mode mode, ReadBatchHost& hb) {
+	const vector<BandedHMMP7::ViterbiAlignPath> vps = findSeeds(hmm, csfm, read, seedLen, seedRegion, mode);
+	for (size_t i = 0; i < read.length(); ++i) {
+		const int8_t b = DNA::encode((char) ::toupper(read.seq[i]));
+		if (b < 0) throw invalid_argument("read '" + read.id + "' holds a character outside the nucleotide alphabet");
+		hb.codes.push_back(b);
+	}
+	hb.offsets.push_back((int64_t) hb.codes.size());
+	for (int i = 0; i < 2; ++i) {
+		hu_vpath v = {0, 0, 0, 0, 0, 0};
+		if (i < (int) vps.size()) { v.start = vps[i].start; v.end = vps[i].end; v.from = vps[i].from; v.to = vps[i].to; v.nIns = vps[i].nIns; v.nDel = vps[i].nDel; }
+		hb.vpaths.push_back(v);
+	}
+	hb.nPaths.push_back((int32_t) vps.size());
+}
+
+#define HU_CHECK(call) do { if ((call) != HU_OK) { cerr << "Error: " << hu_last_error() << endl; return EXIT_FAILURE; } } while (0)
+
+int main(int argc, char* argv[]) {
+	CommandOptions cmdOpts(argc, argv);
+	if (cmdOpts.hasOpt("-h") || cmdOpts.hasOpt("--help")) { printUsage(argv[0]); return EXIT_SUCCESS; }
+	if (cmdOpts.hasOpt("--version")) {
+		cout << argv[0] << ": v" << progVer[0] << "." << progVer[1] << "." << progVer[2] << endl << "Package: " << hu_version() << endl;
+		return EXIT_SUCCESS;
+	}
+	const bool checkDb = cmdOpts.hasOpt("--check-db");
+	if (!(cmdOpts.mainOpts.size() == 2 || cmdOpts.mainOpts.size() == 3 || (checkDb && cmdOpts.mainOpts.size() == 1))) {
+		cerr << "Error:" << endl;
+		printUsage(argv[0]);
+		return EXIT_FAILURE;
+	}
+	const string dbName = cmdOpts.mainOpts[0];
+	string fwdFn = cmdOpts.mainOpts.size() > 1 ? cmdOpts.mainOpts[1] : "", revFn = cmdOpts.mainOpts.size() > 2 ? cmdOpts.mainOpts[2] : "";
+	const string outFn = cmdOpts.get("-o", "-o", ""), alnFn = cmdOpts.get("-a", "-a", ""), chiFn = cmdOpts.get("--chimera-out", "--chimera-out", "");
+	int seedLen = atoi(cmdOpts.get("-L", "--seed-len", "20").c_str());
+	int seedRegion = atoi(cmdOpts.get("-R", "-R", "50").c_str());
+	int rStrand = atoi(cmdOpts.get("-s", "--strand", "0").c_str());
+	int nTest = atoi(cmdOpts.get("-t", "--test", "100").c_str());
+	const bool ignoreOrient = cmdOpts.hasOpt("-i") || cmdOpts.hasOpt("--ignore");
+	const bool alignOnly = cmdOpts.hasOpt("--align-only");
+	const bool verbose = cmdOpts.hasOpt("-v");
+	const BandedHMMP7::align_mode mode = cmdOpts.hasOpt("--single") ? BandedHMMP7::NGCL : BandedHMMP7::GLOBAL; // :358
+	hu_sep_params sp;
+	hu_sep_params_default(&sp);
+	sp.maxNSeed = atoi(cmdOpts.get("-N", "-N", "50").c_str());
+	if (cmdOpts.hasOpt("-d") || cmdOpts.hasOpt("--max-diff")) sp.maxDiff = atof(cmdOpts.get("-d", "--max-diff", "inf").c_str());
+	if (cmdOpts.hasOpt("-H") || cmdOpts.hasOpt("--max-height")) sp.maxHeight = atof(cmdOpts.get("-H", "--max-height", "inf").c_str());
+	sp.maxError = atof(cmdOpts.get("-e", "--err", "20").c_str());
+	sp.useTrueLoglik = cmdOpts.hasOpt("--true-loglik");
+	unsigned seed = (unsigned) time(NULL);
+	if (cmdOpts.hasOpt("-S") || cmdOpts.hasOpt("--seed")) seed = (unsigned) atoi(cmdOpts.get("-S", "--seed", "0").c_str());
+	const int device = atoi(cmdOpts.get("--gpu", "--gpu", "0").c_str());
+	const int batchSize = atoi(cmdOpts.get("--batch", "--batch", "4096").c_str());
+	string seqFmt = cmdOpts.get("--fmt", "--fmt", "");
+	// option validation, :318-348
+	if (!(MIN_SEED_LEN <= seedLen && seedLen <= MAX_SEED_LEN)) { cerr << "-L|--seed-len must be in range [" << MIN_SEED_LEN << ", " << MAX_SEED_LEN << "]" << endl; return EXIT_FAILURE; }
+	if (seedRegion < seedLen) { cerr << "-R cannot be smaller than -L" << endl; return EXIT_FAILURE; }
+	if (!(0 <= rStrand && rStrand <= 2)) { cerr << "-s|--strand must be 0, 1, or 2" << endl; return EXIT_FAILURE; }
+	if (nTest < MIN_STRAND_TEST && rStrand == 0 && !cmdOpts.hasOpt("-t") && !cmdOpts.hasOpt("--test")) nTest = MIN_STRAND_TEST;
+	if (nTest > MAX_STRAND_TEST) nTest = MAX_STRAND_TEST;
+	if (sp.maxNSeed < 1 || sp.maxNSeed > HU_MAX_SEED) { cerr << "-N must be in range [1, " << HU_MAX_SEED << "]" << endl; return EXIT_FAILURE; }
+	if (!(sp.maxDiff >= 0)) { cerr << "-d must be non-negative" << endl; return EXIT_FAILURE; }
+	if (!(sp.maxError > 0)) { cerr << "-e|--err must be positive" << endl; return EXIT_FAILURE; }
+	if (batchSize < 1) { cerr << "--batch must be positive" << endl; return EXIT_FAILURE; }
+	if (seqFmt.empty() && !fwdFn.empty()) seqFmt = SeqIO::guessFormat(fwdFn);
+	if (!seqFmt.empty() && seqFmt != "fasta" && seqFmt != "fastq") { cerr << "Unsupported sequence format '" << seqFmt << "'" << endl; return EXIT_FAILURE; }
+	srand(seed);
+
+	// ---- database, :352-383, :445-498 ----
+	const string msaFn = dbName + ".msa", hmmFn = dbName + ".hmm", ptuFn = dbName + ".ptu";
+	ifstream msaIn(msaFn.c_str(), ios_base::binary), hmmIn(hmmFn.c_str()), ptuIn(ptuFn.c_str(), ios_base::binary);
+	if (!msaIn.is_open()) { cerr << "Unable to open MSA data '" << msaFn << "': " << ::strerror(errno) << endl; return EXIT_FAILURE; }
+	if (!hmmIn.is_open()) { cerr << "Unable to open HMM profile '" << hmmFn << "': " << ::strerror(errno) << endl; return EXIT_FAILURE; }
+	if (!ptuIn.is_open()) { cerr << "Unable to open PTU data '" << ptuFn << "': " << ::strerror(errno) << endl; return EXIT_FAILURE; }
+	if (loadProgInfo(msaIn).bad()) return EXIT_FAILURE;
+	MSA msa;
+	msa.load(msaIn);
+	if (!msaIn) { cerr << "Failed to load MSA data '" << msaFn << "'" << endl; return EXIT_FAILURE; }
+	const int csLen = (int) msa.getCSLen();
+	BandedHMMP7 hmm;
+	hmmIn >> hmm;
+	if (hmmIn.bad() || hmmIn.fail()) { cerr << "Unable to read HMM profile '" << hmmFn << "'" << endl; return EXIT_FAILURE; }
+	if (hmm.getProfileSize() > csLen) { cerr << "Error: HMM profile size is found greater than the MSA CS length" << endl; return EXIT_FAILURE; }
+	// the reference loads <db>.csfm (libcds serialisation); the same index is rebuilt from the MSA here
+	CSFMIndex csfm;
+	csfm.build(msa);
+	if (csfm.getCSLen() != csLen) { cerr << "Error: Unmatched CS length between CSFM-index and MSA data" << endl; return EXIT_FAILURE; }
+	if (loadProgInfo(ptuIn).bad()) return EXIT_FAILURE;
+	PTUnrooted ptu;
+	ptu.load(ptuIn);
+	if (!ptuIn || ptuIn.bad()) { cerr << "Unable to load Phylogenetic tree data '" << ptuFn << "'" << endl; return EXIT_FAILURE; }
+	if (ptu.getCSLen() != csLen || hmm.getCSLen() != csLen) { cerr << "Error: Unmatched CS length between the database files" << endl; return EXIT_FAILURE; }
+	hmm.setSequenceMode(mode);
+	hmm.wingRetract();
+	if (verbose || checkDb)
+		cerr << "Database loaded: csLen " << csLen << ", profile size " << hmm.getProfileSize() << ", " << ptu.numNodes() << " nodes, model "
+			 << ptu.model.modelType() << (ptu.hasDG ? " + dGamma" : "") << ", " << msa.numSeq << " MSA rows" << endl;
+	if (checkDb) return EXIT_SUCCESS;
+
+	// ---- device ----
+	hu_db* db = NULL;
+	{
+		const hu_hmm_params hp = hmm.params();
+		const hu_tree_desc td = ptu.treeDesc();
+		const hu_model_desc md = ptu.modelDesc();
+		HU_CHECK(hu_db_create(&db, &hp, &td, &md, device));
+	}
+	vector<double>().swap(ptu.up); // the messages now live on the device
+	vector<double>().swap(ptu.dn);
+
+	// ---- strand pre-test, :501-542: align the first nTest reads in both orientations ----
+	const bool paired = !revFn.empty();
+	if (rStrand == 0) {
+		ifstream testIn(fwdFn.c_str());
+		if (!testIn.is_open()) { cerr << "Unable to test forward seq file '" << fwdFn << "' " << ::strerror(errno) << endl; return EXIT_FAILURE; }
+		SeqIO testSeqI(&testIn, seqFmt);
+		ReadBatchHost hb;
+		hb.offsets.push_back(0);
+		int n = 0, maxLen = 1;
+		for (; n < nTest && testSeqI.hasNext(); ++n) { // fwd then rev per read: the order alignSeq draws rand()
+			const PrimarySeq f = testSeqI.nextSeq(), r = f.revcom();
+			stage(hmm, csfm, f, seedLen, seedRegion, mode, hb);
+			stage(hmm, csfm, r, seedLen, seedRegion, mode, hb);
+			maxLen = max(maxLen, (int) f.length());
+		}
+		double fwdScore = 0, revScore = 0;
+		if (n > 0) {
+			hu_batch* tb = NULL;
+			HU_CHECK(hu_batch_create(&tb, db, 2 * n, maxLen, 0));
+			const hu_read_batch rb = {2 * n, 0, hb.codes.data(), hb.offsets.data(), hb.vpaths.data(), hb.nPaths.data()};
+			HU_CHECK(hu_batch_upload(tb, &rb));
+			HU_CHECK(hu_align_batch(tb, mode));
+			vector<hu_align_row> rows(2 * n);
+			HU_CHECK(hu_batch_get_align(tb, rows.data(), NULL, 0, NULL));
+			for (int i = 0; i < n; ++i) (rows[2 * i].cost < rows[2 * i + 1].cost ? fwdScore : revScore)++;
+			hu_batch_destroy(tb);
+		}
+		if (fwdScore >= (fwdScore + revScore) * STRAND_CONFIDENCE) rStrand = 1;
+		else if (revScore >= (fwdScore + revScore) * STRAND_CONFIDENCE) rStrand = 2;
+		else { cerr << "Failed to determine read strandness. Try larger -t|--test or determine manually" << endl; return EXIT_FAILURE; }
+		if (verbose) cerr << "Read strand determined as " << rStrand << endl;
+	}
+	if (rStrand == 2 && paired) std::swap(fwdFn, revFn);
+
+	// ---- inputs / outputs ----
+	ifstream fwdIn(fwdFn.c_str()), revIn;
+	if (!fwdIn.is_open()) { cerr << "Unable to open seq file '" << fwdFn << "' " << ::strerror(errno) << endl; return EXIT_FAILURE; }
+	if (paired) {
+		revIn.open(revFn.c_str());
+		if (!revIn.is_open()) { cerr << "Unable to open reverse seq file '" << revFn << "' " << ::strerror(errno) << endl; return EXIT_FAILURE; }
+	}
+	SeqIO fwdSeqI(&fwdIn, seqFmt), revSeqI(&revIn, seqFmt);
+	ofstream outFile, alnFile, chiFile;
+	if (!outFn.empty()) { outFile.open(outFn.c_str()); if (!outFile.is_open()) { cerr << "Unable to write to '" << outFn << "' " << ::strerror(errno) << endl; return EXIT_FAILURE; } }
+	if (!alnFn.empty()) { alnFile.open(alnFn.c_str()); if (!alnFile.is_open()) { cerr << "Unable to write to '" << alnFn << "' " << ::strerror(errno) << endl; return EXIT_FAILURE; } }
+	if (!chiFn.empty()) { chiFile.open(chiFn.c_str()); if (!chiFile.is_open()) { cerr << "Unable to write to '" << chiFn << "' " << ::strerror(errno) << endl; return EXIT_FAILURE; } }
+	ostream& out = outFn.empty() ? cout : outFile;
+	const string header = string("id\tdescription\t") + BandedHMMP7::HmmAlignment::TSV_HEADER + "\t" + PTUnrooted::PTPlacement::TSV_HEADER;
+	writeProgInfo(out, string(" taxonomy assignment generated by ") + argv[0]);
+	out << "# command: " << cmdOpts.cmd << endl << header << endl;
+	if (chiFile.is_open()) {
+		writeProgInfo(chiFile, string(" taxonomy assignment generated by ") + argv[0]);
+		chiFile << "# command: " << cmdOpts.cmd << endl << header << endl;
+	}
+
+	// ---- the read loop, batched ----
+	hu_batch* batch = NULL;
+	int batchMaxLen = 0;
+	long nDone = 0;
+	while (fwdSeqI.hasNext() && (!paired || revSeqI.hasNext())) {
+		ReadBatchHost hb;
+		hb.offsets.push_back(0);
+		int maxLen = 1;
+		while ((int) hb.fwd.size() < batchSize && fwdSeqI.hasNext() && (!paired || revSeqI.hasNext())) {
+			PrimarySeq f = fwdSeqI.nextSeq();
+			if (rStrand == 2 && !paired) f = f.revcom(); // wrong strand for single-strand reads, :618-619
+			hb.fwd.push_back(f);
+			if (paired) hb.rev.push_back(revSeqI.nextSeq().revcom());
+			maxLen = max(maxLen, (int) f.length());
+			if (paired) maxLen = max(maxLen, (int) hb.rev.back().length());
+		}
+		const int n = (int) hb.fwd.size();
+		// seed search in file order; a pair draws rand() for the forward read first (:621-626).  The device wants
+		// all forward reads, then all mates.
+		ReadBatchHost mates;
+		mates.offsets.push_back(0);
+		for (int i = 0; i < n; ++i) {
+			stage(hmm, csfm, hb.fwd[i], seedLen, seedRegion, mode, hb);
+			if (paired) stage(hmm, csfm, hb.rev[i], seedLen, seedRegion, mode, mates);
+		}
+		if (paired) {
+			const int64_t base = hb.offsets.back();
+			hb.codes.insert(hb.codes.end(), mates.codes.begin(), mates.codes.end());
+			for (size_t i = 1; i < mates.offsets.size(); ++i) hb.offsets.push_back(base + mates.offsets[i]);
+			hb.vpaths.insert(hb.vpaths.end(), mates.vpaths.begin(), mates.vpaths.end());
+			hb.nPaths.insert(hb.nPaths.end(), mates.nPaths.begin(), mates.nPaths.end());
+		}
+		if (!batch || maxLen > batchMaxLen) {
+			if (batch) hu_batch_destroy(batch);
+			batchMaxLen = max(maxLen + maxLen / 4, 64);
+			HU_CHECK(hu_batch_create(&batch, db, batchSize, batchMaxLen, paired ? 1 : 0));
+		}
+		const hu_read_batch rb = {n, paired ? 1 : 0, hb.codes.data(), hb.offsets.data(), hb.vpaths.data(), hb.nPaths.data()};
+		HU_CHECK(hu_batch_upload(batch, &rb));
+		if (alignOnly) HU_CHECK(hu_align_batch(batch, mode));
+		else HU_CHECK(hu_assign_batch(batch, mode, &sp));
+		const int nSeq = n * (paired ? 2 : 1);
+		vector<hu_align_row> rows(nSeq), merged(n);
+		vector<int64_t> traceOff(nSeq + 1);
+		vector<char> traces((size_t) nSeq * (batchMaxLen + hmm.getProfileSize() + 8));
+		HU_CHECK(hu_batch_get_align(batch, rows.data(), traces.data(), (int64_t) traces.size(), traceOff.data()));
+		HU_CHECK(hu_batch_get_merged(batch, merged.data()));
+		vector<hu_place_row> best(n);
+		if (!alignOnly) HU_CHECK(hu_batch_get_best(batch, best.data()));
+		for (int i = 0; i < n; ++i) {
+			const PrimarySeq& f = hb.fwd[i];
+			if (rows[i].flags & HU_ALIGN_INVALID) { cerr << "Warning: read '" << f.getId() << "' could not be aligned, skipped" << endl; continue; }
+			BandedHMMP7::HmmAlignment aln = hmm.buildGlobalAlign(f, rows[i], traces.data() + traceOff[i]);
+			bool isChimera = false;
+			if (paired) {
+				if (rows[n + i].flags & HU_ALIGN_INVALID) { cerr << "Warning: mate of '" << f.getId() << "' could not be aligned, skipped" << endl; continue; }
+				const BandedHMMP7::HmmAlignment revAln = hmm.buildGlobalAlign(hb.rev[i], rows[n + i], traces.data() + traceOff[n + i]);
+				if (!ignoreOrient && !(aln.csStart <= revAln.csStart && aln.csEnd <= revAln.csEnd)) {
+					cerr << "Warning: Bad orientation of forward/reverse read detected, treating as chimera" << endl;
+					isChimera = true;
+				} else
+					aln.merge(revAln);
+			}
+			PTUnrooted::PTPlacement bestPlace;
+			bestPlace.taxonName = "NULL";
+			if (!alignOnly && !isChimera && best[i].nPlaces > 0) bestPlace = ptu.toPlacement(best[i]);
+			ostream& dst = isChimera ? (ostream&) chiFile : out;
+			if (isChimera && !chiFile.is_open()) continue; // chimera reads go to --chimera-out only, :693-706
+			if (!isChimera && alnFile.is_open()) {
+				ostringstream d;
+				d << f.getDesc() << ";csStart=" << aln.csStart << ";csEnd=" << aln.csEnd << ";";
+				alnFile << ">" << f.getId() << " " << d.str() << endl << aln.align << endl;
+			}
+			dst << f.getId() << "\t" << f.getDesc() << "\t" << aln << "\t" << bestPlace << endl;
+		}
+		nDone += n;
+		if (verbose) cerr << nDone << " reads processed" << endl;
+	}
+	if (batch) hu_batch_destroy(batch);
+	hu_db_destroy(db);
+	return EXIT_SUCCESS;
+}

@@ -1,0 +1,224 @@
+// Host-side C++ layer above the C ABI: the reference's class surface for the per-read path, free of Eigen
+// and Boost.  Names and method meanings follow /root/reference/src (file:line cited per declaration) so that
+// the hmmufotu driver (hmmufotu.cpp in this directory) reads like the reference's.  No hot-path arithmetic
+// lives here: Viterbi, seeding scan, estimate and place run on the GPU through include/hmmufotu_b200.h.
+#ifndef HU_HOST_H_
+#define HU_HOST_H_
+
+#include <stdint.h>
+#include <iostream>
+#include <map>
+#include <string>
+#include <vector>
+#include "../../include/hmmufotu_b200.h"
+
+namespace EGriceLab {
+namespace HmmUFOtu {
+
+extern const std::string progName;                 // "HmmUFOtu", src/util/ProgEnv.cpp
+extern const int progVer[3];                       // 1.5.1
+std::istream& loadProgInfo(std::istream& in);      // src/util/ProgEnv.cpp:30-65 (binary header check)
+std::ostream& saveProgInfo(std::ostream& out);     // src/util/ProgEnv.cpp:24-28
+std::ostream& writeProgInfo(std::ostream& out, const std::string& info); // text header, ProgEnv.cpp:101-104
+bool loadString(std::string& dest, std::istream& in);                    // src/util/StringUtils.h:187-194
+void saveString(const std::string& src, std::ostream& out);              // src/util/StringUtils.h:213-218
+
+// ---- alphabet / sequences (src/DegenAlphabet.cpp:43-64, src/IUPACNucl.cpp:33-71, src/PrimarySeq.h) ----
+struct DNA {
+	static int8_t encode(char c);                  // ACGT -> 0..3, IUPAC degenerate -> first member, gap -2, else -1
+	static char decode(int8_t b) { return "ACGT"[b & 3]; }
+	static bool isSymbol(char c) { return encode(c) >= 0; }
+	static bool isGap(char c) { return c == '-' || c == '.' || c == '_'; }
+	static char complement(char c);                // IUPAC complement, case preserved
+};
+
+class PrimarySeq {
+public:
+	PrimarySeq() {}
+	PrimarySeq(const std::string& id, const std::string& seq, const std::string& desc = "", const std::string& qual = "")
+		: id(id), seq(seq), desc(desc), qual(qual) {}
+	const std::string& getId() const { return id; }
+	const std::string& getDesc() const { return desc; }
+	const std::string& getSeq() const { return seq; }
+	size_t length() const { return seq.length(); }
+	PrimarySeq revcom() const;                     // src/PrimarySeq.cpp
+	std::string id, seq, desc, qual;
+};
+
+class SeqIO {                                      // src/SeqIO.cpp: streaming FASTA / FASTQ reader
+public:
+	SeqIO(std::istream* in, const std::string& fmt) : in(in), fmt(fmt) {}
+	bool hasNext();
+	PrimarySeq nextSeq();
+	static std::string guessFormat(const std::string& fn);
+private:
+	std::istream* in;
+	std::string fmt;
+};
+
+// ---- CSLoc + CSFM index (src/CSLoc.h, src/CSFMIndex.{h,cpp}) ----
+struct CSLoc {
+	CSLoc() : start(0), end(0) {}
+	CSLoc(int start, int end, const std::string& CS) : start(start), end(end), CS(CS) {}
+	bool isValid() const { return start > 0 && start <= end && !CS.empty(); }
+	int start, end;                                // 1-based consensus columns of the first / last pattern char
+	std::string CS;                                // the pattern with '-' for every skipped column
+};
+
+struct MSA {                                       // src/MSA.{h,cpp}: only what the run path touches
+	std::string alphabet, name, CS;
+	unsigned numSeq, csLen;
+	bool isPruned;
+	std::vector<std::string> seqNames;
+	std::string concatMSA;                         // numSeq * csLen chars, row-major
+	std::istream& load(std::istream& in);          // src/MSA.cpp:362-430 (whole record is parsed)
+	std::ostream& save(std::ostream& out) const;   // src/MSA.cpp:295-360 (count / weight blocks recomputed plainly)
+	unsigned getCSLen() const { return csLen; }
+	char residualAt(unsigned i, unsigned j) const { return concatMSA[(size_t) i * csLen + j]; }
+};
+
+// FM index over the gap-stripped concatenation of the MSA rows with a map back to consensus columns.
+// The reference serialises libcds structures into <db>.csfm; this class rebuilds the same index from <db>.msa
+// at start-up (the suffix array of a text with a unique terminator is unique, so SA intervals and SA values,
+// hence locateOne()'s rand() pick, are the reference's).
+class CSFMIndex {
+public:
+	CSFMIndex() : csLen(0), concatLen(0) {}
+	CSFMIndex& build(const MSA& msa);              // src/CSFMIndex.cpp:232-368
+	int getCSLen() const { return csLen; }
+	int32_t count(const std::string& pattern) const;                 // src/CSFMIndex.cpp:79-99
+	CSLoc locateOne(const std::string& pattern) const;               // src/CSFMIndex.cpp:121-147 (uses rand())
+	CSLoc locateFirst(const std::string& pattern) const;             // src/CSFMIndex.cpp:101-119
+	std::vector<CSLoc> locate(const std::string& pattern) const;     // src/CSFMIndex.cpp:53-77
+private:
+	bool search(const std::string& pattern, int32_t& start, int32_t& end) const;
+	int32_t occ(int b, int32_t i) const;           // # of symbol b in BWT[0..i]
+	std::string extractCS(int32_t start, const std::string& pattern) const; // src/CSFMIndex.cpp:262-273
+	int csLen;
+	int32_t concatLen;
+	int32_t C[6];
+	std::vector<uint8_t> bwt;                      // symbols 0..4 (0 = separator / terminator)
+	std::vector<int32_t> occSamples;               // [block][5], every 64 positions
+	std::vector<int32_t> sa;                       // full suffix array (1-based text positions as in the reference)
+	std::vector<uint16_t> concat2CS;               // 1-based text position -> 1-based consensus column (0: separator)
+};
+
+// ---- banded plan-7 profile (src/BandedHMMP7.{h,cpp}) ----
+class BandedHMMP7 {
+public:
+	enum align_mode { GLOBAL, LOCAL, NGCL, CGNL };                   // .h:163-168
+	struct ViterbiAlignPath {                                        // .h:229-249
+		ViterbiAlignPath() : start(0), end(0), from(0), to(0), nIns(0), nDel(0) {}
+		ViterbiAlignPath(int start, int end, int from, int to, int nIns, int nDel)
+			: start(start), end(end), from(from), to(to), nIns(nIns), nDel(nDel) {}
+		bool isValid() const { return start > 0 && start <= end && from > 0 && from <= to && nIns >= 0 && nDel >= 0; }
+		int start, end, from, to, nIns, nDel;
+	};
+	struct HmmAlignment {                                            // .h:74-134
+		HmmAlignment() : K(0), L(0), seqStart(0), seqEnd(0), hmmStart(0), hmmEnd(0), csStart(0), csEnd(0), cost(0) {}
+		bool isValid() const;
+		HmmAlignment& merge(const HmmAlignment& other);              // cpp:1188-1213
+		int K, L, seqStart, seqEnd, hmmStart, hmmEnd, csStart, csEnd;
+		double cost;
+		std::string align;
+		static const std::string TSV_HEADER;
+	};
+	BandedHMMP7() : K(0), L(0), wingRetracted(false), mode(GLOBAL) {}
+	int getProfileSize() const { return K; }
+	int getCSLen() const { return L; }
+	int getProfileLoc(int cs) const { return cs2ProfileIdx[cs]; }
+	int getCSLoc(int k) const { return profile2CSIdx[k]; }
+	void setSequenceMode(align_mode m) { mode = m; }                  // cpp:561-583 (costs derived on the device side)
+	align_mode getSequenceMode() const { return mode; }
+	void wingRetract();                                              // cpp:1083-1120 (via hu_hmm_finalize)
+	ViterbiAlignPath buildAlignPath(const CSLoc& csLoc, int csFrom, int csTo) const; // cpp:894-941
+	HmmAlignment buildGlobalAlign(const PrimarySeq& seq, const hu_align_row& row, const char* trace) const; // cpp:1008-1081
+	hu_hmm_params params() const;                                    // view for hu_db_create / hu_trace_to_align
+	friend std::istream& operator>>(std::istream& in, BandedHMMP7& hmm);        // cpp:100-246
+	friend std::ostream& operator<<(std::ostream& out, const BandedHMMP7& hmm); // cpp:324-378
+	std::string name;
+	int K, L;
+	std::vector<double> E_M_cost, E_I_cost, Tmat_cost, entryPr_cost, exitPr_cost; // [k*4+b], [k*9+a*3+b], [k]
+	std::vector<int32_t> cs2ProfileIdx, profile2CSIdx;
+	std::vector<std::pair<std::string, std::string> > optTags;
+	std::vector<std::string> locMap;                                 // per-position text after the MAP column (CONS ...)
+	bool wingRetracted;
+	align_mode mode;
+};
+std::ostream& operator<<(std::ostream& out, const BandedHMMP7::HmmAlignment& aln); // cpp:1215-1221
+
+// ---- substitution models (src/DNASubModel.h, GTR/TN93/HKY85/F81/K80/JC69, DNASubModelFactory) ----
+class DNASubModel {
+public:
+	DNASubModel();
+	std::string modelType() const;
+	void Pr(double v, double* P16) const;          // row-major 4x4 through hu_model_Pr
+	const double* getPi() const { return desc.pi; }
+	std::istream& read(std::istream& in);          // each model's read()
+	std::ostream& write(std::ostream& out) const;  // each model's write()
+	hu_model_desc desc;
+};
+std::istream& operator>>(std::istream& in, DNASubModel& m);
+std::ostream& operator<<(std::ostream& out, const DNASubModel& m);
+
+struct DiscreteGammaModel {                        // src/DiscreteGammaModel.{h,cpp}
+	int K;
+	double alpha;
+	std::vector<double> b, r;
+	double rate(int k) const { return r[k]; }
+	std::istream& load(std::istream& in);          // cpp:57-72
+	std::ostream& save(std::ostream& out) const;   // cpp:74-90
+};
+
+// ---- unrooted phylogenetic tree as stored in <db>.ptu (src/PhyloTreeUnrooted.{h,cpp}) ----
+class PTUnrooted {
+public:
+	enum PRIOR_TYPE { UNIFORM, HEIGHT };
+	struct PTLoc { int start, end; long id; double dist; };          // .h:390-405
+	struct PTPlacement {                                             // .h:410-510
+		PTPlacement() : start(0), end(0), cNode(-1), pNode(-1), aNode(-1), wuv(0), ratio(0), wnr(0), loglik(0), height(0),
+				annoDist(0), qPlace(0), qTaxon(0) {}
+		std::string getId() const;
+		long getTaxonId() const { return aNode; }
+		int start, end;
+		long cNode, pNode, aNode;
+		double wuv, ratio, wnr, loglik, height, annoDist, qPlace, qTaxon;
+		std::string taxonName;
+		static const std::string TSV_HEADER;
+	};
+	PTUnrooted() : csLen(0), root(0), hasDG(false) {}
+	std::istream& load(std::istream& in);          // cpp:496-535
+	std::ostream& save(std::ostream& out) const;   // cpp:537-567
+	size_t numNodes() const { return parent.size(); }
+	int getCSLen() const { return csLen; }
+	double getHeight(long id) const { return height[id]; }
+	const std::string& getAnno(long id) const { return anno[id]; }
+	hu_tree_desc treeDesc() const;                 // view for hu_db_create (messages included)
+	hu_model_desc modelDesc() const;
+	PTPlacement toPlacement(const hu_place_row& row) const;
+	int csLen;
+	long root;
+	std::vector<int32_t> parent;
+	std::vector<double> blen, height, annoDist;
+	std::vector<std::string> name, anno;
+	std::vector<int8_t> seq;                       // numNodes x csLen
+	std::vector<int32_t> taxon;                    // id of the annotation string (equal strings share an id)
+	std::vector<double> up, dn;                    // [node][col][4]
+	std::vector<std::vector<long> > neighbors;     // file order, for save()
+	std::vector<double> rootLoglik;
+	std::vector<std::pair<unsigned, long> > msaIndex;
+	DNASubModel model;
+	bool hasDG;
+	DiscreteGammaModel dG;
+};
+std::ostream& operator<<(std::ostream& out, const PTUnrooted::PTPlacement& place); // .h:1611-1617
+
+// ---- the per-read pipeline, batched (src/HmmUFOtu_main.{h,cpp}) ----
+// Host half of alignSeq (src/HmmUFOtu_main.cpp:39-84): the CSFM seed search, in call order (it draws rand()).
+std::vector<BandedHMMP7::ViterbiAlignPath> findSeeds(const BandedHMMP7& hmm, const CSFMIndex& csfm, const PrimarySeq& read,
+		int seedLen, int seedRegion, BandedHMMP7::align_mode mode);
+
+} // namespace HmmUFOtu
+} // namespace EGriceLab
+
+#endif

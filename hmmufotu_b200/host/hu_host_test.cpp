@@ -1,0 +1,114 @@
+// Test driver of the host layer (CPU only), in the spirit of the reference's test/ programs:
+//   csfm               the known-answer test of /root/reference/test/CSFMIndex_test.cpp:19-63
+//   hmm  IN OUT        load a .hmm, save it (bHmm_IO_test.cpp); prints K L and a checksum of the costs
+//   ptu  IN OUT        load a .ptu, save it (PTU_IO_test.cpp:18-59); prints a summary
+//   msa  IN OUT        load a .msa, save it (MSAIO_test.cpp)
+//   seeds DB FASTA S   CSFM seed search of every read with srand(S): prints the ViterbiAlignPaths
+#include "hu_host.h"
+
+#include <stdlib.h>
+#include <string.h>
+#include <fstream>
+
+using namespace std;
+using namespace EGriceLab::HmmUFOtu;
+
+static int csfmTest() {
+	MSA msa;
+	msa.alphabet = "DNA"; msa.name = "toy"; msa.numSeq = 4; msa.csLen = 8; msa.isPruned = true;
+	const char* rows[4] = {"ATCGNATC", "-TCGAATC", "AT-GCATC", "ATCG-ATC"};
+	for (int i = 0; i < 4; ++i) { msa.seqNames.push_back(string("seq") + char('1' + i)); msa.concatMSA += rows[i]; }
+	msa.CS = "ATCGAATC";
+	CSFMIndex csfm;
+	csfm.build(msa);
+	int rc = 0;
+	const int32_t n = csfm.count("ATC");
+	cout << "count(ATC) = " << n << endl;
+	// ATC occurs at columns 1-3 in rows 1 and 4, and at columns 6-8 in all four rows
+	if (n != 6) rc = 1;
+	const vector<CSLoc> locs = csfm.locate("ATC");
+	for (size_t i = 0; i < locs.size(); ++i) {
+		cout << "loc " << locs[i].start << "-" << locs[i].end << " " << locs[i].CS << endl;
+		if (!((locs[i].start == 1 && locs[i].end == 3) || (locs[i].start == 6 && locs[i].end == 8))) rc = 1;
+	}
+	const CSLoc gap = csfm.locateFirst("TGC"); // row 3: T(2) -(3) G(4) C(5): the CS string shows the skipped column
+	cout << "TGC " << gap.start << "-" << gap.end << " " << gap.CS << endl;
+	if (!(gap.start == 2 && gap.end == 5 && gap.CS == "T-GC")) rc = 1;
+	if (csfm.count("GGGG") != 0 || csfm.locateOne("GGGG").isValid()) rc = 1;
+	srand(1);
+	const CSLoc one = csfm.locateOne("GAATC");
+	cout << "GAATC " << one.start << "-" << one.end << endl;
+	if (!(one.start == 4 && one.end == 8)) rc = 1;
+	cout << (rc ? "FAILED" : "OK") << endl;
+	return rc;
+}
+
+int main(int argc, char** argv) {
+	if (argc < 2) { cerr << "usage: hu_host_test csfm | hmm IN OUT | ptu IN OUT | msa IN OUT | seeds DB FASTA SEED" << endl; return 2; }
+	const string cmd = argv[1];
+	if (cmd == "csfm") return csfmTest();
+	if (cmd == "hmm" && argc == 4) {
+		ifstream in(argv[2]);
+		BandedHMMP7 hmm;
+		in >> hmm;
+		if (!in || in.bad()) { cerr << "cannot load " << argv[2] << endl; return 1; }
+		ofstream out(argv[3]);
+		out << hmm;
+		double sum = 0;
+		for (int k = 1; k <= hmm.K; ++k) sum += hmm.entryPr_cost[k] + hmm.exitPr_cost[k] + hmm.E_M_cost[(size_t) k * 4];
+		cout.precision(17);
+		cout << "K " << hmm.K << " L " << hmm.L << " checksum " << sum << endl;
+		return out.good() ? 0 : 1;
+	}
+	if (cmd == "ptu" && argc == 4) {
+		ifstream in(argv[2], ios_base::binary);
+		if (loadProgInfo(in).bad()) return 1;
+		PTUnrooted ptu;
+		ptu.load(in);
+		if (!in || in.bad()) { cerr << "cannot load " << argv[2] << endl; return 1; }
+		ofstream out(argv[3], ios_base::binary);
+		saveProgInfo(out);
+		ptu.save(out);
+		cout << "nodes " << ptu.numNodes() << " csLen " << ptu.csLen << " root " << ptu.root << " model " << ptu.model.modelType()
+			 << " dG " << (ptu.hasDG ? ptu.dG.K : 0) << endl;
+		return out.good() ? 0 : 1;
+	}
+	if (cmd == "msa" && argc == 4) {
+		ifstream in(argv[2], ios_base::binary);
+		if (loadProgInfo(in).bad()) return 1;
+		MSA msa;
+		msa.load(in);
+		if (!in || in.bad()) { cerr << "cannot load " << argv[2] << endl; return 1; }
+		ofstream out(argv[3], ios_base::binary);
+		saveProgInfo(out);
+		msa.save(out);
+		cout << "numSeq " << msa.numSeq << " csLen " << msa.csLen << endl;
+		return out.good() ? 0 : 1;
+	}
+	if (cmd == "seeds" && argc == 5) {
+		const string db = argv[2];
+		ifstream msaIn((db + ".msa").c_str(), ios_base::binary), hmmIn((db + ".hmm").c_str());
+		if (loadProgInfo(msaIn).bad()) return 1;
+		MSA msa;
+		msa.load(msaIn);
+		BandedHMMP7 hmm;
+		hmmIn >> hmm;
+		if (!msaIn || !hmmIn) { cerr << "cannot load " << db << endl; return 1; }
+		CSFMIndex csfm;
+		csfm.build(msa);
+		srand((unsigned) atoi(argv[4]));
+		ifstream fa(argv[3]);
+		SeqIO io(&fa, SeqIO::guessFormat(argv[3]));
+		while (io.hasNext()) {
+			const PrimarySeq r = io.nextSeq();
+			const vector<BandedHMMP7::ViterbiAlignPath> v = findSeeds(hmm, csfm, r, 20, 50, BandedHMMP7::GLOBAL);
+			cout << r.getId() << "\t" << v.size();
+			for (size_t i = 0; i < v.size(); ++i)
+				cout << "\t" << v[i].start << "," << v[i].end << "," << v[i].from << "," << v[i].to << "," << v[i].nIns << "," << v[i].nDel;
+			cout << endl;
+		}
+		return 0;
+	}
+	cerr << "bad arguments" << endl;
+	return 2;
+}

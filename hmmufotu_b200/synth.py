@@ -60,9 +60,9 @@ def model_text(m: Dict) -> str:
         Q = _rate_matrix(m)
         s += "Q:\n" + "".join(" ".join(fmt(v) for v in row) + "\n" for row in Q)
     elif m["type"] == TN93:
-        s += "kr: %s\nky: %s\nbeta: %s\n" % (fmt(m["kr"]), fmt(m["ky"]), fmt(m["beta"]))
+        s += "kr: %s ky: %s beta: %s\n" % (fmt(m["kr"]), fmt(m["ky"]), fmt(m["beta"]))
     elif m["type"] == HKY85:
-        s += "kappa: %s\nbeta: %s\n" % (fmt(m["kappa"]), fmt(m["beta"]))
+        s += "kappa: %s beta: %s\n" % (fmt(m["kappa"]), fmt(m["beta"]))
     elif m["type"] == F81:
         s += "beta: %s\n" % fmt(m["beta"])
     elif m["type"] == K80:
@@ -430,3 +430,111 @@ def make_reads(db: SynthDB, n: int, read_len: int = 250, seed: int = 1, window: 
         codes.append(bases.astype(np.int8))
         offsets[r + 1] = offsets[r] + N
     return ReadSet(np.concatenate(codes), offsets, vps, nps, src)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Database files in the reference's formats: <db>.msa, <db>.hmm, <db>.ptu.
+# (<db>.csfm holds libcds structures; this repo's host layer rebuilds the index from <db>.msa instead.)
+# ---------------------------------------------------------------------------------------------------------
+import struct
+
+_MAGIC = b"HmmUFOtu" + struct.pack("<iii", 1, 5, 1)
+
+
+def _wstr(f, s) -> None:
+    b = s if isinstance(s, (bytes, bytearray)) else s.encode()
+    f.write(struct.pack("<Q", len(b)))
+    f.write(b)
+
+
+def write_msa(db: SynthDB, path: str, name: str = "synth") -> None:
+    """MSA::save layout (/root/reference/src/MSA.cpp:295-360); rows = leaves in id order."""
+    leaves = db.leaves
+    rows = db.seq[leaves]
+    chars = np.where(rows >= 0, np.frombuffer(b"ACGT", dtype=np.uint8)[np.clip(rows, 0, 3)], ord("-")).astype(np.uint8)
+    n, L = rows.shape
+    with open(path, "wb") as f:
+        f.write(_MAGIC)
+        _wstr(f, "DNA")
+        _wstr(f, name)
+        f.write(struct.pack("<II", n, L))
+        cs = np.full(L, ord("-"), dtype=np.uint8)
+        for j in range(L):
+            col = rows[:, j]
+            col = col[col >= 0]
+            if col.size * 2 >= n:
+                cs[j] = b"ACGT"[int(np.bincount(col, minlength=4).argmax())]
+        _wstr(f, cs.tobytes())
+        f.write(struct.pack("<?", True))
+        for x in leaves:
+            _wstr(f, "leaf%d" % x)
+        _wstr(f, chars.tobytes())
+        valid = rows >= 0
+        first = np.where(valid.any(axis=1), valid.argmax(axis=1), -1).astype(np.int32)
+        last = np.where(valid.any(axis=1), L - 1 - valid[:, ::-1].argmax(axis=1), -1).astype(np.int32)
+        f.write(first.tobytes()); f.write(last.tobytes()); f.write(valid.sum(axis=1).astype(np.int32).tobytes())
+        res = np.stack([(rows == b).sum(axis=0) for b in range(4)], axis=1).astype(np.int32)      # column-major 4 x L
+        gap = (~valid).sum(axis=0).astype(np.int32)
+        f.write(res.tobytes()); f.write(gap.tobytes())
+        f.write(np.ones(n).tobytes()); f.write(res.astype(np.float64).tobytes()); f.write(gap.astype(np.float64).tobytes())
+
+
+def write_ptu(db: SynthDB, up: np.ndarray, dn: np.ndarray, path: str, anno=None) -> None:
+    """PTUnrooted::save layout (/root/reference/src/PhyloTreeUnrooted.cpp:537-567).  up/dn: [node][col][4] log-domain
+    messages; node sequences as currently held in db.seq (internal rows = inferred)."""
+    n, L = db.n_nodes, db.cs_len
+    anno = anno or ["k__Synth;p__Clade%d" % t for t in db.taxon]
+    nbrs = [[] for _ in range(n)]
+    for x in range(n):
+        if db.parent[x] >= 0:
+            nbrs[x].append(int(db.parent[x]))
+    for x in range(n):                      # children after the parent, ascending id
+        if db.parent[x] >= 0:
+            nbrs[int(db.parent[x])].append(x)
+    with open(path, "wb") as f:
+        f.write(_MAGIC)
+        f.write(struct.pack("<Qi", n, L))
+        for x in range(n):
+            f.write(struct.pack("<q", x))
+            _wstr(f, "node%d" % x)
+            f.write(struct.pack("<?", True))
+            _wstr(f, "DNA")
+            _wstr(f, "node%d" % x)
+            _wstr(f, db.seq[x].astype(np.int8).tobytes())
+            _wstr(f, anno[x])
+            f.write(struct.pack("<d", 0.0))
+        f.write(struct.pack("<Q", 2 * (n - 1)))
+        for u in range(n):
+            for v in nbrs[u]:
+                is_par = db.parent[v] == u
+                f.write(struct.pack("<qq?d", u, v, bool(is_par), float(db.blen[v] if is_par else db.blen[u])))
+                f.write(struct.pack("<Q", 4 * L))
+                f.write(np.ascontiguousarray(dn[v] if is_par else up[u], dtype=np.float64).tobytes())
+        f.write(struct.pack("<q", db.root))
+        f.write(np.zeros(4 * L).tobytes())
+        for x in range(n):
+            f.write(struct.pack("<qd", x, float(db.height[x])))
+        leaves = db.leaves
+        f.write(struct.pack("<I", leaves.size))
+        for i, x in enumerate(leaves):
+            f.write(struct.pack("<Iq", i, int(x)))
+        f.write((MODEL_NAMES[db.model["type"]] + "\n" + model_text(db.model)).encode())
+        if db.dg_rates.size:
+            K = db.dg_rates.size
+            f.write(struct.pack("<?id", True, K, 0.5))
+            f.write(np.zeros(K + 1).tobytes())
+            f.write(np.asarray(db.dg_rates, dtype=np.float64).tobytes())
+        else:
+            f.write(struct.pack("<?", False))
+
+
+def write_fasta(db_reads: "ReadSet", path: str, prefix: str = "read") -> None:
+    with open(path, "w") as f:
+        for i in range(db_reads.n):
+            f.write(">%s%d src_leaf=%d\n%s\n" % (prefix, i, db_reads.src_leaf[i], db_reads.read_str(i)))
+
+
+def write_db(db: SynthDB, up: np.ndarray, dn: np.ndarray, prefix: str) -> None:
+    write_msa(db, prefix + ".msa")
+    write_hmm(db, prefix + ".hmm")
+    write_ptu(db, up, dn, prefix + ".ptu")

@@ -1,0 +1,139 @@
+"""The C++ host layer (hmmufotu_b200/host): formats, CSFM seed index, command line.  CPU tests, plus one
+end-to-end run of the hmmufotu executable on a GPU."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle_py as O
+from hmmufotu_b200 import synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "hmmufotu_b200", "bin")
+
+
+@pytest.fixture(scope="module")
+def exes():
+    from hmmufotu_b200 import build
+    build.build_host()
+    return os.path.join(BIN, "hmmufotu"), os.path.join(BIN, "hu_host_test")
+
+
+@pytest.fixture(scope="module")
+def dbfiles(tmp_path_factory):
+    d = tmp_path_factory.mktemp("db")
+    db = synth.make_db(n_leaves=40, cs_len=600, occupancy=0.85, seed=21, dg_alpha=0.7)
+    otree = O.OracleTree(db)
+    db.seq = otree.seqs()
+    up, dn = otree.messages()
+    prefix = str(d / "synth")
+    synth.write_db(db, up, dn, prefix)
+    reads = synth.make_reads(db, 60, read_len=180, seed=4, drop_seed_prob=0.0)
+    synth.write_fasta(reads, prefix + "_reads.fa")
+    return dict(db=db, otree=otree, prefix=prefix, reads=reads, dir=str(d))
+
+
+def test_csfm_known_answers(exes):
+    """Same shape as the reference's only known-answer test (test/CSFMIndex_test.cpp:19-63)."""
+    out = subprocess.run([exes[1], "csfm"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "count(ATC) = 6" in out.stdout and out.stdout.strip().endswith("OK")
+
+
+def test_ptu_and_msa_roundtrip_bytes(exes, dbfiles):
+    """load -> save reproduces the files byte for byte (the reference's IO tests only check the stream state)."""
+    for kind in ("ptu", "msa"):
+        src = dbfiles["prefix"] + "." + kind
+        dst = os.path.join(dbfiles["dir"], "copy." + kind)
+        out = subprocess.run([exes[1], kind, src, dst], capture_output=True, text=True)
+        assert out.returncode == 0, out.stderr
+        a, b = open(src, "rb").read(), open(dst, "rb").read()
+        if kind == "msa":
+            assert a == b
+        else:  # the substitution model is text: digits may be printed differently, everything else is binary
+            cut = a.index(b"GTR\n# DNA")
+            assert a[:cut] == b[:cut]
+            dst2 = os.path.join(dbfiles["dir"], "copy2." + kind)
+            assert subprocess.run([exes[1], kind, dst, dst2]).returncode == 0
+            assert b == open(dst2, "rb").read()      # save(load(x)) is a fixed point
+            assert "nodes %d csLen %d root 0 model GTR dG 4" % (dbfiles["db"].n_nodes, dbfiles["db"].cs_len) in out.stdout
+
+
+def test_hmm_roundtrip_matches_oracle(exes, dbfiles):
+    src = dbfiles["prefix"] + ".hmm"
+    dst = os.path.join(dbfiles["dir"], "copy.hmm")
+    out = subprocess.run([exes[1], "hmm", src, dst], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    a, b = O.OracleHmm(path=src).params(), O.OracleHmm(path=dst).params()
+    for k in ("eI", "T", "entry", "exit", "p2cs", "cs2p"):
+        assert np.array_equal(a[k], b[k]), k
+    assert np.array_equal(a["eM"][1:], b["eM"][1:])
+    K, L, chk = out.stdout.split()[1], out.stdout.split()[3], float(out.stdout.split()[5])
+    assert (int(K), int(L)) == (dbfiles["db"].K, dbfiles["db"].cs_len)
+    want = (a["entry"][1:] + a["exit"][1:] + a["eM"][1:, 0]).sum()
+    assert abs(chk - want) < 1e-9 * abs(want)       # wing retraction on the host equals the oracle's
+
+
+def test_check_db(exes, dbfiles):
+    out = subprocess.run([exes[0], dbfiles["prefix"], "--check-db"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    assert "csLen %d, profile size %d, %d nodes, model GTR + dGamma" % (dbfiles["db"].cs_len, dbfiles["db"].K, dbfiles["db"].n_nodes) in out.stderr
+    bad = subprocess.run([exes[0], os.path.join(dbfiles["dir"], "nope"), "--check-db"], capture_output=True, text=True)
+    assert bad.returncode != 0 and "Unable to open" in bad.stderr
+    usage = subprocess.run([exes[0]], capture_output=True, text=True)
+    assert usage.returncode != 0 and "Usage:" in usage.stderr
+
+
+def test_seed_search_finds_the_source_columns(exes, dbfiles):
+    """findSeeds (host half of alignSeq) against the generator's own exact-match paths: same read interval,
+    profile interval within the few columns by which sequences holding the same 20-mer can differ."""
+    out = subprocess.run([exes[1], "seeds", dbfiles["prefix"], dbfiles["prefix"] + "_reads.fa", "7"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    rs = dbfiles["reads"]
+    lines = out.stdout.strip().split("\n")
+    assert len(lines) == rs.n
+    same = 0
+    for i, ln in enumerate(lines):
+        f = ln.split("\t")
+        n = int(f[1])
+        assert n >= rs.n_paths[i]                     # the index sees every occurrence, the generator only its own
+        got = [tuple(int(x) for x in p.split(",")) for p in f[2:]]
+        for g in got:
+            assert g[0] >= 1 and g[0] <= g[1] and g[2] >= 1 and g[2] <= g[3]
+        if n == rs.n_paths[i] and all(g[2:4] == tuple(rs.vpaths[i, k, 2:4]) and abs(g[0] - rs.vpaths[i, k, 0]) <= 3 for k, g in enumerate(got)):
+            same += 1
+    assert same >= 0.8 * rs.n
+
+
+@pytest.mark.gpu
+def test_cli_end_to_end(exes, dbfiles):
+    """hmmufotu <db> reads.fa -s 1 -S 0: every TSV row against the oracle fed with the same seeds."""
+    tsv = os.path.join(dbfiles["dir"], "out.tsv")
+    out = subprocess.run([exes[0], dbfiles["prefix"], dbfiles["prefix"] + "_reads.fa", "-o", tsv, "-s", "1", "-S", "0", "--batch", "32"],
+                         capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    seeds = subprocess.run([exes[1], "seeds", dbfiles["prefix"], dbfiles["prefix"] + "_reads.fa", "0"], capture_output=True, text=True).stdout.strip().split("\n")
+    rows = [ln.rstrip("\n").split("\t") for ln in open(tsv) if not ln.startswith("#")]
+    assert rows[0][:3] == ["id", "description", "seq_start"] and rows[0][-1] == "Q_taxon"
+    rs, db, otree = dbfiles["reads"], dbfiles["db"], dbfiles["otree"]
+    ohmm = O.OracleHmm(db)
+    assert len(rows) - 1 == rs.n
+    for i in range(rs.n):
+        r = rows[1 + i]
+        vp = np.array([[int(x) for x in p.split(",")] for p in seeds[i].split("\t")[2:]], dtype=np.int32).reshape(-1, 6)
+        a = ohmm.align(rs.read_str(i), vp)
+        assert r[0] == "read%d" % i and r[1] == "src_leaf=%d" % rs.src_leaf[i]
+        assert [int(x) for x in r[2:8]] == list(a["coords"])
+        assert r[8] == "%g" % a["cost"]
+        assert r[9] == a["align"]
+        seq = O.digitize(a["align"])
+        s, e = a["coords"][4] - 1, a["coords"][5] - 1
+        ids, dist = otree.get_seed(seq, s, e, 50, order=1)
+        want = otree.assign(seq, s, e, ids, dist)
+        est = sorted(w.estLoglik for w in want)
+        tied = any(abs(x - y) <= 1e-11 * abs(x) for x, y in zip(est, est[1:]))
+        if not tied:
+            assert r[10] == "%d->%d" % (want[0].c, want[0].p), i
+            assert r[12] == str(want[0].a)
+            assert r[15] == "%g" % want[0].loglik and r[16] == "%g" % want[0].qPlace
