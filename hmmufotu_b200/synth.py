@@ -363,6 +363,60 @@ def _build_vpath(db: SynthDB, cols: np.ndarray, frm: int) -> Optional[np.ndarray
     return np.array([start, end, frm, to, nins, ndel], dtype=np.int32)
 
 
+def _one_read(db: SynthDB, rng, row: np.ndarray, cols: np.ndarray, sub_rate: float, indel_prob: float, seed_len: int,
+              seed_region: int, drop_seed: bool):
+    """Copy the residues at `cols` of one leaf row, mutate lightly, and return (bases, vpaths) with the
+    ViterbiAlignPaths of the first exact 5' and 3' seeds (HmmUFOtu_main.cpp:52-84)."""
+    cols = cols.copy()
+    L = cols.size
+    bases = row[cols].copy()
+    exact = np.ones(L, dtype=bool)                 # base i is an unmodified copy of column cols[i]
+    mut = rng.random(L) < sub_rate
+    bases[mut] = (bases[mut] + rng.integers(1, 4, int(mut.sum()))) % 4
+    exact[mut] = False
+    if rng.random() < indel_prob and L > 60:       # one deletion
+        i = int(rng.integers(25, L - 25))
+        bases = np.delete(bases, i); cols = np.delete(cols, i); exact = np.delete(exact, i)
+        exact[i - 1:i + 1] = False
+    if rng.random() < indel_prob and L > 60:       # one insertion
+        i = int(rng.integers(25, bases.size - 25))
+        bases = np.insert(bases, i, rng.integers(0, 4)); cols = np.insert(cols, i, -1); exact = np.insert(exact, i, False)
+    N = bases.size
+    paths = []
+    region = min(seed_region, N)
+    if not drop_seed:
+        for sf in range(0, region - seed_len + 1):  # 5' seed
+            if exact[sf:sf + seed_len].all():
+                vp = _build_vpath(db, cols[sf:sf + seed_len], sf + 1)
+                if vp is not None:
+                    paths.append(vp)
+                    break
+        if not paths or N >= 2 * region:             # 3' seed
+            for st in range(N - 1, N - region + seed_len - 2, -1):
+                sf = st - seed_len + 1
+                if sf < 0:
+                    break
+                if exact[sf:st + 1].all():
+                    vp = _build_vpath(db, cols[sf:st + 1], sf + 1)
+                    if vp is not None:
+                        paths.append(vp)
+                        break
+    return bases.astype(np.int8), paths
+
+
+def _pack(reads, src) -> ReadSet:
+    n = len(reads)
+    vps = np.zeros((n, 2, 6), dtype=np.int32)
+    nps = np.zeros(n, dtype=np.int32)
+    offsets = np.zeros(n + 1, dtype=np.int64)
+    for r, (bases, paths) in enumerate(reads):
+        nps[r] = len(paths)
+        for i, vp in enumerate(paths):
+            vps[r, i] = vp
+        offsets[r + 1] = offsets[r] + bases.size
+    return ReadSet(np.concatenate([b for b, _ in reads]), offsets, vps, nps, np.asarray(src, dtype=np.int32))
+
+
 def make_reads(db: SynthDB, n: int, read_len: int = 250, seed: int = 1, window: Optional[tuple] = None,
                sub_rate: float = 0.01, indel_prob: float = 0.1, seed_len: int = 20, seed_region: int = 50,
                len_sd: float = 0.0, drop_seed_prob: float = 0.02) -> ReadSet:
@@ -372,11 +426,7 @@ def make_reads(db: SynthDB, n: int, read_len: int = 250, seed: int = 1, window: 
     (the "V4-like" shape of SURVEY.md 8(d) config C3); None: anywhere the read fits."""
     rng = np.random.default_rng(seed)
     leaves = db.leaves
-    codes: List[np.ndarray] = []
-    vps = np.zeros((n, 2, 6), dtype=np.int32)
-    nps = np.zeros(n, dtype=np.int32)
-    src = np.zeros(n, dtype=np.int32)
-    offsets = np.zeros(n + 1, dtype=np.int64)
+    reads, src = [], []
     for r in range(n):
         leaf = int(leaves[rng.integers(leaves.size)])
         row = db.seq[leaf]
@@ -389,47 +439,33 @@ def make_reads(db: SynthDB, n: int, read_len: int = 250, seed: int = 1, window: 
             s = min(s, pos.size - L)
         else:
             s = int(rng.integers(0, pos.size - L + 1))
-        cols = pos[s:s + L].copy()
-        bases = row[cols].copy()
-        exact = np.ones(L, dtype=bool)                 # base i is an unmodified copy of column cols[i]
-        mut = rng.random(L) < sub_rate
-        bases[mut] = (bases[mut] + rng.integers(1, 4, int(mut.sum()))) % 4
-        exact[mut] = False
-        if rng.random() < indel_prob and L > 60:       # one deletion
-            i = int(rng.integers(25, L - 25))
-            bases = np.delete(bases, i); cols = np.delete(cols, i); exact = np.delete(exact, i)
-            exact[i - 1:i + 1] = False
-        if rng.random() < indel_prob and L > 60:       # one insertion
-            i = int(rng.integers(25, bases.size - 25))
-            bases = np.insert(bases, i, rng.integers(0, 4)); cols = np.insert(cols, i, -1); exact = np.insert(exact, i, False)
-        N = bases.size
-        paths = []
         drop = rng.random() < drop_seed_prob           # occasionally no seed at all -> full Viterbi
-        region = min(seed_region, N)
-        if not drop:
-            for sf in range(0, region - seed_len + 1):  # 5' seed (HmmUFOtu_main.cpp:52-66)
-                if exact[sf:sf + seed_len].all():
-                    vp = _build_vpath(db, cols[sf:sf + seed_len], sf + 1)
-                    if vp is not None:
-                        paths.append(vp)
-                        break
-            if not paths or N >= 2 * region:             # 3' seed (HmmUFOtu_main.cpp:68-84)
-                for st in range(N - 1, N - region + seed_len - 2, -1):
-                    sf = st - seed_len + 1
-                    if sf < 0:
-                        break
-                    if exact[sf:st + 1].all():
-                        vp = _build_vpath(db, cols[sf:st + 1], sf + 1)
-                        if vp is not None:
-                            paths.append(vp)
-                            break
-        nps[r] = len(paths)
-        for i, vp in enumerate(paths):
-            vps[r, i] = vp
-        src[r] = leaf
-        codes.append(bases.astype(np.int8))
-        offsets[r + 1] = offsets[r] + N
-    return ReadSet(np.concatenate(codes), offsets, vps, nps, src)
+        reads.append(_one_read(db, rng, row, pos[s:s + L], sub_rate, indel_prob, seed_len, seed_region, drop))
+        src.append(leaf)
+    return _pack(reads, src)
+
+
+def make_pairs(db: SynthDB, n: int, read_len: int = 150, insert_len: int = 260, insert_sd: float = 15.0, seed: int = 1,
+               sub_rate: float = 0.01, indel_prob: float = 0.1, swap_prob: float = 0.0):
+    """Paired-end reads: a fragment of ~insert_len residues of one leaf; the forward read is its first read_len
+    bases, the mate its last read_len bases -- returned already in forward orientation, as the reference holds
+    it after `revSeqI.nextSeq().revcom()` (src/hmmufotu.cpp:609).  swap_prob: fraction of pairs handed over in the
+    wrong order (mate upstream), which the orientation test must flag as chimera.  -> (fwd ReadSet, mate ReadSet)"""
+    rng = np.random.default_rng(seed)
+    leaves = db.leaves
+    fwd, rev, src = [], [], []
+    for r in range(n):
+        leaf = int(leaves[rng.integers(leaves.size)])
+        row = db.seq[leaf]
+        pos = np.flatnonzero(row >= 0)
+        F = int(np.clip(round(rng.normal(insert_len, insert_sd)), read_len + 10, pos.size))
+        s = int(rng.integers(0, pos.size - F + 1))
+        a = _one_read(db, rng, row, pos[s:s + read_len], sub_rate, indel_prob, 20, 50, False)
+        b = _one_read(db, rng, row, pos[s + F - read_len:s + F], sub_rate, indel_prob, 20, 50, False)
+        if rng.random() < swap_prob:
+            a, b = b, a
+        fwd.append(a); rev.append(b); src.append(leaf)
+    return _pack(fwd, src), _pack(rev, src)
 
 
 # ---------------------------------------------------------------------------------------------------------
