@@ -127,6 +127,16 @@ class CpuReference:
 
 
 def main():
+    # stdout carries exactly ONE JSON line: everything else that libraries print there (e.g. NCCL's version
+    # banner) is sent to stderr
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    rc = _main(real_stdout)
+    real_stdout.flush()
+    return rc
+
+
+def _main(real_stdout):
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=6)
@@ -165,7 +175,7 @@ def main():
                     cpu_baseline=dict(value=v, unit="reads/s", cores=cores, kind="port",
                                       sample="%d reads per step on %d threads; oracle tree cut to consensus columns %d..%d" % (sample, cores, vals[0]["columns"][0], vals[0]["columns"][1])),
                     e2e=dict(value=v, unit="reads/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=real_stdout, flush=True)
         return 0
 
     import torch
@@ -320,12 +330,12 @@ def main():
     line = dict(metric=METRIC, value=value, unit="reads/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
                 ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
                 config=dict(workload=cfg["workload"], batch=B, parallelism="replicated DB, reads sharded x%d" % world,
-                            l2="inputs larger than L2 (DB %.0f GB, per-batch key matrix %.1f GB)" % (gdb.bytes / 1e9, B * db.n_nodes * 8 / 1e9),
+                            l2="inputs larger than L2 (DB %.0f GB, per-batch key matrix %.1f GB)" % (gdb.bytes / 1e9, B * db.n_nodes * 4 / 1e9),
                             workspaces=n_ws),
                 e2e=dict(value=e2e_value, unit="reads/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h),
                 gpu_launches=int(launches_per_step * args.steps), roofline=roofline, cpu_baseline=cpu, clocks=clocks,
                 viterbi_gcups=stages[names[0]].get("gcups"), stages=stages)
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=real_stdout, flush=True)
     return 0
 
 

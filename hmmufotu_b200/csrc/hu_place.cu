@@ -35,9 +35,26 @@ struct PlaceArgs {
 	double* slab;      // [warp slots][csLen]
 };
 
-struct WarpShared {
-	double P[3][HU_MAX_DG][16]; // P(lu r_k), P(lv r_k), P(ln r_k)
-	double NP[HU_MAX_DG][5][4]; // P(ln r_k) applied to the leaf vector of base b / gap (linear)
+// per-warp shared memory: P[3][KK][16] = P(lu r_k), P(lv r_k), P(ln r_k); NP[KK][5][4] = P(ln r_k) applied to the
+// leaf vector of base b / gap (linear); sized by the actual number of rate categories KK
+__host__ __device__ inline int placeWarpDoubles(int KK) { return 3 * KK * 16 + KK * 20; }
+
+// register double buffer over the columns of one lane: the loads of column c+32 are in flight while column c
+// is being worked on (the rebuild loops were stalled on these loads: 12 warps per SM cannot hide HBM latency)
+struct ColPrefetch {
+	double eu[4], ev[4];
+	int b;
+	__device__ __forceinline__ void init(const double* U, const double* V, const int8_t* x, int c, int W) {
+		b = 0;
+		if (c < W) { ld4(U + (size_t) c * 4, eu); ld4(V + (size_t) c * 4, ev); b = x[c]; }
+	}
+	// hands out the buffered column and starts loading column `cn`
+	__device__ __forceinline__ int next(const double* U, const double* V, const int8_t* x, int cn, int W, double* ou, double* ov) {
+		for (int k = 0; k < 4; ++k) { ou[k] = eu[k]; ov[k] = ev[k]; }
+		const int ob = b;
+		if (cn < W) { ld4(U + (size_t) cn * 4, eu); ld4(V + (size_t) cn * 4, ev); b = x[cn]; }
+		return ob;
+	}
 };
 
 __device__ __forceinline__ double warpSum(double v) {
@@ -93,11 +110,12 @@ __device__ double emBranch(const double* __restrict__ rho, int W, int nValid, do
 __global__ void __launch_bounds__(HU_PLACE_WARPS * 32) placeKernel(PlaceArgs a, TreeDev t, Model m) {
 	extern __shared__ __align__(16) unsigned char smemRaw[];
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	WarpShared* ws = reinterpret_cast<WarpShared*>(smemRaw) + warp;
-	double* rhoS = reinterpret_cast<double*>(smemRaw + sizeof(WarpShared) * HU_PLACE_WARPS) + (size_t) warp * a.capW;
+	const int KK = m.dgK > 0 ? m.dgK : 1;
+	double* wsP = reinterpret_cast<double*>(smemRaw) + (size_t) warp * placeWarpDoubles(KK);
+	double* wsNP = wsP + 3 * KK * 16;
+	double* rhoS = reinterpret_cast<double*>(smemRaw) + (size_t) HU_PLACE_WARPS * placeWarpDoubles(KK) + (size_t) warp * a.capW;
 	const int slot = blockIdx.x * HU_PLACE_WARPS + warp;
 	const int total = a.nReads * a.maxNSeed;
-	const int KK = m.dgK > 0 ? m.dgK : 1;
 	double piSq = 0; // pi . pi: (pi . n) for a gap column of the read
 	for (int k = 0; k < 4; ++k) piSq += m.pi[k] * m.pi[k];
 	for (;;) {
@@ -125,20 +143,20 @@ __global__ void __launch_bounds__(HU_PLACE_WARPS * 32) placeKernel(PlaceArgs a, 
 		for (iter = 0; iter < HU_MAX_ITER && 0 <= wur && wur <= w0j; ++iter) {
 			// ---- msg(r->n) from u and v, then optimise the n-r branch (cap 1) ----
 			__syncwarp();
-			if (lane < KK) modelPr(m, lu * (m.dgK ? m.dgR[lane] : 1.0), ws->P[0][lane]);
-			else if (lane >= 8 && lane < 8 + KK) modelPr(m, lv * (m.dgK ? m.dgR[lane - 8] : 1.0), ws->P[1][lane - 8]);
+			if (lane < KK) modelPr(m, lu * (m.dgK ? m.dgR[lane] : 1.0), wsP + (0 * KK + (lane)) * 16);
+			else if (lane >= 8 && lane < 8 + KK) modelPr(m, lv * (m.dgK ? m.dgR[lane - 8] : 1.0), wsP + (1 * KK + (lane - 8)) * 16);
 			__syncwarp();
 			int nValid = 0;
+			ColPrefetch pf;
+			pf.init(U, V, x, lane, W);
 			for (int cI = lane; cI < W; cI += 32) {
 				double eu[4], ev[4], ya[4], yb[4], g[4] = {0, 0, 0, 0};
-				ld4(U + (size_t) cI * 4, eu);
-				ld4(V + (size_t) cI * 4, ev);
+				const int b = pf.next(U, V, x, cI + 32, W, eu, ev);
 				for (int k = 0; k < KK; ++k) {
-					matVec4(ws->P[0][k], eu, ya);
-					matVec4(ws->P[1][k], ev, yb);
+					matVec4(wsP + (0 * KK + (k)) * 16, eu, ya);
+					matVec4(wsP + (1 * KK + (k)) * 16, ev, yb);
 					for (int i = 0; i < 4; ++i) g[i] += ya[i] * yb[i];
 				}
-				const int b = x[cI];
 				// A = log pi.(g n), B = log pi.g + log pi.n; the 1/K of the rate mixture cancels
 				const double num = b >= 0 ? m.pi[b] * g[b] : ((m.pi[0] * m.pi[0] * g[0] + m.pi[2] * m.pi[2] * g[2]) + (m.pi[1] * m.pi[1] * g[1] + m.pi[3] * m.pi[3] * g[3]));
 				const double den = dotPi(m, g) * (b >= 0 ? m.pi[b] : piSq);
@@ -152,25 +170,24 @@ __global__ void __launch_bounds__(HU_PLACE_WARPS * 32) placeKernel(PlaceArgs a, 
 			ln = wnr;
 			// ---- msg(r->u) from v and n, then optimise the u-r branch (cap w0) ----
 			__syncwarp();
-			if (lane < KK) modelPr(m, ln * (m.dgK ? m.dgR[lane] : 1.0), ws->P[2][lane]);
+			if (lane < KK) modelPr(m, ln * (m.dgK ? m.dgR[lane] : 1.0), wsP + (2 * KK + (lane)) * 16);
 			__syncwarp();
 			for (int q = lane; q < KK * 5; q += 32) {
 				const int k = q / 5, b = q % 5;
 				double n[4], y[4];
 				leafLin(m, b < 4 ? b : -1, n);
-				matVec4(ws->P[2][k], n, y);
-				for (int i = 0; i < 4; ++i) ws->NP[k][b][i] = y[i];
+				matVec4(wsP + (2 * KK + (k)) * 16, n, y);
+				for (int i = 0; i < 4; ++i) wsNP[(k * 5 + b) * 4 + i] = y[i];
 			}
 			__syncwarp();
 			nValid = 0;
+			pf.init(U, V, x, lane, W);
 			for (int cI = lane; cI < W; cI += 32) {
 				double eu[4], ev[4], yb[4], g[4] = {0, 0, 0, 0};
-				ld4(U + (size_t) cI * 4, eu);
-				ld4(V + (size_t) cI * 4, ev);
-				const int b = x[cI];
+				const int b = pf.next(U, V, x, cI + 32, W, eu, ev);
 				for (int k = 0; k < KK; ++k) {
-					matVec4(ws->P[1][k], ev, yb);
-					const double* np = ws->NP[k][b >= 0 ? b : 4];
+					matVec4(wsP + (1 * KK + (k)) * 16, ev, yb);
+					const double* np = wsNP + (k * 5 + (b >= 0 ? b : 4)) * 4;
 					for (int i = 0; i < 4; ++i) g[i] += yb[i] * np[i];
 				}
 				double z[4];
@@ -193,29 +210,29 @@ __global__ void __launch_bounds__(HU_PLACE_WARPS * 32) placeKernel(PlaceArgs a, 
 		}
 		// ---- intended root log-likelihood: sum_j log(pi . exp(loglik(r, j))) ----
 		__syncwarp();
-		if (lane < KK) modelPr(m, lu * (m.dgK ? m.dgR[lane] : 1.0), ws->P[0][lane]);
-		else if (lane >= 8 && lane < 8 + KK) modelPr(m, lv * (m.dgK ? m.dgR[lane - 8] : 1.0), ws->P[1][lane - 8]);
-		else if (lane >= 16 && lane < 16 + KK) modelPr(m, ln * (m.dgK ? m.dgR[lane - 16] : 1.0), ws->P[2][lane - 16]);
+		if (lane < KK) modelPr(m, lu * (m.dgK ? m.dgR[lane] : 1.0), wsP + (0 * KK + (lane)) * 16);
+		else if (lane >= 8 && lane < 8 + KK) modelPr(m, lv * (m.dgK ? m.dgR[lane - 8] : 1.0), wsP + (1 * KK + (lane - 8)) * 16);
+		else if (lane >= 16 && lane < 16 + KK) modelPr(m, ln * (m.dgK ? m.dgR[lane - 16] : 1.0), wsP + (2 * KK + (lane - 16)) * 16);
 		__syncwarp();
 		for (int q = lane; q < KK * 5; q += 32) {
 			const int k = q / 5, b = q % 5;
 			double n[4], y[4];
 			leafLin(m, b < 4 ? b : -1, n);
-			matVec4(ws->P[2][k], n, y);
-			for (int i = 0; i < 4; ++i) ws->NP[k][b][i] = y[i];
+			matVec4(wsP + (2 * KK + (k)) * 16, n, y);
+			for (int i = 0; i < 4; ++i) wsNP[(k * 5 + b) * 4 + i] = y[i];
 		}
 		__syncwarp();
 		double tl = 0;
+		ColPrefetch pf;
+		pf.init(U, V, x, lane, W);
 		for (int cI = lane; cI < W; cI += 32) {
 			double eu[4], ev[4], ya[4], yb[4], g[4] = {0, 0, 0, 0};
-			ld4(U + (size_t) cI * 4, eu);
-			ld4(V + (size_t) cI * 4, ev);
 			const double sc = __ldg(US + cI) + __ldg(VS + cI);
-			const int b = x[cI];
+			const int b = pf.next(U, V, x, cI + 32, W, eu, ev);
 			for (int k = 0; k < KK; ++k) {
-				matVec4(ws->P[0][k], eu, ya);
-				matVec4(ws->P[1][k], ev, yb);
-				const double* np = ws->NP[k][b >= 0 ? b : 4];
+				matVec4(wsP + (0 * KK + (k)) * 16, eu, ya);
+				matVec4(wsP + (1 * KK + (k)) * 16, ev, yb);
+				const double* np = wsNP + (k * 5 + (b >= 0 ? b : 4)) * 4;
 				for (int i = 0; i < 4; ++i) g[i] += (ya[i] * yb[i]) * np[i];
 			}
 			tl += log(dotPi(m, g) / (double) KK) + sc;
@@ -314,13 +331,14 @@ int launchPlace(hu_batch* b, const hu_sep_params* p) {
 	a.cursor = b->workCount + 1;
 	int sms = 0;
 	HU_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, db->device));
-	const int ctasPerSm = 3;
+	const int ctasPerSm = 4;
 	const int grid = sms * ctasPerSm;
-	const size_t smem = sizeof(WarpShared) * HU_PLACE_WARPS + (size_t) HU_PLACE_WARPS * HU_PLACE_CAPW * sizeof(double);
-	static bool attr = false;
-	if (!attr) {
+	const int KKh = db->model.dgK > 0 ? db->model.dgK : 1;
+	const size_t smem = (size_t) HU_PLACE_WARPS * (placeWarpDoubles(KKh) + HU_PLACE_CAPW) * sizeof(double);
+	static size_t attr = 0;
+	if (smem > attr) {
 		HU_CUDA(cudaFuncSetAttribute(placeKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-		attr = true;
+		attr = smem;
 	}
 	// global slab for windows wider than the shared-memory capacity
 	const size_t slabBytes = (size_t) grid * HU_PLACE_WARPS * db->tree.csLen * sizeof(double);
