@@ -1,0 +1,107 @@
+"""-m gpu: BASELINE.json configs[2] at full size (99 322 leaves, 198 643 nodes, csLen 7 682; ~125 GB on the
+device) through size-independent properties -- the oracle cannot hold this database, so nothing here uses it."""
+import numpy as np
+import pytest
+
+from hmmufotu_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def full():
+    import torch
+    from hmmufotu_b200 import engine
+    if torch.cuda.get_device_properties(0).total_memory < 150e9:
+        pytest.skip("needs a 180 GB device")
+    db = synth.make_db(n_leaves=99322, cs_len=7682, occupancy=0.18, seed=20260103)
+    gdb = engine.Database(db, device=0)               # all 397 284 messages evaluated on the device
+    db.seq = None                                      # the inferred sequences live on the device
+    reads = synth.make_reads(synth_db_for_reads(db), 1024, read_len=250, seed=77, window=(2000, 2300))
+    return dict(db=db, gdb=gdb, reads=reads, engine=engine)
+
+
+_LEAFSEQ = {}
+
+
+def synth_db_for_reads(db):
+    """make_reads needs leaf rows only; db.seq was dropped above to save host memory, so regenerate it once."""
+    if "db" not in _LEAFSEQ:
+        _LEAFSEQ["db"] = synth.make_db(n_leaves=99322, cs_len=7682, occupancy=0.18, seed=20260103)
+    return _LEAFSEQ["db"]
+
+
+def test_tree_likelihood_is_the_same_on_every_edge(full):
+    """Felsenstein's pulley principle: log(pi . ((P(b_x) e^up_x) * e^dn_x)) is the column's tree log-likelihood
+    whichever edge x it is evaluated on -- a check of the level-synchronous all-roots evaluation (depth 39)."""
+    engine, gdb, db = full["engine"], full["gdb"], full["db"]
+    rng = np.random.default_rng(5)
+    cols = rng.choice(db.cs_len, 48, replace=False)
+    nodes = rng.choice(np.arange(1, db.n_nodes), 40, replace=False)
+    pi = np.asarray(db.model["pi"])
+    ll = np.zeros((nodes.size, cols.size))
+    for a, x in enumerate(nodes):
+        up, dn = gdb.messages(int(x), 1)
+        P = engine.model_Pr(db.model, float(db.blen[x]))
+        u, d = up[0][cols], dn[0][cols]                       # [cols, 4] log domain
+        su, sd = u.max(axis=1, keepdims=True), d.max(axis=1, keepdims=True)
+        ll[a] = np.log(((np.exp(u - su) @ P.T) * np.exp(d - sd)) @ pi) + su[:, 0] + sd[:, 0]
+    assert np.isfinite(ll).all()
+    np.testing.assert_allclose(ll, np.broadcast_to(ll[0], ll.shape), rtol=1e-10)
+
+
+def test_pipeline_properties_and_determinism(full):
+    engine, gdb, db, rs = full["engine"], full["gdb"], full["db"], full["reads"]
+    n = rs.n
+    p = engine.SepParams()
+    outs = []
+    for rep in range(2):
+        b = engine.Batch(gdb, n, 260)
+        b.upload(rs)
+        b.assign(p)
+        rows, traces = b.alignments()
+        ns, ids, dist = b.seeds(with_dist=True)
+        nk, est = b.estimates()
+        _, pl = b.places()
+        best = b.best()
+        codes = b.aligned_codes() if rep == 0 else None
+        outs.append((rows.tobytes(), tuple(traces), ns.tobytes(), ids.tobytes(), dist.tobytes(), nk.tobytes(), est.tobytes(), pl.tobytes(), best.tobytes()))
+        b.close()
+    assert outs[0] == outs[1]                                    # bit-identical across workspaces and runs
+    lens = np.diff(rs.offsets)
+    assert (rows["flags"] & 16 == 0).all()
+    assert (rows["seqStart"] == 1).all() and (rows["seqEnd"] == lens).all()          # GLOBAL mode: the whole read aligns
+    for i in range(n):
+        t = traces[i]
+        assert t[0] == "B" and t[-1] == "E" and t.count("M") + t.count("I") == lens[i]
+        assert rows["hmmEnd"][i] - rows["hmmStart"][i] + 1 == t.count("M") + t.count("D")
+    assert (rows["cost"] > 0).all() and np.isfinite(rows["cost"]).all()
+    # seeds: 50 distinct non-root nodes in non-decreasing p-distance
+    assert (ns == 50).all()
+    assert (np.diff(dist, axis=1) >= 0).all()
+    assert all(len(set(ids[i])) == 50 and db.root not in ids[i] for i in range(n))
+    # exact check of the scan + select against a host scan of all 198 642 nodes, for a few reads
+    seq_dev = gdb.seqs()
+    for i in (0, n // 2, n - 1):
+        s, e = rows["csStart"][i] - 1, rows["csEnd"][i] - 1
+        x = codes[i, s:e + 1]
+        sub = seq_dev[:, s:e + 1]
+        both = (sub >= 0) & (x >= 0)[None, :]
+        N = both.sum(axis=1)
+        d = (both & (sub != x[None, :])).sum(axis=1)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            dd = d / N
+        dd[db.root] = np.inf
+        order = np.lexsort((np.arange(db.n_nodes), dd))[:50]
+        assert np.array_equal(order, ids[i]), i
+        assert np.array_equal(dd[order], dist[i]), i
+    # estimates in descending order inside the error window, placements inside their boxes
+    for i in range(n):
+        e_ = est[i, :nk[i]]["estLoglik"]
+        assert nk[i] >= 1 and (np.diff(e_) <= 0).all() and e_[0] - e_[-1] <= 20.0
+        q = pl[i, :nk[i]]
+        assert ((q["ratio"] >= 0) & (q["ratio"] <= 1) & (q["wnr"] >= 0) & (q["wnr"] <= 1)).all()
+        W = rows["csEnd"][i] - rows["csStart"][i] + 1
+        assert np.allclose(q["loglik"], W, rtol=1e-9)            # literal placeSeq return: W (1 + log sum(pi))
+        assert (q["outerIters"] >= 1).all() and (q["loglikTrue"] < 0).all()
+        assert best[i]["nPlaces"] == nk[i] and best[i]["cNode"] in q["cNode"]
