@@ -64,7 +64,8 @@ def test_pipeline_properties_and_determinism(full):
         nk, est = b.estimates()
         _, pl = b.places()
         best = b.best()
-        codes = b.aligned_codes() if rep == 0 else None
+        if rep == 0:
+            codes = b.aligned_codes()
         outs.append((rows.tobytes(), tuple(traces), ns.tobytes(), ids.tobytes(), dist.tobytes(), nk.tobytes(), est.tobytes(), pl.tobytes(), best.tobytes()))
         b.close()
     assert outs[0] == outs[1]                                    # bit-identical across workspaces and runs
