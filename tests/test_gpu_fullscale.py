@@ -101,7 +101,7 @@ def test_pipeline_properties_and_determinism(full):
         e_ = est[i, :nk[i]]["estLoglik"]
         assert nk[i] >= 1 and (np.diff(e_) <= 0).all() and e_[0] - e_[-1] <= 20.0
         q = pl[i, :nk[i]]
-        assert ((q["ratio"] >= 0) & (q["ratio"] <= 1) & (q["wnr"] >= 0) & (q["wnr"] <= 1)).all()
+        assert ((q["ratio"] >= 0) & (q["ratio"] <= 1 + 1e-12) & (q["wnr"] >= 0) & (q["wnr"] <= 1)).all()  # w0*r + w0*(1-r) can exceed w0 by an ulp
         W = rows["csEnd"][i] - rows["csStart"][i] + 1
         assert np.allclose(q["loglik"], W, rtol=1e-9)            # literal placeSeq return: W (1 + log sum(pi))
         assert (q["outerIters"] >= 1).all() and (q["loglikTrue"] < 0).all()
