@@ -11,6 +11,7 @@ LIB_PATH = os.path.join(HERE, "lib", "libhmmufotu_b200.so")
 HU_MAX_SEED = 64
 HU_MAX_DG = 8
 GLOBAL, LOCAL, NGCL, CGNL = 0, 1, 2, 3
+SEED_ORDER_STDSORT, SEED_ORDER_ID = 0, 1
 ALIGN_FALLBACK, ALIGN_NOSEED, ALIGN_IRREGULAR, ALIGN_CHIMERA, ALIGN_INVALID = 1, 2, 4, 8, 16
 
 
@@ -52,7 +53,8 @@ class PlaceRow(C.Structure):
 
 class SepParams(C.Structure):
     _fields_ = [("maxNSeed", C.c_int32), ("useTrueLoglik", C.c_int32), ("maxDiff", C.c_double),
-                ("maxHeight", C.c_double), ("maxError", C.c_double), ("equalSortPerm", C.c_void_p)]
+                ("maxHeight", C.c_double), ("maxError", C.c_double), ("equalSortPerm", C.c_void_p),
+                ("seedOrder", C.c_int32), ("reserved", C.c_int32)]
 
 
 class BatchStats(C.Structure):

@@ -123,6 +123,8 @@ void hu_sep_params_default(hu_sep_params* p) {
 	p->maxHeight = INFINITY;
 	p->maxError = 20;
 	p->equalSortPerm = NULL;
+	p->seedOrder = HU_SEED_ORDER_STDSORT;
+	p->reserved = 0;
 }
 
 int hu_batch_create(hu_batch** out, hu_db* db, int32_t maxReads, int32_t maxSeqLen, int32_t paired) {
@@ -135,7 +137,7 @@ int hu_batch_create(hu_batch** out, hu_db* db, int32_t maxReads, int32_t maxSeqL
 	b->db = db; b->maxReads = maxReads; b->maxSeqLen = maxSeqLen; b->paired = paired ? 1 : 0;
 	b->maxSeq = maxReads * (paired ? 2 : 1);
 	b->nReads = b->nSeq = 0; b->launches = 0;
-	b->dPtrs = NULL; b->ptrsCap = 0; b->placeSlab = NULL;
+	b->dPtrs = NULL; b->ptrsCap = 0; b->placeSlab = NULL; b->litIds = NULL;
 	*out = b;
 	HU_CUDA(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
 	for (int i = 0; i < 16; ++i) HU_CUDA(cudaEventCreate(&b->ev[i]));
@@ -175,6 +177,7 @@ int hu_batch_create(hu_batch** out, hu_db* db, int32_t maxReads, int32_t maxSeqL
 	b->seed.sparseCap = maxSeqLen * (paired ? 2 : 1); // a read cannot have more bases in non-match columns than bases
 	HU_TRY(balloc(b, &b->seed.sparse, (size_t) maxReads * b->seed.sparseCap));
 	HU_TRY(balloc(b, &b->seed.keys, (size_t) maxReads * t.scanPitch));
+	HU_CUDA(cudaMemset(b->seed.keys, 0xff, (size_t) maxReads * t.scanPitch * sizeof(uint32_t))); // tail positions stay excluded
 	HU_TRY(balloc(b, &b->seed.seedIds, (size_t) maxReads * HU_MAX_SEED));
 	HU_TRY(balloc(b, &b->seed.nSeeds, (size_t) maxReads));
 	HU_TRY(balloc(b, &b->est, (size_t) maxReads * HU_MAX_SEED));

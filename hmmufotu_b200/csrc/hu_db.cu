@@ -463,6 +463,18 @@ static int createImpl(hu_db* db, const hu_hmm_params* hp, const hu_tree_desc* td
 	t.scanPitch = (int) scanNode.size();
 	// padding slots (inside the gap block and at the tail) carry node -1 and all-zero planes
 	HU_TRY(upload(db, &t.scanNode, scanNode.data(), scanNode.size()));
+	{
+		// getSeed() visits the non-root nodes in id order: that is the order of the per-read key vector
+		std::vector<int> posOfNode(n, -1), posOfSlot(scanNode.size(), -1), nodeOfPos(scanNode.size(), 0x7fffffff);
+		int pos = 0;
+		for (int x = 0; x < n; ++x)
+			if (x != td->root) { posOfNode[x] = pos; nodeOfPos[pos] = x; pos++; }
+		for (size_t sl = 0; sl < scanNode.size(); ++sl)
+			if (scanNode[sl] >= 0) posOfSlot[sl] = posOfNode[scanNode[sl]];
+		t.nCand = pos;
+		HU_TRY(upload(db, &t.posOfSlot, posOfSlot.data(), posOfSlot.size()));
+		HU_TRY(upload(db, &t.nodeOfPos, nodeOfPos.data(), nodeOfPos.size()));
+	}
 	uint32_t* planes;
 	t.nPWords = (K + 31) / 32;
 	HU_TRY(devAlloc(db, &planes, (size_t) t.nPWords * 3 * t.scanPitch));

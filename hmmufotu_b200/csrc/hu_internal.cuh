@@ -217,6 +217,9 @@ struct TreeDev {
 	int nScan;               // number of scan slots (non-root nodes), padded to scanPitch
 	int scanPitch;
 	const int* scanNode;     // slot -> node id
+	const int* posOfSlot;    // slot -> position in getSeed's candidate vector (non-root nodes in id order), -1 for padding
+	const int* nodeOfPos;    // position -> node id, padded to scanPitch with 0x7fffffff
+	int nCand;               // number of candidates (nNodes - 1)
 	int nGapSlots;           // slots [0, nGapSlots) hold nodes whose sequence has gaps (need the valid plane)
 };
 

@@ -129,12 +129,13 @@ __global__ void __launch_bounds__(128) seedScanKernel(SeedArgs a, TreeDev t, int
 			}
 		}
 	}
-	int node[4];
+	int pos[4];
 	bool excl[4];
 #pragma unroll
 	for (int s = 0; s < 4; ++s) {
-		node[s] = __ldg(t.scanNode + slot + s);
-		excl[s] = node[s] < 0 || !(__ldg(t.height + max(node[s], 0)) <= a.maxHeight);
+		const int node = __ldg(t.scanNode + slot + s);
+		pos[s] = __ldg(t.posOfSlot + slot + s);
+		excl[s] = node < 0 || !(__ldg(t.height + max(node, 0)) <= a.maxHeight);
 	}
 #pragma unroll
 	for (int r = 0; r < HU_SCAN_READS; ++r) {
@@ -155,10 +156,11 @@ __global__ void __launch_bounds__(128) seedScanKernel(SeedArgs a, TreeDev t, int
 			for (int s = 0; s < 4; ++s)
 				if (b4[s] >= 0) { nn[s]++; dd[s] += b4[s] != rb; }
 		}
-		uint4 k;
-		k.x = makeKey(dd[0], nn[0], excl[0] || ns < 0); k.y = makeKey(dd[1], nn[1], excl[1] || ns < 0);
-		k.z = makeKey(dd[2], nn[2], excl[2] || ns < 0); k.w = makeKey(dd[3], nn[3], excl[3] || ns < 0);
-		*reinterpret_cast<uint4*>(a.keys + (size_t) rr * pitch + slot) = k;
+		// the key vector of a read is in getSeed's candidate order (node id), not in slot order
+		uint32_t* krow = a.keys + (size_t) rr * pitch;
+#pragma unroll
+		for (int s = 0; s < 4; ++s)
+			if (pos[s] >= 0) krow[pos[s]] = makeKey(dd[s], nn[s], excl[s] || ns < 0);
 	}
 }
 
@@ -167,7 +169,7 @@ __global__ void __launch_bounds__(128) seedScanKernel(SeedArgs a, TreeDev t, int
 #define HU_SEL_CAND 2048
 #define HU_SEL_BINS 2048
 
-__global__ void __launch_bounds__(HU_SEL_THREADS) seedSelectKernel(SeedArgs a, int scanPitch, const int* __restrict__ scanNode) {
+__global__ void __launch_bounds__(HU_SEL_THREADS) seedSelectKernel(SeedArgs a, int scanPitch, const int* __restrict__ nodeOfPos) {
 	__shared__ unsigned int hist[HU_SEL_BINS];
 	__shared__ unsigned long long cand[HU_SEL_CAND];
 	__shared__ unsigned int sCount, sValid, sDigit, sBelow;
@@ -179,7 +181,7 @@ __global__ void __launch_bounds__(HU_SEL_THREADS) seedSelectKernel(SeedArgs a, i
 		return;
 	}
 	const uint4* keys4 = reinterpret_cast<const uint4*>(a.keys + (size_t) r * scanPitch);
-	const int4* node4 = reinterpret_cast<const int4*>(scanNode);
+	const int4* node4 = reinterpret_cast<const int4*>(nodeOfPos);
 	const int n4 = scanPitch / 4;
 	// composite value c = (key << 32) | node id, refined 11 bits at a time from the top
 	const int shifts[6] = {53, 42, 31, 20, 9, 0};
@@ -290,6 +292,225 @@ __global__ void __launch_bounds__(HU_SEL_THREADS) seedSelectKernel(SeedArgs a, i
 	if (tid == 0) a.nSeeds[r] = (int) nOut;
 }
 
+// ---- the seeds std::sort leaves in front (HU_SEED_ORDER_STDSORT) ----
+// getSeed() sorts all candidates with libstdc++'s unstable introsort and the caller keeps the first maxNSeed
+// (src/HmmUFOtu_main.cpp:139, src/hmmufotu.cpp:646-647).  p-distances are small rationals, so the maxNSeed-th
+// value is nearly always a tie group cut in two, and WHICH of its members survive is decided by the sort's
+// data movement.  This kernel replays that movement exactly, but only on the part of the array that can
+// reach the first maxNSeed positions: __introsort_loop (bits/stl_algo.h) partitions [first, last) around the
+// median of (first+1, mid, last-1), recurses into the right part and loops on the left part, so a sub-range
+// that starts at or after position maxNSeed is never looked at again.  One CTA per read; the Hoare partition
+// (__unguarded_partition) is evaluated in parallel from two bitmaps (elements >= pivot, elements <= pivot):
+// the k-th stop of the left scan is swapped with the k-th stop of the right scan while the former lies left
+// of the latter, which prefix counts over the bitmaps decide for every element at once.
+#define HU_LIT_THREADS 512
+#define HU_LIT_SEQ 96 // ranges up to this size are partitioned by one thread, literally
+
+struct LitState {
+	uint32_t* q;   // keys of this read, candidate order (permuted in place)
+	uint32_t* id;  // candidate positions travelling with the keys
+};
+
+__device__ void litSwap(LitState& st, int x, int y) {
+	const uint32_t tq = st.q[x], ti = st.id[x];
+	st.q[x] = st.q[y]; st.id[x] = st.id[y];
+	st.q[y] = tq; st.id[y] = ti;
+}
+__device__ void litMedianToFirst(LitState& st, int result, int a, int b, int c) { // __move_median_to_first
+	const uint32_t* q = st.q;
+	if (q[a] < q[b]) {
+		if (q[b] < q[c]) litSwap(st, result, b);
+		else if (q[a] < q[c]) litSwap(st, result, c);
+		else litSwap(st, result, a);
+	} else if (q[a] < q[c]) litSwap(st, result, a);
+	else if (q[b] < q[c]) litSwap(st, result, c);
+	else litSwap(st, result, b);
+}
+__device__ int litPartitionSeq(LitState& st, int first, int last, int pivot) { // __unguarded_partition, literally
+	const uint32_t pv = st.q[pivot];
+	for (;;) {
+		while (st.q[first] < pv) ++first;
+		--last;
+		while (pv < st.q[last]) --last;
+		if (!(first < last)) return first;
+		litSwap(st, first, last);
+		++first;
+	}
+}
+// k-th (0-based) set bit of a bitmap with exclusive per-word prefix counts
+__device__ int litSelect(const uint32_t* bits, const uint32_t* pre, int nWords, uint32_t k) {
+	int lo = 0, hi = nWords - 1;
+	while (lo < hi) { // last word with pre[w] <= k
+		const int mid = (lo + hi + 1) >> 1;
+		if (pre[mid] <= k) lo = mid; else hi = mid - 1;
+	}
+	return lo * 32 + (int) __fns(bits[lo], 0, (int) (k - pre[lo]) + 1);
+}
+
+__global__ void __launch_bounds__(HU_LIT_THREADS) seedSortLiteralKernel(SeedArgs a, int n, int pitch, const int* __restrict__ nodeOfPos,
+		uint32_t* __restrict__ idScratch, int maxWords) {
+	extern __shared__ uint32_t smLit[];
+	uint32_t* faW = smLit;              // elements >= pivot  (!(x < pivot))
+	uint32_t* fbW = faW + maxWords;     // elements <= pivot  (!(pivot < x))
+	uint32_t* preA = fbW + maxWords;    // exclusive prefix counts per word
+	uint32_t* preB = preA + maxWords;
+	__shared__ uint32_t red[HU_LIT_THREADS / 32][2];
+	__shared__ uint32_t sTot[2], sK, sMaxQ;
+	__shared__ int sCut, sLo, sHi, sDepth, sTop, sOverflow;
+	__shared__ int stack[64][3];
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const int nWarps = HU_LIT_THREADS / 32;
+	for (int r = blockIdx.x; r < a.nReads; r += gridDim.x) {
+		__syncthreads();
+		if (a.winStart[r] < 0 || n < 1) {
+			if (tid == 0) a.nSeeds[r] = 0;
+			continue;
+		}
+		LitState st;
+		st.q = a.keys + (size_t) r * pitch;
+		st.id = idScratch + (size_t) blockIdx.x * pitch;
+		uint32_t mx = 0;
+		for (int i = tid; i < n; i += HU_LIT_THREADS) {
+			st.id[i] = (uint32_t) i;
+			const uint32_t v = st.q[i];
+			if (v != 0xFFFFFFFFu) mx = max(mx, v);
+		}
+		if (tid == 0) { sMaxQ = 0; sTop = 0; sOverflow = 0; }
+		__syncthreads();
+		atomicMax(&sMaxQ, mx);
+		const int want = min(a.maxNSeed, n);
+		if (tid == 0) {
+			int depth = 0;
+			for (int v = n; v > 1; v >>= 1) depth++; // std::__lg(n)
+			stack[0][0] = 0; stack[0][1] = n; stack[0][2] = 2 * depth;
+			sTop = 1;
+		}
+		__syncthreads();
+		while (sTop > 0) {
+			__syncthreads();
+			if (tid == 0) { sTop--; sLo = stack[sTop][0]; sHi = stack[sTop][1]; sDepth = stack[sTop][2]; }
+			__syncthreads();
+			// __introsort_loop on [sLo, sHi); sub-ranges beyond the wanted prefix are dropped
+			while (sHi - sLo > 16 && sLo < want) {
+				const int lo = sLo, hi = sHi;
+				if (sDepth == 0) { if (tid == 0) sOverflow = 1; break; } // would fall back to heap sort: not replayed
+				__syncthreads();
+				if (hi - lo <= HU_LIT_SEQ) {
+					if (tid == 0) {
+						litMedianToFirst(st, lo, lo + 1, lo + (hi - lo) / 2, hi - 1);
+						sCut = litPartitionSeq(st, lo + 1, hi, lo);
+					}
+				} else {
+					if (tid == 0) litMedianToFirst(st, lo, lo + 1, lo + (hi - lo) / 2, hi - 1);
+					__syncthreads();
+					const uint32_t pv = st.q[lo];
+					const int base = lo + 1, cnt = hi - base, nW = (cnt + 31) / 32;
+					for (int w = warp; w < nW; w += nWarps) {
+						const int t = w * 32 + lane;
+						const bool ok = t < cnt;
+						const uint32_t v = ok ? st.q[base + t] : 0u;
+						const uint32_t ba = __ballot_sync(0xffffffffu, ok && !(v < pv));
+						const uint32_t bb = __ballot_sync(0xffffffffu, ok && !(pv < v));
+						if (lane == 0) { faW[w] = ba; fbW[w] = bb; }
+					}
+					__syncthreads();
+					// exclusive prefix counts per word
+					const int seg = (nW + HU_LIT_THREADS - 1) / HU_LIT_THREADS;
+					const int w0 = tid * seg, w1 = min(nW, w0 + seg);
+					uint32_t sa = 0, sb = 0;
+					for (int w = w0; w < w1; ++w) { sa += __popc(faW[w]); sb += __popc(fbW[w]); }
+					uint32_t xa = sa, xb = sb; // inclusive scan over threads
+					for (int o = 1; o < 32; o <<= 1) {
+						const uint32_t ya = __shfl_up_sync(0xffffffffu, xa, o), yb = __shfl_up_sync(0xffffffffu, xb, o);
+						if (lane >= o) { xa += ya; xb += yb; }
+					}
+					if (lane == 31) { red[warp][0] = xa; red[warp][1] = xb; }
+					__syncthreads();
+					uint32_t oa = 0, ob = 0;
+					for (int k = 0; k < warp; ++k) { oa += red[k][0]; ob += red[k][1]; }
+					uint32_t ra = oa + xa - sa, rb = ob + xb - sb;
+					for (int w = w0; w < w1; ++w) { preA[w] = ra; preB[w] = rb; ra += __popc(faW[w]); rb += __popc(fbW[w]); }
+					if (tid == HU_LIT_THREADS - 1) { sTot[0] = oa + xa; sTot[1] = ob + xb; }
+					if (tid == 0) sK = 0;
+					__syncthreads();
+					const uint32_t totA = sTot[0], totB = sTot[1];
+					// K = number of swaps: the k-th left stop (k-th element >= pivot) lies left of the k-th right stop
+					uint32_t myK = 0;
+					for (int w = w0; w < w1; ++w) {
+						uint32_t bits = faW[w];
+						while (bits) {
+							const int bit = __ffs(bits) - 1;
+							bits &= bits - 1;
+							const uint32_t rankA = preA[w] + __popc(faW[w] & ((1u << bit) - 1u));
+							const uint32_t bIncl = preB[w] + __popc(fbW[w] & (0xFFFFFFFFu >> (31 - bit)));
+							if (totB - bIncl > rankA) myK++;
+							else { bits = 0; } // monotone: no later element qualifies
+						}
+					}
+					if (myK) atomicAdd(&sK, myK);
+					__syncthreads();
+					const uint32_t K = sK;
+					if (tid == 0) {
+						const int AK = K < totA ? base + litSelect(faW, preA, nW, K) : hi;
+						int cut = AK;
+						if (K >= 1) cut = min(AK, base + litSelect(fbW, preB, nW, totB - K));
+						sCut = cut;
+					}
+					__syncthreads();
+					const bool full = sCut < want; // the right part is needed too: swap instead of copy
+					// right stops with rank-from-right k < K receive/lose their partner, the k-th left stop
+					for (int w = w0; w < w1; ++w) {
+						uint32_t bits = fbW[w];
+						while (bits) {
+							const int bit = 31 - __clz(bits); // high to low: ranks from the right grow
+							bits &= ~(1u << bit);
+							const uint32_t bIncl = preB[w] + __popc(fbW[w] & (0xFFFFFFFFu >> (31 - bit)));
+							const uint32_t k = totB - bIncl;
+							if (k >= K) continue;
+							const int pq = base + w * 32 + bit;
+							const int pp = base + litSelect(faW, preA, nW, k);
+							const uint32_t vq = st.q[pq], vi = st.id[pq];
+							if (full) { st.q[pq] = st.q[pp]; st.id[pq] = st.id[pp]; }
+							st.q[pp] = vq; st.id[pp] = vi;
+						}
+					}
+				}
+				__syncthreads();
+				if (tid == 0) {
+					sDepth--;
+					if (sCut < want && sHi - sCut > 1 && sTop < 64) { stack[sTop][0] = sCut; stack[sTop][1] = sHi; stack[sTop][2] = sDepth; sTop++; }
+					sHi = sCut;
+				}
+				__syncthreads();
+			}
+			__syncthreads();
+		}
+		// __final_insertion_sort restricted to what can reach the first `want` positions: blocks are at most 16
+		// long and ordered among themselves, and an insertion never crosses a block boundary
+		if (tid == 0) {
+			const int P = min(n, want + 17);
+			for (int i = 1; i < P; ++i) {
+				const uint32_t vq = st.q[i], vi = st.id[i];
+				int j = i;
+				while (j > 0 && vq < st.q[j - 1]) { st.q[j] = st.q[j - 1]; st.id[j] = st.id[j - 1]; j--; }
+				st.q[j] = vq; st.id[j] = vi;
+			}
+			int nOut = want;
+			while (nOut > 0 && st.q[nOut - 1] == 0xFFFFFFFFu) nOut--; // undefined distances (0/0) are not seeds
+			if (a.maxDiff < INFINITY && nOut > 0) { // src/HmmUFOtu_main.cpp:141-150, on the key scale
+				const double best = (double) st.q[0] / 2147483648.0, worst = (double) sMaxQ / 2147483648.0;
+				if (worst < best + a.maxDiff) {
+					int keep = 0;
+					while (keep < nOut && (double) st.q[keep] / 2147483648.0 - best <= a.maxDiff) keep++;
+					nOut = keep;
+				}
+			}
+			for (int i = 0; i < nOut; ++i) a.seedIds[(size_t) r * HU_MAX_SEED + i] = nodeOfPos[st.id[i]];
+			a.nSeeds[r] = sOverflow ? -nOut - 1 : nOut;
+		}
+	}
+}
+
 int launchSeed(hu_batch* b, const hu_sep_params* p) {
 	hu_db* db = b->db;
 	const TreeDev& t = db->tree;
@@ -324,7 +545,29 @@ int launchSeed(hu_batch* b, const hu_sep_params* p) {
 	if (gapTiles > 0) seedScanKernel<true><<<dim3(groups, gapTiles), 128, smem, b->stream>>>(a, t, 0);
 	if (allTiles > gapTiles) seedScanKernel<false><<<dim3(groups, allTiles - gapTiles), 128, smem, b->stream>>>(a, t, gapTiles);
 	HU_CUDA(cudaEventRecord(b->ev[3], b->stream));
-	seedSelectKernel<<<b->nReads, HU_SEL_THREADS, 0, b->stream>>>(a, t.scanPitch, t.scanNode);
+	// literal order needs the candidate vector to be exactly getSeed's: every non-root node (no height filter)
+	const bool literal = p->seedOrder == HU_SEED_ORDER_STDSORT && !(p->maxHeight < INFINITY);
+	if (literal) {
+		int sms = 0;
+		HU_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, db->device));
+		const int maxWords = (t.nCand + 31) / 32 + 1;
+		const size_t smemLit = (size_t) 4 * maxWords * sizeof(uint32_t);
+		if (smemLit > 200 * 1024) { setError("tree too large for the shared-memory bitmaps of the literal seed order (%d nodes)", t.nNodes); return HU_ERR_ARG; }
+		static size_t attrLit = 0;
+		if (smemLit > attrLit) {
+			HU_CUDA(cudaFuncSetAttribute(seedSortLiteralKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smemLit));
+			attrLit = smemLit;
+		}
+		const int grid = std::min(b->nReads, sms * 2);
+		if (!b->litIds) {
+			void* q = NULL;
+			HU_CUDA(cudaMalloc(&q, (size_t) sms * 2 * t.scanPitch * sizeof(uint32_t)));
+			b->allocs.push_back(q);
+			b->litIds = (uint32_t*) q;
+		}
+		seedSortLiteralKernel<<<grid, HU_LIT_THREADS, smemLit, b->stream>>>(a, t.nCand, t.scanPitch, t.nodeOfPos, b->litIds, maxWords);
+	} else
+		seedSelectKernel<<<b->nReads, HU_SEL_THREADS, 0, b->stream>>>(a, t.scanPitch, t.nodeOfPos);
 	HU_CUDA(cudaEventRecord(b->ev[4], b->stream));
 	b->launches += 3 + (gapTiles > 0) + (allTiles > gapTiles);
 	HU_CUDA(cudaGetLastError());

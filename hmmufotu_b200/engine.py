@@ -163,11 +163,12 @@ class Database:
 
 class SepParams:
     def __init__(self, max_n_seed: int = 50, max_error: float = 20.0, max_diff: float = np.inf,
-                 max_height: float = np.inf, use_true_loglik: bool = False):
+                 max_height: float = np.inf, use_true_loglik: bool = False, seed_order: int = _lib.SEED_ORDER_STDSORT):
         p = _lib.SepParams()
         _lib.load().hu_sep_params_default(C.byref(p))
         p.maxNSeed, p.maxError, p.maxDiff, p.maxHeight = max_n_seed, max_error, max_diff, max_height
         p.useTrueLoglik = int(use_true_loglik)
+        p.seedOrder = int(seed_order)
         self.c = p
 
 

@@ -150,7 +150,12 @@ typedef struct hu_sep_params {
 	double maxError;     /* src/hmmufotu.cpp:49  (20) */
 	const int32_t* equalSortPerm; /* optional: for n = 1..HU_MAX_SEED the index std::sort(rbegin,rend) leaves
 	                               * first on n equal keys, at [n]; NULL = library-built table */
+	int32_t seedOrder;   /* HU_SEED_ORDER_STDSORT (default): the seeds libstdc++'s std::sort leaves in front, ties
+	                      * included (src/HmmUFOtu_main.cpp:139); HU_SEED_ORDER_ID: deterministic (dist, id) order */
+	int32_t reserved;
 } hu_sep_params;
+#define HU_SEED_ORDER_STDSORT 0
+#define HU_SEED_ORDER_ID 1
 void hu_sep_params_default(hu_sep_params* p);
 
 /* ---- batch workspace ---- */

@@ -53,7 +53,8 @@ def test_tree_likelihood_is_the_same_on_every_edge(full):
 def test_pipeline_properties_and_determinism(full):
     engine, gdb, db, rs = full["engine"], full["gdb"], full["db"], full["reads"]
     n = rs.n
-    p = engine.SepParams()
+    from hmmufotu_b200 import _lib
+    p = engine.SepParams(seed_order=_lib.SEED_ORDER_ID)   # checked below against a host (dist, id) sort
     outs = []
     for rep in range(2):
         b = engine.Batch(gdb, n, 260)

@@ -103,10 +103,10 @@ def _oracle_aligned(small, n):
 TIE_RTOL = 1e-11  # estimated logliks closer than this are one tie group: their order is rounding noise
 
 
-def _check_read(otree, codes, start, end, ns_i, ids_i, dist_i, nk_i, est_i, pl_i, best_i, use_true=False):
+def _check_read(otree, codes, start, end, ns_i, ids_i, dist_i, nk_i, est_i, pl_i, best_i, use_true=False, order=0):
     """One read: seeds exact, every kept placement within RTOL of the oracle's, order = descending
     estimated loglik (up to tie groups), bestPlace = the element std::sort leaves first."""
-    oid, odist = otree.get_seed(codes, start, end, 50, order=1)
+    oid, odist = otree.get_seed(codes, start, end, 50, order=order)   # 0: libstdc++ std::sort, ties included
     assert ns_i == len(oid)
     assert np.array_equal(ids_i[:ns_i], oid)
     assert np.array_equal(dist_i[:ns_i], odist)                      # exact d/N doubles
@@ -158,7 +158,7 @@ def test_seed_estimate_place(small):
     b.calcQValues(engine.SepParams(use_true_loglik=True))
     best2 = b.best()
     for i in range(n):
-        oid, odist = otree.get_seed(codes[i], start[i], end[i], 50, order=1)
+        oid, odist = otree.get_seed(codes[i], start[i], end[i], 50, order=0)
         rows = otree.assign(codes[i], start[i], end[i], oid, odist, use_true=True)
         top = max(r.loglikTrue for r in rows)
         mine = [r for r in rows if (r.c, r.p) == (best2[i]["cNode"], best2[i]["pNode"])][0]
@@ -180,7 +180,7 @@ def test_full_pipeline_from_reads(small):
         o = _align_oracle(small, i)
         seq = O.digitize(o["align"])
         s, e = o["coords"][4] - 1, o["coords"][5] - 1
-        oid, odist = otree.get_seed(seq, s, e, 50, order=1)
+        oid, odist = otree.get_seed(seq, s, e, 50, order=0)
         rows = otree.assign(seq, s, e, oid, odist)
         assert best[i]["nPlaces"] == len(rows)
         est = sorted(r.estLoglik for r in rows)
@@ -189,4 +189,28 @@ def test_full_pipeline_from_reads(small):
             assert (best[i]["cNode"], best[i]["pNode"], best[i]["aNode"]) == (rows[0].c, rows[0].p, rows[0].a), i
         else:
             assert (best[i]["cNode"], best[i]["pNode"]) in {(r.c, r.p) for r in rows}, i
+    b.close()
+
+
+def test_seed_order_modes(small):
+    """HU_SEED_ORDER_STDSORT replays libstdc++'s introsort (which members of the tie group at the cut survive
+    depends on its data movement); HU_SEED_ORDER_ID is the deterministic (dist, id) order."""
+    engine, otree = small["engine"], small["otree"]
+    from hmmufotu_b200 import _lib
+    n = 64
+    codes, start, end = _oracle_aligned(small, n)
+    b = engine.Batch(small["gdb"], n, 260)
+    b.set_aligned(codes, start, end)
+    differ = 0
+    for order, mode in ((0, _lib.SEED_ORDER_STDSORT), (1, _lib.SEED_ORDER_ID)):
+        for max_n in (50, 7, 64):
+            b.getSeed(engine.SepParams(max_n_seed=max_n, seed_order=mode))
+            ns, ids, _ = b.seeds()
+            for i in range(n):
+                oid, _ = otree.get_seed(codes[i], start[i], end[i], max_n, order=order)
+                assert np.array_equal(ids[i, :ns[i]], oid), (order, max_n, i)
+                if order == 0:
+                    sid, _ = otree.get_seed(codes[i], start[i], end[i], max_n, order=1)
+                    differ += not np.array_equal(sid, oid)
+    assert differ > 0            # the two orders really are different on tied distances
     b.close()

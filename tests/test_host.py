@@ -129,7 +129,7 @@ def test_cli_end_to_end(exes, dbfiles):
         assert r[9] == a["align"]
         seq = O.digitize(a["align"])
         s, e = a["coords"][4] - 1, a["coords"][5] - 1
-        ids, dist = otree.get_seed(seq, s, e, 50, order=1)
+        ids, dist = otree.get_seed(seq, s, e, 50, order=0)
         want = otree.assign(seq, s, e, ids, dist)
         est = sorted(w.estLoglik for w in want)
         tied = any(abs(x - y) <= 1e-11 * abs(x) for x, y in zip(est, est[1:]))
