@@ -356,7 +356,7 @@ __global__ void __launch_bounds__(HU_LIT_THREADS) seedSortLiteralKernel(SeedArgs
 	uint32_t* preB = preA + maxWords;
 	__shared__ uint32_t red[HU_LIT_THREADS / 32][2];
 	__shared__ uint32_t sTot[2], sK, sMaxQ;
-	__shared__ int sCut, sLo, sHi, sDepth, sTop, sOverflow;
+	__shared__ int sCut, sLo, sHi, sDepth, sTop, sOverflow, sBound;
 	__shared__ int stack[64][3];
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const int nWarps = HU_LIT_THREADS / 32;
@@ -375,7 +375,7 @@ __global__ void __launch_bounds__(HU_LIT_THREADS) seedSortLiteralKernel(SeedArgs
 			const uint32_t v = st.q[i];
 			if (v != 0xFFFFFFFFu) mx = max(mx, v);
 		}
-		if (tid == 0) { sMaxQ = 0; sTop = 0; sOverflow = 0; }
+		if (tid == 0) { sMaxQ = 0; sTop = 0; sOverflow = 0; sBound = n; }
 		__syncthreads();
 		atomicMax(&sMaxQ, mx);
 		const int want = min(a.maxNSeed, n);
@@ -479,6 +479,7 @@ __global__ void __launch_bounds__(HU_LIT_THREADS) seedSortLiteralKernel(SeedArgs
 				if (tid == 0) {
 					sDepth--;
 					if (sCut < want && sHi - sCut > 1 && sTop < 64) { stack[sTop][0] = sCut; stack[sTop][1] = sHi; stack[sTop][2] = sDepth; sTop++; }
+					if (sCut >= want) sBound = min(sBound, sCut); // [sCut, sHi) was left stale (copies, not swaps)
 					sHi = sCut;
 				}
 				__syncthreads();
@@ -488,7 +489,7 @@ __global__ void __launch_bounds__(HU_LIT_THREADS) seedSortLiteralKernel(SeedArgs
 		// __final_insertion_sort restricted to what can reach the first `want` positions: blocks are at most 16
 		// long and ordered among themselves, and an insertion never crosses a block boundary
 		if (tid == 0) {
-			const int P = min(n, want + 17);
+			const int P = min(min(n, sBound), want + 17); // nothing at or beyond a dropped cut may be touched
 			for (int i = 1; i < P; ++i) {
 				const uint32_t vq = st.q[i], vi = st.id[i];
 				int j = i;
