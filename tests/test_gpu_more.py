@@ -177,3 +177,28 @@ def test_wide_windows_and_inserts():
         _check_read(otree, seq, s, e, ns[i], ids[i], dist[i], nk[i], est[i], pl[i], best[i])
     assert max(widths) > 1536 and n_sparse > 0
     b.close(); gdb.close()
+
+
+def test_literal_seed_order_on_a_larger_tree():
+    """~4 000 candidates per read: several levels of the parallel Hoare partition before ranges get small."""
+    from hmmufotu_b200 import engine, _lib
+    db = synth.make_db(n_leaves=2000, cs_len=260, occupancy=0.9, seed=71, mean_blen=0.02)
+    otree = O.OracleTree(db, threads=8)
+    db.seq = otree.seqs()
+    gdb = engine.Database(db, messages=otree.messages())
+    rs = synth.make_reads(db, 48, read_len=90, seed=12, drop_seed_prob=0.0)
+    ohmm = O.OracleHmm(db)
+    codes, start, end = _oracle_aligned(ohmm, rs, db.cs_len, rs.n)
+    b = engine.Batch(gdb, rs.n, 128)
+    b.set_aligned(codes, start, end)
+    n_tie_cut = 0
+    for max_n in (50, 17, 1):
+        b.getSeed(engine.SepParams(max_n_seed=max_n, seed_order=_lib.SEED_ORDER_STDSORT))
+        ns, ids, _ = b.seeds()
+        for i in range(rs.n):
+            oid, odist = otree.get_seed(codes[i], start[i], end[i], max_n, order=0)
+            assert np.array_equal(ids[i, :ns[i]], oid), (max_n, i)
+            sid, _ = otree.get_seed(codes[i], start[i], end[i], max_n, order=1)
+            n_tie_cut += set(sid) != set(oid)
+    assert n_tie_cut > 0   # tie groups cut by the truncation: std::sort and (dist, id) keep different members
+    b.close(); gdb.close()
