@@ -92,7 +92,7 @@ struct hu_batch {
 	int* equalPerm;        // [HU_MAX_SEED+1]
 	int* workItems;        // compacted (read, slot) lists for K3/K4
 	int* workCount;
-	uint32_t* litIds;      // candidate-position scratch of the literal seed order, one row per resident CTA
+	unsigned long long* litIds; // (key, candidate position) work rows of the literal seed order, one per resident CTA
 	double* placeSlab;     // global rho slabs for windows wider than the shared-memory capacity
 	long long h2dBytes;
 	// stats

@@ -304,41 +304,38 @@ __global__ void __launch_bounds__(HU_SEL_THREADS) seedSelectKernel(SeedArgs a, i
 // the k-th stop of the left scan is swapped with the k-th stop of the right scan while the former lies left
 // of the latter, which prefix counts over the bitmaps decide for every element at once.
 #define HU_LIT_THREADS 512
-#define HU_LIT_SEQ 96 // ranges up to this size are partitioned by one thread, literally
+#define HU_LIT_SMALL 256 // ranges up to this size are finished by one thread on a shared-memory copy, literally
 
-struct LitState {
-	uint32_t* q;   // keys of this read, candidate order (permuted in place)
-	uint32_t* id;  // candidate positions travelling with the keys
-};
+typedef unsigned long long lit_t;               // (key << 32) | candidate position; only the key is compared
+#define LIT_KEY(v) ((uint32_t) ((v) >> 32))
 
-__device__ void litSwap(LitState& st, int x, int y) {
-	const uint32_t tq = st.q[x], ti = st.id[x];
-	st.q[x] = st.q[y]; st.id[x] = st.id[y];
-	st.q[y] = tq; st.id[y] = ti;
+template <typename Arr>
+__device__ __forceinline__ void litSwap(Arr& w, int x, int y) { const lit_t t = w[x]; w[x] = w[y]; w[y] = t; }
+template <typename Arr>
+__device__ __forceinline__ void litMedianToFirst(Arr& w, int result, int a, int b, int c) { // __move_median_to_first
+	const uint32_t qa = LIT_KEY(w[a]), qb = LIT_KEY(w[b]), qc = LIT_KEY(w[c]);
+	if (qa < qb) {
+		if (qb < qc) litSwap(w, result, b);
+		else if (qa < qc) litSwap(w, result, c);
+		else litSwap(w, result, a);
+	} else if (qa < qc) litSwap(w, result, a);
+	else if (qb < qc) litSwap(w, result, c);
+	else litSwap(w, result, b);
 }
-__device__ void litMedianToFirst(LitState& st, int result, int a, int b, int c) { // __move_median_to_first
-	const uint32_t* q = st.q;
-	if (q[a] < q[b]) {
-		if (q[b] < q[c]) litSwap(st, result, b);
-		else if (q[a] < q[c]) litSwap(st, result, c);
-		else litSwap(st, result, a);
-	} else if (q[a] < q[c]) litSwap(st, result, a);
-	else if (q[b] < q[c]) litSwap(st, result, c);
-	else litSwap(st, result, b);
-}
-__device__ int litPartitionSeq(LitState& st, int first, int last, int pivot) { // __unguarded_partition, literally
-	const uint32_t pv = st.q[pivot];
+template <typename Arr>
+__device__ __forceinline__ int litPartitionSeq(Arr& w, int first, int last, int pivot) { // __unguarded_partition, literally
+	const uint32_t pv = LIT_KEY(w[pivot]);
 	for (;;) {
-		while (st.q[first] < pv) ++first;
+		while (LIT_KEY(w[first]) < pv) ++first;
 		--last;
-		while (pv < st.q[last]) --last;
+		while (pv < LIT_KEY(w[last])) --last;
 		if (!(first < last)) return first;
-		litSwap(st, first, last);
+		litSwap(w, first, last);
 		++first;
 	}
 }
 // k-th (0-based) set bit of a bitmap with exclusive per-word prefix counts
-__device__ int litSelect(const uint32_t* bits, const uint32_t* pre, int nWords, uint32_t k) {
+__device__ __forceinline__ int litSelect(const uint32_t* bits, const uint32_t* pre, int nWords, uint32_t k) {
 	int lo = 0, hi = nWords - 1;
 	while (lo < hi) { // last word with pre[w] <= k
 		const int mid = (lo + hi + 1) >> 1;
@@ -348,31 +345,31 @@ __device__ int litSelect(const uint32_t* bits, const uint32_t* pre, int nWords, 
 }
 
 __global__ void __launch_bounds__(HU_LIT_THREADS) seedSortLiteralKernel(SeedArgs a, int n, int pitch, const int* __restrict__ nodeOfPos,
-		uint32_t* __restrict__ idScratch, int maxWords) {
+		lit_t* __restrict__ scratch, int maxWords) {
 	extern __shared__ uint32_t smLit[];
 	uint32_t* faW = smLit;              // elements >= pivot  (!(x < pivot))
 	uint32_t* fbW = faW + maxWords;     // elements <= pivot  (!(pivot < x))
 	uint32_t* preA = fbW + maxWords;    // exclusive prefix counts per word
 	uint32_t* preB = preA + maxWords;
+	__shared__ lit_t sbuf[HU_LIT_SMALL];
 	__shared__ uint32_t red[HU_LIT_THREADS / 32][2];
 	__shared__ uint32_t sTot[2], sK, sMaxQ;
 	__shared__ int sCut, sLo, sHi, sDepth, sTop, sOverflow, sBound;
 	__shared__ int stack[64][3];
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const int nWarps = HU_LIT_THREADS / 32;
+	lit_t* w = scratch + (size_t) blockIdx.x * pitch;
 	for (int r = blockIdx.x; r < a.nReads; r += gridDim.x) {
 		__syncthreads();
 		if (a.winStart[r] < 0 || n < 1) {
 			if (tid == 0) a.nSeeds[r] = 0;
 			continue;
 		}
-		LitState st;
-		st.q = a.keys + (size_t) r * pitch;
-		st.id = idScratch + (size_t) blockIdx.x * pitch;
+		const uint32_t* keys = a.keys + (size_t) r * pitch;
 		uint32_t mx = 0;
 		for (int i = tid; i < n; i += HU_LIT_THREADS) {
-			st.id[i] = (uint32_t) i;
-			const uint32_t v = st.q[i];
+			const uint32_t v = keys[i];
+			w[i] = ((lit_t) v << 32) | (uint32_t) i;
 			if (v != 0xFFFFFFFFu) mx = max(mx, v);
 		}
 		if (tid == 0) { sMaxQ = 0; sTop = 0; sOverflow = 0; sBound = n; }
@@ -395,83 +392,115 @@ __global__ void __launch_bounds__(HU_LIT_THREADS) seedSortLiteralKernel(SeedArgs
 				const int lo = sLo, hi = sHi;
 				if (sDepth == 0) { if (tid == 0) sOverflow = 1; break; } // would fall back to heap sort: not replayed
 				__syncthreads();
-				if (hi - lo <= HU_LIT_SEQ) {
+				if (hi - lo <= HU_LIT_SMALL) {
+					// the rest of this range, every level of it, by one thread on a shared-memory copy
+					const int m = hi - lo;
+					for (int i = tid; i < m; i += HU_LIT_THREADS) sbuf[i] = w[lo + i];
+					__syncthreads();
 					if (tid == 0) {
-						litMedianToFirst(st, lo, lo + 1, lo + (hi - lo) / 2, hi - 1);
-						sCut = litPartitionSeq(st, lo + 1, hi, lo);
-					}
-				} else {
-					if (tid == 0) litMedianToFirst(st, lo, lo + 1, lo + (hi - lo) / 2, hi - 1);
-					__syncthreads();
-					const uint32_t pv = st.q[lo];
-					const int base = lo + 1, cnt = hi - base, nW = (cnt + 31) / 32;
-					for (int w = warp; w < nW; w += nWarps) {
-						const int t = w * 32 + lane;
-						const bool ok = t < cnt;
-						const uint32_t v = ok ? st.q[base + t] : 0u;
-						const uint32_t ba = __ballot_sync(0xffffffffu, ok && !(v < pv));
-						const uint32_t bb = __ballot_sync(0xffffffffu, ok && !(pv < v));
-						if (lane == 0) { faW[w] = ba; fbW[w] = bb; }
-					}
-					__syncthreads();
-					// exclusive prefix counts per word
-					const int seg = (nW + HU_LIT_THREADS - 1) / HU_LIT_THREADS;
-					const int w0 = tid * seg, w1 = min(nW, w0 + seg);
-					uint32_t sa = 0, sb = 0;
-					for (int w = w0; w < w1; ++w) { sa += __popc(faW[w]); sb += __popc(fbW[w]); }
-					uint32_t xa = sa, xb = sb; // inclusive scan over threads
-					for (int o = 1; o < 32; o <<= 1) {
-						const uint32_t ya = __shfl_up_sync(0xffffffffu, xa, o), yb = __shfl_up_sync(0xffffffffu, xb, o);
-						if (lane >= o) { xa += ya; xb += yb; }
-					}
-					if (lane == 31) { red[warp][0] = xa; red[warp][1] = xb; }
-					__syncthreads();
-					uint32_t oa = 0, ob = 0;
-					for (int k = 0; k < warp; ++k) { oa += red[k][0]; ob += red[k][1]; }
-					uint32_t ra = oa + xa - sa, rb = ob + xb - sb;
-					for (int w = w0; w < w1; ++w) { preA[w] = ra; preB[w] = rb; ra += __popc(faW[w]); rb += __popc(fbW[w]); }
-					if (tid == HU_LIT_THREADS - 1) { sTot[0] = oa + xa; sTot[1] = ob + xb; }
-					if (tid == 0) sK = 0;
-					__syncthreads();
-					const uint32_t totA = sTot[0], totB = sTot[1];
-					// K = number of swaps: the k-th left stop (k-th element >= pivot) lies left of the k-th right stop
-					uint32_t myK = 0;
-					for (int w = w0; w < w1; ++w) {
-						uint32_t bits = faW[w];
-						while (bits) {
-							const int bit = __ffs(bits) - 1;
-							bits &= bits - 1;
-							const uint32_t rankA = preA[w] + __popc(faW[w] & ((1u << bit) - 1u));
-							const uint32_t bIncl = preB[w] + __popc(fbW[w] & (0xFFFFFFFFu >> (31 - bit)));
-							if (totB - bIncl > rankA) myK++;
-							else { bits = 0; } // monotone: no later element qualifies
+						int st[24][3], top = 0;
+						st[0][0] = 0; st[0][1] = m; st[0][2] = sDepth; top = 1;
+						while (top > 0) {
+							top--;
+							int l = st[top][0], h = st[top][1], dep = st[top][2];
+							while (h - l > 16 && lo + l < want) {
+								if (dep == 0) { sOverflow = 1; break; }
+								dep--;
+								litMedianToFirst(sbuf, l, l + 1, l + (h - l) / 2, h - 1);
+								const int cut = litPartitionSeq(sbuf, l + 1, h, l);
+								if (lo + cut < want && top < 24) { st[top][0] = cut; st[top][1] = h; st[top][2] = dep; top++; }
+								h = cut;
+							}
 						}
-					}
-					if (myK) atomicAdd(&sK, myK);
-					__syncthreads();
-					const uint32_t K = sK;
-					if (tid == 0) {
-						const int AK = K < totA ? base + litSelect(faW, preA, nW, K) : hi;
-						int cut = AK;
-						if (K >= 1) cut = min(AK, base + litSelect(fbW, preB, nW, totB - K));
-						sCut = cut;
+						sHi = lo; // range finished
 					}
 					__syncthreads();
-					const bool full = sCut < want; // the right part is needed too: swap instead of copy
-					// right stops with rank-from-right k < K receive/lose their partner, the k-th left stop
-					for (int w = w0; w < w1; ++w) {
-						uint32_t bits = fbW[w];
-						while (bits) {
-							const int bit = 31 - __clz(bits); // high to low: ranks from the right grow
-							bits &= ~(1u << bit);
-							const uint32_t bIncl = preB[w] + __popc(fbW[w] & (0xFFFFFFFFu >> (31 - bit)));
-							const uint32_t k = totB - bIncl;
-							if (k >= K) continue;
-							const int pq = base + w * 32 + bit;
-							const int pp = base + litSelect(faW, preA, nW, k);
-							const uint32_t vq = st.q[pq], vi = st.id[pq];
-							if (full) { st.q[pq] = st.q[pp]; st.id[pq] = st.id[pp]; }
-							st.q[pp] = vq; st.id[pp] = vi;
+					for (int i = tid; i < m; i += HU_LIT_THREADS) w[lo + i] = sbuf[i];
+					__syncthreads();
+					continue;
+				}
+				if (tid == 0) litMedianToFirst(w, lo, lo + 1, lo + (hi - lo) / 2, hi - 1);
+				__syncthreads();
+				const uint32_t pv = LIT_KEY(w[lo]);
+				const int base = lo + 1, cnt = hi - base, nW = (cnt + 31) / 32;
+				for (int wd = warp; wd < nW; wd += nWarps) {
+					const int t = wd * 32 + lane;
+					const bool ok = t < cnt;
+					const uint32_t v = ok ? LIT_KEY(w[base + t]) : 0u;
+					const uint32_t ba = __ballot_sync(0xffffffffu, ok && !(v < pv));
+					const uint32_t bb = __ballot_sync(0xffffffffu, ok && !(pv < v));
+					if (lane == 0) { faW[wd] = ba; fbW[wd] = bb; }
+				}
+				__syncthreads();
+				// exclusive prefix counts per word
+				const int seg = (nW + HU_LIT_THREADS - 1) / HU_LIT_THREADS;
+				const int w0 = tid * seg, w1 = min(nW, w0 + seg);
+				uint32_t sa = 0, sb = 0;
+				for (int wd = w0; wd < w1; ++wd) { sa += __popc(faW[wd]); sb += __popc(fbW[wd]); }
+				uint32_t xa = sa, xb = sb; // inclusive scan over threads
+				for (int o = 1; o < 32; o <<= 1) {
+					const uint32_t ya = __shfl_up_sync(0xffffffffu, xa, o), yb = __shfl_up_sync(0xffffffffu, xb, o);
+					if (lane >= o) { xa += ya; xb += yb; }
+				}
+				if (lane == 31) { red[warp][0] = xa; red[warp][1] = xb; }
+				__syncthreads();
+				uint32_t oa = 0, ob = 0;
+				for (int k = 0; k < warp; ++k) { oa += red[k][0]; ob += red[k][1]; }
+				uint32_t ra = oa + xa - sa, rb = ob + xb - sb;
+				for (int wd = w0; wd < w1; ++wd) { preA[wd] = ra; preB[wd] = rb; ra += __popc(faW[wd]); rb += __popc(fbW[wd]); }
+				if (tid == HU_LIT_THREADS - 1) { sTot[0] = oa + xa; sTot[1] = ob + xb; }
+				if (tid == 0) sK = 0;
+				__syncthreads();
+				const uint32_t totA = sTot[0], totB = sTot[1];
+				// K = number of swaps: the k-th left stop (k-th element >= pivot) lies left of the k-th right stop
+				uint32_t myK = 0;
+				for (int wd = w0; wd < w1; ++wd) {
+					uint32_t bits = faW[wd];
+					while (bits) {
+						const int bit = __ffs(bits) - 1;
+						bits &= bits - 1;
+						const uint32_t rankA = preA[wd] + __popc(faW[wd] & ((1u << bit) - 1u));
+						const uint32_t bIncl = preB[wd] + __popc(fbW[wd] & (0xFFFFFFFFu >> (31 - bit)));
+						if (totB - bIncl > rankA) myK++;
+						else bits = 0; // monotone: no later element qualifies
+					}
+				}
+				if (myK) atomicAdd(&sK, myK);
+				__syncthreads();
+				const uint32_t K = sK;
+				if (tid == 0) {
+					const int AK = K < totA ? base + litSelect(faW, preA, nW, K) : hi;
+					int cut = AK;
+					if (K >= 1) cut = min(AK, base + litSelect(fbW, preB, nW, totB - K));
+					sCut = cut;
+				}
+				__syncthreads();
+				const bool full = sCut < want; // the right part is needed too: swap instead of copy
+				// swap k: k-th left stop <-> k-th right stop.  Each thread takes a contiguous run of k and walks the
+				// two bitmaps from its first pair (fa forwards, fb backwards).
+				{
+					const uint32_t per = (K + HU_LIT_THREADS - 1) / HU_LIT_THREADS;
+					const uint32_t k0 = (uint32_t) tid * per, k1 = min(K, k0 + per);
+					if (k0 < k1) {
+						int pa = litSelect(faW, preA, nW, k0);            // bit index of the k0-th left stop
+						int pb = litSelect(fbW, preB, nW, totB - 1 - k0); // bit index of the k0-th right stop (from the right)
+						for (uint32_t k = k0; k < k1; ++k) {
+							const int pp = base + pa, pq = base + pb;
+							const lit_t vq = w[pq];
+							if (full) w[pq] = w[pp];
+							w[pp] = vq;
+							if (k + 1 < k1) {
+								// next set bit of fa after pa
+								int wd = pa >> 5;
+								uint32_t bits = faW[wd] & ~(0xFFFFFFFFu >> (31 - (pa & 31)));
+								while (!bits) bits = faW[++wd];
+								pa = wd * 32 + __ffs(bits) - 1;
+								// previous set bit of fb before pb
+								wd = pb >> 5;
+								bits = fbW[wd] & ((1u << (pb & 31)) - 1u);
+								while (!bits) bits = fbW[--wd];
+								pb = wd * 32 + 31 - __clz(bits);
+							}
 						}
 					}
 				}
@@ -487,26 +516,29 @@ __global__ void __launch_bounds__(HU_LIT_THREADS) seedSortLiteralKernel(SeedArgs
 			__syncthreads();
 		}
 		// __final_insertion_sort restricted to what can reach the first `want` positions: blocks are at most 16
-		// long and ordered among themselves, and an insertion never crosses a block boundary
+		// long and ordered among themselves, and an insertion never crosses a block boundary.  Nothing at or beyond a
+		// dropped cut may be touched.
+		const int P = min(min(n, sBound), want + 17);
+		for (int i = tid; i < P; i += HU_LIT_THREADS) sbuf[i] = w[i];
+		__syncthreads();
 		if (tid == 0) {
-			const int P = min(min(n, sBound), want + 17); // nothing at or beyond a dropped cut may be touched
 			for (int i = 1; i < P; ++i) {
-				const uint32_t vq = st.q[i], vi = st.id[i];
+				const lit_t v = sbuf[i];
 				int j = i;
-				while (j > 0 && vq < st.q[j - 1]) { st.q[j] = st.q[j - 1]; st.id[j] = st.id[j - 1]; j--; }
-				st.q[j] = vq; st.id[j] = vi;
+				while (j > 0 && LIT_KEY(v) < LIT_KEY(sbuf[j - 1])) { sbuf[j] = sbuf[j - 1]; j--; }
+				sbuf[j] = v;
 			}
-			int nOut = want;
-			while (nOut > 0 && st.q[nOut - 1] == 0xFFFFFFFFu) nOut--; // undefined distances (0/0) are not seeds
+			int nOut = min(want, P);
+			while (nOut > 0 && LIT_KEY(sbuf[nOut - 1]) == 0xFFFFFFFFu) nOut--; // undefined distances (0/0) are not seeds
 			if (a.maxDiff < INFINITY && nOut > 0) { // src/HmmUFOtu_main.cpp:141-150, on the key scale
-				const double best = (double) st.q[0] / 2147483648.0, worst = (double) sMaxQ / 2147483648.0;
+				const double best = (double) LIT_KEY(sbuf[0]) / 2147483648.0, worst = (double) sMaxQ / 2147483648.0;
 				if (worst < best + a.maxDiff) {
 					int keep = 0;
-					while (keep < nOut && (double) st.q[keep] / 2147483648.0 - best <= a.maxDiff) keep++;
+					while (keep < nOut && (double) LIT_KEY(sbuf[keep]) / 2147483648.0 - best <= a.maxDiff) keep++;
 					nOut = keep;
 				}
 			}
-			for (int i = 0; i < nOut; ++i) a.seedIds[(size_t) r * HU_MAX_SEED + i] = nodeOfPos[st.id[i]];
+			for (int i = 0; i < nOut; ++i) a.seedIds[(size_t) r * HU_MAX_SEED + i] = nodeOfPos[(uint32_t) sbuf[i]];
 			a.nSeeds[r] = sOverflow ? -nOut - 1 : nOut;
 		}
 	}
@@ -562,9 +594,9 @@ int launchSeed(hu_batch* b, const hu_sep_params* p) {
 		const int grid = std::min(b->nReads, sms * 2);
 		if (!b->litIds) {
 			void* q = NULL;
-			HU_CUDA(cudaMalloc(&q, (size_t) sms * 2 * t.scanPitch * sizeof(uint32_t)));
+			HU_CUDA(cudaMalloc(&q, (size_t) sms * 2 * t.scanPitch * sizeof(unsigned long long)));
 			b->allocs.push_back(q);
-			b->litIds = (uint32_t*) q;
+			b->litIds = (unsigned long long*) q;
 		}
 		seedSortLiteralKernel<<<grid, HU_LIT_THREADS, smemLit, b->stream>>>(a, t.nCand, t.scanPitch, t.nodeOfPos, b->litIds, maxWords);
 	} else
