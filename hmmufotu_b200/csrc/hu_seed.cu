@@ -366,20 +366,130 @@ __global__ void __launch_bounds__(HU_LIT_THREADS) seedSortLiteralKernel(SeedArgs
 			continue;
 		}
 		const uint32_t* keys = a.keys + (size_t) r * pitch;
+		const int want = min(a.maxNSeed, n);
+		// Level 1 straight from the key vector when the array is large: flags, cut, then only the left part
+		// [0, cut) is materialised as (key, position) pairs -- the right part is never needed (cut >= want).
+		const bool direct = n > 4 * HU_LIT_SMALL;
 		uint32_t mx = 0;
-		for (int i = tid; i < n; i += HU_LIT_THREADS) {
-			const uint32_t v = keys[i];
-			w[i] = ((lit_t) v << 32) | (uint32_t) i;
-			if (v != 0xFFFFFFFFu) mx = max(mx, v);
-		}
+		if (!direct)
+			for (int i = tid; i < n; i += HU_LIT_THREADS) {
+				const uint32_t v = keys[i];
+				w[i] = ((lit_t) v << 32) | (uint32_t) i;
+				if (v != 0xFFFFFFFFu) mx = max(mx, v);
+			}
 		if (tid == 0) { sMaxQ = 0; sTop = 0; sOverflow = 0; sBound = n; }
 		__syncthreads();
+		int depth0 = 0;
+		for (int v = n; v > 1; v >>= 1) depth0++; // std::__lg(n)
+		depth0 *= 2;
+		bool started = false;
+		if (direct) {
+			// __move_median_to_first(first, first+1, mid, last-1): positions 0 and mS trade places (virtually)
+			const int ia = 1, ib = n / 2, ic = n - 1;
+			const uint32_t qa = keys[ia], qb = keys[ib], qc = keys[ic];
+			int mS;
+			if (qa < qb) mS = qb < qc ? ib : (qa < qc ? ic : ia);
+			else mS = qa < qc ? ia : (qb < qc ? ic : ib);
+			const uint32_t pv = keys[mS], k0v = keys[0];
+#define VKEY(p) ((p) == mS ? k0v : keys[p])
+#define VPOS(p) ((p) == mS ? 0 : (p))
+			const int base = 1, cnt = n - 1, nW = (cnt + 31) / 32;
+			for (int wd = warp; wd < nW; wd += nWarps) {
+				const int t = wd * 32 + lane;
+				const bool ok = t < cnt;
+				const uint32_t v = ok ? VKEY(base + t) : 0u;
+				if (ok && v != 0xFFFFFFFFu) mx = max(mx, v);
+				const uint32_t ba = __ballot_sync(0xffffffffu, ok && !(v < pv));
+				const uint32_t bb = __ballot_sync(0xffffffffu, ok && !(pv < v));
+				if (lane == 0) { faW[wd] = ba; fbW[wd] = bb; }
+			}
+			if (pv != 0xFFFFFFFFu) mx = max(mx, pv);
+			__syncthreads();
+			const int seg = (nW + HU_LIT_THREADS - 1) / HU_LIT_THREADS;
+			const int w0 = tid * seg, w1 = min(nW, w0 + seg);
+			uint32_t sa = 0, sb = 0;
+			for (int wd = w0; wd < w1; ++wd) { sa += __popc(faW[wd]); sb += __popc(fbW[wd]); }
+			uint32_t xa = sa, xb = sb;
+			for (int o = 1; o < 32; o <<= 1) {
+				const uint32_t ya = __shfl_up_sync(0xffffffffu, xa, o), yb = __shfl_up_sync(0xffffffffu, xb, o);
+				if (lane >= o) { xa += ya; xb += yb; }
+			}
+			if (lane == 31) { red[warp][0] = xa; red[warp][1] = xb; }
+			__syncthreads();
+			uint32_t oa = 0, ob = 0;
+			for (int k = 0; k < warp; ++k) { oa += red[k][0]; ob += red[k][1]; }
+			uint32_t ra = oa + xa - sa, rb = ob + xb - sb;
+			for (int wd = w0; wd < w1; ++wd) { preA[wd] = ra; preB[wd] = rb; ra += __popc(faW[wd]); rb += __popc(fbW[wd]); }
+			if (tid == HU_LIT_THREADS - 1) { sTot[0] = oa + xa; sTot[1] = ob + xb; }
+			if (tid == 0) sK = 0;
+			__syncthreads();
+			const uint32_t totA = sTot[0], totB = sTot[1];
+			uint32_t myK = 0;
+			for (int wd = w0; wd < w1; ++wd) {
+				uint32_t bits = faW[wd];
+				while (bits) {
+					const int bit = __ffs(bits) - 1;
+					bits &= bits - 1;
+					const uint32_t rankA = preA[wd] + __popc(faW[wd] & ((1u << bit) - 1u));
+					const uint32_t bIncl = preB[wd] + __popc(fbW[wd] & (0xFFFFFFFFu >> (31 - bit)));
+					if (totB - bIncl > rankA) myK++;
+					else bits = 0;
+				}
+			}
+			if (myK) atomicAdd(&sK, myK);
+			__syncthreads();
+			const uint32_t K = sK;
+			if (tid == 0) {
+				const int AK = K < totA ? base + litSelect(faW, preA, nW, K) : n;
+				int cut = AK;
+				if (K >= 1) cut = min(AK, base + litSelect(fbW, preB, nW, totB - K));
+				sCut = cut;
+			}
+			__syncthreads();
+			const int cut = sCut;
+			if (cut >= want) {
+				// materialise [0, cut): a left stop of rank k takes the k-th right stop (from the right), the rest stay
+				if (tid == 0) w[0] = ((lit_t) pv << 32) | (uint32_t) mS;
+				const int per = (cut - 1 + HU_LIT_THREADS - 1) / HU_LIT_THREADS;
+				const int p0 = 1 + tid * per, p1 = min(cut, p0 + per);
+				if (p0 < p1) {
+					const int t0 = p0 - base;
+					uint32_t k = preA[t0 >> 5] + __popc(faW[t0 >> 5] & ((1u << (t0 & 31)) - 1u)); // left stops before p0
+					int pb = -1;
+					for (int pp = p0; pp < p1; ++pp) {
+						const int t = pp - base;
+						if ((faW[t >> 5] >> (t & 31)) & 1u) {
+							if (pb < 0) pb = litSelect(fbW, preB, nW, totB - 1 - k);
+							else { // previous set bit of fb before pb
+								int wd = pb >> 5;
+								uint32_t bits = fbW[wd] & ((1u << (pb & 31)) - 1u);
+								while (!bits) bits = fbW[--wd];
+								pb = wd * 32 + 31 - __clz(bits);
+							}
+							const int pq = base + pb;
+							w[pp] = ((lit_t) VKEY(pq) << 32) | (uint32_t) VPOS(pq);
+							k++;
+						} else
+							w[pp] = ((lit_t) VKEY(pp) << 32) | (uint32_t) VPOS(pp);
+					}
+				}
+				if (tid == 0) {
+					stack[0][0] = 0; stack[0][1] = cut; stack[0][2] = depth0 - 1;
+					sTop = 1;
+					sBound = cut;
+				}
+				started = true;
+			} else {
+				// tiny cut: fall back to the in-place path on a full copy
+				for (int i = tid; i < n; i += HU_LIT_THREADS) w[i] = ((lit_t) keys[i] << 32) | (uint32_t) i;
+			}
+#undef VKEY
+#undef VPOS
+		}
+		__syncthreads();
 		atomicMax(&sMaxQ, mx);
-		const int want = min(a.maxNSeed, n);
-		if (tid == 0) {
-			int depth = 0;
-			for (int v = n; v > 1; v >>= 1) depth++; // std::__lg(n)
-			stack[0][0] = 0; stack[0][1] = n; stack[0][2] = 2 * depth;
+		if (!started && tid == 0) {
+			stack[0][0] = 0; stack[0][1] = n; stack[0][2] = depth0;
 			sTop = 1;
 		}
 		__syncthreads();
