@@ -148,7 +148,10 @@ int hu_batch_create(hu_batch** out, hu_db* db, int32_t maxReads, int32_t maxSeqL
 	HU_TRY(balloc(b, &b->dPlans, (size_t) b->maxSeq));
 	b->tracesCap = (long long) b->maxSeq * (maxSeqLen + K + 4);
 	HU_TRY(balloc(b, &b->dTraces, (size_t) b->tracesCap));
-	HU_TRY(balloc(b, &b->vit.aligned, (size_t) b->maxSeq * L));
+	HU_TRY(balloc(b, &b->vit.aligned, (size_t) b->maxSeq * L + 64)); // + slack for 16-byte rounded bulk copies
+	HU_TRY(balloc(b, &b->workItems, (size_t) maxReads * HU_MAX_SEED));
+	HU_TRY(balloc(b, &b->estItems, (size_t) maxReads * HU_MAX_SEED));
+	HU_TRY(balloc(b, &b->estItemsP, (size_t) maxReads * HU_MAX_SEED));
 	HU_TRY(balloc(b, &b->vit.rows, (size_t) b->maxSeq));
 	HU_TRY(balloc(b, &b->merged, (size_t) maxReads));
 	HU_TRY(balloc(b, &b->vit.fullCount, 2));

@@ -58,6 +58,20 @@ struct SeedArgs {
 	int* nSeeds;            // [nReads]
 };
 
+// one (read, seed) of the estimate stage, resolved once so that the streaming kernel has no dependent loads
+struct EstItem {
+	int rs;       // read * HU_MAX_SEED + seed slot
+	int u, v;     // seed node and its parent
+	int start, W; // window
+	int kind;     // 0: nothing to do (also the end-of-stream mark), 1: staged kernel, 2: wide-window kernel
+	double w0;    // branch length of (u, v)
+};
+
+struct EstItemP {
+	double cDist, ratio; // pDist(child seq, read); attachment ratio cDist / (cDist + pDist)
+	double P[2][16];     // P(w0 ratio), P(w0 (1 - ratio))
+};
+
 } // namespace hu
 
 struct hu_batch {
@@ -90,7 +104,9 @@ struct hu_batch {
 	hu_place_row* places;  // [maxReads][HU_MAX_SEED] placeSeq results, filter order
 	hu_place_row* best;    // [maxReads]
 	int* equalPerm;        // [HU_MAX_SEED+1]
-	int* workItems;        // compacted (read, slot) lists for K3/K4
+	int* workItems;        // items of K3 whose window is wider than the staged kernel takes
+	hu::EstItem* estItems; // [maxReads][HU_MAX_SEED] item records of K3
+	hu::EstItemP* estItemsP;
 	int* workCount;
 	unsigned long long* litIds; // (key, candidate position) work rows of the literal seed order, one per resident CTA
 	double* placeSlab;     // global rho slabs for windows wider than the shared-memory capacity

@@ -224,6 +224,36 @@ __global__ void toLogKernel(const double* __restrict__ E, const double* __restri
 	st4(logMsg + i * 4, v);
 }
 
+// prefix sums of the per-column scales at 32-column granularity, one warp per node row:
+// P32[row][b] = sum of S[row][c] over c < 32 b.  The SEP kernels need the scales only summed over a window.
+__global__ void scalePrefixKernel(const double* __restrict__ S, long long nRows, int csLen, int nWords, double* __restrict__ P32) {
+	const long long row = (long long) blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+	const int lane = threadIdx.x & 31;
+	if (row >= nRows) return;
+	const double* s = S + (size_t) row * csLen;
+	double* out = P32 + (size_t) row * (nWords + 1);
+	double run = 0;
+	if (lane == 0) out[0] = 0;
+	for (int b = 0; b < nWords; ++b) {
+		const int c = b * 32 + lane;
+		double v = c < csLen ? s[c] : 0.0;
+		for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+		run += v;
+		if (lane == 0) out[b + 1] = run;
+	}
+}
+
+// placeSeq()'s literal return value for a window of W columns: the reference adds log(pi . e^1) W times
+// (src/PhyloTreeUnrooted.cpp:707-712 over a root message of INVALID_LOGLIK)
+__global__ void litTabKernel(Model m, int csLen, double* __restrict__ tab) {
+	if (blockIdx.x || threadIdx.x) return;
+	const double ones[4] = {1.0, 1.0, 1.0, 1.0};
+	const double c1 = dpsVec(m.pi, ones);
+	double lit = 0;
+	tab[0] = 0;
+	for (int j = 1; j <= csLen; ++j) { lit += c1; tab[j] = lit; }
+}
+
 // inferSeq(): arg-max of the upward message for internal nodes (src/PhyloTreeUnrooted.cpp:1085-1093)
 __global__ void inferSeqKernel(int nNodes, int csLen, int root, const int* __restrict__ childStart,
 		const double* __restrict__ up, const double* __restrict__ rootMsg, int8_t* __restrict__ seq) {
@@ -338,7 +368,8 @@ static int createImpl(hu_db* db, const hu_hmm_params* hp, const hu_tree_desc* td
 	HU_TRY(upload(db, &t.taxon, td->taxon, (size_t) n));
 	db->heightHost.assign(td->height, td->height + n);
 	int8_t* seq;
-	HU_TRY(devAlloc(db, &seq, (size_t) n * csLen));
+	HU_TRY(devAlloc(db, &seq, (size_t) n * csLen + 64)); // + slack: bulk copies of a window are rounded to 16 bytes
+	HU_CUDA(cudaMemset(seq + (size_t) n * csLen, 0xfe, 64));
 	HU_CUDA(cudaMemcpy(seq, td->seq, (size_t) n * csLen, cudaMemcpyHostToDevice));
 	t.seq = seq;
 	double *up, *dn, *upS, *dnS;
@@ -434,6 +465,22 @@ static int createImpl(hu_db* db, const hu_hmm_params* hp, const hu_tree_desc* td
 		HU_CUDA(cudaMemset(dn + (size_t) td->root * csLen * 4, 0, (size_t) csLen * 4 * sizeof(double)));
 		HU_CUDA(cudaMemset(upS + (size_t) td->root * csLen, 0, (size_t) csLen * sizeof(double)));
 		HU_CUDA(cudaMemset(dnS + (size_t) td->root * csLen, 0, (size_t) csLen * sizeof(double)));
+	}
+	// ---- derived tables of the SEP kernels ----
+	{
+		double *upP, *dnP, *lit;
+		Model* md;
+		HU_TRY(devAlloc(db, &upP, (size_t) n * (t.nWords + 1)));
+		HU_TRY(devAlloc(db, &dnP, (size_t) n * (t.nWords + 1)));
+		HU_TRY(devAlloc(db, &lit, (size_t) csLen + 1));
+		HU_TRY(devAlloc(db, &md, 1));
+		scalePrefixKernel<<<(n + 7) / 8, 256>>>(upS, n, csLen, t.nWords, upP);
+		scalePrefixKernel<<<(n + 7) / 8, 256>>>(dnS, n, csLen, t.nWords, dnP);
+		litTabKernel<<<1, 32>>>(db->model, csLen, lit);
+		HU_CUDA(cudaMemcpy(md, &db->model, sizeof(Model), cudaMemcpyHostToDevice));
+		HU_CUDA(cudaGetLastError());
+		HU_CUDA(cudaDeviceSynchronize());
+		t.upP32 = upP; t.dnP32 = dnP; t.litTab = lit; t.modelDev = md;
 	}
 	// ---- scan order + bit planes (after sequence inference) ----
 	std::vector<int8_t> hseq;

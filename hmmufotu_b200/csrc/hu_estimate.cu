@@ -1,18 +1,29 @@
 // K3: the "Estimate" stage of SEP -- PTUnrooted::estimateSeq for every (read, seed)
 // (src/PhyloTreeUnrooted.cpp:849-877) followed by filterPlacements (src/HmmUFOtu_main.cpp:162-173).
 //
-// One warp per (read, seed), persistent over the item space; no block-level synchronisation.  The two message
-// windows of the seed edge (linear form: 32 B of max-normalised exponentials + 8 B scale per column, see
-// hu_internal.cuh) are streamed from HBM with 128-bit loads, columns across lanes.  Per column
+// HBM-bound: an item streams the two message windows of its seed edge (linear form, 32 B per column each,
+// hu_internal.cuh) exactly once.  estimateStagedKernel is a persistent producer/consumer pipeline, two CTAs per
+// SM: one producer lane walks the item list and issues cp.async.bulk copies (hu_pipe.cuh) of 256-column chunks
+// of U and V into a 3-stage shared-memory ring, plus the three byte windows (read, child, parent sequence) of
+// the NEXT item; eight consumer warps take one column per thread and chunk.  Per column
 //   g_j = (P(wur) E^U_j) * (P(wvr) E^V_j)              (= e^{R_j} of the reference up to the column scale)
-// pass 1 counts the columns whose arg-max state differs from the read's (wnr, cpp:1018-1032); pass 2 re-reads
-// the window (L1/L2-resident by then) and sums log(pi . (g_j * P(wnr) n_j)) + scales (cpp:872-874):
-// 64 fused multiply-adds and one log per column, no exp.
+// pass 1 counts the columns whose arg-max state differs from the read's (wnr, cpp:1018-1032) and parks g_j in
+// shared memory; pass 2 sums log(pi . (g_j * P(wnr) n_j)) from there (cpp:872-874).  The per-column scales enter
+// only through their sum over the window, taken from 32-column prefix sums (TreeDev::upP32) plus the two ragged
+// ends.  64 fused multiply-adds and one log per column, no exp.  Windows wider than the shared-memory budget
+// (HU_EST_CAPW columns) go to estimateWideKernel, one warp per item, which reads the window twice.
 #include "hu_batch.cuh"
+#include "hu_pipe.cuh"
 
 namespace hu {
 
-#define HU_EST_WARPS 8
+#define HU_EST_CONS 256                  // consumer threads (8 warps), one column of a chunk each
+#define HU_EST_THREADS (HU_EST_CONS + 32) // + the producer warp
+#define HU_EST_CH 256                    // columns per ring stage
+#define HU_EST_STAGES 3
+#define HU_EST_CAPW 1536                 // widest window the staged kernel takes
+#define HU_EST_HDR (HU_EST_CAPW + 32)    // bytes per staged sequence window (16-byte alignment slack on both sides)
+#define HU_EST_WARPS 8                   // warps per CTA of the wide-window kernel
 
 struct EstArgs {
 	int nReads, maxNSeed, pad0, pad1;
@@ -22,35 +33,277 @@ struct EstArgs {
 	const int* seedIds;
 	const int* nSeeds;
 	hu_place_row* est;
-	int* cursor;
+	EstItem* items;   // [nReads * maxNSeed]
+	EstItemP* itemsP; // [nReads * maxNSeed]: distances, ratio and the two transition matrices of an item
+	int* wideCount;   // [0] number of wide items, [1] cursor of the wide kernel
+	int* wideList;
 };
+
+// DNASubModel::Pr(v) by a half warp: `l` = 0..15 is this lane's matrix entry (row l / 4, column l % 4).  GTR
+// spreads the four exponentials and the sixteen 4-term products over the lanes (same operand order as modelPr,
+// so the same bits); the closed-form models are evaluated by the half warp's first lane.
+__device__ __forceinline__ void modelPrHalfWarp(const Model& m, double v, double* P, int l, unsigned int mask) {
+	if (m.type == HU_GTR) {
+		const double ek = exp(m.lambda[l & 3] * v);
+		const int i = l >> 2, j = l & 3, base = (threadIdx.x & 31) & ~3;
+		double sacc = 0;
+		for (int k = 0; k < 4; ++k) {
+			const double e = __shfl_sync(mask, ek, base + k);
+			sacc += m.U[i * 4 + k] * e * m.Ui[k * 4 + j];
+		}
+		P[l] = v == 0 ? ((i == j) ? 1.0 : 0.0) : sacc;
+	} else if (l == 0)
+		modelPr(m, v, P);
+}
+
+// ---- item list: one record per (read, seed), so that the streaming kernel has no dependent loads and no
+// per-item serial prologue.  One warp per item: the p-distances of the read to the child and parent sequences
+// (SeqUtils::pDist over the window), the attachment ratio and the two transition matrices P(wur), P(wvr). ----
+__global__ void __launch_bounds__(256) estPlanKernel(EstArgs a, TreeDev t, Model m) {
+	const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+	const int lane = threadIdx.x & 31;
+	if (i >= a.nReads * a.maxNSeed) return;
+	const int r = i / a.maxNSeed, s = i % a.maxNSeed;
+	EstItem it;
+	it.rs = r * HU_MAX_SEED + s; it.u = 0; it.v = 0; it.start = 0; it.W = 0; it.kind = 0; it.w0 = 0;
+	const int ws = a.winStart[r];
+	if (ws >= 0 && s < a.nSeeds[r]) {
+		const int u = a.seedIds[(size_t) r * HU_MAX_SEED + s];
+		it.u = u; it.v = t.parent[u]; it.start = ws; it.W = a.winEnd[r] - ws + 1; it.w0 = t.blen[u];
+		it.kind = it.W <= HU_EST_CAPW ? 1 : 2;
+		const int8_t* x = a.aligned + (size_t) r * t.csLen + ws;
+		const int8_t* su = t.seq + (size_t) it.u * t.csLen + ws;
+		const int8_t* sv = t.seq + (size_t) it.v * t.csLen + ws;
+		unsigned int cu = 0, cv = 0; // (N << 16) | d
+		for (int c = lane; c < it.W; c += 32) {
+			const int b = x[c];
+			if (b >= 0) {
+				const int bu = su[c], bv = sv[c];
+				if (bu >= 0) cu += 0x10000u + (bu != b);
+				if (bv >= 0) cv += 0x10000u + (bv != b);
+			}
+		}
+		for (int o = 16; o > 0; o >>= 1) {
+			cu += __shfl_xor_sync(0xffffffffu, cu, o);
+			cv += __shfl_xor_sync(0xffffffffu, cv, o);
+		}
+		const double cDist = (double) (cu & 0xffffu) / (double) (cu >> 16);
+		const double pDist = (double) (cv & 0xffffu) / (double) (cv >> 16);
+		double ratio = cDist / (cDist + pDist);
+		if (isnan(ratio)) ratio = 0.5;
+		const double wur = it.w0 * ratio, wvr = it.w0 - wur;
+		EstItemP& ip = a.itemsP[i];
+		modelPrHalfWarp(m, lane < 16 ? wur : wvr, ip.P[lane >> 4], lane & 15, 0xffffffffu);
+		if (lane == 0) {
+			ip.cDist = cDist; ip.ratio = ratio;
+			if (it.kind == 2) a.wideList[atomicAdd(a.wideCount, 1)] = i;
+		}
+	}
+	if (lane == 0) a.items[i] = it;
+}
+
+struct EstSmem {
+	double ring[HU_EST_STAGES][2][HU_EST_CH * 4]; // U chunk, V chunk
+	double g[4][HU_EST_CAPW];                     // g_j of the current item, one plane per state
+	EstItemP rec[2];                              // cDist, ratio, P(wur), P(wvr) of the staged items (bulk-copied)
+	int8_t hdr[2][HU_EST_HDR];                    // the read's window, double buffered
+	EstItem meta[2];
+	int hoff[2];                                  // offset of the window inside hdr (alignment remainder)
+	double P2[16];                                // P(wnr)
+	double Np[5][4];                              // P(wnr) applied to the read's leaf vector, per base / gap
+	unsigned int redB[HU_EST_CONS / 32];
+	double redC[HU_EST_CONS / 32];
+	unsigned long long full[HU_EST_STAGES], empty[HU_EST_STAGES], hfull[2], hempty[2];
+};
+
+// one message column out of a ring stage: two 128-bit reads whose halves are swapped for every other group of
+// four threads, so that a quarter-warp covers all 32 banks
+__device__ __forceinline__ void ldsColumn(const double* __restrict__ chunk, int tid, double* v) {
+	const int sw = (tid >> 2) & 1;
+	const double2 a = *reinterpret_cast<const double2*>(chunk + 4 * tid + 2 * sw);
+	const double2 b = *reinterpret_cast<const double2*>(chunk + 4 * tid + 2 * (1 - sw));
+	v[0] = sw ? b.x : a.x; v[1] = sw ? b.y : a.y;
+	v[2] = sw ? a.x : b.x; v[3] = sw ? a.y : b.y;
+}
+
+__global__ void __launch_bounds__(HU_EST_THREADS, 2) estimateStagedKernel(EstArgs a, TreeDev t, Model m) {
+	extern __shared__ __align__(128) unsigned char estRaw[];
+	EstSmem& sm = *reinterpret_cast<EstSmem*>(estRaw);
+	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+	const int total = a.nReads * a.maxNSeed;
+	const int nBatches = (total + 31) / 32;
+	if (tid == 0) {
+		for (int i = 0; i < HU_EST_STAGES; ++i) { mbarInit(&sm.full[i], 1); mbarInit(&sm.empty[i], HU_EST_CONS / 32); }
+		for (int i = 0; i < 2; ++i) { mbarInit(&sm.hfull[i], 1); mbarInit(&sm.hempty[i], 1); }
+		mbarInitFence();
+	}
+	__syncthreads();
+	if (warp == HU_EST_CONS / 32) {
+		// ================= producer warp: lane l holds item 32 * batch + l; lane 0 issues =================
+		int st = 0, ph = 0, h = 0, hph = 0;
+		EstItem cur;
+		cur.kind = 0;
+		int batch = blockIdx.x;
+		if (batch < nBatches && batch * 32 + lane < total) cur = a.items[batch * 32 + lane];
+		for (; batch < nBatches; batch += gridDim.x) {
+			EstItem nxt; // the records of the next batch are in flight while this one is issued
+			nxt.kind = 0;
+			const int nb = batch + gridDim.x;
+			if (nb < nBatches && nb * 32 + lane < total) nxt = a.items[nb * 32 + lane];
+			unsigned int todo = __ballot_sync(0xffffffffu, cur.kind == 1);
+			while (todo) {
+				const int l = __ffs(todo) - 1;
+				todo &= todo - 1;
+				EstItem it;
+				it.rs = __shfl_sync(0xffffffffu, cur.rs, l); it.u = __shfl_sync(0xffffffffu, cur.u, l);
+				it.v = __shfl_sync(0xffffffffu, cur.v, l); it.start = __shfl_sync(0xffffffffu, cur.start, l);
+				it.W = __shfl_sync(0xffffffffu, cur.W, l); it.kind = 1;
+				it.w0 = __shfl_sync(0xffffffffu, cur.w0, l);
+				if (lane == 0) {
+					const int r = it.rs / HU_MAX_SEED;
+					mbarWaitRelaxed(&sm.hempty[h], hph ^ 1);
+					sm.meta[h] = it;
+					const int8_t* src = a.aligned + (size_t) r * t.csLen + it.start;
+					const int off = (int) ((uintptr_t) src & 15);
+					const uint32_t bytes = (uint32_t) ((off + it.W + 15) & ~15);
+					sm.hoff[h] = off;
+					mbarArriveExpectTx(&sm.hfull[h], bytes + (uint32_t) sizeof(EstItemP));
+					bulkLoad(sm.hdr[h], src - off, bytes, &sm.hfull[h]);
+					bulkLoad(&sm.rec[h], a.itemsP + ((size_t) r * a.maxNSeed + it.rs % HU_MAX_SEED), (uint32_t) sizeof(EstItemP), &sm.hfull[h]);
+					const double* U = t.up + ((size_t) it.u * t.csLen + it.start) * 4;
+					const double* V = t.dn + ((size_t) it.u * t.csLen + it.start) * 4;
+					for (int c0 = 0; c0 < it.W; c0 += HU_EST_CH) {
+						const uint32_t nb32 = (uint32_t) min(HU_EST_CH, it.W - c0) * 32u;
+						mbarWaitRelaxed(&sm.empty[st], ph ^ 1);
+						mbarArriveExpectTx(&sm.full[st], 2 * nb32);
+						bulkLoad(sm.ring[st][0], U + (size_t) c0 * 4, nb32, &sm.full[st]);
+						bulkLoad(sm.ring[st][1], V + (size_t) c0 * 4, nb32, &sm.full[st]);
+						if (++st == HU_EST_STAGES) { st = 0; ph ^= 1; }
+					}
+				}
+				h ^= 1;
+				if (h == 0) hph ^= 1;
+			}
+			cur = nxt;
+		}
+		if (lane == 0) { // end of the item stream
+			mbarWaitRelaxed(&sm.hempty[h], hph ^ 1);
+			sm.meta[h].kind = 0;
+			mbarArrive(&sm.hfull[h]);
+		}
+		return;
+	}
+	// ================= consumer warps =================
+	int piMax = 0; // argmax of log(pi): state of a gap column of the read
+	for (int k = 1; k < 4; ++k) if (m.logPi[k] > m.logPi[piMax]) piMax = k;
+	int st = 0, ph = 0, h = 0, hph = 0;
+	for (;;) {
+		mbarWait(&sm.hfull[h], hph);
+		const EstItem it = sm.meta[h];
+		if (it.kind == 0) break;
+		const int W = it.W;
+		const int8_t* x = sm.hdr[h] + sm.hoff[h];
+		const double* P0 = sm.rec[h].P[0];
+		const double* P1 = sm.rec[h].P[1];
+		// the window sums of the scales ride along in the log-likelihood accumulators of two warps
+		double ll = 0;
+		if (warp == 2) ll = windowScale(t.upS, t.upP32, it.u, t.csLen, t.nWords, it.start, it.start + W - 1, lane);
+		if (warp == 3) ll = windowScale(t.dnS, t.dnP32, it.u, t.csLen, t.nWords, it.start, it.start + W - 1, lane);
+		// ---- pass 1: the unweighted branch-length estimate; g_j parked in shared memory ----
+		unsigned int diff = 0;
+		for (int c0 = 0; c0 < W; c0 += HU_EST_CH) {
+			mbarWait(&sm.full[st], ph);
+			const int c = c0 + tid;
+			if (c < W) {
+				double eu[4], ev[4], ya[4], yb[4], g[4];
+				ldsColumn(sm.ring[st][0], tid, eu);
+				ldsColumn(sm.ring[st][1], tid, ev);
+				matVec4(P0, eu, ya);
+				matVec4(P1, ev, yb);
+				for (int k = 0; k < 4; ++k) { g[k] = ya[k] * yb[k]; sm.g[k][c] = g[k]; }
+				const int b = x[c];
+				diff += argmax4(g) != (b >= 0 ? b : piMax);
+			}
+			__syncwarp();
+			if (lane == 0) mbarArrive(&sm.empty[st]);
+			if (++st == HU_EST_STAGES) { st = 0; ph ^= 1; }
+		}
+		for (int o = 16; o > 0; o >>= 1) diff += __shfl_xor_sync(0xffffffffu, diff, o);
+		if (lane == 0) sm.redB[warp] = diff;
+		consumerSync(HU_EST_CONS);
+		diff = 0;
+		for (int k = 0; k < HU_EST_CONS / 32; ++k) diff += sm.redB[k];
+		const double wnr = (double) diff / (double) W;
+		// ---- P(wnr) applied to the read's leaf vector: depends on the base only ----
+		if (warp == 0) {
+			if (lane < 16) modelPrHalfWarp(m, wnr, sm.P2, lane, 0x0000ffffu);
+			__syncwarp();
+			if (lane < 5) {
+				double n[4], y[4];
+				leafLin(m, lane < 4 ? lane : -1, n);
+				matVec4(sm.P2, n, y);
+				for (int k = 0; k < 4; ++k) sm.Np[lane][k] = y[k];
+			}
+		}
+		consumerSync(HU_EST_CONS);
+		// ---- pass 2: treeLoglik(pi, UPr + VPr + NPr) ----
+		for (int c = tid; c < W; c += HU_EST_CONS) {
+			const int b = x[c];
+			const double* np = sm.Np[b >= 0 ? b : 4];
+			double z[4];
+			for (int k = 0; k < 4; ++k) z[k] = sm.g[k][c] * np[k];
+			ll += log(dotPi(m, z));
+		}
+		for (int o = 16; o > 0; o >>= 1) ll += __shfl_xor_sync(0xffffffffu, ll, o);
+		if (lane == 0) sm.redC[warp] = ll;
+		consumerSync(HU_EST_CONS);
+		if (tid == 0) {
+			const double cDist = sm.rec[h].cDist, ratio = sm.rec[h].ratio;
+			mbarArrive(&sm.hempty[h]); // every consumer is past its last read of this item's staged window and record
+			ll = 0;
+			for (int k = 0; k < HU_EST_CONS / 32; ++k) ll += sm.redC[k];
+			const int r = it.rs / HU_MAX_SEED;
+			hu_place_row row;
+			row.start = it.start; row.end = it.start + W - 1;
+			row.cNode = it.u; row.pNode = it.v; row.aNode = ratio <= 0.5 ? it.u : it.v;
+			row.taxon = t.taxon[row.aNode];
+			row.dist = cDist;
+			row.wuv = it.w0; row.ratio = ratio; row.wnr = wnr;
+			row.loglik = ll; row.loglikTrue = 0; row.estLoglik = ll;
+			row.height = 0; row.annoDist = 0; row.qPlace = 0; row.qTaxon = 0;
+			row.outerIters = 0; row.nPlaces = 0;
+			a.est[(size_t) r * HU_MAX_SEED + (it.rs % HU_MAX_SEED)] = row;
+		}
+		h ^= 1;
+		if (h == 0) hph ^= 1;
+	}
+}
 
 struct EstShared {
 	double P[3][16]; // P(wur), P(wvr), P(wnr)
 	double Np[5][4]; // P(wnr) applied to the read's leaf vector, per base / gap
 };
 
-__global__ void __launch_bounds__(HU_EST_WARPS * 32) estimateKernel(EstArgs a, TreeDev t, Model m) {
+// windows wider than HU_EST_CAPW: one warp per item, the window is read twice (second time mostly from L2)
+__global__ void __launch_bounds__(HU_EST_WARPS * 32) estimateWideKernel(EstArgs a, TreeDev t, Model m) {
 	__shared__ EstShared sh[HU_EST_WARPS];
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	EstShared& ws = sh[warp];
-	const int total = a.nReads * a.maxNSeed;
-	int piMax = 0; // argmax of log(pi): state of a gap column of the read
+	const int total = a.wideCount[0];
+	int piMax = 0;
 	for (int k = 1; k < 4; ++k) if (m.logPi[k] > m.logPi[piMax]) piMax = k;
 	for (;;) {
-		int item = 0;
-		if (lane == 0) item = atomicAdd(a.cursor, 1);
-		item = __shfl_sync(0xffffffffu, item, 0);
-		if (item >= total) return;
-		const int r = item / a.maxNSeed, s = item % a.maxNSeed;
-		if (a.winStart[r] < 0 || s >= a.nSeeds[r]) continue;
-		const int start = a.winStart[r], end = a.winEnd[r], W = end - start + 1;
-		const int u = a.seedIds[(size_t) r * HU_MAX_SEED + s];
-		const int v = t.parent[u];
+		int q = 0;
+		if (lane == 0) q = atomicAdd(a.wideCount + 1, 1);
+		q = __shfl_sync(0xffffffffu, q, 0);
+		if (q >= total) return;
+		const EstItem it = a.items[a.wideList[q]];
+		const int r = it.rs / HU_MAX_SEED, s = it.rs % HU_MAX_SEED;
+		const int start = it.start, W = it.W, end = start + W - 1;
+		const int u = it.u, v = it.v;
 		const int8_t* x = a.aligned + (size_t) r * t.csLen + start;
 		const int8_t* su = t.seq + (size_t) u * t.csLen + start;
 		const int8_t* sv = t.seq + (size_t) v * t.csLen + start;
-		// ---- p-distances to the child and parent sequences (SeqUtils::pDist); counts < 2^16 packed in pairs ----
 		unsigned int cu = 0, cv = 0; // (N << 16) | d
 		for (int c = lane; c < W; c += 32) {
 			const int b = x[c];
@@ -68,23 +321,18 @@ __global__ void __launch_bounds__(HU_EST_WARPS * 32) estimateKernel(EstArgs a, T
 		const double pDist = (double) (cv & 0xffffu) / (double) (cv >> 16);
 		double ratio = cDist / (cDist + pDist);
 		if (isnan(ratio)) ratio = 0.5;
-		const double w0 = t.blen[u];
+		const double w0 = it.w0;
 		const double wur = w0 * ratio, wvr = w0 - wur;
 		__syncwarp();
 		if (lane < 2) modelPr(m, lane == 0 ? wur : wvr, ws.P[lane]);
 		__syncwarp();
 		const double* U = t.up + ((size_t) u * t.csLen + start) * 4;
 		const double* V = t.dn + ((size_t) u * t.csLen + start) * 4;
-		const double* US = t.upS + (size_t) u * t.csLen + start;
-		const double* VS = t.dnS + (size_t) u * t.csLen + start;
-		// ---- pass 1: the unweighted branch-length estimate ----
 		int diff = 0;
-		double sumScale = 0;
 		for (int c = lane; c < W; c += 32) {
 			double eu[4], ev[4], ya[4], yb[4], g[4];
 			ld4(U + (size_t) c * 4, eu);
 			ld4(V + (size_t) c * 4, ev);
-			sumScale += __ldg(US + c) + __ldg(VS + c);
 			matVec4(ws.P[0], eu, ya);
 			matVec4(ws.P[1], ev, yb);
 			for (int k = 0; k < 4; ++k) g[k] = ya[k] * yb[k];
@@ -93,7 +341,6 @@ __global__ void __launch_bounds__(HU_EST_WARPS * 32) estimateKernel(EstArgs a, T
 		}
 		for (int o = 16; o > 0; o >>= 1) diff += __shfl_xor_sync(0xffffffffu, diff, o);
 		const double wnr = (double) diff / (double) W;
-		// ---- P(wnr) applied to the read's leaf vector: depends on the base only ----
 		if (lane == 0) modelPr(m, wnr, ws.P[2]);
 		__syncwarp();
 		if (lane < 5) {
@@ -103,8 +350,8 @@ __global__ void __launch_bounds__(HU_EST_WARPS * 32) estimateKernel(EstArgs a, T
 			for (int k = 0; k < 4; ++k) ws.Np[lane][k] = y[k];
 		}
 		__syncwarp();
-		// ---- pass 2: treeLoglik(pi, UPr + VPr + NPr) ----
-		double ll = 0;
+		double ll = windowScale(t.upS, t.upP32, u, t.csLen, t.nWords, start, end, lane)
+		          + windowScale(t.dnS, t.dnP32, u, t.csLen, t.nWords, start, end, lane);
 		for (int c = lane; c < W; c += 32) {
 			double eu[4], ev[4], ya[4], yb[4], z[4];
 			ld4(U + (size_t) c * 4, eu);
@@ -116,7 +363,6 @@ __global__ void __launch_bounds__(HU_EST_WARPS * 32) estimateKernel(EstArgs a, T
 			for (int k = 0; k < 4; ++k) z[k] = (ya[k] * yb[k]) * np[k];
 			ll += log(dotPi(m, z));
 		}
-		ll += sumScale;
 		for (int o = 16; o > 0; o >>= 1) ll += __shfl_xor_sync(0xffffffffu, ll, o);
 		if (lane == 0) {
 			hu_place_row row;
@@ -162,15 +408,22 @@ int launchEstimate(hu_batch* b, const hu_sep_params* p) {
 	a.nReads = b->nReads; a.maxNSeed = p->maxNSeed; a.pad0 = a.pad1 = 0;
 	a.aligned = b->vit.aligned; a.winStart = b->winStart; a.winEnd = b->winEnd;
 	a.seedIds = b->seed.seedIds; a.nSeeds = b->seed.nSeeds;
-	a.est = b->est; a.cursor = b->workCount;
+	a.est = b->est; a.items = b->estItems; a.itemsP = b->estItemsP; a.wideCount = b->workCount + 2; a.wideList = b->workItems;
 	int sms = 0;
 	HU_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, db->device));
 	HU_CUDA(cudaMemsetAsync(b->workCount, 0, 4 * sizeof(int), b->stream));
-	const int grid = sms * 4;
-	estimateKernel<<<grid, HU_EST_WARPS * 32, 0, b->stream>>>(a, db->tree, db->model);
+	static bool attr = false;
+	if (!attr) {
+		HU_CUDA(cudaFuncSetAttribute(estimateStagedKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(EstSmem)));
+		attr = true;
+	}
+	const int total = a.nReads * a.maxNSeed;
+	estPlanKernel<<<(total + 7) / 8, 256, 0, b->stream>>>(a, db->tree, db->model);
+	estimateStagedKernel<<<sms * 2, HU_EST_THREADS, sizeof(EstSmem), b->stream>>>(a, db->tree, db->model);
+	estimateWideKernel<<<sms * 4, HU_EST_WARPS * 32, 0, b->stream>>>(a, db->tree, db->model); // exits at once when no window is wide
 	filterKernel<<<(b->nReads + 127) / 128, 128, 0, b->stream>>>(b->nReads, b->winStart, a.nSeeds, b->est, p->maxError, b->order, b->nKept);
 	HU_CUDA(cudaEventRecord(b->ev[5], b->stream));
-	b->launches += 2;
+	b->launches += 4;
 	HU_CUDA(cudaGetLastError());
 	return HU_OK;
 }

@@ -208,6 +208,10 @@ struct TreeDev {
 	const double* dn;        //                     exp(msg(parent -> id) - scale)
 	const double* upS;       // [nNodes][csLen]: the scales (max of the log-domain column)
 	const double* dnS;
+	const double* upP32;     // [nNodes][nWords + 1]: prefix sums of the scales at 32-column granularity,
+	const double* dnP32;     //   P32[b] = sum of the scales of columns < 32 b (window sums without streaming the scales)
+	const double* litTab;    // [csLen + 1]: W-fold sequential sum of log(pi . e^1): placeSeq's literal return value
+	const struct Model* modelDev; // copy of the model in global memory, for out-of-line routines
 	// seed scan, in PROFILE coordinates: bit (k-1)%32 of word (k-1)/32 is match column p2cs[k] (k = 1..K);
 	// [word][plane][nodeSlot], planes hi, lo, valid; nodeSlot = position in the scan order
 	const uint32_t* planes;
@@ -222,6 +226,26 @@ struct TreeDev {
 	int nCand;               // number of candidates (nNodes - 1)
 	int nGapSlots;           // slots [0, nGapSlots) hold nodes whose sequence has gaps (need the valid plane)
 };
+
+#ifdef __CUDACC__
+// sum of the scales of columns start..end of one node row, spread over the lanes of a warp
+__device__ __forceinline__ double windowScale(const double* __restrict__ S, const double* __restrict__ P32, int node, int csLen,
+		int nWords, int start, int end, int lane) {
+	const double* s = S + (size_t) node * csLen;
+	const int b0 = (start + 31) >> 5, b1 = (end + 1) >> 5;
+	double v = 0;
+	if (b0 <= b1) {
+		const double* p = P32 + (size_t) node * (nWords + 1);
+		if (lane == 0) v = __ldg(p + b1) - __ldg(p + b0);
+		int c = start + lane;
+		if (c < 32 * b0) v += __ldg(s + c);
+		c = 32 * b1 + lane;
+		if (c <= end) v += __ldg(s + c);
+	} else
+		for (int c = start + lane; c <= end; c += 32) v += __ldg(s + c);
+	return v;
+}
+#endif
 
 } // namespace hu
 

@@ -57,6 +57,20 @@ struct ColPrefetch {
 	}
 };
 
+// The transition matrices of one phase, by ONE out-of-line routine: lane 8 j + k builds matrix j (0: lu, 1: lv,
+// 2: ln) for rate category k.  Inlining the six-model switch at every call site made the kernel 180 KB of
+// code and the warps, each in a different phase, missed the instruction cache (ncu r1b: stall_no_instruction
+// 4.1 cycles per issue).  The model is read from its global-memory copy: taking the address of the by-value
+// kernel parameter would force a local-memory copy of it.
+__device__ __noinline__ void fillP(const Model* __restrict__ mg, double* __restrict__ wsP, int KK, double l0, double l1, double l2, int mask) {
+	const int lane = threadIdx.x & 31;
+	const int job = lane >> 3, k = lane & 7;
+	if (job < 3 && k < KK && ((mask >> job) & 1)) {
+		const double len = job == 0 ? l0 : job == 1 ? l1 : l2;
+		modelPr(*mg, len * (mg->dgK ? mg->dgR[k] : 1.0), wsP + (job * KK + k) * 16);
+	}
+}
+
 __device__ __forceinline__ double warpSum(double v) {
 	for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
 	return v;
@@ -74,7 +88,7 @@ __device__ __forceinline__ double rcpFast(double x) {
 
 // Felsenstein EM for one branch given rho_j, src/PhyloTreeUnrooted.cpp:749-798:
 // p <- (1/N) sum_j e^B p0 / (e^A q0 + e^B p0) = (1/N) sum_j p0 / (rho_j q0 + p0)
-__device__ double emBranch(const double* __restrict__ rho, int W, int nValid, double wInit, double cap, int* itersOut) {
+__device__ __noinline__ double emBranch(const double* __restrict__ rho, int W, int nValid, double wInit, double cap, int* itersOut) {
 	const int lane = threadIdx.x & 31;
 	double q0 = exp(-wInit), p0 = 1 - q0;
 	double p = p0, q = q0;
@@ -131,8 +145,6 @@ __global__ void __launch_bounds__(HU_PLACE_WARPS * 32) placeKernel(PlaceArgs a, 
 		const double w0 = t.blen[c];
 		const double* U = t.up + ((size_t) c * t.csLen + start) * 4;
 		const double* V = t.dn + ((size_t) c * t.csLen + start) * 4;
-		const double* US = t.upS + (size_t) c * t.csLen + start;
-		const double* VS = t.dnS + (size_t) c * t.csLen + start;
 		const int8_t* x = a.aligned + (size_t) r * t.csLen + start;
 		double* rho = W <= a.capW ? rhoS : a.slab + (size_t) slot * t.csLen;
 		double lu = w0 * e.ratio, lv = w0 * (1 - e.ratio), ln = e.wnr; // cpp:906-912
@@ -143,8 +155,7 @@ __global__ void __launch_bounds__(HU_PLACE_WARPS * 32) placeKernel(PlaceArgs a, 
 		for (iter = 0; iter < HU_MAX_ITER && 0 <= wur && wur <= w0j; ++iter) {
 			// ---- msg(r->n) from u and v, then optimise the n-r branch (cap 1) ----
 			__syncwarp();
-			if (lane < KK) modelPr(m, lu * (m.dgK ? m.dgR[lane] : 1.0), wsP + (0 * KK + (lane)) * 16);
-			else if (lane >= 8 && lane < 8 + KK) modelPr(m, lv * (m.dgK ? m.dgR[lane - 8] : 1.0), wsP + (1 * KK + (lane - 8)) * 16);
+			fillP(t.modelDev, wsP, KK, lu, lv, ln, 3);
 			__syncwarp();
 			int nValid = 0;
 			ColPrefetch pf;
@@ -170,7 +181,7 @@ __global__ void __launch_bounds__(HU_PLACE_WARPS * 32) placeKernel(PlaceArgs a, 
 			ln = wnr;
 			// ---- msg(r->u) from v and n, then optimise the u-r branch (cap w0) ----
 			__syncwarp();
-			if (lane < KK) modelPr(m, ln * (m.dgK ? m.dgR[lane] : 1.0), wsP + (2 * KK + (lane)) * 16);
+			fillP(t.modelDev, wsP, KK, lu, lv, ln, 4);
 			__syncwarp();
 			for (int q = lane; q < KK * 5; q += 32) {
 				const int k = q / 5, b = q % 5;
@@ -210,9 +221,7 @@ __global__ void __launch_bounds__(HU_PLACE_WARPS * 32) placeKernel(PlaceArgs a, 
 		}
 		// ---- intended root log-likelihood: sum_j log(pi . exp(loglik(r, j))) ----
 		__syncwarp();
-		if (lane < KK) modelPr(m, lu * (m.dgK ? m.dgR[lane] : 1.0), wsP + (0 * KK + (lane)) * 16);
-		else if (lane >= 8 && lane < 8 + KK) modelPr(m, lv * (m.dgK ? m.dgR[lane - 8] : 1.0), wsP + (1 * KK + (lane - 8)) * 16);
-		else if (lane >= 16 && lane < 16 + KK) modelPr(m, ln * (m.dgK ? m.dgR[lane - 16] : 1.0), wsP + (2 * KK + (lane - 16)) * 16);
+		fillP(t.modelDev, wsP, KK, lu, lv, ln, 7);
 		__syncwarp();
 		for (int q = lane; q < KK * 5; q += 32) {
 			const int k = q / 5, b = q % 5;
@@ -222,12 +231,12 @@ __global__ void __launch_bounds__(HU_PLACE_WARPS * 32) placeKernel(PlaceArgs a, 
 			for (int i = 0; i < 4; ++i) wsNP[(k * 5 + b) * 4 + i] = y[i];
 		}
 		__syncwarp();
-		double tl = 0;
+		double tl = windowScale(t.upS, t.upP32, c, t.csLen, t.nWords, start, end, lane)
+		          + windowScale(t.dnS, t.dnP32, c, t.csLen, t.nWords, start, end, lane);
 		ColPrefetch pf;
 		pf.init(U, V, x, lane, W);
 		for (int cI = lane; cI < W; cI += 32) {
 			double eu[4], ev[4], ya[4], yb[4], g[4] = {0, 0, 0, 0};
-			const double sc = __ldg(US + cI) + __ldg(VS + cI);
 			const int b = pf.next(U, V, x, cI + 32, W, eu, ev);
 			for (int k = 0; k < KK; ++k) {
 				matVec4(wsP + (0 * KK + (k)) * 16, eu, ya);
@@ -235,17 +244,13 @@ __global__ void __launch_bounds__(HU_PLACE_WARPS * 32) placeKernel(PlaceArgs a, 
 				const double* np = wsNP + (k * 5 + (b >= 0 ? b : 4)) * 4;
 				for (int i = 0; i < 4; ++i) g[i] += (ya[i] * yb[i]) * np[i];
 			}
-			tl += log(dotPi(m, g) / (double) KK) + sc;
+			tl += log(dotPi(m, g) / (double) KK);
 		}
 		tl = warpSum(tl);
 		if (lane == 0) {
 			hu_place_row row = e;
-			// literal return value: treeLoglik over a root message of INVALID_LOGLIK = 1
-			const double ones[4] = {1.0, 1.0, 1.0, 1.0};
-			const double c1 = dpsVec(m.pi, ones);
-			double lit = 0;
-			for (int j = 0; j < W; ++j) lit += c1;
-			row.loglik = lit;
+			// literal return value: treeLoglik over a root message of INVALID_LOGLIK = 1, tabulated per W
+			row.loglik = t.litTab[W];
 			row.loglikTrue = tl;
 			row.wnr = ln;
 			row.ratio = lu / w0;

@@ -304,6 +304,7 @@ __global__ void __launch_bounds__(HU_SEL_THREADS) seedSelectKernel(SeedArgs a, i
 // the k-th stop of the left scan is swapped with the k-th stop of the right scan while the former lies left
 // of the latter, which prefix counts over the bitmaps decide for every element at once.
 #define HU_LIT_THREADS 512
+#define HU_LIT_UNROLL 8 // key loads in flight per lane in the flag passes
 #define HU_LIT_SMALL 256 // ranges up to this size are finished by one thread on a shared-memory copy, literally
 
 typedef unsigned long long lit_t;               // (key << 32) | candidate position; only the key is compared
@@ -394,14 +395,25 @@ __global__ void __launch_bounds__(HU_LIT_THREADS) seedSortLiteralKernel(SeedArgs
 #define VKEY(p) ((p) == mS ? k0v : keys[p])
 #define VPOS(p) ((p) == mS ? 0 : (p))
 			const int base = 1, cnt = n - 1, nW = (cnt + 31) / 32;
-			for (int wd = warp; wd < nW; wd += nWarps) {
-				const int t = wd * 32 + lane;
-				const bool ok = t < cnt;
-				const uint32_t v = ok ? VKEY(base + t) : 0u;
-				if (ok && v != 0xFFFFFFFFu) mx = max(mx, v);
-				const uint32_t ba = __ballot_sync(0xffffffffu, ok && !(v < pv));
-				const uint32_t bb = __ballot_sync(0xffffffffu, ok && !(pv < v));
-				if (lane == 0) { faW[wd] = ba; fbW[wd] = bb; }
+			// HU_LIT_UNROLL independent key loads per lane and trip: the pass is bound by load latency, not bandwidth
+			for (int wd0 = warp; wd0 < nW; wd0 += nWarps * HU_LIT_UNROLL) {
+				uint32_t vv[HU_LIT_UNROLL];
+#pragma unroll
+				for (int u = 0; u < HU_LIT_UNROLL; ++u) {
+					const int t = (wd0 + u * nWarps) * 32 + lane;
+					vv[u] = t < cnt ? VKEY(base + t) : 0u;
+				}
+#pragma unroll
+				for (int u = 0; u < HU_LIT_UNROLL; ++u) {
+					const int wd = wd0 + u * nWarps;
+					if (wd >= nW) break;
+					const bool ok = wd * 32 + lane < cnt;
+					const uint32_t v = vv[u];
+					if (ok && v != 0xFFFFFFFFu) mx = max(mx, v);
+					const uint32_t ba = __ballot_sync(0xffffffffu, ok && !(v < pv));
+					const uint32_t bb = __ballot_sync(0xffffffffu, ok && !(pv < v));
+					if (lane == 0) { faW[wd] = ba; fbW[wd] = bb; }
+				}
 			}
 			if (pv != 0xFFFFFFFFu) mx = max(mx, pv);
 			__syncthreads();
@@ -533,13 +545,23 @@ __global__ void __launch_bounds__(HU_LIT_THREADS) seedSortLiteralKernel(SeedArgs
 				__syncthreads();
 				const uint32_t pv = LIT_KEY(w[lo]);
 				const int base = lo + 1, cnt = hi - base, nW = (cnt + 31) / 32;
-				for (int wd = warp; wd < nW; wd += nWarps) {
-					const int t = wd * 32 + lane;
-					const bool ok = t < cnt;
-					const uint32_t v = ok ? LIT_KEY(w[base + t]) : 0u;
-					const uint32_t ba = __ballot_sync(0xffffffffu, ok && !(v < pv));
-					const uint32_t bb = __ballot_sync(0xffffffffu, ok && !(pv < v));
-					if (lane == 0) { faW[wd] = ba; fbW[wd] = bb; }
+				for (int wd0 = warp; wd0 < nW; wd0 += nWarps * HU_LIT_UNROLL) {
+					uint32_t vv[HU_LIT_UNROLL];
+#pragma unroll
+					for (int u = 0; u < HU_LIT_UNROLL; ++u) {
+						const int t = (wd0 + u * nWarps) * 32 + lane;
+						vv[u] = t < cnt ? LIT_KEY(w[base + t]) : 0u;
+					}
+#pragma unroll
+					for (int u = 0; u < HU_LIT_UNROLL; ++u) {
+						const int wd = wd0 + u * nWarps;
+						if (wd >= nW) break;
+						const bool ok = wd * 32 + lane < cnt;
+						const uint32_t v = vv[u];
+						const uint32_t ba = __ballot_sync(0xffffffffu, ok && !(v < pv));
+						const uint32_t bb = __ballot_sync(0xffffffffu, ok && !(pv < v));
+						if (lane == 0) { faW[wd] = ba; fbW[wd] = bb; }
+					}
 				}
 				__syncthreads();
 				// exclusive prefix counts per word
