@@ -146,6 +146,7 @@ def _main(real_stdout):
     ap.add_argument("--batch", type=int, default=int(os.environ.get("HU_BENCH_BATCH", "8192")))
     ap.add_argument("--cpu-sample", type=int, default=int(os.environ.get("HU_BENCH_CPU_SAMPLE", "0")))
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--workspaces", type=int, default=int(os.environ.get("HU_BENCH_WORKSPACES", "2")))
     args = ap.parse_args()
     cfg = SCALES[args.scale]
     rank = int(os.environ.get("RANK", "0"))
@@ -157,7 +158,7 @@ def _main(real_stdout):
         # the reference arm: CPU only, rank 0 only
         if rank != 0:
             return 0
-        sample = args.cpu_sample or max(cores * 4, 32)
+        sample = args.cpu_sample or max(cores * 16, 128)
         db, reads = build_inputs(cfg, sample, read_seed=1000)
         vals = []
         ref = CpuReference(db, reads, cores)
@@ -188,7 +189,7 @@ def _main(real_stdout):
     from hmmufotu_b200 import engine
 
     B = args.batch
-    n_ws = 2
+    n_ws = max(1, args.workspaces)
     pool_batches = 4
     db, reads = build_inputs(cfg, B * pool_batches, read_seed=1 + rank)
     t0 = time.time()
@@ -283,7 +284,7 @@ def _main(real_stdout):
     h2d = int(batches[0].codes.nbytes + (B * 312))
     d2h = int(rows.nbytes + best.nbytes + sum(len(t) for t in traces))
 
-    # ---------------- roofline of the dominant kernel ----------------
+    # ---------------- roofline of every stage, and of the dominant one ----------------
     names = ["viterbi (K1)", "seed scan (K2)", "seed select (K2b)", "estimate (K3)", "place (K4)", "finalize"]
     per = stage[:6] / n_meas
     dom = int(np.argmax(per))
@@ -293,35 +294,46 @@ def _main(real_stdout):
         peaks = dict(hbm_gbs=float(pk["hbm_gbs"]), src="measured")
     except Exception:
         pass
-    alg = {1: stats["seedBytes"], 3: stats["estBytes"], 4: stats["placeBytes"]}
+    # DRAM bytes per launch of each stage's kernels from the last committed `ncu --set full` capture
+    traffic = {}
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    except Exception:
+        pass
+    sm_clock = (clocks.get("sm_mhz") or 1965.0) * 1e6
+    n_sm = torch.cuda.get_device_properties(local).multi_processor_count
+    # algorithmic work per step: bytes for the streaming stages, cell updates for Viterbi;
+    # the literal seed order reads each read's key vector once (4 B per candidate node)
+    alg = {1: stats["seedBytes"] / n_meas, 2: 4.0 * (db.n_nodes - 1) * B, 3: stats["estBytes"] / n_meas, 4: stats["placeBytes"] / n_meas}
     stages = {}
     for i, nme in enumerate(names):
         d = dict(ms=float(per[i]))
-        if i in alg:
-            d["algorithmic_GBps"] = alg[i] / n_meas / (per[i] / 1e3) / 1e9 if per[i] > 0 else None
+        if i in alg and per[i] > 0:
+            d["algorithmic_GBps"] = alg[i] / (per[i] / 1e3) / 1e9
+            d["hbm_frac"] = d["algorithmic_GBps"] / peaks["hbm_gbs"]
         if i == 0 and per[0] > 0:
             d["gcups"] = stats["cells"] / n_meas / (per[0] / 1e3) / 1e9
+            # 15 ALU operations per cell update against one issue per lane and clock (fp64 add/min: SURVEY.md 8(d) K1)
+            d["alu_issue_frac"] = d["gcups"] * 1e9 * 15 / (n_sm * 128 * sm_clock)
+        if nme in traffic:
+            d["dram_bytes_per_launch"] = traffic[nme]
         stages[nme] = d
-    dom_bytes = alg.get(dom, stats["seedBytes"]) / n_meas
-    achieved = dom_bytes / (per[dom] / 1e3) / 1e9 if per[dom] > 0 else 0.0
+    achieved = alg.get(dom, 0.0) / (per[dom] / 1e3) / 1e9 if per[dom] > 0 else 0.0
     roofline = dict(bound="hbm", kernel=names[dom], achieved=achieved, peak=peaks["hbm_gbs"], unit="GB/s",
-                    frac=achieved / peaks["hbm_gbs"], traffic=None, peak_source=peaks["src"],
-                    note="achieved = algorithmic bytes (SURVEY.md 8(d)) / CUDA-event time of the stage")
+                    frac=achieved / peaks["hbm_gbs"], traffic=traffic.get(names[dom]), peak_source=peaks["src"],
+                    note="achieved = algorithmic bytes per step (SURVEY.md 8(d)) / CUDA-event time of the stage; the seed scan "
+                         "shares one node tile among the reads of a batch, so its algorithmic rate exceeds physical HBM "
+                         "(it is bound by POPC issue); per-stage figures under 'stages'")
 
     # ---------------- CPU baseline (rank 0, N = 1) ----------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        sample = args.cpu_sample or max(cores * 2, 16)
+        sample = args.cpu_sample or max(cores * 40, 256)  # about 10-30 s of CPU work
         sub = reads.slice(0, sample)
         r = CpuReference(db, sub, cores).run()
         cpu = dict(value=r["reads_per_s"], unit="reads/s", cores=cores, kind="port",
                    sample="%d reads of the same pool, %d threads, %.1fs; oracle tree cut to consensus columns %d..%d (built in %.0fs, untimed)"
                           % (sample, cores, r["seconds"], r["columns"][0], r["columns"][1], r["build_seconds"]))
-        # and check the GPU result of those reads against it while we are here
-        agree = 0
-        for i in range(sample):
-            agree += int(best[i]["nPlaces"] > 0)
-        cpu["note"] = "seed ties resolved by std::sort in the oracle (literal) vs (dist,id) on the device"
 
     if world > 1:
         dist.destroy_process_group()

@@ -14,6 +14,7 @@
 // The result per (read, node) is the exact order-preserving integer key floor(d*2^31/N) (distinct rationals
 // with denominators < 2^13 differ by more than 2^-26, so keys order exactly like the reference's doubles);
 // a per-read radix select over (key, node id) returns the maxNSeed smallest in (dist, id) order.
+#include <stdlib.h>
 #include "hu_batch.cuh"
 
 namespace hu {
@@ -401,7 +402,9 @@ __global__ void __launch_bounds__(HU_LIT_THREADS) seedSortLiteralKernel(SeedArgs
 #pragma unroll
 				for (int u = 0; u < HU_LIT_UNROLL; ++u) {
 					const int t = (wd0 + u * nWarps) * 32 + lane;
-					vv[u] = t < cnt ? VKEY(base + t) : 0u;
+					const int pth = min(base + t, n - 1); // always in range: the load carries no branch and all of them overlap
+					const uint32_t raw = keys[pth];
+					vv[u] = pth == mS ? k0v : raw;
 				}
 #pragma unroll
 				for (int u = 0; u < HU_LIT_UNROLL; ++u) {
@@ -468,21 +471,37 @@ __global__ void __launch_bounds__(HU_LIT_THREADS) seedSortLiteralKernel(SeedArgs
 					const int t0 = p0 - base;
 					uint32_t k = preA[t0 >> 5] + __popc(faW[t0 >> 5] & ((1u << (t0 & 31)) - 1u)); // left stops before p0
 					int pb = -1;
-					for (int pp = p0; pp < p1; ++pp) {
-						const int t = pp - base;
-						if ((faW[t >> 5] >> (t & 31)) & 1u) {
-							if (pb < 0) pb = litSelect(fbW, preB, nW, totB - 1 - k);
-							else { // previous set bit of fb before pb
-								int wd = pb >> 5;
-								uint32_t bits = fbW[wd] & ((1u << (pb & 31)) - 1u);
-								while (!bits) bits = fbW[--wd];
-								pb = wd * 32 + 31 - __clz(bits);
+					for (int q0 = p0; q0 < p1; q0 += HU_LIT_UNROLL) {
+						// sources of a batch first (shared-memory walk), then all key loads, then all stores
+						int srcp[HU_LIT_UNROLL];
+#pragma unroll
+						for (int u = 0; u < HU_LIT_UNROLL; ++u) {
+							const int pp = q0 + u;
+							srcp[u] = pp;
+							if (pp < p1) {
+								const int t = pp - base;
+								if ((faW[t >> 5] >> (t & 31)) & 1u) {
+									if (pb < 0) pb = litSelect(fbW, preB, nW, totB - 1 - k);
+									else { // previous set bit of fb before pb
+										int wd = pb >> 5;
+										uint32_t bits = fbW[wd] & ((1u << (pb & 31)) - 1u);
+										while (!bits) bits = fbW[--wd];
+										pb = wd * 32 + 31 - __clz(bits);
+									}
+									srcp[u] = base + pb;
+									k++;
+								}
 							}
-							const int pq = base + pb;
-							w[pp] = ((lit_t) VKEY(pq) << 32) | (uint32_t) VPOS(pq);
-							k++;
-						} else
-							w[pp] = ((lit_t) VKEY(pp) << 32) | (uint32_t) VPOS(pp);
+						}
+						uint32_t kv[HU_LIT_UNROLL];
+#pragma unroll
+						for (int u = 0; u < HU_LIT_UNROLL; ++u) kv[u] = keys[min(srcp[u], n - 1)];
+#pragma unroll
+						for (int u = 0; u < HU_LIT_UNROLL; ++u)
+							if (q0 + u < p1) {
+								const int pq = srcp[u];
+								w[q0 + u] = ((lit_t) (pq == mS ? k0v : kv[u]) << 32) | (uint32_t) VPOS(pq);
+							}
 					}
 				}
 				if (tid == 0) {
@@ -550,7 +569,7 @@ __global__ void __launch_bounds__(HU_LIT_THREADS) seedSortLiteralKernel(SeedArgs
 #pragma unroll
 					for (int u = 0; u < HU_LIT_UNROLL; ++u) {
 						const int t = (wd0 + u * nWarps) * 32 + lane;
-						vv[u] = t < cnt ? LIT_KEY(w[base + t]) : 0u;
+						vv[u] = LIT_KEY(w[min(base + t, hi - 1)]); // always in range: branch-free, overlapping loads
 					}
 #pragma unroll
 					for (int u = 0; u < HU_LIT_UNROLL; ++u) {
@@ -723,7 +742,9 @@ int launchSeed(hu_batch* b, const hu_sep_params* p) {
 			HU_CUDA(cudaFuncSetAttribute(seedSortLiteralKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smemLit));
 			attrLit = smemLit;
 		}
-		const int grid = std::min(b->nReads, sms * 2);
+		static int litCtas = 0; // resident CTAs per SM: 2 fills the SM's shared memory; 1 leaves room for another stream's kernels
+		if (!litCtas) { const char* e = getenv("HU_LIT_CTAS_PER_SM"); litCtas = e ? std::max(1, std::min(2, atoi(e))) : 2; }
+		const int grid = std::min(b->nReads, sms * litCtas);
 		if (!b->litIds) {
 			void* q = NULL;
 			HU_CUDA(cudaMalloc(&q, (size_t) sms * 2 * t.scanPitch * sizeof(unsigned long long)));

@@ -1,0 +1,1 @@
+#include "mersenne_twister.hpp"
