@@ -136,7 +136,8 @@ istream& MSA::load(istream& in) {
 	// auxiliary index, counts and weights: present in the file, not used on the run path
 	const size_t skip = (size_t) 3 * numSeq * sizeof(int) + (size_t) 4 * csLen * sizeof(int) + (size_t) csLen * sizeof(int) +
 			(size_t) numSeq * sizeof(double) + (size_t) 4 * csLen * sizeof(double) + (size_t) csLen * sizeof(double);
-	in.ignore((streamsize) skip);
+	auxBlocks.resize(skip);
+	in.read(&auxBlocks[0], (streamsize) skip);
 	if (in.gcount() != (streamsize) skip) in.setstate(ios_base::badbit);
 	return in;
 }
@@ -149,6 +150,10 @@ ostream& MSA::save(ostream& out) const {
 	out.write((const char*) &isPruned, sizeof(bool));
 	for (unsigned i = 0; i < numSeq; ++i) saveString(seqNames[i], out);
 	saveString(concatMSA, out);
+	if (!auxBlocks.empty()) { // a loaded database: the builder's counts and sequence weights go back unchanged
+		out.write(auxBlocks.data(), (streamsize) auxBlocks.size());
+		return out;
+	}
 	vector<int> start(numSeq), end(numSeq), len(numSeq), res((size_t) 4 * csLen, 0), gap(csLen, 0);
 	for (unsigned i = 0; i < numSeq; ++i) {
 		int s = -1, e = -1, n = 0;
@@ -404,7 +409,7 @@ istream& operator>>(istream& in, BandedHMMP7& hmm) {
 static void hmmPrintValue(ostream& out, double v) { if (v == inf) out << "*"; else out << v; }
 
 ostream& operator<<(ostream& out, const BandedHMMP7& hmm) {
-	out << "HMMER3/f\t" << progVer[0] << "." << progVer[1] << "." << progVer[2] << endl;
+	out << "HMMER3/f\t" << progName << "-v" << progVer[0] << "." << progVer[1] << "." << progVer[2] << endl; // hmmVersion as hmmufotu-build sets it
 	out << "NAME\t" << hmm.name << endl;
 	out << "LENG\t" << hmm.K << endl;
 	out << "ALPH\tDNA" << endl;
@@ -539,15 +544,41 @@ istream& DNASubModel::read(istream& in) {
 	}
 	return in;
 }
-ostream& DNASubModel::write(ostream& out) const {
-	const streamsize oldPrec = out.precision();
-	out << setprecision(17);
+// Eigen's `m.format(IOFormat(FullPrecision))` as the reference's model writers use it: 15 significant digits
+// (std::numeric_limits<double>::digits10), every coefficient right-aligned to the widest one, ' ' between
+// columns and '\n' between rows; the stream's precision is restored afterwards (Eigen/src/Core/IO.h).
+static void writeEigenFull(ostream& out, const double* v, int rows, int cols) {
+	const streamsize oldPrec = out.precision(15);
+	size_t width = 0;
+	for (int i = 0; i < rows * cols; ++i) {
+		ostringstream ss;
+		ss.copyfmt(out);
+		ss << v[i];
+		width = max(width, ss.str().length());
+	}
+	for (int i = 0; i < rows; ++i) {
+		for (int j = 0; j < cols; ++j) {
+			if (j) out << " ";
+			out.width((streamsize) width);
+			out << v[i * cols + j];
+		}
+		if (i < rows - 1) out << "\n";
+	}
+	out.precision(oldPrec);
+}
+
+ostream& DNASubModel::write(ostream& out) const { // GTR.cpp:83-90, TN93.cpp:79-86, HKY85.cpp, F81.cpp, K80.cpp, JC69.cpp
 	out << "# DNA Substitution Model" << endl << "Type: " << modelType() << endl;
-	if (desc.type != HU_K80 && desc.type != HU_JC69) out << "pi: " << desc.pi[0] << " " << desc.pi[1] << " " << desc.pi[2] << " " << desc.pi[3] << endl;
+	if (desc.type != HU_K80 && desc.type != HU_JC69) {
+		out << "pi: ";
+		writeEigenFull(out, desc.pi, 1, 4);
+		out << endl;
+	}
 	if (desc.type == HU_GTR) {
 		out << "R:" << endl;
-		for (int i = 0; i < 4; ++i) out << desc.R[i * 4] << " " << desc.R[i * 4 + 1] << " " << desc.R[i * 4 + 2] << " " << desc.R[i * 4 + 3] << endl;
-		// Q is for human readers only (src/GTR.cpp:66-70): R * diag(pi), rows summing to 0, -trace = 1
+		writeEigenFull(out, desc.R, 4, 4);
+		out << endl;
+		// Q (src/GTR.cpp:124-135): R * diag(pi) off the diagonal, rows summing to 0, scaled so that -trace = 1
 		double Q[16], tr = 0;
 		for (int i = 0; i < 4; ++i) {
 			double rs = 0;
@@ -555,13 +586,18 @@ ostream& DNASubModel::write(ostream& out) const {
 			Q[i * 4 + i] = -rs;
 			tr += Q[i * 4 + i];
 		}
+		for (int i = 0; i < 16; ++i) Q[i] /= -tr;
 		out << "Q:" << endl;
-		for (int i = 0; i < 4; ++i) out << Q[i * 4] / -tr << " " << Q[i * 4 + 1] / -tr << " " << Q[i * 4 + 2] / -tr << " " << Q[i * 4 + 3] / -tr << endl;
-	} else if (desc.type == HU_TN93) out << "kr: " << desc.kr << " ky: " << desc.ky << " beta: " << desc.beta << endl;
-	else if (desc.type == HU_HKY85) out << "kappa: " << desc.kappa << " beta: " << desc.beta << endl;
-	else if (desc.type == HU_F81) out << "beta: " << desc.beta << endl;
-	else if (desc.type == HU_K80) out << "kappa: " << desc.kappa << endl;
-	out << setprecision((int) oldPrec);
+		writeEigenFull(out, Q, 4, 4);
+		out << endl;
+	} else {
+		// the scalar parameters go through std::setprecision(DBL_DIG), which the reference leaves set on the stream
+		out << setprecision(15);
+		if (desc.type == HU_TN93) out << "kr: " << desc.kr << " ky: " << desc.ky << " beta: " << desc.beta << endl;
+		else if (desc.type == HU_HKY85) out << "kappa: " << desc.kappa << " beta: " << desc.beta << endl;
+		else if (desc.type == HU_F81) out << "beta: " << desc.beta << endl;
+		else if (desc.type == HU_K80) out << "kappa: " << desc.kappa << endl;
+	}
 	return out;
 }
 istream& operator>>(istream& in, DNASubModel& m) { return m.read(in); }
@@ -595,7 +631,7 @@ istream& PTUnrooted::load(istream& in) {
 	if (!in || nNodes < 2 || nNodes > ((size_t) 1 << 30) || csLen < 1 || csLen > 65535) { in.setstate(ios_base::badbit); return in; }
 	parent.assign(nNodes, -1);
 	blen.assign(nNodes, 0.0); height.assign(nNodes, 0.0); annoDist.assign(nNodes, 0.0);
-	name.resize(nNodes); anno.resize(nNodes); neighbors.assign(nNodes, vector<long>());
+	name.resize(nNodes); anno.resize(nNodes); seqName.resize(nNodes); neighbors.assign(nNodes, vector<long>());
 	seq.assign(nNodes * (size_t) csLen, -2);
 	for (size_t i = 0; i < nNodes; ++i) { // PTUNode::load, cpp:99-114
 		long id;
@@ -606,8 +642,8 @@ istream& PTUnrooted::load(istream& in) {
 		in.read((char*) &hasAbc, sizeof(bool));
 		string tmp, codes;
 		if (hasAbc) loadString(tmp, in);
-		loadString(tmp, in);   // DigitalSeq name
-		loadString(codes, in); // int8 codes
+		loadString(seqName[id], in); // DigitalSeq name
+		loadString(codes, in);       // int8 codes
 		if (!codes.empty()) {
 			if (codes.size() != (size_t) csLen) { in.setstate(ios_base::badbit); return in; }
 			memcpy(&seq[(size_t) id * csLen], codes.data(), csLen);
@@ -696,10 +732,9 @@ ostream& PTUnrooted::save(ostream& out) const {
 		const long id = (long) i;
 		out.write((const char*) &id, sizeof(long));
 		saveString(name[i], out);
-		const bool hasAbc = true;
+		const bool hasAbc = false; // PTUNode::save -> DigitalSeq::save(out) with withAbc = false (src/DigitalSeq.h)
 		out.write((const char*) &hasAbc, sizeof(bool));
-		saveString("DNA", out);
-		saveString(name[i], out);
+		saveString(i < seqName.size() ? seqName[i] : string(), out);
 		saveString(string((const char*) &seq[i * (size_t) csLen], csLen), out);
 		saveString(anno[i], out);
 		out.write((const char*) &annoDist[i], sizeof(double));

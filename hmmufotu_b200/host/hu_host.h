@@ -71,6 +71,7 @@ struct MSA {                                       // src/MSA.{h,cpp}: only what
 	bool isPruned;
 	std::vector<std::string> seqNames;
 	std::string concatMSA;                         // numSeq * csLen chars, row-major
+	std::string auxBlocks;                         // start/end/len, counts and weights exactly as loaded (written back by save)
 	std::istream& load(std::istream& in);          // src/MSA.cpp:362-430 (whole record is parsed)
 	std::ostream& save(std::ostream& out) const;   // src/MSA.cpp:295-360 (count / weight blocks recomputed plainly)
 	unsigned getCSLen() const { return csLen; }
@@ -201,6 +202,7 @@ public:
 	std::vector<int32_t> parent;
 	std::vector<double> blen, height, annoDist;
 	std::vector<std::string> name, anno;
+	std::vector<std::string> seqName;              // DigitalSeq name of a node (the MSA row id for leaves, empty otherwise)
 	std::vector<int8_t> seq;                       // numNodes x csLen
 	std::vector<int32_t> taxon;                    // id of the annotation string (equal strings share an id)
 	std::vector<double> up, dn;                    // [node][col][4]

@@ -44,7 +44,7 @@ static int csfmTest() {
 }
 
 int main(int argc, char** argv) {
-	if (argc < 2) { cerr << "usage: hu_host_test csfm | hmm IN OUT | ptu IN OUT | msa IN OUT | seeds DB FASTA SEED" << endl; return 2; }
+	if (argc < 2) { cerr << "usage: hu_host_test csfm | hmm IN OUT | ptu IN OUT | msa IN OUT | seeds DB FASTA SEED [MATE-FASTA]" << endl; return 2; }
 	const string cmd = argv[1];
 	if (cmd == "csfm") return csfmTest();
 	if (cmd == "hmm" && argc == 4) {
@@ -85,7 +85,7 @@ int main(int argc, char** argv) {
 		cout << "numSeq " << msa.numSeq << " csLen " << msa.csLen << endl;
 		return out.good() ? 0 : 1;
 	}
-	if (cmd == "seeds" && argc == 5) {
+	if (cmd == "seeds" && (argc == 5 || argc == 6)) { // seeds DB FASTA SEED [MATE-FASTA]: rand() is drawn pair by pair, forward read first
 		const string db = argv[2];
 		ifstream msaIn((db + ".msa").c_str(), ios_base::binary), hmmIn((db + ".hmm").c_str());
 		if (loadProgInfo(msaIn).bad()) return 1;
@@ -99,13 +99,19 @@ int main(int argc, char** argv) {
 		srand((unsigned) atoi(argv[4]));
 		ifstream fa(argv[3]);
 		SeqIO io(&fa, SeqIO::guessFormat(argv[3]));
-		while (io.hasNext()) {
-			const PrimarySeq r = io.nextSeq();
-			const vector<BandedHMMP7::ViterbiAlignPath> v = findSeeds(hmm, csfm, r, 20, 50, BandedHMMP7::GLOBAL);
-			cout << r.getId() << "\t" << v.size();
-			for (size_t i = 0; i < v.size(); ++i)
-				cout << "\t" << v[i].start << "," << v[i].end << "," << v[i].from << "," << v[i].to << "," << v[i].nIns << "," << v[i].nDel;
-			cout << endl;
+		ifstream mfa;
+		if (argc == 6) mfa.open(argv[5]);
+		SeqIO mio(&mfa, SeqIO::guessFormat(argc == 6 ? argv[5] : argv[3]));
+		while (io.hasNext() && (argc == 5 || mio.hasNext())) {
+			vector<PrimarySeq> rs(1, io.nextSeq());
+			if (argc == 6) rs.push_back(mio.nextSeq().revcom()); // src/hmmufotu.cpp:609
+			for (size_t q = 0; q < rs.size(); ++q) {
+				const vector<BandedHMMP7::ViterbiAlignPath> v = findSeeds(hmm, csfm, rs[q], 20, 50, BandedHMMP7::GLOBAL);
+				cout << rs[q].getId() << "\t" << v.size();
+				for (size_t i = 0; i < v.size(); ++i)
+					cout << "\t" << v[i].start << "," << v[i].end << "," << v[i].from << "," << v[i].to << "," << v[i].nIns << "," << v[i].nDel;
+				cout << endl;
+			}
 		}
 		return 0;
 	}

@@ -1,0 +1,59 @@
+#!/usr/bin/env python
+"""Golden vectors from the REFERENCE ITSELF (oracle/_ref: HmmUFOtu v1.5.1 compiled in place from /root/reference/src
+against the stand-in Eigen/Boost headers of oracle/shim, see oracle/Makefile.ref).
+
+    python tests/golden/make_ref_golden.py          # needs /root/reference and a built oracle/_ref
+
+Writes tests/golden/ref70/:
+  gg_70_otus_<MODEL>.{msa,csfm,hmm,ptu.gz}   database built by the reference's hmmufotu-build from its own test inputs
+                                              (test/70_otus.fasta + .tree + taxonomy: BASELINE.json configs[0])
+  se<k>.fasta, se<k>.tsv                      reads drawn by the reference's hmmufotu-sim and the assignment TSV of
+                                              the reference's hmmufotu (-s 1 -S <k> -p 1)
+  pe<k>_{1,2}.fasta, pe<k>.tsv                the same for paired-end reads
+Every file holds at most 64 reads: up to 64 OpenMP tasks are deferred and then run in creation order, so the
+reference consumes rand() (CSFM seed picks) in file order, as the batched driver does.
+"""
+import gzip
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = os.path.join(ROOT, "oracle", "_ref")
+SRC = "/root/reference/test"
+OUT = os.path.join(HERE, "ref70")
+
+
+def run(*cmd, **kw):
+    print("+", " ".join(cmd), file=sys.stderr)
+    subprocess.run(cmd, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, **kw)
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "-f", "Makefile.ref", "-j8", "-s"])
+    os.chdir(OUT)
+    for model, extra in (("GTR", []), ("HKY85", ["-V", "-k", "4"])):
+        db = "gg_70_otus_" + model + ("_dG" if extra else "")
+        run(os.path.join(REF, "hmmufotu-build"), os.path.join(SRC, "70_otus.fasta"), os.path.join(SRC, "70_otus.tree"),
+            "-a", os.path.join(SRC, "70_otus_taxonomy.txt"), "-n", db, "-s", model, *extra)
+        with open(db + ".ptu", "rb") as f, gzip.GzipFile(db + ".ptu.gz", "wb", compresslevel=9, mtime=0) as g:
+            shutil.copyfileobj(f, g)
+        n_files = 4 if model == "GTR" else 1
+        for k in range(n_files):
+            tag = "%s_se%d" % (db, k)
+            args = ["-r", "250"] if k % 2 == 0 else []
+            run(os.path.join(REF, "hmmufotu-sim"), db, tag + ".fasta", "-N", "64", "-S", str(k), *args)
+            run(os.path.join(REF, "hmmufotu"), db, tag + ".fasta", "-o", tag + ".tsv", "-s", "1", "-S", str(k), "-p", "1")
+        tag = "%s_pe0" % db
+        run(os.path.join(REF, "hmmufotu-sim"), db, tag + "_1.fasta", tag + "_2.fasta", "-N", "64", "-S", "7", "-r", "150")
+        run(os.path.join(REF, "hmmufotu"), db, tag + "_1.fasta", tag + "_2.fasta", "-o", tag + ".tsv", "-s", "1", "-S", "7", "-p", "1")
+        os.remove(db + ".ptu")
+    for f in sorted(os.listdir(OUT)):
+        print("%10d  %s" % (os.path.getsize(f), f))
+
+
+if __name__ == "__main__":
+    main()
