@@ -1,0 +1,59 @@
+"""The product path against the REFERENCE ITSELF on a GPU: the hmmufotu command line of this repository (C++ host
+layer over the C ABI, all arithmetic on the device) is run on the databases the reference's hmmufotu-build wrote
+and on the reads the reference's hmmufotu assigned (tests/golden/ref70, see tests/golden/make_ref_golden.py); the
+assignment TSV must be the reference's, line for line."""
+import gzip
+import os
+import shutil
+import subprocess
+
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+GOLD = os.path.join(HERE, "golden", "ref70")
+CLI = os.path.join(ROOT, "hmmufotu_b200", "bin", "hmmufotu")
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", params=["gg_70_otus_GTR", "gg_70_otus_HKY85_dG"])
+def refdb_dir(request, tmp_path_factory):
+    name = request.param
+    d = tmp_path_factory.mktemp(name)
+    for ext in (".msa", ".hmm", ".csfm"):
+        shutil.copy(os.path.join(GOLD, name + ext), d / (name + ext))
+    with gzip.open(os.path.join(GOLD, name + ".ptu.gz"), "rb") as f, open(d / (name + ".ptu"), "wb") as g:
+        shutil.copyfileobj(f, g)
+    return name, str(d)
+
+
+def data_lines(path):
+    return [ln.rstrip("\n") for ln in open(path) if not ln.startswith("#")]
+
+
+def run_case(name, d, tag, seed, paired):
+    reads = [os.path.join(GOLD, "%s_%s_%d.fasta" % (name, tag, m)) for m in (1, 2)] if paired else [os.path.join(GOLD, "%s_%s.fasta" % (name, tag))]
+    out = os.path.join(d, tag + ".tsv")
+    p = subprocess.run([CLI, os.path.join(d, name)] + reads + ["-o", out, "-s", "1", "-S", str(seed), "--batch", "64"], capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr[-2000:]
+    got, want = data_lines(out), data_lines(os.path.join(GOLD, "%s_%s.tsv" % (name, tag)))
+    assert got[0] == want[0]                      # column header
+    assert len(got) == len(want) == 65
+    bad = [(g.split("\t")[0], i) for i, (g, w) in enumerate(zip(got, want)) if g != w]
+    return got, want, bad
+
+
+def test_single_end_tsv_is_the_references(refdb_dir):
+    name, d = refdb_dir
+    for k in range(4):
+        if not os.path.exists(os.path.join(GOLD, "%s_se%d.fasta" % (name, k))):
+            continue
+        got, want, bad = run_case(name, d, "se%d" % k, k, False)
+        assert not bad, "rows differ from the reference's TSV: %s\n%s\n%s" % (bad[:5], got[bad[0][1]][-300:], want[bad[0][1]][-300:])
+
+
+def test_paired_end_tsv_is_the_references(refdb_dir):
+    name, d = refdb_dir
+    got, want, bad = run_case(name, d, "pe0", 7, True)
+    assert not bad, "rows differ from the reference's TSV: %s\n%s\n%s" % (bad[:5], got[bad[0][1]][-300:], want[bad[0][1]][-300:])
