@@ -533,9 +533,8 @@ def write_ptu(db: SynthDB, up: np.ndarray, dn: np.ndarray, path: str, anno=None)
         for x in range(n):
             f.write(struct.pack("<q", x))
             _wstr(f, "node%d" % x)
-            f.write(struct.pack("<?", True))
-            _wstr(f, "DNA")
-            _wstr(f, "node%d" % x)
+            f.write(struct.pack("<?", False))   # PTUNode::save writes the DigitalSeq without its alphabet
+            _wstr(f, "node%d" % x)              # DigitalSeq name (the MSA row id in a real database)
             _wstr(f, db.seq[x].astype(np.int8).tobytes())
             _wstr(f, anno[x])
             f.write(struct.pack("<d", 0.0))

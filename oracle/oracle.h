@@ -6,13 +6,15 @@
  * called by the product (hmmufotu_b200/); only tests/, __graft_entry__.smoke()
  * and bench.py's cpu_baseline / --impl reference leg may load it.
  *
- * PARITY UNPINNED: the reference cannot be compiled in this image (Eigen3 and
- * Boost are absent) and its own tests hold no numeric golden vectors for this
- * path.  The restatement follows the reference
- * source line by line (citations below are relative to /root/reference/) and is
- * cross-checked by independent properties (tests/test_oracle_*.py): banded ==
- * full Viterbi when the band covers the optimum, P(t) vs scipy.linalg.expm,
- * detailed balance, Felsenstein pruning vs brute-force enumeration on tiny trees.
+ * PARITY PINNED AGAINST THE REFERENCE ITSELF: the reference's own sources compile in place
+ * (from /root/reference/src, nothing copied) against the stand-in Eigen/Boost headers in
+ * oracle/shim/ (recipe: oracle/Makefile.ref -> oracle/_ref/{hmmufotu,hmmufotu-build,hmmufotu-sim}).
+ * tests/golden/ref70/ holds databases written by that hmmufotu-build and assignment TSVs written by
+ * that hmmufotu (tests/golden/make_ref_golden.py); tests/test_ref_pin.py recomputes every TSV
+ * column with this restatement from the same files: all 448 rows are identical.  The reference's
+ * own tests hold no numeric golden vectors for this path, so these are the pins,
+ * next to the independent properties in tests/test_oracle.py (P(t) vs scipy.linalg.expm, detailed
+ * balance, Felsenstein pruning vs brute force, banded == full Viterbi).
  *
  * Floating-point conventions chosen where Eigen's evaluation order is not
  * visible from the reference source (documented, not verifiable here):

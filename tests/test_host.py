@@ -54,9 +54,15 @@ def test_ptu_and_msa_roundtrip_bytes(exes, dbfiles):
         else:  # the substitution model is text: digits may be printed differently, everything else is binary
             cut = a.index(b"GTR\n# DNA")
             assert a[:cut] == b[:cut]
+            # the model text carries 15 significant digits (Eigen's FullPrecision print, as the reference writes it) and
+            # the human-only Q block is recomputed from what was read: save(load(x)) is a fixed point from the second
+            # generation on, and everything before the model text from the first
             dst2 = os.path.join(dbfiles["dir"], "copy2." + kind)
+            dst3 = os.path.join(dbfiles["dir"], "copy3." + kind)
             assert subprocess.run([exes[1], kind, dst, dst2]).returncode == 0
-            assert b == open(dst2, "rb").read()      # save(load(x)) is a fixed point
+            assert subprocess.run([exes[1], kind, dst2, dst3]).returncode == 0
+            c2 = open(dst2, "rb").read()
+            assert b[:cut] == c2[:cut] and c2 == open(dst3, "rb").read()
             assert "nodes %d csLen %d root 0 model GTR dG 4" % (dbfiles["db"].n_nodes, dbfiles["db"].cs_len) in out.stdout
 
 
