@@ -522,6 +522,11 @@ static int createImpl(hu_db* db, const hu_hmm_params* hp, const hu_tree_desc* td
 		HU_TRY(upload(db, &t.posOfSlot, posOfSlot.data(), posOfSlot.size()));
 		HU_TRY(upload(db, &t.nodeOfPos, nodeOfPos.data(), nodeOfPos.size()));
 	}
+	{
+		std::vector<double> inv(65536, 0.0);
+		for (int i = 1; i < 65536; ++i) inv[i] = ldexp(1.0 / (double) i, 31); // scaling by 2^31 is exact
+		HU_TRY(upload(db, &t.inv2N, inv.data(), inv.size()));
+	}
 	uint32_t* planes;
 	t.nPWords = (K + 31) / 32;
 	HU_TRY(devAlloc(db, &planes, (size_t) t.nPWords * 3 * t.scanPitch));

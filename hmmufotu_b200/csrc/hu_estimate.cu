@@ -93,7 +93,9 @@ __global__ void __launch_bounds__(256) estPlanKernel(EstArgs a, TreeDev t, Model
 		if (isnan(ratio)) ratio = 0.5;
 		const double wur = it.w0 * ratio, wvr = it.w0 - wur;
 		EstItemP& ip = a.itemsP[i];
-		modelPrHalfWarp(m, lane < 16 ? wur : wvr, ip.P[lane >> 4], lane & 15, 0xffffffffu);
+		modelPrHalfWarp(m, lane < 16 ? wur : wvr, ip.P[lane >> 4][0], lane & 15, 0xffffffffu);
+		__syncwarp();
+		ip.P[lane >> 4][1][lane & 15] = ip.P[lane >> 4][0][(lane & 15) ^ 2]; // entry (i, j) <- (i, j ^ 2)
 		if (lane == 0) {
 			ip.cDist = cDist; ip.ratio = ratio;
 			if (it.kind == 2) a.wideList[atomicAdd(a.wideCount, 1)] = i;
@@ -116,14 +118,15 @@ struct EstSmem {
 	unsigned long long full[HU_EST_STAGES], empty[HU_EST_STAGES], hfull[2], hempty[2];
 };
 
-// one message column out of a ring stage: two 128-bit reads whose halves are swapped for every other group of
-// four threads, so that a quarter-warp covers all 32 banks
+// one message column out of a ring stage: two 128-bit reads; every other group of four threads reads the halves
+// in the opposite order so that a quarter-warp covers all 32 banks.  Those threads get (v2, v3, v0, v1) and
+// multiply by the matrix whose column pairs are exchanged the same way: the same products, summed as
+// (p2 + p3) + (p0 + p1) instead of (p0 + p1) + (p2 + p3) -- identical bits, no selects.
 __device__ __forceinline__ void ldsColumn(const double* __restrict__ chunk, int tid, double* v) {
 	const int sw = (tid >> 2) & 1;
 	const double2 a = *reinterpret_cast<const double2*>(chunk + 4 * tid + 2 * sw);
 	const double2 b = *reinterpret_cast<const double2*>(chunk + 4 * tid + 2 * (1 - sw));
-	v[0] = sw ? b.x : a.x; v[1] = sw ? b.y : a.y;
-	v[2] = sw ? a.x : b.x; v[3] = sw ? a.y : b.y;
+	v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
 }
 
 __global__ void __launch_bounds__(HU_EST_THREADS, 2) estimateStagedKernel(EstArgs a, TreeDev t, Model m) {
@@ -203,8 +206,9 @@ __global__ void __launch_bounds__(HU_EST_THREADS, 2) estimateStagedKernel(EstArg
 		if (it.kind == 0) break;
 		const int W = it.W;
 		const int8_t* x = sm.hdr[h] + sm.hoff[h];
-		const double* P0 = sm.rec[h].P[0];
-		const double* P1 = sm.rec[h].P[1];
+		const int sw = (tid >> 2) & 1;
+		const double* P0 = sm.rec[h].P[0][sw];
+		const double* P1 = sm.rec[h].P[1][sw];
 		// the window sums of the scales ride along in the log-likelihood accumulators of two warps
 		double ll = 0;
 		if (warp == 2) ll = windowScale(t.upS, t.upP32, it.u, t.csLen, t.nWords, it.start, it.start + W - 1, lane);
@@ -218,7 +222,7 @@ __global__ void __launch_bounds__(HU_EST_THREADS, 2) estimateStagedKernel(EstArg
 				double eu[4], ev[4], ya[4], yb[4], g[4];
 				ldsColumn(sm.ring[st][0], tid, eu);
 				ldsColumn(sm.ring[st][1], tid, ev);
-				matVec4(P0, eu, ya);
+				matVec4(P0, eu, ya); // rows are not permuted: ya, yb and g are in state order for every thread
 				matVec4(P1, ev, yb);
 				for (int k = 0; k < 4; ++k) { g[k] = ya[k] * yb[k]; sm.g[k][c] = g[k]; }
 				const int b = x[c];
@@ -247,13 +251,18 @@ __global__ void __launch_bounds__(HU_EST_THREADS, 2) estimateStagedKernel(EstArg
 		}
 		consumerSync(HU_EST_CONS);
 		// ---- pass 2: treeLoglik(pi, UPr + VPr + NPr) ----
+		// sum of logs as the log of a running product: one log per thread instead of one per column (the product of
+		// the <= 6 factors of a thread is flushed long before it could underflow)
+		double prod = 1.0;
 		for (int c = tid; c < W; c += HU_EST_CONS) {
 			const int b = x[c];
 			const double* np = sm.Np[b >= 0 ? b : 4];
 			double z[4];
 			for (int k = 0; k < 4; ++k) z[k] = sm.g[k][c] * np[k];
-			ll += log(dotPi(m, z));
+			prod *= dotPi(m, z);
+			if (prod < 1e-150) { ll += log(prod); prod = 1.0; }
 		}
+		ll += log(prod);
 		for (int o = 16; o > 0; o >>= 1) ll += __shfl_xor_sync(0xffffffffu, ll, o);
 		if (lane == 0) sm.redC[warp] = ll;
 		consumerSync(HU_EST_CONS);

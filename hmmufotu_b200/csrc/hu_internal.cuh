@@ -225,6 +225,7 @@ struct TreeDev {
 	const int* nodeOfPos;    // position -> node id, padded to scanPitch with 0x7fffffff
 	int nCand;               // number of candidates (nNodes - 1)
 	int nGapSlots;           // slots [0, nGapSlots) hold nodes whose sequence has gaps (need the valid plane)
+	const double* inv2N;     // [65536]: 2^31 / N correctly rounded (seed keys without a division), inv2N[0] = 0
 };
 
 #ifdef __CUDACC__

@@ -33,7 +33,7 @@ __device__ __forceinline__ void mbarWait(unsigned long long* bar, uint32_t parit
 }
 // the producer lane's wait: backs off between probes so that its spinning does not take issue slots from the consumers
 __device__ __forceinline__ void mbarWaitRelaxed(unsigned long long* bar, uint32_t parity) {
-	while (!mbarTryWait(bar, parity)) __nanosleep(100);
+	while (!mbarTryWait(bar, parity)) __nanosleep(400);
 }
 
 // global -> shared bulk copy; src, dst 16-byte aligned, bytes a multiple of 16; completes `bytes` on `bar`

@@ -75,18 +75,31 @@ __global__ void sparseListKernel(SeedArgs a, int L, const int* __restrict__ colK
 	if (lane == 0) a.nSparse[r] = n <= a.sparseCap ? n : -1;
 }
 
-__device__ __forceinline__ uint32_t makeKey(int d, int N, bool excluded) {
-	if (excluded || N <= 0) return 0xFFFFFFFFu; // 0/0: the reference's NaN distance; such nodes sort last here
-	return (uint32_t) __double2ll_rd(__ddiv_rn((double) d * 2147483648.0, (double) N));
+// Seed key floor(d * 2^31 / N) for 0 <= d <= N < 2^16, exactly and without a division or 64-bit integer
+// arithmetic: inv2N[N] is 2^31 / N correctly rounded, so d * inv2N[N] is within 2^-21 of the quotient.  A quotient
+// that is not an integer has a fractional part in [1/N, 1 - 1/N], far from both ends, and an integer quotient
+// is lifted over the rounding error by the 2^-20 bias: the floor of the biased product is the exact key
+// (checked on the host for every d <= N < 3000 and sampled N up to 65535, tests/test_abi.py).
+#define HU_KEY_BIAS 9.5367431640625e-07 // 2^-20
+__device__ __forceinline__ uint32_t makeKey(int d, int N, bool excluded, const double* __restrict__ inv2N) {
+	const double q = __dadd_rn(__dmul_rn((double) d, __ldg(inv2N + N)), HU_KEY_BIAS);
+	return (excluded || N <= 0) ? 0xFFFFFFFFu : __double2uint_rd(q); // 0/0: the reference's NaN distance; such nodes sort last here
 }
 
 template <bool GAP>
 __global__ void __launch_bounds__(128) seedScanKernel(SeedArgs a, TreeDev t, int tile0) {
 	extern __shared__ uint4 sR[]; // [word - gLo][8]
 	__shared__ int sLo, sHi;
+	__shared__ int sNs[HU_SCAN_READS], sNv[HU_SCAN_READS]; // per read: # sparse bases (-2: no such read), # valid bases
 	const int g = blockIdx.x;             // read group
 	const int tile = tile0 + blockIdx.y;  // slot tile
 	const int r0 = g * HU_SCAN_READS;
+	if (threadIdx.x >= 32 && threadIdx.x < 32 + HU_SCAN_READS) {
+		const int rr = r0 + (int) threadIdx.x - 32;
+		const bool ok = rr < a.nReads && a.winStart[rr] >= 0;
+		sNs[threadIdx.x - 32] = ok ? a.nSparse[rr] : -2;
+		sNv[threadIdx.x - 32] = ok ? a.rValid[rr] : 0;
+	}
 	if (threadIdx.x == 0) {
 		int lo = 0x7fffffff, hi = -1;
 		for (int r = r0; r < r0 + HU_SCAN_READS; ++r)
@@ -141,12 +154,12 @@ __global__ void __launch_bounds__(128) seedScanKernel(SeedArgs a, TreeDev t, int
 #pragma unroll
 	for (int r = 0; r < HU_SCAN_READS; ++r) {
 		const int rr = r0 + r;
-		if (rr >= a.nReads || a.winStart[rr] < 0) continue;
+		const int ns = sNs[r];
+		if (ns == -2) continue; // uniform over the CTA
 		int dd[4], nn[4];
 #pragma unroll
-		for (int s = 0; s < 4; ++s) { dd[s] = d[r][s]; nn[s] = GAP ? n[r][s] : a.rValid[rr]; }
+		for (int s = 0; s < 4; ++s) { dd[s] = d[r][s]; nn[s] = GAP ? n[r][s] : sNv[r]; }
 		// insert bases of the read in non-match columns
-		const int ns = a.nSparse[rr];
 		const uint32_t* sp = a.sparse + (size_t) rr * a.sparseCap;
 		for (int i = 0; i < ns; ++i) {
 			const uint32_t e = __ldg(sp + i);
@@ -160,8 +173,10 @@ __global__ void __launch_bounds__(128) seedScanKernel(SeedArgs a, TreeDev t, int
 		// the key vector of a read is in getSeed's candidate order (node id), not in slot order
 		uint32_t* krow = a.keys + (size_t) rr * pitch;
 #pragma unroll
-		for (int s = 0; s < 4; ++s)
-			if (pos[s] >= 0) krow[pos[s]] = makeKey(dd[s], nn[s], excl[s] || ns < 0);
+		for (int s = 0; s < 4; ++s) {
+			const uint32_t key = makeKey(dd[s], nn[s], excl[s] || ns < 0, t.inv2N);
+			if (pos[s] >= 0) krow[pos[s]] = key;
+		}
 	}
 }
 
@@ -311,6 +326,19 @@ __global__ void __launch_bounds__(HU_SEL_THREADS) seedSelectKernel(SeedArgs a, i
 typedef unsigned long long lit_t;               // (key << 32) | candidate position; only the key is compared
 #define LIT_KEY(v) ((uint32_t) ((v) >> 32))
 
+// loads the compiler may not sink towards their first use: the flag passes issue a batch of these back to back, so
+// that HU_LIT_UNROLL requests per lane are in flight (plain loads were re-serialised into load / use pairs)
+__device__ __forceinline__ uint32_t ldKeyNow(const uint32_t* p) {
+	uint32_t v;
+	asm volatile("ld.global.u32 %0, [%1];" : "=r"(v) : "l"(p));
+	return v;
+}
+__device__ __forceinline__ uint32_t ldPairKeyNow(const unsigned long long* p) { // high word of a (key, position) pair
+	uint32_t v;
+	asm volatile("ld.global.u32 %0, [%1+4];" : "=r"(v) : "l"(p));
+	return v;
+}
+
 template <typename Arr>
 __device__ __forceinline__ void litSwap(Arr& w, int x, int y) { const lit_t t = w[x]; w[x] = w[y]; w[y] = t; }
 template <typename Arr>
@@ -402,10 +430,11 @@ __global__ void __launch_bounds__(HU_LIT_THREADS) seedSortLiteralKernel(SeedArgs
 #pragma unroll
 				for (int u = 0; u < HU_LIT_UNROLL; ++u) {
 					const int t = (wd0 + u * nWarps) * 32 + lane;
-					const int pth = min(base + t, n - 1); // always in range: the load carries no branch and all of them overlap
-					const uint32_t raw = keys[pth];
-					vv[u] = pth == mS ? k0v : raw;
+					vv[u] = ldKeyNow(keys + min(base + t, n - 1)); // always in range: no branch, all of them overlap
 				}
+#pragma unroll
+				for (int u = 0; u < HU_LIT_UNROLL; ++u)
+					if (min(base + (wd0 + u * nWarps) * 32 + lane, n - 1) == mS) vv[u] = k0v;
 #pragma unroll
 				for (int u = 0; u < HU_LIT_UNROLL; ++u) {
 					const int wd = wd0 + u * nWarps;
@@ -569,7 +598,7 @@ __global__ void __launch_bounds__(HU_LIT_THREADS) seedSortLiteralKernel(SeedArgs
 #pragma unroll
 					for (int u = 0; u < HU_LIT_UNROLL; ++u) {
 						const int t = (wd0 + u * nWarps) * 32 + lane;
-						vv[u] = LIT_KEY(w[min(base + t, hi - 1)]); // always in range: branch-free, overlapping loads
+						vv[u] = ldPairKeyNow(w + min(base + t, hi - 1)); // always in range: branch-free, overlapping loads
 					}
 #pragma unroll
 					for (int u = 0; u < HU_LIT_UNROLL; ++u) {

@@ -86,3 +86,18 @@ def test_no_cpu_fallback(lib):
     with pytest.raises(_lib.HuError) as e:
         engine.Database(db)
     assert "no CPU fallback" in str(e.value)
+
+
+def test_seed_key_formula_is_exact():
+    """hu_seed.cu makeKey(): floor(d * inv2N[N] + 2^-20) with inv2N = 2^31 / N correctly rounded is floor(d * 2^31 / N)."""
+    rng = np.random.default_rng(3)
+    Ns = list(range(1, 700)) + [int(x) for x in rng.integers(700, 65536, 400)]
+    for N in Ns:
+        inv2 = np.ldexp(np.float64(1.0) / np.float64(N), 31)
+        m = N
+        while m % 2 == 0:
+            m //= 2
+        ds = np.unique(np.concatenate([np.arange(0, N + 1) if N < 700 else rng.integers(0, N + 1, 64), np.arange(0, N + 1, m), [0, 1, N - 1, N]])).astype(np.int64)
+        got = np.floor(ds.astype(np.float64) * inv2 + np.float64(2.0 ** -20)).astype(np.int64)
+        want = (ds << 31) // N
+        assert (got == want).all(), N
