@@ -589,9 +589,23 @@ __global__ void __launch_bounds__(HU_LIT_THREADS) seedSortLiteralKernel(SeedArgs
 					__syncthreads();
 					continue;
 				}
-				if (tid == 0) litMedianToFirst(w, lo, lo + 1, lo + (hi - lo) / 2, hi - 1);
-				__syncthreads();
-				const uint32_t pv = LIT_KEY(w[lo]);
+				// __move_median_to_first(lo, lo+1, mid, hi-1): every thread reads the three candidates and w[lo] itself
+				// (no hand-over through one thread and a barrier); the exchange of w[lo] and w[mS] is applied to the
+				// flag pass virtually and written by thread 0 on the side, well before the swap phase reads it
+				int mS;
+				uint32_t pv, k0v;
+				lit_t wmKeep, w0Keep;
+				{
+					const int ia = lo + 1, ib = lo + (hi - lo) / 2, ic = hi - 1;
+					const lit_t wa = w[ia], wb = w[ib], wc = w[ic], w0 = w[lo];
+					const uint32_t qa = LIT_KEY(wa), qb = LIT_KEY(wb), qc = LIT_KEY(wc);
+					if (qa < qb) mS = qb < qc ? ib : (qa < qc ? ic : ia);
+					else mS = qa < qc ? ia : (qb < qc ? ic : ib);
+					const lit_t wm = mS == ia ? wa : (mS == ib ? wb : wc);
+					pv = LIT_KEY(wm);
+					k0v = LIT_KEY(w0);
+					wmKeep = wm; w0Keep = w0;
+				}
 				const int base = lo + 1, cnt = hi - base, nW = (cnt + 31) / 32;
 				for (int wd0 = warp; wd0 < nW; wd0 += nWarps * HU_LIT_UNROLL) {
 					uint32_t vv[HU_LIT_UNROLL];
@@ -600,6 +614,9 @@ __global__ void __launch_bounds__(HU_LIT_THREADS) seedSortLiteralKernel(SeedArgs
 						const int t = (wd0 + u * nWarps) * 32 + lane;
 						vv[u] = ldPairKeyNow(w + min(base + t, hi - 1)); // always in range: branch-free, overlapping loads
 					}
+#pragma unroll
+					for (int u = 0; u < HU_LIT_UNROLL; ++u)
+						if (base + (wd0 + u * nWarps) * 32 + lane == mS) vv[u] = k0v;
 #pragma unroll
 					for (int u = 0; u < HU_LIT_UNROLL; ++u) {
 						const int wd = wd0 + u * nWarps;
@@ -612,6 +629,7 @@ __global__ void __launch_bounds__(HU_LIT_THREADS) seedSortLiteralKernel(SeedArgs
 					}
 				}
 				__syncthreads();
+				if (tid == 0) { w[lo] = wmKeep; w[mS] = w0Keep; } // every thread has read the four elements by now
 				// exclusive prefix counts per word
 				const int seg = (nW + HU_LIT_THREADS - 1) / HU_LIT_THREADS;
 				const int w0 = tid * seg, w1 = min(nW, w0 + seg);
@@ -701,13 +719,23 @@ __global__ void __launch_bounds__(HU_LIT_THREADS) seedSortLiteralKernel(SeedArgs
 		const int P = min(min(n, sBound), want + 17);
 		for (int i = tid; i < P; i += HU_LIT_THREADS) sbuf[i] = w[i];
 		__syncthreads();
-		if (tid == 0) {
-			for (int i = 1; i < P; ++i) {
-				const lit_t v = sbuf[i];
-				int j = i;
-				while (j > 0 && LIT_KEY(v) < LIT_KEY(sbuf[j - 1])) { sbuf[j] = sbuf[j - 1]; j--; }
-				sbuf[j] = v;
+		{
+			// insertion sort is a stable sort: every element goes straight to (# smaller keys) + (# equal keys before it)
+			lit_t mine = 0;
+			int rank = 0;
+			if (tid < P) {
+				mine = sbuf[tid];
+				const uint32_t k = LIT_KEY(mine);
+				for (int j = 0; j < P; ++j) {
+					const uint32_t kj = LIT_KEY(sbuf[j]);
+					rank += (kj < k) || (kj == k && j < tid);
+				}
 			}
+			__syncthreads();
+			if (tid < P) sbuf[rank] = mine;
+			__syncthreads();
+		}
+		if (tid == 0) {
 			int nOut = min(want, P);
 			while (nOut > 0 && LIT_KEY(sbuf[nOut - 1]) == 0xFFFFFFFFu) nOut--; // undefined distances (0/0) are not seeds
 			if (a.maxDiff < INFINITY && nOut > 0) { // src/HmmUFOtu_main.cpp:141-150, on the key scale
@@ -718,9 +746,11 @@ __global__ void __launch_bounds__(HU_LIT_THREADS) seedSortLiteralKernel(SeedArgs
 					nOut = keep;
 				}
 			}
-			for (int i = 0; i < nOut; ++i) a.seedIds[(size_t) r * HU_MAX_SEED + i] = nodeOfPos[(uint32_t) sbuf[i]];
+			sCut = nOut;
 			a.nSeeds[r] = sOverflow ? -nOut - 1 : nOut;
 		}
+		__syncthreads();
+		if (tid < sCut) a.seedIds[(size_t) r * HU_MAX_SEED + tid] = nodeOfPos[(uint32_t) sbuf[tid]];
 	}
 }
 
