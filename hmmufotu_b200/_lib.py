@@ -54,7 +54,7 @@ class PlaceRow(C.Structure):
 class SepParams(C.Structure):
     _fields_ = [("maxNSeed", C.c_int32), ("useTrueLoglik", C.c_int32), ("maxDiff", C.c_double),
                 ("maxHeight", C.c_double), ("maxError", C.c_double), ("equalSortPerm", C.c_void_p),
-                ("seedOrder", C.c_int32), ("reserved", C.c_int32)]
+                ("seedOrder", C.c_int32), ("estMethod", C.c_int32), ("prior", C.c_int32), ("onlyML", C.c_int32)]
 
 
 class BatchStats(C.Structure):

@@ -124,7 +124,9 @@ void hu_sep_params_default(hu_sep_params* p) {
 	p->maxError = 20;
 	p->equalSortPerm = NULL;
 	p->seedOrder = HU_SEED_ORDER_STDSORT;
-	p->reserved = 0;
+	p->estMethod = HU_EST_UNWEIGHTED;
+	p->prior = HU_PRIOR_UNIFORM;
+	p->onlyML = 0;
 }
 
 int hu_batch_create(hu_batch** out, hu_db* db, int32_t maxReads, int32_t maxSeqLen, int32_t paired) {

@@ -26,7 +26,7 @@ namespace hu {
 #define HU_EST_WARPS 8                   // warps per CTA of the wide-window kernel
 
 struct EstArgs {
-	int nReads, maxNSeed, pad0, pad1;
+	int nReads, maxNSeed, weighted, pad1; // weighted: estimateBranchLengthWeighted instead of ...Unweighted
 	const int8_t* aligned;
 	const int* winStart;
 	const int* winEnd;
@@ -115,6 +115,7 @@ struct EstSmem {
 	double Np[5][4];                              // P(wnr) applied to the read's leaf vector, per base / gap
 	unsigned int redB[HU_EST_CONS / 32];
 	double redC[HU_EST_CONS / 32];
+	double redW[2][HU_EST_CONS / 32];
 	unsigned long long full[HU_EST_STAGES], empty[HU_EST_STAGES], hfull[2], hempty[2];
 };
 
@@ -199,6 +200,7 @@ __global__ void __launch_bounds__(HU_EST_THREADS, 2) estimateStagedKernel(EstArg
 	// ================= consumer warps =================
 	int piMax = 0; // argmax of log(pi): state of a gap column of the read
 	for (int k = 1; k < 4; ++k) if (m.logPi[k] > m.logPi[piMax]) piMax = k;
+	const double wGap = m.pi[piMax] / ((m.pi[0] + m.pi[1]) + (m.pi[2] + m.pi[3])); // inferWeight(log pi) at its arg-max
 	int st = 0, ph = 0, h = 0, hph = 0;
 	for (;;) {
 		mbarWait(&sm.hfull[h], hph);
@@ -215,6 +217,7 @@ __global__ void __launch_bounds__(HU_EST_THREADS, 2) estimateStagedKernel(EstArg
 		if (warp == 3) ll = windowScale(t.dnS, t.dnP32, it.u, t.csLen, t.nWords, it.start, it.start + W - 1, lane);
 		// ---- pass 1: the unweighted branch-length estimate; g_j parked in shared memory ----
 		unsigned int diff = 0;
+		double dW = 0, nW = 0; // weighted variant: sums of w1 w2 over mismatching / all columns (cpp:1034-1052)
 		for (int c0 = 0; c0 < W; c0 += HU_EST_CH) {
 			mbarWait(&sm.full[st], ph);
 			const int c = c0 + tid;
@@ -226,7 +229,14 @@ __global__ void __launch_bounds__(HU_EST_THREADS, 2) estimateStagedKernel(EstArg
 				matVec4(P1, ev, yb);
 				for (int k = 0; k < 4; ++k) { g[k] = ya[k] * yb[k]; sm.g[k][c] = g[k]; }
 				const int b = x[c];
-				diff += argmax4(g) != (b >= 0 ? b : piMax);
+				const int st1 = argmax4(g);
+				const bool mis = st1 != (b >= 0 ? b : piMax);
+				diff += mis;
+				if (a.weighted) { // inferWeight at the arg-max: max / sum for the tree side, 1 (base) or pi_max / sum(pi) (gap) for the read
+					const double ww = g[st1] / ((g[0] + g[1]) + (g[2] + g[3])) * (b >= 0 ? 1.0 : wGap);
+					if (mis) dW += ww;
+					nW += ww;
+				}
 			}
 			__syncwarp();
 			if (lane == 0) mbarArrive(&sm.empty[st]);
@@ -237,7 +247,16 @@ __global__ void __launch_bounds__(HU_EST_THREADS, 2) estimateStagedKernel(EstArg
 		consumerSync(HU_EST_CONS);
 		diff = 0;
 		for (int k = 0; k < HU_EST_CONS / 32; ++k) diff += sm.redB[k];
-		const double wnr = (double) diff / (double) W;
+		double wnr = (double) diff / (double) W;
+		if (a.weighted) { // block sums of the two weights (uniform branch)
+			for (int o = 16; o > 0; o >>= 1) { dW += __shfl_xor_sync(0xffffffffu, dW, o); nW += __shfl_xor_sync(0xffffffffu, nW, o); }
+			if (lane == 0) { sm.redW[0][warp] = dW; sm.redW[1][warp] = nW; }
+			consumerSync(HU_EST_CONS);
+			dW = nW = 0;
+			for (int k = 0; k < HU_EST_CONS / 32; ++k) { dW += sm.redW[0][k]; nW += sm.redW[1][k]; }
+			wnr = dW / nW;
+			consumerSync(HU_EST_CONS); // redW is reused by the next item
+		}
 		// ---- P(wnr) applied to the read's leaf vector: depends on the base only ----
 		if (warp == 0) {
 			if (lane < 16) modelPrHalfWarp(m, wnr, sm.P2, lane, 0x0000ffffu);
@@ -338,6 +357,8 @@ __global__ void __launch_bounds__(HU_EST_WARPS * 32) estimateWideKernel(EstArgs 
 		const double* U = t.up + ((size_t) u * t.csLen + start) * 4;
 		const double* V = t.dn + ((size_t) u * t.csLen + start) * 4;
 		int diff = 0;
+		double dW = 0, nW = 0;
+		const double wGap = m.pi[piMax] / ((m.pi[0] + m.pi[1]) + (m.pi[2] + m.pi[3]));
 		for (int c = lane; c < W; c += 32) {
 			double eu[4], ev[4], ya[4], yb[4], g[4];
 			ld4(U + (size_t) c * 4, eu);
@@ -346,10 +367,21 @@ __global__ void __launch_bounds__(HU_EST_WARPS * 32) estimateWideKernel(EstArgs 
 			matVec4(ws.P[1], ev, yb);
 			for (int k = 0; k < 4; ++k) g[k] = ya[k] * yb[k];
 			const int b = x[c];
-			diff += argmax4(g) != (b >= 0 ? b : piMax);
+			const int st1 = argmax4(g);
+			const bool mis = st1 != (b >= 0 ? b : piMax);
+			diff += mis;
+			if (a.weighted) {
+				const double ww = g[st1] / ((g[0] + g[1]) + (g[2] + g[3])) * (b >= 0 ? 1.0 : wGap);
+				if (mis) dW += ww;
+				nW += ww;
+			}
 		}
 		for (int o = 16; o > 0; o >>= 1) diff += __shfl_xor_sync(0xffffffffu, diff, o);
-		const double wnr = (double) diff / (double) W;
+		double wnr = (double) diff / (double) W;
+		if (a.weighted) {
+			for (int o = 16; o > 0; o >>= 1) { dW += __shfl_xor_sync(0xffffffffu, dW, o); nW += __shfl_xor_sync(0xffffffffu, nW, o); }
+			wnr = dW / nW;
+		}
 		if (lane == 0) modelPr(m, wnr, ws.P[2]);
 		__syncwarp();
 		if (lane < 5) {
@@ -414,7 +446,7 @@ __global__ void filterKernel(int nReads, const int* __restrict__ winStart, const
 int launchEstimate(hu_batch* b, const hu_sep_params* p) {
 	hu_db* db = b->db;
 	EstArgs a;
-	a.nReads = b->nReads; a.maxNSeed = p->maxNSeed; a.pad0 = a.pad1 = 0;
+	a.nReads = b->nReads; a.maxNSeed = p->maxNSeed; a.weighted = p->estMethod == HU_EST_WEIGHTED; a.pad1 = 0;
 	a.aligned = b->vit.aligned; a.winStart = b->winStart; a.winEnd = b->winEnd;
 	a.seedIds = b->seed.seedIds; a.nSeeds = b->seed.nSeeds;
 	a.est = b->est; a.items = b->estItems; a.itemsP = b->estItemsP; a.wideCount = b->workCount + 2; a.wideList = b->workItems;

@@ -266,7 +266,8 @@ __global__ void __launch_bounds__(HU_PLACE_WARPS * 32) placeKernel(PlaceArgs a, 
 
 // calcQValues (UNIFORM prior) + sort by qPlace + bestPlace; one thread per read.
 __global__ void finalizeKernel(int nReads, const int* __restrict__ winStart, const int* __restrict__ nKept,
-		hu_place_row* __restrict__ places, int useTrue, const int* __restrict__ equalPerm, hu_place_row* __restrict__ best) {
+		hu_place_row* __restrict__ places, int useTrue, int priorHeight, int onlyML, const int* __restrict__ equalPerm,
+		hu_place_row* __restrict__ best) {
 	const int r = blockIdx.x * blockDim.x + threadIdx.x;
 	if (r >= nReads) return;
 	const int n = winStart[r] < 0 ? 0 : nKept[r];
@@ -287,7 +288,25 @@ __global__ void finalizeKernel(int nReads, const int* __restrict__ winStart, con
 	double norm = -INFINITY, mx = -INFINITY;
 	for (int i = 0; i < n; ++i) {
 		if (useTrue) pl[i].loglik = pl[i].loglikTrue;
-		const double p = pl[i].loglik + 0.0;
+		pl[i].annoDist = (pl[i].aNode == pl[i].cNode ? pl[i].wuv * pl[i].ratio : (1 - pl[i].ratio) * pl[i].wuv) + pl[i].wnr;
+		pl[i].nPlaces = n;
+		pl[i].qPlace = pl[i].qTaxon = 0;
+	}
+	if (onlyML) { // --ML (src/hmmufotu.cpp:725-727): std::sort(rbegin, rend, compareByLoglik), no Q values
+		bool allEq = true;
+		int pickML = 0;
+		for (int i = 1; i < n; ++i) {
+			if (pl[i].loglik < pl[0].loglik || pl[0].loglik < pl[i].loglik) allEq = false; // NaN keys compare like equal keys in std::sort
+			if (pl[i].loglik > pl[pickML].loglik) pickML = i;
+		}
+		best[r] = pl[allEq ? equalPerm[n] : pickML];
+		return;
+	}
+	for (int i = 0; i < n; ++i) {
+		// PTPlacement::logPriorPr (src/PhyloTreeUnrooted.cpp:1166-1177): -0 (uniform) or -(annoDist - wnr + height)
+		const double prior = priorHeight ? -(pl[i].annoDist - pl[i].wnr + pl[i].height) : -0.0;
+		const double p = pl[i].loglik + prior;
+		pl[i].qPlace = p; // parked: the posterior log-probability, replaced by the Q value below
 		mx = fmax(mx, p);
 		int tIdx = -1;
 		for (int k = 0; k < nTax; ++k) if (tax[k] == pl[i].taxon) { tIdx = k; break; }
@@ -300,23 +319,26 @@ __global__ void finalizeKernel(int nReads, const int* __restrict__ winStart, con
 		norm = log(exp(norm - sc) + exp(p - sc)) + sc;
 	}
 	double sum = 0;
-	for (int i = 0; i < n; ++i) sum += exp(pl[i].loglik - mx);
+	for (int i = 0; i < n; ++i) sum += exp(pl[i].qPlace - mx);
 	bool allEqual = true;
 	double q0 = 0;
 	for (int i = 0; i < n; ++i) {
-		const double pr = exp(pl[i].loglik - mx) / sum;
+		const double pr = exp(pl[i].qPlace - mx) / sum;
 		double q = -10.0 * log(1 - pr) / LOG10; // p2q
 		if (q > MAX_Q) q = MAX_Q;
+		// A placement whose ratio is 0/0 makes the height prior, hence every posterior, NaN.  On x86 that NaN reaches the
+		// output with its sign bit cleared (the prior's unary minus flips the default NaN); the device's canonical NaN
+		// has it set, and the TSV shows the sign.
+		if (q != q) q = __longlong_as_double(0x7FF8000000000000LL);
 		pl[i].qPlace = q;
 		if (i == 0) q0 = q;
-		else if (!(q == q0)) allEqual = false;
+		else if (q < q0 || q0 < q) allEqual = false; // NaN keys (a NaN prior makes every posterior NaN) compare like equal keys
 		double pt = 0;
 		for (int k = 0; k < nTax; ++k) if (tax[k] == pl[i].taxon) pt = taxPP[k];
 		double qt = -10.0 * log(1 - exp(pt - norm)) / LOG10;
 		if (qt > MAX_Q) qt = MAX_Q;
+		if (qt != qt) qt = __longlong_as_double(0x7FF8000000000000LL);
 		pl[i].qTaxon = qt;
-		pl[i].annoDist = (pl[i].aNode == pl[i].cNode ? pl[i].wuv * pl[i].ratio : (1 - pl[i].ratio) * pl[i].wuv) + pl[i].wnr;
-		pl[i].nPlaces = n;
 	}
 	// std::sort(places.rbegin(), places.rend(), compareByQPlace); bestPlace = places[0]
 	int pick = 0;
@@ -362,7 +384,8 @@ int launchPlace(hu_batch* b, const hu_sep_params* p) {
 }
 
 int launchFinalize(hu_batch* b, const hu_sep_params* p) {
-	finalizeKernel<<<(b->nReads + 63) / 64, 64, 0, b->stream>>>(b->nReads, b->winStart, b->nKept, b->places, p->useTrueLoglik, b->equalPerm, b->best);
+	finalizeKernel<<<(b->nReads + 63) / 64, 64, 0, b->stream>>>(b->nReads, b->winStart, b->nKept, b->places, p->useTrueLoglik,
+			p->prior == HU_PRIOR_HEIGHT, p->onlyML, b->equalPerm, b->best);
 	HU_CUDA(cudaEventRecord(b->ev[7], b->stream));
 	b->launches += 1;
 	HU_CUDA(cudaGetLastError());

@@ -163,12 +163,14 @@ class Database:
 
 class SepParams:
     def __init__(self, max_n_seed: int = 50, max_error: float = 20.0, max_diff: float = np.inf,
-                 max_height: float = np.inf, use_true_loglik: bool = False, seed_order: int = _lib.SEED_ORDER_STDSORT):
+                 max_height: float = np.inf, use_true_loglik: bool = False, seed_order: int = _lib.SEED_ORDER_STDSORT,
+                 weighted: bool = False, prior_height: bool = False, only_ml: bool = False):
         p = _lib.SepParams()
         _lib.load().hu_sep_params_default(C.byref(p))
         p.maxNSeed, p.maxError, p.maxDiff, p.maxHeight = max_n_seed, max_error, max_diff, max_height
         p.useTrueLoglik = int(use_true_loglik)
         p.seedOrder = int(seed_order)
+        p.estMethod, p.prior, p.onlyML = int(weighted), int(prior_height), int(only_ml)
         self.c = p
 
 

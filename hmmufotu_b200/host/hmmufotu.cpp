@@ -38,6 +38,9 @@ static void printUsage(const string& prog) {
 		 << "            -d|--max-diff  DBL   : max p-dist difference allowed for sub-optimal seeds [inf]" << endl
 		 << "            -H|--max-height  DBL : max height of seed nodes to be used in the SEP algorithm [inf]" << endl
 		 << "            -e|--err  DBL        : max placement error used in the 'Estimate' stage of SEP algorithm [20]" << endl
+		 << "            -m|--method  STR     : branch length estimating method during the estimated-placement stage, 'unweighted' or 'weighted' [unweighted]" << endl
+		 << "            --ML  FLAG           : use maximum likelihood in phylogenetic placement, do not calculate posterior p-values" << endl
+		 << "            --prior  STR         : method for calculating prior probability of a placement, either 'uniform' or 'height' [uniform]" << endl
 		 << "            --true-loglik  FLAG  : report the root log-likelihood of each placement instead of the reference's constant (DESIGN.md 5)" << endl
 		 << "            --chimera-out  FILE  : keep assignment output of chimera reads (bad mate orientation) in FILE" << endl
 		 << "            -S|--seed  INT       : random seed used for CSFM-index seed searches, for debug only" << endl
@@ -129,6 +132,15 @@ int main(int argc, char* argv[]) {
 	if (cmdOpts.hasOpt("-H") || cmdOpts.hasOpt("--max-height")) sp.maxHeight = atof(cmdOpts.get("-H", "--max-height", "inf").c_str());
 	sp.maxError = atof(cmdOpts.get("-e", "--err", "20").c_str());
 	sp.useTrueLoglik = cmdOpts.hasOpt("--true-loglik");
+	{ // -m|--method, --ML, --prior: src/hmmufotu.cpp:229-246, 335-338
+		const string estMethod = cmdOpts.get("-m", "--method", "unweighted");
+		if (estMethod != "unweighted" && estMethod != "weighted") { cerr << "Unsupported branch estimating method '" << estMethod << "'" << endl; return EXIT_FAILURE; }
+		sp.estMethod = estMethod == "weighted" ? HU_EST_WEIGHTED : HU_EST_UNWEIGHTED;
+		sp.onlyML = cmdOpts.hasOpt("--ML");
+		const string prior = cmdOpts.get("--prior", "--prior", "uniform");
+		if (prior != "uniform" && prior != "height") { cerr << "Unsupported prior specified, check the --prior option" << endl; return EXIT_FAILURE; }
+		sp.prior = prior == "height" ? HU_PRIOR_HEIGHT : HU_PRIOR_UNIFORM;
+	}
 	unsigned seed = (unsigned) time(NULL);
 	if (cmdOpts.hasOpt("-S") || cmdOpts.hasOpt("--seed")) seed = (unsigned) atoi(cmdOpts.get("-S", "--seed", "0").c_str());
 	const int device = atoi(cmdOpts.get("--gpu", "--gpu", "0").c_str());

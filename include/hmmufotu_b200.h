@@ -152,10 +152,18 @@ typedef struct hu_sep_params {
 	                               * first on n equal keys, at [n]; NULL = library-built table */
 	int32_t seedOrder;   /* HU_SEED_ORDER_STDSORT (default): the seeds libstdc++'s std::sort leaves in front, ties
 	                      * included (src/HmmUFOtu_main.cpp:139); HU_SEED_ORDER_ID: deterministic (dist, id) order */
-	int32_t reserved;
+	int32_t estMethod;   /* -m|--method (src/hmmufotu.cpp:229-232): HU_EST_UNWEIGHTED (default) or HU_EST_WEIGHTED
+	                      * (estimateBranchLengthWeighted, src/PhyloTreeUnrooted.cpp:1034-1052) */
+	int32_t prior;       /* --prior (src/hmmufotu.cpp:236-241): HU_PRIOR_UNIFORM (default) or HU_PRIOR_HEIGHT
+	                      * (PTPlacement::logPriorPr, src/PhyloTreeUnrooted.cpp:1166-1177) */
+	int32_t onlyML;      /* --ML (src/hmmufotu.cpp:233-235, 725-727): order by log-likelihood, no Q values */
 } hu_sep_params;
 #define HU_SEED_ORDER_STDSORT 0
 #define HU_SEED_ORDER_ID 1
+#define HU_EST_UNWEIGHTED 0
+#define HU_EST_WEIGHTED 1
+#define HU_PRIOR_UNIFORM 0
+#define HU_PRIOR_HEIGHT 1
 void hu_sep_params_default(hu_sep_params* p);
 
 /* ---- batch workspace ---- */

@@ -133,6 +133,8 @@ struct Tree {
 	std::vector<double> up, dn;
 	Model model;
 	DGamma dg;                          /* dg.K == 0 -> no discrete Gamma */
+	/* run options of src/hmmufotu.cpp:229-241: -m weighted, --prior height, --ML */
+	int estWeighted = 0, priorHeight = 0, onlyML = 0;
 	const double* U(long id) const { return &up[(size_t) id * csLen * 4]; }
 	const double* V(long id) const { return &dn[(size_t) id * csLen * 4]; }
 	const int8_t* s(long id) const { return &seq[(size_t) id * csLen]; }
@@ -157,6 +159,7 @@ double pDist(const int8_t* s1, const int8_t* s2, int start, int end, long* d = 0
 /* seedOrder: 0 = libstdc++ std::sort (literal), 1 = stable (dist, id) */
 std::vector<PTLoc> getSeed(const Tree&, const int8_t* seq, int start, int end, double maxDiff, double maxHeight, int seedOrder);
 Placement estimateSeq(const Tree&, const int8_t* seq, const PTLoc& loc);           /* src/PhyloTreeUnrooted.cpp:849-877 */
+void sortByLoglik(std::vector<Placement>& places);
 void filterPlacements(std::vector<Placement>&, double maxError);                   /* src/HmmUFOtu_main.cpp:162-173 */
 void placeSeq(const Tree&, const int8_t* seq, Placement&, double maxHeight);       /* src/PhyloTreeUnrooted.cpp:879-954 */
 void calcQValues(const Tree&, std::vector<Placement>&);                            /* src/HmmUFOtu_main.cpp:182-216 */

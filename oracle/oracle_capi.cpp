@@ -307,14 +307,22 @@ int orc_assign(void* op, const int8_t* seq, int start, int end, int nSeeds, cons
 		places[i].outerIters = idx;
 		if (useTrue) places[i].loglik = places[i].loglikTrue;
 	}
-	calcQValues(t, places);
-	sortByQPlace(places);
+	if (t.onlyML) sortByLoglik(places);
+	else {
+		calcQValues(t, places);
+		sortByQPlace(places);
+	}
 	for (size_t i = 0; i < places.size(); ++i) {
 		int idx = places[i].outerIters;
 		places[i].outerIters = iters[idx];
 		fillRow(rows[i], places[i], est[idx]);
 	}
 	return (int) places.size();
+}
+
+void orc_tree_set_options(void* op, int estWeighted, int priorHeight, int onlyML) {
+	Tree& t = ((OrcTree*) op)->t;
+	t.estWeighted = estWeighted; t.priorHeight = priorHeight; t.onlyML = onlyML;
 }
 
 /* permutation std::sort(rbegin, rend) leaves on an all-equal array of n elements: out[i] = old index now at i */

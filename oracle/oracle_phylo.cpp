@@ -279,7 +279,9 @@ Placement estimateSeq(const Tree& t, const int8_t* seq, const PTLoc& loc) { /* s
 	t.model.Pr(wvr, Pv);
 	const int W = loc.end - loc.start + 1;
 	std::vector<double> R((size_t) W * 4);
-	double d = 0;
+	double d = 0, Nw = 0;
+	/* inferWeight(l)(argmax l) (src/PhyloTreeUnrooted.h:1590-1593): exp(l - max l) / sum, i.e. 1 / sum at the arg-max */
+	struct Wt { static double top(const double l[4]) { double mx = l[0]; for (int k = 1; k < 4; ++k) if (l[k] > mx) mx = l[k]; double s = 0; for (int k = 0; k < 4; ++k) s += ::exp(l[k] - mx); return 1.0 / s; } };
 	for (int j = loc.start; j <= loc.end; ++j) {
 		double a[4], b[4], n[4];
 		dpsMat(Pu, U + (size_t) j * 4, a);
@@ -287,9 +289,14 @@ Placement estimateSeq(const Tree& t, const int8_t* seq, const PTLoc& loc) { /* s
 		double* r = &R[(size_t) (j - loc.start) * 4];
 		for (int k = 0; k < 4; ++k) r[k] = a[k] + b[k];
 		leafLoglik(t, seq[j], n);
-		if (argmax4(r) != argmax4(n)) d++; /* estimateBranchLengthUnweighted, :1018-1032 */
+		if (!t.estWeighted) { if (argmax4(r) != argmax4(n)) d++; } /* estimateBranchLengthUnweighted, :1018-1032 */
+		else { /* estimateBranchLengthWeighted, :1034-1052 */
+			const double ww = Wt::top(r) * Wt::top(n);
+			if (argmax4(r) != argmax4(n)) d += ww;
+			Nw += ww;
+		}
 	}
-	double wnr = d / (loc.end - loc.start + 1);
+	double wnr = t.estWeighted ? d / Nw : d / (loc.end - loc.start + 1);
 	t.model.Pr(wnr, Pn);
 	double loglik = 0;
 	for (int j = loc.start; j <= loc.end; ++j) {
@@ -321,6 +328,7 @@ void filterPlacements(std::vector<Placement>& places, double maxError) { /* src/
 }
 
 void sortByQPlace(std::vector<Placement>& places) { std::sort(places.rbegin(), places.rend(), cmpQPlace); }
+void sortByLoglik(std::vector<Placement>& places) { std::sort(places.rbegin(), places.rend(), cmpLoglik); } /* --ML, src/hmmufotu.cpp:725-727 */
 
 /* -------------------------------------------------------------------- place ---- */
 namespace {
@@ -460,7 +468,13 @@ void calcQValues(const Tree& t, std::vector<Placement>& places) { /* src/HmmUFOt
 	std::map<std::string, double> ppTaxon;
 	double ppTaxNorm = NEG_INF;
 	for (size_t i = 0; i < places.size(); ++i) {
-		double p = places[i].loglik + (-0.0);
+		double prior = -0.0; /* PTPlacement::logPriorPr, src/PhyloTreeUnrooted.cpp:1166-1177 */
+		if (t.priorHeight) {
+			const Placement& pl = places[i];
+			const double annoDist = pl.a == pl.c ? pl.wuv * pl.ratio + pl.wnr : (1 - pl.ratio) * pl.wuv + pl.wnr;
+			prior = -(annoDist - pl.wnr + pl.height);
+		}
+		double p = places[i].loglik + prior;
 		pp[i] = p;
 		const std::string& tax = t.anno[places[i].a];
 		if (ppTaxon.find(tax) == ppTaxon.end()) ppTaxon[tax] = p;

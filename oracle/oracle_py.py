@@ -70,6 +70,7 @@ def lib() -> C.CDLL:
         L.orc_place.argtypes = [vp, vp, P(PlaceRow), f64]
         L.orc_assign.argtypes = [vp, vp, i32, i32, i32, vp, vp, f64, f64, i32, P(PlaceRow)]
         L.orc_equal_sort_perm.argtypes = [i32, vp]
+        L.orc_tree_set_options.argtypes = [vp, i32, i32, i32]
         L.orc_tree_evaluate_mt.argtypes = [vp, i32, i32]
         L.orc_run_reads.argtypes = [vp, vp, i32, C.c_char_p, vp, vp, vp, i32, i32, f64, i32, i32, i32, P(PlaceRow), vp, vp]
         assert L.orc_sizeof_place_row() == C.sizeof(PlaceRow)
@@ -196,6 +197,10 @@ class OracleTree:
         if getattr(self, "h", None):
             lib().orc_tree_free(self.h)
             self.h = None
+
+    def set_options(self, weighted: bool = False, prior_height: bool = False, only_ml: bool = False):
+        """-m weighted / --prior height / --ML of the reference's hmmufotu (src/hmmufotu.cpp:229-241)"""
+        lib().orc_tree_set_options(self.h, int(weighted), int(prior_height), int(only_ml))
 
     def messages(self) -> Tuple[np.ndarray, np.ndarray]:
         up = np.zeros((self.n_nodes, self.cs_len, 4)); dn = np.zeros_like(up)

@@ -34,7 +34,7 @@ def test_header_symbols_exported(lib):
 def test_struct_layouts_match_header():
     # sizes the kernels and the Python mirror must agree on (LP64)
     assert C.sizeof(_lib.AlignRow) == 48 and C.sizeof(_lib.PlaceRow) == 120
-    assert C.sizeof(_lib.SepParams) == 48 and C.sizeof(_lib.ReadBatch) == 40
+    assert C.sizeof(_lib.SepParams) == 56 and C.sizeof(_lib.ReadBatch) == 40
 
 
 def test_hmm_finalize_matches_oracle(lib):

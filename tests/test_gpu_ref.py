@@ -32,12 +32,12 @@ def data_lines(path):
     return [ln.rstrip("\n") for ln in open(path) if not ln.startswith("#")]
 
 
-def run_case(name, d, tag, seed, paired):
+def run_case(name, d, tag, seed, paired, opts=(), variant=""):
     reads = [os.path.join(GOLD, "%s_%s_%d.fasta" % (name, tag, m)) for m in (1, 2)] if paired else [os.path.join(GOLD, "%s_%s.fasta" % (name, tag))]
-    out = os.path.join(d, tag + ".tsv")
-    p = subprocess.run([CLI, os.path.join(d, name)] + reads + ["-o", out, "-s", "1", "-S", str(seed), "--batch", "64"], capture_output=True, text=True)
+    out = os.path.join(d, tag + variant + ".tsv")
+    p = subprocess.run([CLI, os.path.join(d, name)] + reads + ["-o", out, "-s", "1", "-S", str(seed), "--batch", "64"] + list(opts), capture_output=True, text=True)
     assert p.returncode == 0, p.stderr[-2000:]
-    got, want = data_lines(out), data_lines(os.path.join(GOLD, "%s_%s.tsv" % (name, tag)))
+    got, want = data_lines(out), data_lines(os.path.join(GOLD, "%s_%s%s.tsv" % (name, tag, variant)))
     assert got[0] == want[0]                      # column header
     assert len(got) == len(want) == 65
     bad = [(g.split("\t")[0], i) for i, (g, w) in enumerate(zip(got, want)) if g != w]
@@ -56,4 +56,13 @@ def test_single_end_tsv_is_the_references(refdb_dir):
 def test_paired_end_tsv_is_the_references(refdb_dir):
     name, d = refdb_dir
     got, want, bad = run_case(name, d, "pe0", 7, True)
+    assert not bad, "rows differ from the reference's TSV: %s\n%s\n%s" % (bad[:5], got[bad[0][1]][-300:], want[bad[0][1]][-300:])
+
+
+@pytest.mark.parametrize("variant,opts", [("weighted", ["-m", "weighted"]), ("ml", ["--ML"]), ("height", ["--prior", "height"])])
+def test_run_options_tsv_is_the_references(refdb_dir, variant, opts):
+    name, d = refdb_dir
+    if not os.path.exists(os.path.join(GOLD, "%s_se0.%s.tsv" % (name, variant))):
+        pytest.skip("variant goldens exist for the GTR database only")
+    got, want, bad = run_case(name, d, "se0", 0, False, opts, "." + variant)
     assert not bad, "rows differ from the reference's TSV: %s\n%s\n%s" % (bad[:5], got[bad[0][1]][-300:], want[bad[0][1]][-300:])

@@ -125,3 +125,22 @@ def test_paired_end_rows_match_the_reference(refcase):
         aligns[rid] = O.merge(L, a, b)
     n, t = check_rows(refcase, os.path.join(GOLD, name + "_pe0.tsv"), aligns)
     assert n + t == len(fwd) and n >= 0.9 * len(fwd)
+
+
+@pytest.mark.parametrize("variant", ["weighted", "ml", "height"])
+def test_run_options_match_the_reference(refcase, variant):
+    """-m weighted, --ML and --prior height (src/hmmufotu.cpp:229-241) against the reference's TSVs of the same reads"""
+    name = refcase["name"]
+    tsv = os.path.join(GOLD, "%s_se0.%s.tsv" % (name, variant))
+    if not os.path.exists(tsv):
+        pytest.skip("variant goldens exist for the GTR database only")
+    fa = os.path.join(GOLD, name + "_se0.fasta")
+    reads = refdb.read_fasta(fa)
+    vps = seeds_of(refcase, fa, 0)
+    aligns = {rid: refcase["ohmm"].align(seq.upper(), vps[i]) for i, (rid, _, seq) in enumerate(reads)}
+    refcase["otree"].set_options(weighted=variant == "weighted", prior_height=variant == "height", only_ml=variant == "ml")
+    try:
+        n, t = check_rows(refcase, tsv, aligns)
+    finally:
+        refcase["otree"].set_options()
+    assert n + t == len(reads) and n >= 0.9 * len(reads)
