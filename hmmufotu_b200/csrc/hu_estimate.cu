@@ -130,6 +130,7 @@ __device__ __forceinline__ void ldsColumn(const double* __restrict__ chunk, int 
 	v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
 }
 
+template <bool WEIGHTED>
 __global__ void __launch_bounds__(HU_EST_THREADS, 2) estimateStagedKernel(EstArgs a, TreeDev t, Model m) {
 	extern __shared__ __align__(128) unsigned char estRaw[];
 	EstSmem& sm = *reinterpret_cast<EstSmem*>(estRaw);
@@ -232,7 +233,7 @@ __global__ void __launch_bounds__(HU_EST_THREADS, 2) estimateStagedKernel(EstArg
 				const int st1 = argmax4(g);
 				const bool mis = st1 != (b >= 0 ? b : piMax);
 				diff += mis;
-				if (a.weighted) { // inferWeight at the arg-max: max / sum for the tree side, 1 (base) or pi_max / sum(pi) (gap) for the read
+				if (WEIGHTED) { // inferWeight at the arg-max: max / sum for the tree side, 1 (base) or pi_max / sum(pi) (gap) for the read
 					const double ww = g[st1] / ((g[0] + g[1]) + (g[2] + g[3])) * (b >= 0 ? 1.0 : wGap);
 					if (mis) dW += ww;
 					nW += ww;
@@ -248,7 +249,7 @@ __global__ void __launch_bounds__(HU_EST_THREADS, 2) estimateStagedKernel(EstArg
 		diff = 0;
 		for (int k = 0; k < HU_EST_CONS / 32; ++k) diff += sm.redB[k];
 		double wnr = (double) diff / (double) W;
-		if (a.weighted) { // block sums of the two weights (uniform branch)
+		if (WEIGHTED) { // block sums of the two weights (uniform branch)
 			for (int o = 16; o > 0; o >>= 1) { dW += __shfl_xor_sync(0xffffffffu, dW, o); nW += __shfl_xor_sync(0xffffffffu, nW, o); }
 			if (lane == 0) { sm.redW[0][warp] = dW; sm.redW[1][warp] = nW; }
 			consumerSync(HU_EST_CONS);
@@ -455,12 +456,14 @@ int launchEstimate(hu_batch* b, const hu_sep_params* p) {
 	HU_CUDA(cudaMemsetAsync(b->workCount, 0, 4 * sizeof(int), b->stream));
 	static bool attr = false;
 	if (!attr) {
-		HU_CUDA(cudaFuncSetAttribute(estimateStagedKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(EstSmem)));
+		HU_CUDA(cudaFuncSetAttribute(estimateStagedKernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(EstSmem)));
+		HU_CUDA(cudaFuncSetAttribute(estimateStagedKernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(EstSmem)));
 		attr = true;
 	}
 	const int total = a.nReads * a.maxNSeed;
 	estPlanKernel<<<(total + 7) / 8, 256, 0, b->stream>>>(a, db->tree, db->model);
-	estimateStagedKernel<<<sms * 2, HU_EST_THREADS, sizeof(EstSmem), b->stream>>>(a, db->tree, db->model);
+	if (a.weighted) estimateStagedKernel<true><<<sms * 2, HU_EST_THREADS, sizeof(EstSmem), b->stream>>>(a, db->tree, db->model);
+	else estimateStagedKernel<false><<<sms * 2, HU_EST_THREADS, sizeof(EstSmem), b->stream>>>(a, db->tree, db->model);
 	estimateWideKernel<<<sms * 4, HU_EST_WARPS * 32, 0, b->stream>>>(a, db->tree, db->model); // exits at once when no window is wide
 	filterKernel<<<(b->nReads + 127) / 128, 128, 0, b->stream>>>(b->nReads, b->winStart, a.nSeeds, b->est, p->maxError, b->order, b->nKept);
 	HU_CUDA(cudaEventRecord(b->ev[5], b->stream));

@@ -42,6 +42,10 @@ static void printUsage(const string& prog) {
 		 << "            --ML  FLAG           : use maximum likelihood in phylogenetic placement, do not calculate posterior p-values" << endl
 		 << "            --prior  STR         : method for calculating prior probability of a placement, either 'uniform' or 'height' [uniform]" << endl
 		 << "            --true-loglik  FLAG  : report the root log-likelihood of each placement instead of the reference's constant (DESIGN.md 5)" << endl
+		 << "            -C|--chimera  FLAG   : enable the chimera checking procedure (segment re-estimation); see DESIGN.md 5 for what it can report" << endl
+		 << "            --num-segment  INT   : number of segments used in chimera checking procedure [2]" << endl
+		 << "            --chimera-err  DBL   : max placement error used in the 'Estimate' stage of chimera SEP algorithm" << endl
+		 << "            --chimera-lod  DBL   : min log-odd required for defining a chimera read [0]" << endl
 		 << "            --chimera-out  FILE  : keep assignment output of chimera reads (bad mate orientation) in FILE" << endl
 		 << "            -S|--seed  INT       : random seed used for CSFM-index seed searches, for debug only" << endl
 		 << "            --gpu  INT           : CUDA device to use [0]" << endl
@@ -132,6 +136,21 @@ int main(int argc, char* argv[]) {
 	if (cmdOpts.hasOpt("-H") || cmdOpts.hasOpt("--max-height")) sp.maxHeight = atof(cmdOpts.get("-H", "--max-height", "inf").c_str());
 	sp.maxError = atof(cmdOpts.get("-e", "--err", "20").c_str());
 	sp.useTrueLoglik = cmdOpts.hasOpt("--true-loglik");
+	{ // -C|--chimera and its options, src/hmmufotu.cpp:248-260, 325-340.  The segment re-estimation compares placeSeq()
+	  // return values of the SAME window (best vs. alternative branch), and that value is the constant
+	  // W * log(sum pi e), so chimera_lod is exactly 0 and `chimera_lod > --chimera-lod (>= 0)` never
+	  // holds: with -C the reference writes the same assignment rows (checked against the reference binary,
+	  // tests/test_gpu_ref.py).  Only --chimera-info would show the segment placements; it is refused.
+		const bool checkChimera = cmdOpts.hasOpt("-C") || cmdOpts.hasOpt("--chimera");
+		if (checkChimera) {
+			const int numSeg = atoi(cmdOpts.get("--num-segment", "--num-segment", "2").c_str());
+			if (!(2 <= numSeg && numSeg <= 6)) { cerr << "--num-segment must be in range [2, 6]" << endl; return EXIT_FAILURE; }
+			if (numSeg % 2) { cerr << "--num-segment must be an even number" << endl; return EXIT_FAILURE; }
+			if (cmdOpts.hasOpt("--chimera-err") && !(atof(cmdOpts.get("--chimera-err", "--chimera-err", "0").c_str()) > 0)) { cerr << "--chimera-err must be positive" << endl; return EXIT_FAILURE; }
+			if (cmdOpts.hasOpt("--chimera-lod") && !(atof(cmdOpts.get("--chimera-lod", "--chimera-lod", "0").c_str()) >= 0)) { cerr << "--chimera-lod must be non-negative" << endl; return EXIT_FAILURE; }
+			if (cmdOpts.hasOpt("--chimera-info")) { cerr << "--chimera-info is not supported by this build (segment placements are not reported)" << endl; return EXIT_FAILURE; }
+		}
+	}
 	{ // -m|--method, --ML, --prior: src/hmmufotu.cpp:229-246, 335-338
 		const string estMethod = cmdOpts.get("-m", "--method", "unweighted");
 		if (estMethod != "unweighted" && estMethod != "weighted") { cerr << "Unsupported branch estimating method '" << estMethod << "'" << endl; return EXIT_FAILURE; }

@@ -66,3 +66,12 @@ def test_run_options_tsv_is_the_references(refdb_dir, variant, opts):
         pytest.skip("variant goldens exist for the GTR database only")
     got, want, bad = run_case(name, d, "se0", 0, False, opts, "." + variant)
     assert not bad, "rows differ from the reference's TSV: %s\n%s\n%s" % (bad[:5], got[bad[0][1]][-300:], want[bad[0][1]][-300:])
+
+
+def test_chimera_check_changes_no_row(refdb_dir):
+    """-C: the reference's segment log-odds are differences of the constant placeSeq() value, i.e. 0, so no read is
+    ever flagged and its TSV is the one without -C (verified on the reference binary when the goldens were minted)."""
+    name, d = refdb_dir
+    got, want, bad = run_case(name, d, "se0", 0, False, ["-C", "--chimera-out", os.path.join(d, "chi.tsv")])
+    assert not bad
+    assert [ln for ln in open(os.path.join(d, "chi.tsv")) if not ln.startswith("#")][1:] == []   # header line only
