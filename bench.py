@@ -31,6 +31,9 @@ SCALES = {
     # BASELINE.json configs[2]; window: all reads start inside one 300-column stretch
     "full": dict(n_leaves=99322, cs_len=7682, occupancy=0.18, seed=20260103, window=(2000, 2300), read_len=250,
                  workload="C3: synthetic gg_97-scale DB (99322 leaves, 198643 nodes, csLen 7682, GTR) + 250 bp V4-like SE reads"),
+    # BASELINE.json configs[4]-like stress shape: near-full-length reads, windows of ~6500 columns (wide-window kernels)
+    "long": dict(n_leaves=99322, cs_len=7682, occupancy=0.18, seed=20260103, window=(0, 300), read_len=1200,
+                 workload="C5-like: synthetic gg_97-scale DB (GTR) + 1200 bp near-full-length SE reads (NOT the headline workload)"),
     # a shrunken stand-in for quick functional runs (NOT the benchmark configuration)
     "small": dict(n_leaves=2000, cs_len=2000, occupancy=0.5, seed=20260101, window=(300, 500), read_len=250,
                   workload="reduced functional config (2000 leaves, csLen 2000) -- not the BASELINE workload"),
@@ -331,6 +334,9 @@ def _main(real_stdout):
         sample = args.cpu_sample or max(cores * 40, 256)  # about 10-30 s of CPU work
         sub = reads.slice(0, sample)
         r = CpuReference(db, sub, cores).run()
+        # kind "port": the reference's own binary (oracle/_ref) needs the database as files, and configs[2]'s .ptu is
+        # 98 GB; the port is pinned to that binary row by row (tests/test_ref_pin.py) and is the FASTER CPU program
+        # (39.8 vs 5.8 reads/s single-threaded on the 70_otus database, where both run), so it is the conservative baseline
         cpu = dict(value=r["reads_per_s"], unit="reads/s", cores=cores, kind="port",
                    sample="%d reads of the same pool, %d threads, %.1fs; oracle tree cut to consensus columns %d..%d (built in %.0fs, untimed)"
                           % (sample, cores, r["seconds"], r["columns"][0], r["columns"][1], r["build_seconds"]))
