@@ -143,3 +143,17 @@ def test_cli_end_to_end(exes, dbfiles):
             assert r[10] == "%d->%d" % (want[0].c, want[0].p), i
             assert r[12] == str(want[0].a)
             assert r[15] == "%g" % want[0].loglik and r[16] == "%g" % want[0].qPlace
+
+
+def test_cli_rejects_what_the_reference_rejects(exes):
+    """option validation of src/hmmufotu.cpp:318-348 (no GPU needed: the checks come before the database is opened)"""
+    def err(*opts):
+        p = subprocess.run([exes[0], "nodb", "noreads.fa", *opts], capture_output=True, text=True)
+        assert p.returncode != 0
+        return p.stderr
+    assert "even number" in err("-C", "--num-segment", "3")
+    assert "--chimera-lod must be non-negative" in err("-C", "--chimera-lod", "-1")
+    assert "--chimera-info" in err("-C", "--chimera-info")
+    assert "Unsupported prior" in err("--prior", "depth")
+    assert "Unsupported branch estimating method" in err("-m", "both")
+    assert "-L|--seed-len" in err("-L", "99")
