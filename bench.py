@@ -34,6 +34,9 @@ SCALES = {
     # BASELINE.json configs[4]-like stress shape: near-full-length reads, windows of ~6500 columns (wide-window kernels)
     "long": dict(n_leaves=99322, cs_len=7682, occupancy=0.18, seed=20260103, window=(0, 300), read_len=1200,
                  workload="C5-like: synthetic gg_97-scale DB (GTR) + 1200 bp near-full-length SE reads (NOT the headline workload)"),
+    # BASELINE.json configs[3]-like shape on one GPU: 2 x 250 bp pairs with overlapping mates (merged windows of 1.5-2.5 k columns)
+    "pe": dict(n_leaves=99322, cs_len=7682, occupancy=0.18, seed=20260103, window=None, read_len=250, paired=True, insert_len=420,
+               workload="C4-like: synthetic gg_97-scale DB (GTR) + 2x250 bp PE reads, one GPU (NOT the headline workload)"),
     # a shrunken stand-in for quick functional runs (NOT the benchmark configuration)
     "small": dict(n_leaves=2000, cs_len=2000, occupancy=0.5, seed=20260101, window=(300, 500), read_len=250,
                   workload="reduced functional config (2000 leaves, csLen 2000) -- not the BASELINE workload"),
@@ -91,7 +94,10 @@ def build_inputs(cfg, n_reads, read_seed):
     t0 = time.time()
     db = synth.make_db(n_leaves=cfg["n_leaves"], cs_len=cfg["cs_len"], occupancy=cfg["occupancy"], seed=cfg["seed"])
     t1 = time.time()
-    reads = synth.make_reads(db, n_reads, read_len=cfg["read_len"], seed=read_seed, window=cfg["window"])
+    if cfg.get("paired"):
+        reads = synth.make_pairs(db, n_reads, read_len=cfg["read_len"], insert_len=cfg["insert_len"], insert_sd=20.0, seed=read_seed)
+    else:
+        reads = synth.make_reads(db, n_reads, read_len=cfg["read_len"], seed=read_seed, window=cfg["window"])
     log("synthetic DB %.1fs (K=%d, nodes=%d), %d reads %.1fs" % (t1 - t0, db.K, db.n_nodes, n_reads, time.time() - t1))
     return db, reads
 
@@ -198,15 +204,22 @@ def _main(real_stdout):
     t0 = time.time()
     gdb = engine.Database(db, device=local)          # uploads, evaluates all messages on the device, repacks
     log("rank %d: device DB %.1f GB in %.1fs" % (rank, gdb.bytes / 1e9, time.time() - t0))
-    max_len = int(np.max(np.diff(reads.offsets))) + 8
-    ws = [engine.Batch(gdb, B, max_len) for _ in range(n_ws)]
+    paired = bool(cfg.get("paired"))
+    if paired and (world > 1 or not args.no_cpu):
+        raise SystemExit("bench.py: the paired-end shape is a single-GPU functional run (--no-cpu)")
+    sets = reads if paired else (reads,)
+    max_len = max(int(np.max(np.diff(x.offsets))) for x in sets) + 8
+    ws = [engine.Batch(gdb, B, max_len, paired=paired) for _ in range(n_ws)]
     params = engine.SepParams()
     batches = []
     for i in range(pool_batches):
-        s = reads.slice(i * B, (i + 1) * B)
-        s.codes = engine.pinned_copy(s.codes); s.offsets = engine.pinned_copy(s.offsets)
-        s.vpaths = engine.pinned_copy(s.vpaths); s.n_paths = engine.pinned_copy(s.n_paths)
-        batches.append(s)
+        parts = []
+        for x in sets:
+            s = x.slice(i * B, (i + 1) * B)
+            s.codes = engine.pinned_copy(s.codes); s.offsets = engine.pinned_copy(s.offsets)
+            s.vpaths = engine.pinned_copy(s.vpaths); s.n_paths = engine.pinned_copy(s.n_paths)
+            parts.append(s)
+        batches.append(parts)
 
     def barrier():
         for w in ws:
@@ -224,7 +237,7 @@ def _main(real_stdout):
 
     # ---------------- kernel-resident throughput: inputs already in HBM ----------------
     for i, w in enumerate(ws):
-        w.upload(batches[i % pool_batches])
+        w.upload(*batches[i % pool_batches])
     for i in range(args.warmup):
         ws[i % n_ws].assign(params)
     barrier()
@@ -258,7 +271,7 @@ def _main(real_stdout):
     # ---------------- end to end: host buffers in, assignment rows out, every step ----------------
     def e2e_step(i):
         w = ws[i % n_ws]
-        w.upload(batches[i % pool_batches])
+        w.upload(*batches[i % pool_batches])
         w.assign(params)
 
     def e2e_collect(i):
@@ -284,7 +297,7 @@ def _main(real_stdout):
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_value = world * B * args.steps / e2e_s
-    h2d = int(batches[0].codes.nbytes + (B * 312))
+    h2d = int(sum(x.codes.nbytes for x in batches[0]) + (B * 312 * len(batches[0])))
     d2h = int(rows.nbytes + best.nbytes + sum(len(t) for t in traces))
 
     # ---------------- roofline of every stage, and of the dominant one ----------------
@@ -332,7 +345,7 @@ def _main(real_stdout):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         sample = args.cpu_sample or max(cores * 40, 256)  # about 10-30 s of CPU work
-        sub = reads.slice(0, sample)
+        sub = sets[0].slice(0, sample)
         r = CpuReference(db, sub, cores).run()
         # kind "port": the reference's own binary (oracle/_ref) needs the database as files, and configs[2]'s .ptu is
         # 98 GB; the port is pinned to that binary row by row (tests/test_ref_pin.py) and is the FASTER CPU program

@@ -21,12 +21,12 @@ namespace hu {
 #define HU_EST_THREADS (HU_EST_CONS + 32) // + the producer warp
 #define HU_EST_CH 256                    // columns per ring stage
 #define HU_EST_STAGES 3
-#define HU_EST_CAPW 1536                 // widest window the staged kernel takes
-#define HU_EST_HDR (HU_EST_CAPW + 32)    // bytes per staged sequence window (16-byte alignment slack on both sides)
+#define HU_EST_CAPW 1536                 // widest window the staged kernel takes with two CTAs per SM (single-end amplicon reads)
+#define HU_EST_CAPW_BIG 3328             // ... with one CTA per SM (merged paired-end windows)
 #define HU_EST_WARPS 8                   // warps per CTA of the wide-window kernel
 
 struct EstArgs {
-	int nReads, maxNSeed, weighted, pad1; // weighted: estimateBranchLengthWeighted instead of ...Unweighted
+	int nReads, maxNSeed, weighted, capW; // weighted: estimateBranchLengthWeighted instead of ...Unweighted; capW: widest staged window
 	const int8_t* aligned;
 	const int* winStart;
 	const int* winEnd;
@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(256) estPlanKernel(EstArgs a, TreeDev t, Model
 	if (ws >= 0 && s < a.nSeeds[r]) {
 		const int u = a.seedIds[(size_t) r * HU_MAX_SEED + s];
 		it.u = u; it.v = t.parent[u]; it.start = ws; it.W = a.winEnd[r] - ws + 1; it.w0 = t.blen[u];
-		it.kind = it.W <= HU_EST_CAPW ? 1 : 2;
+		it.kind = it.W <= a.capW ? 1 : 2;
 		const int8_t* x = a.aligned + (size_t) r * t.csLen + ws;
 		const int8_t* su = t.seq + (size_t) it.u * t.csLen + ws;
 		const int8_t* sv = t.seq + (size_t) it.v * t.csLen + ws;
@@ -106,18 +106,20 @@ __global__ void __launch_bounds__(256) estPlanKernel(EstArgs a, TreeDev t, Model
 
 struct EstSmem {
 	double ring[HU_EST_STAGES][2][HU_EST_CH * 4]; // U chunk, V chunk
-	double g[4][HU_EST_CAPW];                     // g_j of the current item, one plane per state
 	EstItemP rec[2];                              // cDist, ratio, P(wur), P(wvr) of the staged items (bulk-copied)
-	int8_t hdr[2][HU_EST_HDR];                    // the read's window, double buffered
 	EstItem meta[2];
-	int hoff[2];                                  // offset of the window inside hdr (alignment remainder)
+	int hoff[4];                                  // [0..1]: offset of the window inside hdr (alignment remainder); rest: padding
 	double P2[16];                                // P(wnr)
 	double Np[5][4];                              // P(wnr) applied to the read's leaf vector, per base / gap
 	unsigned int redB[HU_EST_CONS / 32];
 	double redC[HU_EST_CONS / 32];
 	double redW[2][HU_EST_CONS / 32];
 	unsigned long long full[HU_EST_STAGES], empty[HU_EST_STAGES], hfull[2], hempty[2];
+	// followed in dynamic shared memory by g[4][capW] (g_j of the current item, one plane per state) and
+	// hdr[2][capW + 32] (the read's window, double buffered, 16-byte alignment slack on both sides)
 };
+static_assert(sizeof(EstSmem) % 16 == 0, "the arrays behind EstSmem are targets of 16-byte bulk copies");
+__host__ __device__ inline size_t estSmemBytes(int capW) { return sizeof(EstSmem) + (size_t) 4 * capW * sizeof(double) + (size_t) 2 * (capW + 32); }
 
 // one message column out of a ring stage: two 128-bit reads; every other group of four threads reads the halves
 // in the opposite order so that a quarter-warp covers all 32 banks.  Those threads get (v2, v3, v0, v1) and
@@ -134,6 +136,9 @@ template <bool WEIGHTED>
 __global__ void __launch_bounds__(HU_EST_THREADS, 2) estimateStagedKernel(EstArgs a, TreeDev t, Model m) {
 	extern __shared__ __align__(128) unsigned char estRaw[];
 	EstSmem& sm = *reinterpret_cast<EstSmem*>(estRaw);
+	double* const gS = reinterpret_cast<double*>(estRaw + sizeof(EstSmem));
+	int8_t* const hdrS = reinterpret_cast<int8_t*>(gS + (size_t) 4 * a.capW);
+	const int capW = a.capW, hdrPitch = a.capW + 32;
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 	const int total = a.nReads * a.maxNSeed;
 	const int nBatches = (total + 31) / 32;
@@ -173,7 +178,7 @@ __global__ void __launch_bounds__(HU_EST_THREADS, 2) estimateStagedKernel(EstArg
 					const uint32_t bytes = (uint32_t) ((off + it.W + 15) & ~15);
 					sm.hoff[h] = off;
 					mbarArriveExpectTx(&sm.hfull[h], bytes + (uint32_t) sizeof(EstItemP));
-					bulkLoad(sm.hdr[h], src - off, bytes, &sm.hfull[h]);
+					bulkLoad(hdrS + (size_t) h * hdrPitch, src - off, bytes, &sm.hfull[h]);
 					bulkLoad(&sm.rec[h], a.itemsP + ((size_t) r * a.maxNSeed + it.rs % HU_MAX_SEED), (uint32_t) sizeof(EstItemP), &sm.hfull[h]);
 					const double* U = t.up + ((size_t) it.u * t.csLen + it.start) * 4;
 					const double* V = t.dn + ((size_t) it.u * t.csLen + it.start) * 4;
@@ -208,7 +213,7 @@ __global__ void __launch_bounds__(HU_EST_THREADS, 2) estimateStagedKernel(EstArg
 		const EstItem it = sm.meta[h];
 		if (it.kind == 0) break;
 		const int W = it.W;
-		const int8_t* x = sm.hdr[h] + sm.hoff[h];
+		const int8_t* x = hdrS + (size_t) h * hdrPitch + sm.hoff[h];
 		const int sw = (tid >> 2) & 1;
 		const double* P0 = sm.rec[h].P[0][sw];
 		const double* P1 = sm.rec[h].P[1][sw];
@@ -228,7 +233,7 @@ __global__ void __launch_bounds__(HU_EST_THREADS, 2) estimateStagedKernel(EstArg
 				ldsColumn(sm.ring[st][1], tid, ev);
 				matVec4(P0, eu, ya); // rows are not permuted: ya, yb and g are in state order for every thread
 				matVec4(P1, ev, yb);
-				for (int k = 0; k < 4; ++k) { g[k] = ya[k] * yb[k]; sm.g[k][c] = g[k]; }
+				for (int k = 0; k < 4; ++k) { g[k] = ya[k] * yb[k]; gS[k * capW + c] = g[k]; }
 				const int b = x[c];
 				const int st1 = argmax4(g);
 				const bool mis = st1 != (b >= 0 ? b : piMax);
@@ -278,7 +283,7 @@ __global__ void __launch_bounds__(HU_EST_THREADS, 2) estimateStagedKernel(EstArg
 			const int b = x[c];
 			const double* np = sm.Np[b >= 0 ? b : 4];
 			double z[4];
-			for (int k = 0; k < 4; ++k) z[k] = sm.g[k][c] * np[k];
+			for (int k = 0; k < 4; ++k) z[k] = gS[k * capW + c] * np[k];
 			prod *= dotPi(m, z);
 			if (prod < 1e-150) { ll += log(prod); prod = 1.0; }
 		}
@@ -447,7 +452,9 @@ __global__ void filterKernel(int nReads, const int* __restrict__ winStart, const
 int launchEstimate(hu_batch* b, const hu_sep_params* p) {
 	hu_db* db = b->db;
 	EstArgs a;
-	a.nReads = b->nReads; a.maxNSeed = p->maxNSeed; a.weighted = p->estMethod == HU_EST_WEIGHTED; a.pad1 = 0;
+	a.nReads = b->nReads; a.maxNSeed = p->maxNSeed; a.weighted = p->estMethod == HU_EST_WEIGHTED;
+	// merged paired-end windows and long reads are wider than an amplicon read's: one CTA per SM with a larger g buffer
+	a.capW = (b->paired || b->maxSeqLen > 400) ? HU_EST_CAPW_BIG : HU_EST_CAPW;
 	a.aligned = b->vit.aligned; a.winStart = b->winStart; a.winEnd = b->winEnd;
 	a.seedIds = b->seed.seedIds; a.nSeeds = b->seed.nSeeds;
 	a.est = b->est; a.items = b->estItems; a.itemsP = b->estItemsP; a.wideCount = b->workCount + 2; a.wideList = b->workItems;
@@ -456,14 +463,16 @@ int launchEstimate(hu_batch* b, const hu_sep_params* p) {
 	HU_CUDA(cudaMemsetAsync(b->workCount, 0, 4 * sizeof(int), b->stream));
 	static bool attr = false;
 	if (!attr) {
-		HU_CUDA(cudaFuncSetAttribute(estimateStagedKernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(EstSmem)));
-		HU_CUDA(cudaFuncSetAttribute(estimateStagedKernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(EstSmem)));
+		HU_CUDA(cudaFuncSetAttribute(estimateStagedKernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) estSmemBytes(HU_EST_CAPW_BIG)));
+		HU_CUDA(cudaFuncSetAttribute(estimateStagedKernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) estSmemBytes(HU_EST_CAPW_BIG)));
 		attr = true;
 	}
 	const int total = a.nReads * a.maxNSeed;
 	estPlanKernel<<<(total + 7) / 8, 256, 0, b->stream>>>(a, db->tree, db->model);
-	if (a.weighted) estimateStagedKernel<true><<<sms * 2, HU_EST_THREADS, sizeof(EstSmem), b->stream>>>(a, db->tree, db->model);
-	else estimateStagedKernel<false><<<sms * 2, HU_EST_THREADS, sizeof(EstSmem), b->stream>>>(a, db->tree, db->model);
+	const size_t smem = estSmemBytes(a.capW);
+	const int grid = sms * (smem <= 112 * 1024 ? 2 : 1);
+	if (a.weighted) estimateStagedKernel<true><<<grid, HU_EST_THREADS, smem, b->stream>>>(a, db->tree, db->model);
+	else estimateStagedKernel<false><<<grid, HU_EST_THREADS, smem, b->stream>>>(a, db->tree, db->model);
 	estimateWideKernel<<<sms * 4, HU_EST_WARPS * 32, 0, b->stream>>>(a, db->tree, db->model); // exits at once when no window is wide
 	filterKernel<<<(b->nReads + 127) / 128, 128, 0, b->stream>>>(b->nReads, b->winStart, a.nSeeds, b->est, p->maxError, b->order, b->nKept);
 	HU_CUDA(cudaEventRecord(b->ev[5], b->stream));
