@@ -135,6 +135,63 @@ class CpuReference:
                     bad=bad, rows=rows, coords=coords)
 
 
+def calibrate_reference(threads):
+    """The reference's OWN binary (oracle/_ref/hmmufotu, built from /root/reference/src against the stand-in
+    Eigen/Boost headers) and the oracle port on the same 128 reads of the reference-built 70_otus database
+    (tests/golden/ref70, BASELINE.json configs[0]), both on `threads` host threads: how the port used for the
+    configs[2] baseline relates to the real program.  None when the prebuilt binary is absent."""
+    import gzip
+    import shutil
+    import tempfile
+    exe = os.path.join(ROOT, "oracle", "_ref", "hmmufotu")
+    gold = os.path.join(ROOT, "tests", "golden", "ref70")
+    name = "gg_70_otus_GTR"
+    if not (os.path.exists(exe) and os.path.exists(os.path.join(gold, name + ".ptu.gz"))):
+        return None
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "oracle")); sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import oracle_py as O
+        import refdb
+        from types import SimpleNamespace
+        d = tempfile.mkdtemp(prefix="hu_cal_")
+        for ext in (".msa", ".hmm", ".csfm"):
+            shutil.copy(os.path.join(gold, name + ext), os.path.join(d, name + ext))
+        with gzip.open(os.path.join(gold, name + ".ptu.gz"), "rb") as f, open(os.path.join(d, name + ".ptu"), "wb") as g:
+            shutil.copyfileobj(f, g)
+        fa = os.path.join(d, "cal.fasta")
+        with open(fa, "w") as out:
+            for k in (0, 2):
+                out.write(open(os.path.join(gold, "%s_se%d.fasta" % (name, k))).read())
+        t0 = time.time()
+        subprocess.run([exe, name, "cal.fasta", "-o", "cal.tsv", "-s", "1", "-S", "0", "-p", str(threads)], cwd=d, check=True,
+                       stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        t_ref = time.time() - t0
+        db = refdb.load_ptu(os.path.join(d, name + ".ptu"))
+        tree = O.OracleTree(db, evaluate=False)
+        up, dn = np.ascontiguousarray(db.up), np.ascontiguousarray(db.dn)
+        O.lib().orc_tree_set_messages(tree.h, up.ctypes.data_as(O.C.c_void_p), dn.ctypes.data_as(O.C.c_void_p))
+        hmm = O.OracleHmm(path=os.path.join(d, name + ".hmm"))
+        reads = refdb.read_fasta(fa)
+        seeds = subprocess.run([os.path.join(ROOT, "hmmufotu_b200", "bin", "hu_host_test"), "seeds", os.path.join(d, name), fa, "0"],
+                               capture_output=True, text=True, check=True).stdout.strip().split("\n")
+        vp = np.zeros((len(reads), 2, 6), dtype=np.int32); npth = np.zeros(len(reads), dtype=np.int32)
+        for i, ln in enumerate(seeds):
+            v = np.array([[int(x) for x in q.split(",")] for q in ln.split("\t")[2:]], dtype=np.int32).reshape(-1, 6)
+            npth[i] = len(v); vp[i, :len(v)] = v
+        codes = np.concatenate([np.array(["ACGT".index(c) for c in sq.upper()], dtype=np.int8) for _, _, sq in reads])
+        offs = np.concatenate([[0], np.cumsum([len(sq) for _, _, sq in reads])]).astype(np.int64)
+        rs = SimpleNamespace(n=len(reads), codes=codes, offsets=offs, vpaths=vp, n_paths=npth)
+        t0 = time.time()
+        O.run_reads(hmm, tree, rs, threads=threads)
+        t_port = time.time() - t0
+        shutil.rmtree(d, ignore_errors=True)
+        return dict(db="70_otus GTR built by the reference's hmmufotu-build (configs[0])", reads=len(reads), threads=threads,
+                    reference_binary_reads_per_s=len(reads) / t_ref, port_reads_per_s=len(reads) / t_port,
+                    note="reference binary = oracle/_ref/hmmufotu (wall time incl. its 0.2 s database load)")
+    except Exception as e:  # a calibration failure must not take the bench line down
+        return dict(error=str(e)[:200])
+
+
 def main():
     # stdout carries exactly ONE JSON line: everything else that libraries print there (e.g. NCCL's version
     # banner) is sent to stderr
@@ -183,7 +240,8 @@ def _main(real_stdout):
                     ms_per_step=1e3 * tot / len(vals), higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64",
                     data="synthetic", config=dict(workload=cfg["workload"], batch=sample, l2="inputs larger than L2"),
                     cpu_baseline=dict(value=v, unit="reads/s", cores=cores, kind="port",
-                                      sample="%d reads per step on %d threads; oracle tree cut to consensus columns %d..%d" % (sample, cores, vals[0]["columns"][0], vals[0]["columns"][1])),
+                                      sample="%d reads per step on %d threads; oracle tree cut to consensus columns %d..%d" % (sample, cores, vals[0]["columns"][0], vals[0]["columns"][1]),
+                                      calibration=calibrate_reference(cores)),
                     e2e=dict(value=v, unit="reads/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
         print(json.dumps(line), file=real_stdout, flush=True)
         return 0
@@ -352,7 +410,8 @@ def _main(real_stdout):
         # (39.8 vs 5.8 reads/s single-threaded on the 70_otus database, where both run), so it is the conservative baseline
         cpu = dict(value=r["reads_per_s"], unit="reads/s", cores=cores, kind="port",
                    sample="%d reads of the same pool, %d threads, %.1fs; oracle tree cut to consensus columns %d..%d (built in %.0fs, untimed)"
-                          % (sample, cores, r["seconds"], r["columns"][0], r["columns"][1], r["build_seconds"]))
+                          % (sample, cores, r["seconds"], r["columns"][0], r["columns"][1], r["build_seconds"]),
+                   calibration=calibrate_reference(cores))
 
     if world > 1:
         dist.destroy_process_group()
