@@ -75,3 +75,37 @@ def test_chimera_check_changes_no_row(refdb_dir):
     got, want, bad = run_case(name, d, "se0", 0, False, ["-C", "--chimera-out", os.path.join(d, "chi.tsv")])
     assert not bad
     assert [ln for ln in open(os.path.join(d, "chi.tsv")) if not ln.startswith("#")][1:] == []   # header line only
+
+
+def test_device_tree_evaluation_matches_the_reference_builder(refdb_dir):
+    """hu_db_create() without messages (the path the benchmark's synthetic database takes): all-roots messages and
+    inferred internal sequences evaluated on the device from the leaves, against what the reference's hmmufotu-build
+    stored in its .ptu (src/hmmufotu-build.cpp:455-470)."""
+    import sys
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    sys.path.insert(0, HERE)
+    import oracle_py as O
+    import refdb
+    from types import SimpleNamespace
+    from hmmufotu_b200 import engine
+    name, d = refdb_dir
+    ref = refdb.load_ptu(os.path.join(d, name + ".ptu"))
+    hp = O.OracleHmm(path=os.path.join(d, name + ".hmm")).params()
+    is_leaf = np.ones(ref.n_nodes, dtype=bool)
+    is_leaf[ref.parent[ref.parent >= 0]] = False
+    seq = ref.seq.copy()
+    seq[~is_leaf] = 0                                   # internal rows are placeholders: the device infers them
+    ns = SimpleNamespace(K=hp["eM"].shape[0] - 1, cs_len=ref.cs_len, n_nodes=ref.n_nodes, root=ref.root, eM=hp["eM"], eI=hp["eI"],
+                         T=hp["T"], p2cs=hp["p2cs"], parent=ref.parent, blen=ref.blen, height=ref.height, seq=seq, taxon=ref.taxon,
+                         model=ref.model, dg_rates=ref.dg_rates)
+    gdb = engine.Database(ns, messages=None, infer_internal=True)
+    up, dn = gdb.messages()
+    nonroot = np.arange(ref.n_nodes) != ref.root
+    for got, want in ((up, ref.up), (dn, ref.dn)):
+        got, want = got[nonroot], want[nonroot]
+        fin = np.isfinite(want)
+        assert np.array_equal(np.isfinite(got), fin)
+        np.testing.assert_allclose(got[fin], want[fin], rtol=1e-9, atol=0)
+    assert np.array_equal(gdb.seqs(), ref.seq)          # leaves untouched, internal nodes as the reference inferred them
+    gdb.close()
