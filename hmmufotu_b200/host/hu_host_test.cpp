@@ -85,6 +85,8 @@ int main(int argc, char** argv) {
 		cout << "numSeq " << msa.numSeq << " csLen " << msa.csLen << endl;
 		return out.good() ? 0 : 1;
 	}
+	const bool single = argc > 5 && string(argv[argc - 1]) == "--single"; // NGCL mode: no 3' seed (src/HmmUFOtu_main.cpp:66)
+	if (single) argc--;
 	if (cmd == "seeds" && (argc == 5 || argc == 6)) { // seeds DB FASTA SEED [MATE-FASTA]: rand() is drawn pair by pair, forward read first
 		const string db = argv[2];
 		ifstream msaIn((db + ".msa").c_str(), ios_base::binary), hmmIn((db + ".hmm").c_str());
@@ -106,7 +108,7 @@ int main(int argc, char** argv) {
 			vector<PrimarySeq> rs(1, io.nextSeq());
 			if (argc == 6) rs.push_back(mio.nextSeq().revcom()); // src/hmmufotu.cpp:609
 			for (size_t q = 0; q < rs.size(); ++q) {
-				const vector<BandedHMMP7::ViterbiAlignPath> v = findSeeds(hmm, csfm, rs[q], 20, 50, BandedHMMP7::GLOBAL);
+				const vector<BandedHMMP7::ViterbiAlignPath> v = findSeeds(hmm, csfm, rs[q], 20, 50, single ? BandedHMMP7::NGCL : BandedHMMP7::GLOBAL);
 				cout << rs[q].getId() << "\t" << v.size();
 				for (size_t i = 0; i < v.size(); ++i)
 					cout << "\t" << v[i].start << "," << v[i].end << "," << v[i].from << "," << v[i].to << "," << v[i].nIns << "," << v[i].nDel;

@@ -10,7 +10,7 @@ Writes tests/golden/ref70/:
   se<k>.fasta, se<k>.tsv                      reads drawn by the reference's hmmufotu-sim and the assignment TSV of
                                               the reference's hmmufotu (-s 1 -S <k> -p 1)
   pe<k>_{1,2}.fasta, pe<k>.tsv                the same for paired-end reads
-  se0.{weighted,ml,height}.tsv                se0 again with -m weighted / --ML / --prior height
+  se0.{weighted,ml,height,single}.tsv         se0 again with -m weighted / --ML / --prior height / --single (NGCL alignment mode)
 Every file holds at most 64 reads: up to 64 OpenMP tasks are deferred and then run in creation order, so the
 reference consumes rand() (CSFM seed picks) in file order, as the batched driver does.
 """
@@ -50,7 +50,7 @@ def main():
             run(os.path.join(REF, "hmmufotu"), db, tag + ".fasta", "-o", tag + ".tsv", "-s", "1", "-S", str(k), "-p", "1")
         if model == "GTR":  # the other run options of the per-read path, on the first read file
             tag = "%s_se0" % db
-            for name, opts in (("weighted", ["-m", "weighted"]), ("ml", ["--ML"]), ("height", ["--prior", "height"])):
+            for name, opts in (("weighted", ["-m", "weighted"]), ("ml", ["--ML"]), ("height", ["--prior", "height"]), ("single", ["--single"])):
                 run(os.path.join(REF, "hmmufotu"), db, tag + ".fasta", "-o", "%s.%s.tsv" % (tag, name), "-s", "1", "-S", "0", "-p", "1", *opts)
         tag = "%s_pe0" % db
         run(os.path.join(REF, "hmmufotu-sim"), db, tag + "_1.fasta", tag + "_2.fasta", "-N", "64", "-S", "7", "-r", "150")

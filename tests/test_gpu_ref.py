@@ -59,7 +59,7 @@ def test_paired_end_tsv_is_the_references(refdb_dir):
     assert not bad, "rows differ from the reference's TSV: %s\n%s\n%s" % (bad[:5], got[bad[0][1]][-300:], want[bad[0][1]][-300:])
 
 
-@pytest.mark.parametrize("variant,opts", [("weighted", ["-m", "weighted"]), ("ml", ["--ML"]), ("height", ["--prior", "height"])])
+@pytest.mark.parametrize("variant,opts", [("weighted", ["-m", "weighted"]), ("ml", ["--ML"]), ("height", ["--prior", "height"]), ("single", ["--single"])])
 def test_run_options_tsv_is_the_references(refdb_dir, variant, opts):
     name, d = refdb_dir
     if not os.path.exists(os.path.join(GOLD, "%s_se0.%s.tsv" % (name, variant))):

@@ -41,9 +41,9 @@ def refcase(request, tmp_path_factory):
     return dict(name=name, dir=str(d), db=db, otree=otree, ohmm=ohmm)
 
 
-def seeds_of(case, fasta, seed, mate=None):
+def seeds_of(case, fasta, seed, mate=None, single=False):
     """Host CSFM seed search (product host code, rand() in the reference's order) -> per sequence VPath arrays."""
-    cmd = [HOST_TEST, "seeds", os.path.join(case["dir"], case["name"]), fasta, str(seed)] + ([mate] if mate else [])
+    cmd = [HOST_TEST, "seeds", os.path.join(case["dir"], case["name"]), fasta, str(seed)] + ([mate] if mate else []) + (["--single"] if single else [])
     out = subprocess.run(cmd, capture_output=True, text=True, check=True).stdout.strip().split("\n")
     return [np.array([[int(x) for x in p.split(",")] for p in ln.split("\t")[2:]], dtype=np.int32).reshape(-1, 6) for ln in out]
 
@@ -125,6 +125,51 @@ def test_paired_end_rows_match_the_reference(refcase):
         aligns[rid] = O.merge(L, a, b)
     n, t = check_rows(refcase, os.path.join(GOLD, name + "_pe0.tsv"), aligns)
     assert n + t == len(fwd) and n >= 0.9 * len(fwd)
+
+
+def test_single_mode_matches_the_reference(refcase):
+    """--single: NGCL alignment mode (src/hmmufotu.cpp:358, src/BandedHMMP7.cpp:561-583)"""
+    name = refcase["name"]
+    tsv = os.path.join(GOLD, "%s_se0.single.tsv" % name)
+    if not os.path.exists(tsv):
+        pytest.skip("variant goldens exist for the GTR database only")
+    fa = os.path.join(GOLD, name + "_se0.fasta")
+    reads = refdb.read_fasta(fa)
+    vps = seeds_of(refcase, fa, 0, single=True)
+    ohmm = O.OracleHmm(path=os.path.join(GOLD, name + ".hmm"), mode=O.NGCL)
+    aligns = {rid: ohmm.align(seq.upper(), vps[i]) for i, (rid, _, seq) in enumerate(reads)}
+    n, t = check_rows(refcase, tsv, aligns)
+    assert n + t == len(reads) and n >= 0.9 * len(reads)
+
+
+REF_BIN = os.path.join(ROOT, "oracle", "_ref")
+REF_TEST = "/root/reference/test"
+
+
+@pytest.mark.skipif(not (os.path.exists(os.path.join(REF_BIN, "hmmufotu-build")) and os.path.isdir(REF_TEST)),
+                    reason="needs the reference tree and oracle/_ref (this container only)")
+@pytest.mark.parametrize("model,extra", [("TN93", []), ("F81", ["-V", "-k", "3"]), ("K80", []), ("JC69", ["-V", "-k", "5"])])
+def test_other_models_built_and_run_by_the_reference(model, extra, tmp_path):
+    """The four substitution models without a committed golden: database built, reads drawn and assigned by the
+    reference's own programs on the spot, every TSV column recomputed by the oracle."""
+    db_name = "gg_70_otus_" + model
+    run = lambda *c: subprocess.run(c, cwd=str(tmp_path), check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    run(os.path.join(REF_BIN, "hmmufotu-build"), os.path.join(REF_TEST, "70_otus.fasta"), os.path.join(REF_TEST, "70_otus.tree"),
+        "-a", os.path.join(REF_TEST, "70_otus_taxonomy.txt"), "-n", db_name, "-s", model, *extra)
+    run(os.path.join(REF_BIN, "hmmufotu-sim"), db_name, "r.fasta", "-N", "32", "-S", "5", "-r", "250")
+    run(os.path.join(REF_BIN, "hmmufotu"), db_name, "r.fasta", "-o", "r.tsv", "-s", "1", "-S", "5", "-p", "1")
+    db = refdb.load_ptu(str(tmp_path / (db_name + ".ptu")))
+    assert db.model["type"] == refdb.MODEL_TYPES[model] and (len(db.dg_rates) > 0) == bool(extra)
+    otree = O.OracleTree(db, evaluate=False)
+    up, dn = np.ascontiguousarray(db.up), np.ascontiguousarray(db.dn)
+    O.lib().orc_tree_set_messages(otree.h, up.ctypes.data_as(O.C.c_void_p), dn.ctypes.data_as(O.C.c_void_p))
+    case = dict(name=db_name, dir=str(tmp_path), db=db, otree=otree, ohmm=O.OracleHmm(path=str(tmp_path / (db_name + ".hmm"))))
+    fa = str(tmp_path / "r.fasta")
+    reads = refdb.read_fasta(fa)
+    vps = seeds_of(case, fa, 5)
+    aligns = {rid: case["ohmm"].align(seq.upper(), vps[i]) for i, (rid, _, seq) in enumerate(reads)}
+    n, t = check_rows(case, str(tmp_path / "r.tsv"), aligns)
+    assert n + t == len(reads) and n >= 0.9 * len(reads)
 
 
 @pytest.mark.parametrize("variant", ["weighted", "ml", "height"])
