@@ -347,7 +347,9 @@ int main(int argc, char* argv[]) {
 			if (!isChimera && alnFile.is_open()) {
 				ostringstream d;
 				d << f.getDesc() << ";csStart=" << aln.csStart << ";csEnd=" << aln.csEnd << ";";
-				alnFile << ">" << f.getId() << " " << d.str() << endl << aln.align << endl;
+				alnFile << ">" << f.getId() << " " << d.str() << endl;
+				for (size_t o = 0; o < aln.align.length(); o += 60) // SeqIO::writeFastaSeq, DEFAULT_MAX_LINE = 60 (src/SeqIO.cpp:121-132)
+					alnFile << aln.align.substr(o, 60) << '\n';
 			}
 			dst << f.getId() << "\t" << f.getDesc() << "\t" << aln << "\t" << bestPlace << endl;
 		}

@@ -10,6 +10,7 @@ Writes tests/golden/ref70/:
   se<k>.fasta, se<k>.tsv                      reads drawn by the reference's hmmufotu-sim and the assignment TSV of
                                               the reference's hmmufotu (-s 1 -S <k> -p 1)
   pe<k>_{1,2}.fasta, pe<k>.tsv                the same for paired-end reads
+  se0.aln.fasta                               the -a alignment output of se0
   se0.{weighted,ml,height,single}.tsv         se0 again with -m weighted / --ML / --prior height / --single (NGCL alignment mode)
 Every file holds at most 64 reads: up to 64 OpenMP tasks are deferred and then run in creation order, so the
 reference consumes rand() (CSFM seed picks) in file order, as the batched driver does.
@@ -52,6 +53,7 @@ def main():
             tag = "%s_se0" % db
             for name, opts in (("weighted", ["-m", "weighted"]), ("ml", ["--ML"]), ("height", ["--prior", "height"]), ("single", ["--single"])):
                 run(os.path.join(REF, "hmmufotu"), db, tag + ".fasta", "-o", "%s.%s.tsv" % (tag, name), "-s", "1", "-S", "0", "-p", "1", *opts)
+            run(os.path.join(REF, "hmmufotu"), db, tag + ".fasta", "-o", os.devnull, "-a", tag + ".aln.fasta", "-s", "1", "-S", "0", "-p", "1")
         tag = "%s_pe0" % db
         run(os.path.join(REF, "hmmufotu-sim"), db, tag + "_1.fasta", tag + "_2.fasta", "-N", "64", "-S", "7", "-r", "150")
         run(os.path.join(REF, "hmmufotu"), db, tag + "_1.fasta", tag + "_2.fasta", "-o", tag + ".tsv", "-s", "1", "-S", "7", "-p", "1")

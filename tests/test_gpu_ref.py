@@ -109,3 +109,15 @@ def test_device_tree_evaluation_matches_the_reference_builder(refdb_dir):
         np.testing.assert_allclose(got[fin], want[fin], rtol=1e-9, atol=0)
     assert np.array_equal(gdb.seqs(), ref.seq)          # leaves untouched, internal nodes as the reference inferred them
     gdb.close()
+
+
+def test_alignment_fasta_is_the_references(refdb_dir):
+    """-a: the aligned reads as the reference writes them (src/hmmufotu.cpp:709-715, 60 columns per line)"""
+    name, d = refdb_dir
+    want = os.path.join(GOLD, name + "_se0.aln.fasta")
+    if not os.path.exists(want):
+        pytest.skip("the alignment golden exists for the GTR database only")
+    aln = os.path.join(d, "se0.aln.fasta")
+    got, ref, bad = run_case(name, d, "se0", 0, False, ["-a", aln])
+    assert not bad
+    assert open(aln).read() == open(want).read()
