@@ -231,8 +231,12 @@ int main(int argc, char* argv[]) {
 		hb.offsets.push_back(0);
 		int n = 0, maxLen = 1;
 		for (; n < nTest && testSeqI.hasNext(); ++n) { // fwd then rev per read: the order alignSeq draws rand()
+			// Literal behaviour: the reference's PrimarySeq::revcom() works IN PLACE (src/PrimarySeq.h:229), so
+			// `PrimarySeq revRead = fwdRead.revcom();` (src/hmmufotu.cpp:525) leaves BOTH reads reverse-complemented.
+			// The two alignments differ only through the rand() draws of the seed search, "fwd < rev" rarely holds,
+			// and the test settles on strand 2 (then every single-end read is reverse-complemented, :617-618).
 			const PrimarySeq f = testSeqI.nextSeq(), r = f.revcom();
-			stage(hmm, csfm, f, seedLen, seedRegion, mode, hb);
+			stage(hmm, csfm, r, seedLen, seedRegion, mode, hb);
 			stage(hmm, csfm, r, seedLen, seedRegion, mode, hb);
 			maxLen = max(maxLen, (int) f.length());
 		}
