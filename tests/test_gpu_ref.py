@@ -143,3 +143,16 @@ def test_strand_autodetection_is_the_references(refdb_dir):
     assert not aln_bad, aln_bad[:8]
     same = sum(g == w for g, w in zip(got, ref))
     assert same >= 0.7 * len(ref), same
+
+
+def test_fastq_input_gives_the_same_rows(refdb_dir):
+    """FASTQ reads (format guessed from the file name, src/SeqIO.cpp): the reference writes the rows of the FASTA run
+    (checked on its binary when the golden was minted), and so must this command line"""
+    name, d = refdb_dir
+    fq = os.path.join(GOLD, name + "_se0.fastq")
+    if not os.path.exists(fq):
+        pytest.skip("the FASTQ golden exists for the GTR database only")
+    out = os.path.join(d, "se0.fq.tsv")
+    p = subprocess.run([CLI, os.path.join(d, name), fq, "-o", out, "-s", "1", "-S", "0", "--batch", "64"], capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr[-2000:]
+    assert data_lines(out) == data_lines(os.path.join(GOLD, name + "_se0.tsv"))
