@@ -69,6 +69,8 @@ struct EstItem {
 
 struct EstItemP {
 	double cDist, ratio; // pDist(child seq, read); attachment ratio cDist / (cDist + pDist)
+	double sumScale;     // sum over the window of the per-column scales of both messages
+	int taxU, taxV;      // taxon ids of the child and the parent node (the row's taxon is one of them)
 	double P[2][2][16];  // [m][h]: P(w0 ratio) (m = 0) and P(w0 (1 - ratio)) (m = 1); h = 1: the same matrix with its
 	                     // column pairs (0,1) and (2,3) exchanged, for the threads that read a message column half-swapped
 };

@@ -96,8 +96,13 @@ __global__ void __launch_bounds__(256) estPlanKernel(EstArgs a, TreeDev t, Model
 		modelPrHalfWarp(m, lane < 16 ? wur : wvr, ip.P[lane >> 4][0], lane & 15, 0xffffffffu);
 		__syncwarp();
 		ip.P[lane >> 4][1][lane & 15] = ip.P[lane >> 4][0][(lane & 15) ^ 2]; // entry (i, j) <- (i, j ^ 2)
+		// everything else the streaming kernel would have to fetch from global memory
+		double sc = windowScale(t.upS, t.upP32, it.u, t.csLen, t.nWords, ws, ws + it.W - 1, lane)
+		          + windowScale(t.dnS, t.dnP32, it.u, t.csLen, t.nWords, ws, ws + it.W - 1, lane);
+		for (int o = 16; o > 0; o >>= 1) sc += __shfl_xor_sync(0xffffffffu, sc, o);
 		if (lane == 0) {
-			ip.cDist = cDist; ip.ratio = ratio;
+			ip.cDist = cDist; ip.ratio = ratio; ip.sumScale = sc;
+			ip.taxU = t.taxon[it.u]; ip.taxV = t.taxon[it.v];
 			if (it.kind == 2) a.wideList[atomicAdd(a.wideCount, 1)] = i;
 		}
 	}
@@ -118,6 +123,7 @@ struct EstSmem {
 	// followed in dynamic shared memory by g[4][capW] (g_j of the current item, one plane per state) and
 	// hdr[2][capW + 32] (the read's window, double buffered, 16-byte alignment slack on both sides)
 };
+static_assert(sizeof(EstItemP) % 16 == 0, "item records are bulk-copied");
 static_assert(sizeof(EstSmem) % 16 == 0, "the arrays behind EstSmem are targets of 16-byte bulk copies");
 __host__ __device__ inline size_t estSmemBytes(int capW) { return sizeof(EstSmem) + (size_t) 4 * capW * sizeof(double) + (size_t) 2 * (capW + 32); }
 
@@ -217,10 +223,7 @@ __global__ void __launch_bounds__(HU_EST_THREADS, 2) estimateStagedKernel(EstArg
 		const int sw = (tid >> 2) & 1;
 		const double* P0 = sm.rec[h].P[0][sw];
 		const double* P1 = sm.rec[h].P[1][sw];
-		// the window sums of the scales ride along in the log-likelihood accumulators of two warps
 		double ll = 0;
-		if (warp == 2) ll = windowScale(t.upS, t.upP32, it.u, t.csLen, t.nWords, it.start, it.start + W - 1, lane);
-		if (warp == 3) ll = windowScale(t.dnS, t.dnP32, it.u, t.csLen, t.nWords, it.start, it.start + W - 1, lane);
 		// ---- pass 1: the unweighted branch-length estimate; g_j parked in shared memory ----
 		unsigned int diff = 0;
 		double dW = 0, nW = 0; // weighted variant: sums of w1 w2 over mismatching / all columns (cpp:1034-1052)
@@ -293,14 +296,15 @@ __global__ void __launch_bounds__(HU_EST_THREADS, 2) estimateStagedKernel(EstArg
 		consumerSync(HU_EST_CONS);
 		if (tid == 0) {
 			const double cDist = sm.rec[h].cDist, ratio = sm.rec[h].ratio;
+			const int taxon = ratio <= 0.5 ? sm.rec[h].taxU : sm.rec[h].taxV;
+			ll = sm.rec[h].sumScale;
 			mbarArrive(&sm.hempty[h]); // every consumer is past its last read of this item's staged window and record
-			ll = 0;
 			for (int k = 0; k < HU_EST_CONS / 32; ++k) ll += sm.redC[k];
 			const int r = it.rs / HU_MAX_SEED;
 			hu_place_row row;
 			row.start = it.start; row.end = it.start + W - 1;
 			row.cNode = it.u; row.pNode = it.v; row.aNode = ratio <= 0.5 ? it.u : it.v;
-			row.taxon = t.taxon[row.aNode];
+			row.taxon = taxon;
 			row.dist = cDist;
 			row.wuv = it.w0; row.ratio = ratio; row.wnr = wnr;
 			row.loglik = ll; row.loglikTrue = 0; row.estLoglik = ll;
