@@ -3,12 +3,15 @@
 //   hmm  IN OUT        load a .hmm, save it (bHmm_IO_test.cpp); prints K L and a checksum of the costs
 //   ptu  IN OUT        load a .ptu, save it (PTU_IO_test.cpp:18-59); prints a summary
 //   msa  IN OUT        load a .msa, save it (MSAIO_test.cpp)
+//   locate DB.msa      count() and sorted locate() hits of every pattern on stdin (compared with the reference's own index)
 //   seeds DB FASTA S   CSFM seed search of every read with srand(S): prints the ViterbiAlignPaths
 #include "hu_host.h"
 
 #include <stdlib.h>
 #include <string.h>
+#include <algorithm>
 #include <fstream>
+#include <iostream>
 
 using namespace std;
 using namespace EGriceLab::HmmUFOtu;
@@ -44,7 +47,7 @@ static int csfmTest() {
 }
 
 int main(int argc, char** argv) {
-	if (argc < 2) { cerr << "usage: hu_host_test csfm | hmm IN OUT | ptu IN OUT | msa IN OUT | seeds DB FASTA SEED [MATE-FASTA]" << endl; return 2; }
+	if (argc < 2) { cerr << "usage: hu_host_test csfm | locate DB.msa | hmm IN OUT | ptu IN OUT | msa IN OUT | seeds DB FASTA SEED [MATE-FASTA]" << endl; return 2; }
 	const string cmd = argv[1];
 	if (cmd == "csfm") return csfmTest();
 	if (cmd == "hmm" && argc == 4) {
@@ -84,6 +87,28 @@ int main(int argc, char** argv) {
 		msa.save(out);
 		cout << "numSeq " << msa.numSeq << " csLen " << msa.csLen << endl;
 		return out.good() ? 0 : 1;
+	}
+	if (cmd == "locate" && argc == 3) { // locate DB.msa < patterns: count and sorted hits, the format of oracle/ref_csfm_probe.cpp
+		ifstream in(argv[2], ios_base::binary);
+		if (loadProgInfo(in).bad()) return 1;
+		MSA msa;
+		msa.load(in);
+		if (!in) { cerr << "cannot load " << argv[2] << endl; return 1; }
+		CSFMIndex csfm;
+		csfm.build(msa);
+		string pat;
+		while (getline(cin, pat)) {
+			if (pat.empty()) continue;
+			const vector<CSLoc> locs = csfm.locate(pat);
+			vector<string> items;
+			for (size_t i = 0; i < locs.size(); ++i)
+				items.push_back(to_string(locs[i].start) + "," + to_string(locs[i].end) + "," + locs[i].CS);
+			sort(items.begin(), items.end());
+			cout << pat << "\t" << csfm.count(pat);
+			for (size_t i = 0; i < items.size(); ++i) cout << "\t" << items[i];
+			cout << "\n";
+		}
+		return 0;
 	}
 	const bool single = argc > 5 && string(argv[argc - 1]) == "--single"; // NGCL mode: no 3' seed (src/HmmUFOtu_main.cpp:66)
 	if (single) argc--;

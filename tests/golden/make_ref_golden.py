@@ -11,6 +11,8 @@ Writes tests/golden/ref70/:
                                               the reference's hmmufotu (-s 1 -S <k> -p 1)
   pe<k>_{1,2}.fasta, pe<k>.tsv                the same for paired-end reads
   se0.aln.fasta                               the -a alignment output of se0
+  csfm_locate.{txt,tsv}                       patterns (k-mers cut from se1's reads, plus misses) and what the reference's own
+                                              CSFMIndex (oracle/_ref/csfm_probe on gg_70_otus_GTR.csfm) counts and locates for them
   se0.{weighted,ml,height,single}.tsv         se0 again with -m weighted / --ML / --prior height / --single (NGCL alignment mode)
 Every file holds at most 64 reads: up to 64 OpenMP tasks are deferred and then run in creation order, so the
 reference consumes rand() (CSFM seed picks) in file order, as the batched driver does.
@@ -58,6 +60,19 @@ def main():
         run(os.path.join(REF, "hmmufotu-sim"), db, tag + "_1.fasta", tag + "_2.fasta", "-N", "64", "-S", "7", "-r", "150")
         run(os.path.join(REF, "hmmufotu"), db, tag + "_1.fasta", tag + "_2.fasta", "-o", tag + ".tsv", "-s", "1", "-S", "7", "-p", "1")
         os.remove(db + ".ptu")
+    import random
+    random.seed(5)
+    seqs = [l.strip() for l in open("gg_70_otus_GTR_se1.fasta") if not l.startswith(">")]
+    pats = []
+    for q in seqs[:40]:
+        for k in (20, 12, 8):  # 20 = the seed length of the run path; shorter ones have many hits
+            i = random.randrange(0, len(q) - k)
+            pats.append(q[i:i + k])
+    pats += ["ACGT", "GGGGGGGGGGGGGGGGGGGG", "TTTTTTTTTT"]
+    with open("csfm_locate.txt", "w") as f:
+        f.write("\n".join(pats) + "\n")
+    with open("csfm_locate.txt") as fin, open("csfm_locate.tsv", "w") as fout:
+        subprocess.run([os.path.join(REF, "csfm_probe"), "gg_70_otus_GTR.csfm"], stdin=fin, stdout=fout, check=True)
     for f in sorted(os.listdir(OUT)):
         print("%10d  %s" % (os.path.getsize(f), f))
 

@@ -41,6 +41,23 @@ def test_csfm_known_answers(exes):
     assert "count(ATC) = 6" in out.stdout and out.stdout.strip().endswith("OK")
 
 
+def test_csfm_matches_the_reference_index_hit_for_hit(exes):
+    """The host index rebuilt from <db>.msa against the reference's own CSFMIndex loaded from the <db>.csfm its
+    hmmufotu-build wrote (golden: oracle/_ref/csfm_probe, see tests/golden/make_ref_golden.py): count() and every
+    locate() hit (start, end, gapped CS string) of 123 patterns, 1 551 hits."""
+    g = os.path.join(ROOT, "tests", "golden", "ref70")
+    with open(os.path.join(g, "csfm_locate.txt")) as fin:
+        out = subprocess.run([exes[1], "locate", os.path.join(g, "gg_70_otus_GTR.msa")], stdin=fin, capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    want = open(os.path.join(g, "csfm_locate.tsv")).read()
+    assert out.stdout == want
+    probe = os.path.join(ROOT, "oracle", "_ref", "csfm_probe")
+    if os.path.exists(probe):  # the reference's index itself, live, where oracle/_ref is built
+        with open(os.path.join(g, "csfm_locate.txt")) as fin:
+            ref = subprocess.run([probe, os.path.join(g, "gg_70_otus_GTR.csfm")], stdin=fin, capture_output=True, text=True)
+        assert ref.returncode == 0 and ref.stdout == want
+
+
 def test_ptu_and_msa_roundtrip_bytes(exes, dbfiles):
     """load -> save reproduces the files byte for byte (the reference's IO tests only check the stream state)."""
     for kind in ("ptu", "msa"):
