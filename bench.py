@@ -325,6 +325,15 @@ def _main(real_stdout):
         for k, v in ws[0].stats().items():
             stats[k] = stats.get(k, 0) + v
     launches_per_step = stats["launches"] / n_meas
+    if os.environ.get("HU_PROF"):  # a library built with HU_PROF=1 carries phase clocks of CTA 0 (see hu_seed.cu, hu_estimate.cu)
+        import ctypes
+        from hmmufotu_b200 import _lib
+        L = _lib.load()
+        for sym in ("hu_prof_seed", "hu_prof_est"):
+            if hasattr(L, sym):
+                buf = (ctypes.c_ulonglong * 16)()
+                getattr(L, sym)(buf)
+                log("%s %s" % (sym, list(buf)))
 
     # ---------------- end to end: host buffers in, assignment rows out, every step ----------------
     def e2e_step(i):

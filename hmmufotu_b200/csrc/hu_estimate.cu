@@ -109,6 +109,14 @@ __global__ void __launch_bounds__(256) estPlanKernel(EstArgs a, TreeDev t, Model
 	if (lane == 0) a.items[i] = it;
 }
 
+#ifdef HU_PROF // build-time instrumentation: phase clocks of consumer thread 0 of CTA 0
+__device__ unsigned long long huProfEst[16];
+#define ESTP_MARK(i) do { if (blockIdx.x == 0 && tid == 0) { const long long now_ = clock64(); atomicAdd(&huProfEst[i], (unsigned long long) (now_ - pt_)); pt_ = now_; } } while (0)
+extern "C" void hu_prof_est(unsigned long long* out) { cudaMemcpyFromSymbol(out, huProfEst, sizeof(huProfEst)); }
+#else
+#define ESTP_MARK(i) do {} while (0)
+#endif
+
 struct EstSmem {
 	double ring[HU_EST_STAGES][2][HU_EST_CH * 4]; // U chunk, V chunk
 	EstItemP rec[2];                              // cDist, ratio, P(wur), P(wvr) of the staged items (bulk-copied)
@@ -214,10 +222,18 @@ __global__ void __launch_bounds__(HU_EST_THREADS, 2) estimateStagedKernel(EstArg
 	for (int k = 1; k < 4; ++k) if (m.logPi[k] > m.logPi[piMax]) piMax = k;
 	const double wGap = m.pi[piMax] / ((m.pi[0] + m.pi[1]) + (m.pi[2] + m.pi[3])); // inferWeight(log pi) at its arg-max
 	int st = 0, ph = 0, h = 0, hph = 0;
+#ifdef HU_PROF
+	long long pt_ = clock64();
+#endif
 	for (;;) {
+		ESTP_MARK(5);
 		mbarWait(&sm.hfull[h], hph);
+		ESTP_MARK(0);
 		const EstItem it = sm.meta[h];
 		if (it.kind == 0) break;
+#ifdef HU_PROF
+		if (blockIdx.x == 0 && tid == 0) { atomicAdd(&huProfEst[8], 1ull); atomicAdd(&huProfEst[9], (unsigned long long) it.W); }
+#endif
 		const int W = it.W;
 		const int8_t* x = hdrS + (size_t) h * hdrPitch + sm.hoff[h];
 		const int sw = (tid >> 2) & 1;
@@ -229,6 +245,7 @@ __global__ void __launch_bounds__(HU_EST_THREADS, 2) estimateStagedKernel(EstArg
 		double dW = 0, nW = 0; // weighted variant: sums of w1 w2 over mismatching / all columns (cpp:1034-1052)
 		for (int c0 = 0; c0 < W; c0 += HU_EST_CH) {
 			mbarWait(&sm.full[st], ph);
+			ESTP_MARK(1);
 			const int c = c0 + tid;
 			if (c < W) {
 				double eu[4], ev[4], ya[4], yb[4], g[4];
@@ -250,6 +267,7 @@ __global__ void __launch_bounds__(HU_EST_THREADS, 2) estimateStagedKernel(EstArg
 			__syncwarp();
 			if (lane == 0) mbarArrive(&sm.empty[st]);
 			if (++st == HU_EST_STAGES) { st = 0; ph ^= 1; }
+			ESTP_MARK(2);
 		}
 		for (int o = 16; o > 0; o >>= 1) diff += __shfl_xor_sync(0xffffffffu, diff, o);
 		if (lane == 0) sm.redB[warp] = diff;
@@ -278,6 +296,7 @@ __global__ void __launch_bounds__(HU_EST_THREADS, 2) estimateStagedKernel(EstArg
 			}
 		}
 		consumerSync(HU_EST_CONS);
+		ESTP_MARK(3);
 		// ---- pass 2: treeLoglik(pi, UPr + VPr + NPr) ----
 		// sum of logs as the log of a running product: one log per thread instead of one per column (the product of
 		// the <= 6 factors of a thread is flushed long before it could underflow)
@@ -314,6 +333,7 @@ __global__ void __launch_bounds__(HU_EST_THREADS, 2) estimateStagedKernel(EstArg
 		}
 		h ^= 1;
 		if (h == 0) hph ^= 1;
+		ESTP_MARK(4);
 	}
 }
 

@@ -321,7 +321,18 @@ __global__ void __launch_bounds__(HU_SEL_THREADS) seedSelectKernel(SeedArgs a, i
 // of the latter, which prefix counts over the bitmaps decide for every element at once.
 #define HU_LIT_THREADS 512
 #define HU_LIT_UNROLL 8 // key loads in flight per lane in the flag passes
+#define HU_LIT_ROWS 4   // 32-position rows a warp has in flight while it materialises the first left part
 #define HU_LIT_SMALL 256 // ranges up to this size are finished by one thread on a shared-memory copy, literally
+
+#ifdef HU_PROF // build-time instrumentation (HU_PROF=1 python -m hmmufotu_b200.build --force): phase clocks of CTA 0
+__device__ unsigned long long huProfSeed[16];
+#define LITP_MARK(i) do { if (blockIdx.x == 0 && tid == 0) { const long long now_ = clock64(); atomicAdd(&huProfSeed[i], (unsigned long long) (now_ - pt_)); pt_ = now_; } } while (0)
+#define LITP_COUNT(i) do { if (blockIdx.x == 0 && tid == 0) atomicAdd(&huProfSeed[i], 1ull); } while (0)
+extern "C" void hu_prof_seed(unsigned long long* out) { cudaMemcpyFromSymbol(out, huProfSeed, sizeof(huProfSeed)); }
+#else
+#define LITP_MARK(i) do {} while (0)
+#define LITP_COUNT(i) do {} while (0)
+#endif
 
 typedef unsigned long long lit_t;               // (key << 32) | candidate position; only the key is compared
 #define LIT_KEY(v) ((uint32_t) ((v) >> 32))
@@ -374,6 +385,30 @@ __device__ __forceinline__ int litSelect(const uint32_t* bits, const uint32_t* p
 	return lo * 32 + (int) __fns(bits[lo], 0, (int) (k - pre[lo]) + 1);
 }
 
+// number of swaps of a partition, this thread's words [w0, w1): left stops whose rank-mate on the right lies to their
+// right.  The test is monotone along the array, so a word whose highest left stop passes counts whole and the
+// first word that does not ends the walk.
+__device__ __forceinline__ uint32_t litCountSwaps(const uint32_t* faW, const uint32_t* fbW, const uint32_t* preA, const uint32_t* preB,
+		int w0, int w1, uint32_t totB) {
+	uint32_t myK = 0;
+	for (int wd = w0; wd < w1; ++wd) {
+		uint32_t bits = faW[wd];
+		if (!bits) continue;
+		const int hb = 31 - __clz(bits);
+		if (totB - (preB[wd] + __popc(fbW[wd] & (0xFFFFFFFFu >> (31 - hb)))) > preA[wd] + __popc(bits) - 1) { myK += __popc(bits); continue; }
+		while (bits) {
+			const int bit = __ffs(bits) - 1;
+			bits &= bits - 1;
+			const uint32_t rankA = preA[wd] + __popc(faW[wd] & ((1u << bit) - 1u));
+			const uint32_t bIncl = preB[wd] + __popc(fbW[wd] & (0xFFFFFFFFu >> (31 - bit)));
+			if (totB - bIncl > rankA) myK++;
+			else break;
+		}
+		break;
+	}
+	return myK;
+}
+
 __global__ void __launch_bounds__(HU_LIT_THREADS) seedSortLiteralKernel(SeedArgs a, int n, int pitch, const int* __restrict__ nodeOfPos,
 		lit_t* __restrict__ scratch, int maxWords) {
 	extern __shared__ uint32_t smLit[];
@@ -389,8 +424,13 @@ __global__ void __launch_bounds__(HU_LIT_THREADS) seedSortLiteralKernel(SeedArgs
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const int nWarps = HU_LIT_THREADS / 32;
 	lit_t* w = scratch + (size_t) blockIdx.x * pitch;
+#ifdef HU_PROF
+	long long pt_ = clock64();
+#endif
 	for (int r = blockIdx.x; r < a.nReads; r += gridDim.x) {
 		__syncthreads();
+		LITP_MARK(7);
+		LITP_COUNT(8);
 		if (a.winStart[r] < 0 || n < 1) {
 			if (tid == 0) a.nSeeds[r] = 0;
 			continue;
@@ -449,6 +489,7 @@ __global__ void __launch_bounds__(HU_LIT_THREADS) seedSortLiteralKernel(SeedArgs
 			}
 			if (pv != 0xFFFFFFFFu) mx = max(mx, pv);
 			__syncthreads();
+			LITP_MARK(0);
 			const int seg = (nW + HU_LIT_THREADS - 1) / HU_LIT_THREADS;
 			const int w0 = tid * seg, w1 = min(nW, w0 + seg);
 			uint32_t sa = 0, sb = 0;
@@ -468,18 +509,7 @@ __global__ void __launch_bounds__(HU_LIT_THREADS) seedSortLiteralKernel(SeedArgs
 			if (tid == 0) sK = 0;
 			__syncthreads();
 			const uint32_t totA = sTot[0], totB = sTot[1];
-			uint32_t myK = 0;
-			for (int wd = w0; wd < w1; ++wd) {
-				uint32_t bits = faW[wd];
-				while (bits) {
-					const int bit = __ffs(bits) - 1;
-					bits &= bits - 1;
-					const uint32_t rankA = preA[wd] + __popc(faW[wd] & ((1u << bit) - 1u));
-					const uint32_t bIncl = preB[wd] + __popc(fbW[wd] & (0xFFFFFFFFu >> (31 - bit)));
-					if (totB - bIncl > rankA) myK++;
-					else bits = 0;
-				}
-			}
+			const uint32_t myK = litCountSwaps(faW, fbW, preA, preB, w0, w1, totB);
 			if (myK) atomicAdd(&sK, myK);
 			__syncthreads();
 			const uint32_t K = sK;
@@ -490,47 +520,57 @@ __global__ void __launch_bounds__(HU_LIT_THREADS) seedSortLiteralKernel(SeedArgs
 				sCut = cut;
 			}
 			__syncthreads();
+			LITP_MARK(1);
 			const int cut = sCut;
 			if (cut >= want) {
 				// materialise [0, cut): a left stop of rank k takes the k-th right stop (from the right), the rest stay
 				if (tid == 0) w[0] = ((lit_t) pv << 32) | (uint32_t) mS;
-				const int per = (cut - 1 + HU_LIT_THREADS - 1) / HU_LIT_THREADS;
-				const int p0 = 1 + tid * per, p1 = min(cut, p0 + per);
-				if (p0 < p1) {
-					const int t0 = p0 - base;
-					uint32_t k = preA[t0 >> 5] + __popc(faW[t0 >> 5] & ((1u << (t0 & 31)) - 1u)); // left stops before p0
-					int pb = -1;
-					for (int q0 = p0; q0 < p1; q0 += HU_LIT_UNROLL) {
-						// sources of a batch first (shared-memory walk), then all key loads, then all stores
-						int srcp[HU_LIT_UNROLL];
+				// (a) the K right stops that move, listed by their rank from the right: posB[k] = bit index of B_k.  The
+				//     list lives in the part of this CTA's scratch row that level 1 never fills (K <= n - cut).
+				uint32_t* posB = reinterpret_cast<uint32_t*>(w + cut);
+				for (int wd = nW - 1 - tid; wd >= 0; wd -= HU_LIT_THREADS) {
+					uint32_t bits = fbW[wd];
+					uint32_t rr = totB - preB[wd] - __popc(bits); // rank from the right of the word's highest set bit
+					if (rr >= K) continue;                        // uniform enough: words left of B_{K-1} carry nothing
+					while (bits) {
+						const int bit = 31 - __clz(bits);
+						bits &= ~(1u << bit);
+						if (rr < K) posB[rr] = (uint32_t) (wd * 32 + bit);
+						rr++;
+					}
+				}
+				__syncthreads();
+				// (b) rows of 32 positions, lane = position: what stays is copied, a left stop of rank k takes B_k.
+				//     Consecutive lanes read consecutive list entries and neighbouring keys, and write one 256-byte line.
+				const int nWc = (cut - 1 + 31) / 32;
+				for (int wdq = warp; wdq < nWc; wdq += nWarps * HU_LIT_ROWS) {
+					int srcp[HU_LIT_ROWS];
+					const uint32_t* lp[HU_LIT_ROWS];
 #pragma unroll
-						for (int u = 0; u < HU_LIT_UNROLL; ++u) {
-							const int pp = q0 + u;
-							srcp[u] = pp;
-							if (pp < p1) {
-								const int t = pp - base;
-								if ((faW[t >> 5] >> (t & 31)) & 1u) {
-									if (pb < 0) pb = litSelect(fbW, preB, nW, totB - 1 - k);
-									else { // previous set bit of fb before pb
-										int wd = pb >> 5;
-										uint32_t bits = fbW[wd] & ((1u << (pb & 31)) - 1u);
-										while (!bits) bits = fbW[--wd];
-										pb = wd * 32 + 31 - __clz(bits);
-									}
-									srcp[u] = base + pb;
-									k++;
-								}
-							}
+					for (int u = 0; u < HU_LIT_ROWS; ++u) {
+						const int wd = min(wdq + u * nWarps, nWc - 1);
+						const uint32_t fa = faW[wd];
+						srcp[u] = base + wd * 32 + lane;
+						const bool mine = srcp[u] < cut && ((fa >> lane) & 1u);
+						lp[u] = mine ? posB + (preA[wd] + __popc(fa & ((1u << lane) - 1u))) : reinterpret_cast<const uint32_t*>(w);
+						if (!mine) srcp[u] = -srcp[u]; // stays
+					}
+					uint32_t pk[HU_LIT_ROWS];
+#pragma unroll
+					for (int u = 0; u < HU_LIT_ROWS; ++u) pk[u] = ldKeyNow(lp[u]);
+#pragma unroll
+					for (int u = 0; u < HU_LIT_ROWS; ++u) srcp[u] = srcp[u] < 0 ? -srcp[u] : base + (int) pk[u];
+					uint32_t kv[HU_LIT_ROWS];
+#pragma unroll
+					for (int u = 0; u < HU_LIT_ROWS; ++u) kv[u] = ldKeyNow(keys + min(srcp[u], n - 1));
+#pragma unroll
+					for (int u = 0; u < HU_LIT_ROWS; ++u) {
+						const int wd = wdq + u * nWarps;
+						const int pp = base + wd * 32 + lane;
+						if (wd < nWc && pp < cut) {
+							const int pq = srcp[u];
+							w[pp] = ((lit_t) (pq == mS ? k0v : kv[u]) << 32) | (uint32_t) VPOS(pq);
 						}
-						uint32_t kv[HU_LIT_UNROLL];
-#pragma unroll
-						for (int u = 0; u < HU_LIT_UNROLL; ++u) kv[u] = keys[min(srcp[u], n - 1)];
-#pragma unroll
-						for (int u = 0; u < HU_LIT_UNROLL; ++u)
-							if (q0 + u < p1) {
-								const int pq = srcp[u];
-								w[q0 + u] = ((lit_t) (pq == mS ? k0v : kv[u]) << 32) | (uint32_t) VPOS(pq);
-							}
 					}
 				}
 				if (tid == 0) {
@@ -547,6 +587,7 @@ __global__ void __launch_bounds__(HU_LIT_THREADS) seedSortLiteralKernel(SeedArgs
 #undef VPOS
 		}
 		__syncthreads();
+		LITP_MARK(2);
 		atomicMax(&sMaxQ, mx);
 		if (!started && tid == 0) {
 			stack[0][0] = 0; stack[0][1] = n; stack[0][2] = depth0;
@@ -587,6 +628,8 @@ __global__ void __launch_bounds__(HU_LIT_THREADS) seedSortLiteralKernel(SeedArgs
 					__syncthreads();
 					for (int i = tid; i < m; i += HU_LIT_THREADS) w[lo + i] = sbuf[i];
 					__syncthreads();
+					LITP_MARK(6);
+					LITP_COUNT(10);
 					continue;
 				}
 				// __move_median_to_first(lo, lo+1, mid, hi-1): every thread reads the three candidates and w[lo] itself
@@ -629,6 +672,8 @@ __global__ void __launch_bounds__(HU_LIT_THREADS) seedSortLiteralKernel(SeedArgs
 					}
 				}
 				__syncthreads();
+				LITP_MARK(3);
+				LITP_COUNT(9);
 				if (tid == 0) { w[lo] = wmKeep; w[mS] = w0Keep; } // every thread has read the four elements by now
 				// exclusive prefix counts per word
 				const int seg = (nW + HU_LIT_THREADS - 1) / HU_LIT_THREADS;
@@ -651,18 +696,7 @@ __global__ void __launch_bounds__(HU_LIT_THREADS) seedSortLiteralKernel(SeedArgs
 				__syncthreads();
 				const uint32_t totA = sTot[0], totB = sTot[1];
 				// K = number of swaps: the k-th left stop (k-th element >= pivot) lies left of the k-th right stop
-				uint32_t myK = 0;
-				for (int wd = w0; wd < w1; ++wd) {
-					uint32_t bits = faW[wd];
-					while (bits) {
-						const int bit = __ffs(bits) - 1;
-						bits &= bits - 1;
-						const uint32_t rankA = preA[wd] + __popc(faW[wd] & ((1u << bit) - 1u));
-						const uint32_t bIncl = preB[wd] + __popc(fbW[wd] & (0xFFFFFFFFu >> (31 - bit)));
-						if (totB - bIncl > rankA) myK++;
-						else bits = 0; // monotone: no later element qualifies
-					}
-				}
+				const uint32_t myK = litCountSwaps(faW, fbW, preA, preB, w0, w1, totB);
 				if (myK) atomicAdd(&sK, myK);
 				__syncthreads();
 				const uint32_t K = sK;
@@ -673,6 +707,7 @@ __global__ void __launch_bounds__(HU_LIT_THREADS) seedSortLiteralKernel(SeedArgs
 					sCut = cut;
 				}
 				__syncthreads();
+				LITP_MARK(4);
 				const bool full = sCut < want; // the right part is needed too: swap instead of copy
 				// swap k: k-th left stop <-> k-th right stop.  Each thread takes a contiguous run of k and walks the
 				// two bitmaps from its first pair (fa forwards, fb backwards).
@@ -710,9 +745,11 @@ __global__ void __launch_bounds__(HU_LIT_THREADS) seedSortLiteralKernel(SeedArgs
 					sHi = sCut;
 				}
 				__syncthreads();
+				LITP_MARK(5);
 			}
 			__syncthreads();
 		}
+		LITP_MARK(11);
 		// __final_insertion_sort restricted to what can reach the first `want` positions: blocks are at most 16
 		// long and ordered among themselves, and an insertion never crosses a block boundary.  Nothing at or beyond a
 		// dropped cut may be touched.
