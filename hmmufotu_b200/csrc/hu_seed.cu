@@ -321,8 +321,11 @@ __global__ void __launch_bounds__(HU_SEL_THREADS) seedSelectKernel(SeedArgs a, i
 // of the latter, which prefix counts over the bitmaps decide for every element at once.
 #define HU_LIT_THREADS 512
 #define HU_LIT_UNROLL 8 // key loads in flight per lane in the flag passes
+#define HU_LIT_VEC 8    // 128-bit key loads a lane has in flight in the first flag pass
 #define HU_LIT_ROWS 4   // 32-position rows a warp has in flight while it materialises the first left part
-#define HU_LIT_SMALL 256 // ranges up to this size are finished by one thread on a shared-memory copy, literally
+#define HU_LIT_SWAPS 4  // swaps a thread has in flight in the swap phase of the later levels
+#define HU_LIT_SMALL 256 // ranges up to this size (<= 1024: one bitmap word per lane) are finished by one warp in shared memory
+#define HU_LIT_SMEM 8192 // once the range that holds the wanted prefix is this small it moves to shared memory for good
 
 #ifdef HU_PROF // build-time instrumentation (HU_PROF=1 python -m hmmufotu_b200.build --force): phase clocks of CTA 0
 __device__ unsigned long long huProfSeed[16];
@@ -344,11 +347,72 @@ __device__ __forceinline__ uint32_t ldKeyNow(const uint32_t* p) {
 	asm volatile("ld.global.u32 %0, [%1];" : "=r"(v) : "l"(p));
 	return v;
 }
-__device__ __forceinline__ uint32_t ldPairKeyNow(const unsigned long long* p) { // high word of a (key, position) pair
-	uint32_t v;
-	asm volatile("ld.global.u32 %0, [%1+4];" : "=r"(v) : "l"(p));
+__device__ __forceinline__ unsigned long long ldPairNow(const unsigned long long* p) {
+	unsigned long long v;
+	asm volatile("ld.global.u64 %0, [%1];" : "=l"(v) : "l"(p));
 	return v;
 }
+__device__ __forceinline__ uint4 ldKey4Now(const uint32_t* p) {
+	uint4 v;
+	asm volatile("ld.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+	return v;
+}
+__device__ __forceinline__ uint32_t ldPairKeyNow(const unsigned long long* p) { // high word of a (key, position) pair
+	uint32_t v;
+	asm volatile("ld.u32 %0, [%1+4];" : "=r"(v) : "l"(p)); // generic address: the later levels also run on a shared-memory copy
+	return v;
+}
+
+// Batches of loads as ONE asm statement: ptxas otherwise re-serialises a run of independent loads into load / use
+// pairs when registers are tight, and the passes that use these are bound by load latency.
+__device__ __forceinline__ void ldKey4x8(const uint32_t* p, uint4 (&v)[8]) { // eight 128-bit loads, 8192 bytes apart
+	asm volatile(
+		"ld.global.v4.u32 {%0, %1, %2, %3}, [%32];\n\t"
+		"ld.global.v4.u32 {%4, %5, %6, %7}, [%32+8192];\n\t"
+		"ld.global.v4.u32 {%8, %9, %10, %11}, [%32+16384];\n\t"
+		"ld.global.v4.u32 {%12, %13, %14, %15}, [%32+24576];\n\t"
+		"ld.global.v4.u32 {%16, %17, %18, %19}, [%32+32768];\n\t"
+		"ld.global.v4.u32 {%20, %21, %22, %23}, [%32+40960];\n\t"
+		"ld.global.v4.u32 {%24, %25, %26, %27}, [%32+49152];\n\t"
+		"ld.global.v4.u32 {%28, %29, %30, %31}, [%32+57344];"
+		: "=r"(v[0].x), "=r"(v[0].y), "=r"(v[0].z), "=r"(v[0].w), "=r"(v[1].x), "=r"(v[1].y), "=r"(v[1].z), "=r"(v[1].w),
+		  "=r"(v[2].x), "=r"(v[2].y), "=r"(v[2].z), "=r"(v[2].w), "=r"(v[3].x), "=r"(v[3].y), "=r"(v[3].z), "=r"(v[3].w),
+		  "=r"(v[4].x), "=r"(v[4].y), "=r"(v[4].z), "=r"(v[4].w), "=r"(v[5].x), "=r"(v[5].y), "=r"(v[5].z), "=r"(v[5].w),
+		  "=r"(v[6].x), "=r"(v[6].y), "=r"(v[6].z), "=r"(v[6].w), "=r"(v[7].x), "=r"(v[7].y), "=r"(v[7].z), "=r"(v[7].w)
+		: "l"(p));
+}
+__device__ __forceinline__ void ldPairKeyx8(const unsigned long long* p, uint32_t (&v)[8]) { // high words of eight pairs, 4096 bytes apart (generic address)
+	asm volatile(
+		"ld.u32 %0, [%8+4];\n\t"
+		"ld.u32 %1, [%8+4100];\n\t"
+		"ld.u32 %2, [%8+8196];\n\t"
+		"ld.u32 %3, [%8+12292];\n\t"
+		"ld.u32 %4, [%8+16388];\n\t"
+		"ld.u32 %5, [%8+20484];\n\t"
+		"ld.u32 %6, [%8+24580];\n\t"
+		"ld.u32 %7, [%8+28676];"
+		: "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+		: "l"(p));
+}
+__device__ __forceinline__ void ldKeyx4(const uint32_t* p0, const uint32_t* p1, const uint32_t* p2, const uint32_t* p3, uint32_t (&v)[4]) {
+	asm volatile(
+		"ld.global.u32 %0, [%4];\n\t"
+		"ld.global.u32 %1, [%5];\n\t"
+		"ld.global.u32 %2, [%6];\n\t"
+		"ld.global.u32 %3, [%7];"
+		: "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "l"(p0), "l"(p1), "l"(p2), "l"(p3));
+}
+__device__ __forceinline__ void ldPairx4(const unsigned long long* p0, const unsigned long long* p1, const unsigned long long* p2,
+		const unsigned long long* p3, unsigned long long (&v)[4]) {
+	asm volatile(
+		"ld.u64 %0, [%4];\n\t"
+		"ld.u64 %1, [%5];\n\t"
+		"ld.u64 %2, [%6];\n\t"
+		"ld.u64 %3, [%7];"
+		: "=l"(v[0]), "=l"(v[1]), "=l"(v[2]), "=l"(v[3]) : "l"(p0), "l"(p1), "l"(p2), "l"(p3));
+}
+static_assert(HU_LIT_THREADS == 512 && HU_LIT_VEC == 8 && HU_LIT_UNROLL == 8 && HU_LIT_ROWS == 4 && HU_LIT_SWAPS == 4,
+              "the batch loaders above spell out these strides and counts");
 
 template <typename Arr>
 __device__ __forceinline__ void litSwap(Arr& w, int x, int y) { const lit_t t = w[x]; w[x] = w[y]; w[y] = t; }
@@ -375,6 +439,16 @@ __device__ __forceinline__ int litPartitionSeq(Arr& w, int first, int last, int 
 		++first;
 	}
 }
+// n-th (0-based, from bit 0) set bit of a word: five popc steps (the __fns intrinsic is a long dependent sequence)
+__device__ __forceinline__ int litNthBit(uint32_t bits, int n) {
+	int pos = 0, c;
+	c = __popc(bits & 0xFFFFu); if (n >= c) { n -= c; pos += 16; bits >>= 16; }
+	c = __popc(bits & 0xFFu); if (n >= c) { n -= c; pos += 8; bits >>= 8; }
+	c = __popc(bits & 0xFu); if (n >= c) { n -= c; pos += 4; bits >>= 4; }
+	c = __popc(bits & 0x3u); if (n >= c) { n -= c; pos += 2; bits >>= 2; }
+	c = (int) (bits & 1u); if (n >= c) pos += 1;
+	return pos;
+}
 // k-th (0-based) set bit of a bitmap with exclusive per-word prefix counts
 __device__ __forceinline__ int litSelect(const uint32_t* bits, const uint32_t* pre, int nWords, uint32_t k) {
 	int lo = 0, hi = nWords - 1;
@@ -382,7 +456,7 @@ __device__ __forceinline__ int litSelect(const uint32_t* bits, const uint32_t* p
 		const int mid = (lo + hi + 1) >> 1;
 		if (pre[mid] <= k) lo = mid; else hi = mid - 1;
 	}
-	return lo * 32 + (int) __fns(bits[lo], 0, (int) (k - pre[lo]) + 1);
+	return lo * 32 + litNthBit(bits[lo], (int) (k - pre[lo]));
 }
 
 // number of swaps of a partition, this thread's words [w0, w1): left stops whose rank-mate on the right lies to their
@@ -409,14 +483,90 @@ __device__ __forceinline__ uint32_t litCountSwaps(const uint32_t* faW, const uin
 	return myK;
 }
 
+// __introsort_loop (bits/stl_algo.h) on sbuf[0, m), m <= 1024, by one warp: the same literal data movement as the
+// CTA-wide levels (Hoare partition evaluated from the two bitmaps), with one bitmap word per lane, prefix counts by
+// warp scan and no block barrier.  Sub-ranges that start at or beyond `want` (global position lo + l) are dropped.
+// wsc: 128 words of shared scratch (fa, fb words and their exclusive prefix counts, for cross-lane selects).
+__device__ __noinline__ void litWarpIntrosort(lit_t* sbuf, uint32_t* wsc, int m, int depth, int lo, int want, int* overflow) {
+	const int lane = threadIdx.x & 31;
+	int st[24][3], top = 0;
+	st[0][0] = 0; st[0][1] = m; st[0][2] = depth; top = 1;
+	while (top > 0) {
+		top--;
+		int l = st[top][0], h = st[top][1], dep = st[top][2];
+		while (h - l > 16 && lo + l < want) {
+			if (dep == 0) { if (lane == 0) *overflow = 1; break; }
+			dep--;
+			if (lane == 0) litMedianToFirst(sbuf, l, l + 1, l + (h - l) / 2, h - 1);
+			__syncwarp();
+			const uint32_t pv = LIT_KEY(sbuf[l]);
+			const int base = l + 1, cnt = h - base, nWs = (cnt + 31) / 32;
+			uint32_t myA = 0, myB = 0;
+			for (int r = 0; r < nWs; ++r) {
+				const int t = r * 32 + lane;
+				const bool ok = t < cnt;
+				const uint32_t v = ok ? LIT_KEY(sbuf[base + t]) : 0u;
+				const uint32_t ba = __ballot_sync(0xffffffffu, ok && !(v < pv));
+				const uint32_t bb = __ballot_sync(0xffffffffu, ok && !(pv < v));
+				if (lane == r) { myA = ba; myB = bb; }
+			}
+			uint32_t xa = __popc(myA), xb = __popc(myB);
+			for (int o = 1; o < 32; o <<= 1) {
+				const uint32_t ya = __shfl_up_sync(0xffffffffu, xa, o), yb = __shfl_up_sync(0xffffffffu, xb, o);
+				if (lane >= o) { xa += ya; xb += yb; }
+			}
+			const uint32_t preA = xa - __popc(myA), preB = xb - __popc(myB);
+			const uint32_t totA = __shfl_sync(0xffffffffu, xa, 31), totB = __shfl_sync(0xffffffffu, xb, 31);
+			uint32_t K = 0;
+			for (uint32_t bits = myA; bits;) {
+				const int bit = __ffs(bits) - 1;
+				bits &= bits - 1;
+				const uint32_t rankA = preA + __popc(myA & ((1u << bit) - 1u));
+				const uint32_t bIncl = preB + __popc(myB & (0xFFFFFFFFu >> (31 - bit)));
+				if (totB - bIncl > rankA) K++;
+				else break;
+			}
+			for (int o = 16; o > 0; o >>= 1) K += __shfl_xor_sync(0xffffffffu, K, o);
+			wsc[lane] = myA; wsc[32 + lane] = myB; wsc[64 + lane] = preA; wsc[96 + lane] = preB;
+			__syncwarp();
+			const int AK = K < totA ? base + litSelect(wsc, wsc + 64, 32, K) : h;
+			int cut = AK;
+			if (K >= 1) cut = min(AK, base + litSelect(wsc + 32, wsc + 96, 32, totB - K));
+			// swap k: k-th left stop <-> k-th right stop (from the right); a lane takes the left stops of its own word
+			if (myA && preA < K) {
+				int pb = litSelect(wsc + 32, wsc + 96, 32, totB - 1 - preA); // right stop of this lane's first left stop
+				uint32_t k = preA;
+				for (uint32_t bits = myA; bits && k < K; ++k) {
+					const int bit = __ffs(bits) - 1;
+					bits &= bits - 1;
+					litSwap(sbuf, base + lane * 32 + bit, base + pb);
+					if (bits && k + 1 < K) { // previous set bit of fb before pb
+						int wd = pb >> 5;
+						uint32_t bb = wsc[32 + wd] & ((1u << (pb & 31)) - 1u);
+						while (!bb) bb = wsc[32 + --wd];
+						pb = wd * 32 + 31 - __clz(bb);
+					}
+				}
+			}
+			__syncwarp();
+			if (lo + cut < want && top < 24) { st[top][0] = cut; st[top][1] = h; st[top][2] = dep; top++; }
+			h = cut;
+		}
+	}
+	__syncwarp();
+}
+
 __global__ void __launch_bounds__(HU_LIT_THREADS) seedSortLiteralKernel(SeedArgs a, int n, int pitch, const int* __restrict__ nodeOfPos,
 		lit_t* __restrict__ scratch, int maxWords) {
-	extern __shared__ uint32_t smLit[];
+	extern __shared__ __align__(16) uint32_t smLit[];
 	uint32_t* faW = smLit;              // elements >= pivot  (!(x < pivot))
 	uint32_t* fbW = faW + maxWords;     // elements <= pivot  (!(pivot < x))
 	uint32_t* preA = fbW + maxWords;    // exclusive prefix counts per word
 	uint32_t* preB = preA + maxWords;
+	// shared-memory mode (ranges <= HU_LIT_SMEM): four bitmaps of HU_LIT_SMEM / 32 words, then the range itself
+	lit_t* const sdata = reinterpret_cast<lit_t*>(smLit + 4 * (HU_LIT_SMEM / 32));
 	__shared__ lit_t sbuf[HU_LIT_SMALL];
+	__shared__ uint32_t wsc[128];
 	__shared__ uint32_t red[HU_LIT_THREADS / 32][2];
 	__shared__ uint32_t sTot[2], sK, sMaxQ;
 	__shared__ int sCut, sLo, sHi, sDepth, sTop, sOverflow, sBound;
@@ -437,6 +587,10 @@ __global__ void __launch_bounds__(HU_LIT_THREADS) seedSortLiteralKernel(SeedArgs
 		}
 		const uint32_t* keys = a.keys + (size_t) r * pitch;
 		const int want = min(a.maxNSeed, n);
+		faW = smLit; fbW = faW + maxWords; preA = fbW + maxWords; preB = preA + maxWords;
+		lit_t* wp = w;            // where positions live: the scratch row, or (shared-memory mode) sdata - smLo
+		bool inSm = false;
+		int smLo = 0, smHi = 0;
 		// Level 1 straight from the key vector when the array is large: flags, cut, then only the left part
 		// [0, cut) is materialised as (key, position) pairs -- the right part is never needed (cut >= want).
 		const bool direct = n > 4 * HU_LIT_SMALL;
@@ -463,30 +617,42 @@ __global__ void __launch_bounds__(HU_LIT_THREADS) seedSortLiteralKernel(SeedArgs
 			const uint32_t pv = keys[mS], k0v = keys[0];
 #define VKEY(p) ((p) == mS ? k0v : keys[p])
 #define VPOS(p) ((p) == mS ? 0 : (p))
-			const int base = 1, cnt = n - 1, nW = (cnt + 31) / 32;
-			// HU_LIT_UNROLL independent key loads per lane and trip: the pass is bound by load latency, not bandwidth
-			for (int wd0 = warp; wd0 < nW; wd0 += nWarps * HU_LIT_UNROLL) {
-				uint32_t vv[HU_LIT_UNROLL];
+			// Bit p of the two bitmaps is position p itself (bit 0, the pivot's slot, stays clear), so that the key vector
+			// can be read with aligned 128-bit loads: HU_LIT_VEC of them in flight per lane (the pass is bound by load
+			// latency).  A lane's four flags form a nibble; three exchanges assemble the words of eight lanes.
+			const int base = 0, nW = (n + 31) / 32, nCh = (n + 127) / 128;
+#define LIT_FLAG_CHUNK(ch, val) { \
+				const uint32_t q_[4] = {(val).x, (val).y, (val).z, (val).w}; \
+				uint32_t na_ = 0, nb_ = 0; \
+				_Pragma("unroll") \
+				for (int c = 0; c < 4; ++c) { \
+					const int pp = (ch) * 128 + 4 * lane + c; \
+					const uint32_t v = pp == mS ? k0v : q_[c]; \
+					const bool ok = pp < n && pp > 0; \
+					if (ok && v != 0xFFFFFFFFu) mx = max(mx, v); \
+					na_ |= (uint32_t) (ok && !(v < pv)) << c; \
+					nb_ |= (uint32_t) (ok && !(pv < v)) << c; \
+				} \
+				uint32_t xa_ = na_ << (4 * (lane & 7)), xb_ = nb_ << (4 * (lane & 7)); \
+				_Pragma("unroll") \
+				for (int o = 1; o < 8; o <<= 1) { \
+					xa_ |= __shfl_xor_sync(0xffffffffu, xa_, o); \
+					xb_ |= __shfl_xor_sync(0xffffffffu, xb_, o); \
+				} \
+				const int wd_ = (ch) * 4 + (lane >> 3); \
+				if ((lane & 7) == 0 && wd_ < nW) { faW[wd_] = xa_; fbW[wd_] = xb_; } }
+			int ch0 = warp;
+			for (; ch0 + (HU_LIT_VEC - 1) * nWarps < nCh; ch0 += nWarps * HU_LIT_VEC) {
+				uint4 vv[HU_LIT_VEC];
+				ldKey4x8(keys + (size_t) ch0 * 128 + 4 * lane, vv);
 #pragma unroll
-				for (int u = 0; u < HU_LIT_UNROLL; ++u) {
-					const int t = (wd0 + u * nWarps) * 32 + lane;
-					vv[u] = ldKeyNow(keys + min(base + t, n - 1)); // always in range: no branch, all of them overlap
-				}
-#pragma unroll
-				for (int u = 0; u < HU_LIT_UNROLL; ++u)
-					if (min(base + (wd0 + u * nWarps) * 32 + lane, n - 1) == mS) vv[u] = k0v;
-#pragma unroll
-				for (int u = 0; u < HU_LIT_UNROLL; ++u) {
-					const int wd = wd0 + u * nWarps;
-					if (wd >= nW) break;
-					const bool ok = wd * 32 + lane < cnt;
-					const uint32_t v = vv[u];
-					if (ok && v != 0xFFFFFFFFu) mx = max(mx, v);
-					const uint32_t ba = __ballot_sync(0xffffffffu, ok && !(v < pv));
-					const uint32_t bb = __ballot_sync(0xffffffffu, ok && !(pv < v));
-					if (lane == 0) { faW[wd] = ba; fbW[wd] = bb; }
-				}
+				for (int u = 0; u < HU_LIT_VEC; ++u) LIT_FLAG_CHUNK(ch0 + u * nWarps, vv[u])
 			}
+			for (; ch0 < nCh; ch0 += nWarps) {
+				const uint4 v1 = ldKey4Now(keys + (size_t) ch0 * 128 + 4 * lane);
+				LIT_FLAG_CHUNK(ch0, v1)
+			}
+#undef LIT_FLAG_CHUNK
 			if (pv != 0xFFFFFFFFu) mx = max(mx, pv);
 			__syncthreads();
 			LITP_MARK(0);
@@ -542,24 +708,30 @@ __global__ void __launch_bounds__(HU_LIT_THREADS) seedSortLiteralKernel(SeedArgs
 				__syncthreads();
 				// (b) rows of 32 positions, lane = position: what stays is copied, a left stop of rank k takes B_k.
 				//     Consecutive lanes read consecutive list entries and neighbouring keys, and write one 256-byte line.
-				const int nWc = (cut - 1 + 31) / 32;
+				const int nWc = (cut + 31) / 32;
+				//     The list entries of the next batch of rows are requested before the keys of this one.
+				int pos[HU_LIT_ROWS]; // > 0: stays there; < 0: a left stop, takes the right stop in pk
+				uint32_t pk[HU_LIT_ROWS];
+				const uint32_t* lp[HU_LIT_ROWS];
+#define LIT_ROW_PLAN(row, u) { \
+					const int wd_ = min((row), nWc - 1); \
+					const uint32_t fa_ = faW[wd_]; \
+					pos[u] = base + wd_ * 32 + lane; \
+					const bool mine_ = pos[u] < cut && ((fa_ >> lane) & 1u); \
+					lp[u] = mine_ ? posB + (preA[wd_] + __popc(fa_ & ((1u << lane) - 1u))) : reinterpret_cast<const uint32_t*>(w); \
+					if (mine_) pos[u] = -pos[u]; }
+#pragma unroll
+				for (int u = 0; u < HU_LIT_ROWS; ++u) LIT_ROW_PLAN(warp + u * nWarps, u)
+#pragma unroll
+				for (int u = 0; u < HU_LIT_ROWS; ++u) pk[u] = ldKeyNow(lp[u]);
 				for (int wdq = warp; wdq < nWc; wdq += nWarps * HU_LIT_ROWS) {
 					int srcp[HU_LIT_ROWS];
-					const uint32_t* lp[HU_LIT_ROWS];
 #pragma unroll
-					for (int u = 0; u < HU_LIT_ROWS; ++u) {
-						const int wd = min(wdq + u * nWarps, nWc - 1);
-						const uint32_t fa = faW[wd];
-						srcp[u] = base + wd * 32 + lane;
-						const bool mine = srcp[u] < cut && ((fa >> lane) & 1u);
-						lp[u] = mine ? posB + (preA[wd] + __popc(fa & ((1u << lane) - 1u))) : reinterpret_cast<const uint32_t*>(w);
-						if (!mine) srcp[u] = -srcp[u]; // stays
-					}
-					uint32_t pk[HU_LIT_ROWS];
+					for (int u = 0; u < HU_LIT_ROWS; ++u) srcp[u] = pos[u] > 0 ? pos[u] : base + (int) pk[u];
+#pragma unroll
+					for (int u = 0; u < HU_LIT_ROWS; ++u) LIT_ROW_PLAN(wdq + nWarps * HU_LIT_ROWS + u * nWarps, u)
 #pragma unroll
 					for (int u = 0; u < HU_LIT_ROWS; ++u) pk[u] = ldKeyNow(lp[u]);
-#pragma unroll
-					for (int u = 0; u < HU_LIT_ROWS; ++u) srcp[u] = srcp[u] < 0 ? -srcp[u] : base + (int) pk[u];
 					uint32_t kv[HU_LIT_ROWS];
 #pragma unroll
 					for (int u = 0; u < HU_LIT_ROWS; ++u) kv[u] = ldKeyNow(keys + min(srcp[u], n - 1));
@@ -567,12 +739,13 @@ __global__ void __launch_bounds__(HU_LIT_THREADS) seedSortLiteralKernel(SeedArgs
 					for (int u = 0; u < HU_LIT_ROWS; ++u) {
 						const int wd = wdq + u * nWarps;
 						const int pp = base + wd * 32 + lane;
-						if (wd < nWc && pp < cut) {
+						if (wd < nWc && pp < cut && pp > 0) { // position 0 holds the pivot
 							const int pq = srcp[u];
 							w[pp] = ((lit_t) (pq == mS ? k0v : kv[u]) << 32) | (uint32_t) VPOS(pq);
 						}
 					}
 				}
+#undef LIT_ROW_PLAN
 				if (tid == 0) {
 					stack[0][0] = 0; stack[0][1] = cut; stack[0][2] = depth0 - 1;
 					sTop = 1;
@@ -603,28 +776,30 @@ __global__ void __launch_bounds__(HU_LIT_THREADS) seedSortLiteralKernel(SeedArgs
 				const int lo = sLo, hi = sHi;
 				if (sDepth == 0) { if (tid == 0) sOverflow = 1; break; } // would fall back to heap sort: not replayed
 				__syncthreads();
+				if (!inSm && sTop == 0 && hi - lo <= HU_LIT_SMEM) {
+					// nothing is pending outside [lo, hi): every later range lies inside it, and it fits in shared memory.
+					// From here on no level waits for global memory.
+					for (int i = tid; i < hi - lo; i += HU_LIT_THREADS) sdata[i] = w[lo + i];
+					faW = smLit; fbW = faW + HU_LIT_SMEM / 32; preA = fbW + HU_LIT_SMEM / 32; preB = preA + HU_LIT_SMEM / 32;
+					wp = sdata - lo;
+					inSm = true; smLo = lo; smHi = hi;
+					__syncthreads();
+				}
+				if (inSm && hi - lo <= HU_LIT_SMALL) {
+					if (warp == 0) litWarpIntrosort(wp + lo, wsc, hi - lo, sDepth, lo, want, &sOverflow);
+					if (tid == 0) sHi = lo; // range finished
+					__syncthreads();
+					LITP_MARK(6);
+					LITP_COUNT(10);
+					continue;
+				}
 				if (hi - lo <= HU_LIT_SMALL) {
-					// the rest of this range, every level of it, by one thread on a shared-memory copy
+					// the rest of this range, every level of it, by one warp on a shared-memory copy
 					const int m = hi - lo;
 					for (int i = tid; i < m; i += HU_LIT_THREADS) sbuf[i] = w[lo + i];
 					__syncthreads();
-					if (tid == 0) {
-						int st[24][3], top = 0;
-						st[0][0] = 0; st[0][1] = m; st[0][2] = sDepth; top = 1;
-						while (top > 0) {
-							top--;
-							int l = st[top][0], h = st[top][1], dep = st[top][2];
-							while (h - l > 16 && lo + l < want) {
-								if (dep == 0) { sOverflow = 1; break; }
-								dep--;
-								litMedianToFirst(sbuf, l, l + 1, l + (h - l) / 2, h - 1);
-								const int cut = litPartitionSeq(sbuf, l + 1, h, l);
-								if (lo + cut < want && top < 24) { st[top][0] = cut; st[top][1] = h; st[top][2] = dep; top++; }
-								h = cut;
-							}
-						}
-						sHi = lo; // range finished
-					}
+					if (warp == 0) litWarpIntrosort(sbuf, wsc, m, sDepth, lo, want, &sOverflow);
+					if (tid == 0) sHi = lo; // range finished
 					__syncthreads();
 					for (int i = tid; i < m; i += HU_LIT_THREADS) w[lo + i] = sbuf[i];
 					__syncthreads();
@@ -640,7 +815,7 @@ __global__ void __launch_bounds__(HU_LIT_THREADS) seedSortLiteralKernel(SeedArgs
 				lit_t wmKeep, w0Keep;
 				{
 					const int ia = lo + 1, ib = lo + (hi - lo) / 2, ic = hi - 1;
-					const lit_t wa = w[ia], wb = w[ib], wc = w[ic], w0 = w[lo];
+					const lit_t wa = wp[ia], wb = wp[ib], wc = wp[ic], w0 = wp[lo];
 					const uint32_t qa = LIT_KEY(wa), qb = LIT_KEY(wb), qc = LIT_KEY(wc);
 					if (qa < qb) mS = qb < qc ? ib : (qa < qc ? ic : ia);
 					else mS = qa < qc ? ia : (qb < qc ? ic : ib);
@@ -650,31 +825,28 @@ __global__ void __launch_bounds__(HU_LIT_THREADS) seedSortLiteralKernel(SeedArgs
 					wmKeep = wm; w0Keep = w0;
 				}
 				const int base = lo + 1, cnt = hi - base, nW = (cnt + 31) / 32;
-				for (int wd0 = warp; wd0 < nW; wd0 += nWarps * HU_LIT_UNROLL) {
+#define LIT_FLAG_ROW(wd, val) { \
+					const int t_ = (wd) * 32 + lane; \
+					const uint32_t v_ = base + t_ == mS ? k0v : (val); \
+					const uint32_t ba_ = __ballot_sync(0xffffffffu, t_ < cnt && !(v_ < pv)); \
+					const uint32_t bb_ = __ballot_sync(0xffffffffu, t_ < cnt && !(pv < v_)); \
+					if (lane == 0) { faW[wd] = ba_; fbW[wd] = bb_; } }
+				int wd0 = warp;
+				for (; wd0 + (HU_LIT_UNROLL - 1) * nWarps < nW - 1; wd0 += nWarps * HU_LIT_UNROLL) { // every row of the batch is whole
 					uint32_t vv[HU_LIT_UNROLL];
+					ldPairKeyx8(wp + base + wd0 * 32 + lane, vv);
 #pragma unroll
-					for (int u = 0; u < HU_LIT_UNROLL; ++u) {
-						const int t = (wd0 + u * nWarps) * 32 + lane;
-						vv[u] = ldPairKeyNow(w + min(base + t, hi - 1)); // always in range: branch-free, overlapping loads
-					}
-#pragma unroll
-					for (int u = 0; u < HU_LIT_UNROLL; ++u)
-						if (base + (wd0 + u * nWarps) * 32 + lane == mS) vv[u] = k0v;
-#pragma unroll
-					for (int u = 0; u < HU_LIT_UNROLL; ++u) {
-						const int wd = wd0 + u * nWarps;
-						if (wd >= nW) break;
-						const bool ok = wd * 32 + lane < cnt;
-						const uint32_t v = vv[u];
-						const uint32_t ba = __ballot_sync(0xffffffffu, ok && !(v < pv));
-						const uint32_t bb = __ballot_sync(0xffffffffu, ok && !(pv < v));
-						if (lane == 0) { faW[wd] = ba; fbW[wd] = bb; }
-					}
+					for (int u = 0; u < HU_LIT_UNROLL; ++u) LIT_FLAG_ROW(wd0 + u * nWarps, vv[u])
 				}
+				for (; wd0 < nW; wd0 += nWarps) {
+					const uint32_t v1 = ldPairKeyNow(wp + min(base + wd0 * 32 + lane, hi - 1));
+					LIT_FLAG_ROW(wd0, v1)
+				}
+#undef LIT_FLAG_ROW
 				__syncthreads();
 				LITP_MARK(3);
 				LITP_COUNT(9);
-				if (tid == 0) { w[lo] = wmKeep; w[mS] = w0Keep; } // every thread has read the four elements by now
+				if (tid == 0) { wp[lo] = wmKeep; wp[mS] = w0Keep; } // every thread has read the four elements by now
 				// exclusive prefix counts per word
 				const int seg = (nW + HU_LIT_THREADS - 1) / HU_LIT_THREADS;
 				const int w0 = tid * seg, w1 = min(nW, w0 + seg);
@@ -717,23 +889,36 @@ __global__ void __launch_bounds__(HU_LIT_THREADS) seedSortLiteralKernel(SeedArgs
 					if (k0 < k1) {
 						int pa = litSelect(faW, preA, nW, k0);            // bit index of the k0-th left stop
 						int pb = litSelect(fbW, preB, nW, totB - 1 - k0); // bit index of the k0-th right stop (from the right)
-						for (uint32_t k = k0; k < k1; ++k) {
-							const int pp = base + pa, pq = base + pb;
-							const lit_t vq = w[pq];
-							if (full) w[pq] = w[pp];
-							w[pp] = vq;
-							if (k + 1 < k1) {
-								// next set bit of fa after pa
-								int wd = pa >> 5;
-								uint32_t bits = faW[wd] & ~(0xFFFFFFFFu >> (31 - (pa & 31)));
-								while (!bits) bits = faW[++wd];
-								pa = wd * 32 + __ffs(bits) - 1;
-								// previous set bit of fb before pb
-								wd = pb >> 5;
-								bits = fbW[wd] & ((1u << (pb & 31)) - 1u);
-								while (!bits) bits = fbW[--wd];
-								pb = wd * 32 + 31 - __clz(bits);
+						for (uint32_t k = k0; k < k1; k += HU_LIT_SWAPS) {
+							// positions of a batch first (bitmap walk in shared memory), then every load, then every store: the
+							// pairs are disjoint, but the compiler cannot know and would wait for each swap in turn
+							int ppv[HU_LIT_SWAPS], pqv[HU_LIT_SWAPS];
+#pragma unroll
+							for (int u = 0; u < HU_LIT_SWAPS; ++u) {
+								ppv[u] = base + pa; pqv[u] = base + pb;
+								if (k + u + 1 < k1) {
+									// next set bit of fa after pa
+									int wd = pa >> 5;
+									uint32_t bits = faW[wd] & ~(0xFFFFFFFFu >> (31 - (pa & 31)));
+									while (!bits) bits = faW[++wd];
+									pa = wd * 32 + __ffs(bits) - 1;
+									// previous set bit of fb before pb
+									wd = pb >> 5;
+									bits = fbW[wd] & ((1u << (pb & 31)) - 1u);
+									while (!bits) bits = fbW[--wd];
+									pb = wd * 32 + 31 - __clz(bits);
+								}
 							}
+							if (full) { // rare (the cut fell inside the wanted prefix): plain swaps
+								for (int u = 0; u < HU_LIT_SWAPS; ++u)
+									if (k + u < k1) litSwap(wp, ppv[u], pqv[u]);
+								continue;
+							}
+							lit_t vq[HU_LIT_SWAPS];
+							ldPairx4(wp + pqv[0], wp + pqv[1], wp + pqv[2], wp + pqv[3], vq); // past k1: the last pair again
+#pragma unroll
+							for (int u = 0; u < HU_LIT_SWAPS; ++u)
+								if (k + u < k1) wp[ppv[u]] = vq[u];
 						}
 					}
 				}
@@ -754,7 +939,7 @@ __global__ void __launch_bounds__(HU_LIT_THREADS) seedSortLiteralKernel(SeedArgs
 		// long and ordered among themselves, and an insertion never crosses a block boundary.  Nothing at or beyond a
 		// dropped cut may be touched.
 		const int P = min(min(n, sBound), want + 17);
-		for (int i = tid; i < P; i += HU_LIT_THREADS) sbuf[i] = w[i];
+		for (int i = tid; i < P; i += HU_LIT_THREADS) sbuf[i] = (inSm && i >= smLo && i < smHi) ? wp[i] : w[i];
 		__syncthreads();
 		{
 			// insertion sort is a stable sort: every element goes straight to (# smaller keys) + (# equal keys before it)
@@ -831,7 +1016,9 @@ int launchSeed(hu_batch* b, const hu_sep_params* p) {
 		int sms = 0;
 		HU_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, db->device));
 		const int maxWords = (t.nCand + 31) / 32 + 1;
-		const size_t smemLit = (size_t) 4 * maxWords * sizeof(uint32_t);
+		// the four bitmaps of the CTA-wide levels, or (shared-memory mode) four small bitmaps and the range itself
+		const size_t smemLit = std::max((size_t) 4 * maxWords * sizeof(uint32_t),
+		                                (size_t) 4 * (HU_LIT_SMEM / 32) * sizeof(uint32_t) + (size_t) std::min(t.nCand, HU_LIT_SMEM) * sizeof(lit_t));
 		if (smemLit > 200 * 1024) { setError("tree too large for the shared-memory bitmaps of the literal seed order (%d nodes)", t.nNodes); return HU_ERR_ARG; }
 		static size_t attrLit = 0;
 		if (smemLit > attrLit) {
