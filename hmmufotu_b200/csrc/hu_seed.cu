@@ -411,7 +411,7 @@ __device__ __forceinline__ void ldPairx4(const unsigned long long* p0, const uns
 		"ld.u64 %3, [%7];"
 		: "=l"(v[0]), "=l"(v[1]), "=l"(v[2]), "=l"(v[3]) : "l"(p0), "l"(p1), "l"(p2), "l"(p3));
 }
-static_assert(HU_LIT_THREADS == 512 && HU_LIT_VEC == 8 && HU_LIT_UNROLL == 8 && HU_LIT_ROWS == 4 && HU_LIT_SWAPS == 4,
+static_assert(HU_LIT_THREADS == 512 && HU_LIT_VEC == 8 && HU_LIT_UNROLL == 8 && HU_LIT_SWAPS == 4,
               "the batch loaders above spell out these strides and counts");
 
 template <typename Arr>
@@ -515,38 +515,26 @@ __device__ __noinline__ void litWarpIntrosort(lit_t* sbuf, uint32_t* wsc, int m,
 				const uint32_t ya = __shfl_up_sync(0xffffffffu, xa, o), yb = __shfl_up_sync(0xffffffffu, xb, o);
 				if (lane >= o) { xa += ya; xb += yb; }
 			}
-			const uint32_t preA = xa - __popc(myA), preB = xb - __popc(myB);
 			const uint32_t totA = __shfl_sync(0xffffffffu, xa, 31), totB = __shfl_sync(0xffffffffu, xb, 31);
-			uint32_t K = 0;
-			for (uint32_t bits = myA; bits;) {
-				const int bit = __ffs(bits) - 1;
-				bits &= bits - 1;
-				const uint32_t rankA = preA + __popc(myA & ((1u << bit) - 1u));
-				const uint32_t bIncl = preB + __popc(myB & (0xFFFFFFFFu >> (31 - bit)));
-				if (totB - bIncl > rankA) K++;
-				else break;
-			}
-			for (int o = 16; o > 0; o >>= 1) K += __shfl_xor_sync(0xffffffffu, K, o);
-			wsc[lane] = myA; wsc[32 + lane] = myB; wsc[64 + lane] = preA; wsc[96 + lane] = preB;
+			wsc[lane] = myA; wsc[32 + lane] = myB; wsc[64 + lane] = xa - __popc(myA); wsc[96 + lane] = xb - __popc(myB);
 			__syncwarp();
-			const int AK = K < totA ? base + litSelect(wsc, wsc + 64, 32, K) : h;
+			// one position per lane and round (a lane walking the 32 bits of its own word would leave the warp idle):
+			// K = number of left stops whose rank-mate on the right lies to their right
+			const uint32_t lt = (1u << lane) - 1u, le = 0xFFFFFFFFu >> (31 - lane);
+			uint32_t K = 0;
+			for (int r = 0; r < nWs; ++r) {
+				const uint32_t fa = wsc[r], fb = wsc[32 + r];
+				const bool q = ((fa >> lane) & 1u) && totB - (wsc[96 + r] + __popc(fb & le)) > wsc[64 + r] + __popc(fa & lt);
+				K += __popc(__ballot_sync(0xffffffffu, q));
+			}
+			const int AK = K < totA ? base + litSelect(wsc, wsc + 64, nWs, K) : h;
 			int cut = AK;
-			if (K >= 1) cut = min(AK, base + litSelect(wsc + 32, wsc + 96, 32, totB - K));
-			// swap k: k-th left stop <-> k-th right stop (from the right); a lane takes the left stops of its own word
-			if (myA && preA < K) {
-				int pb = litSelect(wsc + 32, wsc + 96, 32, totB - 1 - preA); // right stop of this lane's first left stop
-				uint32_t k = preA;
-				for (uint32_t bits = myA; bits && k < K; ++k) {
-					const int bit = __ffs(bits) - 1;
-					bits &= bits - 1;
-					litSwap(sbuf, base + lane * 32 + bit, base + pb);
-					if (bits && k + 1 < K) { // previous set bit of fb before pb
-						int wd = pb >> 5;
-						uint32_t bb = wsc[32 + wd] & ((1u << (pb & 31)) - 1u);
-						while (!bb) bb = wsc[32 + --wd];
-						pb = wd * 32 + 31 - __clz(bb);
-					}
-				}
+			if (K >= 1) cut = min(AK, base + litSelect(wsc + 32, wsc + 96, nWs, totB - K));
+			// swap k: k-th left stop <-> k-th right stop (from the right); the pairs are disjoint
+			for (int r = 0; r < nWs; ++r) {
+				const uint32_t fa = wsc[r];
+				const uint32_t k = wsc[64 + r] + __popc(fa & lt);
+				if (((fa >> lane) & 1u) && k < K) litSwap(sbuf, base + r * 32 + lane, base + litSelect(wsc + 32, wsc + 96, nWs, totB - 1 - k));
 			}
 			__syncwarp();
 			if (lo + cut < want && top < 24) { st[top][0] = cut; st[top][1] = h; st[top][2] = dep; top++; }
@@ -712,18 +700,18 @@ __global__ void __launch_bounds__(HU_LIT_THREADS) seedSortLiteralKernel(SeedArgs
 				//     The list entries of the next batch of rows are requested before the keys of this one.
 				int pos[HU_LIT_ROWS]; // > 0: stays there; < 0: a left stop, takes the right stop in pk
 				uint32_t pk[HU_LIT_ROWS];
-				const uint32_t* lp[HU_LIT_ROWS];
+				uint32_t lp[HU_LIT_ROWS];
 #define LIT_ROW_PLAN(row, u) { \
 					const int wd_ = min((row), nWc - 1); \
 					const uint32_t fa_ = faW[wd_]; \
 					pos[u] = base + wd_ * 32 + lane; \
 					const bool mine_ = pos[u] < cut && ((fa_ >> lane) & 1u); \
-					lp[u] = mine_ ? posB + (preA[wd_] + __popc(fa_ & ((1u << lane) - 1u))) : reinterpret_cast<const uint32_t*>(w); \
+					lp[u] = mine_ ? 2u * (uint32_t) cut + preA[wd_] + __popc(fa_ & ((1u << lane) - 1u)) : 0u; /* word offset from w; posB = w + cut */ \
 					if (mine_) pos[u] = -pos[u]; }
 #pragma unroll
 				for (int u = 0; u < HU_LIT_ROWS; ++u) LIT_ROW_PLAN(warp + u * nWarps, u)
 #pragma unroll
-				for (int u = 0; u < HU_LIT_ROWS; ++u) pk[u] = ldKeyNow(lp[u]);
+				for (int u = 0; u < HU_LIT_ROWS; ++u) pk[u] = ldKeyNow(reinterpret_cast<const uint32_t*>(w) + lp[u]);
 				for (int wdq = warp; wdq < nWc; wdq += nWarps * HU_LIT_ROWS) {
 					int srcp[HU_LIT_ROWS];
 #pragma unroll
@@ -731,7 +719,7 @@ __global__ void __launch_bounds__(HU_LIT_THREADS) seedSortLiteralKernel(SeedArgs
 #pragma unroll
 					for (int u = 0; u < HU_LIT_ROWS; ++u) LIT_ROW_PLAN(wdq + nWarps * HU_LIT_ROWS + u * nWarps, u)
 #pragma unroll
-					for (int u = 0; u < HU_LIT_ROWS; ++u) pk[u] = ldKeyNow(lp[u]);
+					for (int u = 0; u < HU_LIT_ROWS; ++u) pk[u] = ldKeyNow(reinterpret_cast<const uint32_t*>(w) + lp[u]);
 					uint32_t kv[HU_LIT_ROWS];
 #pragma unroll
 					for (int u = 0; u < HU_LIT_ROWS; ++u) kv[u] = ldKeyNow(keys + min(srcp[u], n - 1));
