@@ -154,6 +154,17 @@ ostream& MSA::save(ostream& out) const {
 		out.write(auxBlocks.data(), (streamsize) auxBlocks.size());
 		return out;
 	}
+	if (seqWeight.size() == numSeq && resWCount.size() == (size_t) 4 * csLen && numSeq > 0) { // built here (hu_build.cpp)
+		out.write((const char*) startIdx.data(), sizeof(int) * numSeq);
+		out.write((const char*) endIdx.data(), sizeof(int) * numSeq);
+		out.write((const char*) lenIdx.data(), sizeof(int) * numSeq);
+		out.write((const char*) resCount.data(), sizeof(int) * resCount.size());
+		out.write((const char*) gapCount.data(), sizeof(int) * gapCount.size());
+		out.write((const char*) seqWeight.data(), sizeof(double) * numSeq);
+		out.write((const char*) resWCount.data(), sizeof(double) * resWCount.size());
+		out.write((const char*) gapWCount.data(), sizeof(double) * gapWCount.size());
+		return out;
+	}
 	vector<int> start(numSeq), end(numSeq), len(numSeq), res((size_t) 4 * csLen, 0), gap(csLen, 0);
 	for (unsigned i = 0; i < numSeq; ++i) {
 		int s = -1, e = -1, n = 0;

@@ -73,7 +73,14 @@ struct MSA {                                       // src/MSA.{h,cpp}: only what
 	std::string concatMSA;                         // numSeq * csLen chars, row-major
 	std::string auxBlocks;                         // start/end/len, counts and weights exactly as loaded (written back by save)
 	std::istream& load(std::istream& in);          // src/MSA.cpp:362-430 (whole record is parsed)
-	std::ostream& save(std::ostream& out) const;   // src/MSA.cpp:295-360 (count / weight blocks recomputed plainly)
+	std::ostream& save(std::ostream& out) const;   // src/MSA.cpp:295-360 (built: the builder's counts and weights; loaded: as read)
+	// database builder, host half (hu_build.cpp): what hmmufotu-build does to the alignment before anything else
+	long loadFasta(std::istream& in);              // src/MSA.cpp:140-164 (+ counts, position-based weights, consensus)
+	MSA& prune();                                  // src/MSA.cpp:87-138: columns without a residue are dropped
+	void updateCounts();                           // src/MSA.cpp:226-293: raw counts, sequence weights, weighted counts
+	void calculateCS();                            // src/MSA.cpp:211-226
+	std::vector<int> startIdx, endIdx, lenIdx, resCount, gapCount; // resCount[j * 4 + b], as Eigen's column-major 4 x csLen
+	std::vector<double> seqWeight, resWCount, gapWCount;
 	unsigned getCSLen() const { return csLen; }
 	char residualAt(unsigned i, unsigned j) const { return concatMSA[(size_t) i * csLen + j]; }
 };
@@ -214,6 +221,21 @@ public:
 	DiscreteGammaModel dG;
 };
 std::ostream& operator<<(std::ostream& out, const PTUnrooted::PTPlacement& place); // .h:1611-1617
+
+// ---- database builder, host half (src/hmmufotu-build.cpp:308-392; hu_build.cpp) ----
+struct NewickTree {                                // src/NewickTree.h: name, branch length to the parent, children in file order
+	NewickTree() : length(0) {}
+	std::string name;
+	double length;
+	std::vector<NewickTree> children;
+	bool read(std::istream& in);                   // the grammar of src/NewickTree.h:172-236
+};
+// PTUnrooted(NewickTree) + loadMSA + fixBranchLength + loadAnnotation + formatName + annotate + calcNodeHeight
+// (src/PhyloTreeUnrooted.cpp:131-296, 974-1006): everything of <db>.ptu that does not need the likelihood evaluation
+// (node ids, edges in file order, branch lengths, leaf sequences, names, annotations, heights).  Messages and the
+// inferred internal sequences come from hu_db_create() with hu_tree_desc.up == NULL.
+bool buildTree(PTUnrooted& tree, const NewickTree& nt, const MSA& msa, std::istream* annoIn,
+		const std::string& rootName = "cellular_organisms");
 
 // ---- the per-read pipeline, batched (src/HmmUFOtu_main.{h,cpp}) ----
 // Host half of alignSeq (src/HmmUFOtu_main.cpp:39-84): the CSFM seed search, in call order (it draws rand()).

@@ -4,10 +4,13 @@
 //   ptu  IN OUT        load a .ptu, save it (PTU_IO_test.cpp:18-59); prints a summary
 //   msa  IN OUT        load a .msa, save it (MSAIO_test.cpp)
 //   locate DB.msa      count() and sorted locate() hits of every pattern on stdin (compared with the reference's own index)
+//   msabuild FASTA NAME OUT   the builder's MSA: load an aligned FASTA, prune, weights, consensus, save (hu_build.cpp)
+//   treebuild FASTA TREE [TAX] / ptuskel DB.ptu   the tree skeleton built from Newick + MSA + taxonomy, or read from a database
 //   seeds DB FASTA S   CSFM seed search of every read with srand(S): prints the ViterbiAlignPaths
 #include "hu_host.h"
 
 #include <stdlib.h>
+#include <stdio.h>
 #include <string.h>
 #include <algorithm>
 #include <fstream>
@@ -47,7 +50,7 @@ static int csfmTest() {
 }
 
 int main(int argc, char** argv) {
-	if (argc < 2) { cerr << "usage: hu_host_test csfm | locate DB.msa | hmm IN OUT | ptu IN OUT | msa IN OUT | seeds DB FASTA SEED [MATE-FASTA]" << endl; return 2; }
+	if (argc < 2) { cerr << "usage: hu_host_test csfm | locate DB.msa | msabuild FASTA NAME OUT | treebuild FASTA TREE [TAX] | ptuskel DB.ptu | hmm IN OUT | ptu IN OUT | msa IN OUT | seeds DB FASTA SEED [MATE-FASTA]" << endl; return 2; }
 	const string cmd = argv[1];
 	if (cmd == "csfm") return csfmTest();
 	if (cmd == "hmm" && argc == 4) {
@@ -87,6 +90,59 @@ int main(int argc, char** argv) {
 		msa.save(out);
 		cout << "numSeq " << msa.numSeq << " csLen " << msa.csLen << endl;
 		return out.good() ? 0 : 1;
+	}
+	if (cmd == "msabuild" && argc == 5) { // msabuild FASTA NAME OUT.msa: the builder's first step (load, name, prune, save)
+		ifstream fa(argv[2]);
+		MSA msa;
+		if (!fa || msa.loadFasta(fa) < 0) { cerr << "cannot load " << argv[2] << endl; return 1; }
+		msa.name = argv[3];
+		msa.prune();
+		ofstream out(argv[4], ios_base::binary);
+		saveProgInfo(out);
+		msa.save(out);
+		cout << "numSeq " << msa.numSeq << " csLen " << msa.csLen << " pruned " << msa.isPruned << endl;
+		return out.good() ? 0 : 1;
+	}
+	if ((cmd == "treebuild" && (argc == 4 || argc == 5)) || (cmd == "ptuskel" && argc == 3)) {
+		// treebuild FASTA TREE [TAXONOMY] / ptuskel DB.ptu: the tree skeleton (ids, edges in file order, branch lengths, names,
+		// annotations, heights, leaf sequences), built here or read from a database, as exact text
+		PTUnrooted tree;
+		if (cmd == "treebuild") {
+			ifstream fa(argv[2]), tr(argv[3]), an;
+			if (argc == 5) an.open(argv[4]);
+			MSA msa;
+			NewickTree nt;
+			if (!fa || msa.loadFasta(fa) < 0 || !tr || !nt.read(tr) || (argc == 5 && !an)) { cerr << "cannot load the inputs" << endl; return 1; }
+			msa.prune();
+			if (!buildTree(tree, nt, msa, argc == 5 ? &an : NULL)) { cerr << "cannot build the tree" << endl; return 1; }
+		} else {
+			ifstream in(argv[2], ios_base::binary);
+			if (loadProgInfo(in).bad()) return 1;
+			tree.load(in);
+			if (!in) { cerr << "cannot load " << argv[2] << endl; return 1; }
+			sort(tree.msaIndex.begin(), tree.msaIndex.end()); // the file keeps hash-map order
+		}
+		char buf[64];
+		cout << "nodes " << tree.numNodes() << " csLen " << tree.csLen << " root " << tree.root << "\n";
+		for (size_t i = 0; i < tree.numNodes(); ++i) {
+			cout << i << "\t" << tree.parent[i];
+			snprintf(buf, sizeof buf, "\t%.17g", tree.blen[i]); cout << buf;
+			snprintf(buf, sizeof buf, "\t%.17g", tree.height[i]); cout << buf;
+			snprintf(buf, sizeof buf, "\t%.17g", tree.annoDist[i]); cout << buf;
+			cout << "\t[" << tree.name[i] << "]\t[" << tree.anno[i] << "]\t[" << tree.seqName[i] << "]\t";
+			for (size_t k = 0; k < tree.neighbors[i].size(); ++k) cout << (k ? "," : "") << tree.neighbors[i][k];
+			cout << "\t";
+			if (tree.neighbors[i].size() == 1 && !tree.seqName[i].empty()) { // leaf sequences come from the MSA; inferred ones need the evaluation
+				unsigned long long h = 1469598103934665603ull;
+				for (int j = 0; j < tree.csLen; ++j) { h ^= (unsigned char) tree.seq[i * (size_t) tree.csLen + j]; h *= 1099511628211ull; }
+				cout << h;
+			}
+			cout << "\n";
+		}
+		cout << "msaIndex";
+		for (size_t i = 0; i < tree.msaIndex.size(); ++i) cout << " " << tree.msaIndex[i].first << ":" << tree.msaIndex[i].second;
+		cout << "\n";
+		return 0;
 	}
 	if (cmd == "locate" && argc == 3) { // locate DB.msa < patterns: count and sorted hits, the format of oracle/ref_csfm_probe.cpp
 		ifstream in(argv[2], ios_base::binary);

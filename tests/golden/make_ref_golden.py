@@ -13,6 +13,9 @@ Writes tests/golden/ref70/:
   se0.aln.fasta                               the -a alignment output of se0
   csfm_locate.{txt,tsv}                       patterns (k-mers cut from se1's reads, plus misses) and what the reference's own
                                               CSFMIndex (oracle/_ref/csfm_probe on gg_70_otus_GTR.csfm) counts and locates for them
+  ../build/hand.{msa,ptu}                     the reference's hmmufotu-build on the hand-written inputs next to them (quoted label,
+                                              negative and missing branch lengths, partly canonical taxonomy, lower case, N,
+                                              nothing to prune): what tests/test_host.py compares the host half of the builder with
   se0.{weighted,ml,height,single}.tsv         se0 again with -m weighted / --ML / --prior height / --single (NGCL alignment mode)
 Every file holds at most 64 reads: up to 64 OpenMP tasks are deferred and then run in creation order, so the
 reference consumes rand() (CSFM seed picks) in file order, as the batched driver does.
@@ -73,6 +76,10 @@ def main():
         f.write("\n".join(pats) + "\n")
     with open("csfm_locate.txt") as fin, open("csfm_locate.tsv", "w") as fout:
         subprocess.run([os.path.join(REF, "csfm_probe"), "gg_70_otus_GTR.csfm"], stdin=fin, stdout=fout, check=True)
+    bdir = os.path.join(HERE, "build")
+    run(os.path.join(REF, "hmmufotu-build"), "hand.fasta", "hand.tree", "-a", "hand_taxonomy.txt", "-n", "hand", "-s", "GTR", cwd=bdir)
+    for ext in ("csfm", "hmm"):
+        os.remove(os.path.join(bdir, "hand." + ext))
     for f in sorted(os.listdir(OUT)):
         print("%10d  %s" % (os.path.getsize(f), f))
 

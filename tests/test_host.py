@@ -58,6 +58,52 @@ def test_csfm_matches_the_reference_index_hit_for_hit(exes):
         assert ref.returncode == 0 and ref.stdout == want
 
 
+REF_TEST = "/root/reference/test"
+
+
+def _skeleton(exe, *args):
+    out = subprocess.run([exe] + list(args), capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    return out.stdout
+
+
+def test_builder_host_half_on_handwritten_inputs(exes, tmp_path):
+    """SURVEY.md 8(f-1), host half (hu_build.cpp): FASTA -> pruned MSA with counts, position-based weights and consensus,
+    and Newick + MSA + taxonomy -> tree skeleton (ids, edges in file order, branch lengths, names, annotations, heights,
+    leaf sequences), against what the reference's own hmmufotu-build wrote for the same inputs (tests/golden/build:
+    quoted label, negative and missing lengths, partly canonical taxonomy, lower case, N, nothing to prune)."""
+    g = os.path.join(ROOT, "tests", "golden", "build")
+    msa = str(tmp_path / "hand.msa")
+    out = subprocess.run([exes[1], "msabuild", os.path.join(g, "hand.fasta"), "hand", msa], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    assert open(msa, "rb").read() == open(os.path.join(g, "hand.msa"), "rb").read()
+    want = _skeleton(exes[1], "ptuskel", os.path.join(g, "hand.ptu"))
+    got = _skeleton(exes[1], "treebuild", os.path.join(g, "hand.fasta"), os.path.join(g, "hand.tree"), os.path.join(g, "hand_taxonomy.txt"))
+    assert got == want
+    assert "[k__Bac;k__Bac;p__Foo;c__Bar;s__zed]" in got      # the reference's literal annotation path (prefix repeated)
+    assert "1.0000000000000001e-05" in got                      # leaf branches of length <= 0 lifted to BRANCH_EPS
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REF_TEST, "70_otus.fasta")), reason="needs the reference's test inputs")
+def test_builder_host_half_on_70_otus(exes, tmp_path):
+    """The same on BASELINE.json configs[0]'s inputs: <db>.msa byte for byte (125 x 7 682 -> 1 486 columns) and all 249
+    nodes of <db>.ptu field by field, doubles to the last bit."""
+    import gzip
+    g = os.path.join(ROOT, "tests", "golden", "ref70")
+    for db in ("gg_70_otus_GTR", "gg_70_otus_HKY85_dG"):
+        msa = str(tmp_path / (db + ".msa"))
+        out = subprocess.run([exes[1], "msabuild", os.path.join(REF_TEST, "70_otus.fasta"), db, msa], capture_output=True, text=True)
+        assert out.returncode == 0, out.stderr
+        assert open(msa, "rb").read() == open(os.path.join(g, db + ".msa"), "rb").read()
+    ptu = str(tmp_path / "ref.ptu")
+    with gzip.open(os.path.join(g, "gg_70_otus_GTR.ptu.gz"), "rb") as f, open(ptu, "wb") as o:
+        o.write(f.read())
+    want = _skeleton(exes[1], "ptuskel", ptu)
+    got = _skeleton(exes[1], "treebuild", os.path.join(REF_TEST, "70_otus.fasta"), os.path.join(REF_TEST, "70_otus.tree"),
+                    os.path.join(REF_TEST, "70_otus_taxonomy.txt"))
+    assert got == want and got.startswith("nodes 249 csLen 1486 root 0")
+
+
 def test_ptu_and_msa_roundtrip_bytes(exes, dbfiles):
     """load -> save reproduces the files byte for byte (the reference's IO tests only check the stream state)."""
     for kind in ("ptu", "msa"):
