@@ -7,6 +7,7 @@
 #include "hu_host.h"
 
 #include <ctype.h>
+#include <math.h>
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
@@ -124,6 +125,79 @@ MSA& MSA::prune() { // src/MSA.cpp:87-138
 	updateCounts();
 	isPruned = true;
 	return *this;
+}
+
+// ------------------------------------------------------------------ discrete Gamma ----
+// The reference takes these from Boost.Math (gamma_p, quantile(gamma_distribution)); Boost is not a dependency here.
+double gammaP(double a, double x) {
+	if (!(x > 0)) return 0;
+	if (x == INFINITY) return 1;
+	const double lg = ::lgamma(a);
+	if (x < a + 1) { // series: P = e^-x x^a / Gamma(a) * sum_n x^n / (a (a+1) ... (a+n))
+		double term = 1 / a, sum = term;
+		for (int n = 1; n < 100000; ++n) {
+			term *= x / (a + n);
+			sum += term;
+			if (::fabs(term) < ::fabs(sum) * 1e-17) break;
+		}
+		return sum * ::exp(-x + a * ::log(x) - lg);
+	}
+	// continued fraction for Q = 1 - P (modified Lentz)
+	const double tiny = 1e-300;
+	double b = x + 1 - a, c = 1 / tiny, d = 1 / b, h = d;
+	for (int n = 1; n < 100000; ++n) {
+		const double an = -n * (n - a);
+		b += 2;
+		d = an * d + b; if (::fabs(d) < tiny) d = tiny;
+		c = b + an / c; if (::fabs(c) < tiny) c = tiny;
+		d = 1 / d;
+		const double del = d * c;
+		h *= del;
+		if (::fabs(del - 1) < 1e-16) break;
+	}
+	return 1 - ::exp(-x + a * ::log(x) - lg) * h;
+}
+
+double gammaQuantile(double shape, double scale, double p) {
+	if (!(p > 0)) return 0;
+	if (!(p < 1)) return INFINITY;
+	// bracket, then bisection polished by Newton steps on P(shape, y) = p (density e^-y y^(shape-1) / Gamma(shape))
+	double lo = 0, hi = shape > 1 ? shape : 1;
+	while (gammaP(shape, hi) < p) hi *= 2;
+	double y = 0.5 * (lo + hi);
+	const double lg = ::lgamma(shape);
+	for (int it = 0; it < 200; ++it) {
+		const double f = gammaP(shape, y) - p;
+		if (f > 0) hi = y; else lo = y;
+		const double dens = ::exp(-y + (shape - 1) * ::log(y) - lg);
+		double next = dens > 0 ? y - f / dens : 0.5 * (lo + hi);
+		if (!(next > lo && next < hi)) next = 0.5 * (lo + hi);
+		if (::fabs(next - y) <= 1e-16 * ::fabs(y)) { y = next; break; }
+		y = next;
+	}
+	return y * scale;
+}
+
+DiscreteGammaModel& DiscreteGammaModel::build(int K_, double alpha_) {
+	K = K_; alpha = alpha_;
+	b.assign(K + 1, 0.0); r.assign(K, 0.0);
+	for (int i = 0; i < K; ++i) b[i] = gammaQuantile(alpha, alpha, i / (double) K); // setBreaks, cpp:40-45
+	b[K] = INFINITY;
+	for (int i = 0; i < K; ++i)                                                     // setRates, cpp:47-55
+		r[i] = b[i + 1] != INFINITY ? gammaP(alpha + 1, b[i + 1] * alpha) - gammaP(alpha + 1, b[i] * alpha)
+		                            : 1 - gammaP(alpha + 1, b[i] * alpha);
+	return *this;
+}
+
+double DiscreteGammaModel::estimateShape(const vector<double>& X) {
+	if (X.size() < 2) return INFINITY;
+	double m = 0;
+	for (size_t i = 0; i < X.size(); ++i) m += X[i];
+	m /= (double) X.size();
+	double ss = 0;
+	for (size_t i = 0; i < X.size(); ++i) ss += (X[i] - m) * (X[i] - m);
+	const double s = ss / (double) (X.size() - 1);
+	return m * m / (s - m);
 }
 
 // ------------------------------------------------------------------ Newick ----

@@ -176,7 +176,13 @@ struct DiscreteGammaModel {                        // src/DiscreteGammaModel.{h,
 	double rate(int k) const { return r[k]; }
 	std::istream& load(std::istream& in);          // cpp:57-72
 	std::ostream& save(std::ostream& out) const;   // cpp:74-90
+	// builder side (hu_build.cpp): break points and rates from (K, alpha), literally as cpp:40-55 -- quantiles of
+	// Gamma(shape alpha, SCALE alpha) and r_i = P(alpha+1, b_{i+1} alpha) - P(alpha+1, b_i alpha), not multiplied by K
+	DiscreteGammaModel& build(int K, double alpha);
+	static double estimateShape(const std::vector<double>& numMut); // cpp:92-98: m^2 / (s^2 - m), inf for < 2 sites
 };
+double gammaP(double a, double x);                 // regularised lower incomplete gamma function P(a, x)
+double gammaQuantile(double shape, double scale, double p);
 
 // ---- unrooted phylogenetic tree as stored in <db>.ptu (src/PhyloTreeUnrooted.{h,cpp}) ----
 class PTUnrooted {

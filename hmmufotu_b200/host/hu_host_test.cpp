@@ -6,6 +6,7 @@
 //   locate DB.msa      count() and sorted locate() hits of every pattern on stdin (compared with the reference's own index)
 //   msabuild FASTA NAME OUT   the builder's MSA: load an aligned FASTA, prune, weights, consensus, save (hu_build.cpp)
 //   treebuild FASTA TREE [TAX] / ptuskel DB.ptu   the tree skeleton built from Newick + MSA + taxonomy, or read from a database
+//   dgamma K ALPHA / dgshow DB.ptu   discrete-Gamma break points and rates, built here or as stored in a database
 //   seeds DB FASTA S   CSFM seed search of every read with srand(S): prints the ViterbiAlignPaths
 #include "hu_host.h"
 
@@ -142,6 +143,32 @@ int main(int argc, char** argv) {
 		cout << "msaIndex";
 		for (size_t i = 0; i < tree.msaIndex.size(); ++i) cout << " " << tree.msaIndex[i].first << ":" << tree.msaIndex[i].second;
 		cout << "\n";
+		return 0;
+	}
+	if ((cmd == "dgamma" && argc == 4) || (cmd == "dgshow" && argc == 3)) { // dgamma K ALPHA: built here; dgshow DB.ptu: as stored
+		DiscreteGammaModel dg;
+		if (cmd == "dgamma") dg.build(atoi(argv[2]), atof(argv[3]));
+		else {
+			ifstream in(argv[2], ios_base::binary);
+			PTUnrooted tree;
+			if (loadProgInfo(in).bad()) return 1;
+			tree.load(in);
+			if (!in || !tree.hasDG) { cerr << "no discrete Gamma model in " << argv[2] << endl; return 1; }
+			dg = tree.dG;
+		}
+		char buf[64];
+		snprintf(buf, sizeof buf, "%d %.17g", dg.K, dg.alpha); cout << buf << "\n";
+		for (int i = 0; i <= dg.K; ++i) { snprintf(buf, sizeof buf, "%.17g", dg.b[i]); cout << (i ? " " : "") << buf; }
+		cout << "\n";
+		for (int i = 0; i < dg.K; ++i) { snprintf(buf, sizeof buf, "%.17g", dg.r[i]); cout << (i ? " " : "") << buf; }
+		cout << "\n";
+		return 0;
+	}
+	if (cmd == "dgshape" && argc >= 3) { // dgshape X1 X2 ...: moment estimate of the shape from per-site mutation counts
+		vector<double> x;
+		for (int i = 2; i < argc; ++i) x.push_back(atof(argv[i]));
+		char buf[64];
+		snprintf(buf, sizeof buf, "%.17g", DiscreteGammaModel::estimateShape(x)); cout << buf << "\n";
 		return 0;
 	}
 	if (cmd == "locate" && argc == 3) { // locate DB.msa < patterns: count and sorted hits, the format of oracle/ref_csfm_probe.cpp

@@ -104,6 +104,37 @@ def test_builder_host_half_on_70_otus(exes, tmp_path):
     assert got == want and got.startswith("nodes 249 csLen 1486 root 0")
 
 
+def test_builder_discrete_gamma(exes, tmp_path):
+    """DiscreteGammaModel(K, alpha) as the builder derives it (src/DiscreteGammaModel.cpp:40-55, literal: Gamma(shape alpha,
+    SCALE alpha) quantiles, rates not multiplied by K) with this repository's own incomplete-gamma code: against the block the
+    reference's builder stored in the HKY85+dG4 database (1e-12 relative; Boost's and these series differ in the last bits)
+    and against scipy; the moment estimate of the shape against numpy."""
+    import gzip
+    from scipy.special import gammainc
+    from scipy.stats import gamma as G
+    ptu = str(tmp_path / "dg.ptu")
+    with gzip.open(os.path.join(ROOT, "tests", "golden", "ref70", "gg_70_otus_HKY85_dG.ptu.gz"), "rb") as f, open(ptu, "wb") as o:
+        o.write(f.read())
+    ref = _skeleton(exes[1], "dgshow", ptu).split("\n")
+    K, alpha = int(ref[0].split()[0]), float(ref[0].split()[1])
+    for k, a in ((K, alpha), (8, 0.31), (2, 5.5), (4, 40.0)):
+        got = _skeleton(exes[1], "dgamma", str(k), repr(a)).split("\n")
+        b = np.array([float(x) for x in got[1].split()])
+        r = np.array([float(x) for x in got[2].split()])
+        if (k, a) == (K, alpha):
+            assert np.allclose(b[:-1], [float(x) for x in ref[1].split()][:-1], rtol=1e-12, atol=0)
+            assert np.allclose(r, [float(x) for x in ref[2].split()], rtol=1e-12, atol=0)
+        wb = G.ppf(np.arange(k) / k, a, scale=a)
+        assert np.allclose(b[:-1], wb, rtol=1e-10, atol=1e-300) and np.isinf(b[-1])
+        wr = np.diff(np.append(gammainc(a + 1, wb * a), 1.0))
+        assert np.allclose(r, wr, rtol=1e-9, atol=1e-15)
+    x = [3.0, 0.0, 7.0, 1.0, 12.0, 2.0, 0.0, 5.0]
+    got = float(_skeleton(exes[1], "dgshape", *[repr(v) for v in x]))
+    m, s2 = np.mean(x), np.var(x, ddof=1)
+    assert abs(got - m * m / (s2 - m)) < 1e-12 * abs(got)
+    assert np.isinf(float(_skeleton(exes[1], "dgshape", "4")))
+
+
 def test_ptu_and_msa_roundtrip_bytes(exes, dbfiles):
     """load -> save reproduces the files byte for byte (the reference's IO tests only check the stream state)."""
     for kind in ("ptu", "msa"):
