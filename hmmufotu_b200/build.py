@@ -74,7 +74,7 @@ def build_host(force: bool = False) -> str:
         exe = os.path.join(BINDIR, name)
         deps = srcs + [os.path.join(HOST, main), lib]
         if force or _stale(exe, deps):
-            subprocess.check_call([CXX, "-O2", "-g", "-std=c++11", "-Wall", "-Wextra", os.path.join(HOST, "hu_host.cpp"),
+            subprocess.check_call([CXX, "-O2", "-g", "-std=c++11", "-pthread", "-Wall", "-Wextra", os.path.join(HOST, "hu_host.cpp"),
                                    os.path.join(HOST, "hu_build.cpp"), os.path.join(HOST, main), "-L" + LIBDIR, "-lhmmufotu_b200", "-Wl,-rpath," + LIBDIR,
                                    "-Wl,-rpath,$ORIGIN/../lib", "-o", exe])
         out.append(exe)

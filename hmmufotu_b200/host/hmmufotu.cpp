@@ -5,6 +5,8 @@
 // host, in file order, so that its rand() stream is the reference's for a given -S.
 #include "hu_host.h"
 
+#include <unistd.h>
+
 #include <errno.h>
 #include <stdlib.h>
 #include <string.h>
@@ -86,9 +88,7 @@ struct ReadBatchHost { // one batch of (pairs of) reads staged for hu_batch_uplo
 	vector<int32_t> nPaths;
 };
 
-static void stage(const BandedHMMP7& hmm, const CSFMIndex& csfm, const PrimarySeq& read, int seedLen, int seedRegion,
-		BandedHMMP7::align_mode mode, ReadBatchHost& hb) {
-	const vector<BandedHMMP7::ViterbiAlignPath> vps = findSeeds(hmm, csfm, read, seedLen, seedRegion, mode);
+static void stage(const PrimarySeq& read, const vector<BandedHMMP7::ViterbiAlignPath>& vps, ReadBatchHost& hb) {
 	for (size_t i = 0; i < read.length(); ++i) {
 		const int8_t b = DNA::encode((char) ::toupper(read.seq[i]));
 		if (b < 0) throw invalid_argument("read '" + read.id + "' holds a character outside the nucleotide alphabet");
@@ -164,6 +164,9 @@ int main(int argc, char* argv[]) {
 	if (cmdOpts.hasOpt("-S") || cmdOpts.hasOpt("--seed")) seed = (unsigned) atoi(cmdOpts.get("-S", "--seed", "0").c_str());
 	const int device = atoi(cmdOpts.get("--gpu", "--gpu", "0").c_str());
 	const int batchSize = atoi(cmdOpts.get("--batch", "--batch", "4096").c_str());
+	// -p|--process (src/hmmufotu.cpp:269-272, 343-346): here the threads of the host-side seed search; the assignment does not depend on it
+	const long nCpu = sysconf(_SC_NPROCESSORS_ONLN);
+	const int nThreads = (cmdOpts.hasOpt("-p") || cmdOpts.hasOpt("--process")) ? atoi(cmdOpts.get("-p", "--process", "1").c_str()) : (int) (nCpu > 0 ? nCpu : 1);
 	string seqFmt = cmdOpts.get("--fmt", "--fmt", "");
 	// option validation, :318-348
 	if (!(MIN_SEED_LEN <= seedLen && seedLen <= MAX_SEED_LEN)) { cerr << "-L|--seed-len must be in range [" << MIN_SEED_LEN << ", " << MAX_SEED_LEN << "]" << endl; return EXIT_FAILURE; }
@@ -175,6 +178,7 @@ int main(int argc, char* argv[]) {
 	if (!(sp.maxDiff >= 0)) { cerr << "-d must be non-negative" << endl; return EXIT_FAILURE; }
 	if (!(sp.maxError > 0)) { cerr << "-e|--err must be positive" << endl; return EXIT_FAILURE; }
 	if (batchSize < 1) { cerr << "--batch must be positive" << endl; return EXIT_FAILURE; }
+	if (nThreads < 1) { cerr << "-p|--process must be positive" << endl; return EXIT_FAILURE; }
 	if (seqFmt.empty() && !fwdFn.empty()) seqFmt = SeqIO::guessFormat(fwdFn);
 	if (!seqFmt.empty() && seqFmt != "fasta" && seqFmt != "fastq") { cerr << "Unsupported sequence format '" << seqFmt << "'" << endl; return EXIT_FAILURE; }
 	srand(seed);
@@ -236,8 +240,8 @@ int main(int argc, char* argv[]) {
 			// The two alignments differ only through the rand() draws of the seed search, "fwd < rev" rarely holds,
 			// and the test settles on strand 2 (then every single-end read is reverse-complemented, :617-618).
 			const PrimarySeq f = testSeqI.nextSeq(), r = f.revcom();
-			stage(hmm, csfm, r, seedLen, seedRegion, mode, hb);
-			stage(hmm, csfm, r, seedLen, seedRegion, mode, hb);
+			stage(r, findSeeds(hmm, csfm, r, seedLen, seedRegion, mode), hb);
+			stage(r, findSeeds(hmm, csfm, r, seedLen, seedRegion, mode), hb);
 			maxLen = max(maxLen, (int) f.length());
 		}
 		double fwdScore = 0, revScore = 0;
@@ -301,9 +305,16 @@ int main(int argc, char* argv[]) {
 		// all forward reads, then all mates.
 		ReadBatchHost mates;
 		mates.offsets.push_back(0);
+		vector<const PrimarySeq*> inOrder;
 		for (int i = 0; i < n; ++i) {
-			stage(hmm, csfm, hb.fwd[i], seedLen, seedRegion, mode, hb);
-			if (paired) stage(hmm, csfm, hb.rev[i], seedLen, seedRegion, mode, mates);
+			inOrder.push_back(&hb.fwd[i]);
+			if (paired) inOrder.push_back(&hb.rev[i]);
+		}
+		// backward searches on -p threads, rand() picks in this order (findSeedsBatch): the paths of the one-by-one loop
+		const vector<vector<BandedHMMP7::ViterbiAlignPath> > seeds = findSeedsBatch(hmm, csfm, inOrder, seedLen, seedRegion, mode, nThreads);
+		for (int i = 0; i < n; ++i) {
+			stage(hb.fwd[i], seeds[paired ? 2 * i : i], hb);
+			if (paired) stage(hb.rev[i], seeds[2 * i + 1], mates);
 		}
 		if (paired) {
 			const int64_t base = hb.offsets.back();

@@ -2,6 +2,8 @@
 // over the C ABI.  See hu_host.h.  Citations are relative to /root/reference/src.
 #include "hu_host.h"
 
+#include <pthread.h>
+
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
@@ -252,29 +254,30 @@ CSFMIndex& CSFMIndex::build(const MSA& msa) {
 	for (int32_t i = 0; i < N; ++i) freq[text[i]]++;
 	for (int b = 0; b < 5; ++b) C[b + 1] = C[b] + freq[b];
 	buildSuffixArray(text, sa);
-	bwt.resize(N);
-	for (int32_t i = 0; i < N; ++i) bwt[i] = sa[i] == 0 ? 0 : text[sa[i] - 1];
-	occSamples.assign(((size_t) N / 64 + 2) * 5, 0);
-	int32_t run[5] = {0, 0, 0, 0, 0};
+	rank.assign((size_t) N / 64 + 2, RankBlock());
+	uint32_t run[5] = {0, 0, 0, 0, 0};
 	for (int32_t i = 0; i < N; ++i) {
+		RankBlock& rb = rank[(size_t) i / 64];
 		if (i % 64 == 0)
-			for (int b = 0; b < 5; ++b) occSamples[(size_t) (i / 64) * 5 + b] = run[b];
-		run[bwt[i]]++;
+			for (int b = 0; b < 5; ++b) { rb.cnt[b] = run[b]; rb.mask[b] = 0; }
+		const int b = sa[i] == 0 ? 0 : text[sa[i] - 1]; // BWT symbol
+		rb.mask[b] |= 1ull << (i % 64);
+		run[b]++;
 	}
 	for (int32_t i = 0; i < N; ++i) sa[i] += 1; // the reference's SA holds 1-based text positions
 	return *this;
 }
 
-int32_t CSFMIndex::occ(int b, int32_t i) const { // symbols b in BWT[0..i]
+int32_t CSFMIndex::occ(int b, int32_t i) const { // symbols b in BWT[0..i]: one cache line and one popcount
 	if (i < 0) return 0;
-	int32_t n = occSamples[(size_t) (i / 64) * 5 + b];
-	for (int32_t p = (i / 64) * 64; p <= i; ++p) n += bwt[p] == b;
-	return n;
+	const RankBlock& rb = rank[(size_t) i / 64];
+	const int r = i % 64;
+	return (int32_t) (rb.cnt[b] + __builtin_popcountll(rb.mask[b] & (r == 63 ? ~0ull : ((1ull << (r + 1)) - 1ull))));
 }
 
 // backward search, src/CSFMIndex.cpp:79-99 / 121-135: [start, end] in SA coordinates
 bool CSFMIndex::search(const string& pattern, int32_t& start, int32_t& end) const {
-	if (pattern.empty() || bwt.empty()) return false;
+	if (pattern.empty() || rank.empty()) return false;
 	start = 0;
 	end = concatLen;
 	bool first = true;
@@ -305,12 +308,15 @@ string CSFMIndex::extractCS(int32_t start, const string& pattern) const {
 	}
 	return cs;
 }
-CSLoc CSFMIndex::locateOne(const string& pattern) const {
-	int32_t s, e;
-	if (!search(pattern, s, e)) return CSLoc();
+CSLoc CSFMIndex::locateAt(const string& pattern, int32_t s, int32_t e) const {
 	const int32_t i = s + rand() % (e - s + 1);  // src/CSFMIndex.cpp:139
 	const int32_t pos = sa[i];
 	return CSLoc(concat2CS[pos], concat2CS[pos + pattern.length() - 1], extractCS(pos, pattern));
+}
+CSLoc CSFMIndex::locateOne(const string& pattern) const {
+	int32_t s, e;
+	if (!search(pattern, s, e)) return CSLoc();
+	return locateAt(pattern, s, e);
 }
 CSLoc CSFMIndex::locateFirst(const string& pattern) const {
 	int32_t s, e;
@@ -844,6 +850,96 @@ vector<BandedHMMP7::ViterbiAlignPath> findSeeds(const BandedHMMP7& hmm, const CS
 		}
 	}
 	return vpaths;
+}
+
+namespace {
+struct SeedIntervals { // phase 1 of findSeedsBatch: intervals of the attempts at each end, in attempt order
+	vector<pair<int32_t, int32_t> > at5, at3; // (1, 0) = empty interval
+};
+void speculate(const CSFMIndex& csfm, const PrimarySeq& read, int seedLen, int seedRegion, BandedHMMP7::align_mode mode, SeedIntervals& si) {
+	const int N = (int) read.length();
+	const int regionLen = seedRegion < N ? seedRegion : N;
+	int32_t s, e;
+	for (int seedFrom = 0; seedFrom + seedLen - 1 < regionLen; ++seedFrom) {
+		const bool hit = csfm.interval(read.getSeq().substr(seedFrom, seedLen), s, e);
+		si.at5.push_back(hit ? make_pair(s, e) : make_pair((int32_t) 1, (int32_t) 0));
+		if (hit) break; // nearly always the seed that is kept
+	}
+	if (mode != BandedHMMP7::GLOBAL) return;
+	for (int seedTo = N - 1; seedTo - seedLen + 1 >= N - regionLen; --seedTo) {
+		const int seedFrom = seedTo - seedLen + 1;
+		if (seedFrom < 0) break;
+		const bool hit = csfm.interval(read.getSeq().substr(seedFrom, seedLen), s, e);
+		si.at3.push_back(hit ? make_pair(s, e) : make_pair((int32_t) 1, (int32_t) 0));
+		if (hit) break;
+	}
+}
+// locateOne() with the interval taken from phase 1 when it has it
+CSLoc locateCached(const CSFMIndex& csfm, const string& pattern, const vector<pair<int32_t, int32_t> >& cache, size_t attempt) {
+	int32_t s, e;
+	if (attempt < cache.size()) { s = cache[attempt].first; e = cache[attempt].second; }
+	else if (!csfm.interval(pattern, s, e)) return CSLoc();
+	if (s > e) return CSLoc();
+	return csfm.locateAt(pattern, s, e);
+}
+struct SpecArgs {
+	const CSFMIndex* csfm; const vector<const PrimarySeq*>* reads; vector<SeedIntervals>* out;
+	int seedLen, seedRegion; BandedHMMP7::align_mode mode; size_t begin, end;
+};
+void* specThread(void* p) {
+	SpecArgs* a = (SpecArgs*) p;
+	for (size_t i = a->begin; i < a->end; ++i) speculate(*a->csfm, *(*a->reads)[i], a->seedLen, a->seedRegion, a->mode, (*a->out)[i]);
+	return NULL;
+}
+}
+
+vector<vector<BandedHMMP7::ViterbiAlignPath> > findSeedsBatch(const BandedHMMP7& hmm, const CSFMIndex& csfm,
+		const vector<const PrimarySeq*>& reads, int seedLen, int seedRegion, BandedHMMP7::align_mode mode, int nThreads) {
+	const size_t n = reads.size();
+	vector<SeedIntervals> spec(n);
+	// phase 1: no random draws, any order
+	nThreads = max(1, min(nThreads, (int) ((n + 63) / 64)));
+	vector<SpecArgs> args(nThreads);
+	vector<pthread_t> th(nThreads);
+	for (int t = 0; t < nThreads; ++t) {
+		SpecArgs a = {&csfm, &reads, &spec, seedLen, seedRegion, mode, n * t / nThreads, n * (t + 1) / nThreads};
+		args[t] = a;
+	}
+	for (int t = 1; t < nThreads; ++t)
+		if (pthread_create(&th[t], NULL, specThread, &args[t]) != 0) { specThread(&args[t]); th[t] = pthread_self(); }
+	specThread(&args[0]);
+	for (int t = 1; t < nThreads; ++t)
+		if (!pthread_equal(th[t], pthread_self())) pthread_join(th[t], NULL);
+	// phase 2: findSeeds' control flow, read by read, rand() drawn as the one-by-one loop draws it
+	vector<vector<BandedHMMP7::ViterbiAlignPath> > out(n);
+	for (size_t r = 0; r < n; ++r) {
+		const PrimarySeq& read = *reads[r];
+		vector<BandedHMMP7::ViterbiAlignPath>& vpaths = out[r];
+		const int N = (int) read.length();
+		const int regionLen = seedRegion < N ? seedRegion : N;
+		size_t attempt = 0;
+		for (int seedFrom = 0; seedFrom + seedLen - 1 < regionLen; ++seedFrom, ++attempt) { // 5' seed
+			const int seedTo = seedFrom + seedLen - 1;
+			const CSLoc loc = locateCached(csfm, read.getSeq().substr(seedFrom, seedLen), spec[r].at5, attempt);
+			if (loc.isValid()) {
+				const BandedHMMP7::ViterbiAlignPath vp = hmm.buildAlignPath(loc, seedFrom + 1, seedTo + 1);
+				if (vp.isValid()) { vpaths.push_back(vp); break; }
+			}
+		}
+		if (mode == BandedHMMP7::GLOBAL && (vpaths.empty() || N >= 2 * regionLen)) { // 3' seed
+			attempt = 0;
+			for (int seedTo = N - 1; seedTo - seedLen + 1 >= N - regionLen; --seedTo, ++attempt) {
+				const int seedFrom = seedTo - seedLen + 1;
+				if (seedFrom < 0) break;
+				const CSLoc loc = locateCached(csfm, read.getSeq().substr(seedFrom, seedLen), spec[r].at3, attempt);
+				if (loc.isValid()) {
+					const BandedHMMP7::ViterbiAlignPath vp = hmm.buildAlignPath(loc, seedFrom + 1, seedTo + 1);
+					if (vp.isValid()) { vpaths.push_back(vp); break; }
+				}
+			}
+		}
+	}
+	return out;
 }
 
 } // namespace HmmUFOtu

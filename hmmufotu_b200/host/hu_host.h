@@ -98,6 +98,11 @@ public:
 	CSLoc locateOne(const std::string& pattern) const;               // src/CSFMIndex.cpp:121-147 (uses rand())
 	CSLoc locateFirst(const std::string& pattern) const;             // src/CSFMIndex.cpp:101-119
 	std::vector<CSLoc> locate(const std::string& pattern) const;     // src/CSFMIndex.cpp:53-77
+	// locateOne() in two halves, so that the backward searches of a batch of reads can run on many threads while the
+	// rand() picks stay in file order: the SA interval of a pattern (no random draw) ...
+	bool interval(const std::string& pattern, int32_t& start, int32_t& end) const { return search(pattern, start, end); }
+	// ... and the random hit inside a non-empty interval (the rand() call and what follows it in locateOne)
+	CSLoc locateAt(const std::string& pattern, int32_t start, int32_t end) const;
 private:
 	bool search(const std::string& pattern, int32_t& start, int32_t& end) const;
 	int32_t occ(int b, int32_t i) const;           // # of symbol b in BWT[0..i]
@@ -105,8 +110,11 @@ private:
 	int csLen;
 	int32_t concatLen;
 	int32_t C[6];
-	std::vector<uint8_t> bwt;                      // symbols 0..4 (0 = separator / terminator)
-	std::vector<int32_t> occSamples;               // [block][5], every 64 positions
+	struct RankBlock {                             // 64 BWT positions in one cache line: counts before the block, one bit mask per symbol
+		uint32_t cnt[5], pad;
+		uint64_t mask[5];
+	};
+	std::vector<RankBlock> rank;                   // BWT symbols 0..4 (0 = separator / terminator)
 	std::vector<int32_t> sa;                       // full suffix array (1-based text positions as in the reference)
 	std::vector<uint16_t> concat2CS;               // 1-based text position -> 1-based consensus column (0: separator)
 };
@@ -247,6 +255,12 @@ bool buildTree(PTUnrooted& tree, const NewickTree& nt, const MSA& msa, std::istr
 // Host half of alignSeq (src/HmmUFOtu_main.cpp:39-84): the CSFM seed search, in call order (it draws rand()).
 std::vector<BandedHMMP7::ViterbiAlignPath> findSeeds(const BandedHMMP7& hmm, const CSFMIndex& csfm, const PrimarySeq& read,
 		int seedLen, int seedRegion, BandedHMMP7::align_mode mode);
+// The same for a batch of reads, in the given order, with the backward searches on nThreads threads: phase 1 (parallel)
+// finds, per read, the SA intervals of the seed attempts up to the first non-empty one at each end; phase 2 (sequential,
+// file order) replays findSeeds' control flow on those intervals and draws rand() exactly as the one-by-one loop does
+// (an attempt whose hit turns out unusable continues with on-the-spot searches).  Same paths, same rand() stream.
+std::vector<std::vector<BandedHMMP7::ViterbiAlignPath> > findSeedsBatch(const BandedHMMP7& hmm, const CSFMIndex& csfm,
+		const std::vector<const PrimarySeq*>& reads, int seedLen, int seedRegion, BandedHMMP7::align_mode mode, int nThreads);
 
 } // namespace HmmUFOtu
 } // namespace EGriceLab

@@ -193,6 +193,8 @@ int main(int argc, char** argv) {
 		}
 		return 0;
 	}
+	int seedThreads = 0; // --threads N (last): the batched two-phase search of findSeedsBatch instead of the one-by-one loop
+	if (argc > 6 && string(argv[argc - 2]) == "--threads") { seedThreads = atoi(argv[argc - 1]); argc -= 2; }
 	const bool single = argc > 5 && string(argv[argc - 1]) == "--single"; // NGCL mode: no 3' seed (src/HmmUFOtu_main.cpp:66)
 	if (single) argc--;
 	if (cmd == "seeds" && (argc == 5 || argc == 6)) { // seeds DB FASTA SEED [MATE-FASTA]: rand() is drawn pair by pair, forward read first
@@ -212,6 +214,28 @@ int main(int argc, char** argv) {
 		ifstream mfa;
 		if (argc == 6) mfa.open(argv[5]);
 		SeqIO mio(&mfa, SeqIO::guessFormat(argc == 6 ? argv[5] : argv[3]));
+		if (seedThreads > 0) { // batches of 4096 reads (pairs: forward read, then its mate), as the command line stages them
+			bool more = true;
+			while (more) {
+				vector<PrimarySeq> rs;
+				while (rs.size() < 4096 * (size_t) (argc == 6 ? 2 : 1) && io.hasNext() && (argc == 5 || mio.hasNext())) {
+					rs.push_back(io.nextSeq());
+					if (argc == 6) rs.push_back(mio.nextSeq().revcom());
+				}
+				more = !rs.empty();
+				vector<const PrimarySeq*> ptr;
+				for (size_t q = 0; q < rs.size(); ++q) ptr.push_back(&rs[q]);
+				const vector<vector<BandedHMMP7::ViterbiAlignPath> > all = findSeedsBatch(hmm, csfm, ptr, 20, 50, single ? BandedHMMP7::NGCL : BandedHMMP7::GLOBAL, seedThreads);
+				for (size_t q = 0; q < rs.size(); ++q) {
+					const vector<BandedHMMP7::ViterbiAlignPath>& v = all[q];
+					cout << rs[q].getId() << "\t" << v.size();
+					for (size_t i = 0; i < v.size(); ++i)
+						cout << "\t" << v[i].start << "," << v[i].end << "," << v[i].from << "," << v[i].to << "," << v[i].nIns << "," << v[i].nDel;
+					cout << "\n";
+				}
+			}
+			return 0;
+		}
 		while (io.hasNext() && (argc == 5 || mio.hasNext())) {
 			vector<PrimarySeq> rs(1, io.nextSeq());
 			if (argc == 6) rs.push_back(mio.nextSeq().revcom()); // src/hmmufotu.cpp:609

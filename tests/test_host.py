@@ -135,6 +135,22 @@ def test_builder_discrete_gamma(exes, tmp_path):
     assert np.isinf(float(_skeleton(exes[1], "dgshape", "4")))
 
 
+def test_batched_seed_search_equals_the_one_by_one_loop(exes):
+    """findSeedsBatch (backward searches on several threads, rand() picks replayed in file order) returns the paths of the
+    one-by-one findSeeds loop -- which tests/test_ref_pin.py pins to the reference's alignments -- for every thread count,
+    single-end, paired-end (forward read, then its reverse-complemented mate) and --single."""
+    g = os.path.join(ROOT, "tests", "golden", "ref70")
+    db = os.path.join(g, "gg_70_otus_GTR")
+    cases = [[os.path.join(g, "gg_70_otus_GTR_se%d.fasta" % k), str(k)] for k in range(4)]
+    cases.append([os.path.join(g, "gg_70_otus_GTR_pe0_1.fasta"), "7", os.path.join(g, "gg_70_otus_GTR_pe0_2.fasta")])
+    cases.append([os.path.join(g, "gg_70_otus_GTR_se0.fasta"), "0", "--single"])
+    for c in cases:
+        want = _skeleton(exes[1], "seeds", db, *c)
+        assert want.count("\n") >= 64
+        for t in (1, 3, 8):
+            assert _skeleton(exes[1], "seeds", db, *(c + ["--threads", str(t)])) == want, (c, t)
+
+
 def test_ptu_and_msa_roundtrip_bytes(exes, dbfiles):
     """load -> save reproduces the files byte for byte (the reference's IO tests only check the stream state)."""
     for kind in ("ptu", "msa"):
