@@ -17,6 +17,13 @@ CLI = os.path.join(ROOT, "hmmufotu_b200", "bin", "hmmufotu")
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(scope="module", autouse=True)
+def _cli_built():
+    """The command line is a build product (not tracked): make sure it exists and is current."""
+    from hmmufotu_b200 import build
+    build.build_host()
+
+
 @pytest.fixture(scope="module", params=["gg_70_otus_GTR", "gg_70_otus_HKY85_dG"])
 def refdb_dir(request, tmp_path_factory):
     name = request.param
