@@ -103,6 +103,45 @@ static void stage(const PrimarySeq& read, const vector<BandedHMMP7::ViterbiAlign
 	hb.nPaths.push_back((int32_t) vps.size());
 }
 
+// One batch of the read loop (src/hmmufotu.cpp:603-626, batched): up to batchSize reads (pairs), the seed search in file
+// order (a pair draws rand() for the forward read first, :621-626), everything staged the way the device wants it: all
+// forward reads, then all mates.  Returns the number of reads (pairs).
+static int readBatch(SeqIO& fwdSeqI, SeqIO& revSeqI, bool paired, int rStrand, int batchSize, const BandedHMMP7& hmm, const CSFMIndex& csfm,
+		int seedLen, int seedRegion, BandedHMMP7::align_mode mode, int nThreads, ReadBatchHost& hb, int& maxLen) {
+	hb.offsets.push_back(0);
+	maxLen = 1;
+	while ((int) hb.fwd.size() < batchSize && fwdSeqI.hasNext() && (!paired || revSeqI.hasNext())) {
+		PrimarySeq f = fwdSeqI.nextSeq();
+		if (rStrand == 2 && !paired) f = f.revcom(); // wrong strand for single-strand reads, :618-619
+		hb.fwd.push_back(f);
+		if (paired) hb.rev.push_back(revSeqI.nextSeq().revcom());
+		maxLen = max(maxLen, (int) f.length());
+		if (paired) maxLen = max(maxLen, (int) hb.rev.back().length());
+	}
+	const int n = (int) hb.fwd.size();
+	ReadBatchHost mates;
+	mates.offsets.push_back(0);
+	vector<const PrimarySeq*> inOrder;
+	for (int i = 0; i < n; ++i) {
+		inOrder.push_back(&hb.fwd[i]);
+		if (paired) inOrder.push_back(&hb.rev[i]);
+	}
+	// backward searches on -p threads, rand() picks in this order (findSeedsBatch): the paths of the one-by-one loop
+	const vector<vector<BandedHMMP7::ViterbiAlignPath> > seeds = findSeedsBatch(hmm, csfm, inOrder, seedLen, seedRegion, mode, nThreads);
+	for (int i = 0; i < n; ++i) {
+		stage(hb.fwd[i], seeds[paired ? 2 * i : i], hb);
+		if (paired) stage(hb.rev[i], seeds[2 * i + 1], mates);
+	}
+	if (paired) {
+		const int64_t base = hb.offsets.back();
+		hb.codes.insert(hb.codes.end(), mates.codes.begin(), mates.codes.end());
+		for (size_t i = 1; i < mates.offsets.size(); ++i) hb.offsets.push_back(base + mates.offsets[i]);
+		hb.vpaths.insert(hb.vpaths.end(), mates.vpaths.begin(), mates.vpaths.end());
+		hb.nPaths.insert(hb.nPaths.end(), mates.nPaths.begin(), mates.nPaths.end());
+	}
+	return n;
+}
+
 #define HU_CHECK(call) do { if ((call) != HU_OK) { cerr << "Error: " << hu_last_error() << endl; return EXIT_FAILURE; } } while (0)
 
 int main(int argc, char* argv[]) {
@@ -213,6 +252,33 @@ int main(int argc, char* argv[]) {
 		cerr << "Database loaded: csLen " << csLen << ", profile size " << hmm.getProfileSize() << ", " << ptu.numNodes() << " nodes, model "
 			 << ptu.model.modelType() << (ptu.hasDG ? " + dGamma" : "") << ", " << msa.numSeq << " MSA rows" << endl;
 	if (checkDb) return EXIT_SUCCESS;
+	if (cmdOpts.hasOpt("--stage-only")) {
+		// test hook, no device needed: run the read loop's staging (readBatch) and print what would be uploaded per read,
+		// in the format of `hu_host_test seeds` (pairs: forward read, then its mate)
+		if (rStrand != 1 && rStrand != 2) { cerr << "--stage-only needs -s 1 or -s 2 (the strand pre-test runs on the device)" << endl; return EXIT_FAILURE; }
+		const bool pairedS = !revFn.empty();
+		if (rStrand == 2 && pairedS) std::swap(fwdFn, revFn);
+		ifstream f1(fwdFn.c_str()), f2;
+		if (pairedS) f2.open(revFn.c_str());
+		if (!f1.is_open() || (pairedS && !f2.is_open())) { cerr << "Unable to open the seq files" << endl; return EXIT_FAILURE; }
+		SeqIO s1(&f1, seqFmt), s2(&f2, seqFmt);
+		while (s1.hasNext() && (!pairedS || s2.hasNext())) {
+			ReadBatchHost hb;
+			int maxLen = 1;
+			const int n = readBatch(s1, s2, pairedS, rStrand, batchSize, hmm, csfm, seedLen, seedRegion, mode, nThreads, hb, maxLen);
+			for (int i = 0; i < n; ++i)
+				for (int m = 0; m < (pairedS ? 2 : 1); ++m) {
+					const int q = m * n + i;
+					cout << (m ? hb.rev[i] : hb.fwd[i]).getId() << "\t" << hb.nPaths[q];
+					for (int k = 0; k < hb.nPaths[q]; ++k) {
+						const hu_vpath& v = hb.vpaths[(size_t) q * 2 + k];
+						cout << "\t" << v.start << "," << v.end << "," << v.from << "," << v.to << "," << v.nIns << "," << v.nDel;
+					}
+					cout << "\t" << (hb.offsets[q + 1] - hb.offsets[q]) << "\n";
+				}
+		}
+		return EXIT_SUCCESS;
+	}
 
 	// ---- device ----
 	hu_db* db = NULL;
@@ -290,39 +356,8 @@ int main(int argc, char* argv[]) {
 	long nDone = 0;
 	while (fwdSeqI.hasNext() && (!paired || revSeqI.hasNext())) {
 		ReadBatchHost hb;
-		hb.offsets.push_back(0);
 		int maxLen = 1;
-		while ((int) hb.fwd.size() < batchSize && fwdSeqI.hasNext() && (!paired || revSeqI.hasNext())) {
-			PrimarySeq f = fwdSeqI.nextSeq();
-			if (rStrand == 2 && !paired) f = f.revcom(); // wrong strand for single-strand reads, :618-619
-			hb.fwd.push_back(f);
-			if (paired) hb.rev.push_back(revSeqI.nextSeq().revcom());
-			maxLen = max(maxLen, (int) f.length());
-			if (paired) maxLen = max(maxLen, (int) hb.rev.back().length());
-		}
-		const int n = (int) hb.fwd.size();
-		// seed search in file order; a pair draws rand() for the forward read first (:621-626).  The device wants
-		// all forward reads, then all mates.
-		ReadBatchHost mates;
-		mates.offsets.push_back(0);
-		vector<const PrimarySeq*> inOrder;
-		for (int i = 0; i < n; ++i) {
-			inOrder.push_back(&hb.fwd[i]);
-			if (paired) inOrder.push_back(&hb.rev[i]);
-		}
-		// backward searches on -p threads, rand() picks in this order (findSeedsBatch): the paths of the one-by-one loop
-		const vector<vector<BandedHMMP7::ViterbiAlignPath> > seeds = findSeedsBatch(hmm, csfm, inOrder, seedLen, seedRegion, mode, nThreads);
-		for (int i = 0; i < n; ++i) {
-			stage(hb.fwd[i], seeds[paired ? 2 * i : i], hb);
-			if (paired) stage(hb.rev[i], seeds[2 * i + 1], mates);
-		}
-		if (paired) {
-			const int64_t base = hb.offsets.back();
-			hb.codes.insert(hb.codes.end(), mates.codes.begin(), mates.codes.end());
-			for (size_t i = 1; i < mates.offsets.size(); ++i) hb.offsets.push_back(base + mates.offsets[i]);
-			hb.vpaths.insert(hb.vpaths.end(), mates.vpaths.begin(), mates.vpaths.end());
-			hb.nPaths.insert(hb.nPaths.end(), mates.nPaths.begin(), mates.nPaths.end());
-		}
+		const int n = readBatch(fwdSeqI, revSeqI, paired, rStrand, batchSize, hmm, csfm, seedLen, seedRegion, mode, nThreads, hb, maxLen);
 		if (!batch || maxLen > batchMaxLen) {
 			if (batch) hu_batch_destroy(batch);
 			batchMaxLen = max(maxLen + maxLen / 4, 64);

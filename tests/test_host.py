@@ -151,6 +151,38 @@ def test_batched_seed_search_equals_the_one_by_one_loop(exes):
             assert _skeleton(exes[1], "seeds", db, *(c + ["--threads", str(t)])) == want, (c, t)
 
 
+def test_command_line_staging_equals_the_seed_driver(exes, tmp_path):
+    """The read loop of the hmmufotu command line up to the upload (`--stage-only`, no device): batches of reads, the
+    batched seed search on -p threads, forward reads then mates -- what it would hand to hu_batch_upload per read equals the
+    one-by-one seed search in file order, for single-end and paired-end input, several batch sizes and thread counts."""
+    import gzip
+    g = os.path.join(ROOT, "tests", "golden", "ref70")
+    for ext in ("msa", "hmm"):
+        with open(os.path.join(g, "gg_70_otus_GTR." + ext), "rb") as f, open(tmp_path / ("db." + ext), "wb") as o:
+            o.write(f.read())
+    with gzip.open(os.path.join(g, "gg_70_otus_GTR.ptu.gz"), "rb") as f, open(tmp_path / "db.ptu", "wb") as o:
+        o.write(f.read())
+    db = str(tmp_path / "db")
+    lens = {}
+    for fa in ("gg_70_otus_GTR_se1.fasta", "gg_70_otus_GTR_pe0_1.fasta", "gg_70_otus_GTR_pe0_2.fasta"):
+        rid = None
+        for ln in open(os.path.join(g, fa)):
+            if ln.startswith(">"):
+                rid = (fa, ln[1:].split()[0]); lens[rid] = 0
+            else:
+                lens[rid] += len(ln.strip())
+    for reads, seed in (([os.path.join(g, "gg_70_otus_GTR_se1.fasta")], "1"),
+                        ([os.path.join(g, "gg_70_otus_GTR_pe0_1.fasta"), os.path.join(g, "gg_70_otus_GTR_pe0_2.fasta")], "7")):
+        want = _skeleton(exes[1], "seeds", os.path.join(g, "gg_70_otus_GTR"), reads[0], seed, *reads[1:]).strip().split("\n")
+        for batch, p in ((64, 1), (7, 4), (4096, 8)):
+            got = _skeleton(exes[0], db, *reads, "-s", "1", "-S", seed, "--batch", str(batch), "-p", str(p), "--stage-only").strip().split("\n")
+            assert len(got) == len(want) == 64 * len(reads)
+            for i, (a, b) in enumerate(zip(got, want)):
+                fa = a.split("\t")
+                assert fa[:-1] == b.split("\t"), (batch, p, a, b)
+                assert int(fa[-1]) == lens[(os.path.basename(reads[i % len(reads)]), fa[0])]   # staged code length = read length
+
+
 def test_ptu_and_msa_roundtrip_bytes(exes, dbfiles):
     """load -> save reproduces the files byte for byte (the reference's IO tests only check the stream state)."""
     for kind in ("ptu", "msa"):
