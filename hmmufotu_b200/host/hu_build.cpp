@@ -10,6 +10,8 @@
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
+#include <stdio.h>
 #include <algorithm>
 #include <sstream>
 
@@ -198,6 +200,232 @@ double DiscreteGammaModel::estimateShape(const vector<double>& X) {
 	for (size_t i = 0; i < X.size(); ++i) ss += (X[i] - m) * (X[i] - m);
 	const double s = ss / (double) (X.size() - 1);
 	return m * m / (s - m);
+}
+
+// ------------------------------------------------------------------ profile training ----
+namespace {
+struct Dirichlet { // a density (L = 1) or a mixture of L densities over K categories (src/math/DirichletDensity, DirichletMixture)
+	int K, L;
+	vector<double> q, alpha; // alpha[i * L + j]
+	Dirichlet() : K(0), L(0) {}
+	bool read(istream& in) { // DirichletDensity::read, cpp:135-162 / DirichletMixture::read, cpp:254-285
+		string line;
+		if (!getline(in, line)) return false;
+		const bool mix = line == "Dirichlet Mixture Model";
+		if (!mix && line != "Dirichlet Density Model") return false;
+		getline(in, line); // training cost
+		getline(in, line);
+		L = 1;
+		if (mix ? sscanf(line.c_str(), "K: %d L: %d", &K, &L) != 2 : sscanf(line.c_str(), "K: %d", &K) != 1) return false;
+		q.assign(L, 1.0);
+		alpha.assign((size_t) K * L, 0.0);
+		if (mix) {
+			getline(in, line); // "Mixture coefficients:"
+			for (int j = 0; j < L; ++j) in >> q[j];
+			getline(in, line);
+		}
+		getline(in, line); // "alpha:"
+		for (int i = 0; i < K; ++i)
+			for (int j = 0; j < L; ++j) in >> alpha[(size_t) i * L + j];
+		getline(in, line);
+		return !in.fail();
+	}
+	// posterior mean of the category probabilities given observed (weighted) counts v[0..K)
+	void meanPostP(double* v) const {
+		double dataSum = 0;
+		for (int i = 0; i < K; ++i) dataSum += v[i];
+		if (L == 1) { // DirichletDensity::meanPostP, cpp:25-27
+			double aSum = 0;
+			for (int i = 0; i < K; ++i) aSum += alpha[i];
+			for (int i = 0; i < K; ++i) v[i] = (v[i] + alpha[i]) / (dataSum + aSum);
+			return;
+		}
+		vector<double> logB(L), aSum(L, 0.0), X(K, 0.0); // DirichletMixture::meanPostP, cpp:45-61
+		double mx = -INFINITY;
+		for (int j = 0; j < L; ++j) {
+			double s1 = 0, t1 = 0, s0 = 0, t0 = 0;
+			for (int i = 0; i < K; ++i) {
+				const double a = alpha[(size_t) i * L + j];
+				s1 += ::lgamma(a + v[i]); t1 += a + v[i];
+				s0 += ::lgamma(a); t0 += a;
+			}
+			aSum[j] = t0;
+			logB[j] = (s1 - ::lgamma(t1)) - (s0 - ::lgamma(t0));
+			mx = max(mx, logB[j]);
+		}
+		double tot = 0;
+		for (int i = 0; i < K; ++i) {
+			for (int j = 0; j < L; ++j) X[i] += q[j] * ::exp(logB[j] - mx) * (alpha[(size_t) i * L + j] + v[i]) / (aSum[j] + dataSum);
+			tot += X[i];
+		}
+		for (int i = 0; i < K; ++i) v[i] = X[i] / tot;
+	}
+};
+struct P7Counts { // probabilities or counts: emissions [k * 4 + b], transitions [k * 9 + a * 3 + b] with M, I, D = 0, 1, 2
+	int K;
+	vector<double> EM, EI, T;
+	void scale(double r) {
+		for (size_t i = 0; i < EM.size(); ++i) { EM[i] *= r; EI[i] *= r; }
+		for (size_t i = 0; i < T.size(); ++i) T[i] *= r;
+	}
+	void estimate(const Dirichlet& ME, const Dirichlet& IE, const Dirichlet& MT, const Dirichlet& IT, const Dirichlet& DT) { // estimateParams, cpp:280-315
+		for (int k = 0; k <= K; ++k) {
+			double* t = &T[(size_t) k * 9];
+			MT.meanPostP(t);                 // M -> M, I, D
+			IT.meanPostP(t + 3);             // I -> M, I
+			double d[2] = {t[6], t[8]};      // D -> M, D
+			DT.meanPostP(d);
+			t[6] = d[0]; t[8] = d[1];
+			ME.meanPostP(&EM[(size_t) k * 4]);
+			IE.meanPostP(&EI[(size_t) k * 4]);
+		}
+		T[6] = 1; T[8] = 0;                                   // T[0](D, M) = 1, T[0](D, D) = 0
+		double* tk = &T[(size_t) K * 9];
+		tk[2] = 0; tk[6] = 1; tk[8] = 0;                      // T[K](M, D) = 0, T[K](D, M) = 1, T[K](D, D) = 0
+	}
+	double meanRelativeEntropy() const { // cpp:317-322 against the uniform background a fresh profile carries, in bits
+		double ent = 0;
+		for (int k = 1; k <= K; ++k) {
+			double e = 0;
+			for (int b = 0; b < 4; ++b) {
+				const double p = EM[(size_t) k * 4 + b];
+				if (p > 0) e += p * ::log(p / 0.25);
+			}
+			ent += e / ::log(2.0);
+		}
+		return ent / K;
+	}
+};
+inline int matchingState(const vector<int32_t>& cs2p, int loc, int b) { // src/BandedHMMP7.h:713-716: M, I, D = 0, 1, 2; 3 = nothing here
+	const bool isPos = cs2p[loc] != cs2p[loc - 1];
+	return isPos && b >= 0 ? 0 : isPos && b < 0 ? 2 : !isPos && b >= 0 ? 1 : 3;
+}
+}
+
+bool BandedHMMP7::build(const MSA& msa, double symfrac, istream& priorIn, bool asCompiled) {
+	if (msa.numSeq == 0 || msa.csLen == 0 || !(symfrac > 0 && symfrac < 1)) return false;
+	if (msa.seqWeight.size() != msa.numSeq) return false; // counts and weights come from MSA::loadFasta / prune
+	Dirichlet ME, IE, MT, IT, DT;
+	{ // BandedHMMP7Prior, src/BandedHMMP7Prior.cpp:20-45
+		string head;
+		while (getline(priorIn, head)) {
+			Dirichlet* d = head.compare(0, 15, "Match emission:") == 0 ? &ME : head.compare(0, 16, "Insert emission:") == 0 ? &IE :
+			               head.compare(0, 17, "Match transition:") == 0 ? &MT : head.compare(0, 18, "Insert transition:") == 0 ? &IT :
+			               head.compare(0, 18, "Delete transition:") == 0 ? &DT : NULL;
+			if (d && !d->read(priorIn)) return false;
+		}
+		if (ME.K != 4 || IE.K != 4 || MT.K != 3 || IT.K != 2 || DT.K != 2) return false;
+	}
+	name = msa.name;
+	L = (int) msa.csLen;
+	const unsigned N = msa.numSeq;
+	// match columns: weighted symbol fraction >= symfrac (cpp:405-411)
+	cs2ProfileIdx.assign(L + 1, 0);
+	profile2CSIdx.assign(1, 0);
+	int k = 0;
+	for (int j = 1; j <= L; ++j) {
+		double res = 0;
+		for (int b = 0; b < 4; ++b) res += msa.resWCount[(size_t) (j - 1) * 4 + b];
+		if (res / (res + msa.gapWCount[j - 1]) >= symfrac) { profile2CSIdx.push_back(j); ++k; }
+		cs2ProfileIdx[j] = k;
+	}
+	K = k;
+	if (K < 1) return false;
+	P7Counts c;
+	c.K = K;
+	c.EM.assign((size_t) (K + 1) * 4, 0.0); c.EI.assign((size_t) (K + 1) * 4, 0.0); c.T.assign((size_t) (K + 1) * 9, 0.0);
+	// observed weighted counts (cpp:428-478)
+	for (int j = 1; j <= L; ++j) {
+		k = cs2ProfileIdx[j];
+		for (unsigned i = 0; i < N; ++i) {
+			const int b = DNA::encode((char) ::toupper(msa.residualAt(i, j - 1)));
+			const double w = msa.seqWeight[i];
+			const int sm = matchingState(cs2ProfileIdx, j, b);
+			if (sm == 3) continue;
+			if (sm == 0) { c.EM[b] += w; c.EM[(size_t) k * 4 + b] += w; } // M0 collects the composition
+			else if (sm == 1) c.EI[(size_t) k * 4 + b] += w;
+			int jN, smN = 3;
+			for (jN = j + 1; jN <= L; ++jN) { // the next position of this row that is in some state
+				smN = matchingState(cs2ProfileIdx, jN, DNA::encode((char) ::toupper(msa.residualAt(i, jN - 1))));
+				if (smN != 3) break;
+			}
+			if (!(jN <= L && smN != 3)) continue;
+			if (asCompiled) smN = 0; // the variable the reference tests and indexes with here is never assigned: GCC reads it as M
+			if ((sm == 1 && smN == 2) || (sm == 2 && smN == 1)) continue; // no I->D or D->I
+			c.T[(size_t) k * 9 + sm * 3 + smN] += w;
+		}
+	}
+	for (unsigned i = 0; i < N; ++i) { // B -> first state, last state -> E (cpp:466-476)
+		const double w = msa.seqWeight[i];
+		const int start = msa.startIdx[i], end = msa.endIdx[i];
+		if (start < 0) continue;
+		const int smS = matchingState(cs2ProfileIdx, start + 1, DNA::encode((char) ::toupper(msa.residualAt(i, start))));
+		c.T[0 * 3 + smS] += w;
+		const int smE = matchingState(cs2ProfileIdx, end + 1, DNA::encode((char) ::toupper(msa.residualAt(i, end))));
+		c.T[(size_t) K * 9 + smE * 3 + 0] += w;
+	}
+	// effective sequence number: bisection on [0, N] to a mean relative entropy of DEFAULT_ERE = 1 bit
+	// (RelativeEntropyTargetFunc, cpp:1122-1135; RootFinder::rootBisection, src/math/RootFinder.cpp:22-78)
+	const double nSeq = N;
+	struct Target {
+		const P7Counts& c; double nSeq; const Dirichlet &ME, &IE, &MT, &IT, &DT;
+		double operator()(double x) const {
+			if (x > nSeq) return 0;
+			P7Counts t = c;
+			t.scale(x / nSeq);
+			t.estimate(ME, IE, MT, IT, DT);
+			return t.meanRelativeEntropy() - 1.0;
+		}
+	} f = {c, nSeq, ME, IE, MT, IT, DT};
+	double effN = nSeq;
+	{
+		double xl = 0, xr = nSeq, x = NAN;
+		double fxl = f(xl), fxr = f(xr);
+		if (fxl * fxr < 0) {
+			for (;;) {
+				x = (xl + xr) / 2;
+				const double fx = f(x);
+				if (fx == 0) break;
+				if (xr - xl < 1e-10 + 1e-10 * x) break;
+				if (fxl > 0) { if (fx > 0) { xl = x; fxl = fx; } else { xr = x; fxr = fx; } }
+				else { if (fx < 0) { xl = x; fxl = fx; } else { xr = x; fxr = fx; } }
+			}
+		}
+		if (!::isnan(x)) effN = x;
+	}
+	c.scale(effN / nSeq);
+	c.estimate(ME, IE, MT, IT, DT);
+	// costs
+	E_M_cost.assign(c.EM.size(), 0.0); E_I_cost.assign(c.EI.size(), 0.0); Tmat_cost.assign(c.T.size(), 0.0);
+	for (size_t i = 0; i < c.EM.size(); ++i) { E_M_cost[i] = -::log(c.EM[i]); E_I_cost[i] = -::log(c.EI[i]); }
+	for (size_t i = 0; i < c.T.size(); ++i) Tmat_cost[i] = -::log(c.T[i]);
+	entryPr_cost.assign(K + 1, INFINITY); exitPr_cost.assign(K + 1, INFINITY);
+	wingRetracted = false;
+	// tags (cpp:496-538)
+	char value[128];
+	optTags.clear();
+	snprintf(value, sizeof value, "%d", L); optTags.push_back(make_pair(string("MAXL"), string(value)));
+	optTags.push_back(make_pair(string("RF"), string("no")));
+	optTags.push_back(make_pair(string("MM"), string("no")));
+	optTags.push_back(make_pair(string("CONS"), string("yes")));
+	optTags.push_back(make_pair(string("CS"), string("no")));
+	optTags.push_back(make_pair(string("MAP"), string("yes")));
+	snprintf(value, sizeof value, "%u", N); optTags.push_back(make_pair(string("NSEQ"), string(value)));
+	snprintf(value, sizeof value, "%g", effN); optTags.push_back(make_pair(string("EFFN"), string(value)));
+	locMap.assign(K + 1, "");
+	for (k = 1; k <= K; ++k) {
+		const int map = profile2CSIdx[k];
+		int bb = 0; // MSA::CSBaseAt, src/MSA.cpp:52-57: the most frequent base by weighted count (first maximum), never a gap
+		for (int b = 1; b < 4; ++b) if (msa.resWCount[(size_t) (map - 1) * 4 + b] > msa.resWCount[(size_t) (map - 1) * 4 + bb]) bb = b;
+		char ch = DNA::decode((int8_t) bb);
+		if (msa.resWCount[(size_t) (map - 1) * 4 + bb] / N < 0.9) ch = (char) ::tolower(ch); // wIdentityAt < CONS_THRESHOLD
+		locMap[k] = string(1, ch) + "\t-\t-\t-";
+	}
+	time_t raw;
+	time(&raw);
+	strftime(value, sizeof value, "%c", localtime(&raw));
+	optTags.push_back(make_pair(string("DATE"), string(value)));
+	return true;
 }
 
 // ------------------------------------------------------------------ Newick ----

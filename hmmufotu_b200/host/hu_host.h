@@ -150,6 +150,14 @@ public:
 	ViterbiAlignPath buildAlignPath(const CSLoc& csLoc, int csFrom, int csTo) const; // cpp:894-941
 	HmmAlignment buildGlobalAlign(const PrimarySeq& seq, const hu_align_row& row, const char* trace) const; // cpp:1008-1081
 	hu_hmm_params params() const;                                    // view for hu_db_create / hu_trace_to_align
+	// database builder (hu_build.cpp): profile training from the pruned MSA, src/BandedHMMP7.cpp:386-541 -- match columns by
+	// weighted symbol fraction, weighted emission / transition counts, effective sequence number by bisection to a mean
+	// relative entropy of 1 bit, posterior means under the Dirichlet priors of a .dm file.  The reference's transition loop reads
+	// a variable its inner loop shadows (:446-463, undefined behaviour).  asCompiled = true reproduces what the reference's
+	// GCC -O2 build does with it (oracle/_ref, read off its disassembly: the never-assigned variable is taken as M, so every
+	// counted transition goes to a match state) and with it the reference builder's <db>.hmm, every line but DATE;
+	// asCompiled = false counts the state of the next non-gap position, which is what the loop evidently means.
+	bool build(const MSA& msa, double symfrac, std::istream& priorIn, bool asCompiled = true);
 	friend std::istream& operator>>(std::istream& in, BandedHMMP7& hmm);        // cpp:100-246
 	friend std::ostream& operator<<(std::ostream& out, const BandedHMMP7& hmm); // cpp:324-378
 	std::string name;

@@ -6,6 +6,7 @@
 //   locate DB.msa      count() and sorted locate() hits of every pattern on stdin (compared with the reference's own index)
 //   msabuild FASTA NAME OUT   the builder's MSA: load an aligned FASTA, prune, weights, consensus, save (hu_build.cpp)
 //   treebuild FASTA TREE [TAX] / ptuskel DB.ptu   the tree skeleton built from Newick + MSA + taxonomy, or read from a database
+//   hmmbuild FASTA NAME PRIOR.dm OUT   the builder's profile training (hu_build.cpp)
 //   dgamma K ALPHA / dgshow DB.ptu   discrete-Gamma break points and rates, built here or as stored in a database
 //   seeds DB FASTA S   CSFM seed search of every read with srand(S): prints the ViterbiAlignPaths
 #include "hu_host.h"
@@ -170,6 +171,19 @@ int main(int argc, char** argv) {
 		char buf[64];
 		snprintf(buf, sizeof buf, "%.17g", DiscreteGammaModel::estimateShape(x)); cout << buf << "\n";
 		return 0;
+	}
+	if (cmd == "hmmbuild" && (argc == 6 || (argc == 7 && string(argv[6]) == "--intended"))) { // hmmbuild FASTA NAME PRIOR.dm OUT.hmm [--intended]: the builder's profile (symfrac 0.5, the reference's default)
+		ifstream fa(argv[2]), dm(argv[4]);
+		MSA msa;
+		if (!fa || !dm || msa.loadFasta(fa) < 0) { cerr << "cannot load the inputs" << endl; return 1; }
+		msa.name = argv[3];
+		msa.prune();
+		BandedHMMP7 hmm;
+		if (!hmm.build(msa, 0.5, dm, argc == 6)) { cerr << "cannot train the profile" << endl; return 1; }
+		ofstream out(argv[5]);
+		out << hmm;
+		cout << "K " << hmm.getProfileSize() << " L " << hmm.getCSLen() << endl;
+		return out.good() ? 0 : 1;
 	}
 	if (cmd == "locate" && argc == 3) { // locate DB.msa < patterns: count and sorted hits, the format of oracle/ref_csfm_probe.cpp
 		ifstream in(argv[2], ios_base::binary);

@@ -104,6 +104,41 @@ def test_builder_host_half_on_70_otus(exes, tmp_path):
     assert got == want and got.startswith("nodes 249 csLen 1486 root 0")
 
 
+REF_DM = "/root/reference/data/gg_97_otus.dm"
+
+
+@pytest.mark.skipif(not (os.path.exists(REF_DM) and os.path.exists(os.path.join(REF_TEST, "70_otus.fasta"))), reason="needs the reference's prior file and test inputs")
+def test_builder_profile_training(exes, tmp_path):
+    """BandedHMMP7::build (hu_build.cpp) against the .hmm files the reference's hmmufotu-build wrote: match columns, MAP and
+    CONS annotations, match / insert emissions, effective sequence number and -- with the transition counts taken the way the
+    reference's GCC build takes them (its loop reads a shadowed, never-assigned variable; the disassembly shows it as M) --
+    every transition line: identical text except the DATE tag, on 70_otus (K = 1 285) and on the hand-written alignment.
+    `--intended` (next state as the loop evidently means it) changes transition lines only and still writes distributions."""
+    g70, gb = os.path.join(ROOT, "tests", "golden", "ref70"), os.path.join(ROOT, "tests", "golden", "build")
+    strip = lambda path: [ln for ln in open(path).read().split("\n") if not ln.startswith("DATE")]
+    for fasta, name, want in ((os.path.join(REF_TEST, "70_otus.fasta"), "gg_70_otus_GTR", os.path.join(g70, "gg_70_otus_GTR.hmm")),
+                              (os.path.join(gb, "hand.fasta"), "hand", os.path.join(gb, "hand.hmm"))):
+        out = str(tmp_path / (name + ".hmm"))
+        r = subprocess.run([exes[1], "hmmbuild", fasta, name, REF_DM, out], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        assert strip(out) == strip(want)
+    out2 = str(tmp_path / "intended.hmm")
+    r = subprocess.run([exes[1], "hmmbuild", os.path.join(REF_TEST, "70_otus.fasta"), "gg_70_otus_GTR", REF_DM, out2, "--intended"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    a, b = strip(str(tmp_path / "gg_70_otus_GTR.hmm")), strip(out2)
+    assert len(a) == len(b)
+    body = a.index("HMM\t\tA\tC\tG\tT") + 2
+    ndiff = 0
+    for i, (x, y) in enumerate(zip(a, b)):
+        if x != y:
+            assert i >= body and (i - body) % 3 == 2, (i, x, y)       # only the third line of a node: the transitions
+            ndiff += 1
+            t = [0.0 if v == "*" else np.exp(-float(v)) for v in y.split()]
+            last = i + 3 >= len(a) - 2                                    # node K: M->D is forced to 0 after the estimate, not renormalised
+            assert (last or abs(sum(t[0:3]) - 1) < 1e-4) and abs(sum(t[3:5]) - 1) < 1e-4 and abs(sum(t[5:7]) - 1) < 1e-4
+    assert ndiff > 100
+
+
 def test_builder_discrete_gamma(exes, tmp_path):
     """DiscreteGammaModel(K, alpha) as the builder derives it (src/DiscreteGammaModel.cpp:40-55, literal: Gamma(shape alpha,
     SCALE alpha) quantiles, rates not multiplied by K) with this repository's own incomplete-gamma code: against the block the
