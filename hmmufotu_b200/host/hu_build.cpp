@@ -428,6 +428,84 @@ bool BandedHMMP7::build(const MSA& msa, double symfrac, istream& priorIn, bool a
 	return true;
 }
 
+// ------------------------------------------------------------------ after the evaluation ----
+namespace {
+const double kMinLoglikExp = -1021 / 2; // MIN_LOGLIK_EXP = DBL_MIN_EXP / 2 (integer division), src/PhyloTreeUnrooted.cpp:68
+// dot_product_scaled(X, V), src/PhyloTreeUnrooted.h:1495-1503: log(X exp(V)) row by row, V lifted when it would underflow
+void dotProductScaled(const double* P16, const double* V, double* Y) {
+	const double maxV = max(max(V[0], V[1]), max(V[2], V[3]));
+	const double scale = maxV != -INFINITY && maxV < kMinLoglikExp ? kMinLoglikExp - maxV : 0;
+	double e[4];
+	for (int k = 0; k < 4; ++k) e[k] = ::exp(V[k] + scale);
+	for (int i = 0; i < 4; ++i) {
+		double d = 0;
+		for (int k = 0; k < 4; ++k) d += P16[i * 4 + k] * e[k];
+		Y[i] = ::log(d) - scale;
+	}
+}
+}
+
+void PTUnrooted::updateRootLoglik() {
+	const size_t per = (size_t) csLen * 4;
+	rootLoglik.assign(per, 0.0);
+	const int K = hasDG ? dG.K : 1;
+	vector<vector<double> > P; // [child][rate] 4x4
+	vector<long> kids;
+	for (size_t c = 0; c < neighbors[root].size(); ++c) {
+		const long ch = neighbors[root][c];
+		if (parent[ch] != root) continue;
+		kids.push_back(ch);
+		for (int k = 0; k < K; ++k) {
+			P.push_back(vector<double>(16));
+			model.Pr(blen[ch] * (hasDG ? dG.rate(k) : 1.0), P.back().data());
+		}
+	}
+	vector<double> mat((size_t) 4 * K);
+	for (int j = 0; j < csLen; ++j) {
+		fill(mat.begin(), mat.end(), 0.0);
+		for (size_t c = 0; c < kids.size(); ++c)
+			for (int k = 0; k < K; ++k) {
+				double y[4];
+				dotProductScaled(P[c * K + k].data(), &up[(size_t) kids[c] * per + (size_t) j * 4], y);
+				for (int i = 0; i < 4; ++i) mat[(size_t) i * K + k] += y[i];
+			}
+		double* out = &rootLoglik[(size_t) j * 4];
+		if (!hasDG) { for (int i = 0; i < 4; ++i) out[i] = mat[i]; continue; }
+		for (int i = 0; i < 4; ++i) { // row_mean_exp_scaled, .h:1521-1529
+			double mx = -INFINITY;
+			for (int k = 0; k < K; ++k) mx = max(mx, mat[(size_t) i * K + k]);
+			const double scale = mx != -INFINITY && mx < kMinLoglikExp ? kMinLoglikExp - mx : 0;
+			double sum = 0;
+			for (int k = 0; k < K; ++k) sum += ::exp(mat[(size_t) i * K + k] + scale);
+			out[i] = ::log(sum / K) - scale;
+		}
+	}
+}
+
+vector<double> PTUnrooted::numMutations() const {
+	// estimateNumMutations(j): edges whose two ends infer different states, a node's state being the arg-max (first maximum)
+	// of its message towards the parent.  When hmmufotu-build asks, the root's own block still holds the INVALID_LOGLIK
+	// constant (initRootLoglik fills it, evaluate() does not cache the root), so the root "infers" state 0 at every site.
+	const size_t per = (size_t) csLen * 4;
+	vector<double> n(csLen, 0.0);
+	vector<int8_t> state(numNodes());
+	for (int j = 0; j < csLen; ++j) {
+		for (size_t id = 0; id < numNodes(); ++id) {
+			int best = 0;
+			if ((long) id != root) {
+				const double* v = &up[id * per + (size_t) j * 4];
+				for (int k = 1; k < 4; ++k) if (v[k] > v[best]) best = k;
+			}
+			state[id] = (int8_t) best;
+		}
+		int cnt = 0;
+		for (size_t id = 0; id < numNodes(); ++id)
+			if ((long) id != root && state[id] != state[parent[id]]) cnt++;
+		n[j] = cnt;
+	}
+	return n;
+}
+
 // ------------------------------------------------------------------ Newick ----
 // tree = subtree ';'    subtree = -('(' subtree % ',' ')') >> -label >> -(':' double)    skipper: white space
 // label = +(printable - space - "()[]':;,")  |  '\'' +(printable - '\'') '\''            (src/NewickTree.h:172-236)

@@ -224,6 +224,9 @@ public:
 	double getHeight(long id) const { return height[id]; }
 	const std::string& getAnno(long id) const { return anno[id]; }
 	hu_tree_desc treeDesc() const;                 // view for hu_db_create (messages included)
+	// builder side (hu_build.cpp), from the evaluated messages up[] = msg(node -> parent):
+	void updateRootLoglik();                       // cpp:298-301 with loglik(root, j), cpp:320-346
+	std::vector<double> numMutations() const;      // cpp:1008-1016 per site, as hmmufotu-build feeds estimateShape (:431-436)
 	hu_model_desc modelDesc() const;
 	PTPlacement toPlacement(const hu_place_row& row) const;
 	int csLen;

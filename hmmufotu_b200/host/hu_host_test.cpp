@@ -7,11 +7,13 @@
 //   msabuild FASTA NAME OUT   the builder's MSA: load an aligned FASTA, prune, weights, consensus, save (hu_build.cpp)
 //   treebuild FASTA TREE [TAX] / ptuskel DB.ptu   the tree skeleton built from Newick + MSA + taxonomy, or read from a database
 //   hmmbuild FASTA NAME PRIOR.dm OUT   the builder's profile training (hu_build.cpp)
+//   rootll DB.ptu      root log-likelihood block recomputed from the stored messages; shape estimate from the messages
 //   dgamma K ALPHA / dgshow DB.ptu   discrete-Gamma break points and rates, built here or as stored in a database
 //   seeds DB FASTA S   CSFM seed search of every read with srand(S): prints the ViterbiAlignPaths
 #include "hu_host.h"
 
 #include <stdlib.h>
+#include <math.h>
 #include <stdio.h>
 #include <string.h>
 #include <algorithm>
@@ -184,6 +186,24 @@ int main(int argc, char** argv) {
 		out << hmm;
 		cout << "K " << hmm.getProfileSize() << " L " << hmm.getCSLen() << endl;
 		return out.good() ? 0 : 1;
+	}
+	if (cmd == "rootll" && argc == 3) { // rootll DB.ptu: the root block recomputed from the stored messages vs the stored one; alpha from the messages
+		ifstream in(argv[2], ios_base::binary);
+		PTUnrooted tree;
+		if (loadProgInfo(in).bad()) return 1;
+		tree.load(in);
+		if (!in) { cerr << "cannot load " << argv[2] << endl; return 1; }
+		const vector<double> stored = tree.rootLoglik;
+		tree.updateRootLoglik();
+		double worst = 0;
+		for (size_t i = 0; i < stored.size(); ++i) {
+			const double d = fabs(tree.rootLoglik[i] - stored[i]) / max(1.0, fabs(stored[i]));
+			if (!(d <= worst)) worst = d;
+		}
+		char buf[96];
+		snprintf(buf, sizeof buf, "max_rel_diff %.3g alpha %.17g", worst, DiscreteGammaModel::estimateShape(tree.numMutations()));
+		cout << buf << endl;
+		return 0;
 	}
 	if (cmd == "locate" && argc == 3) { // locate DB.msa < patterns: count and sorted hits, the format of oracle/ref_csfm_probe.cpp
 		ifstream in(argv[2], ios_base::binary);

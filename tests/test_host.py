@@ -139,6 +139,36 @@ def test_builder_profile_training(exes, tmp_path):
     assert ndiff > 100
 
 
+def test_builder_root_block_and_shape_estimate(exes, tmp_path):
+    """What the builder derives from the evaluated messages on the host (hu_build.cpp): the root log-likelihood block
+    (loglik(root, j) over the children's messages, discrete-Gamma mixture included) recomputed from the messages stored in the
+    reference-built databases equals the stored block (GTR and HKY85+dG4), and the shape estimate from the per-site mutation
+    counts of the fixed-rate GTR messages -- including the literal root quirk: the root's own block still holds the
+    INVALID_LOGLIK constant when hmmufotu-build asks, so the root infers state 0 everywhere -- is the alpha the reference's
+    builder stores when run with -V on the same inputs (recorded; re-run live where the reference is available)."""
+    import gzip
+    g = os.path.join(ROOT, "tests", "golden", "ref70")
+    alpha = {}
+    for db in ("gg_70_otus_GTR", "gg_70_otus_HKY85_dG"):
+        ptu = str(tmp_path / (db + ".ptu"))
+        with gzip.open(os.path.join(g, db + ".ptu.gz"), "rb") as f, open(ptu, "wb") as o:
+            o.write(f.read())
+        out = _skeleton(exes[1], "rootll", ptu).split()
+        assert float(out[1]) < 1e-12, out
+        alpha[db] = out[3]
+    assert alpha["gg_70_otus_GTR"] == "1.8236165938119167"      # oracle/_ref/hmmufotu-build ... -s GTR -V -k 4 stores exactly this
+    builder = os.path.join(ROOT, "oracle", "_ref", "hmmufotu-build")
+    if os.path.exists(builder) and os.path.exists(os.path.join(REF_TEST, "70_otus.fasta")):
+        r = subprocess.run([builder, os.path.join(REF_TEST, "70_otus.fasta"), os.path.join(REF_TEST, "70_otus.tree"), "-a",
+                            os.path.join(REF_TEST, "70_otus_taxonomy.txt"), "-n", "gtrv", "-s", "GTR", "-V", "-k", "4"],
+                           cwd=str(tmp_path), capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-500:]
+        stored = _skeleton(exes[1], "dgshow", str(tmp_path / "gtrv.ptu")).split("\n")
+        assert stored[0].split()[1] == alpha["gg_70_otus_GTR"]
+        ours = _skeleton(exes[1], "dgamma", "4", alpha["gg_70_otus_GTR"]).split("\n")
+        assert np.allclose([float(x) for x in ours[2].split()], [float(x) for x in stored[2].split()], rtol=1e-12, atol=0)
+
+
 def test_builder_discrete_gamma(exes, tmp_path):
     """DiscreteGammaModel(K, alpha) as the builder derives it (src/DiscreteGammaModel.cpp:40-55, literal: Gamma(shape alpha,
     SCALE alpha) quantiles, rates not multiplied by K) with this repository's own incomplete-gamma code: against the block the
