@@ -205,6 +205,40 @@ int main(int argc, char** argv) {
 		cout << buf << endl;
 		return 0;
 	}
+	if (cmd == "smdump" && argc == 4) { // smdump DB.ptu OUT.sm: the substitution model of a database as a model file
+		ifstream in(argv[2], ios_base::binary);
+		PTUnrooted tree;
+		if (loadProgInfo(in).bad()) return 1;
+		tree.load(in);
+		if (!in) { cerr << "cannot load " << argv[2] << endl; return 1; }
+		ofstream out(argv[3]);
+		out << tree.model;
+		return out.good() ? 0 : 1;
+	}
+	if (cmd == "ptucmp" && argc == 4) { // ptucmp A.ptu B.ptu: largest relative difference of the messages, inferred sequences equal?
+		PTUnrooted t[2];
+		for (int q = 0; q < 2; ++q) {
+			ifstream in(argv[2 + q], ios_base::binary);
+			if (loadProgInfo(in).bad()) return 1;
+			t[q].load(in);
+			if (!in) { cerr << "cannot load " << argv[2 + q] << endl; return 1; }
+		}
+		if (t[0].numNodes() != t[1].numNodes() || t[0].csLen != t[1].csLen) { cout << "shape differs" << endl; return 1; }
+		double worst = 0;
+		for (int d = 0; d < 2; ++d) {
+			const vector<double>& a = d ? t[0].dn : t[0].up;
+			const vector<double>& b = d ? t[1].dn : t[1].up;
+			for (size_t i = 0; i < a.size(); ++i) {
+				if (a[i] == b[i]) continue; // also -inf against -inf
+				const double e = fabs(a[i] - b[i]) / max(1.0, fabs(b[i]));
+				if (!(e <= worst)) worst = e;
+			}
+		}
+		char buf[64];
+		snprintf(buf, sizeof buf, "%.3g", worst);
+		cout << "max_rel_diff " << buf << " seq_equal " << (t[0].seq == t[1].seq ? 1 : 0) << endl;
+		return 0;
+	}
 	if (cmd == "locate" && argc == 3) { // locate DB.msa < patterns: count and sorted hits, the format of oracle/ref_csfm_probe.cpp
 		ifstream in(argv[2], ios_base::binary);
 		if (loadProgInfo(in).bad()) return 1;

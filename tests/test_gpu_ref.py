@@ -163,3 +163,24 @@ def test_fastq_input_gives_the_same_rows(refdb_dir):
     p = subprocess.run([CLI, os.path.join(d, name), fq, "-o", out, "-s", "1", "-S", "0", "--batch", "64"], capture_output=True, text=True)
     assert p.returncode == 0, p.stderr[-2000:]
     assert data_lines(out) == data_lines(os.path.join(GOLD, name + "_se0.tsv"))
+
+
+@pytest.mark.skipif(os.environ.get("HU_TEST_BUILDER_GPU") != "1", reason="the builder's device path has not been run on a GPU yet (set HU_TEST_BUILDER_GPU=1)")
+def test_builder_on_the_device(tmp_path):
+    """hmmufotu-build of this repository with the all-roots evaluation on the device (no --messages-from hook) on the
+    hand-written inputs of tests/golden/build: messages within 1e-9 of the reference builder's .ptu, inferred sequences
+    equal, skeleton identical.  Written when no GPU time was left in round 1: enable with HU_TEST_BUILDER_GPU=1."""
+    from hmmufotu_b200 import build
+    build.build_host()
+    b = os.path.join(HERE, "golden", "build")
+    tool = os.path.join(ROOT, "hmmufotu_b200", "bin", "hu_host_test")
+    sm = str(tmp_path / "hand.sm")
+    assert subprocess.run([tool, "smdump", os.path.join(b, "hand.ptu"), sm]).returncode == 0
+    r = subprocess.run([os.path.join(ROOT, "hmmufotu_b200", "bin", "hmmufotu-build"), os.path.join(b, "hand.fasta"), os.path.join(b, "hand.tree"),
+                        "-a", os.path.join(b, "hand_taxonomy.txt"), "-n", "hand", "--dm", os.path.join(b, "test_prior.dm"), "--sm", sm],
+                       cwd=str(tmp_path), capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-800:]
+    out = subprocess.run([tool, "ptucmp", str(tmp_path / "hand.ptu"), os.path.join(b, "hand.ptu")], capture_output=True, text=True).stdout.split()
+    assert float(out[1]) < 1e-9 and out[3] == "1", out
+    sk = lambda f: subprocess.run([tool, "ptuskel", f], capture_output=True, text=True).stdout
+    assert sk(str(tmp_path / "hand.ptu")) == sk(os.path.join(b, "hand.ptu"))

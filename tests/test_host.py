@@ -169,6 +169,47 @@ def test_builder_root_block_and_shape_estimate(exes, tmp_path):
         assert np.allclose([float(x) for x in ours[2].split()], [float(x) for x in stored[2].split()], rtol=1e-12, atol=0)
 
 
+@pytest.mark.skipif(not (os.path.exists(REF_DM) and os.path.exists(os.path.join(REF_TEST, "70_otus.fasta"))), reason="needs the reference's data files and test inputs")
+def test_builder_program_glue(exes, tmp_path):
+    """hmmufotu-build of this repository end to end on BASELINE.json configs[0]'s inputs, with the one device step (all-roots
+    evaluation + ancestral sequences) replaced by its TEST HOOK --messages-from (the messages of the reference-built
+    database; no arithmetic stands in for the device's): <db>.msa byte-identical, <db>.hmm identical but DATE, <db>.ptu with
+    the reference's skeleton, node records and edge blocks byte for byte (the files agree up to the root block / hash-ordered
+    index / model text at the very end), and the result loads as a database (`hmmufotu --check-db`)."""
+    import gzip
+    builder = os.path.join(BIN, "hmmufotu-build")
+    g = os.path.join(ROOT, "tests", "golden", "ref70")
+    for db, sm, extra in (("gg_70_otus_GTR", "gg_97_otus_GTR.sm", []), ("gg_70_otus_HKY85_dG", "gg_97_otus_HKY85.sm", ["-V", "-k", "4"])):
+        ref_ptu = str(tmp_path / (db + ".ref.ptu"))
+        with gzip.open(os.path.join(g, db + ".ptu.gz"), "rb") as f, open(ref_ptu, "wb") as o:
+            o.write(f.read())
+        r = subprocess.run([builder, os.path.join(REF_TEST, "70_otus.fasta"), os.path.join(REF_TEST, "70_otus.tree"), "-a",
+                            os.path.join(REF_TEST, "70_otus_taxonomy.txt"), "-n", db, "--dm", REF_DM, "--sm", os.path.join(os.path.dirname(REF_DM), sm),
+                            "--messages-from", ref_ptu] + extra, cwd=str(tmp_path), capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-800:]
+        assert open(tmp_path / (db + ".msa"), "rb").read() == open(os.path.join(g, db + ".msa"), "rb").read()
+        strip = lambda path: [ln for ln in open(path).read().split("\n") if not ln.startswith("DATE")]
+        assert strip(str(tmp_path / (db + ".hmm"))) == strip(os.path.join(g, db + ".hmm"))
+        ours = str(tmp_path / (db + ".ptu"))
+        assert _skeleton(exes[1], "ptuskel", ours) == _skeleton(exes[1], "ptuskel", ref_ptu)
+        a, b = open(ours, "rb").read(), open(ref_ptu, "rb").read()
+        same = next((i for i in range(0, min(len(a), len(b)), 4096) if a[i:i + 4096] != b[i:i + 4096]), min(len(a), len(b)))
+        assert same > 0.99 * len(b), (same, len(a), len(b))          # node records and every edge block (messages) are the reference's bytes
+        assert float(_skeleton(exes[1], "rootll", ours).split()[1]) < 1e-12
+        if extra:
+            assert _skeleton(exes[1], "dgshow", ours).split("\n")[0] == _skeleton(exes[1], "dgshow", ref_ptu).split("\n")[0]
+        chk = subprocess.run([exes[0], str(tmp_path / db), "--check-db"], capture_output=True, text=True)
+        assert chk.returncode == 0 and "Database loaded" in chk.stderr, chk.stderr[-500:]
+    # the hand-written inputs with this repository's own prior file and the model dumped from the reference-built database
+    b = os.path.join(ROOT, "tests", "golden", "build")
+    sm = str(tmp_path / "hand.sm")
+    assert subprocess.run([exes[1], "smdump", os.path.join(b, "hand.ptu"), sm]).returncode == 0
+    r = subprocess.run([builder, os.path.join(b, "hand.fasta"), os.path.join(b, "hand.tree"), "-a", os.path.join(b, "hand_taxonomy.txt"), "-n", "hand",
+                        "--dm", os.path.join(b, "test_prior.dm"), "--sm", sm, "--messages-from", os.path.join(b, "hand.ptu")], cwd=str(tmp_path), capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-800:]
+    assert _skeleton(exes[1], "ptucmp", str(tmp_path / "hand.ptu"), os.path.join(b, "hand.ptu")).split() == ["max_rel_diff", "0", "seq_equal", "1"]
+
+
 def test_builder_discrete_gamma(exes, tmp_path):
     """DiscreteGammaModel(K, alpha) as the builder derives it (src/DiscreteGammaModel.cpp:40-55, literal: Gamma(shape alpha,
     SCALE alpha) quantiles, rates not multiplied by K) with this repository's own incomplete-gamma code: against the block the
