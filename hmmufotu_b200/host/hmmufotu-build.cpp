@@ -1,9 +1,9 @@
 // hmmufotu-build over the C ABI (the reference's src/hmmufotu-build.cpp:308-502): aligned FASTA + Newick tree
-// [+ taxonomy] -> <db>.msa, <db>.hmm, <db>.ptu.  The host half (hu_build.cpp: MSA pruning / weights / consensus, profile
+// [+ taxonomy] -> <db>.msa, <db>.csfm, <db>.hmm, <db>.ptu.  The host half (hu_build.cpp: MSA pruning / weights / consensus, profile
 // training, tree skeleton, discrete Gamma, root block, shape estimate) is checked file by file against the reference's
 // builder on the CPU; the likelihood evaluation at every rooting and the ancestral sequences come from the device
 // (hu_db_create with hu_tree_desc.up == NULL, hu_db_get_messages / hu_db_get_seq; checked against the reference
-// builder's .ptu on the GPU).  No <db>.csfm is written: this repository's hmmufotu rebuilds the index from <db>.msa.
+// builder's .ptu on the GPU).  All four database files are written: <db>.msa, <db>.csfm, <db>.hmm, <db>.ptu.
 //
 //   hmmufotu-build MSA.fasta TREE.newick -n DBNAME --dm PRIOR.dm --sm MODEL.sm [-a TAXONOMY] [-r ROOTNAME]
 //                  [-f SYMFRAC] [-V [-k K]] [--intended-hmm] [--device N]
@@ -180,15 +180,21 @@ int main(int argc, char* argv[]) {
 	tree.updateRootLoglik();
 
 	// ---- files (:468-502) ----
-	const string msaFn = dbName + ".msa", hmmFn = dbName + ".hmm", ptuFn = dbName + ".ptu";
-	ofstream msaOut(msaFn.c_str(), ios_base::binary), hmmOut(hmmFn.c_str()), ptuOut(ptuFn.c_str(), ios_base::binary);
-	if (!msaOut.is_open() || !hmmOut.is_open() || !ptuOut.is_open()) { cerr << "Unable to write the database files of '" << dbName << "': " << ::strerror(errno) << endl; return EXIT_FAILURE; }
+	const string msaFn = dbName + ".msa", csfmFn = dbName + ".csfm", hmmFn = dbName + ".hmm", ptuFn = dbName + ".ptu";
+	ofstream msaOut(msaFn.c_str(), ios_base::binary), csfmOut(csfmFn.c_str(), ios_base::binary), hmmOut(hmmFn.c_str()), ptuOut(ptuFn.c_str(), ios_base::binary);
+	if (!msaOut.is_open() || !csfmOut.is_open() || !hmmOut.is_open() || !ptuOut.is_open()) { cerr << "Unable to write the database files of '" << dbName << "': " << ::strerror(errno) << endl; return EXIT_FAILURE; }
 	saveProgInfo(msaOut);
 	msa.save(msaOut);
+	{ // the seed index in libcds' serialisation, for the reference's hmmufotu (this repository's rebuilds it from the .msa)
+		CSFMIndex csfm;
+		csfm.build(msa);
+		saveProgInfo(csfmOut);
+		csfm.save(csfmOut, msa);
+	}
 	hmmOut << hmm;
 	saveProgInfo(ptuOut);
 	tree.save(ptuOut);
-	if (!msaOut || !hmmOut || !ptuOut) { cerr << "Unable to save the database files: " << ::strerror(errno) << endl; return EXIT_FAILURE; }
-	cerr << "Database '" << dbName << "' saved (no .csfm: hmmufotu rebuilds the index from the .msa)" << endl;
+	if (!msaOut || !csfmOut || !hmmOut || !ptuOut) { cerr << "Unable to save the database files: " << ::strerror(errno) << endl; return EXIT_FAILURE; }
+	cerr << "Database '" << dbName << "' saved" << endl;
 	return EXIT_SUCCESS;
 }

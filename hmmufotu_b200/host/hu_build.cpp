@@ -129,6 +129,175 @@ MSA& MSA::prune() { // src/MSA.cpp:87-138
 	return *this;
 }
 
+// ------------------------------------------------------------------ <db>.csfm in libcds' serialisation ----
+namespace {
+// libcds packs fields LSB first into 32-bit words (libcdsBasics.h: set_field / set_var_field)
+struct BitWords {
+	vector<uint32_t> w;
+	explicit BitWords(size_t nWords) : w(nWords, 0u) {}
+	void put(size_t pos, unsigned len, uint32_t x) { // bits pos .. pos+len-1 <- x
+		for (unsigned b = 0; b < len; ++b)
+			if ((x >> b) & 1u) w[(pos + b) / 32] |= 1u << ((pos + b) % 32);
+	}
+	void setBit(size_t pos) { w[pos / 32] |= 1u << (pos % 32); }
+	bool bit(size_t pos) const { return (w[pos / 32] >> (pos % 32)) & 1u; }
+};
+unsigned bitsOf(uint32_t n) { unsigned b = 0; while (n) { b++; n >>= 1; } return b; }
+size_t uintLen(uint64_t e, uint64_t n) { return (size_t) ((e * n + 31) / 32); }
+
+// table_offset(15) of libcds (TableOffsetRRR.cpp): a 15-bit block is stored as (class = popcount, offset = its index in
+// the enumeration of that class: positions chosen in increasing order, lowest first position first); an offset takes
+// bits(C(15, class) - 1) bits
+struct RrrTable {
+	enum { U = 15 };
+	vector<uint16_t> offsetOf; // [block value]
+	unsigned logBinom[U + 1];
+	unsigned next;
+	void gen(unsigned cls, unsigned placed, unsigned from, uint32_t value) {
+		if (cls == placed) { offsetOf[value] = (uint16_t) next++; return; }
+		for (unsigned i = from; i < U; ++i) gen(cls, placed + 1, i + 1, value | (1u << i));
+	}
+	RrrTable() : offsetOf(1u << U, 0) {
+		uint32_t binom[U + 1][U + 1];
+		for (int i = 0; i <= U; ++i)
+			for (int j = 0; j <= U; ++j) binom[i][j] = j == 0 || j == i ? 1 : (j > i ? 0 : binom[i - 1][j - 1] + binom[i - 1][j]);
+		for (unsigned c = 0; c <= U; ++c) {
+			logBinom[c] = (c == 0 || c == U) ? 0 : bitsOf(binom[U][c] - 1);
+			next = 0;
+			gen(c, 0, 0, 0);
+		}
+	}
+};
+}
+namespace {
+// BitSequenceRRR::build + save (BitSequenceRRR.cpp:51-87, 379-402): classes in C (4 bits each), offsets in O; the
+// samplings are rebuilt by the loader
+void saveRRR(ostream& out, const BitWords& bm, size_t len, uint32_t sampleRate, const RrrTable& E) {
+	const uint32_t cLen = (uint32_t) (len / 15 + (len % 15 != 0)), cFieldBits = bitsOf(15);
+	BitWords C(uintLen(cLen, cFieldBits));
+	vector<uint16_t> blocks(cLen);
+	uint64_t ones = 0;
+	uint32_t oBits = 0;
+	for (uint32_t i = 0; i < cLen; ++i) {
+		uint32_t v = 0;
+		const size_t lo = (size_t) i * 15, hi = min(len - 1, (size_t) (i + 1) * 15 - 1);
+		for (size_t p = lo; p <= hi; ++p) if (bm.bit(p)) v |= 1u << (p - lo);
+		blocks[i] = (uint16_t) v;
+		const unsigned cls = (unsigned) __builtin_popcount(v);
+		C.put((size_t) i * cFieldBits, cFieldBits, cls);
+		ones += cls;
+		oBits += E.logBinom[cls];
+	}
+	const uint32_t oLen = (uint32_t) uintLen(1, oBits);
+	BitWords O(oLen);
+	size_t oPos = 0;
+	for (uint32_t i = 0; i < cLen; ++i) {
+		const unsigned nb = E.logBinom[__builtin_popcount(blocks[i])];
+		O.put(oPos, nb, E.offsetOf[blocks[i]]);
+		oPos += nb;
+	}
+	const uint32_t hdr = 2; // RRR02_HDR
+	const uint64_t length = len;
+	out.write((const char*) &hdr, 4);
+	out.write((const char*) &length, 8);
+	out.write((const char*) &ones, 8);
+	out.write((const char*) &cLen, 4);
+	out.write((const char*) &cFieldBits, 4);
+	out.write((const char*) &oLen, 4);
+	out.write((const char*) &oBits, 4);
+	out.write((const char*) &sampleRate, 4);
+	out.write((const char*) C.w.data(), (streamsize) (C.w.size() * 4));
+	out.write((const char*) O.w.data(), (streamsize) (O.w.size() * 4));
+}
+}
+
+ostream& CSFMIndex::save(ostream& out, const MSA& msa) const {
+	const int32_t N = concatLen + 1;
+	saveString("IUPACNucl", out);                 // abc->getName()
+	const char gapCh = '-';
+	out.write(&gapCh, 1);
+	const uint16_t cs16 = (uint16_t) csLen;
+	out.write((const char*) &cs16, 2);
+	out.write((const char*) &concatLen, 4);
+	int32_t C256[256];
+	memset(C256, 0, sizeof C256);
+	for (int b = 0; b < 6; ++b) C256[b] = C[b];
+	out.write((const char*) C256, sizeof C256);
+	saveString(" " + msa.CS, out);                // csSeq: dummy position 0
+	vector<double> ident(csLen + 1, 0.0);         // identityAt(j) = largest raw residue count / numSeq
+	for (int j = 0; j < csLen; ++j) {
+		int cnt[4] = {0, 0, 0, 0};
+		for (unsigned i = 0; i < msa.numSeq; ++i) {
+			const int8_t b = DNA::encode((char) ::toupper(msa.residualAt(i, j)));
+			if (b >= 0) cnt[b]++;
+		}
+		ident[j + 1] = max(max(cnt[0], cnt[1]), max(cnt[2], cnt[3])) / (double) msa.numSeq;
+	}
+	out.write((const char*) ident.data(), (streamsize) (ident.size() * sizeof(double)));
+	// concat2CS of the file: 0-based text positions (this class keeps them 1-based with a dummy entry in front)
+	out.write((const char*) (concat2CS.data() + 1), (streamsize) ((size_t) N * sizeof(uint16_t)));
+	// every 4th text position is sampled (SA_SAMPLE_RATE), in suffix-array order; a bitmap marks the sampled ranks
+	vector<uint32_t> sampled;
+	BitWords B((size_t) N / 32 + 1);
+	for (int32_t i = 0; i < N; ++i) {
+		const int32_t v = sa[i] - 1; // 0-based suffix position
+		if (v % 4 == 0) { sampled.push_back((uint32_t) v); B.setBit(i); }
+	}
+	sampled.resize((size_t) N / 4 + 1, 0u);
+	out.write((const char*) sampled.data(), (streamsize) ((size_t) (concatLen / 4) * sizeof(uint32_t)));
+	const RrrTable E;
+	saveRRR(out, B, (size_t) N, 8, E);            // saIdx, RRR_SAMPLE_RATE
+	// WaveletTreeNoptrs over the BWT symbols 0..4 (WaveletTreeNoptrs.cpp:157-225, 245-257), MapperNone, RRR levels
+	vector<uint8_t> sym(N);
+	uint32_t maxV = 0;
+	for (int32_t i = 0; i < N; ++i) {
+		int b = 0;
+		for (int q = 0; q < 5; ++q) if ((rank[(size_t) i / 64].mask[q] >> (i % 64)) & 1ull) b = q;
+		sym[i] = (uint8_t) b;
+		maxV = max(maxV, (uint32_t) b);
+	}
+	const uint32_t height = bitsOf(maxV);
+	vector<uint32_t> OCC(maxV + 2, 0u);
+	for (int32_t i = 0; i < N; ++i) OCC[sym[i] + 1]++;
+	for (uint32_t i = 1; i <= maxV + 1; ++i)     // symbols that never occur are appended once
+		if (OCC[i] == 0) { OCC[i]++; sym.push_back((uint8_t) (i - 1)); }
+	const uint64_t newN = sym.size(), length = (uint64_t) N;
+	for (uint32_t i = 1; i <= maxV + 1; ++i) OCC[i] += OCC[i - 1];
+	vector<BitWords> levels(height, BitWords((size_t) newN / 32 + 1));
+	{ // build_level: level by level, a stable split of every node's range by the level's bit (most significant first)
+		vector<uint8_t> cur(sym), nxt(sym.size());
+		vector<pair<size_t, size_t> > ranges(1, make_pair((size_t) 0, (size_t) newN)), nextRanges;
+		for (uint32_t level = 0; level < height; ++level) {
+			const unsigned bitIx = height - level - 1;
+			nextRanges.clear();
+			for (size_t r = 0; r < ranges.size(); ++r) {
+				const size_t off = ranges[r].first, len = ranges[r].second;
+				size_t nl = 0;
+				for (size_t i = 0; i < len; ++i) nl += !((cur[off + i] >> bitIx) & 1u);
+				size_t l = off, rr = off + nl;
+				for (size_t i = 0; i < len; ++i) {
+					if ((cur[off + i] >> bitIx) & 1u) { levels[level].setBit(off + i); nxt[rr++] = cur[off + i]; }
+					else nxt[l++] = cur[off + i];
+				}
+				nextRanges.push_back(make_pair(off, nl));
+				nextRanges.push_back(make_pair(off + nl, len - nl));
+			}
+			cur.swap(nxt);
+			ranges.swap(nextRanges);
+		}
+	}
+	const uint32_t wtHdr = 3, mapHdr = 2;         // WVTREE_NOPTRS_HDR, MAPPER_NONE_HDR
+	out.write((const char*) &wtHdr, 4);
+	out.write((const char*) &newN, 8);
+	out.write((const char*) &length, 8);
+	out.write((const char*) &maxV, 4);
+	out.write((const char*) &height, 4);
+	out.write((const char*) &mapHdr, 4);
+	for (uint32_t level = 0; level < height; ++level) saveRRR(out, levels[level], (size_t) newN, 8, E);
+	out.write((const char*) OCC.data(), (streamsize) (OCC.size() * 4));
+	return out;
+}
+
 // ------------------------------------------------------------------ discrete Gamma ----
 // The reference takes these from Boost.Math (gamma_p, quantile(gamma_distribution)); Boost is not a dependency here.
 double gammaP(double a, double x) {

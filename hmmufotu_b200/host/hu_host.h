@@ -103,6 +103,10 @@ public:
 	bool interval(const std::string& pattern, int32_t& start, int32_t& end) const { return search(pattern, start, end); }
 	// ... and the random hit inside a non-empty interval (the rand() call and what follows it in locateOne)
 	CSLoc locateAt(const std::string& pattern, int32_t start, int32_t end) const;
+	// <db>.csfm as the reference's hmmufotu loads it (src/CSFMIndex.cpp:176-230): the index in libcds' serialisation --
+	// sampled suffix array + RRR bitmap of the sampled positions + pointerless wavelet tree over the BWT with RRR-compressed
+	// levels (hu_build.cpp).  msa: the alignment this index was built from.
+	std::ostream& save(std::ostream& out, const MSA& msa) const;
 private:
 	bool search(const std::string& pattern, int32_t& start, int32_t& end) const;
 	int32_t occ(int b, int32_t i) const;           // # of symbol b in BWT[0..i]

@@ -9,6 +9,7 @@
 //   hmmbuild FASTA NAME PRIOR.dm OUT   the builder's profile training (hu_build.cpp)
 //   rootll DB.ptu      root log-likelihood block recomputed from the stored messages; shape estimate from the messages
 //   dgamma K ALPHA / dgshow DB.ptu   discrete-Gamma break points and rates, built here or as stored in a database
+//   csfmwrite DB.msa OUT.csfm   the index file as the reference's hmmufotu loads it (libcds serialisation)
 //   seeds DB FASTA S   CSFM seed search of every read with srand(S): prints the ViterbiAlignPaths
 #include "hu_host.h"
 
@@ -238,6 +239,19 @@ int main(int argc, char** argv) {
 		snprintf(buf, sizeof buf, "%.3g", worst);
 		cout << "max_rel_diff " << buf << " seq_equal " << (t[0].seq == t[1].seq ? 1 : 0) << endl;
 		return 0;
+	}
+	if (cmd == "csfmwrite" && argc == 4) { // csfmwrite DB.msa OUT.csfm: the index file in libcds' serialisation
+		ifstream in(argv[2], ios_base::binary);
+		if (loadProgInfo(in).bad()) return 1;
+		MSA msa;
+		msa.load(in);
+		if (!in) { cerr << "cannot load " << argv[2] << endl; return 1; }
+		CSFMIndex csfm;
+		csfm.build(msa);
+		ofstream out(argv[3], ios_base::binary);
+		saveProgInfo(out);
+		csfm.save(out, msa);
+		return out.good() ? 0 : 1;
 	}
 	if (cmd == "locate" && argc == 3) { // locate DB.msa < patterns: count and sorted hits, the format of oracle/ref_csfm_probe.cpp
 		ifstream in(argv[2], ios_base::binary);

@@ -13,7 +13,7 @@ Writes tests/golden/ref70/:
   se0.aln.fasta                               the -a alignment output of se0
   csfm_locate.{txt,tsv}                       patterns (k-mers cut from se1's reads, plus misses) and what the reference's own
                                               CSFMIndex (oracle/_ref/csfm_probe on gg_70_otus_GTR.csfm) counts and locates for them
-  ../build/hand.{msa,hmm,ptu}                    the reference's hmmufotu-build on the hand-written inputs next to them (quoted label,
+  ../build/hand.{msa,csfm,hmm,ptu}                    the reference's hmmufotu-build on the hand-written inputs next to them (quoted label,
                                               negative and missing branch lengths, partly canonical taxonomy, lower case, N,
                                               nothing to prune): what tests/test_host.py compares the host half of the builder with
   se0.{weighted,ml,height,single}.tsv         se0 again with -m weighted / --ML / --prior height / --single (NGCL alignment mode)
@@ -78,7 +78,6 @@ def main():
         subprocess.run([os.path.join(REF, "csfm_probe"), "gg_70_otus_GTR.csfm"], stdin=fin, stdout=fout, check=True)
     bdir = os.path.join(HERE, "build")
     run(os.path.join(REF, "hmmufotu-build"), "hand.fasta", "hand.tree", "-a", "hand_taxonomy.txt", "-n", "hand", "-s", "GTR", cwd=bdir)
-    os.remove(os.path.join(bdir, "hand.csfm"))
     for f in sorted(os.listdir(OUT)):
         print("%10d  %s" % (os.path.getsize(f), f))
 

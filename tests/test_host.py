@@ -188,6 +188,7 @@ def test_builder_program_glue(exes, tmp_path):
                             "--messages-from", ref_ptu] + extra, cwd=str(tmp_path), capture_output=True, text=True)
         assert r.returncode == 0, r.stderr[-800:]
         assert open(tmp_path / (db + ".msa"), "rb").read() == open(os.path.join(g, db + ".msa"), "rb").read()
+        assert open(tmp_path / (db + ".csfm"), "rb").read() == open(os.path.join(g, db + ".csfm"), "rb").read()
         strip = lambda path: [ln for ln in open(path).read().split("\n") if not ln.startswith("DATE")]
         assert strip(str(tmp_path / (db + ".hmm"))) == strip(os.path.join(g, db + ".hmm"))
         ours = str(tmp_path / (db + ".ptu"))
@@ -208,6 +209,25 @@ def test_builder_program_glue(exes, tmp_path):
                         "--dm", os.path.join(b, "test_prior.dm"), "--sm", sm, "--messages-from", os.path.join(b, "hand.ptu")], cwd=str(tmp_path), capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-800:]
     assert _skeleton(exes[1], "ptucmp", str(tmp_path / "hand.ptu"), os.path.join(b, "hand.ptu")).split() == ["max_rel_diff", "0", "seq_equal", "1"]
+
+
+def test_builder_csfm_file_is_the_references(exes, tmp_path):
+    """<db>.csfm in libcds' serialisation (sampled suffix array, RRR bitmap of the sampled ranks, pointerless wavelet tree over
+    the BWT with RRR-compressed levels; hu_build.cpp) written from <db>.msa: byte-identical to the file the reference's builder
+    wrote, for 70_otus (544 055 bytes) and the hand-written alignment; and the reference's own loader answers from it exactly
+    as from its own file (oracle/_ref/csfm_probe, where built)."""
+    for msa, want in ((os.path.join(ROOT, "tests", "golden", "ref70", "gg_70_otus_GTR.msa"), os.path.join(ROOT, "tests", "golden", "ref70", "gg_70_otus_GTR.csfm")),
+                      (os.path.join(ROOT, "tests", "golden", "build", "hand.msa"), os.path.join(ROOT, "tests", "golden", "build", "hand.csfm"))):
+        out = str(tmp_path / (os.path.basename(msa) + ".csfm"))
+        r = subprocess.run([exes[1], "csfmwrite", msa, out], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        assert open(out, "rb").read() == open(want, "rb").read()
+    probe = os.path.join(ROOT, "oracle", "_ref", "csfm_probe")
+    if os.path.exists(probe):
+        g = os.path.join(ROOT, "tests", "golden", "ref70")
+        with open(os.path.join(g, "csfm_locate.txt")) as fin:
+            ref = subprocess.run([probe, str(tmp_path / "gg_70_otus_GTR.msa.csfm")], stdin=fin, capture_output=True, text=True)
+        assert ref.returncode == 0 and ref.stdout == open(os.path.join(g, "csfm_locate.tsv")).read()
 
 
 def test_builder_discrete_gamma(exes, tmp_path):
