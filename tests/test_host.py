@@ -230,6 +230,89 @@ def test_builder_csfm_file_is_the_references(exes, tmp_path):
         assert ref.returncode == 0 and ref.stdout == open(os.path.join(g, "csfm_locate.tsv")).read()
 
 
+def _sim_statistics(fasta, ptu, gap_frac):
+    """z-scores of a keep-gap simulation against the model it was drawn from: total log-probability of the sampled bases
+    (per column: normalised exp(log(P(v rc) e^U) + log(P(v (1-rc)) e^V)) at the read's own branch and branching point),
+    number of gap columns (weighted gap fraction per column), plus the sample moments of start and window length."""
+    import oracle_py as O
+    from refdb import read_fasta
+    model = O.OracleModel(ptu.model)
+    s_obs = s_exp = s_var = 0.0
+    g_obs = g_exp = g_var = 0.0
+    starts, lens = [], []
+    for rid, desc, seq in read_fasta(fasta):
+        f = dict(kv.split("=", 1) for kv in desc.strip(";").split(";") if "=" in kv)
+        c, p = (int(x) for x in f["branchID"].split("->"))
+        rc, a, b = float(f["branchPoint"]), int(f["csStart"]), int(f["csEnd"])
+        assert ptu.parent[c] == p and len(seq) == ptu.cs_len and 0.0 <= rc < 1.0 and 0 <= a <= b < ptu.cs_len
+        assert set(seq[:a]) <= {"."} and set(seq[b + 1:]) <= {"."}
+        starts.append(a); lens.append(b - a)
+        v = ptu.blen[c]
+        P1, P2 = model.Pr(v * rc), model.Pr(v * (1 - rc))
+        U, V = ptu.up[c, a:b + 1], ptu.dn[c, a:b + 1]
+        lu = np.log(np.exp(U - U.max(1, keepdims=True)) @ P1.T) + U.max(1, keepdims=True)
+        lv = np.log(np.exp(V - V.max(1, keepdims=True)) @ P2.T) + V.max(1, keepdims=True)
+        w = lu + lv
+        w = np.exp(w - w.max(1, keepdims=True))
+        pr = w / w.sum(1, keepdims=True)
+        win = np.frombuffer(seq[a:b + 1].encode(), dtype=np.uint8)
+        gap = win == ord("-")
+        gf = gap_frac[a:b + 1]
+        g_obs += gap.sum(); g_exp += gf.sum(); g_var += (gf * (1 - gf)).sum()
+        code = np.full(win.shape, -1)
+        for k, ch in enumerate("ACGT"):
+            code[win == ord(ch)] = k
+        assert ((code >= 0) | gap).all()
+        nz = ~gap
+        lp = np.log(np.maximum(pr[nz], 1e-300))
+        s_obs += lp[np.arange(nz.sum()), code[nz]].sum()
+        e1 = (pr[nz] * lp).sum(1)
+        s_exp += e1.sum()
+        s_var += ((pr[nz] * lp * lp).sum(1) - e1 * e1).sum()
+    return (s_obs - s_exp) / np.sqrt(s_var), (g_obs - g_exp) / np.sqrt(g_var), np.array(starts), np.array(lens)
+
+
+def test_simulator_draws_from_the_tree_model(exes, tmp_path):
+    """hmmufotu-sim of this repository (statistical parity: the reference draws from Boost's generators):
+    3 000 keep-gap reads from the reference-built GTR database follow the model they claim to be drawn from -- sampled bases,
+    gap columns, window starts and lengths -- within 4.5 sigma, and the reference's own simulator passes the same checks
+    where it is built."""
+    import gzip
+    from refdb import load_ptu
+    g = os.path.join(ROOT, "tests", "golden", "ref70")
+    with gzip.open(os.path.join(g, "gg_70_otus_GTR.ptu.gz"), "rb") as f, open(tmp_path / "db.ptu", "wb") as o:
+        o.write(f.read())
+    with open(os.path.join(g, "gg_70_otus_GTR.msa"), "rb") as f, open(tmp_path / "db.msa", "wb") as o:
+        o.write(f.read())
+    ptu = load_ptu(str(tmp_path / "db.ptu"))
+    # weighted gap fraction per column from the .msa's auxiliary blocks: ... resWCount (4 x csLen f64), gapWCount (csLen f64) at the end
+    raw = open(tmp_path / "db.msa", "rb").read()
+    L = ptu.cs_len
+    gapw = np.frombuffer(raw[-8 * L:], dtype="<f8")
+    resw = np.frombuffer(raw[-8 * 5 * L:-8 * L], dtype="<f8").reshape(L, 4).sum(1)
+    gap_frac = gapw / (gapw + resw)
+    sims = [(os.path.join(BIN, "hmmufotu-sim"), "ours")]
+    if os.path.exists(os.path.join(ROOT, "oracle", "_ref", "hmmufotu-sim")):
+        sims.append((os.path.join(ROOT, "oracle", "_ref", "hmmufotu-sim"), "reference"))
+    for exe, tag in sims:
+        out = str(tmp_path / (tag + ".fa"))
+        r = subprocess.run([exe, str(tmp_path / "db"), out, "-N", "3000", "-S", "11", "-k"], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-500:]
+        zb, zg, starts, lens = _sim_statistics(out, ptu, gap_frac)
+        assert abs(zb) < 4.5 and abs(zg) < 4.5, (tag, zb, zg)
+        assert abs(lens.mean() - 500) < 4.5 * 30 / np.sqrt(len(lens)) + 1.0 and abs(lens.std() - 30) < 3.0, (tag, lens.mean(), lens.std())
+        assert starts.min() >= 0 and (starts + lens).max() < L
+        # uniform start, cut where the window would leave the alignment: mean (L - 500) / 2 within sampling error
+        assert abs(starts.mean() - (L - 500) / 2) < 4.5 * (L - 500) / np.sqrt(12 * len(starts)) + 2.0, (tag, starts.mean())
+    # un-aligned single-end and paired-end output: read length, mate = reverse complement of the insert
+    o1, o2 = str(tmp_path / "pe_1.fa"), str(tmp_path / "pe_2.fa")
+    r = subprocess.run([sims[0][0], str(tmp_path / "db"), o1, o2, "-N", "50", "-S", "5", "-r", "150"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-500:]
+    from refdb import read_fasta
+    a, b = read_fasta(o1), read_fasta(o2)
+    assert len(a) == len(b) == 50 and all(x[0] == y[0] and len(x[2]) <= 150 and set(x[2]) <= set("ACGT") for x, y in zip(a, b))
+
+
 def test_builder_discrete_gamma(exes, tmp_path):
     """DiscreteGammaModel(K, alpha) as the builder derives it (src/DiscreteGammaModel.cpp:40-55, literal: Gamma(shape alpha,
     SCALE alpha) quantiles, rates not multiplied by K) with this repository's own incomplete-gamma code: against the block the
