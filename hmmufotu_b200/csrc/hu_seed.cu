@@ -319,6 +319,11 @@ __global__ void __launch_bounds__(HU_SEL_THREADS) seedSelectKernel(SeedArgs a, i
 // (__unguarded_partition) is evaluated in parallel from two bitmaps (elements >= pivot, elements <= pivot):
 // the k-th stop of the left scan is swapped with the k-th stop of the right scan while the former lies left
 // of the latter, which prefix counts over the bitmaps decide for every element at once.
+// Shape of a read's replay (phase clocks: profiles/r1d_summary.md): level 1 works straight on the key vector (flag pass
+// with 128-bit loads, then only the left part [0, cut) is materialised as (key, position) pairs, row-wise, from a
+// rank-ordered list of the right stops that move); later levels swap in place in the CTA's scratch row; once the live range
+// is <= HU_LIT_SMEM pairs and nothing is pending outside it, it moves into shared memory for good; ranges <= HU_LIT_SMALL
+// are finished by one warp (litWarpIntrosort); the final insertion sort is a rank computation over <= maxNSeed + 17 pairs.
 #define HU_LIT_THREADS 512
 #define HU_LIT_UNROLL 8 // key loads in flight per lane in the flag passes
 #define HU_LIT_VEC 8    // 128-bit key loads a lane has in flight in the first flag pass
@@ -345,11 +350,6 @@ typedef unsigned long long lit_t;               // (key << 32) | candidate posit
 __device__ __forceinline__ uint32_t ldKeyNow(const uint32_t* p) {
 	uint32_t v;
 	asm volatile("ld.global.u32 %0, [%1];" : "=r"(v) : "l"(p));
-	return v;
-}
-__device__ __forceinline__ unsigned long long ldPairNow(const unsigned long long* p) {
-	unsigned long long v;
-	asm volatile("ld.global.u64 %0, [%1];" : "=l"(v) : "l"(p));
 	return v;
 }
 __device__ __forceinline__ uint4 ldKey4Now(const uint32_t* p) {
@@ -394,14 +394,6 @@ __device__ __forceinline__ void ldPairKeyx8(const unsigned long long* p, uint32_
 		: "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
 		: "l"(p));
 }
-__device__ __forceinline__ void ldKeyx4(const uint32_t* p0, const uint32_t* p1, const uint32_t* p2, const uint32_t* p3, uint32_t (&v)[4]) {
-	asm volatile(
-		"ld.global.u32 %0, [%4];\n\t"
-		"ld.global.u32 %1, [%5];\n\t"
-		"ld.global.u32 %2, [%6];\n\t"
-		"ld.global.u32 %3, [%7];"
-		: "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "l"(p0), "l"(p1), "l"(p2), "l"(p3));
-}
 __device__ __forceinline__ void ldPairx4(const unsigned long long* p0, const unsigned long long* p1, const unsigned long long* p2,
 		const unsigned long long* p3, unsigned long long (&v)[4]) {
 	asm volatile(
@@ -426,18 +418,6 @@ __device__ __forceinline__ void litMedianToFirst(Arr& w, int result, int a, int 
 	} else if (qa < qc) litSwap(w, result, a);
 	else if (qb < qc) litSwap(w, result, c);
 	else litSwap(w, result, b);
-}
-template <typename Arr>
-__device__ __forceinline__ int litPartitionSeq(Arr& w, int first, int last, int pivot) { // __unguarded_partition, literally
-	const uint32_t pv = LIT_KEY(w[pivot]);
-	for (;;) {
-		while (LIT_KEY(w[first]) < pv) ++first;
-		--last;
-		while (pv < LIT_KEY(w[last])) --last;
-		if (!(first < last)) return first;
-		litSwap(w, first, last);
-		++first;
-	}
 }
 // n-th (0-based, from bit 0) set bit of a word: five popc steps (the __fns intrinsic is a long dependent sequence)
 __device__ __forceinline__ int litNthBit(uint32_t bits, int n) {
