@@ -237,9 +237,16 @@ int main(int argc, char* argv[]) {
 	hmmIn >> hmm;
 	if (hmmIn.bad() || hmmIn.fail()) { cerr << "Unable to read HMM profile '" << hmmFn << "'" << endl; return EXIT_FAILURE; }
 	if (hmm.getProfileSize() > csLen) { cerr << "Error: HMM profile size is found greater than the MSA CS length" << endl; return EXIT_FAILURE; }
-	// the reference loads <db>.csfm (libcds serialisation); the same index is rebuilt from the MSA here
+	// <db>.csfm (libcds serialisation, src/hmmufotu.cpp:470-480) when the database has one, else the same index rebuilt from
+	// the MSA (databases written by tools that do not produce the file): the two are equal field for field
 	CSFMIndex csfm;
-	csfm.build(msa);
+	{
+		ifstream csfmIn((dbName + ".csfm").c_str(), ios_base::binary);
+		if (csfmIn.is_open()) {
+			if (loadProgInfo(csfmIn).bad() || !csfm.load(csfmIn)) { cerr << "Unable to load CSFM-index '" << dbName << ".csfm'" << endl; return EXIT_FAILURE; }
+		} else
+			csfm.build(msa);
+	}
 	if (csfm.getCSLen() != csLen) { cerr << "Error: Unmatched CS length between CSFM-index and MSA data" << endl; return EXIT_FAILURE; }
 	if (loadProgInfo(ptuIn).bad()) return EXIT_FAILURE;
 	PTUnrooted ptu;

@@ -298,6 +298,156 @@ ostream& CSFMIndex::save(ostream& out, const MSA& msa) const {
 	return out;
 }
 
+namespace {
+// BitSequenceRRR::load: header, classes, offsets -> the plain bitmap
+bool loadRRR(istream& in, vector<uint8_t>& bits, const RrrTable& E, const vector<vector<uint16_t> >& valueOf) {
+	uint32_t hdr = 0, cLen = 0, cFieldBits = 0, oLen = 0, oBits = 0, sampleRate = 0;
+	uint64_t length = 0, ones = 0;
+	in.read((char*) &hdr, 4); in.read((char*) &length, 8); in.read((char*) &ones, 8);
+	in.read((char*) &cLen, 4); in.read((char*) &cFieldBits, 4); in.read((char*) &oLen, 4); in.read((char*) &oBits, 4); in.read((char*) &sampleRate, 4);
+	if (!in || hdr != 2 || cFieldBits != 4 || length > ((uint64_t) 1 << 40) || cLen != length / 15 + (length % 15 != 0)) return false;
+	BitWords C(uintLen(cLen, cFieldBits)), O(oLen);
+	in.read((char*) C.w.data(), (streamsize) (C.w.size() * 4));
+	in.read((char*) O.w.data(), (streamsize) (O.w.size() * 4));
+	if (!in) return false;
+	bits.assign(length, 0);
+	size_t oPos = 0;
+	for (uint32_t i = 0; i < cLen; ++i) {
+		unsigned cls = 0;
+		for (unsigned b = 0; b < 4; ++b) cls |= (unsigned) C.bit((size_t) i * 4 + b) << b;
+		if (cls > 15) return false;
+		const unsigned nb = E.logBinom[cls];
+		uint32_t off = 0;
+		for (unsigned b = 0; b < nb; ++b) off |= (uint32_t) O.bit(oPos + b) << b;
+		oPos += nb;
+		if (off >= valueOf[cls].size()) return false;
+		const uint16_t v = valueOf[cls][off];
+		for (unsigned b = 0; b < 15 && (size_t) i * 15 + b < length; ++b) bits[(size_t) i * 15 + b] = (v >> b) & 1u;
+	}
+	return true;
+}
+}
+
+istream& CSFMIndex::load(istream& in) {
+	string abcName;
+	char gapCh;
+	uint16_t cs16 = 0;
+	loadString(abcName, in);
+	in.read(&gapCh, 1);
+	in.read((char*) &cs16, 2);
+	in.read((char*) &concatLen, 4);
+	int32_t C256[256];
+	in.read((char*) C256, sizeof C256);
+	if (!in || concatLen < 1) { in.setstate(ios_base::badbit); return in; }
+	csLen = cs16;
+	for (int b = 0; b < 6; ++b) C[b] = C256[b];
+	const int32_t N = concatLen + 1;
+	string csSeq;
+	loadString(csSeq, in);
+	in.ignore((streamsize) ((size_t) (csLen + 1) * sizeof(double))); // csIdentity: not used on the run path
+	concat2CS.assign((size_t) N + 1, 0);                              // 1-based here, 0-based in the file
+	in.read((char*) (concat2CS.data() + 1), (streamsize) ((size_t) N * sizeof(uint16_t)));
+	vector<uint32_t> sampled((size_t) concatLen / 4);                 // every 4th text position, in suffix-array order
+	in.read((char*) sampled.data(), (streamsize) (sampled.size() * sizeof(uint32_t)));
+	const RrrTable E;
+	vector<vector<uint16_t> > valueOf(16);
+	for (uint32_t v = 0; v < (1u << 15); ++v) {
+		vector<uint16_t>& list = valueOf[__builtin_popcount(v)];
+		if (list.size() <= E.offsetOf[v]) list.resize((size_t) E.offsetOf[v] + 1);
+		list[E.offsetOf[v]] = (uint16_t) v;
+	}
+	vector<uint8_t> bm;
+	if (!loadRRR(in, bm, E, valueOf) || bm.size() != (size_t) N) { in.setstate(ios_base::badbit); return in; } // saIdx
+	// the row of text position 0 (its BWT symbol is the wrapped-around terminator): the sampled rank whose value is 0, or
+	// the one sampled rank the file does not carry (it holds concatLen / 4 values for ceil(N / 4) sampled rows)
+	int32_t wrapRow = -1;
+	{
+		size_t k = 0, missing = (size_t) -1;
+		for (int32_t i = 0; i < N && wrapRow < 0; ++i)
+			if (bm[i]) {
+				if (k < sampled.size()) { if (sampled[k] == 0) wrapRow = i; }
+				else missing = (size_t) i;
+				k++;
+			}
+		if (wrapRow < 0 && missing != (size_t) -1) wrapRow = (int32_t) missing;
+		if (wrapRow < 0) { in.setstate(ios_base::badbit); return in; }
+	}
+	uint32_t wtHdr = 0, maxV = 0, height = 0, mapHdr = 0;
+	uint64_t newN = 0, length = 0;
+	in.read((char*) &wtHdr, 4); in.read((char*) &newN, 8); in.read((char*) &length, 8); in.read((char*) &maxV, 4); in.read((char*) &height, 4); in.read((char*) &mapHdr, 4);
+	if (!in || wtHdr != 3 || mapHdr != 2 || length != (uint64_t) N || newN < length || maxV > 4 || height > 3) { in.setstate(ios_base::badbit); return in; }
+	// the wavelet tree, undone level by level: a level's bit is the symbol's next bit (most significant first), and the
+	// elements of every node move on in a stable split
+	vector<uint8_t> sym(newN, 0);
+	{
+		vector<uint32_t> orig(newN), next(newN);
+		for (uint64_t i = 0; i < newN; ++i) orig[i] = (uint32_t) i;
+		vector<pair<size_t, size_t> > ranges(1, make_pair((size_t) 0, (size_t) newN)), nextRanges;
+		for (uint32_t level = 0; level < height; ++level) {
+			if (!loadRRR(in, bm, E, valueOf) || bm.size() != newN) { in.setstate(ios_base::badbit); return in; }
+			nextRanges.clear();
+			for (size_t r = 0; r < ranges.size(); ++r) {
+				const size_t off = ranges[r].first, len = ranges[r].second;
+				size_t nl = 0;
+				for (size_t i = 0; i < len; ++i) nl += !bm[off + i];
+				size_t l = off, rr = off + nl;
+				for (size_t i = 0; i < len; ++i) {
+					if (bm[off + i]) { sym[orig[off + i]] |= (uint8_t) (1u << (height - level - 1)); next[rr++] = orig[off + i]; }
+					else next[l++] = orig[off + i];
+				}
+				nextRanges.push_back(make_pair(off, nl));
+				nextRanges.push_back(make_pair(off + nl, len - nl));
+			}
+			orig.swap(next);
+			ranges.swap(nextRanges);
+		}
+	}
+	in.ignore((streamsize) ((size_t) (maxV + 2) * 4)); // OCC
+	if (!in) { in.setstate(ios_base::badbit); return in; }
+	// rank blocks over the BWT
+	rank.assign((size_t) N / 64 + 2, RankBlock());
+	uint32_t run[5] = {0, 0, 0, 0, 0};
+	for (int32_t i = 0; i < N; ++i) {
+		RankBlock& rb = rank[(size_t) i / 64];
+		if (i % 64 == 0)
+			for (int b = 0; b < 5; ++b) { rb.cnt[b] = run[b]; rb.mask[b] = 0; }
+		const int b = sym[i] > 4 ? 0 : sym[i];
+		rb.mask[b] |= 1ull << (i % 64);
+		run[b]++;
+	}
+	// the suffix array from the BWT: the lone terminator is the smallest suffix (row 0, text position N - 1); an LF step
+	// leads from the row of position p to the row of position p - 1
+	// leads from the row of position p to the row of position p - 1.  Separators and the terminator share symbol 0, for
+	// which the usual rank formula is off: the rows that start with a separator are ordered by what FOLLOWS them, i.e. by the
+	// rows of the terminator (row 0) and of the sequence starts -- exactly the rows whose BWT symbol is 0, the wrapped row of
+	// text position 0 aside -- so the k-th such row (k = 0 for row 0) leads to row k + 1.
+	vector<int32_t> zeroRows;
+	for (int32_t i = 0; i < N; ++i)
+		if ((sym[i] > 4 ? 0 : sym[i]) == 0 && i != wrapRow) zeroRows.push_back(i);
+	sa.assign(N, 0);
+	int32_t row = 0;
+	sa[0] = N; // 1-based text positions, as build() keeps them
+	for (int32_t p = N - 1; p >= 1; --p) {
+		const int c = sym[row] > 4 ? 0 : sym[row];
+		if (c == 0) {
+			const vector<int32_t>::const_iterator it = lower_bound(zeroRows.begin(), zeroRows.end(), row);
+			if (it == zeroRows.end() || *it != row) { in.setstate(ios_base::badbit); return in; }
+			row = (int32_t) (it - zeroRows.begin()) + 1;
+		} else
+			row = C[c] + occ(c, row) - 1;
+		if (row < 0 || row >= N || sa[row] != 0) { in.setstate(ios_base::badbit); return in; }
+		sa[row] = p;
+	}
+	return in;
+}
+
+bool CSFMIndex::operator==(const CSFMIndex& o) const {
+	if (csLen != o.csLen || concatLen != o.concatLen || memcmp(C, o.C, sizeof C) != 0 || sa != o.sa || concat2CS != o.concat2CS || rank.size() != o.rank.size()) return false;
+	for (size_t i = 0; i + 1 < rank.size(); ++i) // the last block is never read
+		if ((size_t) i * 64 <= (size_t) concatLen && (memcmp(rank[i].cnt, o.rank[i].cnt, sizeof rank[i].cnt) != 0 || memcmp(rank[i].mask, o.rank[i].mask, sizeof rank[i].mask) != 0)) return false;
+	return true;
+}
+
 // ------------------------------------------------------------------ discrete Gamma ----
 // The reference takes these from Boost.Math (gamma_p, quantile(gamma_distribution)); Boost is not a dependency here.
 double gammaP(double a, double x) {

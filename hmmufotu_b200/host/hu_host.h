@@ -107,6 +107,11 @@ public:
 	// sampled suffix array + RRR bitmap of the sampled positions + pointerless wavelet tree over the BWT with RRR-compressed
 	// levels (hu_build.cpp).  msa: the alignment this index was built from.
 	std::ostream& save(std::ostream& out, const MSA& msa) const;
+	// ... and read back (src/CSFMIndex.cpp:198-230): the RRR bitmaps and the wavelet tree are decoded into this class's own
+	// rank blocks, and the full suffix array is recovered from the BWT by LF steps (seconds where a suffix sort of a large
+	// alignment takes minutes).  The result is the index build() makes from the same alignment, field for field.
+	std::istream& load(std::istream& in);
+	bool operator==(const CSFMIndex& o) const;
 private:
 	bool search(const std::string& pattern, int32_t& start, int32_t& end) const;
 	int32_t occ(int b, int32_t i) const;           // # of symbol b in BWT[0..i]

@@ -9,6 +9,7 @@
 //   hmmbuild FASTA NAME PRIOR.dm OUT   the builder's profile training (hu_build.cpp)
 //   rootll DB.ptu      root log-likelihood block recomputed from the stored messages; shape estimate from the messages
 //   dgamma K ALPHA / dgshow DB.ptu   discrete-Gamma break points and rates, built here or as stored in a database
+//   csfmload DB.csfm DB.msa     the index read from the reference's file = the index built from the alignment?
 //   csfmwrite DB.msa OUT.csfm   the index file as the reference's hmmufotu loads it (libcds serialisation)
 //   seeds DB FASTA S   CSFM seed search of every read with srand(S): prints the ViterbiAlignPaths
 #include "hu_host.h"
@@ -252,6 +253,16 @@ int main(int argc, char** argv) {
 		saveProgInfo(out);
 		csfm.save(out, msa);
 		return out.good() ? 0 : 1;
+	}
+	if (cmd == "csfmload" && argc == 4) { // csfmload DB.csfm DB.msa: the index read from the file against the one built from the alignment
+		ifstream in(argv[2], ios_base::binary), min(argv[3], ios_base::binary);
+		CSFMIndex loaded, built;
+		MSA msa;
+		if (loadProgInfo(in).bad() || !loaded.load(in)) { cerr << "cannot load " << argv[2] << endl; return 1; }
+		if (loadProgInfo(min).bad() || !msa.load(min)) { cerr << "cannot load " << argv[3] << endl; return 1; }
+		built.build(msa);
+		cout << (loaded == built ? "identical" : "DIFFERENT") << endl;
+		return loaded == built ? 0 : 1;
 	}
 	if (cmd == "locate" && argc == 3) { // locate DB.msa < patterns: count and sorted hits, the format of oracle/ref_csfm_probe.cpp
 		ifstream in(argv[2], ios_base::binary);

@@ -228,6 +228,10 @@ def test_builder_csfm_file_is_the_references(exes, tmp_path):
         with open(os.path.join(g, "csfm_locate.txt")) as fin:
             ref = subprocess.run([probe, str(tmp_path / "gg_70_otus_GTR.msa.csfm")], stdin=fin, capture_output=True, text=True)
         assert ref.returncode == 0 and ref.stdout == open(os.path.join(g, "csfm_locate.tsv")).read()
+    # and back: the index read from the reference's file (RRR bitmaps and wavelet tree decoded, full suffix array recovered from
+    # the BWT) is the index built from the alignment, field for field
+    for stem in (os.path.join(ROOT, "tests", "golden", "ref70", "gg_70_otus_GTR"), os.path.join(ROOT, "tests", "golden", "build", "hand")):
+        assert _skeleton(exes[1], "csfmload", stem + ".csfm", stem + ".msa").strip() == "identical"
 
 
 def _sim_statistics(fasta, ptu, gap_frac):
@@ -384,6 +388,10 @@ def test_command_line_staging_equals_the_seed_driver(exes, tmp_path):
                         ([os.path.join(g, "gg_70_otus_GTR_pe0_1.fasta"), os.path.join(g, "gg_70_otus_GTR_pe0_2.fasta")], "7")):
         want = _skeleton(exes[1], "seeds", os.path.join(g, "gg_70_otus_GTR"), reads[0], seed, *reads[1:]).strip().split("\n")
         for batch, p in ((64, 1), (7, 4), (4096, 8)):
+            # first configuration: the index rebuilt from the .msa; the others: <db>.csfm as written by the reference's builder
+            if batch == 7:
+                with open(os.path.join(g, "gg_70_otus_GTR.csfm"), "rb") as f, open(tmp_path / "db.csfm", "wb") as o:
+                    o.write(f.read())
             got = _skeleton(exes[0], db, *reads, "-s", "1", "-S", seed, "--batch", str(batch), "-p", str(p), "--stage-only").strip().split("\n")
             assert len(got) == len(want) == 64 * len(reads)
             for i, (a, b) in enumerate(zip(got, want)):
