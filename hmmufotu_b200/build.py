@@ -70,7 +70,7 @@ def build_host(force: bool = False) -> str:
     os.makedirs(BINDIR, exist_ok=True)
     srcs = [os.path.join(HOST, f) for f in ("hu_host.cpp", "hu_build.cpp", "hu_host.h")]
     out = []
-    for name, main in (("hmmufotu", "hmmufotu.cpp"), ("hmmufotu-build", "hmmufotu-build.cpp"), ("hmmufotu-sim", "hmmufotu-sim.cpp"),
+    for name, main in (("hmmufotu", "hmmufotu.cpp"), ("hmmufotu-build", "hmmufotu-build.cpp"), ("hmmufotu-sim", "hmmufotu-sim.cpp"), ("hmmufotu-inspect", "hmmufotu-inspect.cpp"),
                        ("hu_host_test", "hu_host_test.cpp")):
         exe = os.path.join(BINDIR, name)
         deps = srcs + [os.path.join(HOST, main), lib]

@@ -94,6 +94,7 @@ public:
 	CSFMIndex() : csLen(0), concatLen(0) {}
 	CSFMIndex& build(const MSA& msa);              // src/CSFMIndex.cpp:232-368
 	int getCSLen() const { return csLen; }
+	int32_t getConcatLen() const { return concatLen; }
 	int32_t count(const std::string& pattern) const;                 // src/CSFMIndex.cpp:79-99
 	CSLoc locateOne(const std::string& pattern) const;               // src/CSFMIndex.cpp:121-147 (uses rand())
 	CSLoc locateFirst(const std::string& pattern) const;             // src/CSFMIndex.cpp:101-119

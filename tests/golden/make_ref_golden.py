@@ -78,6 +78,18 @@ def main():
         subprocess.run([os.path.join(REF, "csfm_probe"), "gg_70_otus_GTR.csfm"], stdin=fin, stdout=fout, check=True)
     bdir = os.path.join(HERE, "build")
     run(os.path.join(REF, "hmmufotu-build"), "hand.fasta", "hand.tree", "-a", "hand_taxonomy.txt", "-n", "hand", "-s", "GTR", cwd=bdir)
+    idir = os.path.join(HERE, "inspect")  # what the reference's hmmufotu-inspect prints for the two databases
+    os.makedirs(idir, exist_ok=True)
+    for db, extra in (("gg_70_otus_GTR", []), ("gg_70_otus_HKY85_dG", ["-n", "--use-dbname"])):
+        with gzip.open(db + ".ptu.gz", "rb") as f, open(db + ".ptu", "wb") as o:
+            shutil.copyfileobj(f, o)
+        with open(os.path.join(idir, db + ".stdout.txt"), "w") as so:
+            subprocess.run([os.path.join(REF, "hmmufotu-inspect"), db, "-sm", "-dg", "-t", os.path.join(idir, db + ".tree"), "-a", os.path.join(idir, db + ".anno.txt"),
+                            "-s", os.path.join(idir, db + ".seq.fa")] + extra, stdout=so, check=True)
+        os.remove(db + ".ptu")
+        os.remove(os.path.join(idir, db + ".seq.fa"))  # large: the test keeps its md5
+    for f in ("gg_70_otus_HKY85_dG.tree", "gg_70_otus_HKY85_dG.anno.txt"):
+        os.remove(os.path.join(idir, f))
     for f in sorted(os.listdir(OUT)):
         print("%10d  %s" % (os.path.getsize(f), f))
 

@@ -317,6 +317,36 @@ def test_simulator_draws_from_the_tree_model(exes, tmp_path):
     assert len(a) == len(b) == 50 and all(x[0] == y[0] and len(x[2]) <= 150 and set(x[2]) <= set("ACGT") for x, y in zip(a, b))
 
 
+def test_inspect_output_is_the_references(exes, tmp_path):
+    """hmmufotu-inspect of this repository on the reference-built databases: summary lines, substitution model, discrete
+    Gamma model, tree (Newick), node annotations and node sequences are the text the reference's hmmufotu-inspect writes
+    (committed under tests/golden/inspect; compared live as well where oracle/_ref is built)."""
+    import gzip, hashlib
+    g, gi = os.path.join(ROOT, "tests", "golden", "ref70"), os.path.join(ROOT, "tests", "golden", "inspect")
+    ours, ref = os.path.join(BIN, "hmmufotu-inspect"), os.path.join(ROOT, "oracle", "_ref", "hmmufotu-inspect")
+    for db in ("gg_70_otus_GTR", "gg_70_otus_HKY85_dG"):
+        for ext in ("msa", "csfm", "hmm"):
+            with open(os.path.join(g, db + "." + ext), "rb") as f, open(tmp_path / (db + "." + ext), "wb") as o:
+                o.write(f.read())
+        with gzip.open(os.path.join(g, db + ".ptu.gz"), "rb") as f, open(tmp_path / (db + ".ptu"), "wb") as o:
+            o.write(f.read())
+    r = subprocess.run([ours, "gg_70_otus_GTR", "-sm", "-dg", "-t", "t.nwk", "-a", "a.txt", "-s", "s.fa"], cwd=str(tmp_path), capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert r.stdout == open(os.path.join(gi, "gg_70_otus_GTR.stdout.txt")).read()
+    assert open(tmp_path / "t.nwk").read() == open(os.path.join(gi, "gg_70_otus_GTR.tree")).read()
+    assert open(tmp_path / "a.txt").read() == open(os.path.join(gi, "gg_70_otus_GTR.anno.txt")).read()
+    assert hashlib.md5(open(tmp_path / "s.fa", "rb").read()).hexdigest() == "7bed962f6aaa472b95c277a548f477dc"
+    r = subprocess.run([ours, "gg_70_otus_HKY85_dG", "-sm", "-dg", "-t", "dt.nwk", "-a", "da.txt", "-s", "ds.fa", "-n", "--use-dbname"], cwd=str(tmp_path), capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert r.stdout == open(os.path.join(gi, "gg_70_otus_HKY85_dG.stdout.txt")).read()
+    assert hashlib.md5(open(tmp_path / "ds.fa", "rb").read()).hexdigest() == "936fc6a380eecfd5fbf788fa46584b2b"
+    if os.path.exists(ref):
+        rr = subprocess.run([ref, "gg_70_otus_HKY85_dG", "-sm", "-dg", "-t", "rt.nwk", "-a", "ra.txt", "-s", "rs.fa", "-n", "--use-dbname"], cwd=str(tmp_path), capture_output=True, text=True)
+        assert rr.returncode == 0 and rr.stdout == r.stdout
+        for a, b in (("dt.nwk", "rt.nwk"), ("da.txt", "ra.txt"), ("ds.fa", "rs.fa")):
+            assert open(tmp_path / a, "rb").read() == open(tmp_path / b, "rb").read()
+
+
 def test_builder_discrete_gamma(exes, tmp_path):
     """DiscreteGammaModel(K, alpha) as the builder derives it (src/DiscreteGammaModel.cpp:40-55, literal: Gamma(shape alpha,
     SCALE alpha) quantiles, rates not multiplied by K) with this repository's own incomplete-gamma code: against the block the
