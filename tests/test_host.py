@@ -347,6 +347,27 @@ def test_inspect_output_is_the_references(exes, tmp_path):
             assert open(tmp_path / a, "rb").read() == open(tmp_path / b, "rb").read()
 
 
+@pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "tsv_probe")), reason="needs oracle/_ref/tsv_probe (the reference's own TSV reader)")
+def test_assignment_tsv_is_read_by_the_references_consumers(tmp_path):
+    """the reference's downstream programs (hmmufotu-sum, hmmufotu-jplace) read the assignment TSV with
+    readProgInfo() + TSVScanner and fetch fields by name.  The only lines in which this repository's TSV differs from the
+    reference's are the two comment lines in front (tests/golden/ours_cli/header.txt: as written by hmmufotu_b200/bin/hmmufotu
+    on a B200; the rows are the reference's line for line, tests/test_gpu_ref.py): with them in front, the reference's own reader
+    (oracle/_ref/tsv_probe) accepts the file and returns every named field exactly as from the reference's TSV."""
+    g = os.path.join(ROOT, "tests", "golden", "ref70")
+    probe = os.path.join(ROOT, "oracle", "_ref", "tsv_probe")
+    ref_tsv = os.path.join(g, "gg_70_otus_GTR_se0.tsv")
+    body = [ln for ln in open(ref_tsv) if not ln.startswith("#")]
+    hdr = open(os.path.join(ROOT, "tests", "golden", "ours_cli", "header.txt")).readlines()
+    assert hdr[2] == body[0]                                    # same column header
+    ours = tmp_path / "ours.tsv"
+    ours.write_text("".join(hdr[:2] + body))
+    a = subprocess.run([probe, str(ours)], capture_output=True, text=True)
+    b = subprocess.run([probe, ref_tsv], capture_output=True, text=True)
+    assert a.returncode == 0 and b.returncode == 0, a.stderr + b.stderr
+    assert a.stdout == b.stdout and a.stdout.count("\n") == 64
+
+
 def test_builder_discrete_gamma(exes, tmp_path):
     """DiscreteGammaModel(K, alpha) as the builder derives it (src/DiscreteGammaModel.cpp:40-55, literal: Gamma(shape alpha,
     SCALE alpha) quantiles, rates not multiplied by K) with this repository's own incomplete-gamma code: against the block the
