@@ -10,4 +10,4 @@ try:
 except Exception as e:
     print("no bench line:", e)
 PY
-bash scripts/gpu_check.sh capw
+bash scripts/gpu_quick.sh capw
