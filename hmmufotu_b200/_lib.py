@@ -59,7 +59,8 @@ class SepParams(C.Structure):
 
 class BatchStats(C.Structure):
     _fields_ = [("cells", C.c_int64), ("seedPairs", C.c_int64), ("seedBytes", C.c_int64), ("estItems", C.c_int64),
-                ("estBytes", C.c_int64), ("placeItems", C.c_int64), ("placeBytes", C.c_int64), ("launches", C.c_int64)]
+                ("estBytes", C.c_int64), ("placeItems", C.c_int64), ("placeBytes", C.c_int64), ("launches", C.c_int64),
+                ("seedHeapSorts", C.c_int64)]
 
 
 # every symbol include/hmmufotu_b200.h declares
@@ -69,7 +70,8 @@ SYMBOLS = ["hu_hmm_finalize", "hu_model_Pr", "hu_db_create", "hu_db_destroy", "h
            "hu_finalize_batch", "hu_assign_batch", "hu_batch_sync", "hu_batch_get_align", "hu_batch_get_merged",
            "hu_batch_get_aligned_codes", "hu_batch_get_seeds", "hu_batch_get_estimates", "hu_batch_get_places",
            "hu_batch_get_best", "hu_batch_stage_ms", "hu_batch_get_stats", "hu_trace_to_align", "hu_last_error",
-           "hu_version", "hu_host_alloc", "hu_host_free", "hu_batch_mark", "hu_batch_elapsed"]
+           "hu_version", "hu_host_alloc", "hu_host_free", "hu_batch_mark", "hu_batch_elapsed", "hu_batch_get_seed_keys",
+           "hu_debug_literal_order", "hu_debug_stdsort"]
 
 _LIB = None
 
@@ -118,6 +120,9 @@ def load() -> C.CDLL:
     L.hu_host_free.argtypes = [vp]
     L.hu_batch_mark.argtypes = [vp, C.c_int]
     L.hu_batch_elapsed.argtypes = [vp, C.c_int, vp, C.c_int, P(C.c_float)]
+    L.hu_batch_get_seed_keys.argtypes = [vp, i32, vp, P(i32)]
+    L.hu_debug_literal_order.argtypes = [C.c_int, vp, i32, i32, i32, vp, vp, vp]
+    L.hu_debug_stdsort.argtypes = [vp, i32, vp]
     _LIB = L
     return L
 

@@ -1,5 +1,6 @@
 // C ABI: batch workspace, host-side band planning, staging, stage drivers and result read-back.
 #include "hu_batch.cuh"
+#include "hu_stdsort.cuh"
 #include <string.h>
 #include <ctype.h>
 #include <utility>
@@ -84,19 +85,6 @@ __global__ void windowsKernel(int n, const hu_align_row* __restrict__ merged, in
 	winEnd[r] = bad ? -1 : a.csEnd - 1;
 }
 
-static void buildEqualPerm(int* perm) {
-	// the permutation std::sort(rbegin, rend, cmp) applies to n equal keys depends on n only; run the very
-	// call the reference makes (src/hmmufotu.cpp:730) on tagged elements and record what lands first
-	struct Cmp { static bool lt(const std::pair<double, int>& a, const std::pair<double, int>& b) { return a.first < b.first; } };
-	perm[0] = 0;
-	for (int n = 1; n <= HU_MAX_SEED; ++n) {
-		std::vector<std::pair<double, int> > v(n);
-		for (int i = 0; i < n; ++i) v[i] = std::make_pair(1.0, i);
-		std::sort(v.rbegin(), v.rend(), Cmp::lt);
-		perm[n] = v[0].second;
-	}
-}
-
 } // namespace hu
 
 using namespace hu;
@@ -132,6 +120,11 @@ void hu_sep_params_default(hu_sep_params* p) {
 int hu_batch_create(hu_batch** out, hu_db* db, int32_t maxReads, int32_t maxSeqLen, int32_t paired) {
 	if (!out || !db || maxReads < 1 || maxSeqLen < 1) { setError("hu_batch_create: bad arguments"); return HU_ERR_ARG; }
 	HU_CUDA(cudaSetDevice(db->device));
+	if (std::min((long long) db->hmm.L, (long long) maxSeqLen * (paired ? 2 : 1)) > HU_SEED_MAX_N) {
+		setError("hu_batch_create: reads of %d bases over %d consensus columns exceed the %d compared columns for which the seed keys are exact",
+		         maxSeqLen * (paired ? 2 : 1), db->hmm.L, HU_SEED_MAX_N);
+		return HU_ERR_ARG;
+	}
 	hu_batch* b = new hu_batch();
 	memset(&b->vit, 0, sizeof b->vit);
 	memset(&b->seed, 0, sizeof b->seed);
@@ -140,6 +133,7 @@ int hu_batch_create(hu_batch** out, hu_db* db, int32_t maxReads, int32_t maxSeqL
 	b->maxSeq = maxReads * (paired ? 2 : 1);
 	b->nReads = b->nSeq = 0; b->launches = 0;
 	b->dPtrs = NULL; b->ptrsCap = 0; b->placeSlab = NULL; b->litIds = NULL;
+	b->posOfSlotH = b->nodeOfPosH = NULL; b->nCandH = 0; b->heightCached = 0;
 	*out = b;
 	HU_CUDA(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
 	for (int i = 0; i < 16; ++i) HU_CUDA(cudaEventCreate(&b->ev[i]));
@@ -190,13 +184,10 @@ int hu_batch_create(hu_batch** out, hu_db* db, int32_t maxReads, int32_t maxSeqL
 	HU_TRY(balloc(b, &b->order, (size_t) maxReads * HU_MAX_SEED));
 	HU_TRY(balloc(b, &b->nKept, (size_t) maxReads));
 	HU_TRY(balloc(b, &b->best, (size_t) maxReads));
-	HU_TRY(balloc(b, &b->equalPerm, (size_t) HU_MAX_SEED + 1));
-	HU_TRY(balloc(b, &b->workCount, 4));
+	HU_TRY(balloc(b, &b->workCount, 8));
+	HU_CUDA(cudaMemset(b->workCount, 0, 8 * sizeof(int)));
 	HU_CUDA(cudaMemset(b->seed.nSeeds, 0, (size_t) maxReads * sizeof(int)));
 	HU_CUDA(cudaMemset(b->nKept, 0, (size_t) maxReads * sizeof(int)));
-	int perm[HU_MAX_SEED + 1];
-	buildEqualPerm(perm);
-	HU_CUDA(cudaMemcpy(b->equalPerm, perm, sizeof perm, cudaMemcpyHostToDevice));
 	HU_TRY(palloc(b, &b->hPlansPinned, (size_t) b->maxSeq));
 	return HU_OK;
 }
@@ -308,7 +299,6 @@ int hu_place_batch(hu_batch* b, const hu_sep_params* p) {
 int hu_finalize_batch(hu_batch* b, const hu_sep_params* p) {
 	if (!b || !p || b->nReads < 1) { setError("hu_finalize_batch: empty batch"); return HU_ERR_STATE; }
 	HU_CUDA(cudaSetDevice(b->db->device));
-	if (p->equalSortPerm) HU_CUDA(cudaMemcpyAsync(b->equalPerm, p->equalSortPerm, (HU_MAX_SEED + 1) * sizeof(int), cudaMemcpyHostToDevice, b->stream));
 	return launchFinalize(b, p);
 }
 int hu_assign_batch(hu_batch* b, int mode, const hu_sep_params* p) {
@@ -422,6 +412,22 @@ int hu_batch_get_best(hu_batch* b, hu_place_row* rows) {
 	return HU_OK;
 }
 
+int hu_batch_get_seed_keys(hu_batch* b, int32_t read, uint32_t* keys, int32_t* nCand) {
+	if (!b || read < 0 || read >= b->nReads) { setError("hu_batch_get_seed_keys: bad read index"); return HU_ERR_ARG; }
+	HU_CUDA(cudaSetDevice(b->db->device));
+	HU_CUDA(cudaStreamSynchronize(b->stream));
+	const int n = b->seed.nCand > 0 ? b->seed.nCand : b->db->tree.nCand;
+	if (nCand) *nCand = n;
+	if (keys) HU_CUDA(cudaMemcpy(keys, b->seed.keys + (size_t) read * b->db->tree.scanPitch, (size_t) n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+	return HU_OK;
+}
+
+int hu_debug_stdsort(const double* keys, int32_t n, int32_t* perm) {
+	if (!keys || !perm || n < 0) { setError("hu_debug_stdsort: bad arguments"); return HU_ERR_ARG; }
+	stdSortDescendingPerm(keys, n, perm);
+	return HU_OK;
+}
+
 int hu_batch_mark(hu_batch* b, int id) {
 	if (!b || id < 0 || id > 7) { setError("hu_batch_mark: bad mark id"); return HU_ERR_ARG; }
 	HU_CUDA(cudaSetDevice(b->db->device));
@@ -473,6 +479,9 @@ int hu_batch_get_stats(hu_batch* b, hu_batch_stats* s) {
 		s->placeBytes += 64 * W * nk[r];
 	}
 	s->launches = b->launches;
+	int hf = 0;
+	HU_CUDA(cudaMemcpy(&hf, b->workCount + 4, sizeof(int), cudaMemcpyDeviceToHost));
+	s->seedHeapSorts = hf;
 	return HU_OK;
 }
 

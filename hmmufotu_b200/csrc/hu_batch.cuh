@@ -7,6 +7,7 @@
 #define HU_VIT_WARPS 8   // max warps (= sequences) per Viterbi CTA
 #define HU_SCAN_TILE 512 // node slots per seed-scan CTA
 #define HU_SCAN_READS 8  // reads per seed-scan CTA
+#define HU_SEED_MAX_N 46340 // compared columns per (read, node) for which the integer seed keys are exact (hu_seed.cu)
 
 namespace hu {
 
@@ -56,6 +57,10 @@ struct SeedArgs {
 	uint32_t* keys;         // [nReads][scanPitch]: floor(d * 2^31 / N), 0xFFFFFFFF = excluded
 	int* seedIds;           // [nReads][HU_MAX_SEED]
 	int* nSeeds;            // [nReads]
+	const int* posOfSlot;   // slot -> position in this run's candidate vector (TreeDev's, or the height-filtered one), -1: not a candidate
+	const int* nodeOfPos;   // position -> node id
+	int nCand;              // number of candidates of this run
+	int* heapFallbacks;     // diagnostic counter: reads whose literal replay reached introsort's heap-sort fallback
 };
 
 // one (read, seed) of the estimate stage, resolved once so that the streaming kernel has no dependent loads
@@ -106,12 +111,15 @@ struct hu_batch {
 	int* nKept;            // [maxReads]
 	hu_place_row* places;  // [maxReads][HU_MAX_SEED] placeSeq results, filter order
 	hu_place_row* best;    // [maxReads]
-	int* equalPerm;        // [HU_MAX_SEED+1]
 	int* workItems;        // items of K3 whose window is wider than the staged kernel takes
 	hu::EstItem* estItems; // [maxReads][HU_MAX_SEED] item records of K3
 	hu::EstItemP* estItemsP;
 	int* workCount;
 	unsigned long long* litIds; // (key, candidate position) work rows of the literal seed order, one per resident CTA
+	int* posOfSlotH;       // candidate map of the literal seed order under -H/--max-height (built on first use per height)
+	int* nodeOfPosH;
+	int nCandH;
+	double heightCached;
 	double* placeSlab;     // global rho slabs for windows wider than the shared-memory capacity
 	long long h2dBytes;
 	// stats

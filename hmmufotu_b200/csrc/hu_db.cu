@@ -510,6 +510,7 @@ static int createImpl(hu_db* db, const hu_hmm_params* hp, const hu_tree_desc* td
 	t.scanPitch = (int) scanNode.size();
 	// padding slots (inside the gap block and at the tail) carry node -1 and all-zero planes
 	HU_TRY(upload(db, &t.scanNode, scanNode.data(), scanNode.size()));
+	db->scanNodeHost = scanNode;
 	{
 		// getSeed() visits the non-root nodes in id order: that is the order of the per-read key vector
 		std::vector<int> posOfNode(n, -1), posOfSlot(scanNode.size(), -1), nodeOfPos(scanNode.size(), 0x7fffffff);
@@ -605,6 +606,14 @@ int hu_db_create(hu_db** out, const hu_hmm_params* hmm, const hu_tree_desc* tree
 		return HU_ERR_CUDA;
 	}
 	HU_CUDA(cudaSetDevice(device));
+	// kernel attributes are per device: set them for this one (no process-wide "already done" flags)
+	{
+		int rcA = hu::configViterbiKernels();
+		if (rcA == HU_OK) rcA = hu::configSeedKernels();
+		if (rcA == HU_OK) rcA = hu::configEstimateKernels();
+		if (rcA == HU_OK) rcA = hu::configPlaceKernels();
+		if (rcA != HU_OK) return rcA;
+	}
 	hu_db* db = new hu_db();
 	db->device = device;
 	int rc = hu::createImpl(db, hmm, tree, model);

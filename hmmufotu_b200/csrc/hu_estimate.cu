@@ -14,6 +14,7 @@
 // (HU_EST_CAPW columns) go to estimateWideKernel, one warp per item, which reads the window twice.
 #include "hu_batch.cuh"
 #include "hu_pipe.cuh"
+#include "hu_stdsort.cuh"
 
 namespace hu {
 
@@ -450,27 +451,32 @@ __global__ void __launch_bounds__(HU_EST_WARPS * 32) estimateWideKernel(EstArgs 
 	}
 }
 
-// filterPlacements: order by estimated loglik (descending; equal logliks keep seed order) and keep the
-// placements within maxError of the best.
+// filterPlacements: std::sort(places.rbegin(), places.rend(), compareByLoglik) and keep the placements within maxError
+// of the best (src/HmmUFOtu_main.cpp:162-173).  The sort is libstdc++'s introsort, replayed move for move
+// (hu_stdsort.cuh): exactly equal estimated log-likelihoods come out in the order the reference leaves them in.
 __global__ void filterKernel(int nReads, const int* __restrict__ winStart, const int* __restrict__ nSeeds,
 		const hu_place_row* __restrict__ est, double maxError, int* __restrict__ order, int* __restrict__ nKept) {
 	const int r = blockIdx.x * blockDim.x + threadIdx.x;
 	if (r >= nReads) return;
-	const int n = winStart[r] < 0 ? 0 : nSeeds[r];
-	int* o = order + (size_t) r * HU_MAX_SEED;
+	const int n = winStart[r] < 0 ? 0 : max(nSeeds[r], 0);
 	const hu_place_row* e = est + (size_t) r * HU_MAX_SEED;
-	for (int i = 0; i < n; ++i) { // insertion sort, stable
-		const double v = e[i].estLoglik;
-		int p = i;
-		while (p > 0 && e[o[p - 1]].estLoglik < v) { o[p] = o[p - 1]; p--; }
-		o[p] = i;
-	}
+	double key[HU_MAX_SEED];
+	int o[HU_MAX_SEED];
+	for (int i = 0; i < n; ++i) key[i] = e[i].estLoglik;
+	stdSortDescendingPerm(key, n, o);
 	int keep = 0;
 	if (n > 0) {
-		const double best = e[o[0]].estLoglik;
-		while (keep < n && !(best - e[o[keep]].estLoglik > maxError)) keep++;
+		const double best = key[o[0]];
+		while (keep < n && !(best - key[o[keep]] > maxError)) keep++;
 	}
+	for (int i = 0; i < n; ++i) order[(size_t) r * HU_MAX_SEED + i] = o[i];
 	nKept[r] = keep;
+}
+
+int configEstimateKernels() {
+	HU_CUDA(cudaFuncSetAttribute(estimateStagedKernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) estSmemBytes(HU_EST_CAPW_BIG)));
+	HU_CUDA(cudaFuncSetAttribute(estimateStagedKernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) estSmemBytes(HU_EST_CAPW_BIG)));
+	return HU_OK;
 }
 
 int launchEstimate(hu_batch* b, const hu_sep_params* p) {
@@ -485,12 +491,6 @@ int launchEstimate(hu_batch* b, const hu_sep_params* p) {
 	int sms = 0;
 	HU_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, db->device));
 	HU_CUDA(cudaMemsetAsync(b->workCount, 0, 4 * sizeof(int), b->stream));
-	static bool attr = false;
-	if (!attr) {
-		HU_CUDA(cudaFuncSetAttribute(estimateStagedKernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) estSmemBytes(HU_EST_CAPW_BIG)));
-		HU_CUDA(cudaFuncSetAttribute(estimateStagedKernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) estSmemBytes(HU_EST_CAPW_BIG)));
-		attr = true;
-	}
 	const int total = a.nReads * a.maxNSeed;
 	estPlanKernel<<<(total + 7) / 8, 256, 0, b->stream>>>(a, db->tree, db->model);
 	const size_t smem = estSmemBytes(a.capW);

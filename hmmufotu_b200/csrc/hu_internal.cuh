@@ -248,6 +248,12 @@ __device__ __forceinline__ double windowScale(const double* __restrict__ S, cons
 }
 #endif
 
+// per-device kernel attributes (dynamic shared memory limits): set for the current device by hu_db_create
+int configViterbiKernels();
+int configSeedKernels();
+int configEstimateKernels();
+int configPlaceKernels();
+
 } // namespace hu
 
 struct hu_db {
@@ -261,5 +267,6 @@ struct hu_db {
 	int K, L;
 	std::vector<int> p2cs;
 	std::vector<double> heightHost;
+	std::vector<int> scanNodeHost; // slot -> node id of the seed scan order (-1: padding)
 	hu_db() : device(0), bytes(0), K(0), L(0) {}
 };

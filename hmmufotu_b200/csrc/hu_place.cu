@@ -13,6 +13,7 @@
 // Same iterates, same stopping rules, same caps as the reference; the values differ from it only by rounding
 // (checked to 1e-9 relative against the oracle in tests/test_gpu_parity.py).
 #include "hu_batch.cuh"
+#include "hu_stdsort.cuh"
 
 namespace hu {
 
@@ -266,8 +267,7 @@ __global__ void __launch_bounds__(HU_PLACE_WARPS * 32) placeKernel(PlaceArgs a, 
 
 // calcQValues (UNIFORM prior) + sort by qPlace + bestPlace; one thread per read.
 __global__ void finalizeKernel(int nReads, const int* __restrict__ winStart, const int* __restrict__ nKept,
-		hu_place_row* __restrict__ places, int useTrue, int priorHeight, int onlyML, const int* __restrict__ equalPerm,
-		hu_place_row* __restrict__ best) {
+		hu_place_row* __restrict__ places, int useTrue, int priorHeight, int onlyML, hu_place_row* __restrict__ best) {
 	const int r = blockIdx.x * blockDim.x + threadIdx.x;
 	if (r >= nReads) return;
 	const int n = winStart[r] < 0 ? 0 : nKept[r];
@@ -292,14 +292,12 @@ __global__ void finalizeKernel(int nReads, const int* __restrict__ winStart, con
 		pl[i].nPlaces = n;
 		pl[i].qPlace = pl[i].qTaxon = 0;
 	}
+	double key[HU_MAX_SEED];
+	int perm[HU_MAX_SEED];
 	if (onlyML) { // --ML (src/hmmufotu.cpp:725-727): std::sort(rbegin, rend, compareByLoglik), no Q values
-		bool allEq = true;
-		int pickML = 0;
-		for (int i = 1; i < n; ++i) {
-			if (pl[i].loglik < pl[0].loglik || pl[0].loglik < pl[i].loglik) allEq = false; // NaN keys compare like equal keys in std::sort
-			if (pl[i].loglik > pl[pickML].loglik) pickML = i;
-		}
-		best[r] = pl[allEq ? equalPerm[n] : pickML];
+		for (int i = 0; i < n; ++i) key[i] = pl[i].loglik;
+		stdSortDescendingPerm(key, n, perm); // libstdc++'s introsort replayed: ties and NaN keys land where the reference leaves them
+		best[r] = pl[perm[0]];
 		return;
 	}
 	for (int i = 0; i < n; ++i) {
@@ -320,8 +318,6 @@ __global__ void finalizeKernel(int nReads, const int* __restrict__ winStart, con
 	}
 	double sum = 0;
 	for (int i = 0; i < n; ++i) sum += exp(pl[i].qPlace - mx);
-	bool allEqual = true;
-	double q0 = 0;
 	for (int i = 0; i < n; ++i) {
 		const double pr = exp(pl[i].qPlace - mx) / sum;
 		double q = -10.0 * log(1 - pr) / LOG10; // p2q
@@ -331,8 +327,7 @@ __global__ void finalizeKernel(int nReads, const int* __restrict__ winStart, con
 		// has it set, and the TSV shows the sign.
 		if (q != q) q = __longlong_as_double(0x7FF8000000000000LL);
 		pl[i].qPlace = q;
-		if (i == 0) q0 = q;
-		else if (q < q0 || q0 < q) allEqual = false; // NaN keys (a NaN prior makes every posterior NaN) compare like equal keys
+		key[i] = q;
 		double pt = 0;
 		for (int k = 0; k < nTax; ++k) if (tax[k] == pl[i].taxon) pt = taxPP[k];
 		double qt = -10.0 * log(1 - exp(pt - norm)) / LOG10;
@@ -340,12 +335,17 @@ __global__ void finalizeKernel(int nReads, const int* __restrict__ winStart, con
 		if (qt != qt) qt = __longlong_as_double(0x7FF8000000000000LL);
 		pl[i].qTaxon = qt;
 	}
-	// std::sort(places.rbegin(), places.rend(), compareByQPlace); bestPlace = places[0]
-	int pick = 0;
-	if (allEqual) pick = equalPerm[n]; // what libstdc++'s introsort leaves first on n equal keys
-	else
-		for (int i = 1; i < n; ++i) if (pl[i].qPlace > pl[pick].qPlace) pick = i;
-	best[r] = pl[pick];
+	// std::sort(places.rbegin(), places.rend(), compareByQPlace); bestPlace = places[0] (src/hmmufotu.cpp:729-733).  Under
+	// SURVEY.md F6 all keys are equal and the winner is whatever introsort's data movement leaves first: replayed literally
+	// (hu_stdsort.cuh), which also covers partial ties and NaN keys (they compare like equal keys).
+	stdSortDescendingPerm(key, n, perm);
+	best[r] = pl[perm[0]];
+}
+
+int configPlaceKernels() {
+	const size_t smem = (size_t) HU_PLACE_WARPS * (placeWarpDoubles(HU_MAX_DG) + HU_PLACE_CAPW) * sizeof(double);
+	HU_CUDA(cudaFuncSetAttribute(placeKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+	return HU_OK;
 }
 
 int launchPlace(hu_batch* b, const hu_sep_params* p) {
@@ -362,11 +362,6 @@ int launchPlace(hu_batch* b, const hu_sep_params* p) {
 	const int grid = sms * ctasPerSm;
 	const int KKh = db->model.dgK > 0 ? db->model.dgK : 1;
 	const size_t smem = (size_t) HU_PLACE_WARPS * (placeWarpDoubles(KKh) + HU_PLACE_CAPW) * sizeof(double);
-	static size_t attr = 0;
-	if (smem > attr) {
-		HU_CUDA(cudaFuncSetAttribute(placeKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-		attr = smem;
-	}
 	// global slab for windows wider than the shared-memory capacity
 	const size_t slabBytes = (size_t) grid * HU_PLACE_WARPS * db->tree.csLen * sizeof(double);
 	if (!b->placeSlab) {
@@ -385,7 +380,7 @@ int launchPlace(hu_batch* b, const hu_sep_params* p) {
 
 int launchFinalize(hu_batch* b, const hu_sep_params* p) {
 	finalizeKernel<<<(b->nReads + 63) / 64, 64, 0, b->stream>>>(b->nReads, b->winStart, b->nKept, b->places, p->useTrueLoglik,
-			p->prior == HU_PRIOR_HEIGHT, p->onlyML, b->equalPerm, b->best);
+			p->prior == HU_PRIOR_HEIGHT, p->onlyML, b->best);
 	HU_CUDA(cudaEventRecord(b->ev[7], b->stream));
 	b->launches += 1;
 	HU_CUDA(cudaGetLastError());

@@ -11,11 +11,16 @@
 //     internal-node) sequences skip the valid plane.
 //   * the non-match columns, where a read only has the few insert bases buildGlobalAlign could place: these are
 //     listed per read and added from a slot-major transposed copy of the node sequences in the scan epilogue.
-// The result per (read, node) is the exact order-preserving integer key floor(d*2^31/N) (distinct rationals
-// with denominators < 2^13 differ by more than 2^-26, so keys order exactly like the reference's doubles);
+// The result per (read, node) is the exact order-preserving integer key floor(d*2^31/N): two distinct rationals
+// d1/N1 != d2/N2 differ by at least 1/(N1 N2), so their keys differ whenever N1 N2 <= 2^31, i.e. for N <= 46 340
+// compared columns, and equal rationals give equal keys and equal doubles -- keys order, and tie, exactly like the
+// reference's d/N doubles.  N is bounded by the bases a read has in its window; hu_batch_create refuses workspaces
+// whose reads could exceed the bound (HU_SEED_MAX_N);
 // a per-read radix select over (key, node id) returns the maxNSeed smallest in (dist, id) order.
 #include <stdlib.h>
+#include <string.h>
 #include "hu_batch.cuh"
+#include "hu_stdsort.cuh"
 
 namespace hu {
 
@@ -148,7 +153,7 @@ __global__ void __launch_bounds__(128) seedScanKernel(SeedArgs a, TreeDev t, int
 #pragma unroll
 	for (int s = 0; s < 4; ++s) {
 		const int node = __ldg(t.scanNode + slot + s);
-		pos[s] = __ldg(t.posOfSlot + slot + s);
+		pos[s] = __ldg(a.posOfSlot + slot + s);
 		excl[s] = node < 0 || !(__ldg(t.height + max(node, 0)) <= a.maxHeight);
 	}
 #pragma unroll
@@ -344,6 +349,7 @@ extern "C" void hu_prof_seed(unsigned long long* out) { cudaMemcpyFromSymbol(out
 
 typedef unsigned long long lit_t;               // (key << 32) | candidate position; only the key is compared
 #define LIT_KEY(v) ((uint32_t) ((v) >> 32))
+struct LitLess { __device__ __forceinline__ bool operator()(lit_t a, lit_t b) const { return LIT_KEY(a) < LIT_KEY(b); } };
 
 // loads the compiler may not sink towards their first use: the flag passes issue a batch of these back to back, so
 // that HU_LIT_UNROLL requests per lane are in flight (plain loads were re-serialised into load / use pairs)
@@ -475,7 +481,11 @@ __device__ __noinline__ void litWarpIntrosort(lit_t* sbuf, uint32_t* wsc, int m,
 		top--;
 		int l = st[top][0], h = st[top][1], dep = st[top][2];
 		while (h - l > 16 && lo + l < want) {
-			if (dep == 0) { if (lane == 0) *overflow = 1; break; }
+			if (dep == 0) { // depth budget spent: std::__partial_sort(first, last, last) = heap sort of the range, literally (hu_stdsort.cuh)
+				if (lane == 0) { ssHeapSort(sbuf + l, h - l, LitLess()); *overflow = 1; }
+				__syncwarp();
+				break;
+			}
 			dep--;
 			if (lane == 0) litMedianToFirst(sbuf, l, l + 1, l + (h - l) / 2, h - 1);
 			__syncwarp();
@@ -742,7 +752,14 @@ __global__ void __launch_bounds__(HU_LIT_THREADS) seedSortLiteralKernel(SeedArgs
 			// __introsort_loop on [sLo, sHi); sub-ranges beyond the wanted prefix are dropped
 			while (sHi - sLo > 16 && sLo < want) {
 				const int lo = sLo, hi = sHi;
-				if (sDepth == 0) { if (tid == 0) sOverflow = 1; break; } // would fall back to heap sort: not replayed
+				if (sDepth == 0) {
+					// depth budget (2 lg n) spent: __introsort_loop finishes the range with std::__partial_sort(first, last, last),
+					// i.e. make_heap + sort_heap.  Replayed literally by one thread (hu_stdsort.cuh); a median-of-3 adversary is
+					// needed to get here, so speed does not matter, the element order does.
+					if (tid == 0) { ssHeapSort(wp + lo, hi - lo, LitLess()); sOverflow = 1; }
+					__syncthreads();
+					break;
+				}
 				__syncthreads();
 				if (!inSm && sTop == 0 && hi - lo <= HU_LIT_SMEM) {
 					// nothing is pending outside [lo, hi): every later range lies inside it, and it fits in shared memory.
@@ -937,11 +954,22 @@ __global__ void __launch_bounds__(HU_LIT_THREADS) seedSortLiteralKernel(SeedArgs
 				}
 			}
 			sCut = nOut;
-			a.nSeeds[r] = sOverflow ? -nOut - 1 : nOut;
+			a.nSeeds[r] = nOut;
+			if (sOverflow && a.heapFallbacks) atomicAdd(a.heapFallbacks, 1); // diagnostic: reads whose replay took the heap-sort path
 		}
 		__syncthreads();
 		if (tid < sCut) a.seedIds[(size_t) r * HU_MAX_SEED + tid] = nodeOfPos[(uint32_t) sbuf[tid]];
 	}
+}
+
+#define HU_LIT_SMEM_MAX (200 * 1024)
+
+// per-device kernel attributes (hu_db_create calls this with the device current)
+int configSeedKernels() {
+	HU_CUDA(cudaFuncSetAttribute(seedScanKernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+	HU_CUDA(cudaFuncSetAttribute(seedScanKernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+	HU_CUDA(cudaFuncSetAttribute(seedSortLiteralKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HU_LIT_SMEM_MAX));
+	return HU_OK;
 }
 
 int launchSeed(hu_batch* b, const hu_sep_params* p) {
@@ -957,6 +985,37 @@ int launchSeed(hu_batch* b, const hu_sep_params* p) {
 	a.aligned = b->vit.aligned;
 	a.winStart = b->winStart;
 	a.winEnd = b->winEnd;
+	a.heapFallbacks = b->workCount + 4;
+	HU_CUDA(cudaMemsetAsync(a.heapFallbacks, 0, sizeof(int), b->stream));
+	// The key vector of a read is getSeed's candidate vector: the non-root nodes in id order that pass the height filter
+	// (src/HmmUFOtu_main.cpp:131-137).  The literal order replays std::sort on exactly that vector, so with -H/--max-height
+	// the candidates are compacted (positions = ranks among the passing nodes); the (dist, id) order keeps one position per
+	// non-root node and marks the filtered ones excluded.
+	const bool literal = p->seedOrder == HU_SEED_ORDER_STDSORT;
+	a.posOfSlot = t.posOfSlot; a.nodeOfPos = t.nodeOfPos; a.nCand = t.nCand;
+	if (literal && p->maxHeight < INFINITY) {
+		if (!b->posOfSlotH || b->heightCached != p->maxHeight) {
+			std::vector<int> posOfNode(t.nNodes, -1), posOfSlot(t.scanPitch, -1), nodeOfPos(t.scanPitch, 0x7fffffff);
+			int pos = 0;
+			for (int x = 0; x < t.nNodes; ++x)
+				if (x != t.root && db->heightHost[x] <= p->maxHeight) { posOfNode[x] = pos; nodeOfPos[pos] = x; pos++; }
+			for (int sl = 0; sl < t.scanPitch; ++sl)
+				if (db->scanNodeHost[sl] >= 0) posOfSlot[sl] = posOfNode[db->scanNodeHost[sl]];
+			if (!b->posOfSlotH) {
+				void* q = NULL;
+				HU_CUDA(cudaMalloc(&q, (size_t) 2 * t.scanPitch * sizeof(int)));
+				b->allocs.push_back(q);
+				b->posOfSlotH = (int*) q;
+				b->nodeOfPosH = b->posOfSlotH + t.scanPitch;
+			}
+			HU_CUDA(cudaStreamSynchronize(b->stream)); // a previous run may still read the old map
+			HU_CUDA(cudaMemcpy(b->posOfSlotH, posOfSlot.data(), (size_t) t.scanPitch * sizeof(int), cudaMemcpyHostToDevice));
+			HU_CUDA(cudaMemcpy(b->nodeOfPosH, nodeOfPos.data(), (size_t) t.scanPitch * sizeof(int), cudaMemcpyHostToDevice));
+			b->nCandH = pos;
+			b->heightCached = p->maxHeight;
+		}
+		a.posOfSlot = b->posOfSlotH; a.nodeOfPos = b->nodeOfPosH; a.nCand = b->nCandH;
+	}
 	b->seed = a;
 	HU_CUDA(cudaEventRecord(b->ev[2], b->stream));
 	HU_CUDA(cudaMemsetAsync(a.rValid, 0, (size_t) a.nReadsPad * sizeof(int), b->stream));
@@ -966,20 +1025,12 @@ int launchSeed(hu_batch* b, const hu_sep_params* p) {
 	sparseListKernel<<<(b->nReads + 3) / 4, 128, 0, b->stream>>>(a, t.csLen, t.colK);
 	const int groups = a.nReadsPad / HU_SCAN_READS;
 	const size_t smem = (size_t) t.nPWords * HU_SCAN_READS * sizeof(uint4);
-	static bool attr = false;
-	if (!attr) {
-		HU_CUDA(cudaFuncSetAttribute(seedScanKernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-		HU_CUDA(cudaFuncSetAttribute(seedScanKernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-		attr = true;
-	}
 	if (smem > 200 * 1024) { setError("profile too long for the seed-scan read tile (%d words)", t.nPWords); return HU_ERR_ARG; }
 	const int gapTiles = t.nGapSlots / HU_SCAN_TILE, allTiles = t.scanPitch / HU_SCAN_TILE;
 	// grid.x (fast) runs over read groups so that consecutive CTAs reuse the same node tile from L2
 	if (gapTiles > 0) seedScanKernel<true><<<dim3(groups, gapTiles), 128, smem, b->stream>>>(a, t, 0);
 	if (allTiles > gapTiles) seedScanKernel<false><<<dim3(groups, allTiles - gapTiles), 128, smem, b->stream>>>(a, t, gapTiles);
 	HU_CUDA(cudaEventRecord(b->ev[3], b->stream));
-	// literal order needs the candidate vector to be exactly getSeed's: every non-root node (no height filter)
-	const bool literal = p->seedOrder == HU_SEED_ORDER_STDSORT && !(p->maxHeight < INFINITY);
 	if (literal) {
 		int sms = 0;
 		HU_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, db->device));
@@ -987,12 +1038,7 @@ int launchSeed(hu_batch* b, const hu_sep_params* p) {
 		// the four bitmaps of the CTA-wide levels, or (shared-memory mode) four small bitmaps and the range itself
 		const size_t smemLit = std::max((size_t) 4 * maxWords * sizeof(uint32_t),
 		                                (size_t) 4 * (HU_LIT_SMEM / 32) * sizeof(uint32_t) + (size_t) std::min(t.nCand, HU_LIT_SMEM) * sizeof(lit_t));
-		if (smemLit > 200 * 1024) { setError("tree too large for the shared-memory bitmaps of the literal seed order (%d nodes)", t.nNodes); return HU_ERR_ARG; }
-		static size_t attrLit = 0;
-		if (smemLit > attrLit) {
-			HU_CUDA(cudaFuncSetAttribute(seedSortLiteralKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smemLit));
-			attrLit = smemLit;
-		}
+		if (smemLit > HU_LIT_SMEM_MAX) { setError("tree too large for the shared-memory bitmaps of the literal seed order (%d nodes; limit about %d)", t.nNodes, (int) (HU_LIT_SMEM_MAX / 16 * 32)); return HU_ERR_ARG; }
 		static int litCtas = 0; // resident CTAs per SM: 2 fills the SM's shared memory; 1 leaves room for another stream's kernels
 		if (!litCtas) { const char* e = getenv("HU_LIT_CTAS_PER_SM"); litCtas = e ? std::max(1, std::min(2, atoi(e))) : 2; }
 		const int grid = std::min(b->nReads, sms * litCtas);
@@ -1002,7 +1048,7 @@ int launchSeed(hu_batch* b, const hu_sep_params* p) {
 			b->allocs.push_back(q);
 			b->litIds = (unsigned long long*) q;
 		}
-		seedSortLiteralKernel<<<grid, HU_LIT_THREADS, smemLit, b->stream>>>(a, t.nCand, t.scanPitch, t.nodeOfPos, b->litIds, maxWords);
+		seedSortLiteralKernel<<<grid, HU_LIT_THREADS, smemLit, b->stream>>>(a, a.nCand, t.scanPitch, a.nodeOfPos, b->litIds, maxWords);
 	} else
 		seedSelectKernel<<<b->nReads, HU_SEL_THREADS, 0, b->stream>>>(a, t.scanPitch, t.nodeOfPos);
 	HU_CUDA(cudaEventRecord(b->ev[4], b->stream));
@@ -1012,3 +1058,58 @@ int launchSeed(hu_batch* b, const hu_sep_params* p) {
 }
 
 } // namespace hu
+
+// ---- diagnostics (tests): the literal-order kernel on caller-supplied key rows, without a database ----
+extern "C" int hu_debug_literal_order(int device, const uint32_t* keys, int32_t nRows, int32_t n, int32_t want, int32_t* outPos, int32_t* nOut,
+		int32_t* heapFallbacks) {
+	using namespace hu;
+	if (!keys || !outPos || !nOut || nRows < 1 || n < 1 || want < 1 || want > HU_MAX_SEED) { setError("hu_debug_literal_order: bad arguments"); return HU_ERR_ARG; }
+	HU_CUDA(cudaSetDevice(device));
+	if (configSeedKernels() != HU_OK) return HU_ERR_CUDA;
+	const int pitch = (n + 511) / 512 * 512;
+	uint32_t* dKeys = NULL;
+	int *dWin = NULL, *dIds = NULL, *dN = NULL, *dPos = NULL, *dHeap = NULL;
+	lit_t* dScratch = NULL;
+	int sms = 0;
+	HU_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+	const int grid = std::min((int) nRows, sms * 2);
+	HU_CUDA(cudaMalloc(&dKeys, (size_t) nRows * pitch * sizeof(uint32_t)));
+	HU_CUDA(cudaMemset(dKeys, 0xff, (size_t) nRows * pitch * sizeof(uint32_t)));
+	HU_CUDA(cudaMemcpy2D(dKeys, (size_t) pitch * sizeof(uint32_t), keys, (size_t) n * sizeof(uint32_t), (size_t) n * sizeof(uint32_t), nRows, cudaMemcpyHostToDevice));
+	HU_CUDA(cudaMalloc(&dWin, (size_t) nRows * sizeof(int)));
+	HU_CUDA(cudaMemset(dWin, 0, (size_t) nRows * sizeof(int)));
+	HU_CUDA(cudaMalloc(&dIds, (size_t) nRows * HU_MAX_SEED * sizeof(int)));
+	HU_CUDA(cudaMalloc(&dN, (size_t) nRows * sizeof(int)));
+	HU_CUDA(cudaMalloc(&dHeap, sizeof(int)));
+	HU_CUDA(cudaMemset(dHeap, 0, sizeof(int)));
+	HU_CUDA(cudaMalloc(&dScratch, (size_t) grid * pitch * sizeof(lit_t)));
+	std::vector<int> ident(pitch);
+	for (int i = 0; i < pitch; ++i) ident[i] = i;
+	HU_CUDA(cudaMalloc(&dPos, (size_t) pitch * sizeof(int)));
+	HU_CUDA(cudaMemcpy(dPos, ident.data(), (size_t) pitch * sizeof(int), cudaMemcpyHostToDevice));
+	SeedArgs a;
+	memset(&a, 0, sizeof a);
+	a.nReads = nRows; a.maxNSeed = want; a.maxDiff = INFINITY; a.maxHeight = INFINITY;
+	a.winStart = dWin; a.winEnd = dWin; a.keys = dKeys; a.seedIds = dIds; a.nSeeds = dN; a.heapFallbacks = dHeap;
+	a.nodeOfPos = dPos; a.nCand = n;
+	const int maxWords = (n + 31) / 32 + 1;
+	const size_t smemLit = std::max((size_t) 4 * maxWords * sizeof(uint32_t),
+	                                (size_t) 4 * (HU_LIT_SMEM / 32) * sizeof(uint32_t) + (size_t) std::min((int) n, HU_LIT_SMEM) * sizeof(lit_t));
+	int rc = HU_OK;
+	if (smemLit > HU_LIT_SMEM_MAX) { setError("hu_debug_literal_order: n too large"); rc = HU_ERR_ARG; }
+	else {
+		seedSortLiteralKernel<<<grid, HU_LIT_THREADS, smemLit>>>(a, n, pitch, dPos, dScratch, maxWords);
+		cudaError_t e = cudaDeviceSynchronize();
+		if (e != cudaSuccess) { setError("hu_debug_literal_order: %s", cudaGetErrorString(e)); rc = HU_ERR_CUDA; }
+	}
+	if (rc == HU_OK) {
+		std::vector<int> ids((size_t) nRows * HU_MAX_SEED);
+		cudaMemcpy(ids.data(), dIds, ids.size() * sizeof(int), cudaMemcpyDeviceToHost);
+		cudaMemcpy(nOut, dN, (size_t) nRows * sizeof(int), cudaMemcpyDeviceToHost);
+		if (heapFallbacks) cudaMemcpy(heapFallbacks, dHeap, sizeof(int), cudaMemcpyDeviceToHost);
+		for (int r = 0; r < nRows; ++r)
+			for (int k = 0; k < want; ++k) outPos[(size_t) r * want + k] = k < nOut[r] ? ids[(size_t) r * HU_MAX_SEED + k] : -1;
+	}
+	cudaFree(dKeys); cudaFree(dWin); cudaFree(dIds); cudaFree(dN); cudaFree(dHeap); cudaFree(dScratch); cudaFree(dPos);
+	return rc;
+}

@@ -614,6 +614,13 @@ __global__ void copyRowsKernel(int n, const hu_align_row* __restrict__ rows, hu_
 	if (r < n) merged[r] = rows[r];
 }
 
+#define HU_VIT_SMEM_MAX (227 * 1024)
+int configViterbiKernels() {
+	HU_CUDA(cudaFuncSetAttribute(viterbiBandedKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HU_VIT_SMEM_MAX));
+	HU_CUDA(cudaFuncSetAttribute(viterbiFullKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HU_VIT_SMEM_MAX));
+	return HU_OK;
+}
+
 int launchViterbi(hu_batch* b, int mode) {
 	hu_db* db = b->db;
 	const HmmDev& h = db->hmm;
@@ -635,17 +642,8 @@ int launchViterbi(hu_batch* b, int mode) {
 	const size_t perWarp = (viterbiWarpSmem(a.maxLen) + 15) / 16 * 16;
 	const int wpb = a.warpsPerBlock;
 	const size_t smem = perWarp * wpb;
-	static size_t attrSet = 0;
-	if (smem > attrSet) {
-		HU_CUDA(cudaFuncSetAttribute(viterbiBandedKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-		attrSet = smem;
-	}
 	const size_t smemFull = viterbiFullSmem(a.maxLen, wpb);
-	static size_t attrFull = 0;
-	if (smemFull > attrFull) {
-		HU_CUDA(cudaFuncSetAttribute(viterbiFullKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smemFull));
-		attrFull = smemFull;
-	}
+	if (smem > HU_VIT_SMEM_MAX || smemFull > HU_VIT_SMEM_MAX) { setError("maxSeqLen %d too long for the Viterbi shared-memory layout", a.maxLen); return HU_ERR_ARG; }
 	HU_CUDA(cudaMemsetAsync(a.fullCount, 0, 2 * sizeof(int), b->stream)); // count + cursor
 	HU_CUDA(cudaMemsetAsync(a.aligned, HU_CODE_PAD & 0xff, (size_t) nSeq * h.L, b->stream));
 	viterbiBandedKernel<<<(nSeq + wpb - 1) / wpb, wpb * 32, smem, b->stream>>>(h, a);

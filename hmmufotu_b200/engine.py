@@ -287,6 +287,14 @@ class Batch:
         check(_lib.load().hu_batch_get_seeds(self.h, _p(n), _p(ids), _p(dist)))
         return n, ids, dist
 
+    def seed_keys(self, read: int) -> np.ndarray:
+        """Diagnostic: the integer p-distance keys of one read over getSeed's candidate vector (after getSeed)."""
+        n = C.c_int32()
+        check(_lib.load().hu_batch_get_seed_keys(self.h, read, None, C.byref(n)))
+        keys = np.zeros(n.value, dtype=np.uint32)
+        check(_lib.load().hu_batch_get_seed_keys(self.h, read, _p(keys), C.byref(n)))
+        return keys
+
     def estimates(self):
         n = np.zeros(self.n, dtype=np.int32)
         rows = np.zeros((self.n, self.max_n_seed), dtype=PLACE_DT)

@@ -148,10 +148,14 @@ typedef struct hu_sep_params {
 	double maxDiff;      /* src/hmmufotu.cpp:50  (inf) */
 	double maxHeight;    /* src/hmmufotu.cpp:52  (inf) */
 	double maxError;     /* src/hmmufotu.cpp:49  (20) */
-	const int32_t* equalSortPerm; /* optional: for n = 1..HU_MAX_SEED the index std::sort(rbegin,rend) leaves
-	                               * first on n equal keys, at [n]; NULL = library-built table */
+	const int32_t* equalSortPerm; /* ignored (kept for layout compatibility): the std::sort calls of filterPlacements and of
+	                               * the final ordering (src/HmmUFOtu_main.cpp:164, src/hmmufotu.cpp:725-731) are replayed on
+	                               * the device move for move, ties and NaN keys included */
 	int32_t seedOrder;   /* HU_SEED_ORDER_STDSORT (default): the seeds libstdc++'s std::sort leaves in front, ties
-	                      * included (src/HmmUFOtu_main.cpp:139); HU_SEED_ORDER_ID: deterministic (dist, id) order */
+	                      * included (src/HmmUFOtu_main.cpp:139), also under maxHeight (the candidate vector is then the
+	                      * height-filtered one, as in getSeed); HU_SEED_ORDER_ID: deterministic (dist, id) order.
+	                      * Limits of the seed stage (HU_ERR_ARG beyond them): consensus length < 65536 columns; the
+	                      * literal order keeps four bitmaps of the candidate vector in shared memory: <= ~409 000 nodes */
 	int32_t estMethod;   /* -m|--method (src/hmmufotu.cpp:229-232): HU_EST_UNWEIGHTED (default) or HU_EST_WEIGHTED
 	                      * (estimateBranchLengthWeighted, src/PhyloTreeUnrooted.cpp:1034-1052) */
 	int32_t prior;       /* --prior (src/hmmufotu.cpp:236-241): HU_PRIOR_UNIFORM (default) or HU_PRIOR_HEIGHT
@@ -200,6 +204,15 @@ int hu_batch_get_estimates(hu_batch* b, int32_t* nKept, hu_place_row* rows /* nR
 int hu_batch_get_places(hu_batch* b, int32_t* nKept, hu_place_row* rows /* nReads x maxNSeed */);
 int hu_batch_get_best(hu_batch* b, hu_place_row* rows /* nReads */);
 
+/* diagnostics (tests): the key vector of one read after hu_seed_batch -- floor(d * 2^31 / N) per candidate, candidates =
+ * the non-root nodes in id order that pass maxHeight (0xFFFFFFFF: undefined distance); nCand = their number */
+int hu_batch_get_seed_keys(hu_batch* b, int32_t read, uint32_t* keys, int32_t* nCand);
+/* the device's literal-order kernel on caller-supplied key rows (nRows x n), positions of the first `want` out */
+int hu_debug_literal_order(int device, const uint32_t* keys, int32_t nRows, int32_t n, int32_t want, int32_t* outPos /* nRows x want */,
+		int32_t* nOut /* nRows */, int32_t* heapFallbacks /* 1, may be NULL */);
+/* the library's restatement of std::sort(rbegin, rend) on n keys (host): perm[k] = index of the element left at k */
+int hu_debug_stdsort(const double* keys, int32_t n, int32_t* perm);
+
 /* user timing marks: record CUDA event `id` (0..7) on the batch stream; elapsed ms between two marks
  * (possibly of two workspaces of the same device), both of which must have completed */
 int hu_batch_mark(hu_batch* b, int id);
@@ -217,6 +230,7 @@ typedef struct hu_batch_stats {
 	int64_t placeItems;   /* (read, placement) items */
 	int64_t placeBytes;   /* 64 * W per item */
 	int64_t launches;     /* kernels launched since the last hu_batch_upload / set_aligned */
+	int64_t seedHeapSorts; /* reads whose literal seed order reached introsort's heap-sort fallback (replayed; diagnostic) */
 } hu_batch_stats;
 int hu_batch_get_stats(hu_batch* b, hu_batch_stats* s);
 

@@ -388,4 +388,49 @@ int orc_run_reads(void* hp, void* op, int nReads, const char* reads, const long*
 
 int orc_sizeof_place_row() { return (int) sizeof(OrcPlaceRow); }
 
+/* ---- the real std::sort of this toolchain's libstdc++, for pinning the device's replay of it ---- */
+/* std::sort(v.rbegin(), v.rend(), byKey) as filterPlacements / the final ordering call it (src/HmmUFOtu_main.cpp:164,
+ * src/hmmufotu.cpp:725-731): perm[k] = original index of the element left at position k */
+void orc_stdsort_desc_perm(const double* keys, int n, int* perm) {
+	std::vector<std::pair<double, int> > v(n);
+	for (int i = 0; i < n; ++i) v[i] = std::make_pair(keys[i], i);
+	struct Cmp { static bool lt(const std::pair<double, int>& a, const std::pair<double, int>& b) { return a.first < b.first; } };
+	std::sort(v.rbegin(), v.rend(), Cmp::lt);
+	for (int i = 0; i < n; ++i) perm[i] = v[i].second;
+}
+/* std::sort(locs.begin(), locs.end()) as getSeed calls it (src/HmmUFOtu_main.cpp:139) on integer keys that order like the
+ * p-distances: the candidate positions of the first `want` elements */
+void orc_stdsort_keys(const unsigned int* keys, int n, int want, int* outPos) {
+	std::vector<PTLoc> v(n);
+	for (int i = 0; i < n; ++i) { PTLoc l = {0, 0, i, (double) keys[i]}; v[i] = l; }
+	std::sort(v.begin(), v.end());
+	for (int i = 0; i < want && i < n; ++i) outPos[i] = (int) v[i].id;
+}
+/* McIlroy's adversary ("A killer adversary for quicksort", 1999) run against this libstdc++'s std::sort: a key vector on
+ * which its median-of-3 quicksort degenerates, so that __introsort_loop spends its depth budget and falls back to
+ * __partial_sort (heap sort).  keys: n values (a permutation of 0..n-1 up to ties among the last few) */
+namespace {
+struct Adversary {
+	std::vector<int> val;
+	int nsolid, candidate, gas;
+	bool lt(int x, int y) {
+		if (val[x] == gas && val[y] == gas) { if (x == candidate) val[x] = nsolid++; else val[y] = nsolid++; }
+		if (val[x] == gas) candidate = x; else if (val[y] == gas) candidate = y;
+		return val[x] < val[y];
+	}
+};
+Adversary* g_adv = NULL;
+bool advLess(int a, int b) { return g_adv->lt(a, b); }
+}
+void orc_sort_killer(int n, unsigned int* keys) {
+	Adversary adv;
+	adv.val.assign(n, n - 1); adv.nsolid = 0; adv.candidate = 0; adv.gas = n - 1;
+	std::vector<int> ptr(n);
+	for (int i = 0; i < n; ++i) ptr[i] = i;
+	g_adv = &adv;
+	std::sort(ptr.begin(), ptr.end(), advLess);
+	g_adv = NULL;
+	for (int i = 0; i < n; ++i) keys[i] = (unsigned int) adv.val[i];
+}
+
 } // extern "C"

@@ -73,6 +73,9 @@ def lib() -> C.CDLL:
         L.orc_tree_set_options.argtypes = [vp, i32, i32, i32]
         L.orc_tree_evaluate_mt.argtypes = [vp, i32, i32]
         L.orc_run_reads.argtypes = [vp, vp, i32, C.c_char_p, vp, vp, vp, i32, i32, f64, i32, i32, i32, P(PlaceRow), vp, vp]
+        L.orc_stdsort_desc_perm.argtypes = [vp, i32, vp]
+        L.orc_stdsort_keys.argtypes = [vp, i32, i32, vp]
+        L.orc_sort_killer.argtypes = [i32, vp]
         assert L.orc_sizeof_place_row() == C.sizeof(PlaceRow)
         _LIB = L
     return _LIB
@@ -265,4 +268,27 @@ def run_reads(hmm: "OracleHmm", tree: "OracleTree", reads, col0: int = 0, max_n_
 def equal_sort_perm(n: int) -> np.ndarray:
     out = np.zeros(n, dtype=np.int32)
     lib().orc_equal_sort_perm(n, _p(out))
+    return out
+
+
+def stdsort_desc_perm(keys: np.ndarray) -> np.ndarray:
+    """The real std::sort(rbegin, rend, byKey): index of the element left at each position."""
+    k = np.ascontiguousarray(keys, dtype=np.float64)
+    out = np.zeros(k.size, dtype=np.int32)
+    lib().orc_stdsort_desc_perm(_p(k), k.size, _p(out))
+    return out
+
+
+def stdsort_keys(keys: np.ndarray, want: int) -> np.ndarray:
+    """The real std::sort(begin, end) of getSeed on integer keys: candidate positions of the first `want` elements."""
+    k = np.ascontiguousarray(keys, dtype=np.uint32)
+    out = np.zeros(min(want, k.size), dtype=np.int32)
+    lib().orc_stdsort_keys(_p(k), k.size, want, _p(out))
+    return out
+
+
+def sort_killer(n: int) -> np.ndarray:
+    """Key vector on which this libstdc++'s std::sort exhausts introsort's depth budget (McIlroy's adversary)."""
+    out = np.zeros(n, dtype=np.uint32)
+    lib().orc_sort_killer(n, _p(out))
     return out

@@ -101,3 +101,33 @@ def test_seed_key_formula_is_exact():
         got = np.floor(ds.astype(np.float64) * inv2 + np.float64(2.0 ** -20)).astype(np.int64)
         want = (ds << 31) // N
         assert (got == want).all(), N
+
+
+def _replay_desc(lib, keys):
+    k = np.ascontiguousarray(keys, dtype=np.float64)
+    perm = np.zeros(max(1, k.size), dtype=np.int32)
+    assert lib.hu_debug_stdsort(k.ctypes.data_as(C.c_void_p), k.size, perm.ctypes.data_as(C.c_void_p)) == 0
+    return perm[:k.size]
+
+
+def test_stdsort_replay_is_libstdcxx_sort(lib):
+    """hu_stdsort.cuh (what filterKernel / finalizeKernel and the heap-sort fallback of the literal seed order run on the
+    device) against the REAL std::sort(rbegin, rend) of this toolchain (oracle): same permutation for every n = 1..64 with
+    heavy ties, all-equal keys, NaN keys, sorted / reversed input, and -- well past 64 -- on key vectors built by McIlroy's
+    adversary, on which introsort exhausts its 2 lg n depth budget and finishes with __partial_sort (heap sort)."""
+    rng = np.random.default_rng(11)
+    for n in range(1, 65):
+        cases = [np.zeros(n), np.arange(n, dtype=float), np.arange(n, dtype=float)[::-1]]
+        for vals in (2, 3, 5, n):
+            cases += [rng.integers(0, vals, n).astype(float) for _ in range(6)]
+        nan = rng.integers(0, 3, n).astype(float)
+        nan[rng.random(n) < 0.3] = np.nan
+        cases += [nan, np.full(n, np.nan)]
+        for keys in cases:
+            assert np.array_equal(_replay_desc(lib, keys), O.stdsort_desc_perm(keys)), (n, keys)
+    assert [int(_replay_desc(lib, np.ones(n))[0]) for n in (17, 20, 33, 50)] == [15, 18, 31, 25]   # SURVEY.md F6/F8: the equal-key artefact
+    for n in (40, 64, 1000, 5000):
+        killer = O.sort_killer(n).astype(float)[::-1].copy()    # reverse-iterator sort sees the mirrored array
+        assert np.array_equal(_replay_desc(lib, killer), O.stdsort_desc_perm(killer)), n
+        ties = rng.integers(0, 7, n).astype(float)
+        assert np.array_equal(_replay_desc(lib, ties), O.stdsort_desc_perm(ties)), n
