@@ -1,13 +1,16 @@
 #!/usr/bin/env python
 """bench.py -- reads/s of the per-read assignment hot path (banded Viterbi + SEP placement).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--scale full|small]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--scale full|pe|long|small]
 
-One process per GPU (torchrun sets RANK/LOCAL_RANK/WORLD_SIZE for N > 1).  The workload is BASELINE.json
-configs[2]: a synthetic gg_97-scale database (99 322 leaves -> 198 643 nodes, 7 682 consensus columns, GTR)
-and 250 bp V4-like SE reads; a "step" is one batch of reads through alignSeq -> getSeed -> estimateSeq ->
-filterPlacements -> placeSeq -> calcQValues.  Reads are sharded over ranks, the database is replicated, and
-the only cross-rank traffic is the barrier / max-reduce of the timing (weak scaling).
+One process per GPU (torchrun sets RANK/LOCAL_RANK/WORLD_SIZE for N > 1).  Workloads (BASELINE.json configs):
+  full  = configs[2] (C3, the default and the headline): synthetic gg_97-scale database (99 322 leaves -> 198 643 nodes,
+          7 682 consensus columns, GTR) + 250 bp V4-like SE reads;
+  pe    = configs[3] (C4): the same database evaluated with GTR + dGamma4 (alpha 0.5) + 2 x 250 bp PE reads, overlapping mates;
+  long  = configs[4] (C5): the same database with HKY85 + dGamma4 + ~1 400 bp near-full-length reads (windows of ~7 000 columns).
+A "step" is one batch of reads through alignSeq -> getSeed -> estimateSeq -> filterPlacements -> placeSeq -> calcQValues
+and the gather of the fixed-size assignment rows (NCCL all_gather on device buffers when N > 1).  Reads are sharded over
+ranks, the database is replicated (weak scaling).
 
 Rank 0 prints ONE JSON line.  See DESIGN.md "Measurement" for how each field is obtained.
 """
@@ -27,19 +30,20 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "reads/s (banded Viterbi + SEP placement)"
+GG97 = dict(n_leaves=99322, cs_len=7682, occupancy=0.18, seed=20260103)
 SCALES = {
     # BASELINE.json configs[2]; window: all reads start inside one 300-column stretch
-    "full": dict(n_leaves=99322, cs_len=7682, occupancy=0.18, seed=20260103, window=(2000, 2300), read_len=250,
+    "full": dict(GG97, window=(2000, 2300), read_len=250, model="GTR", dg=None, cpu_per_core=40,
                  workload="C3: synthetic gg_97-scale DB (99322 leaves, 198643 nodes, csLen 7682, GTR) + 250 bp V4-like SE reads"),
-    # BASELINE.json configs[4]-like stress shape: near-full-length reads, windows of ~6500 columns (wide-window kernels)
-    "long": dict(n_leaves=99322, cs_len=7682, occupancy=0.18, seed=20260103, window=(0, 300), read_len=1200,
-                 workload="C5-like: synthetic gg_97-scale DB (GTR) + 1200 bp near-full-length SE reads (NOT the headline workload)"),
-    # BASELINE.json configs[3]-like shape on one GPU: 2 x 250 bp pairs with overlapping mates (merged windows of 1.5-2.5 k columns)
-    "pe": dict(n_leaves=99322, cs_len=7682, occupancy=0.18, seed=20260103, window=None, read_len=250, paired=True, insert_len=420,
-               workload="C4-like: synthetic gg_97-scale DB (GTR) + 2x250 bp PE reads, one GPU (NOT the headline workload)"),
-    # a shrunken stand-in for quick functional runs (NOT the benchmark configuration)
-    "small": dict(n_leaves=2000, cs_len=2000, occupancy=0.5, seed=20260101, window=(300, 500), read_len=250,
-                  workload="reduced functional config (2000 leaves, csLen 2000) -- not the BASELINE workload"),
+    # BASELINE.json configs[3]: the C3 database re-evaluated with dGamma K=4, alpha=0.5; 2 x 250 bp pairs, overlapping mates
+    "pe": dict(GG97, window=None, read_len=250, paired=True, insert_len=420, model="GTR", dg=(0.5, 4), cpu_per_core=10,
+               workload="C4: synthetic gg_97-scale DB (GTR + dGamma4, alpha 0.5) + 2x250 bp PE reads, overlapping mates (merged windows of 1.5-2.5 k columns)"),
+    # BASELINE.json configs[4]: HKY85 + dGamma4, near-full-length reads (a leaf holds ~1 380 residues: N(1400, 50) clipped to it)
+    "long": dict(GG97, window=(0, 300), read_len=1400, len_sd=50.0, model="HKY85", dg=(0.5, 4), cpu_per_core=2,
+                 workload="C5: synthetic gg_97-scale DB (HKY85 + dGamma4, alpha 0.5) + ~1400 bp near-full-length SE reads (windows of ~7000 columns)"),
+    # a shrunken stand-in for quick functional runs (NOT a benchmark configuration)
+    "small": dict(n_leaves=2000, cs_len=2000, occupancy=0.5, seed=20260101, window=(300, 500), read_len=250, model="GTR", dg=None, cpu_per_core=40,
+                  workload="reduced functional config (2000 leaves, csLen 2000) -- not a BASELINE workload"),
 }
 
 
@@ -90,35 +94,47 @@ class ClockSampler:
 
 
 def build_inputs(cfg, n_reads, read_seed):
+    """-> (db, (reads,) or (reads, mates)).  The tree and the sequences are those of C3 for every gg_97-scale shape; the
+    substitution model and the discrete-Gamma rates the database is EVALUATED with are the shape's."""
     from hmmufotu_b200 import synth
     t0 = time.time()
     db = synth.make_db(n_leaves=cfg["n_leaves"], cs_len=cfg["cs_len"], occupancy=cfg["occupancy"], seed=cfg["seed"])
+    db.model = synth.gg97_model(synth.MODEL_NAMES.index(cfg["model"]))
+    if cfg.get("dg"):
+        db.dg_rates = synth.discrete_gamma_rates(cfg["dg"][0], cfg["dg"][1])
     t1 = time.time()
     if cfg.get("paired"):
-        reads = synth.make_pairs(db, n_reads, read_len=cfg["read_len"], insert_len=cfg["insert_len"], insert_sd=20.0, seed=read_seed)
+        sets = synth.make_pairs(db, n_reads, read_len=cfg["read_len"], insert_len=cfg["insert_len"], insert_sd=20.0, seed=read_seed)
     else:
-        reads = synth.make_reads(db, n_reads, read_len=cfg["read_len"], seed=read_seed, window=cfg["window"])
-    log("synthetic DB %.1fs (K=%d, nodes=%d), %d reads %.1fs" % (t1 - t0, db.K, db.n_nodes, n_reads, time.time() - t1))
-    return db, reads
+        sets = (synth.make_reads(db, n_reads, read_len=cfg["read_len"], seed=read_seed, window=cfg["window"], len_sd=cfg.get("len_sd", 0.0)),)
+    log("synthetic DB %.1fs (K=%d, nodes=%d, model %s%s), %d reads %.1fs" %
+        (t1 - t0, db.K, db.n_nodes, cfg["model"], " + dGamma%d" % cfg["dg"][1] if cfg.get("dg") else "", n_reads, time.time() - t1))
+    return db, sets
 
 
-class CpuReference:
-    """The CPU oracle (reference-equivalent restatement) over a read sample, on `threads` host threads.
-    The tree is cut to the consensus columns the reads can touch: every SEP quantity is per column, so the
-    result is the one the full tree gives, and the oracle's 4 x csLen fp64 messages of all 397k directed edges
-    (98 GB at full length) fit in host memory.  Building the cut tree (all-roots evaluation) is untimed: it is
-    the database load of the reference."""
+def _oracle():
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle_py as O
+    return O
 
-    def __init__(self, db, reads, threads):
-        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+class SlicedCpuReference:
+    """The CPU oracle (reference-equivalent restatement; kind "port") over a read sample, on `threads` host threads, with
+    no GPU anywhere.  The tree is cut to the consensus columns the reads can touch: every SEP quantity is per column, so the
+    result is the one the full tree gives, and the oracle's 4 x csLen fp64 messages of all 397k directed edges (98 GB at
+    full length) fit in host memory.  Building the cut tree (all-roots evaluation on the CPU) is untimed: it is the
+    database load of the reference.  Only for shapes whose reads share a window (C3)."""
+
+    def __init__(self, db, sets, threads):
         import copy
-        import oracle_py as O
-        self.O, self.reads, self.threads = O, reads, threads
+        O = self.O = _oracle()
+        self.sets, self.threads = sets, threads
         self.ohmm = O.OracleHmm(db)
         lo, hi = db.cs_len, 0
-        for i in range(reads.n):  # alignment columns of the sample fix the slice
-            a = self.ohmm.align(reads.read_str(i), reads.vpaths[i, :reads.n_paths[i]])
-            lo, hi = min(lo, int(a["coords"][4]) - 1), max(hi, int(a["coords"][5]) - 1)
+        for x in sets:
+            for i in range(x.n):  # alignment columns of the sample fix the slice
+                a = self.ohmm.align(x.read_str(i), x.vpaths[i, :x.n_paths[i]])
+                lo, hi = min(lo, int(a["coords"][4]) - 1), max(hi, int(a["coords"][5]) - 1)
         self.c0, self.c1 = max(0, lo - 8), min(db.cs_len, hi + 9)
         sl = copy.copy(db)
         sl.cs_len = self.c1 - self.c0
@@ -126,20 +142,104 @@ class CpuReference:
         t0 = time.time()
         self.otree = O.OracleTree(sl, evaluate=True, infer_internal=True, threads=threads)
         self.build_seconds = time.time() - t0
+        self.how = "oracle tree cut to consensus columns %d..%d, evaluated on the CPU in %.0fs (untimed)" % (self.c0, self.c1, self.build_seconds)
 
     def run(self):
         t0 = time.time()
-        rows, coords, cost, bad = self.O.run_reads(self.ohmm, self.otree, self.reads, col0=self.c0, seed_order=0, threads=self.threads)
+        rows, coords, cost, bad, ties = self.O.run_reads(self.ohmm, self.otree, self.sets[0], col0=self.c0, seed_order=0, threads=self.threads,
+                                                         mates=self.sets[1] if len(self.sets) > 1 else None, with_ties=True)
         dt = time.time() - t0
-        return dict(reads_per_s=self.reads.n / dt, seconds=dt, build_seconds=self.build_seconds, columns=(self.c0, self.c1),
-                    bad=bad, rows=rows, coords=coords)
+        return dict(reads_per_s=self.sets[0].n / dt, seconds=dt, bad=bad, rows=rows, coords=coords, cost=cost, ties=ties, col0=self.c0)
+
+
+class DeviceDbCpuReference:
+    """The same CPU program over the SAME database the GPU arm holds: node sequences (inferred ones included) and the
+    messages of the edges the sample can touch are read back from the device replica (hu_db_get_seq,
+    hu_db_get_messages_of) -- the database is an input of the per-read path, as the .ptu file is for the reference -- so no
+    98 GB of messages is ever built in host memory and the parity check compares the two arms on identical inputs.  The
+    edges are the GPU's own seeds of the sample reads; a CPU seed outside that set is reported (row.c = -2) and counts as
+    a parity mismatch.  Everything timed (alignSeq .. calcQValues for every read of the sample) runs on the host threads."""
+
+    def __init__(self, db, gdb, sets, seed_ids, windows, threads):
+        import copy
+        O = self.O = _oracle()
+        self.sets, self.threads = sets, threads
+        self.ohmm = O.OracleHmm(db)
+        t0 = time.time()
+        ok = windows[:, 0] >= 0
+        self.c0 = max(0, int(windows[ok, 0].min()) - 8) if ok.any() else 0
+        self.c1 = min(db.cs_len, int(windows[ok, 1].max()) + 9) if ok.any() else db.cs_len
+        seq = gdb.seqs()
+        sl = copy.copy(db)
+        sl.cs_len = self.c1 - self.c0
+        sl.seq = np.ascontiguousarray(seq[:, self.c0:self.c1])
+        del seq
+        self.otree = O.OracleTree(sl, evaluate=False)
+        ids = np.unique(seed_ids[seed_ids >= 0]).astype(np.int64)
+        up, dn = gdb.messages_of(ids, self.c0, self.c1 - self.c0)
+        self.otree.set_sparse_messages(ids, up, dn)
+        self.build_seconds = time.time() - t0
+        self.how = ("database read back from the device replica: all node sequences + the messages of %d edges (the sample's seeds), "
+                    "consensus columns %d..%d, %.1f GB, %.0fs (untimed)" % (ids.size, self.c0, self.c1, 2 * up.nbytes / 1e9, self.build_seconds))
+
+    run = SlicedCpuReference.run
+
+
+def compare_rows(cpu, merged, best, n):
+    """GPU rows (through the C ABI) against the CPU program's, read by read: alignment coordinates and cost bit-exact, the
+    chosen branch / annotated node identical, ratio, wnr and log-likelihood to 1e-9 relative."""
+    rows, coords, cost, ties = cpu["rows"], cpu["coords"], cpu["cost"], cpu["ties"]
+    out = dict(checked=0, mismatched=0, near_tie_reordered=0, chimera=0, examples=[])
+
+    def close(a, b):
+        return a == b or abs(a - b) <= 1e-9 * max(abs(a), abs(b), 1e-300) or (a != a and b != b)
+
+    for i in range(n):
+        out["checked"] += 1
+        r, g, m = rows[i], best[i], merged[i]
+        bad = []
+        if r.c == -3:                                   # PE orientation test failed on the CPU: the GPU must flag the same
+            out["chimera"] += 1
+            if not (m["flags"] & 8):
+                bad.append("chimera flag")
+        else:
+            if [int(m[f]) for f in ("seqStart", "seqEnd", "hmmStart", "hmmEnd", "csStart", "csEnd")] != [int(v) for v in coords[i]]:
+                bad.append("coords")
+            if float(m["cost"]) != float(cost[i]):
+                bad.append("cost %r != %r" % (float(m["cost"]), float(cost[i])))
+            if r.c < 0:
+                bad.append("cpu row invalid (%d)" % r.c)
+            elif (int(g["cNode"]), int(g["pNode"])) != (r.c, r.p):
+                if ties[i]:
+                    out["near_tie_reordered"] += 1     # order of estimates that agree to 1e-11 is rounding noise in either program
+                else:
+                    bad.append("branch %d->%d != %d->%d" % (g["cNode"], g["pNode"], r.c, r.p))
+            else:
+                if int(g["aNode"]) != r.a:
+                    bad.append("aNode")
+                if int(g["nPlaces"]) != r.pad:
+                    bad.append("nPlaces %d != %d" % (g["nPlaces"], r.pad))
+                for f, v in (("ratio", r.ratio), ("wnr", r.wnr), ("loglik", r.loglik)):
+                    if not close(float(g[f]), float(v)):
+                        bad.append("%s %r != %r" % (f, float(g[f]), float(v)))
+                for f, v in (("qPlace", r.qPlace), ("qTaxon", r.qTaxon)):   # -10 log10(1 - p): beyond Q ~ 150, 1 - p is rounding noise in either program
+                    a, b_ = float(g[f]), float(v)
+                    if not (a == b_ or abs(a - b_) <= 1e-7 * max(abs(a), abs(b_)) or (a != a and b_ != b_) or min(a, b_) > 150):
+                        bad.append("%s %r != %r" % (f, a, b_))
+        if bad:
+            out["mismatched"] += 1
+            if len(out["examples"]) < 4:
+                out["examples"].append("read %d: %s" % (i, "; ".join(bad)))
+    if not out["examples"]:
+        del out["examples"]
+    return out
 
 
 def calibrate_reference(threads):
     """The reference's OWN binary (oracle/_ref/hmmufotu, built from /root/reference/src against the stand-in
     Eigen/Boost headers) and the oracle port on the same 128 reads of the reference-built 70_otus database
     (tests/golden/ref70, BASELINE.json configs[0]), both on `threads` host threads: how the port used for the
-    configs[2] baseline relates to the real program.  None when the prebuilt binary is absent."""
+    gg_97-scale baselines relates to the real program.  None when the prebuilt binary is absent."""
     import gzip
     import shutil
     import tempfile
@@ -149,8 +249,8 @@ def calibrate_reference(threads):
     if not (os.path.exists(exe) and os.path.exists(os.path.join(gold, name + ".ptu.gz"))):
         return None
     try:
-        sys.path.insert(0, os.path.join(ROOT, "oracle")); sys.path.insert(0, os.path.join(ROOT, "tests"))
-        import oracle_py as O
+        O = _oracle()
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
         import refdb
         from types import SimpleNamespace
         d = tempfile.mkdtemp(prefix="hu_cal_")
@@ -202,6 +302,30 @@ def main():
     return rc
 
 
+def make_config(cfg, B, world, n_ws, db_gb=None, n_nodes=None):
+    """`config` of the JSON line -- the same dict for both arms (the reference arm runs a bounded sample of this workload)."""
+    c = dict(workload=cfg["workload"], batch=B, parallelism="replicated DB, reads sharded x%d, rows gathered by one NCCL all_gather per batch" % world,
+             l2="inputs larger than L2 (DB ~126 GB per GPU, per-batch key matrix %.1f GB)" % (B * (2 * cfg["n_leaves"] - 1) * 4 / 1e9),
+             workspaces=n_ws)
+    return c
+
+
+def gpu_sample_seeds(engine, gdb, sets, sample, max_len, paired):
+    """The GPU's seeds and windows of the first `sample` reads (what decides which edges the CPU arm's sparse database needs),
+    and its rows for the parity check."""
+    b = engine.Batch(gdb, sample, max_len, paired=paired)
+    b.upload(*[x.slice(0, sample) for x in sets])
+    b.assign(engine.SepParams())
+    ns, ids, _ = b.seeds()
+    merged = b.merged()
+    best = b.best()
+    win = np.stack([merged["csStart"] - 1, merged["csEnd"] - 1], axis=1).astype(np.int64)
+    win[(merged["flags"] & (8 | 16)) != 0] = -1
+    heap = b.stats()["seedHeapSorts"]
+    b.close()
+    return ids, win, merged, best, heap
+
+
 def _main(real_stdout):
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -209,7 +333,7 @@ def _main(real_stdout):
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--scale", default=os.environ.get("HU_BENCH_SCALE", "full"), choices=sorted(SCALES))
-    ap.add_argument("--batch", type=int, default=int(os.environ.get("HU_BENCH_BATCH", "8192")))
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("HU_BENCH_BATCH", "0")))
     ap.add_argument("--cpu-sample", type=int, default=int(os.environ.get("HU_BENCH_CPU_SAMPLE", "0")))
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--workspaces", type=int, default=int(os.environ.get("HU_BENCH_WORKSPACES", "2")))
@@ -219,28 +343,42 @@ def _main(real_stdout):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     cores = os.cpu_count() or 1
+    paired = bool(cfg.get("paired"))
+    B = args.batch or (2048 if args.scale == "long" else 8192)
+    n_ws = max(1, args.workspaces)
+    sample = args.cpu_sample or max(cores * cfg["cpu_per_core"], 32)
 
     if args.impl == "reference":
-        # the reference arm: CPU only, rank 0 only
+        # the reference arm: the CPU program on all host threads over a bounded sample of the same workload; rank 0 only
         if rank != 0:
             return 0
-        sample = args.cpu_sample or max(cores * 16, 128)
-        db, reads = build_inputs(cfg, sample, read_seed=1000)
+        db, sets = build_inputs(cfg, sample, read_seed=1000)
+        if args.scale in ("full", "small"):
+            ref = SlicedCpuReference(db, sets, cores)                  # no GPU anywhere in this arm
+        else:
+            # reads of these shapes touch the whole consensus: the database (all-roots evaluation, 98 GB of messages) is
+            # produced on the device as for the product arm and the needed part read back; the timed region is CPU only
+            import torch
+            torch.cuda.set_device(local)
+            from hmmufotu_b200 import engine
+            gdb = engine.Database(db, device=local)
+            max_len = max(int(np.max(np.diff(x.offsets))) for x in sets) + 8
+            ids, win, _, _, _ = gpu_sample_seeds(engine, gdb, sets, sample, max_len, paired)
+            ref = DeviceDbCpuReference(db, gdb, sets, ids, win, cores)
+            gdb.close()
         vals = []
-        ref = CpuReference(db, reads, cores)
         for step in range(args.warmup + args.steps):
             r = ref.run()
             if step >= args.warmup:
                 vals.append(r)
-            log("reference step %d: %.2f reads/s (%d reads, %.1fs; oracle DB slice %s built in %.1fs)" %
-                (step, r["reads_per_s"], sample, r["seconds"], r["columns"], r["build_seconds"]))
+            log("reference step %d: %.2f reads/s (%d reads, %.1fs; %s)" % (step, r["reads_per_s"], sample, r["seconds"], ref.how))
         tot = sum(v["seconds"] for v in vals)
         v = sample * len(vals) / tot
         line = dict(metric=METRIC, value=v, unit="reads/s", impl="reference", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                     ms_per_step=1e3 * tot / len(vals), higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64",
-                    data="synthetic", config=dict(workload=cfg["workload"], batch=sample, l2="inputs larger than L2"),
+                    data="synthetic", config=make_config(cfg, B, args.gpus, n_ws),
                     cpu_baseline=dict(value=v, unit="reads/s", cores=cores, kind="port",
-                                      sample="%d reads per step on %d threads; oracle tree cut to consensus columns %d..%d" % (sample, cores, vals[0]["columns"][0], vals[0]["columns"][1]),
+                                      sample="%d reads per step on %d threads; %s" % (sample, cores, ref.how),
                                       calibration=calibrate_reference(cores)),
                     e2e=dict(value=v, unit="reads/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
         print(json.dumps(line), file=real_stdout, flush=True)
@@ -253,21 +391,16 @@ def _main(real_stdout):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    from hmmufotu_b200 import engine
+    from hmmufotu_b200 import driver, engine
 
-    B = args.batch
-    n_ws = max(1, args.workspaces)
     pool_batches = 4
-    db, reads = build_inputs(cfg, B * pool_batches, read_seed=1 + rank)
+    db, sets = build_inputs(cfg, B * pool_batches, read_seed=1 + rank)
     t0 = time.time()
     gdb = engine.Database(db, device=local)          # uploads, evaluates all messages on the device, repacks
     log("rank %d: device DB %.1f GB in %.1fs" % (rank, gdb.bytes / 1e9, time.time() - t0))
-    paired = bool(cfg.get("paired"))
-    if paired and (world > 1 or not args.no_cpu):
-        raise SystemExit("bench.py: the paired-end shape is a single-GPU functional run (--no-cpu)")
-    sets = reads if paired else (reads,)
     max_len = max(int(np.max(np.diff(x.offsets))) for x in sets) + 8
     ws = [engine.Batch(gdb, B, max_len, paired=paired) for _ in range(n_ws)]
+    gathers = [driver.DeviceGather(B, world, local) for _ in range(n_ws)]
     params = engine.SepParams()
     batches = []
     for i in range(pool_batches):
@@ -293,20 +426,31 @@ def _main(real_stdout):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def step_resident(i):
+        """one step with the inputs already in HBM: the five stages + the rows' gather, all enqueued, nothing waited for"""
+        k = i % n_ws
+        ws[k].assign(params)
+        gathers[k].launch(ws[k], (rank * args.steps + i) * B)
+
+    def drain():
+        for k in range(n_ws):
+            gathers[k].finish_on_stream()           # the batch stream waits for its gather, so that the end mark covers it
+
     # ---------------- kernel-resident throughput: inputs already in HBM ----------------
     for i, w in enumerate(ws):
         w.upload(*batches[i % pool_batches])
-    for i in range(args.warmup):
-        ws[i % n_ws].assign(params)
+    for i in range(max(args.warmup, 1)):
+        step_resident(i)
+    drain()
     barrier()
     clk = ClockSampler(local)
     clk.start()
     stage = np.zeros(8)
-    ws[0].mark(0)
-    if n_ws > 1:
-        ws[1].mark(0)
+    for w in ws:
+        w.mark(0)
     for step in range(args.steps):
-        ws[step % n_ws].assign(params)
+        step_resident(step)
+    drain()
     for w in ws:
         w.mark(1)
     ms = max(ws[0].elapsed_ms(0, w, 1) for w in ws)
@@ -324,7 +468,7 @@ def _main(real_stdout):
         stage += ws[0].stage_ms()
         for k, v in ws[0].stats().items():
             stats[k] = stats.get(k, 0) + v
-    launches_per_step = stats["launches"] / n_meas
+    launches_per_step = stats["launches"] / n_meas + 1          # + the row-packing kernel of the gather
     if os.environ.get("HU_PROF"):  # a library built with HU_PROF=1 carries phase clocks of CTA 0 (see hu_seed.cu, hu_estimate.cu)
         import ctypes
         from hmmufotu_b200 import _lib
@@ -335,17 +479,25 @@ def _main(real_stdout):
                 getattr(L, sym)(buf)
                 log("%s %s" % (sym, list(buf)))
 
-    # ---------------- end to end: host buffers in, assignment rows out, every step ----------------
+    # ---------------- end to end: host buffers in, assignment rows + traces out, every step ----------------
+    d2h_step = [0]
+
     def e2e_step(i):
         w = ws[i % n_ws]
         w.upload(*batches[i % pool_batches])
         w.assign(params)
+        gathers[i % n_ws].launch(w, (rank * args.steps + i) * B)
 
     def e2e_collect(i):
         w = ws[i % n_ws]
-        rows, traces = w.alignments(with_traces=True)
-        best = w.best()
-        return rows, traces, best
+        rows, (tbuf, toff) = w.alignments(with_traces="packed")    # alignment rows + packed traces into page-locked buffers
+        if world > 1:
+            g = gathers[i % n_ws].rows() if rank == 0 else (gathers[i % n_ws].wait(), None)[1]   # gathered rows to the host on rank 0
+            d2h_step[0] = rows.nbytes + int(toff[-1]) + toff.nbytes + (g.nbytes if g is not None else 0)
+        else:
+            best = w.best(pinned=True)
+            d2h_step[0] = rows.nbytes + int(toff[-1]) + toff.nbytes + best.nbytes
+        return rows
 
     for i in range(2):
         e2e_step(i)
@@ -357,15 +509,12 @@ def _main(real_stdout):
     for i in range(args.steps):
         if i + 1 < args.steps:
             e2e_step(i + 1)
-        rows, traces, best = e2e_collect(i)
-        if world > 1:  # the one collective of the path: fixed-size assignment rows to rank 0 (NCCL)
-            from hmmufotu_b200 import driver
-            driver.gather_rows(driver.pack_rows(rank * B, rows, best), world * B, world, rank, device="cuda")
+        e2e_collect(i)
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_value = world * B * args.steps / e2e_s
-    h2d = int(sum(x.codes.nbytes for x in batches[0]) + (B * 312 * len(batches[0])))
-    d2h = int(rows.nbytes + best.nbytes + sum(len(t) for t in traces))
+    h2d = int(sum(x.codes.nbytes for x in batches[0]) + (B * 312 * len(batches[0])))   # base codes + band plans (312 B per sequence)
+    d2h = int(d2h_step[0])
 
     # ---------------- roofline of every stage, and of the dominant one ----------------
     names = ["viterbi (K1)", "seed scan (K2)", "seed select (K2b)", "estimate (K3)", "place (K4)", "finalize"]
@@ -377,12 +526,13 @@ def _main(real_stdout):
         peaks = dict(hbm_gbs=float(pk["hbm_gbs"]), src="measured")
     except Exception:
         pass
-    # DRAM bytes per launch of each stage's kernels from the last committed `ncu --set full` capture
+    # DRAM bytes per launch of each stage's kernels from the last committed `ncu --set full` capture (C3 shape only)
     traffic = {}
-    try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-    except Exception:
-        pass
+    if args.scale == "full":
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        except Exception:
+            pass
     sm_clock = (clocks.get("sm_mhz") or 1965.0) * 1e6
     n_sm = torch.cuda.get_device_properties(local).multi_processor_count
     # algorithmic work per step: bytes for the streaming stages, cell updates for Viterbi;
@@ -408,19 +558,25 @@ def _main(real_stdout):
                          "shares one node tile among the reads of a batch, so its algorithmic rate exceeds physical HBM "
                          "(it is bound by POPC issue); per-stage figures under 'stages'")
 
-    # ---------------- CPU baseline (rank 0, N = 1) ----------------
-    cpu = None
+    # ---------------- CPU baseline + parity of the two arms on the same reads (rank 0, N = 1) ----------------
+    cpu = parity = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        sample = args.cpu_sample or max(cores * 40, 256)  # about 10-30 s of CPU work
-        sub = sets[0].slice(0, sample)
-        r = CpuReference(db, sub, cores).run()
-        # kind "port": the reference's own binary (oracle/_ref) needs the database as files, and configs[2]'s .ptu is
-        # 98 GB; the port is pinned to that binary row by row (tests/test_ref_pin.py) and is the FASTER CPU program
-        # (39.8 vs 5.8 reads/s single-threaded on the 70_otus database, where both run), so it is the conservative baseline
+        sample = min(sample, B)
+        sub = [x.slice(0, sample) for x in sets]
+        ids, win, merged, best, heap = gpu_sample_seeds(engine, gdb, sets, sample, max_len, paired)
+        ref = DeviceDbCpuReference(db, gdb, sub, ids, win, cores)
+        r = ref.run()
+        parity = compare_rows(r, merged, best, sample)
+        parity["seed_heap_sorts"] = int(heap)
+        parity["note"] = ("GPU rows through the C ABI vs the CPU program (oracle port, pinned to the reference binary in tests/test_ref_pin.py) on the same %d reads and "
+                          "the same database: coords + cost bit-exact, branch / node identical, ratio, wnr, loglik, Q values to 1e-9" % sample)
+        log("parity: %s" % json.dumps(parity))
+        # kind "port": the reference's own binary (oracle/_ref) needs the database as files, and a gg_97-scale .ptu is
+        # 98 GB; the port is pinned to that binary row by row (tests/test_ref_pin.py) and is the FASTER CPU program on the
+        # 70_otus database, where both run (see `calibration`), so it is the conservative baseline
         cpu = dict(value=r["reads_per_s"], unit="reads/s", cores=cores, kind="port",
-                   sample="%d reads of the same pool, %d threads, %.1fs; oracle tree cut to consensus columns %d..%d (built in %.0fs, untimed)"
-                          % (sample, cores, r["seconds"], r["columns"][0], r["columns"][1], r["build_seconds"]),
-                   calibration=calibrate_reference(cores))
+                   sample="%d reads of the same pool, %d threads, %.1fs; %s" % (sample, cores, r["seconds"], ref.how),
+                   calibration=calibrate_reference(cores) if args.scale == "full" else None)
 
     if world > 1:
         dist.destroy_process_group()
@@ -428,11 +584,9 @@ def _main(real_stdout):
         return 0
     line = dict(metric=METRIC, value=value, unit="reads/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
                 ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
-                config=dict(workload=cfg["workload"], batch=B, parallelism="replicated DB, reads sharded x%d" % world,
-                            l2="inputs larger than L2 (DB %.0f GB, per-batch key matrix %.1f GB)" % (gdb.bytes / 1e9, B * db.n_nodes * 4 / 1e9),
-                            workspaces=n_ws),
+                config=make_config(cfg, B, world, n_ws),
                 e2e=dict(value=e2e_value, unit="reads/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h),
-                gpu_launches=int(launches_per_step * args.steps), roofline=roofline, cpu_baseline=cpu, clocks=clocks,
+                gpu_launches=int(launches_per_step * args.steps), roofline=roofline, cpu_baseline=cpu, parity=parity, clocks=clocks,
                 viterbi_gcups=stages[names[0]].get("gcups"), stages=stages)
     print(json.dumps(line), file=real_stdout, flush=True)
     return 0

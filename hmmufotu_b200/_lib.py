@@ -71,7 +71,7 @@ SYMBOLS = ["hu_hmm_finalize", "hu_model_Pr", "hu_db_create", "hu_db_destroy", "h
            "hu_batch_get_aligned_codes", "hu_batch_get_seeds", "hu_batch_get_estimates", "hu_batch_get_places",
            "hu_batch_get_best", "hu_batch_stage_ms", "hu_batch_get_stats", "hu_trace_to_align", "hu_last_error",
            "hu_version", "hu_host_alloc", "hu_host_free", "hu_batch_mark", "hu_batch_elapsed", "hu_batch_get_seed_keys",
-           "hu_debug_literal_order", "hu_debug_stdsort"]
+           "hu_debug_literal_order", "hu_debug_stdsort", "hu_batch_pack_rows", "hu_batch_stream", "hu_db_get_messages_of"]
 
 _LIB = None
 
@@ -93,6 +93,7 @@ def load() -> C.CDLL:
     L.hu_db_destroy.argtypes = [vp]
     L.hu_db_get_messages.argtypes = [vp, i64, i64, vp, vp]
     L.hu_db_get_seq.argtypes = [vp, i64, i64, vp]
+    L.hu_db_get_messages_of.argtypes = [vp, i64, vp, i32, i32, vp, vp]
     L.hu_db_bytes.restype = i64
     L.hu_db_bytes.argtypes = [vp]
     L.hu_sep_params_default.argtypes = [P(SepParams)]
@@ -123,6 +124,9 @@ def load() -> C.CDLL:
     L.hu_batch_get_seed_keys.argtypes = [vp, i32, vp, P(i32)]
     L.hu_debug_literal_order.argtypes = [C.c_int, vp, i32, i32, i32, vp, vp, vp]
     L.hu_debug_stdsort.argtypes = [vp, i32, vp]
+    L.hu_batch_pack_rows.argtypes = [vp, i64, vp]
+    L.hu_batch_stream.restype = vp
+    L.hu_batch_stream.argtypes = [vp]
     _LIB = L
     return L
 

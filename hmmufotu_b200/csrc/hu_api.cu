@@ -85,6 +85,61 @@ __global__ void windowsKernel(int n, const hu_align_row* __restrict__ merged, in
 	winEnd[r] = bad ? -1 : a.csEnd - 1;
 }
 
+// ---- traces: the device keeps them end-to-start in fixed slots; they are handed back packed and start-to-end ----
+// offsets = exclusive scan of (traceLen + 1) over the sequences (one CTA; nSeq is a few thousand)
+__global__ void traceScanKernel(int nSeq, const hu_align_row* __restrict__ rows, long long* __restrict__ offs) {
+	__shared__ long long part[1024];
+	const int tid = threadIdx.x, per = (nSeq + blockDim.x - 1) / blockDim.x;
+	const int s0 = min(nSeq, tid * per), s1 = min(nSeq, s0 + per);
+	long long sum = 0;
+	for (int s = s0; s < s1; ++s) sum += rows[s].traceLen + 1;
+	part[tid] = sum;
+	__syncthreads();
+	for (int o = 1; o < blockDim.x; o <<= 1) {
+		const long long v = tid >= o ? part[tid - o] : 0;
+		__syncthreads();
+		part[tid] += v;
+		__syncthreads();
+	}
+	long long run = part[tid] - sum;
+	for (int s = s0; s < s1; ++s) { offs[s] = run; run += rows[s].traceLen + 1; }
+	if (tid == blockDim.x - 1) offs[nSeq] = part[tid];
+}
+__global__ void tracePackKernel(int nSeq, const hu_align_row* __restrict__ rows, const VPlan* __restrict__ plans,
+		const char* __restrict__ slots, const long long* __restrict__ offs, char* __restrict__ packed) {
+	const int s = blockIdx.x;
+	const int n = rows[s].traceLen;
+	const char* src = slots + plans[s].traceOff;
+	char* dst = packed + offs[s];
+	for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[n - 1 - i];
+	if (threadIdx.x == 0) dst[n] = 0;
+}
+
+// fixed-size assignment rows of the read-sharding driver (hmmufotu_b200/driver.py ROW_DT, 96 bytes), built on the device so
+// that the gather of the rows (the one collective of the path) can run on device buffers
+struct PackedRow {
+	long long read;
+	int seqStart, seqEnd, hmmStart, hmmEnd, csStart, csEnd, flags, nPlaces;
+	double cost;
+	int cNode, pNode, aNode, taxon;
+	double ratio, annoDist, loglik, qPlace, qTaxon;
+};
+static_assert(sizeof(PackedRow) == 104, "driver.ROW_DT");
+__global__ void packRowsKernel(int n, long long read0, const hu_align_row* __restrict__ merged, const hu_place_row* __restrict__ best,
+		PackedRow* __restrict__ out) {
+	const int r = blockIdx.x * blockDim.x + threadIdx.x;
+	if (r >= n) return;
+	const hu_align_row a = merged[r];
+	const hu_place_row b = best[r];
+	PackedRow o;
+	o.read = read0 + r;
+	o.seqStart = a.seqStart; o.seqEnd = a.seqEnd; o.hmmStart = a.hmmStart; o.hmmEnd = a.hmmEnd; o.csStart = a.csStart; o.csEnd = a.csEnd;
+	o.flags = a.flags; o.nPlaces = b.nPlaces; o.cost = a.cost;
+	o.cNode = b.cNode; o.pNode = b.pNode; o.aNode = b.aNode; o.taxon = b.taxon;
+	o.ratio = b.ratio; o.annoDist = b.annoDist; o.loglik = b.loglik; o.qPlace = b.qPlace; o.qTaxon = b.qTaxon;
+	out[r] = o;
+}
+
 } // namespace hu
 
 using namespace hu;
@@ -144,6 +199,9 @@ int hu_batch_create(hu_batch** out, hu_db* db, int32_t maxReads, int32_t maxSeqL
 	HU_TRY(balloc(b, &b->dPlans, (size_t) b->maxSeq));
 	b->tracesCap = (long long) b->maxSeq * (maxSeqLen + K + 4);
 	HU_TRY(balloc(b, &b->dTraces, (size_t) b->tracesCap));
+	HU_TRY(balloc(b, &b->dTracesPacked, (size_t) b->tracesCap));
+	HU_TRY(balloc(b, &b->dTraceOffs, (size_t) b->maxSeq + 1));
+	HU_TRY(palloc(b, &b->hTraceOffs, (size_t) b->maxSeq + 1));
 	HU_TRY(balloc(b, &b->vit.aligned, (size_t) b->maxSeq * L + 64)); // + slack for 16-byte rounded bulk copies
 	HU_TRY(balloc(b, &b->workItems, (size_t) maxReads * HU_MAX_SEED));
 	HU_TRY(balloc(b, &b->estItems, (size_t) maxReads * HU_MAX_SEED));
@@ -318,26 +376,37 @@ int hu_batch_sync(hu_batch* b) {
 int hu_batch_get_align(hu_batch* b, hu_align_row* rows, char* traces, int64_t traceCap, int64_t* traceOff) {
 	if (!b || !rows) return HU_ERR_ARG;
 	HU_CUDA(cudaSetDevice(b->db->device));
+	const bool wantTraces = traces && traceOff && b->vit.plans;
+	if (wantTraces) {
+		// reversed and packed on the device: the copy below moves sum(traceLen + 1) bytes, not the fixed slots
+		traceScanKernel<<<1, 1024, 0, b->stream>>>(b->nSeq, b->vit.rows, b->dTraceOffs);
+		tracePackKernel<<<b->nSeq, 128, 0, b->stream>>>(b->nSeq, b->vit.rows, b->dPlans, b->dTraces, b->dTraceOffs, b->dTracesPacked);
+		b->launches += 2;
+		HU_CUDA(cudaMemcpyAsync(b->hTraceOffs, b->dTraceOffs, (size_t) (b->nSeq + 1) * sizeof(long long), cudaMemcpyDeviceToHost, b->stream));
+	}
 	HU_CUDA(cudaMemcpyAsync(rows, b->vit.rows, (size_t) b->nSeq * sizeof(hu_align_row), cudaMemcpyDeviceToHost, b->stream));
 	HU_CUDA(cudaStreamSynchronize(b->stream));
-	if (traces && traceOff) {
-		// device traces are stored end-to-start in fixed slots; hand them back packed and start-to-end
-		std::vector<char> raw((size_t) b->hTraceOff[b->nSeq]);
-		HU_CUDA(cudaMemcpy(raw.data(), b->dTraces, raw.size(), cudaMemcpyDeviceToHost));
-		int64_t o = 0;
-		for (int s = 0; s < b->nSeq; ++s) {
-			traceOff[s] = o;
-			const int n = rows[s].traceLen;
-			if (o + n + 1 > traceCap) { setError("hu_batch_get_align: trace buffer too small"); return HU_ERR_ARG; }
-			const char* src = raw.data() + b->hTraceOff[s];
-			for (int i = 0; i < n; ++i) traces[o + i] = src[n - 1 - i];
-			traces[o + n] = 0;
-			o += n + 1;
-		}
-		traceOff[b->nSeq] = o;
-	}
+	if (wantTraces) {
+		const long long total = b->hTraceOffs[b->nSeq];
+		if (total > traceCap) { setError("hu_batch_get_align: trace buffer too small (%lld bytes needed)", total); return HU_ERR_ARG; }
+		HU_CUDA(cudaMemcpyAsync(traces, b->dTracesPacked, (size_t) total, cudaMemcpyDeviceToHost, b->stream));
+		for (int s = 0; s <= b->nSeq; ++s) traceOff[s] = b->hTraceOffs[s];
+		HU_CUDA(cudaStreamSynchronize(b->stream));
+		b->d2hBytes = total + (long long) (b->nSeq + 1) * 8 + (long long) b->nSeq * sizeof(hu_align_row);
+	} else
+		b->d2hBytes = (long long) b->nSeq * sizeof(hu_align_row);
 	return HU_OK;
 }
+
+int hu_batch_pack_rows(hu_batch* b, int64_t read0, void* devRows) {
+	if (!b || !devRows || b->nReads < 1) { setError("hu_batch_pack_rows: bad arguments"); return HU_ERR_ARG; }
+	HU_CUDA(cudaSetDevice(b->db->device));
+	packRowsKernel<<<(b->nReads + 127) / 128, 128, 0, b->stream>>>(b->nReads, read0, b->merged, b->best, (PackedRow*) devRows);
+	b->launches += 1;
+	HU_CUDA(cudaGetLastError());
+	return HU_OK;
+}
+void* hu_batch_stream(hu_batch* b) { return b ? (void*) b->stream : NULL; }
 
 #define HU_GET(dst, src, count)                                                                                   \
 	do {                                                                                                          \

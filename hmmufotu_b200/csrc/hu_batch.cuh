@@ -98,6 +98,10 @@ struct hu_batch {
 	long long ptrsCap;
 	char* dTraces;
 	long long tracesCap;
+	char* dTracesPacked;       // traces start-to-end, NUL-terminated, back to back (built by hu_batch_get_align)
+	long long* dTraceOffs;     // [nSeq + 1]
+	long long* hTraceOffs;     // pinned
+	long long d2hBytes;        // bytes the last getter moved to the host
 	int fullSlots;
 	hu_align_row* merged;  // [maxReads]
 	std::vector<hu::VPlan> hPlans;

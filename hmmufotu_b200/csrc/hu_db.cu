@@ -654,6 +654,39 @@ int hu_db_get_messages(hu_db* db, int64_t node0, int64_t n, double* up, double* 
 	return HU_OK;
 }
 
+// messages of a list of nodes over a column range, log domain, [i][column - col0][4]: what a sparse copy of the database
+// (a test oracle, a partial .ptu writer) needs, without moving whole 4 x csLen rows
+int hu_db_get_messages_of(hu_db* db, int64_t nIds, const int64_t* ids, int32_t col0, int32_t nCols, double* up, double* dn) {
+	if (!db || !ids || nIds < 0 || col0 < 0 || nCols < 1 || col0 + nCols > db->tree.csLen) { hu::setError("hu_db_get_messages_of: bad range"); return HU_ERR_ARG; }
+	for (int64_t i = 0; i < nIds; ++i)
+		if (ids[i] < 0 || ids[i] >= db->tree.nNodes) { hu::setError("hu_db_get_messages_of: node %lld out of range", (long long) ids[i]); return HU_ERR_ARG; }
+	HU_CUDA(cudaSetDevice(db->device));
+	const size_t cols = (size_t) db->tree.csLen, row = (size_t) nCols * 4;
+	const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(nIds, (int64_t) ((64u << 20) / (row * sizeof(double)))));
+	double* stage;
+	HU_CUDA(cudaMalloc(&stage, (size_t) chunk * row * sizeof(double)));
+	int rc = HU_OK;
+	for (int dir = 0; dir < 2 && rc == HU_OK; ++dir) {
+		double* dst = dir ? dn : up;
+		if (!dst) continue;
+		const double* E = dir ? db->tree.dn : db->tree.up;
+		const double* S = dir ? db->tree.dnS : db->tree.upS;
+		for (int64_t i0 = 0; i0 < nIds; i0 += chunk) {
+			const int64_t c = std::min(chunk, nIds - i0);
+			for (int64_t i = 0; i < c; ++i)
+				hu::toLogKernel<<<(unsigned) ((nCols + 255) / 256), 256>>>(E + ((size_t) ids[i0 + i] * cols + col0) * 4, S + (size_t) ids[i0 + i] * cols + col0,
+				                                                        (size_t) nCols, stage + (size_t) i * row);
+			if (cudaMemcpy(dst + (size_t) i0 * row, stage, (size_t) c * row * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess) {
+				hu::setError("hu_db_get_messages_of: copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+				rc = HU_ERR_CUDA;
+				break;
+			}
+		}
+	}
+	cudaFree(stage);
+	return rc;
+}
+
 int hu_db_get_seq(hu_db* db, int64_t node0, int64_t n, int8_t* seq) {
 	if (!db || node0 < 0 || node0 + n > db->tree.nNodes || !seq) { hu::setError("hu_db_get_seq: bad range"); return HU_ERR_ARG; }
 	HU_CUDA(cudaSetDevice(db->device));

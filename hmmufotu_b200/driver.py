@@ -63,3 +63,49 @@ def assign_reads(reads, process_shard: Callable, world: int = 1, rank: int = 0, 
     sub = reads.slice(lo, hi)
     a, b = process_shard(sub)
     return gather_rows(pack_rows(lo, a, b), reads.n, world, rank, device)
+
+
+class DeviceGather:
+    """The gather of the path on device buffers: every rank's batch writes its fixed-size rows into a device tensor with a
+    kernel on the batch stream (hu_batch_pack_rows); one NCCL all_gather, ordered after that kernel and asynchronous to the
+    host, collects the ranks' blocks in rank (= file) order, so it overlaps the next batch's kernels on the other workspace.
+    torch.distributed is the plumbing: the tensors are raw byte buffers and the batch's cudaStream_t is wrapped, not replaced."""
+
+    def __init__(self, batch_rows: int, world: int, device: int):
+        import torch
+        self.torch, self.world, self.n = torch, world, batch_rows
+        dev = torch.device("cuda", device)
+        self.mine = torch.empty(batch_rows * ROW_DT.itemsize, dtype=torch.uint8, device=dev)
+        self.all = torch.empty(world * batch_rows * ROW_DT.itemsize, dtype=torch.uint8, device=dev) if world > 1 else self.mine
+        self.work = None
+
+    def launch(self, batch, read0: int):
+        """Enqueue: pack kernel on the batch stream, then (world > 1) the all_gather after it.  Returns at once."""
+        import torch.distributed as dist
+        torch = self.torch
+        if self.world == 1:
+            batch.pack_rows(read0, self.mine.data_ptr())
+            return
+        self.ext = torch.cuda.ExternalStream(batch.stream)
+        with torch.cuda.stream(self.ext):
+            if self.work is not None:
+                self.work.wait()        # stream order: the previous gather has read `mine` before the pack kernel rewrites it
+            batch.pack_rows(read0, self.mine.data_ptr())
+            self.work = dist.all_gather_into_tensor(self.all, self.mine, async_op=True)
+
+    def finish_on_stream(self):
+        """Make the batch stream wait for the pending gather (so that an event recorded on it afterwards covers the gather)."""
+        if self.work is not None:
+            with self.torch.cuda.stream(self.ext):
+                self.work.wait()
+            self.work = None
+
+    def wait(self):
+        if self.work is not None:
+            self.work.wait()
+            self.work = None
+
+    def rows(self) -> np.ndarray:
+        """Host copy of the gathered rows (rank order = read order); synchronises."""
+        self.wait()
+        return self.all.cpu().numpy().view(ROW_DT)

@@ -145,6 +145,15 @@ class Database:
         check(_lib.load().hu_db_get_messages(self.h, node0, n, _p(up), _p(dn)))
         return up, dn
 
+    def messages_of(self, ids, col0: int = 0, n_cols: Optional[int] = None):
+        """(up, dn) of the listed nodes over columns [col0, col0 + n_cols): [len(ids), n_cols, 4], log domain."""
+        ids = np.ascontiguousarray(ids, dtype=np.int64)
+        n_cols = self.L - col0 if n_cols is None else n_cols
+        up = np.zeros((ids.size, n_cols, 4))
+        dn = np.zeros((ids.size, n_cols, 4))
+        check(_lib.load().hu_db_get_messages_of(self.h, ids.size, _p(ids), col0, n_cols, _p(up), _p(dn)))
+        return up, dn
+
     def seqs(self, node0: int = 0, n: Optional[int] = None) -> np.ndarray:
         n = self.n_nodes - node0 if n is None else n
         s = np.zeros((n, self.L), dtype=np.int8)
@@ -187,6 +196,8 @@ class Batch:
         self.n_seq = 0
         self.max_n_seed = 50
         self._keep = None
+        self._res = None       # page-locked result buffers of alignments()
+        self._best = None
 
     def close(self):
         if getattr(self, "h", None):
@@ -257,16 +268,25 @@ class Batch:
         check(_lib.load().hu_batch_sync(self.h))
 
     # ---- results ----
-    def alignments(self, with_traces: bool = True):
-        rows = np.zeros(self.n_seq, dtype=ALIGN_DT)
-        if not with_traces:
+    def alignments(self, with_traces=True):
+        """-> (rows, traces).  with_traces True: list of "B[MID]*E" strings; "packed": (uint8 buffer, int64 offsets) as the
+        library hands them back (NUL-terminated, back to back), in page-locked buffers owned by this workspace and reused by
+        the next call; False: None."""
+        if with_traces is False or with_traces is None:
+            rows = np.zeros(self.n_seq, dtype=ALIGN_DT)
             check(_lib.load().hu_batch_get_align(self.h, _p(rows), None, 0, None))
             return rows, None
-        cap = int(self.n_seq) * (self.max_len + self.db.K + 8)
-        buf = np.zeros(cap, dtype=np.uint8)
-        off = np.zeros(self.n_seq + 1, dtype=np.int64)
-        check(_lib.load().hu_batch_get_align(self.h, _p(rows), _p(buf), cap, _p(off)))
-        raw = buf.tobytes()
+        if self._res is None:
+            max_seq = self.max_reads * (2 if self.paired else 1)
+            cap = int(max_seq) * (self.max_len + self.db.K + 8)
+            self._res = (pinned_empty(max_seq, ALIGN_DT), pinned_empty(cap, np.uint8), pinned_empty(max_seq + 1, np.int64))
+        rows_p, buf, off = self._res
+        check(_lib.load().hu_batch_get_align(self.h, _p(rows_p), _p(buf), buf.size, _p(off)))
+        rows = rows_p[:self.n_seq]
+        if with_traces == "packed":
+            return rows, (buf, off[:self.n_seq + 1])
+        rows = rows.copy()
+        raw = buf[:int(off[self.n_seq])].tobytes()
         traces = [raw[off[i]:off[i] + rows["traceLen"][i]].decode() for i in range(self.n_seq)]
         return rows, traces
 
@@ -307,10 +327,24 @@ class Batch:
         check(_lib.load().hu_batch_get_places(self.h, _p(n), _p(rows)))
         return n, rows
 
-    def best(self) -> np.ndarray:
-        rows = np.zeros(self.n, dtype=PLACE_DT)
+    def best(self, pinned: bool = False) -> np.ndarray:
+        """bestPlace of every read.  pinned: into a page-locked buffer of this workspace (reused by the next call)."""
+        if pinned:
+            if self._best is None:
+                self._best = pinned_empty(self.max_reads, PLACE_DT)
+            rows = self._best[:self.n]
+        else:
+            rows = np.zeros(self.n, dtype=PLACE_DT)
         check(_lib.load().hu_batch_get_best(self.h, _p(rows)))
         return rows
+
+    def pack_rows(self, read0: int, dev_ptr: int):
+        """The driver's fixed-size assignment rows of this batch, written on the batch stream into device memory."""
+        check(_lib.load().hu_batch_pack_rows(self.h, int(read0), C.c_void_p(dev_ptr)))
+
+    @property
+    def stream(self) -> int:
+        return int(_lib.load().hu_batch_stream(self.h) or 0)
 
     def mark(self, i: int):
         check(_lib.load().hu_batch_mark(self.h, i))

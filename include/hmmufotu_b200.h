@@ -95,6 +95,8 @@ int hu_db_destroy(hu_db* db);
 /* read back device-resident pieces (tests, DB writer): n nodes starting at node0; any pointer may be NULL */
 int hu_db_get_messages(hu_db* db, int64_t node0, int64_t n, double* up, double* dn);
 int hu_db_get_seq(hu_db* db, int64_t node0, int64_t n, int8_t* seq);
+/* messages of the listed nodes over consensus columns [col0, col0 + nCols): [i][column][4], log domain */
+int hu_db_get_messages_of(hu_db* db, int64_t nIds, const int64_t* ids, int32_t col0, int32_t nCols, double* up, double* dn);
 int64_t hu_db_bytes(hu_db* db);
 
 /* BandedHMMP7::ViterbiAlignPath, src/BandedHMMP7.h:229-249 */
@@ -195,7 +197,9 @@ int hu_finalize_batch(hu_batch* b, const hu_sep_params* p);
 int hu_assign_batch(hu_batch* b, int mode, const hu_sep_params* p);
 int hu_batch_sync(hu_batch* b);
 
-/* device -> host results (each call synchronises the batch stream) */
+/* device -> host results (each call synchronises the batch stream).  hu_batch_get_align packs the traces on the device
+ * (start-to-end, NUL-terminated, back to back; traceOff[s] = offset of sequence s, traceOff[nSeq] = total bytes) and copies
+ * exactly those bytes; page-locked `rows` / `traces` buffers (hu_host_alloc) make the copies asynchronous DMA. */
 int hu_batch_get_align(hu_batch* b, hu_align_row* rows /* nSeq */, char* traces, int64_t traceCap, int64_t* traceOff /* nSeq+1 */);
 int hu_batch_get_merged(hu_batch* b, hu_align_row* rows /* nReads */);
 int hu_batch_get_aligned_codes(hu_batch* b, int8_t* codes /* nReads x csLen */);
@@ -203,6 +207,14 @@ int hu_batch_get_seeds(hu_batch* b, int32_t* nSeeds, int32_t* ids /* nReads x ma
 int hu_batch_get_estimates(hu_batch* b, int32_t* nKept, hu_place_row* rows /* nReads x maxNSeed, filter order */);
 int hu_batch_get_places(hu_batch* b, int32_t* nKept, hu_place_row* rows /* nReads x maxNSeed */);
 int hu_batch_get_best(hu_batch* b, hu_place_row* rows /* nReads */);
+
+/* The read-sharding driver's fixed-size assignment row (104 bytes: int64 read; int32 seqStart, seqEnd, hmmStart, hmmEnd,
+ * csStart, csEnd, flags, nPlaces; double cost; int32 cNode, pNode, aNode, taxon; double ratio, annoDist, loglik, qPlace,
+ * qTaxon) for every read of the batch, written by a kernel on the batch stream into DEVICE memory `devRows` (nReads rows):
+ * the gather of these rows over the ranks is the one collective of the path (ncclAllGather on device buffers). */
+int hu_batch_pack_rows(hu_batch* b, int64_t read0, void* devRows);
+/* the batch's cudaStream_t, for ordering a caller's collective after the batch's kernels */
+void* hu_batch_stream(hu_batch* b);
 
 /* diagnostics (tests): the key vector of one read after hu_seed_batch -- floor(d * 2^31 / N) per candidate, candidates =
  * the non-root nodes in id order that pass maxHeight (0xFFFFFFFF: undefined distance); nCand = their number */

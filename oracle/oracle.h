@@ -135,8 +135,12 @@ struct Tree {
 	DGamma dg;                          /* dg.K == 0 -> no discrete Gamma */
 	/* run options of src/hmmufotu.cpp:229-241: -m weighted, --prior height, --ML */
 	int estWeighted = 0, priorHeight = 0, onlyML = 0;
-	const double* U(long id) const { return &up[(size_t) id * csLen * 4]; }
-	const double* V(long id) const { return &dn[(size_t) id * csLen * 4]; }
+	/* sparse storage (bench.py's CPU baseline at gg_97 scale, where all 397 k messages are 98 GB): up/dn hold the rows of the
+	 * nodes with slotOf[id] >= 0 only; empty slotOf = dense */
+	std::vector<long> slotOf;
+	bool hasMsg(long id) const { return slotOf.empty() || slotOf[id] >= 0; }
+	const double* U(long id) const { return &up[(size_t) (slotOf.empty() ? id : slotOf[id]) * csLen * 4]; }
+	const double* V(long id) const { return &dn[(size_t) (slotOf.empty() ? id : slotOf[id]) * csLen * 4]; }
 	const int8_t* s(long id) const { return &seq[(size_t) id * csLen]; }
 	/* all-roots Felsenstein evaluation (src/hmmufotu-build.cpp:455-459,
 	 * src/PhyloTreeUnrooted.cpp:320-374): fills up/dn from leaf sequences */

@@ -248,6 +248,16 @@ void orc_tree_set_messages(void* op, const double* up, const double* dn) {
 	t.dn.assign(dn, dn + n);
 }
 
+/* messages of a subset of the nodes only (ids[i] -> row i of up / dn); every other node has none */
+void orc_tree_set_sparse_messages(void* op, long nSel, const long* ids, const double* up, const double* dn) {
+	Tree& t = ((OrcTree*) op)->t;
+	const size_t row = (size_t) t.csLen * 4;
+	t.slotOf.assign(t.nNodes, -1);
+	for (long i = 0; i < nSel; ++i) t.slotOf[ids[i]] = i;
+	t.up.assign(up, up + (size_t) nSel * row);
+	t.dn.assign(dn, dn + (size_t) nSel * row);
+}
+
 /* getSeed + truncation to maxN (src/HmmUFOtu_main.cpp:127-152, src/hmmufotu.cpp:646-647) */
 int orc_get_seed(void* op, const int8_t* seq, int start, int end, double maxDiff, double maxHeight, int seedOrder, int maxN,
 		long* ids, double* dist) {
@@ -334,45 +344,65 @@ void orc_equal_sort_perm(int n, int* out) {
 	for (int i = 0; i < n; ++i) out[i] = v[i].second;
 }
 
-/* The per-read body of the reference's task loop (src/hmmufotu.cpp:610-748) for a list of SE reads, one
- * std::thread per core pulling reads from a shared counter (the reference uses one OpenMP task per read).
- * The tree may hold a column slice [col0, col0 + csLen) of the consensus; aligned reads are cut to it.
- * seedOrder 0 = std::sort as in the reference.  out: one best-placement row per read; coords: 6 ints + cost. */
-int orc_run_reads(void* hp, void* op, int nReads, const char* reads, const long* offsets, const int* vpaths, const int* nPaths,
-		int col0, int maxNSeed, double maxError, int seedOrder, int useTrue, int nThreads, OrcPlaceRow* out, int* coords, double* cost) {
+/* The per-read body of the reference's task loop (src/hmmufotu.cpp:610-748) for a list of reads, one std::thread per core
+ * pulling reads from a shared counter (the reference uses one OpenMP task per read).  paired != 0: sequences nReads..2 nReads-1
+ * are the already reverse-complemented mates (:609); orientation test and merge as :629-639 (a failed test = chimera: the
+ * read is not placed, out[r].c = -3).  The tree may hold a column slice [col0, col0 + csLen) of the consensus; aligned reads
+ * are cut to it.  seedOrder 0 = std::sort as in the reference.  out: one best-placement row per read (c = -1: invalid
+ * alignment, -2: a seed's messages are not in a sparse tree); coords: 6 ints + cost; nearTie (may be NULL): 1 when two kept
+ * estimated log-likelihoods agree to 1e-11 relative, i.e. their order -- hence, under SURVEY.md F6, the reported placement --
+ * is decided by rounding noise. */
+int orc_run_reads(void* hp, void* op, int nReads, int paired, const char* reads, const long* offsets, const int* vpaths, const int* nPaths,
+		int col0, int maxNSeed, double maxError, int seedOrder, int useTrue, int nThreads, OrcPlaceRow* out, int* coords, double* cost,
+		int* nearTie) {
 	Hmm* h = (Hmm*) hp;
 	Tree& t = ((OrcTree*) op)->t;
 	std::atomic<int> next(0), bad(0);
+	auto alignOne = [&](int s) {
+		std::vector<VPath> paths(nPaths[s]);
+		for (int i = 0; i < nPaths[s]; ++i) {
+			const int* v = vpaths + ((size_t) s * 2 + i) * 6;
+			VPath p = {v[0], v[1], v[2], v[3], v[4], v[5]};
+			paths[i] = p;
+		}
+		return alignWithPaths(*h, std::string(reads + offsets[s], offsets[s + 1] - offsets[s]), paths);
+	};
 	auto work = [&]() {
 		for (;;) {
 			const int r = next.fetch_add(1);
 			if (r >= nReads) return;
-			std::vector<VPath> paths(nPaths[r]);
-			for (int i = 0; i < nPaths[r]; ++i) {
-				const int* v = vpaths + ((size_t) r * 2 + i) * 6;
-				VPath p = {v[0], v[1], v[2], v[3], v[4], v[5]};
-				paths[i] = p;
+			if (nearTie) nearTie[r] = 0;
+			HmmAlignment a = alignOne(r);
+			bool chimera = false;
+			if (paired) {
+				HmmAlignment b = alignOne(nReads + r);
+				if (!a.isValid() || !b.isValid() || !(a.csStart <= b.csStart && a.csEnd <= b.csEnd)) chimera = true;
+				else a.merge(b);
 			}
-			HmmAlignment a = alignWithPaths(*h, std::string(reads + offsets[r], offsets[r + 1] - offsets[r]), paths);
 			if (coords) {
 				int* c = coords + (size_t) r * 6;
 				c[0] = a.seqStart; c[1] = a.seqEnd; c[2] = a.hmmStart; c[3] = a.hmmEnd; c[4] = a.csStart; c[5] = a.csEnd;
 			}
 			if (cost) cost[r] = a.cost;
+			if (chimera) { memset(&out[r], 0, sizeof(OrcPlaceRow)); out[r].c = -3; continue; }
 			std::vector<int8_t> seq = digitalSeq(a.align);
 			const int s = a.csStart - 1 - col0, e = a.csEnd - 1 - col0;
 			if (!a.isValid() || s < 0 || e >= t.csLen) { bad++; memset(&out[r], 0, sizeof(OrcPlaceRow)); out[r].c = -1; continue; }
 			const int8_t* sq = seq.data() + col0;
 			std::vector<PTLoc> seeds = getSeed(t, sq, s, e, INF, INF, seedOrder);
 			if ((int) seeds.size() > maxNSeed) seeds.resize(maxNSeed);
+			bool missing = false;
+			for (size_t i = 0; i < seeds.size(); ++i) missing |= !t.hasMsg(seeds[i].id);
+			if (missing) { bad++; memset(&out[r], 0, sizeof(OrcPlaceRow)); out[r].c = -2; continue; }
 			std::vector<Placement> places;
 			for (size_t i = 0; i < seeds.size(); ++i) places.push_back(estimateSeq(t, sq, seeds[i]));
 			filterPlacements(places, maxError);
+			if (nearTie)
+				for (size_t i = 0; i + 1 < places.size(); ++i)
+					if (std::fabs(places[i].loglik - places[i + 1].loglik) <= 1e-11 * std::fabs(places[i].loglik)) nearTie[r] = 1;
 			for (size_t i = 0; i < places.size(); ++i) {
-				const double est = places[i].loglik;
 				placeSeq(t, sq, places[i], INF);
 				if (useTrue) places[i].loglik = places[i].loglikTrue;
-				places[i].qTaxon = est; /* carried through calcQValues? no: overwritten; kept only for debugging */
 			}
 			calcQValues(t, places);
 			sortByQPlace(places);

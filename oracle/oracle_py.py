@@ -72,7 +72,8 @@ def lib() -> C.CDLL:
         L.orc_equal_sort_perm.argtypes = [i32, vp]
         L.orc_tree_set_options.argtypes = [vp, i32, i32, i32]
         L.orc_tree_evaluate_mt.argtypes = [vp, i32, i32]
-        L.orc_run_reads.argtypes = [vp, vp, i32, C.c_char_p, vp, vp, vp, i32, i32, f64, i32, i32, i32, P(PlaceRow), vp, vp]
+        L.orc_run_reads.argtypes = [vp, vp, i32, i32, C.c_char_p, vp, vp, vp, i32, i32, f64, i32, i32, i32, P(PlaceRow), vp, vp, vp]
+        L.orc_tree_set_sparse_messages.argtypes = [vp, i64, vp, vp, vp]
         L.orc_stdsort_desc_perm.argtypes = [vp, i32, vp]
         L.orc_stdsort_keys.argtypes = [vp, i32, i32, vp]
         L.orc_sort_killer.argtypes = [i32, vp]
@@ -201,6 +202,12 @@ class OracleTree:
             lib().orc_tree_free(self.h)
             self.h = None
 
+    def set_sparse_messages(self, ids: np.ndarray, up: np.ndarray, dn: np.ndarray):
+        """Messages of the nodes `ids` only (row i of up / dn belongs to ids[i]); the other nodes have none."""
+        ids = np.ascontiguousarray(ids, dtype=np.int64)
+        up = np.ascontiguousarray(up, dtype=np.float64); dn = np.ascontiguousarray(dn, dtype=np.float64)
+        lib().orc_tree_set_sparse_messages(self.h, ids.size, _p(ids), _p(up), _p(dn))
+
     def set_options(self, weighted: bool = False, prior_height: bool = False, only_ml: bool = False):
         """-m weighted / --prior height / --ML of the reference's hmmufotu (src/hmmufotu.cpp:229-241)"""
         lib().orc_tree_set_options(self.h, int(weighted), int(prior_height), int(only_ml))
@@ -249,20 +256,26 @@ class OracleTree:
 
 
 def run_reads(hmm: "OracleHmm", tree: "OracleTree", reads, col0: int = 0, max_n_seed: int = 50, max_error: float = 20.0,
-              seed_order: int = 0, use_true: bool = False, threads: int = 1):
-    """The reference's per-read task body for a ReadSet on `threads` host threads.
-    -> (rows: list[PlaceRow], coords int32 [n, 6], cost f64 [n], n_bad)"""
+              seed_order: int = 0, use_true: bool = False, threads: int = 1, mates=None, with_ties: bool = False):
+    """The reference's per-read task body for a ReadSet (and its mates, already reverse-complemented) on `threads` host
+    threads.  -> (rows: list[PlaceRow], coords int32 [n, 6], cost f64 [n], n_bad[, near_tie int32 [n]])"""
     n = reads.n
-    text = "".join("ACGT"[c] for c in reads.codes).encode()
+    sets = (reads,) if mates is None else (reads, mates)
+    text = "".join("".join("ACGT"[c] for c in x.codes) for x in sets).encode()
     offsets = np.ascontiguousarray(reads.offsets, dtype=np.int64)
     vp = np.ascontiguousarray(reads.vpaths, dtype=np.int32)
     npth = np.ascontiguousarray(reads.n_paths, dtype=np.int32)
+    if mates is not None:
+        offsets = np.concatenate([offsets, mates.offsets[1:].astype(np.int64) + offsets[-1]])
+        vp = np.ascontiguousarray(np.concatenate([vp, mates.vpaths.astype(np.int32)]))
+        npth = np.ascontiguousarray(np.concatenate([npth, mates.n_paths.astype(np.int32)]))
     rows = (PlaceRow * n)()
     coords = np.zeros((n, 6), dtype=np.int32)
     cost = np.zeros(n)
-    bad = lib().orc_run_reads(hmm.h, tree.h, n, text, _p(offsets), _p(vp), _p(npth), col0, max_n_seed, max_error,
-                              seed_order, int(use_true), threads, rows, _p(coords), _p(cost))
-    return rows, coords, cost, bad
+    ties = np.zeros(n, dtype=np.int32)
+    bad = lib().orc_run_reads(hmm.h, tree.h, n, int(mates is not None), text, _p(offsets), _p(vp), _p(npth), col0, max_n_seed, max_error,
+                              seed_order, int(use_true), threads, rows, _p(coords), _p(cost), _p(ties))
+    return (rows, coords, cost, bad, ties) if with_ties else (rows, coords, cost, bad)
 
 
 def equal_sort_perm(n: int) -> np.ndarray:

@@ -17,6 +17,8 @@ Writes tests/golden/ref70/:
                                               negative and missing branch lengths, partly canonical taxonomy, lower case, N,
                                               nothing to prune): what tests/test_host.py compares the host half of the builder with
   se0.{weighted,ml,height,single}.tsv         se0 again with -m weighted / --ML / --prior height / --single (NGCL alignment mode)
+  gg_70_otus_GTR_dG.ptu.gz, _se0, _pe0        (round 2, extra()) BASELINE.json configs[1]: GTR + dGamma4 database, SE and 2 x 150 PE reads;
+                                              variant TSVs for both discrete-Gamma databases
 Every file holds at most 64 reads: up to 64 OpenMP tasks are deferred and then run in creation order, so the
 reference consumes rand() (CSFM seed picks) in file order, as the batched driver does.
 """
@@ -63,6 +65,7 @@ def main():
         run(os.path.join(REF, "hmmufotu-sim"), db, tag + "_1.fasta", tag + "_2.fasta", "-N", "64", "-S", "7", "-r", "150")
         run(os.path.join(REF, "hmmufotu"), db, tag + "_1.fasta", tag + "_2.fasta", "-o", tag + ".tsv", "-s", "1", "-S", "7", "-p", "1")
         os.remove(db + ".ptu")
+    extra()
     import random
     random.seed(5)
     seqs = [l.strip() for l in open("gg_70_otus_GTR_se1.fasta") if not l.startswith(">")]
@@ -94,5 +97,41 @@ def main():
         print("%10d  %s" % (os.path.getsize(f), f))
 
 
+def extra():
+    """Round 2: BASELINE.json configs[1]'s database -- 70_otus with GTR + dGamma4 (-s GTR -V -k 4) -- with 2 x 150 bp PE reads
+    and 250 bp SE reads, and the run-option variants (-m weighted, --ML, --prior height, --single) for BOTH discrete-Gamma
+    databases.  <db>.msa / .csfm do not depend on the model and <db>.hmm only in its DATE line, so gg_70_otus_GTR_dG keeps
+    its .ptu.gz only and the tests pair it with gg_70_otus_GTR's other three files."""
+    os.chdir(OUT)
+    db = "gg_70_otus_GTR_dG"
+    run(os.path.join(REF, "hmmufotu-build"), os.path.join(SRC, "70_otus.fasta"), os.path.join(SRC, "70_otus.tree"),
+        "-a", os.path.join(SRC, "70_otus_taxonomy.txt"), "-n", db, "-s", "GTR", "-V", "-k", "4")
+    strip = lambda path: [ln for ln in open(path).read().split("\n") if not ln.startswith("DATE") and not ln.startswith("NAME")]
+    assert open(db + ".csfm", "rb").read() == open("gg_70_otus_GTR.csfm", "rb").read()
+    assert strip(db + ".hmm") == strip("gg_70_otus_GTR.hmm")
+    for tag, k, args in (("se0", 0, ["-r", "250"]),):
+        run(os.path.join(REF, "hmmufotu-sim"), db, "%s_%s.fasta" % (db, tag), "-N", "64", "-S", str(k), *args)
+        run(os.path.join(REF, "hmmufotu"), db, "%s_%s.fasta" % (db, tag), "-o", "%s_%s.tsv" % (db, tag), "-s", "1", "-S", str(k), "-p", "1")
+    tag = "%s_pe0" % db
+    run(os.path.join(REF, "hmmufotu-sim"), db, tag + "_1.fasta", tag + "_2.fasta", "-N", "64", "-S", "7", "-r", "150")
+    run(os.path.join(REF, "hmmufotu"), db, tag + "_1.fasta", tag + "_2.fasta", "-o", tag + ".tsv", "-s", "1", "-S", "7", "-p", "1")
+    with open(db + ".ptu", "rb") as f, gzip.GzipFile(db + ".ptu.gz", "wb", compresslevel=9, mtime=0) as g:
+        shutil.copyfileobj(f, g)
+    for d in (db, "gg_70_otus_HKY85_dG"):
+        if not os.path.exists(d + ".ptu"):
+            with gzip.open(d + ".ptu.gz", "rb") as f, open(d + ".ptu", "wb") as o:
+                shutil.copyfileobj(f, o)
+        tag = "%s_se0" % d
+        for name, opts in (("weighted", ["-m", "weighted"]), ("ml", ["--ML"]), ("height", ["--prior", "height"]), ("single", ["--single"])):
+            run(os.path.join(REF, "hmmufotu"), d, tag + ".fasta", "-o", "%s.%s.tsv" % (tag, name), "-s", "1", "-S", "0", "-p", "1", *opts)
+        os.remove(d + ".ptu")
+    for ext in (".msa", ".csfm", ".hmm"):
+        os.remove(db + ext)
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "--extra":
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "-f", "Makefile.ref", "-j8", "-s"])
+        extra()
+    else:
+        main()

@@ -133,8 +133,8 @@ def test_option_filters():
     ns, ids, dist = b.seeds(with_dist=True)
     nk, est = b.estimates()
     for i in range(rs.n):
-        # with a height filter the device uses the (dist, id) order: compare with the oracle's stable order
-        oid, odist = otree.get_seed(codes[i], start[i], end[i], 12, max_height=hmax, order=1)
+        # getSeed filters by height first and std::sorts what is left (src/HmmUFOtu_main.cpp:131-139): literal order on the compacted vector
+        oid, odist = otree.get_seed(codes[i], start[i], end[i], 12, max_height=hmax, order=0)
         assert np.array_equal(ids[i, :ns[i]], oid) and np.array_equal(dist[i, :ns[i]], odist)
         assert (db.height[oid] <= hmax).all()
         rows = otree.assign(codes[i], start[i], end[i], oid, odist, max_error=3.0, max_height=hmax)
@@ -201,4 +201,65 @@ def test_literal_seed_order_on_a_larger_tree():
             sid, _ = otree.get_seed(codes[i], start[i], end[i], max_n, order=1)
             n_tie_cut += set(sid) != set(oid)
     assert n_tie_cut > 0   # tie groups cut by the truncation: std::sort and (dist, id) keep different members
+    b.close(); gdb.close()
+
+
+def test_long_reads_hky85_dgamma_wide_kernels():
+    """BASELINE.json configs[4]'s shape on a mid-size tree: HKY85 + dGamma4, near-full-length reads over a 7 682-column
+    consensus, windows of ~7 000 columns -- the warp-per-item estimate kernel (estimateWideKernel) and K4's global-memory
+    rho slab -- against the oracle, whole pipeline from the reads."""
+    from hmmufotu_b200 import engine
+    db, otree, gdb = _setup(engine, n_leaves=160, cs_len=7682, occupancy=0.18, seed=20260105, model=synth.gg97_model(synth.HKY85), dg_alpha=0.5)
+    rs = synth.make_reads(db, 12, read_len=1400, len_sd=50.0, seed=4, window=(0, 300))
+    ohmm = O.OracleHmm(db)
+    max_len = int(np.max(np.diff(rs.offsets))) + 8
+    b = engine.Batch(gdb, rs.n, max_len)
+    b.upload(rs)
+    b.assign(engine.SepParams())
+    rows, traces = b.alignments()
+    ns, ids, dist = b.seeds(with_dist=True)
+    nk, est = b.estimates()
+    _, pl = b.places()
+    best = b.best()
+    widths = []
+    for i in range(rs.n):
+        o = ohmm.align(rs.read_str(i), rs.vpaths[i, :rs.n_paths[i]])
+        assert rows[i]["cost"] == o["cost"] and traces[i] == o["trace"], i
+        seq = O.digitize(o["align"])
+        s, e = o["coords"][4] - 1, o["coords"][5] - 1
+        widths.append(e - s + 1)
+        _check_read(otree, seq, s, e, ns[i], ids[i], dist[i], nk[i], est[i], pl[i], best[i])
+    assert min(widths) > 5000
+    b.close(); gdb.close()
+
+
+def test_paired_end_gtr_dgamma_merged_windows():
+    """BASELINE.json configs[1] / [3]'s shape: GTR + dGamma4, 2 x 250 bp pairs with overlapping mates, merged windows wider
+    than a single read's (the big-window configuration of the staged estimate kernel), whole pipeline against the oracle."""
+    from hmmufotu_b200 import engine, _lib
+    db, otree, gdb = _setup(engine, n_leaves=120, cs_len=3200, occupancy=0.3, seed=20260104, model=synth.gg97_model(synth.GTR), dg_alpha=0.5)
+    fwd, rev = synth.make_pairs(db, 24, read_len=250, insert_len=420, insert_sd=20.0, seed=6)
+    ohmm = O.OracleHmm(db)
+    b = engine.Batch(gdb, fwd.n, 260, paired=True)
+    b.upload(fwd, rev)
+    b.assign(engine.SepParams())
+    merged = b.merged()
+    ns, ids, dist = b.seeds(with_dist=True)
+    nk, est = b.estimates()
+    _, pl = b.places()
+    best = b.best()
+    widths = []
+    for i in range(fwd.n):
+        a = ohmm.align(fwd.read_str(i), fwd.vpaths[i, :fwd.n_paths[i]])
+        m = ohmm.align(rev.read_str(i), rev.vpaths[i, :rev.n_paths[i]])
+        if not (a["coords"][4] <= m["coords"][4] and a["coords"][5] <= m["coords"][5]):
+            assert merged[i]["flags"] & _lib.ALIGN_CHIMERA
+            continue
+        mm = O.merge(db.cs_len, a, m)
+        assert merged[i]["cost"] == mm["cost"]
+        seq = O.digitize(mm["align"])
+        s, e = mm["coords"][4] - 1, mm["coords"][5] - 1
+        widths.append(e - s + 1)
+        _check_read(otree, seq, s, e, ns[i], ids[i], dist[i], nk[i], est[i], pl[i], best[i])
+    assert len(widths) > fwd.n // 2 and max(widths) > 1200
     b.close(); gdb.close()

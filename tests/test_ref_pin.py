@@ -27,18 +27,24 @@ def revcom(s):
     return "".join(COMP.get(c, c) for c in reversed(s))
 
 
-@pytest.fixture(scope="module", params=["gg_70_otus_GTR", "gg_70_otus_HKY85_dG"])
+# <db>.msa / .csfm do not depend on the substitution model and <db>.hmm only in its DATE line: the GTR + dGamma4 database
+# (BASELINE.json configs[1]) is committed as its .ptu.gz alone and paired with gg_70_otus_GTR's other files
+SHARED = {"gg_70_otus_GTR_dG": "gg_70_otus_GTR"}
+
+
+@pytest.fixture(scope="module", params=["gg_70_otus_GTR", "gg_70_otus_HKY85_dG", "gg_70_otus_GTR_dG"])
 def refcase(request, tmp_path_factory):
     name = request.param
     d = tmp_path_factory.mktemp(name)
+    src = SHARED.get(name, name)
     for ext in (".msa", ".hmm"):
-        shutil.copy(os.path.join(GOLD, name + ext), d / (name + ext))
+        shutil.copy(os.path.join(GOLD, src + ext), d / (name + ext))
     db = refdb.load_ptu(os.path.join(GOLD, name + ".ptu.gz"))
     otree = O.OracleTree(db, evaluate=False)
     up, dn = np.ascontiguousarray(db.up), np.ascontiguousarray(db.dn)
     O.lib().orc_tree_set_messages(otree.h, up.ctypes.data_as(O.C.c_void_p), dn.ctypes.data_as(O.C.c_void_p))
-    ohmm = O.OracleHmm(path=os.path.join(GOLD, name + ".hmm"))
-    return dict(name=name, dir=str(d), db=db, otree=otree, ohmm=ohmm)
+    ohmm = O.OracleHmm(path=os.path.join(GOLD, src + ".hmm"))
+    return dict(name=name, dir=str(d), db=db, otree=otree, ohmm=ohmm, hmm_path=os.path.join(GOLD, src + ".hmm"))
 
 
 def seeds_of(case, fasta, seed, mate=None, single=False):
@@ -109,6 +115,8 @@ def test_single_end_rows_match_the_reference(refcase):
         total += n
         print("%s se%d: %d rows identical, %d with rounding-tied estimates" % (name, k, n, t))
     assert total >= 57
+    if name == "gg_70_otus_GTR_dG":
+        assert len(refcase["db"].dg_rates) == 4 and refcase["db"].model["type"] == refdb.MODEL_TYPES["GTR"]
 
 
 def test_paired_end_rows_match_the_reference(refcase):
@@ -132,11 +140,11 @@ def test_single_mode_matches_the_reference(refcase):
     name = refcase["name"]
     tsv = os.path.join(GOLD, "%s_se0.single.tsv" % name)
     if not os.path.exists(tsv):
-        pytest.skip("variant goldens exist for the GTR database only")
+        pytest.fail("missing golden " + tsv)
     fa = os.path.join(GOLD, name + "_se0.fasta")
     reads = refdb.read_fasta(fa)
     vps = seeds_of(refcase, fa, 0, single=True)
-    ohmm = O.OracleHmm(path=os.path.join(GOLD, name + ".hmm"), mode=O.NGCL)
+    ohmm = O.OracleHmm(path=refcase["hmm_path"], mode=O.NGCL)
     aligns = {rid: ohmm.align(seq.upper(), vps[i]) for i, (rid, _, seq) in enumerate(reads)}
     n, t = check_rows(refcase, tsv, aligns)
     assert n + t == len(reads) and n >= 0.9 * len(reads)
@@ -178,7 +186,7 @@ def test_run_options_match_the_reference(refcase, variant):
     name = refcase["name"]
     tsv = os.path.join(GOLD, "%s_se0.%s.tsv" % (name, variant))
     if not os.path.exists(tsv):
-        pytest.skip("variant goldens exist for the GTR database only")
+        pytest.fail("missing golden " + tsv)
     fa = os.path.join(GOLD, name + "_se0.fasta")
     reads = refdb.read_fasta(fa)
     vps = seeds_of(refcase, fa, 0)
