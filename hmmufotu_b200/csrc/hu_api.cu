@@ -189,6 +189,7 @@ int hu_batch_create(hu_batch** out, hu_db* db, int32_t maxReads, int32_t maxSeqL
 	b->nReads = b->nSeq = 0; b->launches = 0;
 	b->dPtrs = NULL; b->ptrsCap = 0; b->placeSlab = NULL; b->litIds = NULL;
 	b->posOfSlotH = b->nodeOfPosH = NULL; b->nCandH = 0; b->heightCached = 0;
+	b->estSlab = NULL; b->estSlabCtas = 0;
 	*out = b;
 	HU_CUDA(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
 	for (int i = 0; i < 16; ++i) HU_CUDA(cudaEventCreate(&b->ev[i]));

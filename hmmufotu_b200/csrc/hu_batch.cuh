@@ -68,7 +68,7 @@ struct EstItem {
 	int rs;       // read * HU_MAX_SEED + seed slot
 	int u, v;     // seed node and its parent
 	int start, W; // window
-	int kind;     // 0: nothing to do (also the end-of-stream mark), 1: staged kernel, 2: wide-window kernel
+	int kind;     // 0: nothing to do (also the end-of-stream mark), 1: an item
 	double w0;    // branch length of (u, v)
 };
 
@@ -76,8 +76,7 @@ struct EstItemP {
 	double cDist, ratio; // pDist(child seq, read); attachment ratio cDist / (cDist + pDist)
 	double sumScale;     // sum over the window of the per-column scales of both messages
 	int taxU, taxV;      // taxon ids of the child and the parent node (the row's taxon is one of them)
-	double P[2][2][16];  // [m][h]: P(w0 ratio) (m = 0) and P(w0 (1 - ratio)) (m = 1); h = 1: the same matrix with its
-	                     // column pairs (0,1) and (2,3) exchanged, for the threads that read a message column half-swapped
+	double P[2][16];     // P(w0 ratio) and P(w0 (1 - ratio)), row-major
 };
 
 } // namespace hu
@@ -125,6 +124,8 @@ struct hu_batch {
 	int nCandH;
 	double heightCached;
 	double* placeSlab;     // global rho slabs for windows wider than the shared-memory capacity
+	void* estSlab;         // K3: per-CTA g slabs for windows wider than its shared-memory buffer
+	int estSlabCtas;
 	long long h2dBytes;
 	// stats
 	hu_batch_stats stats;

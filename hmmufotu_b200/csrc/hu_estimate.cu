@@ -2,32 +2,38 @@
 // (src/PhyloTreeUnrooted.cpp:849-877) followed by filterPlacements (src/HmmUFOtu_main.cpp:162-173).
 //
 // HBM-bound: an item streams the two message windows of its seed edge (linear form, 32 B per column each,
-// hu_internal.cuh) exactly once.  estimateStagedKernel is a persistent producer/consumer pipeline, two CTAs per
-// SM: one producer lane walks the item list and issues cp.async.bulk copies (hu_pipe.cuh) of 256-column chunks
-// of U and V into a 3-stage shared-memory ring, plus the three byte windows (read, child, parent sequence) of
-// the NEXT item; eight consumer warps take one column per thread and chunk.  Per column
+// hu_internal.cuh) exactly once.  estimateStagedKernel is a persistent producer/consumer pipeline, three CTAs per
+// SM: one producer lane walks the item list and issues cp.async.bulk copies (hu_pipe.cuh) of 128-column chunks
+// of U and V into a 3-stage shared-memory ring, plus the read's window and the item record of the NEXT item; four
+// consumer warps take one column per thread and chunk.  Per column
 //   g_j = (P(wur) E^U_j) * (P(wvr) E^V_j)              (= e^{R_j} of the reference up to the column scale)
 // pass 1 counts the columns whose arg-max state differs from the read's (wnr, cpp:1018-1032) and parks g_j in
 // shared memory; pass 2 sums log(pi . (g_j * P(wnr) n_j)) from there (cpp:872-874).  The per-column scales enter
 // only through their sum over the window, taken from 32-column prefix sums (TreeDev::upP32) plus the two ragged
-// ends.  64 fused multiply-adds and one log per column, no exp.  Windows wider than the shared-memory budget
-// (HU_EST_CAPW columns) go to estimateWideKernel, one warp per item, which reads the window twice.
+// ends.  36 fp64 operations and 4 shared-memory reads per column in pass 1, no exp.
+//
+// Round-2 shape (profiles/r1d_summary.md found the round-1 kernel bound by shared-memory wavefronts: every thread re-read
+// the item's two 4x4 transition matrices, 256 B, for every column next to the 64 B of message data): the matrices live in
+// REGISTERS for the whole item (64 registers; hence fewer threads per CTA and more CTAs per SM), g_j is kept as two 16-byte
+// halves (128-bit stores / loads), pi is folded into P(wnr) n.  Windows wider than the shared-memory g buffer keep g in a
+// per-CTA slab in global memory (L2-resident) and read the read's window from global memory: any width is streamed from
+// HBM once, and there is no separate wide-window kernel any more.
 #include "hu_batch.cuh"
 #include "hu_pipe.cuh"
 #include "hu_stdsort.cuh"
 
 namespace hu {
 
-#define HU_EST_CONS 256                  // consumer threads (8 warps), one column of a chunk each
+#define HU_EST_CONS 128                   // consumer threads (4 warps), one column of a chunk each
 #define HU_EST_THREADS (HU_EST_CONS + 32) // + the producer warp
-#define HU_EST_CH 256                    // columns per ring stage
+#define HU_EST_CH 128                     // columns per ring stage
 #define HU_EST_STAGES 3
-#define HU_EST_CAPW 1536                 // widest window the staged kernel takes with two CTAs per SM (single-end amplicon reads)
-#define HU_EST_CAPW_BIG 3328             // ... with one CTA per SM (merged paired-end windows)
-#define HU_EST_WARPS 8                   // warps per CTA of the wide-window kernel
+#define HU_EST_CAPW 1408                  // g buffer (columns) with three CTAs per SM: single-end amplicon reads
+#define HU_EST_CAPW_BIG 2560              // ... with two CTAs per SM: merged paired-end windows
 
 struct EstArgs {
-	int nReads, maxNSeed, weighted, capW; // weighted: estimateBranchLengthWeighted instead of ...Unweighted; capW: widest staged window
+	int nReads, maxNSeed, weighted, capW; // weighted: estimateBranchLengthWeighted instead of ...Unweighted; capW: widest window whose g fits shared memory
+	int csLen, pad;
 	const int8_t* aligned;
 	const int* winStart;
 	const int* winEnd;
@@ -36,8 +42,7 @@ struct EstArgs {
 	hu_place_row* est;
 	EstItem* items;   // [nReads * maxNSeed]
 	EstItemP* itemsP; // [nReads * maxNSeed]: distances, ratio and the two transition matrices of an item
-	int* wideCount;   // [0] number of wide items, [1] cursor of the wide kernel
-	int* wideList;
+	double2* slab;    // [grid][2][csLen]: g of windows wider than capW
 };
 
 // DNASubModel::Pr(v) by a half warp: `l` = 0..15 is this lane's matrix entry (row l / 4, column l % 4).  GTR
@@ -60,7 +65,19 @@ __device__ __forceinline__ void modelPrHalfWarp(const Model& m, double v, double
 // ---- item list: one record per (read, seed), so that the streaming kernel has no dependent loads and no
 // per-item serial prologue.  One warp per item: the p-distances of the read to the child and parent sequences
 // (SeqUtils::pDist over the window), the attachment ratio and the two transition matrices P(wur), P(wvr). ----
-__global__ void __launch_bounds__(256) estPlanKernel(EstArgs a, TreeDev t, Model m) {
+__device__ __forceinline__ unsigned int pdistWord(uint32_t xw, uint32_t sw, uint32_t keep) {
+	// four bases per word: both valid (code >= 0, i.e. sign bit clear) -> N += 1 (high half), differ -> d += 1 (low half)
+	unsigned int acc = 0;
+#pragma unroll
+	for (int k = 0; k < 4; ++k) {
+		const uint32_t xb = (xw >> (8 * k)) & 0xffu, sb = (sw >> (8 * k)) & 0xffu;
+		const bool ok = ((keep >> (8 * k)) & 1u) && !((xb | sb) & 0x80u);
+		if (ok) acc += 0x10000u + (xb != sb);
+	}
+	return acc;
+}
+
+__global__ void __launch_bounds__(256, 4) estPlanKernel(EstArgs a, TreeDev t, Model m) {
 	const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
 	const int lane = threadIdx.x & 31;
 	if (i >= a.nReads * a.maxNSeed) return;
@@ -71,19 +88,39 @@ __global__ void __launch_bounds__(256) estPlanKernel(EstArgs a, TreeDev t, Model
 	if (ws >= 0 && s < a.nSeeds[r]) {
 		const int u = a.seedIds[(size_t) r * HU_MAX_SEED + s];
 		it.u = u; it.v = t.parent[u]; it.start = ws; it.W = a.winEnd[r] - ws + 1; it.w0 = t.blen[u];
-		it.kind = it.W <= a.capW ? 1 : 2;
+		it.kind = 1;
+		// the three byte windows are read as aligned 32-bit words (4 columns per lane and load); the rows start at multiples
+		// of csLen, so the three rows share their alignment remainder only when csLen % 4 == 0 -- each gets its own shift
 		const int8_t* x = a.aligned + (size_t) r * t.csLen + ws;
 		const int8_t* su = t.seq + (size_t) it.u * t.csLen + ws;
 		const int8_t* sv = t.seq + (size_t) it.v * t.csLen + ws;
 		unsigned int cu = 0, cv = 0; // (N << 16) | d
-		for (int c = lane; c < it.W; c += 32) {
-			const int b = x[c];
-			if (b >= 0) {
-				const int bu = su[c], bv = sv[c];
-				if (bu >= 0) cu += 0x10000u + (bu != b);
-				if (bv >= 0) cv += 0x10000u + (bv != b);
+		if ((((uintptr_t) x ^ (uintptr_t) su) & 3) == 0 && (((uintptr_t) x ^ (uintptr_t) sv) & 3) == 0) {
+			const int off = (int) ((uintptr_t) x & 3);
+			const uint32_t* xw = reinterpret_cast<const uint32_t*>(x - off);
+			const uint32_t* uw = reinterpret_cast<const uint32_t*>(su - off);
+			const uint32_t* vw = reinterpret_cast<const uint32_t*>(sv - off);
+			const int nWords = (off + it.W + 3) >> 2;
+			for (int w = lane; w < nWords; w += 32) {
+				uint32_t keep = 0x01010101u; // byte k of the word is column 4 w + k - off: inside [0, W)?
+				const int c0 = 4 * w - off;
+				if (c0 < 0 || c0 + 3 >= it.W) {
+					keep = 0;
+					for (int k = 0; k < 4; ++k) if (c0 + k >= 0 && c0 + k < it.W) keep |= 1u << (8 * k);
+				}
+				const uint32_t xv = __ldg(xw + w);
+				cu += pdistWord(xv, __ldg(uw + w), keep);
+				cv += pdistWord(xv, __ldg(vw + w), keep);
 			}
-		}
+		} else
+			for (int c = lane; c < it.W; c += 32) {
+				const int b = x[c];
+				if (b >= 0) {
+					const int bu = su[c], bv = sv[c];
+					if (bu >= 0) cu += 0x10000u + (bu != b);
+					if (bv >= 0) cv += 0x10000u + (bv != b);
+				}
+			}
 		for (int o = 16; o > 0; o >>= 1) {
 			cu += __shfl_xor_sync(0xffffffffu, cu, o);
 			cv += __shfl_xor_sync(0xffffffffu, cv, o);
@@ -94,9 +131,7 @@ __global__ void __launch_bounds__(256) estPlanKernel(EstArgs a, TreeDev t, Model
 		if (isnan(ratio)) ratio = 0.5;
 		const double wur = it.w0 * ratio, wvr = it.w0 - wur;
 		EstItemP& ip = a.itemsP[i];
-		modelPrHalfWarp(m, lane < 16 ? wur : wvr, ip.P[lane >> 4][0], lane & 15, 0xffffffffu);
-		__syncwarp();
-		ip.P[lane >> 4][1][lane & 15] = ip.P[lane >> 4][0][(lane & 15) ^ 2]; // entry (i, j) <- (i, j ^ 2)
+		modelPrHalfWarp(m, lane < 16 ? wur : wvr, ip.P[lane >> 4], lane & 15, 0xffffffffu);
 		// everything else the streaming kernel would have to fetch from global memory
 		double sc = windowScale(t.upS, t.upP32, it.u, t.csLen, t.nWords, ws, ws + it.W - 1, lane)
 		          + windowScale(t.dnS, t.dnP32, it.u, t.csLen, t.nWords, ws, ws + it.W - 1, lane);
@@ -104,7 +139,6 @@ __global__ void __launch_bounds__(256) estPlanKernel(EstArgs a, TreeDev t, Model
 		if (lane == 0) {
 			ip.cDist = cDist; ip.ratio = ratio; ip.sumScale = sc;
 			ip.taxU = t.taxon[it.u]; ip.taxV = t.taxon[it.v];
-			if (it.kind == 2) a.wideList[atomicAdd(a.wideCount, 1)] = i;
 		}
 	}
 	if (lane == 0) a.items[i] = it;
@@ -124,22 +158,23 @@ struct EstSmem {
 	EstItem meta[2];
 	int hoff[4];                                  // [0..1]: offset of the window inside hdr (alignment remainder); rest: padding
 	double P2[16];                                // P(wnr)
-	double Np[5][4];                              // P(wnr) applied to the read's leaf vector, per base / gap
+	double NpPi[5][4];                            // pi * (P(wnr) applied to the read's leaf vector), per base / gap
 	unsigned int redB[HU_EST_CONS / 32];
 	double redC[HU_EST_CONS / 32];
 	double redW[2][HU_EST_CONS / 32];
 	unsigned long long full[HU_EST_STAGES], empty[HU_EST_STAGES], hfull[2], hempty[2];
-	// followed in dynamic shared memory by g[4][capW] (g_j of the current item, one plane per state) and
+	// followed in dynamic shared memory by g01[capW], g23[capW] (g_j of the current item as two 16-byte halves) and
 	// hdr[2][capW + 32] (the read's window, double buffered, 16-byte alignment slack on both sides)
 };
 static_assert(sizeof(EstItemP) % 16 == 0, "item records are bulk-copied");
 static_assert(sizeof(EstSmem) % 16 == 0, "the arrays behind EstSmem are targets of 16-byte bulk copies");
-__host__ __device__ inline size_t estSmemBytes(int capW) { return sizeof(EstSmem) + (size_t) 4 * capW * sizeof(double) + (size_t) 2 * (capW + 32); }
+__host__ __device__ inline size_t estSmemBytes(int capW) { return sizeof(EstSmem) + (size_t) 2 * capW * sizeof(double2) + (size_t) 2 * (capW + 32); }
 
 // one message column out of a ring stage: two 128-bit reads; every other group of four threads reads the halves
 // in the opposite order so that a quarter-warp covers all 32 banks.  Those threads get (v2, v3, v0, v1) and
-// multiply by the matrix whose column pairs are exchanged the same way: the same products, summed as
-// (p2 + p3) + (p0 + p1) instead of (p0 + p1) + (p2 + p3) -- identical bits, no selects.
+// multiply by the matrix whose column pairs are exchanged the same way (done once per item, when the matrices are
+// loaded into registers): the same products, summed as (p2 + p3) + (p0 + p1) instead of (p0 + p1) + (p2 + p3) --
+// identical bits, no selects.
 __device__ __forceinline__ void ldsColumn(const double* __restrict__ chunk, int tid, double* v) {
 	const int sw = (tid >> 2) & 1;
 	const double2 a = *reinterpret_cast<const double2*>(chunk + 4 * tid + 2 * sw);
@@ -148,11 +183,11 @@ __device__ __forceinline__ void ldsColumn(const double* __restrict__ chunk, int 
 }
 
 template <bool WEIGHTED>
-__global__ void __launch_bounds__(HU_EST_THREADS, 2) estimateStagedKernel(EstArgs a, TreeDev t, Model m) {
+__global__ void __launch_bounds__(HU_EST_THREADS, 3) estimateStagedKernel(EstArgs a, TreeDev t, Model m) {
 	extern __shared__ __align__(128) unsigned char estRaw[];
 	EstSmem& sm = *reinterpret_cast<EstSmem*>(estRaw);
-	double* const gS = reinterpret_cast<double*>(estRaw + sizeof(EstSmem));
-	int8_t* const hdrS = reinterpret_cast<int8_t*>(gS + (size_t) 4 * a.capW);
+	double2* const gS = reinterpret_cast<double2*>(estRaw + sizeof(EstSmem));
+	int8_t* const hdrS = reinterpret_cast<int8_t*>(gS + (size_t) 2 * a.capW);
 	const int capW = a.capW, hdrPitch = a.capW + 32;
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 	const int total = a.nReads * a.maxNSeed;
@@ -188,12 +223,13 @@ __global__ void __launch_bounds__(HU_EST_THREADS, 2) estimateStagedKernel(EstArg
 					const int r = it.rs / HU_MAX_SEED;
 					mbarWaitRelaxed(&sm.hempty[h], hph ^ 1);
 					sm.meta[h] = it;
+					uint32_t bytes = 0;
 					const int8_t* src = a.aligned + (size_t) r * t.csLen + it.start;
 					const int off = (int) ((uintptr_t) src & 15);
-					const uint32_t bytes = (uint32_t) ((off + it.W + 15) & ~15);
+					if (it.W <= capW) bytes = (uint32_t) ((off + it.W + 15) & ~15); // wider windows: the consumers read the read's codes from global memory
 					sm.hoff[h] = off;
 					mbarArriveExpectTx(&sm.hfull[h], bytes + (uint32_t) sizeof(EstItemP));
-					bulkLoad(hdrS + (size_t) h * hdrPitch, src - off, bytes, &sm.hfull[h]);
+					if (bytes) bulkLoad(hdrS + (size_t) h * hdrPitch, src - off, bytes, &sm.hfull[h]);
 					bulkLoad(&sm.rec[h], a.itemsP + ((size_t) r * a.maxNSeed + it.rs % HU_MAX_SEED), (uint32_t) sizeof(EstItemP), &sm.hfull[h]);
 					const double* U = t.up + ((size_t) it.u * t.csLen + it.start) * 4;
 					const double* V = t.dn + ((size_t) it.u * t.csLen + it.start) * 4;
@@ -222,6 +258,8 @@ __global__ void __launch_bounds__(HU_EST_THREADS, 2) estimateStagedKernel(EstArg
 	int piMax = 0; // argmax of log(pi): state of a gap column of the read
 	for (int k = 1; k < 4; ++k) if (m.logPi[k] > m.logPi[piMax]) piMax = k;
 	const double wGap = m.pi[piMax] / ((m.pi[0] + m.pi[1]) + (m.pi[2] + m.pi[3])); // inferWeight(log pi) at its arg-max
+	const int sw = (tid >> 2) & 1;
+	double2* const slab = a.slab + (size_t) blockIdx.x * 2 * a.csLen;
 	int st = 0, ph = 0, h = 0, hph = 0;
 #ifdef HU_PROF
 	long long pt_ = clock64();
@@ -236,10 +274,20 @@ __global__ void __launch_bounds__(HU_EST_THREADS, 2) estimateStagedKernel(EstArg
 		if (blockIdx.x == 0 && tid == 0) { atomicAdd(&huProfEst[8], 1ull); atomicAdd(&huProfEst[9], (unsigned long long) it.W); }
 #endif
 		const int W = it.W;
-		const int8_t* x = hdrS + (size_t) h * hdrPitch + sm.hoff[h];
-		const int sw = (tid >> 2) & 1;
-		const double* P0 = sm.rec[h].P[0][sw];
-		const double* P1 = sm.rec[h].P[1][sw];
+		const bool wide = W > capW;
+		const int8_t* x = wide ? a.aligned + (size_t) (it.rs / HU_MAX_SEED) * t.csLen + it.start : hdrS + (size_t) h * hdrPitch + sm.hoff[h];
+		double2* const g01 = wide ? slab : gS;
+		double2* const g23 = wide ? slab + a.csLen : gS + capW;
+		// the item's two transition matrices, in registers for the whole item (column pairs exchanged for the threads that read
+		// their message columns half-swapped)
+		double P0[16], P1[16];
+#pragma unroll
+		for (int i = 0; i < 4; ++i)
+#pragma unroll
+			for (int j = 0; j < 4; ++j) {
+				P0[i * 4 + j] = sm.rec[h].P[0][i * 4 + (j ^ (2 * sw))];
+				P1[i * 4 + j] = sm.rec[h].P[1][i * 4 + (j ^ (2 * sw))];
+			}
 		double ll = 0;
 		// ---- pass 1: the unweighted branch-length estimate; g_j parked in shared memory ----
 		unsigned int diff = 0;
@@ -254,7 +302,10 @@ __global__ void __launch_bounds__(HU_EST_THREADS, 2) estimateStagedKernel(EstArg
 				ldsColumn(sm.ring[st][1], tid, ev);
 				matVec4(P0, eu, ya); // rows are not permuted: ya, yb and g are in state order for every thread
 				matVec4(P1, ev, yb);
-				for (int k = 0; k < 4; ++k) { g[k] = ya[k] * yb[k]; gS[k * capW + c] = g[k]; }
+#pragma unroll
+				for (int k = 0; k < 4; ++k) g[k] = ya[k] * yb[k];
+				g01[c] = make_double2(g[0], g[1]);
+				g23[c] = make_double2(g[2], g[3]);
 				const int b = x[c];
 				const int st1 = argmax4(g);
 				const bool mis = st1 != (b >= 0 ? b : piMax);
@@ -274,6 +325,7 @@ __global__ void __launch_bounds__(HU_EST_THREADS, 2) estimateStagedKernel(EstArg
 		if (lane == 0) sm.redB[warp] = diff;
 		consumerSync(HU_EST_CONS);
 		diff = 0;
+#pragma unroll
 		for (int k = 0; k < HU_EST_CONS / 32; ++k) diff += sm.redB[k];
 		double wnr = (double) diff / (double) W;
 		if (WEIGHTED) { // block sums of the two weights (uniform branch)
@@ -285,7 +337,7 @@ __global__ void __launch_bounds__(HU_EST_THREADS, 2) estimateStagedKernel(EstArg
 			wnr = dW / nW;
 			consumerSync(HU_EST_CONS); // redW is reused by the next item
 		}
-		// ---- P(wnr) applied to the read's leaf vector: depends on the base only ----
+		// ---- pi * P(wnr) applied to the read's leaf vector: depends on the base only ----
 		if (warp == 0) {
 			if (lane < 16) modelPrHalfWarp(m, wnr, sm.P2, lane, 0x0000ffffu);
 			__syncwarp();
@@ -293,21 +345,20 @@ __global__ void __launch_bounds__(HU_EST_THREADS, 2) estimateStagedKernel(EstArg
 				double n[4], y[4];
 				leafLin(m, lane < 4 ? lane : -1, n);
 				matVec4(sm.P2, n, y);
-				for (int k = 0; k < 4; ++k) sm.Np[lane][k] = y[k];
+				for (int k = 0; k < 4; ++k) sm.NpPi[lane][k] = m.pi[k] * y[k];
 			}
 		}
 		consumerSync(HU_EST_CONS);
 		ESTP_MARK(3);
 		// ---- pass 2: treeLoglik(pi, UPr + VPr + NPr) ----
 		// sum of logs as the log of a running product: one log per thread instead of one per column (the product of
-		// the <= 6 factors of a thread is flushed long before it could underflow)
+		// the <= 12 factors of a thread is flushed long before it could underflow)
 		double prod = 1.0;
 		for (int c = tid; c < W; c += HU_EST_CONS) {
 			const int b = x[c];
-			const double* np = sm.Np[b >= 0 ? b : 4];
-			double z[4];
-			for (int k = 0; k < 4; ++k) z[k] = gS[k * capW + c] * np[k];
-			prod *= dotPi(m, z);
+			const double* np = sm.NpPi[b >= 0 ? b : 4];
+			const double2 a01 = g01[c], a23 = g23[c];
+			prod *= (a01.x * np[0] + a23.x * np[2]) + (a01.y * np[1] + a23.y * np[3]);
 			if (prod < 1e-150) { ll += log(prod); prod = 1.0; }
 		}
 		ll += log(prod);
@@ -335,119 +386,6 @@ __global__ void __launch_bounds__(HU_EST_THREADS, 2) estimateStagedKernel(EstArg
 		h ^= 1;
 		if (h == 0) hph ^= 1;
 		ESTP_MARK(4);
-	}
-}
-
-struct EstShared {
-	double P[3][16]; // P(wur), P(wvr), P(wnr)
-	double Np[5][4]; // P(wnr) applied to the read's leaf vector, per base / gap
-};
-
-// windows wider than HU_EST_CAPW: one warp per item, the window is read twice (second time mostly from L2)
-__global__ void __launch_bounds__(HU_EST_WARPS * 32) estimateWideKernel(EstArgs a, TreeDev t, Model m) {
-	__shared__ EstShared sh[HU_EST_WARPS];
-	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	EstShared& ws = sh[warp];
-	const int total = a.wideCount[0];
-	int piMax = 0;
-	for (int k = 1; k < 4; ++k) if (m.logPi[k] > m.logPi[piMax]) piMax = k;
-	for (;;) {
-		int q = 0;
-		if (lane == 0) q = atomicAdd(a.wideCount + 1, 1);
-		q = __shfl_sync(0xffffffffu, q, 0);
-		if (q >= total) return;
-		const EstItem it = a.items[a.wideList[q]];
-		const int r = it.rs / HU_MAX_SEED, s = it.rs % HU_MAX_SEED;
-		const int start = it.start, W = it.W, end = start + W - 1;
-		const int u = it.u, v = it.v;
-		const int8_t* x = a.aligned + (size_t) r * t.csLen + start;
-		const int8_t* su = t.seq + (size_t) u * t.csLen + start;
-		const int8_t* sv = t.seq + (size_t) v * t.csLen + start;
-		unsigned int cu = 0, cv = 0; // (N << 16) | d
-		for (int c = lane; c < W; c += 32) {
-			const int b = x[c];
-			if (b >= 0) {
-				const int bu = su[c], bv = sv[c];
-				if (bu >= 0) cu += 0x10000u + (bu != b);
-				if (bv >= 0) cv += 0x10000u + (bv != b);
-			}
-		}
-		for (int o = 16; o > 0; o >>= 1) {
-			cu += __shfl_xor_sync(0xffffffffu, cu, o);
-			cv += __shfl_xor_sync(0xffffffffu, cv, o);
-		}
-		const double cDist = (double) (cu & 0xffffu) / (double) (cu >> 16);
-		const double pDist = (double) (cv & 0xffffu) / (double) (cv >> 16);
-		double ratio = cDist / (cDist + pDist);
-		if (isnan(ratio)) ratio = 0.5;
-		const double w0 = it.w0;
-		const double wur = w0 * ratio, wvr = w0 - wur;
-		__syncwarp();
-		if (lane < 2) modelPr(m, lane == 0 ? wur : wvr, ws.P[lane]);
-		__syncwarp();
-		const double* U = t.up + ((size_t) u * t.csLen + start) * 4;
-		const double* V = t.dn + ((size_t) u * t.csLen + start) * 4;
-		int diff = 0;
-		double dW = 0, nW = 0;
-		const double wGap = m.pi[piMax] / ((m.pi[0] + m.pi[1]) + (m.pi[2] + m.pi[3]));
-		for (int c = lane; c < W; c += 32) {
-			double eu[4], ev[4], ya[4], yb[4], g[4];
-			ld4(U + (size_t) c * 4, eu);
-			ld4(V + (size_t) c * 4, ev);
-			matVec4(ws.P[0], eu, ya);
-			matVec4(ws.P[1], ev, yb);
-			for (int k = 0; k < 4; ++k) g[k] = ya[k] * yb[k];
-			const int b = x[c];
-			const int st1 = argmax4(g);
-			const bool mis = st1 != (b >= 0 ? b : piMax);
-			diff += mis;
-			if (a.weighted) {
-				const double ww = g[st1] / ((g[0] + g[1]) + (g[2] + g[3])) * (b >= 0 ? 1.0 : wGap);
-				if (mis) dW += ww;
-				nW += ww;
-			}
-		}
-		for (int o = 16; o > 0; o >>= 1) diff += __shfl_xor_sync(0xffffffffu, diff, o);
-		double wnr = (double) diff / (double) W;
-		if (a.weighted) {
-			for (int o = 16; o > 0; o >>= 1) { dW += __shfl_xor_sync(0xffffffffu, dW, o); nW += __shfl_xor_sync(0xffffffffu, nW, o); }
-			wnr = dW / nW;
-		}
-		if (lane == 0) modelPr(m, wnr, ws.P[2]);
-		__syncwarp();
-		if (lane < 5) {
-			double n[4], y[4];
-			leafLin(m, lane < 4 ? lane : -1, n);
-			matVec4(ws.P[2], n, y);
-			for (int k = 0; k < 4; ++k) ws.Np[lane][k] = y[k];
-		}
-		__syncwarp();
-		double ll = windowScale(t.upS, t.upP32, u, t.csLen, t.nWords, start, end, lane)
-		          + windowScale(t.dnS, t.dnP32, u, t.csLen, t.nWords, start, end, lane);
-		for (int c = lane; c < W; c += 32) {
-			double eu[4], ev[4], ya[4], yb[4], z[4];
-			ld4(U + (size_t) c * 4, eu);
-			ld4(V + (size_t) c * 4, ev);
-			matVec4(ws.P[0], eu, ya);
-			matVec4(ws.P[1], ev, yb);
-			const int b = x[c];
-			const double* np = ws.Np[b >= 0 ? b : 4];
-			for (int k = 0; k < 4; ++k) z[k] = (ya[k] * yb[k]) * np[k];
-			ll += log(dotPi(m, z));
-		}
-		for (int o = 16; o > 0; o >>= 1) ll += __shfl_xor_sync(0xffffffffu, ll, o);
-		if (lane == 0) {
-			hu_place_row row;
-			row.start = start; row.end = end;
-			row.cNode = u; row.pNode = v; row.aNode = ratio <= 0.5 ? u : v;
-			row.taxon = t.taxon[row.aNode];
-			row.dist = cDist;
-			row.wuv = w0; row.ratio = ratio; row.wnr = wnr;
-			row.loglik = ll; row.loglikTrue = 0; row.estLoglik = ll;
-			row.height = 0; row.annoDist = 0; row.qPlace = 0; row.qTaxon = 0;
-			row.outerIters = 0; row.nPlaces = 0;
-			a.est[(size_t) r * HU_MAX_SEED + s] = row;
-		}
 	}
 }
 
@@ -483,24 +421,33 @@ int launchEstimate(hu_batch* b, const hu_sep_params* p) {
 	hu_db* db = b->db;
 	EstArgs a;
 	a.nReads = b->nReads; a.maxNSeed = p->maxNSeed; a.weighted = p->estMethod == HU_EST_WEIGHTED;
-	// merged paired-end windows and long reads are wider than an amplicon read's: one CTA per SM with a larger g buffer
-	a.capW = (b->paired || b->maxSeqLen > 400) ? HU_EST_CAPW_BIG : HU_EST_CAPW;
+	// merged paired-end windows (1.5 - 2.5 k columns) get the larger g buffer (two CTAs per SM); single-end amplicon reads
+	// and reads so long that every window spills to the global slab anyway get the small one (three CTAs per SM)
+	a.capW = (b->paired || (b->maxSeqLen > 400 && b->maxSeqLen <= 700)) ? HU_EST_CAPW_BIG : HU_EST_CAPW;
+	a.csLen = db->tree.csLen; a.pad = 0;
 	a.aligned = b->vit.aligned; a.winStart = b->winStart; a.winEnd = b->winEnd;
 	a.seedIds = b->seed.seedIds; a.nSeeds = b->seed.nSeeds;
-	a.est = b->est; a.items = b->estItems; a.itemsP = b->estItemsP; a.wideCount = b->workCount + 2; a.wideList = b->workItems;
+	a.est = b->est; a.items = b->estItems; a.itemsP = b->estItemsP;
 	int sms = 0;
 	HU_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, db->device));
 	HU_CUDA(cudaMemsetAsync(b->workCount, 0, 4 * sizeof(int), b->stream));
 	const int total = a.nReads * a.maxNSeed;
-	estPlanKernel<<<(total + 7) / 8, 256, 0, b->stream>>>(a, db->tree, db->model);
 	const size_t smem = estSmemBytes(a.capW);
-	const int grid = sms * (smem <= 112 * 1024 ? 2 : 1);
+	const int perSm = std::max(1, std::min(3, (int) ((227 * 1024) / (smem + 1024))));
+	const int grid = sms * perSm;
+	if (!b->estSlab || b->estSlabCtas < grid) {
+		void* q = NULL;
+		HU_CUDA(cudaMalloc(&q, (size_t) grid * 2 * a.csLen * sizeof(double2)));
+		b->allocs.push_back(q);
+		b->estSlab = q; b->estSlabCtas = grid;
+	}
+	a.slab = (double2*) b->estSlab;
+	estPlanKernel<<<(total + 7) / 8, 256, 0, b->stream>>>(a, db->tree, db->model);
 	if (a.weighted) estimateStagedKernel<true><<<grid, HU_EST_THREADS, smem, b->stream>>>(a, db->tree, db->model);
 	else estimateStagedKernel<false><<<grid, HU_EST_THREADS, smem, b->stream>>>(a, db->tree, db->model);
-	estimateWideKernel<<<sms * 4, HU_EST_WARPS * 32, 0, b->stream>>>(a, db->tree, db->model); // exits at once when no window is wide
 	filterKernel<<<(b->nReads + 127) / 128, 128, 0, b->stream>>>(b->nReads, b->winStart, a.nSeeds, b->est, p->maxError, b->order, b->nKept);
 	HU_CUDA(cudaEventRecord(b->ev[5], b->stream));
-	b->launches += 4;
+	b->launches += 3;
 	HU_CUDA(cudaGetLastError());
 	return HU_OK;
 }
