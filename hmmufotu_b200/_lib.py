@@ -71,7 +71,8 @@ SYMBOLS = ["hu_hmm_finalize", "hu_model_Pr", "hu_db_create", "hu_db_destroy", "h
            "hu_batch_get_aligned_codes", "hu_batch_get_seeds", "hu_batch_get_estimates", "hu_batch_get_places",
            "hu_batch_get_best", "hu_batch_stage_ms", "hu_batch_get_stats", "hu_trace_to_align", "hu_last_error",
            "hu_version", "hu_host_alloc", "hu_host_free", "hu_batch_mark", "hu_batch_elapsed", "hu_batch_get_seed_keys",
-           "hu_debug_literal_order", "hu_debug_stdsort", "hu_batch_pack_rows", "hu_batch_stream", "hu_db_get_messages_of"]
+           "hu_debug_literal_order", "hu_debug_stdsort", "hu_batch_pack_rows", "hu_batch_stream", "hu_db_get_messages_of", "hu_filter_batch", "hu_batch_set_seeds",
+           "hu_batch_set_estimates", "hu_batch_set_places"]
 
 _LIB = None
 
@@ -102,7 +103,10 @@ def load() -> C.CDLL:
     L.hu_batch_upload.argtypes = [vp, P(ReadBatch)]
     L.hu_batch_set_aligned.argtypes = [vp, i32, vp, vp, vp]
     L.hu_align_batch.argtypes = [vp, C.c_int]
-    for f in ("hu_seed_batch", "hu_estimate_batch", "hu_place_batch", "hu_finalize_batch"):
+    L.hu_batch_set_seeds.argtypes = [vp, vp, vp]
+    L.hu_batch_set_estimates.argtypes = [vp, vp, vp]
+    L.hu_batch_set_places.argtypes = [vp, vp, vp]
+    for f in ("hu_seed_batch", "hu_estimate_batch", "hu_filter_batch", "hu_place_batch", "hu_finalize_batch"):
         getattr(L, f).argtypes = [vp, P(SepParams)]
     L.hu_assign_batch.argtypes = [vp, C.c_int, P(SepParams)]
     L.hu_batch_sync.argtypes = [vp]

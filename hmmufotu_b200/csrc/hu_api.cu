@@ -209,20 +209,29 @@ int hu_batch_create(hu_batch** out, hu_db* db, int32_t maxReads, int32_t maxSeqL
 	HU_TRY(balloc(b, &b->estItemsP, (size_t) maxReads * HU_MAX_SEED));
 	HU_TRY(balloc(b, &b->vit.rows, (size_t) b->maxSeq));
 	HU_TRY(balloc(b, &b->merged, (size_t) maxReads));
-	HU_TRY(balloc(b, &b->vit.fullCount, 2));
+	HU_TRY(balloc(b, &b->vit.fullCount, 4));
 	b->vit.fullCursor = b->vit.fullCount + 1;
+	b->vit.bandCursor = b->vit.fullCount + 2;
 	HU_TRY(balloc(b, &b->vit.fullList, (size_t) b->maxSeq));
 	int sms = 0;
 	HU_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, db->device));
-	// Viterbi CTA shape: as many warps as the per-warp shared memory allows
-	int wpb = HU_VIT_WARPS;
-	const size_t perWarp = ((size_t) (maxSeqLen + 15) / 16 * 16 + (size_t) 3 * (maxSeqLen + 2) * 8 + 320 * 8 + 8 * 24 + 5 * sizeof(VRegion) + 16 + 15) / 16 * 16;
-	while (wpb > 1 && perWarp * wpb > 200 * 1024) wpb >>= 1;
+	// Viterbi CTA shape: the number of warps (= sequences in flight) per CTA that puts most warps on an SM, given the per-warp
+	// shared memory (boundary column, emission tables, codes: grows with maxSeqLen) and the kernel's 96 registers per thread
+	const size_t perWarp = ((size_t) (maxSeqLen + 15) / 16 * 16 + (size_t) 3 * (maxSeqLen + 2 + 32) * 8 + 320 * 8 + 8 * 24 + 5 * sizeof(VRegion) + 16 +
+	                        ((size_t) 2 * (maxSeqLen + 64) + 15) / 16 * 16 + 15) / 16 * 16;
 	if (perWarp > 200 * 1024) { setError("maxSeqLen %d too long for the Viterbi shared-memory layout", maxSeqLen); return HU_ERR_ARG; }
+	int wpb = 1, bestWarps = 0, bestCtas = 1;
+	for (int w = 1; w <= HU_VIT_WARPS; ++w) {
+		if (perWarp * w > 200 * 1024) break;
+		const int bySmem = (int) ((227 * 1024) / (perWarp * w + 1024)), byRegs = 65536 / (96 * 32 * w);
+		const int ctas = std::min(bySmem, byRegs);
+		if (ctas * w >= bestWarps) { bestWarps = ctas * w; wpb = w; bestCtas = ctas; }
+	}
 	b->vit.warpsPerBlock = wpb;
+	b->vitGrid = sms * std::max(1, bestCtas);
 	b->vit.maxLen = maxSeqLen;
 	b->fullSlots = std::min(sms * 2, b->maxSeq); // CTAs of the full-matrix pass, one back-pointer slab each
-	b->vit.fullSlabWords = (size_t) K * ((maxSeqLen + 7) / 8);
+	b->vit.fullSlabWords = (size_t) ((K + 31) / 32) * (maxSeqLen + 31) * 4; // [stripe][step][4 ballot words]
 	HU_TRY(balloc(b, &b->vit.fullPtrs, b->vit.fullSlabWords * b->fullSlots));
 	HU_TRY(balloc(b, &b->winStart, (size_t) maxReads));
 	HU_TRY(balloc(b, &b->winEnd, (size_t) maxReads));
@@ -291,9 +300,9 @@ int hu_batch_upload(hu_batch* b, const hu_read_batch* rb) {
 		else if (!planBand(p.N, K, rb->vpaths + (size_t) s * 2, np, &p)) { p.nReg = 0; p.flags = HU_ALIGN_NOSEED | HU_ALIGN_IRREGULAR; }
 		for (int r = 0; r < p.nReg; ++r) {
 			VRegion& R = p.reg[r];
-			R.rowWords = (R.i1 - R.i0 + 1 + 7) / 8;
+			R.rowWords = R.i1 - R.i0 + 1 + 31; // wavefront steps per 32-column stripe (hu_viterbi.cu: four ballot words per step)
 			R.ptrOff = ptrWords;
-			ptrWords += (long long) R.rowWords * (R.j1 - R.j0 + 1);
+			ptrWords += (long long) ((R.j1 - R.j0 + 1 + 31) / 32) * R.rowWords * 4;
 		}
 	}
 	b->hTraceOff[nSeq] = traceOff;
@@ -328,6 +337,58 @@ int hu_batch_set_aligned(hu_batch* b, int32_t n, const int8_t* codes, const int3
 	return HU_OK;
 }
 
+// ---- stage inputs supplied by the caller: what the reference's free functions take as arguments when they are called one
+// by one (src/HmmUFOtu_main.h:70-113); host/hu_facade.cpp builds those functions on these ----
+int hu_batch_set_seeds(hu_batch* b, const int32_t* nSeeds, const int32_t* ids) {
+	if (!b || !nSeeds || !ids || b->nReads < 1) { setError("hu_batch_set_seeds: bad arguments"); return HU_ERR_ARG; }
+	HU_CUDA(cudaSetDevice(b->db->device));
+	const int mx = b->seed.maxNSeed > 0 ? b->seed.maxNSeed : HU_MAX_SEED;
+	std::vector<int> all((size_t) b->nReads * HU_MAX_SEED, 0);
+	for (int r = 0; r < b->nReads; ++r) {
+		if (nSeeds[r] < 0 || nSeeds[r] > HU_MAX_SEED) { setError("hu_batch_set_seeds: %d seeds for read %d", nSeeds[r], r); return HU_ERR_ARG; }
+		for (int s = 0; s < nSeeds[r]; ++s) {
+			const int id = ids[(size_t) r * mx + s];
+			if (id < 0 || id >= b->db->tree.nNodes || id == b->db->tree.root) { setError("hu_batch_set_seeds: node %d is not a seed candidate", id); return HU_ERR_ARG; }
+			all[(size_t) r * HU_MAX_SEED + s] = id;
+		}
+	}
+	HU_CUDA(cudaMemcpyAsync(b->seed.nSeeds, nSeeds, (size_t) b->nReads * sizeof(int), cudaMemcpyHostToDevice, b->stream));
+	HU_CUDA(cudaMemcpyAsync(b->seed.seedIds, all.data(), all.size() * sizeof(int), cudaMemcpyHostToDevice, b->stream));
+	HU_CUDA(cudaStreamSynchronize(b->stream));
+	return HU_OK;
+}
+static int setRows(hu_batch* b, hu_place_row* dst, const int32_t* n, const hu_place_row* rows, bool identityOrder) {
+	HU_CUDA(cudaSetDevice(b->db->device));
+	const int mx = b->seed.maxNSeed > 0 ? b->seed.maxNSeed : HU_MAX_SEED;
+	std::vector<hu_place_row> all((size_t) b->nReads * HU_MAX_SEED);
+	std::vector<int> ord((size_t) b->nReads * HU_MAX_SEED, 0);
+	memset(all.data(), 0, all.size() * sizeof(hu_place_row));
+	for (int r = 0; r < b->nReads; ++r) {
+		if (n[r] < 0 || n[r] > HU_MAX_SEED) { setError("%d rows for read %d", n[r], r); return HU_ERR_ARG; }
+		for (int i = 0; i < n[r]; ++i) { all[(size_t) r * HU_MAX_SEED + i] = rows[(size_t) r * mx + i]; ord[(size_t) r * HU_MAX_SEED + i] = i; }
+	}
+	HU_CUDA(cudaMemcpyAsync(dst, all.data(), all.size() * sizeof(hu_place_row), cudaMemcpyHostToDevice, b->stream));
+	if (identityOrder) {
+		HU_CUDA(cudaMemcpyAsync(b->order, ord.data(), ord.size() * sizeof(int), cudaMemcpyHostToDevice, b->stream));
+		HU_CUDA(cudaMemcpyAsync(b->nKept, n, (size_t) b->nReads * sizeof(int), cudaMemcpyHostToDevice, b->stream));
+	}
+	HU_CUDA(cudaStreamSynchronize(b->stream));
+	return HU_OK;
+}
+int hu_batch_set_estimates(hu_batch* b, const int32_t* n, const hu_place_row* rows) {
+	if (!b || !n || !rows || b->nReads < 1) { setError("hu_batch_set_estimates: bad arguments"); return HU_ERR_ARG; }
+	// rows in the caller's order become the estimate vector; they count as kept, in that order, until hu_filter_batch runs
+	int rc = setRows(b, b->est, n, rows, true);
+	if (rc == HU_OK) HU_CUDA(cudaMemcpy(b->seed.nSeeds, n, (size_t) b->nReads * sizeof(int), cudaMemcpyHostToDevice));
+	return rc;
+}
+int hu_batch_set_places(hu_batch* b, const int32_t* n, const hu_place_row* rows) {
+	if (!b || !n || !rows || b->nReads < 1) { setError("hu_batch_set_places: bad arguments"); return HU_ERR_ARG; }
+	int rc = setRows(b, b->places, n, rows, false);
+	if (rc == HU_OK) HU_CUDA(cudaMemcpy(b->nKept, n, (size_t) b->nReads * sizeof(int), cudaMemcpyHostToDevice));
+	return rc;
+}
+
 int hu_align_batch(hu_batch* b, int mode) {
 	if (!b || b->nSeq < 1 || !b->vit.plans) { setError("hu_align_batch: no reads uploaded"); return HU_ERR_STATE; }
 	HU_CUDA(cudaSetDevice(b->db->device));
@@ -349,6 +410,11 @@ int hu_estimate_batch(hu_batch* b, const hu_sep_params* p) {
 	if (!b || !p || b->nReads < 1) { setError("hu_estimate_batch: empty batch"); return HU_ERR_STATE; }
 	HU_CUDA(cudaSetDevice(b->db->device));
 	return launchEstimate(b, p);
+}
+int hu_filter_batch(hu_batch* b, const hu_sep_params* p) {
+	if (!b || !p || b->nReads < 1) { setError("hu_filter_batch: empty batch"); return HU_ERR_STATE; }
+	HU_CUDA(cudaSetDevice(b->db->device));
+	return launchFilter(b, p);
 }
 int hu_place_batch(hu_batch* b, const hu_sep_params* p) {
 	if (!b || !p || b->nReads < 1) { setError("hu_place_batch: empty batch"); return HU_ERR_STATE; }

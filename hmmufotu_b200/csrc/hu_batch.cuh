@@ -4,7 +4,7 @@
 
 #define HU_CODE_GAP (-2) // '-' in an aligned string (DegenAlphabet gap code, src/DegenAlphabet.cpp:43-64)
 #define HU_CODE_PAD (-3) // '.' padding outside the aligned region; any negative code is a gap to the SEP stages
-#define HU_VIT_WARPS 8   // max warps (= sequences) per Viterbi CTA
+#define HU_VIT_WARPS 7   // max warps (= sequences) per Viterbi CTA: 3 CTAs of 7 warps fit an SM for reads up to ~270 bases
 #define HU_SCAN_TILE 512 // node slots per seed-scan CTA
 #define HU_SCAN_READS 8  // reads per seed-scan CTA
 #define HU_SEED_MAX_N 46340 // compared columns per (read, node) for which the integer seed keys are exact (hu_seed.cu)
@@ -15,7 +15,7 @@ struct VRegion {
 	int j0, j1, i0, i1;          // box: profile columns j0..j1, read rows i0..i1 (1-based, inclusive)
 	int strip, pStart, pFrom, nIns, nDel; // seed strip: only cells with -nDel <= (i-pFrom)-(j-pStart) <= nIns
 	int useB;                    // begin-state entry allowed (false in the downstream box)
-	int rowWords;                // back-pointer words per column = ceil(rows / 8)
+	int rowWords;                // wavefront steps per 32-column stripe slot = rows + 31 (four back-pointer ballot words per step)
 	int pad;
 	long long ptrOff;            // word offset of this box in the back-pointer buffer
 };
@@ -34,6 +34,7 @@ struct VitArgs {
 	hu_align_row* rows;  // [nSeq]
 	int* fullCount;      // [0] number of queued sequences, [1] cursor
 	int* fullCursor;
+	int* bandCursor;     // [2] next sequence of the banded pass
 	int* fullList;
 	uint32_t* fullPtrs;
 	size_t fullSlabWords;
@@ -102,6 +103,7 @@ struct hu_batch {
 	long long* hTraceOffs;     // pinned
 	long long d2hBytes;        // bytes the last getter moved to the host
 	int fullSlots;
+	int vitGrid;           // resident CTAs of the persistent banded kernel
 	hu_align_row* merged;  // [maxReads]
 	std::vector<hu::VPlan> hPlans;
 	std::vector<long long> hTraceOff;
@@ -141,6 +143,7 @@ namespace hu {
 int launchViterbi(hu_batch* b, int mode);
 int launchSeed(hu_batch* b, const hu_sep_params* p);
 int launchEstimate(hu_batch* b, const hu_sep_params* p);
+int launchFilter(hu_batch* b, const hu_sep_params* p);
 int launchPlace(hu_batch* b, const hu_sep_params* p);
 int launchFinalize(hu_batch* b, const hu_sep_params* p);
 } // namespace hu

@@ -144,14 +144,6 @@ __global__ void __launch_bounds__(256, 4) estPlanKernel(EstArgs a, TreeDev t, Mo
 	if (lane == 0) a.items[i] = it;
 }
 
-#ifdef HU_PROF // build-time instrumentation: phase clocks of consumer thread 0 of CTA 0
-__device__ unsigned long long huProfEst[16];
-#define ESTP_MARK(i) do { if (blockIdx.x == 0 && tid == 0) { const long long now_ = clock64(); atomicAdd(&huProfEst[i], (unsigned long long) (now_ - pt_)); pt_ = now_; } } while (0)
-extern "C" void hu_prof_est(unsigned long long* out) { cudaMemcpyFromSymbol(out, huProfEst, sizeof(huProfEst)); }
-#else
-#define ESTP_MARK(i) do {} while (0)
-#endif
-
 struct EstSmem {
 	double ring[HU_EST_STAGES][2][HU_EST_CH * 4]; // U chunk, V chunk
 	EstItemP rec[2];                              // cDist, ratio, P(wur), P(wvr) of the staged items (bulk-copied)
@@ -180,6 +172,121 @@ __device__ __forceinline__ void ldsColumn(const double* __restrict__ chunk, int 
 	const double2 a = *reinterpret_cast<const double2*>(chunk + 4 * tid + 2 * sw);
 	const double2 b = *reinterpret_cast<const double2*>(chunk + 4 * tid + 2 * (1 - sw));
 	v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+
+// The consumer side of one item.  G / X: where g_j and the read's window live -- shared memory (WIDE = false: typed shared
+// pointers, so that the accesses are LDS / STS) or, for a window wider than the shared-memory buffer, the CTA's slab in global
+// memory and the read's row in global memory.
+template <bool WEIGHTED, bool WIDE>
+__device__ __forceinline__ void estConsumeItem(EstSmem& sm, const EstArgs& a, const Model& m, const EstItem& it, int h, double2* __restrict__ g01,
+		double2* __restrict__ g23, const int8_t* __restrict__ x, int& st, int& ph, int tid, int warp, int lane, int piMax, double wGap) {
+	const int W = it.W;
+	const int sw = (tid >> 2) & 1;
+	// the item's two transition matrices, in registers for the whole item (column pairs exchanged for the threads that read
+	// their message columns half-swapped)
+	double P0[16], P1[16];
+#pragma unroll
+	for (int i = 0; i < 4; ++i)
+#pragma unroll
+		for (int j = 0; j < 4; ++j) {
+			P0[i * 4 + j] = sm.rec[h].P[0][i * 4 + (j ^ (2 * sw))];
+			P1[i * 4 + j] = sm.rec[h].P[1][i * 4 + (j ^ (2 * sw))];
+		}
+	double ll = 0;
+	// ---- pass 1: the unweighted branch-length estimate; g_j parked ----
+	unsigned int diff = 0;
+	double dW = 0, nW = 0; // weighted variant: sums of w1 w2 over mismatching / all columns (cpp:1034-1052)
+	for (int c0 = 0; c0 < W; c0 += HU_EST_CH) {
+		mbarWait(&sm.full[st], ph);
+		const int c = c0 + tid;
+		if (c < W) {
+			double eu[4], ev[4], ya[4], yb[4], g[4];
+			ldsColumn(sm.ring[st][0], tid, eu);
+			ldsColumn(sm.ring[st][1], tid, ev);
+			// matVec4, not a fused chain: the arg-max below is a discrete decision, and on exactly tied columns (uniform pi,
+			// uninformative messages: K80, JC69) the rounding of these sums decides it -- same products, same order of
+			// additions as dot_product_scaled in the oracle (a fused chain changed 4 of 22 kept placements of a K80 read)
+			matVec4(P0, eu, ya); // rows are not permuted: ya, yb and g are in state order for every thread
+			matVec4(P1, ev, yb);
+#pragma unroll
+			for (int k = 0; k < 4; ++k) g[k] = ya[k] * yb[k];
+			g01[c] = make_double2(g[0], g[1]);
+			g23[c] = make_double2(g[2], g[3]);
+			const int b = x[c];
+			const int st1 = argmax4(g);
+			const bool mis = st1 != (b >= 0 ? b : piMax);
+			diff += mis;
+			if (WEIGHTED) { // inferWeight at the arg-max: max / sum for the tree side, 1 (base) or pi_max / sum(pi) (gap) for the read
+				const double ww = fmax(fmax(g[0], g[1]), fmax(g[2], g[3])) / ((g[0] + g[1]) + (g[2] + g[3])) * (b >= 0 ? 1.0 : wGap);
+				if (mis) dW += ww;
+				nW += ww;
+			}
+		}
+		__syncwarp();
+		if (lane == 0) mbarArrive(&sm.empty[st]);
+		if (++st == HU_EST_STAGES) { st = 0; ph ^= 1; }
+	}
+	for (int o = 16; o > 0; o >>= 1) diff += __shfl_xor_sync(0xffffffffu, diff, o);
+	if (lane == 0) sm.redB[warp] = diff;
+	consumerSync(HU_EST_CONS);
+	diff = 0;
+#pragma unroll
+	for (int k = 0; k < HU_EST_CONS / 32; ++k) diff += sm.redB[k];
+	double wnr = (double) diff / (double) W;
+	if (WEIGHTED) { // block sums of the two weights (uniform branch)
+		for (int o = 16; o > 0; o >>= 1) { dW += __shfl_xor_sync(0xffffffffu, dW, o); nW += __shfl_xor_sync(0xffffffffu, nW, o); }
+		if (lane == 0) { sm.redW[0][warp] = dW; sm.redW[1][warp] = nW; }
+		consumerSync(HU_EST_CONS);
+		dW = nW = 0;
+		for (int k = 0; k < HU_EST_CONS / 32; ++k) { dW += sm.redW[0][k]; nW += sm.redW[1][k]; }
+		wnr = dW / nW;
+		consumerSync(HU_EST_CONS); // redW is reused by the next item
+	}
+	// ---- pi * P(wnr) applied to the read's leaf vector: depends on the base only ----
+	if (warp == 0) {
+		if (lane < 16) modelPrHalfWarp(m, wnr, sm.P2, lane, 0x0000ffffu);
+		__syncwarp();
+		if (lane < 5) {
+			double n[4], y[4];
+			leafLin(m, lane < 4 ? lane : -1, n);
+			matVec4(sm.P2, n, y);
+			for (int k = 0; k < 4; ++k) sm.NpPi[lane][k] = m.pi[k] * y[k];
+		}
+	}
+	consumerSync(HU_EST_CONS);
+	// ---- pass 2: treeLoglik(pi, UPr + VPr + NPr) ----
+	// sum of logs as the log of a running product: one log per thread instead of one per column (the product of
+	// the <= 12 factors of a thread is flushed long before it could underflow)
+	double prod = 1.0;
+	for (int c = tid; c < W; c += HU_EST_CONS) {
+		const int b = x[c];
+		const double* np = sm.NpPi[b >= 0 ? b : 4];
+		const double2 a01 = g01[c], a23 = g23[c];
+		prod *= fma(a23.y, np[3], fma(a23.x, np[2], fma(a01.y, np[1], a01.x * np[0])));
+		if (prod < 1e-150) { ll += log(prod); prod = 1.0; }
+	}
+	ll += log(prod);
+	for (int o = 16; o > 0; o >>= 1) ll += __shfl_xor_sync(0xffffffffu, ll, o);
+	if (lane == 0) sm.redC[warp] = ll;
+	consumerSync(HU_EST_CONS);
+	if (tid == 0) {
+		const double cDist = sm.rec[h].cDist, ratio = sm.rec[h].ratio;
+		const int taxon = ratio <= 0.5 ? sm.rec[h].taxU : sm.rec[h].taxV;
+		ll = sm.rec[h].sumScale;
+		mbarArrive(&sm.hempty[h]); // every consumer is past its last read of this item's staged window and record
+		for (int k = 0; k < HU_EST_CONS / 32; ++k) ll += sm.redC[k];
+		const int r = it.rs / HU_MAX_SEED;
+		hu_place_row row;
+		row.start = it.start; row.end = it.start + W - 1;
+		row.cNode = it.u; row.pNode = it.v; row.aNode = ratio <= 0.5 ? it.u : it.v;
+		row.taxon = taxon;
+		row.dist = cDist;
+		row.wuv = it.w0; row.ratio = ratio; row.wnr = wnr;
+		row.loglik = ll; row.loglikTrue = 0; row.estLoglik = ll;
+		row.height = 0; row.annoDist = 0; row.qPlace = 0; row.qTaxon = 0;
+		row.outerIters = 0; row.nPlaces = 0;
+		a.est[(size_t) r * HU_MAX_SEED + (it.rs % HU_MAX_SEED)] = row;
+	}
 }
 
 template <bool WEIGHTED>
@@ -258,134 +365,19 @@ __global__ void __launch_bounds__(HU_EST_THREADS, 3) estimateStagedKernel(EstArg
 	int piMax = 0; // argmax of log(pi): state of a gap column of the read
 	for (int k = 1; k < 4; ++k) if (m.logPi[k] > m.logPi[piMax]) piMax = k;
 	const double wGap = m.pi[piMax] / ((m.pi[0] + m.pi[1]) + (m.pi[2] + m.pi[3])); // inferWeight(log pi) at its arg-max
-	const int sw = (tid >> 2) & 1;
 	double2* const slab = a.slab + (size_t) blockIdx.x * 2 * a.csLen;
 	int st = 0, ph = 0, h = 0, hph = 0;
-#ifdef HU_PROF
-	long long pt_ = clock64();
-#endif
 	for (;;) {
-		ESTP_MARK(5);
 		mbarWait(&sm.hfull[h], hph);
-		ESTP_MARK(0);
 		const EstItem it = sm.meta[h];
 		if (it.kind == 0) break;
-#ifdef HU_PROF
-		if (blockIdx.x == 0 && tid == 0) { atomicAdd(&huProfEst[8], 1ull); atomicAdd(&huProfEst[9], (unsigned long long) it.W); }
-#endif
-		const int W = it.W;
-		const bool wide = W > capW;
-		const int8_t* x = wide ? a.aligned + (size_t) (it.rs / HU_MAX_SEED) * t.csLen + it.start : hdrS + (size_t) h * hdrPitch + sm.hoff[h];
-		double2* const g01 = wide ? slab : gS;
-		double2* const g23 = wide ? slab + a.csLen : gS + capW;
-		// the item's two transition matrices, in registers for the whole item (column pairs exchanged for the threads that read
-		// their message columns half-swapped)
-		double P0[16], P1[16];
-#pragma unroll
-		for (int i = 0; i < 4; ++i)
-#pragma unroll
-			for (int j = 0; j < 4; ++j) {
-				P0[i * 4 + j] = sm.rec[h].P[0][i * 4 + (j ^ (2 * sw))];
-				P1[i * 4 + j] = sm.rec[h].P[1][i * 4 + (j ^ (2 * sw))];
-			}
-		double ll = 0;
-		// ---- pass 1: the unweighted branch-length estimate; g_j parked in shared memory ----
-		unsigned int diff = 0;
-		double dW = 0, nW = 0; // weighted variant: sums of w1 w2 over mismatching / all columns (cpp:1034-1052)
-		for (int c0 = 0; c0 < W; c0 += HU_EST_CH) {
-			mbarWait(&sm.full[st], ph);
-			ESTP_MARK(1);
-			const int c = c0 + tid;
-			if (c < W) {
-				double eu[4], ev[4], ya[4], yb[4], g[4];
-				ldsColumn(sm.ring[st][0], tid, eu);
-				ldsColumn(sm.ring[st][1], tid, ev);
-				matVec4(P0, eu, ya); // rows are not permuted: ya, yb and g are in state order for every thread
-				matVec4(P1, ev, yb);
-#pragma unroll
-				for (int k = 0; k < 4; ++k) g[k] = ya[k] * yb[k];
-				g01[c] = make_double2(g[0], g[1]);
-				g23[c] = make_double2(g[2], g[3]);
-				const int b = x[c];
-				const int st1 = argmax4(g);
-				const bool mis = st1 != (b >= 0 ? b : piMax);
-				diff += mis;
-				if (WEIGHTED) { // inferWeight at the arg-max: max / sum for the tree side, 1 (base) or pi_max / sum(pi) (gap) for the read
-					const double ww = g[st1] / ((g[0] + g[1]) + (g[2] + g[3])) * (b >= 0 ? 1.0 : wGap);
-					if (mis) dW += ww;
-					nW += ww;
-				}
-			}
-			__syncwarp();
-			if (lane == 0) mbarArrive(&sm.empty[st]);
-			if (++st == HU_EST_STAGES) { st = 0; ph ^= 1; }
-			ESTP_MARK(2);
-		}
-		for (int o = 16; o > 0; o >>= 1) diff += __shfl_xor_sync(0xffffffffu, diff, o);
-		if (lane == 0) sm.redB[warp] = diff;
-		consumerSync(HU_EST_CONS);
-		diff = 0;
-#pragma unroll
-		for (int k = 0; k < HU_EST_CONS / 32; ++k) diff += sm.redB[k];
-		double wnr = (double) diff / (double) W;
-		if (WEIGHTED) { // block sums of the two weights (uniform branch)
-			for (int o = 16; o > 0; o >>= 1) { dW += __shfl_xor_sync(0xffffffffu, dW, o); nW += __shfl_xor_sync(0xffffffffu, nW, o); }
-			if (lane == 0) { sm.redW[0][warp] = dW; sm.redW[1][warp] = nW; }
-			consumerSync(HU_EST_CONS);
-			dW = nW = 0;
-			for (int k = 0; k < HU_EST_CONS / 32; ++k) { dW += sm.redW[0][k]; nW += sm.redW[1][k]; }
-			wnr = dW / nW;
-			consumerSync(HU_EST_CONS); // redW is reused by the next item
-		}
-		// ---- pi * P(wnr) applied to the read's leaf vector: depends on the base only ----
-		if (warp == 0) {
-			if (lane < 16) modelPrHalfWarp(m, wnr, sm.P2, lane, 0x0000ffffu);
-			__syncwarp();
-			if (lane < 5) {
-				double n[4], y[4];
-				leafLin(m, lane < 4 ? lane : -1, n);
-				matVec4(sm.P2, n, y);
-				for (int k = 0; k < 4; ++k) sm.NpPi[lane][k] = m.pi[k] * y[k];
-			}
-		}
-		consumerSync(HU_EST_CONS);
-		ESTP_MARK(3);
-		// ---- pass 2: treeLoglik(pi, UPr + VPr + NPr) ----
-		// sum of logs as the log of a running product: one log per thread instead of one per column (the product of
-		// the <= 12 factors of a thread is flushed long before it could underflow)
-		double prod = 1.0;
-		for (int c = tid; c < W; c += HU_EST_CONS) {
-			const int b = x[c];
-			const double* np = sm.NpPi[b >= 0 ? b : 4];
-			const double2 a01 = g01[c], a23 = g23[c];
-			prod *= (a01.x * np[0] + a23.x * np[2]) + (a01.y * np[1] + a23.y * np[3]);
-			if (prod < 1e-150) { ll += log(prod); prod = 1.0; }
-		}
-		ll += log(prod);
-		for (int o = 16; o > 0; o >>= 1) ll += __shfl_xor_sync(0xffffffffu, ll, o);
-		if (lane == 0) sm.redC[warp] = ll;
-		consumerSync(HU_EST_CONS);
-		if (tid == 0) {
-			const double cDist = sm.rec[h].cDist, ratio = sm.rec[h].ratio;
-			const int taxon = ratio <= 0.5 ? sm.rec[h].taxU : sm.rec[h].taxV;
-			ll = sm.rec[h].sumScale;
-			mbarArrive(&sm.hempty[h]); // every consumer is past its last read of this item's staged window and record
-			for (int k = 0; k < HU_EST_CONS / 32; ++k) ll += sm.redC[k];
-			const int r = it.rs / HU_MAX_SEED;
-			hu_place_row row;
-			row.start = it.start; row.end = it.start + W - 1;
-			row.cNode = it.u; row.pNode = it.v; row.aNode = ratio <= 0.5 ? it.u : it.v;
-			row.taxon = taxon;
-			row.dist = cDist;
-			row.wuv = it.w0; row.ratio = ratio; row.wnr = wnr;
-			row.loglik = ll; row.loglikTrue = 0; row.estLoglik = ll;
-			row.height = 0; row.annoDist = 0; row.qPlace = 0; row.qTaxon = 0;
-			row.outerIters = 0; row.nPlaces = 0;
-			a.est[(size_t) r * HU_MAX_SEED + (it.rs % HU_MAX_SEED)] = row;
-		}
+		if (it.W <= capW)
+			estConsumeItem<WEIGHTED, false>(sm, a, m, it, h, gS, gS + capW, hdrS + (size_t) h * hdrPitch + sm.hoff[h], st, ph, tid, warp, lane, piMax, wGap);
+		else
+			estConsumeItem<WEIGHTED, true>(sm, a, m, it, h, slab, slab + a.csLen, a.aligned + (size_t) (it.rs / HU_MAX_SEED) * t.csLen + it.start, st, ph, tid, warp, lane,
+			                               piMax, wGap);
 		h ^= 1;
 		if (h == 0) hph ^= 1;
-		ESTP_MARK(4);
 	}
 }
 
@@ -414,6 +406,15 @@ __global__ void filterKernel(int nReads, const int* __restrict__ winStart, const
 int configEstimateKernels() {
 	HU_CUDA(cudaFuncSetAttribute(estimateStagedKernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) estSmemBytes(HU_EST_CAPW_BIG)));
 	HU_CUDA(cudaFuncSetAttribute(estimateStagedKernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) estSmemBytes(HU_EST_CAPW_BIG)));
+	return HU_OK;
+}
+
+// filterPlacements alone (the estimates are already on the device: hu_estimate_batch ran with another maxError, or
+// hu_batch_set_estimates supplied them)
+int launchFilter(hu_batch* b, const hu_sep_params* p) {
+	filterKernel<<<(b->nReads + 127) / 128, 128, 0, b->stream>>>(b->nReads, b->winStart, b->seed.nSeeds, b->est, p->maxError, b->order, b->nKept);
+	b->launches += 1;
+	HU_CUDA(cudaGetLastError());
 	return HU_OK;
 }
 

@@ -221,6 +221,10 @@ __global__ void __launch_bounds__(HU_PLACE_WARPS * 32) placeKernel(PlaceArgs a, 
 			wur0 = wur; wvr0 = wvr; wnr0 = wnr;
 		}
 		// ---- intended root log-likelihood: sum_j log(pi . exp(loglik(r, j))) ----
+		// One more pass over the two message windows: only when it is asked for (the literal placeSeq value, SURVEY.md F6,
+		// needs none of it; the pass was 1 / (2 iters + 1) of this kernel's DRAM traffic)
+		double tl = 0;
+		if (a.useTrue) {
 		__syncwarp();
 		fillP(t.modelDev, wsP, KK, lu, lv, ln, 7);
 		__syncwarp();
@@ -232,8 +236,8 @@ __global__ void __launch_bounds__(HU_PLACE_WARPS * 32) placeKernel(PlaceArgs a, 
 			for (int i = 0; i < 4; ++i) wsNP[(k * 5 + b) * 4 + i] = y[i];
 		}
 		__syncwarp();
-		double tl = windowScale(t.upS, t.upP32, c, t.csLen, t.nWords, start, end, lane)
-		          + windowScale(t.dnS, t.dnP32, c, t.csLen, t.nWords, start, end, lane);
+		tl = windowScale(t.upS, t.upP32, c, t.csLen, t.nWords, start, end, lane)
+		   + windowScale(t.dnS, t.dnP32, c, t.csLen, t.nWords, start, end, lane);
 		ColPrefetch pf;
 		pf.init(U, V, x, lane, W);
 		for (int cI = lane; cI < W; cI += 32) {
@@ -248,11 +252,12 @@ __global__ void __launch_bounds__(HU_PLACE_WARPS * 32) placeKernel(PlaceArgs a, 
 			tl += log(dotPi(m, g) / (double) KK);
 		}
 		tl = warpSum(tl);
+		}
 		if (lane == 0) {
 			hu_place_row row = e;
 			// literal return value: treeLoglik over a root message of INVALID_LOGLIK = 1, tabulated per W
 			row.loglik = t.litTab[W];
-			row.loglikTrue = tl;
+			row.loglikTrue = a.useTrue ? tl : 0.0; // not evaluated unless hu_sep_params.useTrueLoglik is set
 			row.wnr = ln;
 			row.ratio = lu / w0;
 			row.height = t.height[c] + lu;

@@ -185,6 +185,12 @@ __global__ void __launch_bounds__(128) seedScanKernel(SeedArgs a, TreeDev t, int
 	}
 }
 
+// Measured and dropped in round 2 (profiles/r2_summary.md): a scan tiled by candidate position (a CTA owns 1024 consecutive
+// positions of 8 reads, scans the slots of both classes that map there, parks the keys in shared memory and writes whole
+// 128-byte lines).  It removes the partial-sector key writes (26 GB of DRAM traffic for a 6.5 GB key matrix) but the class
+// mix of a position range varies, the quads of a tile do not divide evenly over the threads, and the kernel is bound by
+// POPC issue, not by DRAM: 15.6 ms against 8.7 ms.
+
 // ---- per-read selection of the maxNSeed smallest (key, node id) ----
 #define HU_SEL_THREADS 256
 #define HU_SEL_CAND 2048

@@ -10,6 +10,15 @@
 // Instead of the reference's four dense (N+1)x(K+2) matrices, only a 4-bit back-pointer per cell is
 // stored (2 bits M: B/M/I/D, 1 bit I: M/I, 1 bit D: M/D), evaluated with exactly the candidate sets and
 // first-strict-minimum tie rule buildViterbiTrace uses (src/BandedHMMP7.cpp:943-1006, .h:722-788).
+//
+// Back-pointer layout of a box: the four pointer bits of a cell (2 bits for DP_M, 1 for DP_I, 1 for DP_D) are compare
+// outcomes, i.e. predicates; each wavefront step turns them into four warp ballots (bit l = lane l = column jb + l of the
+// running 32-column stripe) and lane 0 stores the four words with one 128-bit store: [stripe][step t][4], where
+// t = (i - i0) + ((j - j0) & 31).  No per-lane bit assembly, no per-lane stores.
+//
+// Round 2: the inner loop of a plain rectangle (sweepBoxLean) carries only what a cell needs -- the round-1 loop spent 170
+// instructions per wavefront step, most of them index arithmetic and predicates (profiles/r1d_summary.md); the general loop
+// (seed strips, boxes that contain read position 1 or profile column 1, LOCAL / CGNL modes) is kept as sweepBox.
 #include "hu_batch.cuh"
 
 namespace hu {
@@ -45,6 +54,23 @@ __device__ __forceinline__ void loadCol(const HmmDev& h, int jj, ColParams& p) {
 	p.eM0 = __ldg(h.eM + jj); p.eM1 = __ldg(h.eM + Kp + jj); p.eM2 = __ldg(h.eM + 2 * Kp + jj); p.eM3 = __ldg(h.eM + 3 * Kp + jj);
 	p.eI0 = __ldg(h.eI + jj); p.eI1 = __ldg(h.eI + Kp + jj); p.eI2 = __ldg(h.eI + 2 * Kp + jj); p.eI3 = __ldg(h.eI + 3 * Kp + jj);
 	p.dOn = jj > 1 && jj < h.K;
+}
+// the lean loop's subset: DP_D exists for 1 < j < K only (src/BandedHMMP7.cpp:823-825); +inf transition costs make the
+// recurrence produce the +inf (and the "M" back-pointer bit) that the general code selects explicitly
+struct ColLean { double tMMp, tIMp, tDMp, tMDp, tDDp, tMI, tII; };
+__device__ __forceinline__ void loadColLean(const HmmDev& h, int jj, ColLean& p) {
+	const int Kp = h.Kp;
+	const bool dOn = jj > 1 && jj < h.K;
+	p.tMMp = __ldg(h.tr + T_MM * Kp + jj - 1); p.tIMp = __ldg(h.tr + T_IM * Kp + jj - 1); p.tDMp = __ldg(h.tr + T_DM * Kp + jj - 1);
+	p.tMDp = dOn ? __ldg(h.tr + T_MD * Kp + jj - 1) : INFINITY; p.tDDp = dOn ? __ldg(h.tr + T_DD * Kp + jj - 1) : INFINITY;
+	p.tMI = __ldg(h.tr + T_MI * Kp + jj); p.tII = __ldg(h.tr + T_II * Kp + jj);
+}
+__device__ __forceinline__ void storeEmisCol(const HmmDev& h, int jj, double* emis, int lane) {
+	const int Kp = h.Kp;
+	emis[0 * 32 + lane] = __ldg(h.eM + jj); emis[1 * 32 + lane] = __ldg(h.eM + Kp + jj); emis[2 * 32 + lane] = __ldg(h.eM + 2 * Kp + jj); emis[3 * 32 + lane] = __ldg(h.eM + 3 * Kp + jj);
+	emis[4 * 32 + lane] = INFINITY;
+	emis[5 * 32 + lane] = __ldg(h.eI + jj); emis[6 * 32 + lane] = __ldg(h.eI + Kp + jj); emis[7 * 32 + lane] = __ldg(h.eI + 2 * Kp + jj); emis[8 * 32 + lane] = __ldg(h.eI + 3 * Kp + jj);
+	emis[9 * 32 + lane] = INFINITY;
 }
 
 struct SeqConst { // per-sequence constants of the special states (setSequenceMode, src/BandedHMMP7.cpp:561-583)
@@ -113,12 +139,24 @@ __device__ __forceinline__ void cellScore(const ColParams& p, const SeqConst& q,
 	}
 }
 
+// the four pointer bits of the 32 cells of a wavefront step as four ballots, stored by lane 0
+__device__ __forceinline__ void storePtrBits(uint4* __restrict__ dst, bool b0, bool b1, bool b2, bool b3, int lane) {
+	const uint32_t w0 = __ballot_sync(0xffffffffu, b0), w1 = __ballot_sync(0xffffffffu, b1);
+	const uint32_t w2 = __ballot_sync(0xffffffffu, b2), w3 = __ballot_sync(0xffffffffu, b3);
+	if (lane == 0) *dst = make_uint4(w0, w1, w2, w3);
+}
+// lean boxes store the two DP_M compare outcomes as they are: a = (I candidate < M candidate), b = (D candidate < the
+// smaller of the two); decoded here into the B/M/I/D index of the general layout
+__device__ __forceinline__ uint32_t leanPm(uint32_t a, uint32_t b) { return b ? 3u : (a ? 2u : 1u); }
+__device__ __forceinline__ bool isLeanBox(const VRegion& R, bool nnInf) { return !R.strip && nnInf && R.i0 >= 2 && R.j0 >= 2; }
+
 struct WarpCtx {
 	const int8_t* x;   // read codes, x[i-1]
 	SeqConst q;
-	double* bnd;       // shared: [3][bndPitch]
+	double* bnd;       // shared: [3][bndPitch]: M, I, D of the column left of the running stripe, rows i0-1 .. i1 (+ 32 slack entries)
 	int bndPitch;
 	double* emis;      // shared: [2][5][32] emission tables of the current stripe
+	uint16_t* xbox;    // shared: [maxLen + 64] per-box emission offsets of the lean sweep
 	Cell* win;         // shared: 2x2 window around the current chain corner, [a*2+b] = cell (ic-1+a, jc-1+b)
 	Cell* winNew;      // shared: window being captured around the end corner of the running box
 	int ic, jc;        // chain corner of win
@@ -171,8 +209,7 @@ __device__ long long sweepBox(const HmmDev& h, const VRegion& Rsm, bool hasNext,
 		if (s == 0 && lane == 0) { curM = top0.M; curI = top0.I; curD = top0.D; }
 		double dgM = INFINITY, dgI = INFINITY, dgD = INFINITY;
 		if (lane == 0) { dgM = w.bnd[0]; dgI = w.bnd[w.bndPitch]; dgD = w.bnd[2 * w.bndPitch]; }
-		uint32_t acc = 0;
-		uint32_t* ptrCol = ptrBase + R.ptrOff + (long long) (jj - R.j0) * R.rowWords;
+		uint4* ptrStripe = reinterpret_cast<uint4*>(ptrBase + R.ptrOff) + (size_t) s * R.rowWords; // [step t] of this stripe
 		const int steps = rows + ncols - 1;
 		for (int t = 0; t < steps; ++t) {
 			const int i = R.i0 + t - lane;
@@ -202,12 +239,8 @@ __device__ long long sweepBox(const HmmDev& h, const VRegion& Rsm, bool hasNext,
 			cells += pred;
 			// the end corner is recomputed by the next box: its S candidate is taken there
 			if (pred && (i == w.q.N || w.q.sAllRows) && !(hasNext && i == R.i1 && j == R.j1)) cellScore(cp, w.q, i, j, nM, nI, best);
+			storePtrBits(ptrStripe + t, code & 1u, code & 2u, code & 4u, code & 8u, lane);
 			if (on) {
-				acc |= code << (4 * ((i - R.i0) & 7));
-				if (((i - R.i0) & 7) == 7 || i == R.i1) {
-					ptrCol[(i - R.i0) >> 3] = acc;
-					acc = 0;
-				}
 				if (pred && i >= R.i1 - 1 && j >= R.j1 - 1) {
 					Cell c; c.M = nM; c.I = nI; c.D = nD;
 					w.winNew[(i - (R.i1 - 1)) * 2 + (j - (R.j1 - 1))] = c;
@@ -232,6 +265,163 @@ __device__ long long sweepBox(const HmmDev& h, const VRegion& Rsm, bool hasNext,
 	return cells;
 }
 
+// A plain rectangle (no seed strip) whose rows are all >= 2 and whose columns are all >= 2, in GLOBAL / NGCL mode: the
+// begin state cannot be entered inside the box (DP_M(i, 0) = +inf for i >= 2), so the B candidate of every cell is +inf --
+// it still wins the back-pointer when all three predecessors are +inf, exactly as whichMin does on four +inf candidates --
+// and useB makes no difference.  Same arithmetic, same operand order, same first-strict-minimum rules as cellUpdate; what
+// is gone is the per-step bookkeeping:
+//  * cells outside the rows of the box run the same code: their emission offset (a per-box table, xbox) selects the +inf
+//    emission row and their D state is forced to +inf; their back-pointer nibbles are never read;
+//  * the S candidates and the corner window are looked at only in the last steps of a stripe (TAIL);
+//  * a lane's two emission costs are two shared-memory loads off one address; the left-boundary column is an array of
+//    (M, I, D) triples read by lane 0 with immediate offsets; the back-pointer word of 8 steps is assembled by a funnel
+//    shift and stored by all lanes at once; the steps before the tail run in blocks of 8, fully unrolled.
+#ifndef HU_LEAN_UNROLL
+#define HU_LEAN_UNROLL 4
+#endif
+struct LeanState {
+	double curM, curI, curD, dgM, dgI, dgD;
+};
+// shared-memory accesses by 32-bit shared address (the pointers of WarpCtx travel through a struct and the compiler
+// otherwise falls back to generic addressing: an address-space conversion per access)
+__device__ __forceinline__ uint32_t sAddr(const void* p) { return (uint32_t) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ double ldsF64(uint32_t a) { double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void stsF64(uint32_t a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
+__device__ __forceinline__ uint32_t ldsU16(uint32_t a) { uint32_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+
+// One wavefront step.  bndIn: shared address of the boundary triple lane 0 reads at this step (row offset t + 1);
+// xoA: shared address of this lane's emission offset for this step; emisA: shared address of this lane's slot in the
+// emission table; d = t - lane: the lane's row offset; rowsEff: rows of the box (0 for a lane beyond the stripe's columns).
+template <bool TAIL>
+__device__ __forceinline__ void leanStep(LeanState& q, const ColLean& cp, uint32_t bndIn, uint32_t xoA, uint32_t emisA, uint4* __restrict__ ptrStep, int d, int lane,
+		uint32_t rowsEff, const HmmDev& h, const VRegion& R, bool hasNext, WarpCtx& w, int j, int jj, Best& best) {
+	double lM = __shfl_up_sync(0xffffffffu, q.curM, 1);
+	double lI = __shfl_up_sync(0xffffffffu, q.curI, 1);
+	double lD = __shfl_up_sync(0xffffffffu, q.curD, 1);
+	// lane 0 takes its left neighbour from the boundary column: predicated loads straight into the shuffle's registers
+	asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.s32 p, %3, 0;\n\t@p ld.shared.f64 %0, [%4];\n\t@p ld.shared.f64 %1, [%4+8];\n\t@p ld.shared.f64 %2, [%4+16];\n\t}"
+	             : "+d"(lM), "+d"(lI), "+d"(lD) : "r"(lane), "r"(bndIn));
+	const bool pred = (uint32_t) d < rowsEff;
+	const uint32_t e = emisA + ldsU16(xoA); // byte offset of the base's emission row (the +inf row outside the box)
+	const double eM = ldsF64(e), eI = ldsF64(e + 5 * 32 * 8);
+	// DP_M: first strict minimum of (M, I, D); the B candidate is +inf here and a cell whose three predecessors are all +inf is
+	// never on a traced path (every state the traceback visits has a finite cost), so its pointer needs no B case
+	const double cM = q.dgM + cp.tMMp, cI = q.dgI + cp.tIMp, cD = q.dgD + cp.tDMp;
+	const bool pa = cI < cM;
+	double mn = pa ? cI : cM;
+	const bool pb = cD < mn;
+	mn = pb ? cD : mn;
+	const double nM = eM + mn;
+	// DP_I
+	const double iM = q.curM + cp.tMI, iI = q.curI + cp.tII;
+	const bool pi = iI < iM;
+	const double nI = eI + (pi ? iI : iM);
+	// DP_D (+inf transition costs where the column has no D state; +inf outside the rows of the box)
+	const double dM = lM + cp.tMDp, dD = lD + cp.tDDp;
+	const bool pd = dD < dM;
+	const double nD = pred ? (pd ? dD : dM) : INFINITY;
+	storePtrBits(ptrStep, pa, pb, pi, pd, lane);
+	// lane 31 hands its column to the next stripe: boundary entry of row offset d + 1, i.e. 31 entries behind lane 0's read
+	asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.s32 p, %0, 31;\n\tsetp.lt.and.u32 p, %1, %2, p;\n\t@p st.shared.f64 [%3+-744], %4;\n\t@p st.shared.f64 [%3+-736], %5;\n\t@p st.shared.f64 [%3+-728], %6;\n\t}"
+	             :: "r"(lane), "r"((uint32_t) d), "r"(rowsEff), "r"(bndIn), "d"(nM), "d"(nI), "d"(nD) : "memory");
+	if (TAIL && pred) {
+		const int i = R.i0 + d;
+		// the end corner is recomputed by the next box: its S candidate is taken there
+		if ((i == w.q.N || w.q.sAllRows) && !(hasNext && i == R.i1 && j == R.j1)) {
+			ColParams full; // exit cost etc.: only touched here
+			full.ext = __ldg(h.ext + jj); full.tIMj = __ldg(h.tr + T_IM * h.Kp + jj);
+			cellScore(full, w.q, i, j, nM, nI, best);
+		}
+		if (i >= R.i1 - 1 && j >= R.j1 - 1) {
+			Cell c; c.M = nM; c.I = nI; c.D = nD;
+			w.winNew[(i - (R.i1 - 1)) * 2 + (j - (R.j1 - 1))] = c;
+		}
+	}
+	q.curM = nM; q.curI = nI; q.curD = nD;
+	q.dgM = lM; q.dgI = lI; q.dgD = lD;
+}
+
+__device__ long long sweepBoxLean(const HmmDev& h, const VRegion& Rsm, bool hasNext, WarpCtx& wsm, uint32_t* __restrict__ ptrBase, Best& best) {
+	const int lane = threadIdx.x & 31;
+	const VRegion R = Rsm;
+	WarpCtx w = wsm;
+	const int rows = R.i1 - R.i0 + 1, cols = R.j1 - R.j0 + 1;
+	double* const bnd = w.bnd; // [rows + 33][3]: (M, I, D) of the column left of the running stripe, row i0-1+r at entry r
+	// ---- window around the end corner: start from what is known before this box (as sweepBox) ----
+	if (lane < 4) {
+		const int a = lane >> 1, b = lane & 1;
+		const int ci = R.i1 - 1 + a, cj = R.j1 - 1 + b;
+		Cell c;
+		c.M = c.I = c.D = INFINITY;
+		const int oa = ci - (w.ic - 1), ob = cj - (w.jc - 1);
+		if (oa >= 0 && oa < 2 && ob >= 0 && ob < 2) c = w.win[oa * 2 + ob];
+		w.winNew[lane] = c;
+	}
+	// ---- left boundary column (j0 - 1 >= 1): only its rows i0-1 and i0 are known (the chain corner); 32 slack entries of
+	//      +inf behind row i1 so that lane 0 can read one entry per step to the end of a stripe ----
+	for (int r = lane; r <= rows + 32; r += 32) {
+		Cell c;
+		c.M = c.I = c.D = INFINITY;
+		if (r == 0) c = w.win[0];
+		else if (r == 1) c = w.win[2];
+		bnd[3 * r] = c.M; bnd[3 * r + 1] = c.I; bnd[3 * r + 2] = c.D;
+	}
+	// ---- emission offsets per wavefront row offset d = t - lane in [-31, rows + 31): the base's row of the emission table
+	//      inside the box, the +inf row outside ----
+	uint16_t* const xbox = w.xbox + 32;
+	for (int d = -32 + lane; d < rows + 32; d += 32)
+		xbox[d] = (uint16_t) ((d >= 0 && d < rows ? (int) w.x[R.i0 - 1 + d] : 4) * 256);
+	__syncwarp();
+	const Cell top0 = w.win[1]; // (i0-1, j0)
+	const int nStripes = (cols + 31) / 32;
+	for (int s = 0; s < nStripes; ++s) {
+		const int jb = R.j0 + 32 * s;
+		const int j = jb + lane;
+		const int ncols = min(32, R.j1 - jb + 1);
+		const bool colOn = lane < ncols;
+		const int jj = colOn ? j : R.j1; // clamp for loads
+		ColLean cp;
+		loadColLean(h, jj, cp);
+		__syncwarp();
+		storeEmisCol(h, jj, w.emis, lane);
+		__syncwarp();
+		const double* emisLane = w.emis + lane;
+		LeanState q;
+		q.curM = q.curI = q.curD = INFINITY; // (i-1, j): row i0-1 of the own column
+		if (s == 0 && lane == 0) { q.curM = top0.M; q.curI = top0.I; q.curD = top0.D; }
+		q.dgM = q.dgI = q.dgD = INFINITY;    // (i-1, j-1)
+		if (lane == 0) { q.dgM = bnd[0]; q.dgI = bnd[1]; q.dgD = bnd[2]; }
+		uint4* ptrStripe = reinterpret_cast<uint4*>(ptrBase + R.ptrOff) + (size_t) s * R.rowWords;
+		const int steps = rows + ncols - 1;
+		// running addresses: boundary triple of row offset t + 1 (24 bytes per entry), emission offset of row offset t - lane
+		uint32_t bndIn = sAddr(bnd) + 24, xoA = sAddr(xbox - lane);
+		const uint32_t emisA = sAddr(emisLane), rowsEff = colOn ? (uint32_t) rows : 0u;
+		uint4* ptrStep = ptrStripe;
+		int d = -lane;
+		// steps that cannot touch row i1 - 1 or i1 (S candidates, corner window), in unrolled blocks
+		const int bulk = w.q.sAllRows ? 0 : (max(rows - 2, 0) / HU_LEAN_UNROLL * HU_LEAN_UNROLL);
+		int t = 0;
+		for (; t < bulk; t += HU_LEAN_UNROLL) {
+#pragma unroll
+			for (int k = 0; k < HU_LEAN_UNROLL; ++k)
+				leanStep<false>(q, cp, bndIn + 24 * k, xoA + 2 * k, emisA, ptrStep + k, d + k, lane, rowsEff, h, R, hasNext, w, j, jj, best);
+			bndIn += 24 * HU_LEAN_UNROLL; xoA += 2 * HU_LEAN_UNROLL; ptrStep += HU_LEAN_UNROLL; d += HU_LEAN_UNROLL;
+		}
+		for (; t < steps; ++t) {
+			leanStep<true>(q, cp, bndIn, xoA, emisA, ptrStep, d, lane, rowsEff, h, R, hasNext, w, j, jj, best);
+			bndIn += 24; xoA += 2; ptrStep += 1; d += 1;
+		}
+		__syncwarp();
+		if (lane == 0) { bnd[0] = INFINITY; bnd[1] = INFINITY; bnd[2] = INFINITY; }
+		__syncwarp();
+	}
+	__syncwarp();
+	if (lane < 4) w.win[lane] = w.winNew[lane];
+	wsm.ic = R.i1; wsm.jc = R.j1;
+	__syncwarp();
+	return lane == 0 ? (long long) rows * cols : 0;
+}
+
 __device__ __forceinline__ void initWindow(WarpCtx& w, int i0, int j0) {
 	const int lane = threadIdx.x & 31;
 	if (lane < 4) {
@@ -246,12 +436,17 @@ __device__ __forceinline__ void initWindow(WarpCtx& w, int i0, int j0) {
 	__syncwarp();
 }
 
-__device__ __forceinline__ uint32_t ptrAt(const VRegion* regs, int nReg, const uint32_t* __restrict__ ptrBase, int i, int j) {
+// the 4-bit back-pointer of cell (i, j) in the general encoding: bits 0-1 = B/M/I/D index of DP_M, bit 2 = DP_I, bit 3 = DP_D
+__device__ __forceinline__ uint32_t ptrAt(const VRegion* regs, int nReg, const uint32_t* __restrict__ ptrBase, int i, int j, bool nnInf) {
 	for (int r = nReg - 1; r >= 0; --r) {
 		const VRegion& R = regs[r];
 		if (i >= R.i0 && i <= R.i1 && j >= R.j0 && j <= R.j1) {
-			const uint32_t wv = ptrBase[R.ptrOff + (long long) (j - R.j0) * R.rowWords + ((i - R.i0) >> 3)];
-			return (wv >> (4 * ((i - R.i0) & 7))) & 15u;
+			const int ln = (j - R.j0) & 31, st = (j - R.j0) >> 5;
+			const int t = (i - R.i0) + ln; // wavefront step of the cell inside its stripe
+			const uint4 wv = reinterpret_cast<const uint4*>(ptrBase + R.ptrOff)[(size_t) st * R.rowWords + t];
+			const uint32_t b0 = (wv.x >> ln) & 1u, b1 = (wv.y >> ln) & 1u, b2 = (wv.z >> ln) & 1u, b3 = (wv.w >> ln) & 1u;
+			const uint32_t pm = isLeanBox(R, nnInf) ? leanPm(b0, b1) : (b0 | (b1 << 1));
+			return pm | (b2 << 2) | (b3 << 3);
 		}
 	}
 	return 0;
@@ -301,12 +496,12 @@ __device__ void finishSeq(const HmmDev& h, const VRegion* regs, int nReg, const 
 		trace[pos++] = s;
 		last = s;
 		if (s == 'M') {
-			const uint32_t c = ptrAt(regs, nReg, ptrBase, i, j) & 3u;
+			const uint32_t c = ptrAt(regs, nReg, ptrBase, i, j, w.q.nnInf) & 3u;
 			s = "BMID"[c];
 			i--; j--;
 		} else if (s == 'I') {
 			if (j > 0) {
-				const uint32_t c = (ptrAt(regs, nReg, ptrBase, i, j) >> 2) & 1u;
+				const uint32_t c = (ptrAt(regs, nReg, ptrBase, i, j, w.q.nnInf) >> 2) & 1u;
 				s = c ? 'I' : 'M';
 			} else { // column 0: whichMin(DP_M(i,0)+T[0](M,I), DP_I(i-1,0)+T[0](I,I)) in "BI"
 				const double a = col0M(i, w.q.cNN, w.q.cNB) + __ldg(h.tr + T_MI * h.Kp);
@@ -315,7 +510,7 @@ __device__ void finishSeq(const HmmDev& h, const VRegion* regs, int nReg, const 
 			}
 			i--;
 		} else if (s == 'D') {
-			const uint32_t c = (ptrAt(regs, nReg, ptrBase, i, j) >> 3) & 1u;
+			const uint32_t c = (ptrAt(regs, nReg, ptrBase, i, j, w.q.nnInf) >> 3) & 1u;
 			s = c ? 'D' : 'M';
 			j--;
 		} else
@@ -367,7 +562,8 @@ __device__ void finishSeq(const HmmDev& h, const VRegion* regs, int nReg, const 
 // smem per warp: codes (maxLen, padded to 8) | bnd 3*(maxLen+2) doubles | win 4 cells | winNew 4 cells | regions
 __host__ __device__ inline size_t viterbiWarpSmem(int maxLen) {
 	const size_t codes = ((size_t) maxLen + 15) / 16 * 16;
-	return codes + (size_t) 3 * (maxLen + 2) * sizeof(double) + 320 * sizeof(double) + 8 * sizeof(Cell) + 5 * sizeof(VRegion) + 16;
+	return codes + (size_t) 3 * (maxLen + 2 + 32) * sizeof(double) + 320 * sizeof(double) + 8 * sizeof(Cell) + 5 * sizeof(VRegion) + 16 +
+	       ((size_t) 2 * (maxLen + 64) + 15) / 16 * 16;
 }
 
 struct WarpSmem {
@@ -377,73 +573,88 @@ struct WarpSmem {
 	Cell* win;
 	Cell* winNew;
 	VRegion* regs;
+	uint16_t* xbox;
 };
 __device__ __forceinline__ WarpSmem carve(unsigned char* base, int maxLen) {
 	WarpSmem s;
 	const size_t codes = ((size_t) maxLen + 15) / 16 * 16;
 	s.bnd = reinterpret_cast<double*>(base);
-	s.emis = s.bnd + 3 * (maxLen + 2);
+	s.emis = s.bnd + 3 * (maxLen + 2 + 32);
 	s.win = reinterpret_cast<Cell*>(s.emis + 320);
 	s.winNew = s.win + 4;
 	s.regs = reinterpret_cast<VRegion*>(s.winNew + 4);
 	s.codes = reinterpret_cast<int8_t*>(s.regs + 5);
-	(void) codes;
+	s.xbox = reinterpret_cast<uint16_t*>(s.codes + codes);
 	return s;
 }
 
 // Pass 1: the banded plans.  Sequences without a usable plan, or whose band holds no finite path, are
 // queued for pass 2 (src/HmmUFOtu_main.cpp:86-96).
-__global__ void __launch_bounds__(HU_VIT_WARPS * 32) viterbiBandedKernel(HmmDev h, VitArgs a) {
+#ifndef HU_VIT_REGS
+#define HU_VIT_REGS 96 // 3 CTAs of 7 warps per SM
+#endif
+__global__ void __maxnreg__(HU_VIT_REGS) viterbiBandedKernel(HmmDev h, VitArgs a) {
 	extern __shared__ __align__(16) unsigned char smemRaw[];
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	const int seq = blockIdx.x * a.warpsPerBlock + warp;
-	if (seq >= a.nSeq) return;
 	WarpSmem sm = carve(smemRaw + (size_t) warp * ((viterbiWarpSmem(a.maxLen) + 15) / 16 * 16), a.maxLen);
-	const VPlan& plan = a.plans[seq];
-	const int N = plan.N;
-	const int8_t* gx = a.codes + plan.codeOff;
-	if (plan.nReg == 0) {
-		if (lane == 0) {
-			const int slot = atomicAdd(a.fullCount, 1);
-			a.fullList[slot] = seq;
-			a.rows[seq].flags = plan.flags;
-			a.rows[seq].cells = 0;
+	// persistent: every warp takes the next sequence off a shared cursor, so that long and short reads, banded and failed
+	// bands balance over the resident warps (a fixed 8-reads-per-CTA grid left the last wave half empty)
+	for (;;) {
+		int seq = 0;
+		if (lane == 0) seq = atomicAdd(a.bandCursor, 1);
+		seq = __shfl_sync(0xffffffffu, seq, 0);
+		if (seq >= a.nSeq) return;
+		const VPlan& plan = a.plans[seq];
+		const int N = plan.N;
+		const int8_t* gx = a.codes + plan.codeOff;
+		if (plan.nReg == 0) {
+			if (lane == 0) {
+				const int slot = atomicAdd(a.fullCount, 1);
+				a.fullList[slot] = seq;
+				a.rows[seq].flags = plan.flags;
+				a.rows[seq].cells = 0;
+			}
+			continue;
 		}
-		return;
-	}
-	for (int i = lane; i < N; i += 32) sm.codes[i] = gx[i];
-	if (lane < plan.nReg) sm.regs[lane] = plan.reg[lane];
-	__syncwarp();
-	WarpCtx w;
-	w.x = sm.codes;
-	setSeqConst(w.q, N, h.K, a.cNN, a.cNB, a.cEC, a.cCC);
-	w.bnd = sm.bnd; w.bndPitch = a.maxLen + 2; w.emis = sm.emis;
-	w.win = sm.win; w.winNew = sm.winNew;
-	initWindow(w, sm.regs[0].i0, sm.regs[0].j0);
-	Best best; best.v = INFINITY; best.j = 0x7fffffff; best.i = 0x7fffffff;
-	long long cells = 0;
-	for (int r = 0; r < plan.nReg; ++r) cells += sweepBox(h, sm.regs[r], r + 1 < plan.nReg, w, a.ptrs, best);
-	// warp argmin
-	for (int o = 16; o > 0; o >>= 1) {
-		Best ob;
-		ob.v = __shfl_xor_sync(0xffffffffu, best.v, o);
-		ob.j = __shfl_xor_sync(0xffffffffu, best.j, o);
-		ob.i = __shfl_xor_sync(0xffffffffu, best.i, o);
-		if (better(ob.v, ob.j, ob.i, best)) best = ob;
-		cells += __shfl_xor_sync(0xffffffffu, cells, o);
-	}
-	if (best.v == INFINITY) { // banded version failed
-		if (lane == 0) {
-			const int slot = atomicAdd(a.fullCount, 1);
-			a.fullList[slot] = seq;
-			a.rows[seq].flags = plan.flags | HU_ALIGN_FALLBACK;
-			a.rows[seq].cells = cells;
+		__syncwarp();
+		for (int i = lane; i < N; i += 32) sm.codes[i] = gx[i];
+		if (lane < plan.nReg) sm.regs[lane] = plan.reg[lane];
+		__syncwarp();
+		WarpCtx w;
+		w.x = sm.codes;
+		setSeqConst(w.q, N, h.K, a.cNN, a.cNB, a.cEC, a.cCC);
+		w.bnd = sm.bnd; w.bndPitch = a.maxLen + 2 + 32; w.emis = sm.emis;
+		w.win = sm.win; w.winNew = sm.winNew; w.xbox = sm.xbox;
+		initWindow(w, sm.regs[0].i0, sm.regs[0].j0);
+		Best best; best.v = INFINITY; best.j = 0x7fffffff; best.i = 0x7fffffff;
+		long long cells = 0;
+		for (int r = 0; r < plan.nReg; ++r) {
+			const VRegion& R = sm.regs[r];
+			cells += isLeanBox(R, w.q.nnInf) ? sweepBoxLean(h, R, r + 1 < plan.nReg, w, a.ptrs, best) : sweepBox(h, R, r + 1 < plan.nReg, w, a.ptrs, best);
 		}
-		return;
+		// warp argmin
+		for (int o = 16; o > 0; o >>= 1) {
+			Best ob;
+			ob.v = __shfl_xor_sync(0xffffffffu, best.v, o);
+			ob.j = __shfl_xor_sync(0xffffffffu, best.j, o);
+			ob.i = __shfl_xor_sync(0xffffffffu, best.i, o);
+			if (better(ob.v, ob.j, ob.i, best)) best = ob;
+			cells += __shfl_xor_sync(0xffffffffu, cells, o);
+		}
+		if (best.v == INFINITY) { // banded version failed
+			if (lane == 0) {
+				const int slot = atomicAdd(a.fullCount, 1);
+				a.fullList[slot] = seq;
+				a.rows[seq].flags = plan.flags | HU_ALIGN_FALLBACK;
+				a.rows[seq].cells = cells;
+			}
+			continue;
+		}
+		__syncwarp();
+		int8_t* arow = a.aligned ? a.aligned + (size_t) seq * h.L : NULL;
+		finishSeq(h, sm.regs, plan.nReg, a.ptrs, w, best, cells, plan.flags, gx, a.traces + plan.traceOff, arow, a.rows + seq);
+		__syncwarp();
 	}
-	__syncwarp();
-	int8_t* arow = a.aligned ? a.aligned + (size_t) seq * h.L : NULL;
-	finishSeq(h, sm.regs, plan.nReg, a.ptrs, w, best, cells, plan.flags, gx, a.traces + plan.traceOff, arow, a.rows + seq);
 }
 
 // Pass 2: full Viterbi (src/BandedHMMP7.cpp:748-780) for the queued sequences.  One CTA per sequence, persistent:
@@ -456,7 +667,7 @@ __host__ __device__ inline size_t viterbiFullSmem(int maxLen, int nW) {
 			(size_t) nW * (sizeof(Best) + sizeof(long long)) + sizeof(VRegion) + 64;
 }
 
-__global__ void __launch_bounds__(HU_VIT_WARPS * 32) viterbiFullKernel(HmmDev h, VitArgs a) {
+__global__ void __launch_bounds__(256) viterbiFullKernel(HmmDev h, VitArgs a) {
 	extern __shared__ __align__(16) unsigned char smemRaw[];
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const int nW = blockDim.x >> 5;
@@ -489,14 +700,14 @@ __global__ void __launch_bounds__(HU_VIT_WARPS * 32) viterbiFullKernel(HmmDev h,
 			VRegion R;
 			R.j0 = 1; R.j1 = K; R.i0 = 1; R.i1 = N;
 			R.strip = 0; R.pStart = R.pFrom = R.nIns = R.nDel = 0; R.useB = 1;
-			R.rowWords = (N + 7) / 8; R.pad = 0;
+			R.rowWords = N + 31; R.pad = 0; // steps per stripe slot
+			R.i0 = 1; R.j0 = 1;
 			R.ptrOff = 0;
 			*reg = R;
 		}
 		__syncthreads();
 		SeqConst q;
 		setSeqConst(q, N, K, a.cNN, a.cNB, a.cEC, a.cCC);
-		const int rowWords = (N + 7) / 8;
 		Best best; best.v = INFINITY; best.j = 0x7fffffff; best.i = 0x7fffffff;
 		long long cells = 0;
 		for (int s = warp; s < nStripes; s += nW) {
@@ -514,8 +725,7 @@ __global__ void __launch_bounds__(HU_VIT_WARPS * 32) viterbiFullKernel(HmmDev h,
 			double* out = bndAll + (size_t) (s % nW) * 3 * pitch;
 			double curM = INFINITY, curI = INFINITY, curD = INFINITY; // row 0
 			double dgM = INFINITY, dgI = INFINITY, dgD = INFINITY;    // (0, jb-1)
-			uint32_t acc = 0;
-			uint32_t* ptrCol = slab + (long long) (jj - 1) * rowWords;
+			uint4* ptrStripe = reinterpret_cast<uint4*>(slab) + (size_t) s * (N + 31);
 			const int steps = N + ncols - 1;
 			for (int t = 0; t < steps; ++t) {
 				const int i = 1 + t - lane;
@@ -535,18 +745,17 @@ __global__ void __launch_bounds__(HU_VIT_WARPS * 32) viterbiFullKernel(HmmDev h,
 						lM = lI = lD = INFINITY;
 				}
 				const bool on = colOn && i >= 1 && i <= N;
+				uint32_t code = 0;
+				double nM = INFINITY, nI = INFINITY, nD = INFINITY;
 				if (on) {
-					double nM, nI, nD;
 					const int bb = codes[i - 1];
-					const uint32_t code = cellUpdate<true>(cp, entryCand(q, i, cp.ent), emis[bb * 32 + lane], emis[(5 + bb) * 32 + lane], j == 1, cp.dOn,
+					code = cellUpdate<true>(cp, entryCand(q, i, cp.ent), emis[bb * 32 + lane], emis[(5 + bb) * 32 + lane], j == 1, cp.dOn,
 							dgM, dgI, dgD, curM, curI, lM, lD, nM, nI, nD);
 					if (i == N || q.sAllRows) cellScore(cp, q, i, j, nM, nI, best);
 					cells++;
-					acc |= code << (4 * ((i - 1) & 7));
-					if (((i - 1) & 7) == 7 || i == N) {
-						ptrCol[(i - 1) >> 3] = acc;
-						acc = 0;
-					}
+				}
+				storePtrBits(ptrStripe + t, code & 1u, code & 2u, code & 4u, code & 8u, lane);
+				if (on) {
 					if (lane == 31) {
 						out[i] = nM; out[pitch + i] = nI; out[2 * pitch + i] = nD;
 						__threadfence_block();
@@ -574,7 +783,7 @@ __global__ void __launch_bounds__(HU_VIT_WARPS * 32) viterbiFullKernel(HmmDev h,
 			}
 			WarpCtx w;
 			w.x = codes; w.q = q;
-			w.bnd = NULL; w.bndPitch = 0; w.emis = NULL; w.win = NULL; w.winNew = NULL; w.ic = w.jc = 0;
+			w.bnd = NULL; w.bndPitch = 0; w.emis = NULL; w.win = NULL; w.winNew = NULL; w.xbox = NULL; w.ic = w.jc = 0;
 			int8_t* arow = a.aligned ? a.aligned + (size_t) seq * h.L : NULL;
 			const int flags = a.rows[seq].flags;
 			const long long prior = a.rows[seq].cells;
@@ -642,12 +851,14 @@ int launchViterbi(hu_batch* b, int mode) {
 	const size_t perWarp = (viterbiWarpSmem(a.maxLen) + 15) / 16 * 16;
 	const int wpb = a.warpsPerBlock;
 	const size_t smem = perWarp * wpb;
-	const size_t smemFull = viterbiFullSmem(a.maxLen, wpb);
+	int fullWarps = 8; // the full-matrix pass pipelines the stripes of ONE sequence over the warps of a CTA: as many as its boundary buffers allow
+	while (fullWarps > 1 && viterbiFullSmem(a.maxLen, fullWarps) > 200 * 1024) fullWarps--;
+	const size_t smemFull = viterbiFullSmem(a.maxLen, fullWarps);
 	if (smem > HU_VIT_SMEM_MAX || smemFull > HU_VIT_SMEM_MAX) { setError("maxSeqLen %d too long for the Viterbi shared-memory layout", a.maxLen); return HU_ERR_ARG; }
-	HU_CUDA(cudaMemsetAsync(a.fullCount, 0, 2 * sizeof(int), b->stream)); // count + cursor
+	HU_CUDA(cudaMemsetAsync(a.fullCount, 0, 3 * sizeof(int), b->stream)); // count + cursor of the full-matrix queue, cursor of the banded pass
 	HU_CUDA(cudaMemsetAsync(a.aligned, HU_CODE_PAD & 0xff, (size_t) nSeq * h.L, b->stream));
-	viterbiBandedKernel<<<(nSeq + wpb - 1) / wpb, wpb * 32, smem, b->stream>>>(h, a);
-	viterbiFullKernel<<<b->fullSlots, wpb * 32, smemFull, b->stream>>>(h, a);
+	viterbiBandedKernel<<<std::min((nSeq + wpb - 1) / wpb, b->vitGrid), wpb * 32, smem, b->stream>>>(h, a);
+	viterbiFullKernel<<<b->fullSlots, fullWarps * 32, smemFull, b->stream>>>(h, a);
 	b->launches += 2;
 	if (b->paired) {
 		mergeMatesKernel<<<b->nReads, 128, 0, b->stream>>>(b->nReads, h.L, a.rows, b->merged, a.aligned);

@@ -138,7 +138,7 @@ typedef struct hu_place_row {
 	double dist;             /* PTLoc.dist of the seed: pDist(cNode.seq, read) over the window */
 	double wuv, ratio, wnr;
 	double loglik;           /* literal return value of placeSeq (constant per read) or the root loglik */
-	double loglikTrue;       /* sum_j log(pi . exp(loglik(r, j))) */
+	double loglikTrue;       /* sum_j log(pi . exp(loglik(r, j))): evaluated by hu_place_batch only when useTrueLoglik is set, else 0 */
 	double estLoglik;        /* estimateSeq() loglik */
 	double height, annoDist, qPlace, qTaxon;
 	int32_t outerIters, nPlaces;
@@ -182,6 +182,14 @@ int hu_batch_upload(hu_batch* b, const hu_read_batch* reads);
 /* alternative entry for the SEP stages: aligned DigitalSeq rows (n x csLen codes) + windows */
 int hu_batch_set_aligned(hu_batch* b, int32_t n, const int8_t* codes, const int32_t* start, const int32_t* end);
 
+/* Stage inputs supplied by the caller instead of by the previous stage: what the reference's free functions take as
+ * arguments when called one by one (src/HmmUFOtu_main.h:70-113); rows are nReads x maxNSeed as the getters return them.
+ * set_seeds: the seeds estimateSeq() works on; set_estimates: the vector filterPlacements() / placeSeq() work on (kept,
+ * in the given order, until hu_filter_batch runs); set_places: the vector calcQValues() / the final sort work on. */
+int hu_batch_set_seeds(hu_batch* b, const int32_t* nSeeds, const int32_t* ids);
+int hu_batch_set_estimates(hu_batch* b, const int32_t* n, const hu_place_row* rows);
+int hu_batch_set_places(hu_batch* b, const int32_t* n, const hu_place_row* rows);
+
 /* alignSeq() for every sequence of the batch: banded Viterbi, fallback, trace, aligned codes, PE merge
  * (src/HmmUFOtu_main.cpp:86-104, src/BandedHMMP7.cpp:748-1081, 1188-1213).  Device only. */
 int hu_align_batch(hu_batch* b, int mode);
@@ -189,6 +197,8 @@ int hu_align_batch(hu_batch* b, int mode);
 int hu_seed_batch(hu_batch* b, const hu_sep_params* p);
 /* estimateSeq() over the seeds + filterPlacements() (src/HmmUFOtu_main.cpp:154-173) */
 int hu_estimate_batch(hu_batch* b, const hu_sep_params* p);
+/* filterPlacements() alone over the estimates on the device (src/HmmUFOtu_main.cpp:162-173) */
+int hu_filter_batch(hu_batch* b, const hu_sep_params* p);
 /* placeSeq() over the kept placements (src/HmmUFOtu_main.cpp:175-180, src/PhyloTreeUnrooted.cpp:879-954) */
 int hu_place_batch(hu_batch* b, const hu_sep_params* p);
 /* calcQValues() + sort + bestPlace (src/HmmUFOtu_main.cpp:182-216, src/hmmufotu.cpp:725-733) */
