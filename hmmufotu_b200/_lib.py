@@ -72,7 +72,7 @@ SYMBOLS = ["hu_hmm_finalize", "hu_model_Pr", "hu_db_create", "hu_db_destroy", "h
            "hu_batch_get_best", "hu_batch_stage_ms", "hu_batch_get_stats", "hu_trace_to_align", "hu_last_error",
            "hu_version", "hu_host_alloc", "hu_host_free", "hu_batch_mark", "hu_batch_elapsed", "hu_batch_get_seed_keys",
            "hu_debug_literal_order", "hu_debug_stdsort", "hu_batch_pack_rows", "hu_batch_stream", "hu_db_get_messages_of", "hu_filter_batch", "hu_batch_set_seeds",
-           "hu_batch_set_estimates", "hu_batch_set_places"]
+           "hu_batch_set_estimates", "hu_batch_set_places", "hu_db_create_deferred", "hu_db_put_messages", "hu_db_finish", "hu_db_clone"]
 
 _LIB = None
 
@@ -92,6 +92,10 @@ def load() -> C.CDLL:
     L.hu_model_Pr.argtypes = [P(ModelDesc), f64, vp]
     L.hu_db_create.argtypes = [P(vp), P(HmmParams), P(TreeDesc), P(ModelDesc), C.c_int]
     L.hu_db_destroy.argtypes = [vp]
+    L.hu_db_create_deferred.argtypes = [P(vp), P(HmmParams), P(TreeDesc), P(ModelDesc), C.c_int]
+    L.hu_db_put_messages.argtypes = [vp, i64, vp, vp, vp]
+    L.hu_db_finish.argtypes = [vp]
+    L.hu_db_clone.argtypes = [P(vp), vp, C.c_int]
     L.hu_db_get_messages.argtypes = [vp, i64, i64, vp, vp]
     L.hu_db_get_seq.argtypes = [vp, i64, i64, vp]
     L.hu_db_get_messages_of.argtypes = [vp, i64, vp, i32, i32, vp, vp]

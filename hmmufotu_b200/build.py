@@ -68,7 +68,7 @@ def build_host(force: bool = False) -> str:
     """The C++ host layer: hmmufotu (the reference's command line over the C ABI) and its CPU test driver."""
     lib = build()
     os.makedirs(BINDIR, exist_ok=True)
-    srcs = [os.path.join(HOST, f) for f in ("hu_host.cpp", "hu_build.cpp", "hu_host.h")]
+    srcs = [os.path.join(HOST, f) for f in ("hu_host.cpp", "hu_build.cpp", "hu_facade.cpp", "hu_host.h")]
     out = []
     for name, main in (("hmmufotu", "hmmufotu.cpp"), ("hmmufotu-build", "hmmufotu-build.cpp"), ("hmmufotu-sim", "hmmufotu-sim.cpp"), ("hmmufotu-inspect", "hmmufotu-inspect.cpp"),
                        ("hu_host_test", "hu_host_test.cpp")):
@@ -76,7 +76,7 @@ def build_host(force: bool = False) -> str:
         deps = srcs + [os.path.join(HOST, main), lib]
         if force or _stale(exe, deps):
             subprocess.check_call([CXX, "-O2", "-g", "-std=c++11", "-pthread", "-Wall", "-Wextra", os.path.join(HOST, "hu_host.cpp"),
-                                   os.path.join(HOST, "hu_build.cpp"), os.path.join(HOST, main), "-L" + LIBDIR, "-lhmmufotu_b200", "-Wl,-rpath," + LIBDIR,
+                                   os.path.join(HOST, "hu_build.cpp"), os.path.join(HOST, "hu_facade.cpp"), os.path.join(HOST, main), "-L" + LIBDIR, "-lhmmufotu_b200", "-Wl,-rpath," + LIBDIR,
                                    "-Wl,-rpath,$ORIGIN/../lib", "-o", exe])
         out.append(exe)
     return out[0]

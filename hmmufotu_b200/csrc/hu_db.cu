@@ -317,6 +317,7 @@ static int devAlloc(hu_db* db, T** p, size_t n) {
 		return HU_ERR_NOMEM;
 	}
 	db->allocs.push_back(q);
+	db->allocBytes.push_back(std::max<size_t>(n, 1) * sizeof(T));
 	db->bytes += n * sizeof(T);
 	*p = (T*) q;
 	return HU_OK;
@@ -332,7 +333,9 @@ static int upload(hu_db* db, const T** dst, const T* src, size_t n) {
 	return HU_OK;
 }
 
-static int createImpl(hu_db* db, const hu_hmm_params* hp, const hu_tree_desc* td, const hu_model_desc* md) {
+static int finishMessages(hu_db* db);
+
+static int createImpl(hu_db* db, const hu_hmm_params* hp, const hu_tree_desc* td, const hu_model_desc* md, bool deferMessages) {
 	HU_TRY(buildModel(md, &db->model));
 	// ---- profile: SoA tables with a padded pitch ----
 	const int K = hp->K, Kp = ((K + 1 + 15) / 16) * 16;
@@ -390,7 +393,14 @@ static int createImpl(hu_db* db, const hu_hmm_params* hp, const hu_tree_desc* td
 			if (td->parent[x] >= 0) childList[fill[td->parent[x]]++] = x;
 	}
 	if ((td->up == NULL) != (td->dn == NULL)) { setError("up and dn must both be given or both be NULL"); return HU_ERR_ARG; }
-	if (td->up) {
+	db->deferred = deferMessages ? 1 : 0;
+	if (deferMessages) {
+		// hu_db_put_messages fills the messages later; rows nobody supplies (the root's) stay defined
+		HU_CUDA(cudaMemset(up, 0, msgN * sizeof(double)));
+		HU_CUDA(cudaMemset(dn, 0, msgN * sizeof(double)));
+		HU_CUDA(cudaMemset(upS, 0, msgN / 4 * sizeof(double)));
+		HU_CUDA(cudaMemset(dnS, 0, msgN / 4 * sizeof(double)));
+	} else if (td->up) {
 		// staged conversion of the .ptu's log-domain messages, 16 M columns (512 MB) at a time
 		const size_t nCols = msgN / 4, chunk = (size_t) 16 << 20;
 		double* stage;
@@ -474,13 +484,12 @@ static int createImpl(hu_db* db, const hu_hmm_params* hp, const hu_tree_desc* td
 		HU_TRY(devAlloc(db, &dnP, (size_t) n * (t.nWords + 1)));
 		HU_TRY(devAlloc(db, &lit, (size_t) csLen + 1));
 		HU_TRY(devAlloc(db, &md, 1));
-		scalePrefixKernel<<<(n + 7) / 8, 256>>>(upS, n, csLen, t.nWords, upP);
-		scalePrefixKernel<<<(n + 7) / 8, 256>>>(dnS, n, csLen, t.nWords, dnP);
 		litTabKernel<<<1, 32>>>(db->model, csLen, lit);
 		HU_CUDA(cudaMemcpy(md, &db->model, sizeof(Model), cudaMemcpyHostToDevice));
 		HU_CUDA(cudaGetLastError());
 		HU_CUDA(cudaDeviceSynchronize());
 		t.upP32 = upP; t.dnP32 = dnP; t.litTab = lit; t.modelDev = md;
+		if (!deferMessages) HU_TRY(finishMessages(db));
 	}
 	// ---- scan order + bit planes (after sequence inference) ----
 	std::vector<int8_t> hseq;
@@ -550,6 +559,16 @@ static int createImpl(hu_db* db, const hu_hmm_params* hp, const hu_tree_desc* td
 	return HU_OK;
 }
 
+// what depends on the messages: prefix sums of the per-column scales
+static int finishMessages(hu_db* db) {
+	TreeDev& t = db->tree;
+	scalePrefixKernel<<<(t.nNodes + 7) / 8, 256>>>(t.upS, t.nNodes, t.csLen, t.nWords, const_cast<double*>(t.upP32));
+	scalePrefixKernel<<<(t.nNodes + 7) / 8, 256>>>(t.dnS, t.nNodes, t.csLen, t.nWords, const_cast<double*>(t.dnP32));
+	HU_CUDA(cudaGetLastError());
+	HU_CUDA(cudaDeviceSynchronize());
+	return HU_OK;
+}
+
 } // namespace hu
 
 extern "C" {
@@ -597,7 +616,102 @@ int hu_model_Pr(const hu_model_desc* d, double v, double* P16) {
 	return HU_OK;
 }
 
+static int createDb(hu_db** out, const hu_hmm_params* hmm, const hu_tree_desc* tree, const hu_model_desc* model, int device, bool deferMessages);
+
 int hu_db_create(hu_db** out, const hu_hmm_params* hmm, const hu_tree_desc* tree, const hu_model_desc* model, int device) {
+	return createDb(out, hmm, tree, model, device, false);
+}
+int hu_db_create_deferred(hu_db** out, const hu_hmm_params* hmm, const hu_tree_desc* tree, const hu_model_desc* model, int device) {
+	return createDb(out, hmm, tree, model, device, true);
+}
+
+// n messages in the log domain, each 4 x csLen doubles; nodes[i] / dirs[i] say whose (0: node -> parent, 1: parent -> node)
+int hu_db_put_messages(hu_db* db, int64_t n, const int64_t* nodes, const int32_t* dirs, const double* logMsg) {
+	if (!db || !nodes || !dirs || !logMsg || n < 0) { hu::setError("hu_db_put_messages: bad arguments"); return HU_ERR_ARG; }
+	if (!db->deferred) { hu::setError("hu_db_put_messages: the database was not created with hu_db_create_deferred"); return HU_ERR_STATE; }
+	HU_CUDA(cudaSetDevice(db->device));
+	const size_t cols = (size_t) db->tree.csLen;
+	for (int64_t i = 0; i < n; ++i)
+		if (nodes[i] < 0 || nodes[i] >= db->tree.nNodes || (dirs[i] != 0 && dirs[i] != 1)) { hu::setError("hu_db_put_messages: bad node / direction at %lld", (long long) i); return HU_ERR_ARG; }
+	const int64_t chunk = std::max<int64_t>(1, (int64_t) ((256u << 20) / (cols * 32)));
+	double* stage;
+	HU_CUDA(cudaMalloc(&stage, (size_t) std::min(chunk, std::max<int64_t>(n, 1)) * cols * 4 * sizeof(double)));
+	for (int64_t i0 = 0; i0 < n; i0 += chunk) {
+		const int64_t c = std::min(chunk, n - i0);
+		HU_CUDA(cudaMemcpy(stage, logMsg + (size_t) i0 * cols * 4, (size_t) c * cols * 4 * sizeof(double), cudaMemcpyHostToDevice));
+		for (int64_t i = 0; i < c; ++i) {
+			double* E = const_cast<double*>(dirs[i0 + i] ? db->tree.dn : db->tree.up) + (size_t) nodes[i0 + i] * cols * 4;
+			double* S = const_cast<double*>(dirs[i0 + i] ? db->tree.dnS : db->tree.upS) + (size_t) nodes[i0 + i] * cols;
+			hu::toLinearKernel<<<(unsigned) ((cols + 255) / 256), 256>>>(stage + (size_t) i * cols * 4, cols, E, S);
+		}
+		HU_CUDA(cudaGetLastError());
+		HU_CUDA(cudaDeviceSynchronize());
+	}
+	cudaFree(stage);
+	return HU_OK;
+}
+int hu_db_finish(hu_db* db) {
+	if (!db) return HU_ERR_ARG;
+	HU_CUDA(cudaSetDevice(db->device));
+	int rc = hu::finishMessages(db);
+	if (rc == HU_OK) db->deferred = 0;
+	return rc;
+}
+
+// A second replica on another device, copied allocation by allocation over the peer path (NVLink where the devices are
+// peers): the database is read from disk and converted once, then replicated at link speed.
+int hu_db_clone(hu_db** out, hu_db* src, int device) {
+	if (!out || !src) { hu::setError("hu_db_clone: NULL argument"); return HU_ERR_ARG; }
+	if (src->deferred) { hu::setError("hu_db_clone: the source is not finished (hu_db_finish)"); return HU_ERR_STATE; }
+	HU_CUDA(cudaSetDevice(device));
+	{
+		int rcA = hu::configViterbiKernels();
+		if (rcA == HU_OK) rcA = hu::configSeedKernels();
+		if (rcA == HU_OK) rcA = hu::configEstimateKernels();
+		if (rcA == HU_OK) rcA = hu::configPlaceKernels();
+		if (rcA != HU_OK) return rcA;
+	}
+	hu_db* db = new hu_db(*src); // host-side fields; the device pointers are remapped below
+	db->device = device;
+	db->allocs.clear();
+	for (size_t i = 0; i < src->allocs.size(); ++i) {
+		void* q = NULL;
+		cudaError_t e = cudaMalloc(&q, src->allocBytes[i]);
+		if (e == cudaSuccess) e = cudaMemcpyPeer(q, device, src->allocs[i], src->device, src->allocBytes[i]);
+		if (e != cudaSuccess) {
+			hu::setError("hu_db_clone: allocation %zu of %zu bytes: %s", i, src->allocBytes[i], cudaGetErrorString(e));
+			if (q) cudaFree(q);
+			for (size_t k = 0; k < db->allocs.size(); ++k) cudaFree(db->allocs[k]);
+			delete db;
+			return e == cudaErrorMemoryAllocation ? HU_ERR_NOMEM : HU_ERR_CUDA;
+		}
+		db->allocs.push_back(q);
+	}
+	HU_CUDA(cudaDeviceSynchronize());
+	// every device pointer of the replica points into one of the source's allocations: same offset in the copy
+	struct Remap {
+		const hu_db* s; const hu_db* d;
+		const void* operator()(const void* p) const {
+			if (!p) return p;
+			for (size_t i = 0; i < s->allocs.size(); ++i) {
+				const char* b = (const char*) s->allocs[i];
+				if ((const char*) p >= b && (const char*) p < b + s->allocBytes[i]) return (const char*) d->allocs[i] + ((const char*) p - b);
+			}
+			return NULL;
+		}
+	} rm = {src, db};
+#define HU_RM(field) db->field = (decltype(db->field)) rm(src->field)
+	HU_RM(hmm.eM); HU_RM(hmm.eI); HU_RM(hmm.tr); HU_RM(hmm.ent); HU_RM(hmm.ext); HU_RM(hmm.p2cs);
+	HU_RM(tree.parent); HU_RM(tree.blen); HU_RM(tree.height); HU_RM(tree.seq); HU_RM(tree.taxon);
+	HU_RM(tree.up); HU_RM(tree.dn); HU_RM(tree.upS); HU_RM(tree.dnS); HU_RM(tree.upP32); HU_RM(tree.dnP32);
+	HU_RM(tree.litTab); HU_RM(tree.modelDev); HU_RM(tree.planes); HU_RM(tree.seqT); HU_RM(tree.colK);
+	HU_RM(tree.scanNode); HU_RM(tree.posOfSlot); HU_RM(tree.nodeOfPos); HU_RM(tree.inv2N);
+#undef HU_RM
+	*out = db;
+	return HU_OK;
+}
+
+static int createDb(hu_db** out, const hu_hmm_params* hmm, const hu_tree_desc* tree, const hu_model_desc* model, int device, bool deferMessages) {
 	if (!out || !hmm || !tree || !model) { hu::setError("hu_db_create: NULL argument"); return HU_ERR_ARG; }
 	int nDev = 0;
 	cudaError_t e = cudaGetDeviceCount(&nDev);
@@ -616,7 +730,7 @@ int hu_db_create(hu_db** out, const hu_hmm_params* hmm, const hu_tree_desc* tree
 	}
 	hu_db* db = new hu_db();
 	db->device = device;
-	int rc = hu::createImpl(db, hmm, tree, model);
+	int rc = hu::createImpl(db, hmm, tree, model, deferMessages);
 	if (rc != HU_OK) {
 		hu_db_destroy(db);
 		return rc;

@@ -262,11 +262,13 @@ struct hu_db {
 	hu::HmmDev hmm;
 	hu::TreeDev tree;
 	std::vector<void*> allocs;
+	std::vector<size_t> allocBytes; // size of allocs[i] (hu_db_clone copies the replica allocation by allocation)
 	int64_t bytes;
+	int deferred;                   // created without messages: hu_db_put_messages + hu_db_finish complete it
 	// host copies used by the facades / stage planning
 	int K, L;
 	std::vector<int> p2cs;
 	std::vector<double> heightHost;
 	std::vector<int> scanNodeHost; // slot -> node id of the seed scan order (-1: padding)
-	hu_db() : device(0), bytes(0), K(0), L(0) {}
+	hu_db() : device(0), bytes(0), deferred(0), K(0), L(0) {}
 };

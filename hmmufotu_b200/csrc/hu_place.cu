@@ -3,7 +3,7 @@
 // Felsenstein's single-branch EM (cpp:749-798) and the dGamma-mixed message rebuilds (cpp:320-346),
 // then calcQValues + the final sort (src/HmmUFOtu_main.cpp:182-216, src/hmmufotu.cpp:725-733).
 //
-// One warp per (read, placement), persistent over the item space.  Everything is done in the linear domain
+// One warp, or one four-warp CTA, per (read, placement), persistent over the item space.  Everything is done in the linear domain
 // (hu_internal.cuh, expNorm): with e^U_j, e^V_j the max-normalised exponentials of the two stored messages,
 //   msg(r->n)_j ~ mean_k (P(lu r_k) e^U_j) * (P(lv r_k) e^V_j)           (the per-column scales cancel below)
 //   rho_j = e^{A_j - B_j} = pi.(msg * n_j) / ((pi.msg) (pi.n_j))          A, B of cpp:769-770
@@ -18,7 +18,8 @@
 namespace hu {
 
 #define HU_PLACE_WARPS 4
-#define HU_PLACE_CAPW 1536 // columns of rho kept in shared memory per warp (12 KB); wider windows use a global slab
+#define HU_PLACE_THREADS (HU_PLACE_WARPS * 32)
+#define HU_PLACE_CAPW 1536 // columns of rho kept in shared memory per group of warps (12 KB); wider windows use a global slab
 #define HU_BRANCH_EPS 1e-5 // src/PhyloTreeUnrooted.cpp:70
 #define HU_MAX_ITER 100    // src/PhyloTreeUnrooted.cpp:71
 
@@ -87,10 +88,45 @@ __device__ __forceinline__ double rcpFast(double x) {
 	return fma(r, fma(-x, r, 1.0), r);
 }
 
+// An item is worked on by a GROUP of WPI warps (1 or 4) of a four-warp CTA.  Group-wide sums in a fixed order (lane tree inside
+// a warp, then the warp totals pairwise): every thread of the group gets the same bits, so the iteration control that depends
+// on them stays uniform.  `red` is double buffered: one barrier per sum.
+struct PlaceRed {
+	double d[2][HU_PLACE_WARPS];
+	int i[2][HU_PLACE_WARPS];
+};
+template <int WPI>
+__device__ __forceinline__ void groupSync(int group) {
+	if (WPI == 1) __syncwarp();
+	else asm volatile("bar.sync %0, %1;" ::"r"(1 + group), "r"(WPI * 32) : "memory");
+}
+template <int WPI>
+__device__ __forceinline__ double groupSum(double v, PlaceRed& red, int& flip, int group, int gwarp) {
+	v = warpSum(v);
+	if (WPI == 1) return v;
+	if ((threadIdx.x & 31) == 0) red.d[flip][gwarp] = v;
+	groupSync<WPI>(group);
+	const double s = (red.d[flip][0] + red.d[flip][1]) + (red.d[flip][2] + red.d[flip][3]);
+	flip ^= 1;
+	return s;
+}
+template <int WPI>
+__device__ __forceinline__ int groupSumInt(int v, PlaceRed& red, int& flip, int group, int gwarp) {
+	for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+	if (WPI == 1) { __syncwarp(); return v; }
+	if ((threadIdx.x & 31) == 0) red.i[flip][gwarp] = v;
+	groupSync<WPI>(group);
+	const int s = (red.i[flip][0] + red.i[flip][1]) + (red.i[flip][2] + red.i[flip][3]);
+	flip ^= 1;
+	return s;
+}
+
 // Felsenstein EM for one branch given rho_j, src/PhyloTreeUnrooted.cpp:749-798:
-// p <- (1/N) sum_j e^B p0 / (e^A q0 + e^B p0) = (1/N) sum_j p0 / (rho_j q0 + p0)
-__device__ __noinline__ double emBranch(const double* __restrict__ rho, int W, int nValid, double wInit, double cap, int* itersOut) {
-	const int lane = threadIdx.x & 31;
+// p <- (1/N) sum_j e^B p0 / (e^A q0 + e^B p0) = (1/N) sum_j p0 / (rho_j q0 + p0); the whole group works on one branch
+template <int WPI>
+__device__ __noinline__ double emBranch(const double* __restrict__ rho, int W, int nValid, double wInit, double cap, int* itersOut, PlaceRed& red, int& flip,
+		int group, int gtid) {
+	const int NT = WPI * 32;
 	double q0 = exp(-wInit), p0 = 1 - q0;
 	double p = p0, q = q0;
 	int it = 0;
@@ -98,20 +134,20 @@ __device__ __noinline__ double emBranch(const double* __restrict__ rho, int W, i
 		double s = 0;
 		if (p0 > 1e-200 && q0 >= 0) {
 			double s1 = 0; // two accumulators: independent dependency chains
-			int c = lane;
-			for (; c + 32 < W; c += 64) {
+			int c = gtid;
+			for (; c + NT < W; c += 2 * NT) {
 				s = fma(p0, rcpFast(fma(rho[c], q0, p0)), s);
-				s1 = fma(p0, rcpFast(fma(rho[c + 32], q0, p0)), s1);
+				s1 = fma(p0, rcpFast(fma(rho[c + NT], q0, p0)), s1);
 			}
 			if (c < W) s = fma(p0, rcpFast(fma(rho[c], q0, p0)), s);
 			s += s1;
 		} else { // degenerate branch length: plain division keeps the reference's NaN / inf behaviour
-			for (int c = lane; c < W; c += 32) {
+			for (int c = gtid; c < W; c += NT) {
 				const double rh = rho[c];
 				if (rh < HU_RHO_SKIP) s += p0 / (rh * q0 + p0);
 			}
 		}
-		p = warpSum(s) / (double) nValid;
+		p = groupSum<WPI>(s, red, flip, group, gtid >> 5) / (double) nValid;
 		q = 1 - p;
 		if (fabs(log(q) - log(q0)) < HU_BRANCH_EPS) { it++; break; }
 		p0 = p; q0 = q;
@@ -122,21 +158,34 @@ __device__ __noinline__ double emBranch(const double* __restrict__ rho, int W, i
 	return w;
 }
 
-__global__ void __launch_bounds__(HU_PLACE_WARPS * 32) placeKernel(PlaceArgs a, TreeDev t, Model m) {
+// WPI warps per (read, placement), persistent over the item space.  WPI = 1 (amplicon reads, merged pairs): one warp per item,
+// four items per CTA, no block barriers.  WPI = 4 (long reads, windows of thousands of columns): the columns of an item are
+// spread over the four warps, so that a pass over the window is W / 128 columns per thread and the items in flight -- hence
+// the message windows that are re-streamed 2 iters times -- are four times fewer (they stay in L2 between the passes); the
+// price is one named barrier per EM iteration.  Measured (profiles/r2_summary.md): C3 6.2 ms (WPI 1) vs 8.9 (WPI 4); C5 9.2 vs 5.7.
+template <int WPI>
+__global__ void __launch_bounds__(HU_PLACE_THREADS, 4) placeKernel(PlaceArgs a, TreeDev t, Model m) {
 	extern __shared__ __align__(16) unsigned char smemRaw[];
-	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	constexpr int NT = WPI * 32, GROUPS = HU_PLACE_WARPS / WPI;
+	__shared__ PlaceRed redAll[GROUPS];
+	__shared__ int sItem[GROUPS];
+	const int group = (threadIdx.x >> 5) / WPI, gtid = threadIdx.x - group * NT, gwarp = gtid >> 5;
+	PlaceRed& red = redAll[group];
 	const int KK = m.dgK > 0 ? m.dgK : 1;
-	double* wsP = reinterpret_cast<double*>(smemRaw) + (size_t) warp * placeWarpDoubles(KK);
-	double* wsNP = wsP + 3 * KK * 16;
-	double* rhoS = reinterpret_cast<double*>(smemRaw) + (size_t) HU_PLACE_WARPS * placeWarpDoubles(KK) + (size_t) warp * a.capW;
-	const int slot = blockIdx.x * HU_PLACE_WARPS + warp;
+	const int groupDoubles = placeWarpDoubles(KK) + a.capW;
+	double* wsP = reinterpret_cast<double*>(smemRaw) + (size_t) group * groupDoubles; // P[3][KK][16] = P(lu r_k), P(lv r_k), P(ln r_k)
+	double* wsNP = wsP + 3 * KK * 16;                    // NP[KK][5][4] = P(ln r_k) applied to the leaf vector of base b / gap
+	double* rhoS = wsP + placeWarpDoubles(KK);
+	const int slot = blockIdx.x * GROUPS + group;
 	const int total = a.nReads * a.maxNSeed;
+	int flip = 0;
 	double piSq = 0; // pi . pi: (pi . n) for a gap column of the read
 	for (int k = 0; k < 4; ++k) piSq += m.pi[k] * m.pi[k];
 	for (;;) {
-		int item = 0;
-		if (lane == 0) item = atomicAdd(a.cursor, 1);
-		item = __shfl_sync(0xffffffffu, item, 0);
+		groupSync<WPI>(group);
+		if (gtid == 0) sItem[group] = atomicAdd(a.cursor, 1);
+		groupSync<WPI>(group);
+		const int item = sItem[group];
 		if (item >= total) return;
 		const int r = item / a.maxNSeed, idx = item % a.maxNSeed;
 		if (a.winStart[r] < 0 || idx >= a.nKept[r]) continue;
@@ -155,15 +204,15 @@ __global__ void __launch_bounds__(HU_PLACE_WARPS * 32) placeKernel(PlaceArgs a, 
 		int iter = 0, emIters = 0;
 		for (iter = 0; iter < HU_MAX_ITER && 0 <= wur && wur <= w0j; ++iter) {
 			// ---- msg(r->n) from u and v, then optimise the n-r branch (cap 1) ----
-			__syncwarp();
-			fillP(t.modelDev, wsP, KK, lu, lv, ln, 3);
-			__syncwarp();
+			groupSync<WPI>(group);
+			if (gwarp == 0) fillP(t.modelDev, wsP, KK, lu, lv, ln, 3);
+			groupSync<WPI>(group);
 			int nValid = 0;
 			ColPrefetch pf;
-			pf.init(U, V, x, lane, W);
-			for (int cI = lane; cI < W; cI += 32) {
+			pf.init(U, V, x, gtid, W);
+			for (int cI = gtid; cI < W; cI += NT) {
 				double eu[4], ev[4], ya[4], yb[4], g[4] = {0, 0, 0, 0};
-				const int b = pf.next(U, V, x, cI + 32, W, eu, ev);
+				const int b = pf.next(U, V, x, cI + NT, W, eu, ev);
 				for (int k = 0; k < KK; ++k) {
 					matVec4(wsP + (0 * KK + (k)) * 16, eu, ya);
 					matVec4(wsP + (1 * KK + (k)) * 16, ev, yb);
@@ -176,27 +225,26 @@ __global__ void __launch_bounds__(HU_PLACE_WARPS * 32) placeKernel(PlaceArgs a, 
 				nValid += rh == rh;
 				rho[cI] = rh == rh ? fmin(rh, HU_RHO_SKIP) : HU_RHO_SKIP;
 			}
-			for (int o = 16; o > 0; o >>= 1) nValid += __shfl_xor_sync(0xffffffffu, nValid, o);
-			__syncwarp();
-			wnr = emBranch(rho, W, nValid, ln, 1.0, &emIters);
+			nValid = groupSumInt<WPI>(nValid, red, flip, group, gwarp); // its barrier also publishes rho
+			wnr = emBranch<WPI>(rho, W, nValid, ln, 1.0, &emIters, red, flip, group, gtid);
 			ln = wnr;
 			// ---- msg(r->u) from v and n, then optimise the u-r branch (cap w0) ----
-			__syncwarp();
-			fillP(t.modelDev, wsP, KK, lu, lv, ln, 4);
-			__syncwarp();
-			for (int q = lane; q < KK * 5; q += 32) {
+			groupSync<WPI>(group);
+			if (gwarp == 0) fillP(t.modelDev, wsP, KK, lu, lv, ln, 4);
+			groupSync<WPI>(group);
+			for (int q = gtid; q < KK * 5; q += NT) {
 				const int k = q / 5, b = q % 5;
 				double n[4], y[4];
 				leafLin(m, b < 4 ? b : -1, n);
 				matVec4(wsP + (2 * KK + (k)) * 16, n, y);
 				for (int i = 0; i < 4; ++i) wsNP[(k * 5 + b) * 4 + i] = y[i];
 			}
-			__syncwarp();
+			groupSync<WPI>(group);
 			nValid = 0;
-			pf.init(U, V, x, lane, W);
-			for (int cI = lane; cI < W; cI += 32) {
+			pf.init(U, V, x, gtid, W);
+			for (int cI = gtid; cI < W; cI += NT) {
 				double eu[4], ev[4], yb[4], g[4] = {0, 0, 0, 0};
-				const int b = pf.next(U, V, x, cI + 32, W, eu, ev);
+				const int b = pf.next(U, V, x, cI + NT, W, eu, ev);
 				for (int k = 0; k < KK; ++k) {
 					matVec4(wsP + (1 * KK + (k)) * 16, ev, yb);
 					const double* np = wsNP + (k * 5 + (b >= 0 ? b : 4)) * 4;
@@ -208,9 +256,8 @@ __global__ void __launch_bounds__(HU_PLACE_WARPS * 32) placeKernel(PlaceArgs a, 
 				nValid += rh == rh;
 				rho[cI] = rh == rh ? fmin(rh, HU_RHO_SKIP) : HU_RHO_SKIP;
 			}
-			for (int o = 16; o > 0; o >>= 1) nValid += __shfl_xor_sync(0xffffffffu, nValid, o);
-			__syncwarp();
-			wur = emBranch(rho, W, nValid, lu, w0j, &emIters);
+			nValid = groupSumInt<WPI>(nValid, red, flip, group, gwarp);
+			wur = emBranch<WPI>(rho, W, nValid, lu, w0j, &emIters, red, flip, group, gtid);
 			lu = wur;
 			wvr = w0j - wur;
 			lv = wvr; // msg(r->v) is rebuilt by the reference but never read afterwards
@@ -222,38 +269,39 @@ __global__ void __launch_bounds__(HU_PLACE_WARPS * 32) placeKernel(PlaceArgs a, 
 		}
 		// ---- intended root log-likelihood: sum_j log(pi . exp(loglik(r, j))) ----
 		// One more pass over the two message windows: only when it is asked for (the literal placeSeq value, SURVEY.md F6,
-		// needs none of it; the pass was 1 / (2 iters + 1) of this kernel's DRAM traffic)
+		// needs none of it)
 		double tl = 0;
 		if (a.useTrue) {
-		__syncwarp();
-		fillP(t.modelDev, wsP, KK, lu, lv, ln, 7);
-		__syncwarp();
-		for (int q = lane; q < KK * 5; q += 32) {
-			const int k = q / 5, b = q % 5;
-			double n[4], y[4];
-			leafLin(m, b < 4 ? b : -1, n);
-			matVec4(wsP + (2 * KK + (k)) * 16, n, y);
-			for (int i = 0; i < 4; ++i) wsNP[(k * 5 + b) * 4 + i] = y[i];
-		}
-		__syncwarp();
-		tl = windowScale(t.upS, t.upP32, c, t.csLen, t.nWords, start, end, lane)
-		   + windowScale(t.dnS, t.dnP32, c, t.csLen, t.nWords, start, end, lane);
-		ColPrefetch pf;
-		pf.init(U, V, x, lane, W);
-		for (int cI = lane; cI < W; cI += 32) {
-			double eu[4], ev[4], ya[4], yb[4], g[4] = {0, 0, 0, 0};
-			const int b = pf.next(U, V, x, cI + 32, W, eu, ev);
-			for (int k = 0; k < KK; ++k) {
-				matVec4(wsP + (0 * KK + (k)) * 16, eu, ya);
-				matVec4(wsP + (1 * KK + (k)) * 16, ev, yb);
-				const double* np = wsNP + (k * 5 + (b >= 0 ? b : 4)) * 4;
-				for (int i = 0; i < 4; ++i) g[i] += (ya[i] * yb[i]) * np[i];
+			groupSync<WPI>(group);
+			if (gwarp == 0) fillP(t.modelDev, wsP, KK, lu, lv, ln, 7);
+			groupSync<WPI>(group);
+			for (int q = gtid; q < KK * 5; q += NT) {
+				const int k = q / 5, b = q % 5;
+				double n[4], y[4];
+				leafLin(m, b < 4 ? b : -1, n);
+				matVec4(wsP + (2 * KK + (k)) * 16, n, y);
+				for (int i = 0; i < 4; ++i) wsNP[(k * 5 + b) * 4 + i] = y[i];
 			}
-			tl += log(dotPi(m, g) / (double) KK);
+			groupSync<WPI>(group);
+			if (gwarp == 0)
+				tl = windowScale(t.upS, t.upP32, c, t.csLen, t.nWords, start, end, gtid)
+				   + windowScale(t.dnS, t.dnP32, c, t.csLen, t.nWords, start, end, gtid);
+			ColPrefetch pf;
+			pf.init(U, V, x, gtid, W);
+			for (int cI = gtid; cI < W; cI += NT) {
+				double eu[4], ev[4], ya[4], yb[4], g[4] = {0, 0, 0, 0};
+				const int b = pf.next(U, V, x, cI + NT, W, eu, ev);
+				for (int k = 0; k < KK; ++k) {
+					matVec4(wsP + (0 * KK + (k)) * 16, eu, ya);
+					matVec4(wsP + (1 * KK + (k)) * 16, ev, yb);
+					const double* np = wsNP + (k * 5 + (b >= 0 ? b : 4)) * 4;
+					for (int i = 0; i < 4; ++i) g[i] += (ya[i] * yb[i]) * np[i];
+				}
+				tl += log(dotPi(m, g) / (double) KK);
+			}
+			tl = groupSum<WPI>(tl, red, flip, group, gwarp);
 		}
-		tl = warpSum(tl);
-		}
-		if (lane == 0) {
+		if (gtid == 0) {
 			hu_place_row row = e;
 			// literal return value: treeLoglik over a root message of INVALID_LOGLIK = 1, tabulated per W
 			row.loglik = t.litTab[W];
@@ -349,7 +397,8 @@ __global__ void finalizeKernel(int nReads, const int* __restrict__ winStart, con
 
 int configPlaceKernels() {
 	const size_t smem = (size_t) HU_PLACE_WARPS * (placeWarpDoubles(HU_MAX_DG) + HU_PLACE_CAPW) * sizeof(double);
-	HU_CUDA(cudaFuncSetAttribute(placeKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+	HU_CUDA(cudaFuncSetAttribute(placeKernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+	HU_CUDA(cudaFuncSetAttribute(placeKernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
 	return HU_OK;
 }
 
@@ -366,8 +415,11 @@ int launchPlace(hu_batch* b, const hu_sep_params* p) {
 	const int ctasPerSm = 4;
 	const int grid = sms * ctasPerSm;
 	const int KKh = db->model.dgK > 0 ? db->model.dgK : 1;
-	const size_t smem = (size_t) HU_PLACE_WARPS * (placeWarpDoubles(KKh) + HU_PLACE_CAPW) * sizeof(double);
-	// global slab for windows wider than the shared-memory capacity
+	// long reads (windows of thousands of columns): four warps per item; amplicon reads and merged pairs: one warp per item
+	const bool wideItems = b->maxSeqLen > 700;
+	const int groups = wideItems ? 1 : HU_PLACE_WARPS;
+	const size_t smem = (size_t) groups * (placeWarpDoubles(KKh) + HU_PLACE_CAPW) * sizeof(double);
+	// global slab for windows wider than the shared-memory capacity, one row per group of warps
 	const size_t slabBytes = (size_t) grid * HU_PLACE_WARPS * db->tree.csLen * sizeof(double);
 	if (!b->placeSlab) {
 		void* q = NULL;
@@ -376,7 +428,9 @@ int launchPlace(hu_batch* b, const hu_sep_params* p) {
 		b->placeSlab = (double*) q;
 	}
 	a.slab = b->placeSlab;
-	placeKernel<<<grid, HU_PLACE_WARPS * 32, smem, b->stream>>>(a, db->tree, db->model);
+	HU_CUDA(cudaMemsetAsync(a.cursor, 0, sizeof(int), b->stream)); // the stage can run on its own (per-call facades), not only after hu_estimate_batch
+	if (wideItems) placeKernel<4><<<grid, HU_PLACE_THREADS, smem, b->stream>>>(a, db->tree, db->model);
+	else placeKernel<1><<<grid, HU_PLACE_THREADS, smem, b->stream>>>(a, db->tree, db->model);
 	HU_CUDA(cudaEventRecord(b->ev[6], b->stream));
 	b->launches += 1;
 	HU_CUDA(cudaGetLastError());

@@ -292,8 +292,8 @@ __device__ __forceinline__ uint32_t ldsU16(uint32_t a) { uint32_t v; asm volatil
 // One wavefront step.  bndIn: shared address of the boundary triple lane 0 reads at this step (row offset t + 1);
 // xoA: shared address of this lane's emission offset for this step; emisA: shared address of this lane's slot in the
 // emission table; d = t - lane: the lane's row offset; rowsEff: rows of the box (0 for a lane beyond the stripe's columns).
-template <bool TAIL>
-__device__ __forceinline__ void leanStep(LeanState& q, const ColLean& cp, uint32_t bndIn, uint32_t xoA, uint32_t emisA, uint4* __restrict__ ptrStep, int d, int lane,
+template <bool TAIL, bool CORNER>
+__device__ __forceinline__ void leanStep(LeanState& q, const ColLean& cp, uint32_t bndIn, uint32_t bndOut, uint32_t xoA, uint32_t emisA, uint4* __restrict__ ptrStep, int d, int lane,
 		uint32_t rowsEff, const HmmDev& h, const VRegion& R, bool hasNext, WarpCtx& w, int j, int jj, Best& best) {
 	double lM = __shfl_up_sync(0xffffffffu, q.curM, 1);
 	double lI = __shfl_up_sync(0xffffffffu, q.curI, 1);
@@ -321,9 +321,10 @@ __device__ __forceinline__ void leanStep(LeanState& q, const ColLean& cp, uint32
 	const bool pd = dD < dM;
 	const double nD = pred ? (pd ? dD : dM) : INFINITY;
 	storePtrBits(ptrStep, pa, pb, pi, pd, lane);
-	// lane 31 hands its column to the next stripe: boundary entry of row offset d + 1, i.e. 31 entries behind lane 0's read
-	asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.s32 p, %0, 31;\n\tsetp.lt.and.u32 p, %1, %2, p;\n\t@p st.shared.f64 [%3+-744], %4;\n\t@p st.shared.f64 [%3+-736], %5;\n\t@p st.shared.f64 [%3+-728], %6;\n\t}"
-	             :: "r"(lane), "r"((uint32_t) d), "r"(rowsEff), "r"(bndIn), "d"(nM), "d"(nI), "d"(nD) : "memory");
+	// lane 31 hands its column to the next stripe: boundary entry of row offset d + 1 (bndOut: its shared address; in the banded
+	// sweep the same array, 31 entries behind lane 0's read)
+	asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.s32 p, %0, 31;\n\tsetp.lt.and.u32 p, %1, %2, p;\n\t@p st.shared.f64 [%3], %4;\n\t@p st.shared.f64 [%3+8], %5;\n\t@p st.shared.f64 [%3+16], %6;\n\t}"
+	             :: "r"(lane), "r"((uint32_t) d), "r"(rowsEff), "r"(bndOut), "d"(nM), "d"(nI), "d"(nD) : "memory");
 	if (TAIL && pred) {
 		const int i = R.i0 + d;
 		// the end corner is recomputed by the next box: its S candidate is taken there
@@ -332,9 +333,50 @@ __device__ __forceinline__ void leanStep(LeanState& q, const ColLean& cp, uint32
 			full.ext = __ldg(h.ext + jj); full.tIMj = __ldg(h.tr + T_IM * h.Kp + jj);
 			cellScore(full, w.q, i, j, nM, nI, best);
 		}
-		if (i >= R.i1 - 1 && j >= R.j1 - 1) {
+		if (CORNER && i >= R.i1 - 1 && j >= R.j1 - 1) {
 			Cell c; c.M = nM; c.I = nI; c.D = nD;
 			w.winNew[(i - (R.i1 - 1)) * 2 + (j - (R.j1 - 1))] = c;
+		}
+	}
+	q.curM = nM; q.curI = nI; q.curD = nD;
+	q.dgM = lM; q.dgI = lI; q.dgD = lD;
+}
+
+// The lean step inside the full-matrix pass: the region (1..N, 1..K) is not a lean box (it holds row 1 and column 1), so its
+// back-pointers are in the general encoding: the DP_M index 1 / 2 / 3 instead of the two raw compare outcomes.
+template <bool TAIL>
+__device__ __forceinline__ void leanStepFull(LeanState& q, const ColLean& cp, uint32_t bndIn, uint32_t bndOut, uint32_t xoA, uint32_t emisA, uint4* __restrict__ ptrStep, int d, int lane,
+		uint32_t rowsEff, const HmmDev& h, const VRegion& R, WarpCtx& w, int j, int jj, Best& best) {
+	double lM = __shfl_up_sync(0xffffffffu, q.curM, 1);
+	double lI = __shfl_up_sync(0xffffffffu, q.curI, 1);
+	double lD = __shfl_up_sync(0xffffffffu, q.curD, 1);
+	asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.s32 p, %3, 0;\n\t@p ld.shared.f64 %0, [%4];\n\t@p ld.shared.f64 %1, [%4+8];\n\t@p ld.shared.f64 %2, [%4+16];\n\t}"
+	             : "+d"(lM), "+d"(lI), "+d"(lD) : "r"(lane), "r"(bndIn));
+	const bool pred = (uint32_t) d < rowsEff;
+	const uint32_t e = emisA + ldsU16(xoA);
+	const double eM = ldsF64(e), eI = ldsF64(e + 5 * 32 * 8);
+	const double cM = q.dgM + cp.tMMp, cI = q.dgI + cp.tIMp, cD = q.dgD + cp.tDMp;
+	const bool pa = cI < cM;
+	double mn = pa ? cI : cM;
+	const bool pb = cD < mn;
+	mn = pb ? cD : mn;
+	const double nM = eM + mn;
+	const double iM = q.curM + cp.tMI, iI = q.curI + cp.tII;
+	const bool pi = iI < iM;
+	const double nI = eI + (pi ? iI : iM);
+	const double dM = lM + cp.tMDp, dD = lD + cp.tDDp;
+	const bool pd = dD < dM;
+	const double nD = pred ? (pd ? dD : dM) : INFINITY;
+	// general encoding of the DP_M pointer: 1 (M), 2 (I), 3 (D) -> bit 0 = b | !a, bit 1 = a | b; a traced cell is never all +inf
+	storePtrBits(ptrStep, pb || !pa, pa || pb, pi, pd, lane);
+	asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.s32 p, %0, 31;\n\tsetp.lt.and.u32 p, %1, %2, p;\n\t@p st.shared.f64 [%3], %4;\n\t@p st.shared.f64 [%3+8], %5;\n\t@p st.shared.f64 [%3+16], %6;\n\t}"
+	             :: "r"(lane), "r"((uint32_t) d), "r"(rowsEff), "r"(bndOut), "d"(nM), "d"(nI), "d"(nD) : "memory");
+	if (TAIL && pred) {
+		const int i = R.i0 + d;
+		if (i == w.q.N || w.q.sAllRows) {
+			ColParams full;
+			full.ext = __ldg(h.ext + jj); full.tIMj = __ldg(h.tr + T_IM * h.Kp + jj);
+			cellScore(full, w.q, i, j, nM, nI, best);
 		}
 	}
 	q.curM = nM; q.curI = nI; q.curD = nD;
@@ -404,11 +446,11 @@ __device__ long long sweepBoxLean(const HmmDev& h, const VRegion& Rsm, bool hasN
 		for (; t < bulk; t += HU_LEAN_UNROLL) {
 #pragma unroll
 			for (int k = 0; k < HU_LEAN_UNROLL; ++k)
-				leanStep<false>(q, cp, bndIn + 24 * k, xoA + 2 * k, emisA, ptrStep + k, d + k, lane, rowsEff, h, R, hasNext, w, j, jj, best);
+				leanStep<false, true>(q, cp, bndIn + 24 * k, bndIn + 24 * k - 744, xoA + 2 * k, emisA, ptrStep + k, d + k, lane, rowsEff, h, R, hasNext, w, j, jj, best);
 			bndIn += 24 * HU_LEAN_UNROLL; xoA += 2 * HU_LEAN_UNROLL; ptrStep += HU_LEAN_UNROLL; d += HU_LEAN_UNROLL;
 		}
 		for (; t < steps; ++t) {
-			leanStep<true>(q, cp, bndIn, xoA, emisA, ptrStep, d, lane, rowsEff, h, R, hasNext, w, j, jj, best);
+			leanStep<true, true>(q, cp, bndIn, bndIn - 744, xoA, emisA, ptrStep, d, lane, rowsEff, h, R, hasNext, w, j, jj, best);
 			bndIn += 24; xoA += 2; ptrStep += 1; d += 1;
 		}
 		__syncwarp();
@@ -663,23 +705,28 @@ __global__ void __maxnreg__(HU_VIT_REGS) viterbiBandedKernel(HmmDev h, VitArgs a
 // through a ring of shared-memory buffers, a per-stripe progress counter orders the hand-over.  Same cell
 // code as the banded pass (cellUpdate), so costs and back-pointers are bit-identical to a single-warp sweep.
 __host__ __device__ inline size_t viterbiFullSmem(int maxLen, int nW) {
-	return ((size_t) maxLen + 15) / 16 * 16 + (size_t) nW * (3 * (maxLen + 2) + 320) * sizeof(double) + 2048 * sizeof(int) +
-			(size_t) nW * (sizeof(Best) + sizeof(long long)) + sizeof(VRegion) + 64;
+	return ((size_t) maxLen + 15) / 16 * 16 + ((size_t) 2 * (maxLen + 64) + 15) / 16 * 16 + (size_t) nW * (3 * (maxLen + 2 + 32) + 320) * sizeof(double) +
+			2048 * sizeof(int) + (size_t) nW * (sizeof(Best) + sizeof(long long)) + sizeof(VRegion) + 64;
 }
 
+// Round 2: a stripe beyond the first (columns >= 33) runs its first 32 steps -- the only ones that can touch read position 1,
+// where the begin state enters -- with the general cell code and everything after that with the lean step of the banded sweep
+// (same arithmetic; see leanStep); the boundary columns are (M, I, D) triples; the hand-over between consecutive stripes is
+// checked and published once per block of four steps instead of every step.
 __global__ void __launch_bounds__(256) viterbiFullKernel(HmmDev h, VitArgs a) {
 	extern __shared__ __align__(16) unsigned char smemRaw[];
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const int nW = blockDim.x >> 5;
-	const int pitch = a.maxLen + 2;
-	double* bndAll = reinterpret_cast<double*>(smemRaw);
-	double* emis = bndAll + (size_t) nW * 3 * pitch + (size_t) warp * 320;
-	volatile int* progress = reinterpret_cast<volatile int*>(bndAll + (size_t) nW * (3 * pitch + 320));
+	const int pitchE = a.maxLen + 2 + 32; // entries (rows 0 .. N, + 32 of slack) per boundary array
+	double* bndAll = reinterpret_cast<double*>(smemRaw); // [nW][pitchE][3]
+	double* emis = bndAll + (size_t) nW * 3 * pitchE + (size_t) warp * 320;
+	volatile int* progress = reinterpret_cast<volatile int*>(bndAll + (size_t) nW * (3 * pitchE + 320));
 	Best* wBest = reinterpret_cast<Best*>(const_cast<int*>(progress) + 2048);
 	long long* wCells = reinterpret_cast<long long*>(wBest + nW);
 	VRegion* reg = reinterpret_cast<VRegion*>(wCells + nW);
 	int* sIdx = reinterpret_cast<int*>(reg + 1);
 	int8_t* codes = reinterpret_cast<int8_t*>(sIdx + 4);
+	uint16_t* xboxBase = reinterpret_cast<uint16_t*>(codes + ((size_t) a.maxLen + 15) / 16 * 16);
 	const int count = *a.fullCount;
 	uint32_t* slab = a.fullPtrs + (size_t) blockIdx.x * a.fullSlabWords;
 	const int K = h.K;
@@ -696,18 +743,30 @@ __global__ void __launch_bounds__(256) viterbiFullKernel(HmmDev h, VitArgs a) {
 		const int8_t* gx = a.codes + plan.codeOff;
 		for (int i = threadIdx.x; i < N; i += blockDim.x) codes[i] = gx[i];
 		for (int i = threadIdx.x; i < nStripes; i += blockDim.x) progress[i] = 0;
+		// emission offsets per row offset d = i - 1 in [-32, N + 32) (leanStep), and the parts of the boundary arrays no stripe
+		// writes: row 0 and the slack behind row N are +inf
+		uint16_t* const xbox = xboxBase + 32;
+		for (int d = -32 + (int) threadIdx.x; d < N + 32; d += blockDim.x) xbox[d] = (uint16_t) ((d >= 0 && d < N ? (int) gx[d] : 4) * 256);
+		for (int k = threadIdx.x; k < nW * 33; k += blockDim.x) {
+			const int wq = k / 33, e = k % 33;
+			double* p = bndAll + ((size_t) wq * pitchE + (e == 32 ? 0 : N + 1 + e)) * 3;
+			p[0] = p[1] = p[2] = INFINITY;
+		}
 		if (threadIdx.x == 0) {
 			VRegion R;
 			R.j0 = 1; R.j1 = K; R.i0 = 1; R.i1 = N;
 			R.strip = 0; R.pStart = R.pFrom = R.nIns = R.nDel = 0; R.useB = 1;
 			R.rowWords = N + 31; R.pad = 0; // steps per stripe slot
-			R.i0 = 1; R.j0 = 1;
 			R.ptrOff = 0;
 			*reg = R;
 		}
 		__syncthreads();
-		SeqConst q;
-		setSeqConst(q, N, K, a.cNN, a.cNB, a.cEC, a.cCC);
+		WarpCtx w;
+		w.x = codes;
+		setSeqConst(w.q, N, K, a.cNN, a.cNB, a.cEC, a.cCC);
+		w.bnd = NULL; w.bndPitch = 0; w.emis = NULL; w.win = NULL; w.winNew = NULL; w.xbox = NULL; w.ic = w.jc = 0;
+		const SeqConst& q = w.q;
+		const VRegion R = *reg;
 		Best best; best.v = INFINITY; best.j = 0x7fffffff; best.i = 0x7fffffff;
 		long long cells = 0;
 		for (int s = warp; s < nStripes; s += nW) {
@@ -718,29 +777,36 @@ __global__ void __launch_bounds__(256) viterbiFullKernel(HmmDev h, VitArgs a) {
 			const int jj = colOn ? j : K;
 			ColParams cp;
 			loadCol(h, jj, cp);
+			ColLean cl;
+			cl.tMMp = cp.tMMp; cl.tIMp = cp.tIMp; cl.tDMp = cp.tDMp; cl.tMI = cp.tMI; cl.tII = cp.tII;
+			cl.tMDp = cp.dOn ? cp.tMDp : INFINITY; cl.tDDp = cp.dOn ? cp.tDDp : INFINITY;
 			__syncwarp();
 			storeEmis(emis, cp, lane);
 			__syncwarp();
-			const double* in = bndAll + (size_t) ((s + nW - 1) % nW) * 3 * pitch; // written by stripe s-1
-			double* out = bndAll + (size_t) (s % nW) * 3 * pitch;
-			double curM = INFINITY, curI = INFINITY, curD = INFINITY; // row 0
-			double dgM = INFINITY, dgI = INFINITY, dgD = INFINITY;    // (0, jb-1)
+			const double* in = bndAll + (size_t) ((s + nW - 1) % nW) * 3 * pitchE; // written by stripe s-1: entry i = row i
+			double* out = bndAll + (size_t) (s % nW) * 3 * pitchE;
+			LeanState st;
+			st.curM = st.curI = st.curD = INFINITY; // row 0
+			st.dgM = st.dgI = st.dgD = INFINITY;    // (0, jb-1)
 			uint4* ptrStripe = reinterpret_cast<uint4*>(slab) + (size_t) s * (N + 31);
 			const int steps = N + ncols - 1;
-			for (int t = 0; t < steps; ++t) {
+			// ---- general steps: the whole first stripe (column 1, column 0 to its left), the first 32 steps of the others (row 1) ----
+			const int tG = (s == 0 || !q.nnInf) ? steps : min(32, steps);
+			int t = 0;
+			for (; t < tG; ++t) {
 				const int i = 1 + t - lane;
 				if (s > 0) { // lane 0 needs row t+1 of the previous stripe's last column
 					const int need = min(t + 1, N);
 					while (progress[s - 1] < need) { }
 					__threadfence_block();
 				}
-				double lM = __shfl_up_sync(0xffffffffu, curM, 1);
-				double lI = __shfl_up_sync(0xffffffffu, curI, 1);
-				double lD = __shfl_up_sync(0xffffffffu, curD, 1);
+				double lM = __shfl_up_sync(0xffffffffu, st.curM, 1);
+				double lI = __shfl_up_sync(0xffffffffu, st.curI, 1);
+				double lD = __shfl_up_sync(0xffffffffu, st.curD, 1);
 				if (lane == 0) {
 					if (i <= N) {
 						if (s == 0) { lM = lI = col0M(i, q.cNN, q.cNB); lD = INFINITY; }
-						else { lM = in[i]; lI = in[pitch + i]; lD = in[2 * pitch + i]; }
+						else { lM = in[3 * i]; lI = in[3 * i + 1]; lD = in[3 * i + 2]; }
 					} else
 						lM = lI = lD = INFINITY;
 				}
@@ -750,21 +816,47 @@ __global__ void __launch_bounds__(256) viterbiFullKernel(HmmDev h, VitArgs a) {
 				if (on) {
 					const int bb = codes[i - 1];
 					code = cellUpdate<true>(cp, entryCand(q, i, cp.ent), emis[bb * 32 + lane], emis[(5 + bb) * 32 + lane], j == 1, cp.dOn,
-							dgM, dgI, dgD, curM, curI, lM, lD, nM, nI, nD);
+							st.dgM, st.dgI, st.dgD, st.curM, st.curI, lM, lD, nM, nI, nD);
 					if (i == N || q.sAllRows) cellScore(cp, q, i, j, nM, nI, best);
-					cells++;
 				}
 				storePtrBits(ptrStripe + t, code & 1u, code & 2u, code & 4u, code & 8u, lane);
 				if (on) {
 					if (lane == 31) {
-						out[i] = nM; out[pitch + i] = nI; out[2 * pitch + i] = nD;
+						out[3 * i] = nM; out[3 * i + 1] = nI; out[3 * i + 2] = nD;
 						__threadfence_block();
 						progress[s] = i;
 					}
-					curM = nM; curI = nI; curD = nD;
-				}
-				dgM = lM; dgI = lI; dgD = lD;
+					st.curM = nM; st.curI = nI; st.curD = nD;
+				} else if (i > N) { st.curM = st.curI = st.curD = INFINITY; }
+				st.dgM = lM; st.dgI = lI; st.dgD = lD;
 			}
+			// ---- lean steps (rows >= 2, columns >= 33; leanStep decodes to the general pointer encoding through isLeanBox = false
+			//      here, so the pointer bits are stored in the general form below) ----
+			const uint32_t inA = sAddr(in), outA = sAddr(out), emisA = sAddr(emis + lane), xoA = sAddr(xbox - lane);
+			const uint32_t rowsEff = colOn ? (uint32_t) N : 0u;
+			for (; !q.sAllRows && t + 3 <= N - 3; t += 4) { // lane 0 stays below row N - 1: no S candidates in these steps (GLOBAL: row N only)
+				const int need = min(t + 4, N);
+				while (progress[s - 1] < need) { }
+				__threadfence_block();
+#pragma unroll
+				for (int k = 0; k < 4; ++k)
+					leanStepFull<false>(st, cl, inA + 24 * (t + k + 1), outA + 24 * (t + k - 30), xoA + 2 * (t + k), emisA, ptrStripe + t + k, t + k - lane, lane, rowsEff, h, R, w, j, jj, best);
+				if (lane == 31 && t + 3 - 30 >= 1) {
+					__threadfence_block();
+					progress[s] = t + 3 - 30;
+				}
+			}
+			for (; t < steps; ++t) {
+				const int need = min(t + 1, N);
+				while (progress[s - 1] < need) { }
+				__threadfence_block();
+				leanStepFull<true>(st, cl, inA + 24 * (t + 1), outA + 24 * (t - 30), xoA + 2 * t, emisA, ptrStripe + t, t - lane, lane, rowsEff, h, R, w, j, jj, best);
+				if (lane == 31 && t - 30 >= 1 && t - 30 <= N) {
+					__threadfence_block();
+					progress[s] = t - 30;
+				}
+			}
+			if (lane == 0) cells += (long long) N * ncols;
 		}
 		for (int o = 16; o > 0; o >>= 1) {
 			Best ob;
@@ -781,9 +873,6 @@ __global__ void __launch_bounds__(256) viterbiFullKernel(HmmDev h, VitArgs a) {
 				if (better(wBest[k].v, wBest[k].j, wBest[k].i, best)) best = wBest[k];
 				cells += wCells[k];
 			}
-			WarpCtx w;
-			w.x = codes; w.q = q;
-			w.bnd = NULL; w.bndPitch = 0; w.emis = NULL; w.win = NULL; w.winNew = NULL; w.xbox = NULL; w.ic = w.jc = 0;
 			int8_t* arow = a.aligned ? a.aligned + (size_t) seq * h.L : NULL;
 			const int flags = a.rows[seq].flags;
 			const long long prior = a.rows[seq].cells;

@@ -641,7 +641,7 @@ ostream& DiscreteGammaModel::save(ostream& out) const {
 // ------------------------------------------------------------------ PTUnrooted ----
 const string PTUnrooted::PTPlacement::TSV_HEADER = "branch_id\tbranch_ratio\ttaxon_id\ttaxon_anno\tanno_dist\tloglik\tQ_placement\tQ_taxon";
 
-istream& PTUnrooted::load(istream& in) {
+istream& PTUnrooted::load(istream& in, bool keepMessages) {
 	size_t nNodes = 0;
 	in.read((char*) &nNodes, sizeof(size_t));
 	in.read((char*) &csLen, sizeof(int));
@@ -672,9 +672,15 @@ istream& PTUnrooted::load(istream& in) {
 	in.read((char*) &nEdges, sizeof(size_t));
 	if (!in || nEdges != 2 * (nNodes - 1)) { in.setstate(ios_base::badbit); return in; }
 	const size_t per = (size_t) csLen * 4;
-	up.assign(nNodes * per, 0.0);
-	dn.assign(nNodes * per, 0.0);
-	vector<double> buf(per);
+	// keepMessages = false: the 4 x csLen doubles of every directed edge (98 GB for a gg_97-sized database) are skipped here
+	// and handed to the device(s) edge by edge later (streamMessages); only the records around them are read
+	up.clear(); dn.clear();
+	if (keepMessages) {
+		up.assign(nNodes * per, 0.0);
+		dn.assign(nNodes * per, 0.0);
+	}
+	edgePos = in.tellg();
+	vector<double> buf(keepMessages ? per : 0);
 	vector<pair<long, long> > edges(nEdges);
 	vector<vector<double> > pending; // messages whose direction is known only once every parent flag is read
 	pending.reserve(nEdges);
@@ -691,13 +697,14 @@ istream& PTUnrooted::load(istream& in) {
 		in.read((char*) &length, sizeof(double));
 		in.read((char*) &N, sizeof(size_t));
 		if (!in || id1 < 0 || id2 < 0 || (size_t) id1 >= nNodes || (size_t) id2 >= nNodes || N != per) { in.setstate(ios_base::badbit); return in; }
-		in.read((char*) buf.data(), sizeof(double) * per);
+		if (keepMessages) in.read((char*) buf.data(), sizeof(double) * per);
+		else in.seekg((streamoff) (sizeof(double) * per), ios_base::cur);
 		neighbors[id1].push_back(id2);
 		if (isPar) { // id1 is the parent of id2: this record is msg(parent -> child) = dn[id2]
 			parent[id2] = (int32_t) id1;
 			blen[id2] = length;
-			memcpy(&dn[(size_t) id2 * per], buf.data(), sizeof(double) * per);
-		} else {     // msg(child id1 -> parent id2) = up[id1]
+			if (keepMessages) memcpy(&dn[(size_t) id2 * per], buf.data(), sizeof(double) * per);
+		} else if (keepMessages) { // msg(child id1 -> parent id2) = up[id1]
 			memcpy(&up[(size_t) id1 * per], buf.data(), sizeof(double) * per);
 		}
 	}
@@ -795,7 +802,7 @@ hu_tree_desc PTUnrooted::treeDesc() const {
 	hu_tree_desc td;
 	td.nNodes = (int64_t) numNodes(); td.csLen = csLen; td.root = (int32_t) root;
 	td.parent = parent.data(); td.blen = blen.data(); td.height = height.data(); td.seq = seq.data(); td.taxon = taxon.data();
-	td.up = up.data(); td.dn = dn.data(); td.inferInternalSeq = 0;
+	td.up = up.empty() ? NULL : up.data(); td.dn = dn.empty() ? NULL : dn.data(); td.inferInternalSeq = 0;
 	return td;
 }
 hu_model_desc PTUnrooted::modelDesc() const {
@@ -804,13 +811,52 @@ hu_model_desc PTUnrooted::modelDesc() const {
 	for (int k = 0; k < md.dgK; ++k) md.dgRates[k] = dG.r[k];
 	return md;
 }
+// Second pass over the edge records of a .ptu read with keepMessages = false: every message goes to `sink` as
+// (node, direction, 4 x csLen log-domain doubles); direction 0 = msg(node -> parent), 1 = msg(parent -> node).
+bool PTUnrooted::streamMessages(istream& in, MessageSink& sink) const {
+	const size_t nNodes = parent.size(), nEdges = 2 * (nNodes - 1), per = (size_t) csLen * 4;
+	in.clear();
+	in.seekg(edgePos);
+	vector<double> buf(per);
+	for (size_t e = 0; e < nEdges; ++e) {
+		long id1, id2;
+		bool isPar;
+		double length;
+		size_t N;
+		in.read((char*) &id1, sizeof(long));
+		in.read((char*) &id2, sizeof(long));
+		in.read((char*) &isPar, sizeof(bool));
+		in.read((char*) &length, sizeof(double));
+		in.read((char*) &N, sizeof(size_t));
+		if (!in || N != per) return false;
+		in.read((char*) buf.data(), sizeof(double) * per);
+		if (!in) return false;
+		if (!sink.put(isPar ? id2 : id1, isPar ? 1 : 0, buf.data())) return false;
+	}
+	return sink.flush();
+}
+
 PTUnrooted::PTPlacement PTUnrooted::toPlacement(const hu_place_row& r) const {
 	PTPlacement p;
 	p.start = r.start; p.end = r.end; p.cNode = r.cNode; p.pNode = r.pNode; p.aNode = r.aNode;
 	p.wuv = r.wuv; p.ratio = r.ratio; p.wnr = r.wnr; p.loglik = r.loglik; p.height = r.height;
 	p.annoDist = r.annoDist; p.qPlace = r.qPlace; p.qTaxon = r.qTaxon;
 	p.taxonName = r.aNode >= 0 ? anno[r.aNode] : "NULL";
+	p.raw = r;
+	p.owner = this;
 	return p;
+}
+PTUnrooted::PTPlacement::PTPlacement() : start(0), end(0), cNode(-1), pNode(-1), aNode(-1), wuv(0), ratio(0), wnr(0), loglik(0), height(0),
+		annoDist(0), qPlace(0), qTaxon(0), owner(NULL) {
+	memset(&raw, 0, sizeof raw);
+	raw.cNode = raw.pNode = raw.aNode = raw.taxon = -1;
+}
+hu_place_row PTUnrooted::PTPlacement::toRow() const {
+	hu_place_row r = raw;
+	r.start = start; r.end = end; r.cNode = (int32_t) cNode; r.pNode = (int32_t) pNode; r.aNode = (int32_t) aNode;
+	r.wuv = wuv; r.ratio = ratio; r.wnr = wnr; r.loglik = loglik; r.height = height;
+	r.annoDist = annoDist; r.qPlace = qPlace; r.qTaxon = qTaxon;
+	return r;
 }
 string PTUnrooted::PTPlacement::getId() const {
 	if (cNode < 0 || pNode < 0) return "NULL";

@@ -6,6 +6,7 @@
 #define HU_HOST_H_
 
 #include <stdint.h>
+#include <string.h>
 #include <iostream>
 #include <map>
 #include <string>
@@ -149,7 +150,28 @@ public:
 		std::string align;
 		static const std::string TSV_HEADER;
 	};
-	BandedHMMP7() : K(0), L(0), wingRetracted(false), mode(GLOBAL) {}
+	// ViterbiScores (.h:173-199) holds the reference's four dense DP matrices; here it is the handle of one device alignment:
+	// calcViterbiScores() runs the banded (or full) Viterbi pass of ONE read on the attached device and keeps its result,
+	// buildViterbiTrace() hands it out as the reference's ViterbiAlignTrace (.h:251-270)
+	struct ViterbiScores {
+		ViterbiScores() : seq(NULL) { memset(&row, 0, sizeof row); }
+		explicit ViterbiScores(const PrimarySeq& s) : seq(&s) { memset(&row, 0, sizeof row); }
+		const PrimarySeq* seq;
+		hu_align_row row;
+		std::string trace;
+	};
+	struct ViterbiAlignTrace {
+		ViterbiAlignTrace() : minScore(0), alnStart(0), alnEnd(0), alnFrom(0), alnTo(0) {}
+		double minScore;
+		int alnStart, alnEnd, alnFrom, alnTo;
+		std::string alnTrace;
+	};
+	ViterbiScores& calcViterbiScores(const PrimarySeq& seq, ViterbiScores& vs) const;                                              // cpp:748-780
+	ViterbiScores& calcViterbiScores(const PrimarySeq& seq, ViterbiScores& vs, const std::vector<ViterbiAlignPath>& vpaths) const; // cpp:782-892
+	void buildViterbiTrace(const ViterbiScores& vs, ViterbiAlignTrace& vtrace) const;                                              // cpp:943-1006
+	HmmAlignment buildGlobalAlign(const PrimarySeq& seq, const ViterbiScores& vs, const ViterbiAlignTrace& vtrace) const;           // cpp:1008-1081
+	mutable class DeviceDB* dev;                   // set by DeviceDB: where the per-call facades run
+	BandedHMMP7() : dev(NULL), K(0), L(0), wingRetracted(false), mode(GLOBAL) {}
 	int getProfileSize() const { return K; }
 	int getCSLen() const { return L; }
 	int getProfileLoc(int cs) const { return cs2ProfileIdx[cs]; }
@@ -211,23 +233,43 @@ double gammaP(double a, double x);                 // regularised lower incomple
 double gammaQuantile(double shape, double scale, double p);
 
 // ---- unrooted phylogenetic tree as stored in <db>.ptu (src/PhyloTreeUnrooted.{h,cpp}) ----
+typedef std::vector<int8_t> DigitalSeq;            // src/DigitalSeq.h: an aligned read as codes over the consensus columns (gap < 0)
+DigitalSeq digitalSeq(const std::string& align);   // src/DigitalSeq.cpp:41-48
+
 class PTUnrooted {
 public:
 	enum PRIOR_TYPE { UNIFORM, HEIGHT };
 	struct PTLoc { int start, end; long id; double dist; };          // .h:390-405
 	struct PTPlacement {                                             // .h:410-510
-		PTPlacement() : start(0), end(0), cNode(-1), pNode(-1), aNode(-1), wuv(0), ratio(0), wnr(0), loglik(0), height(0),
-				annoDist(0), qPlace(0), qTaxon(0) {}
+		PTPlacement();
 		std::string getId() const;
 		long getTaxonId() const { return aNode; }
 		int start, end;
 		long cNode, pNode, aNode;
 		double wuv, ratio, wnr, loglik, height, annoDist, qPlace, qTaxon;
 		std::string taxonName;
+		// what the device row holds beyond the reference's fields (p-distance of the seed, estimated log-likelihood, taxon id,
+		// iteration counts): kept so that a placement can travel back to the device through the per-call facades below
+		hu_place_row raw;
+		const PTUnrooted* owner;
+		hu_place_row toRow() const;                 // raw with the visible fields written over it
 		static const std::string TSV_HEADER;
 	};
-	PTUnrooted() : csLen(0), root(0), hasDG(false) {}
-	std::istream& load(std::istream& in);          // cpp:496-535
+	PTUnrooted() : dev(NULL), csLen(0), root(0), hasDG(false) {}
+	// class surface of the per-read path (src/PhyloTreeUnrooted.h:870-900), one placement per call, on the attached device
+	PTPlacement estimateSeq(const DigitalSeq& seq, const PTLoc& loc, const std::string& method = "unweighted") const; // cpp:849-877
+	PTPlacement& placeSeq(const DigitalSeq& seq, PTPlacement& place, double maxHeight) const;                            // cpp:925-954
+	mutable class DeviceDB* dev;                   // set by DeviceDB: where the per-call facades run
+	// cpp:496-535.  keepMessages = false reads everything but the messages (98 GB for a gg_97-sized tree): they are then
+	// streamed from the file to the device(s), edge by edge, by streamMessages()
+	std::istream& load(std::istream& in, bool keepMessages = true);
+	struct MessageSink {
+		virtual ~MessageSink() {}
+		virtual bool put(long node, int dir, const double* logMsg) = 0; // dir 0: msg(node -> parent), 1: msg(parent -> node)
+		virtual bool flush() { return true; }
+	};
+	bool streamMessages(std::istream& in, MessageSink& sink) const;
+	std::streampos edgePos;                        // where the edge records start in the file load() read
 	std::ostream& save(std::ostream& out) const;   // cpp:537-567
 	size_t numNodes() const { return parent.size(); }
 	int getCSLen() const { return csLen; }
@@ -282,6 +324,36 @@ std::vector<BandedHMMP7::ViterbiAlignPath> findSeeds(const BandedHMMP7& hmm, con
 // (an attempt whose hit turns out unusable continues with on-the-spot searches).  Same paths, same rand() stream.
 std::vector<std::vector<BandedHMMP7::ViterbiAlignPath> > findSeedsBatch(const BandedHMMP7& hmm, const CSFMIndex& csfm,
 		const std::vector<const PrimarySeq*>& reads, int seedLen, int seedRegion, BandedHMMP7::align_mode mode, int nThreads);
+
+// ---- the reference's free functions (src/HmmUFOtu_main.h:70-113), one read per call, over the C ABI (hu_facade.cpp) ----
+// One database replica on one device plus a one-read workspace; attaching it to the host objects is what makes their
+// per-call methods and the free functions below run: every stage goes through include/hmmufotu_b200.h (no host arithmetic).
+class DeviceDB {
+public:
+	DeviceDB(const BandedHMMP7& hmm, const PTUnrooted& ptu, int device); // throws std::runtime_error with hu_last_error()
+	~DeviceDB();
+	hu_db* db;
+	hu_batch* one(int maxLen);                     // the one-read workspace, grown on demand
+	const BandedHMMP7& hmm;
+	const PTUnrooted& ptu;
+private:
+	hu_batch* batch;
+	int batchLen;
+	DeviceDB(const DeviceDB&);
+	DeviceDB& operator=(const DeviceDB&);
+};
+BandedHMMP7::HmmAlignment alignSeq(const BandedHMMP7& hmm, const CSFMIndex& csfm, const PrimarySeq& read, int seedLen, int seedRegion,
+		BandedHMMP7::align_mode mode);                                                                                    // cpp:39-105
+// all the device keeps of the sorted candidate vector is its first HU_MAX_SEED (64) entries: callers truncate to -N <= 64
+std::vector<PTUnrooted::PTLoc> getSeed(const PTUnrooted& ptu, const DigitalSeq& seq, int start, int end, double maxDiff, double maxHeight); // cpp:127-152
+std::vector<PTUnrooted::PTPlacement> estimateSeq(const PTUnrooted& ptu, const DigitalSeq& seq, const std::vector<PTUnrooted::PTLoc>& locs,
+		const std::string& method);                                                                                       // cpp:154-160
+std::vector<PTUnrooted::PTPlacement>& filterPlacements(std::vector<PTUnrooted::PTPlacement>& places, double maxError);            // cpp:162-173
+std::vector<PTUnrooted::PTPlacement>& placeSeq(const PTUnrooted& ptu, const DigitalSeq& seq, std::vector<PTUnrooted::PTPlacement>& places,
+		double maxHeight);                                                                                                // cpp:175-180
+void calcQValues(std::vector<PTUnrooted::PTPlacement>& places, PTUnrooted::PRIOR_TYPE type);                                      // cpp:182-216
+bool compareByLoglik(const PTUnrooted::PTPlacement& lhs, const PTUnrooted::PTPlacement& rhs);                                     // .h:1627-1637
+bool compareByQPlace(const PTUnrooted::PTPlacement& lhs, const PTUnrooted::PTPlacement& rhs);
 
 } // namespace HmmUFOtu
 } // namespace EGriceLab

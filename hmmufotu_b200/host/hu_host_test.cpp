@@ -13,6 +13,9 @@
 //   csfmwrite DB.msa OUT.csfm   the index file as the reference's hmmufotu loads it (libcds serialisation)
 //   seeds DB FASTA S   CSFM seed search of every read with srand(S): prints the ViterbiAlignPaths
 #include "hu_host.h"
+#include <limits>
+#include <algorithm>
+#include <stdexcept>
 
 #include <stdlib.h>
 #include <math.h>
@@ -339,6 +342,61 @@ int main(int argc, char** argv) {
 					cout << "\t" << v[i].start << "," << v[i].end << "," << v[i].from << "," << v[i].to << "," << v[i].nIns << "," << v[i].nDel;
 				cout << endl;
 			}
+		}
+		return 0;
+	}
+	if (cmd == "facade" && (argc == 5 || argc == 6)) {
+		// facade DB FASTA SEED [MATE-FASTA]: the reference's per-read loop (src/hmmufotu.cpp:603-751) written with ITS OWN
+		// calls -- alignSeq, getSeed, estimateSeq, filterPlacements, placeSeq, calcQValues, std::sort, places[0] -- one read
+		// at a time over the per-call facades of hu_facade.cpp (device needed).  Prints the TSV data rows.
+		const string db = argv[2];
+		ifstream msaIn((db + ".msa").c_str(), ios_base::binary), hmmIn((db + ".hmm").c_str()), ptuIn((db + ".ptu").c_str(), ios_base::binary);
+		if (loadProgInfo(msaIn).bad() || loadProgInfo(ptuIn).bad()) return 1;
+		MSA msa;
+		msa.load(msaIn);
+		BandedHMMP7 hmm;
+		hmmIn >> hmm;
+		PTUnrooted ptu;
+		ptu.load(ptuIn);
+		if (!msaIn || !hmmIn || !ptuIn) { cerr << "cannot load " << db << endl; return 1; }
+		CSFMIndex csfm;
+		csfm.build(msa);
+		const BandedHMMP7::align_mode mode = single ? BandedHMMP7::NGCL : BandedHMMP7::GLOBAL;
+		hmm.setSequenceMode(mode);
+		hmm.wingRetract();
+		try {
+			DeviceDB dev(hmm, ptu, 0);
+			srand((unsigned) atoi(argv[4]));
+			ifstream fa(argv[3]);
+			SeqIO io(&fa, SeqIO::guessFormat(argv[3]));
+			ifstream mfa;
+			if (argc == 6) mfa.open(argv[5]);
+			SeqIO mio(&mfa, SeqIO::guessFormat(argc == 6 ? argv[5] : argv[3]));
+			const double inf = numeric_limits<double>::infinity();
+			while (io.hasNext() && (argc == 5 || mio.hasNext())) {
+				const PrimarySeq fwdRead = io.nextSeq();
+				BandedHMMP7::HmmAlignment aln = alignSeq(hmm, csfm, fwdRead, 20, 50, mode);
+				bool isChimera = false;
+				if (argc == 6) {
+					const PrimarySeq revRead = mio.nextSeq().revcom();
+					const BandedHMMP7::HmmAlignment revAln = alignSeq(hmm, csfm, revRead, 20, 50, mode);
+					if (!(aln.csStart <= revAln.csStart && aln.csEnd <= revAln.csEnd)) isChimera = true;
+					else aln.merge(revAln);
+				}
+				if (isChimera) continue; // written to --chimera-out only
+				const DigitalSeq seq = digitalSeq(aln.align);
+				vector<PTUnrooted::PTLoc> seeds = getSeed(ptu, seq, aln.csStart - 1, aln.csEnd - 1, inf, inf);
+				if (seeds.size() > 50) seeds.erase(seeds.end() - (seeds.size() - 50), seeds.end());
+				vector<PTUnrooted::PTPlacement> places = estimateSeq(ptu, seq, seeds, "unweighted");
+				filterPlacements(places, 20.0);
+				placeSeq(ptu, seq, places, inf);
+				calcQValues(places, PTUnrooted::UNIFORM);
+				std::sort(places.rbegin(), places.rend(), compareByQPlace);
+				cout << fwdRead.getId() << "\t" << fwdRead.getDesc() << "\t" << aln << "\t" << places[0] << endl;
+			}
+		} catch (const std::exception& e) {
+			cerr << "facade: " << e.what() << endl;
+			return 1;
 		}
 		return 0;
 	}

@@ -92,6 +92,16 @@ typedef struct hu_tree_desc {
 
 int hu_db_create(hu_db** out, const hu_hmm_params* hmm, const hu_tree_desc* tree, const hu_model_desc* model, int device);
 int hu_db_destroy(hu_db* db);
+/* The same replica built in steps, for databases whose messages do not fit in host memory (98 GB at gg_97 scale):
+ * hu_db_create_deferred takes everything but the messages (tree->up / dn are ignored), hu_db_put_messages streams them in
+ * -- n messages of 4 x csLen log-domain doubles each; nodes[i] / dirs[i] name the directed edge (0: node -> parent,
+ * 1: parent -> node), in any order, as PTUnrooted::load meets them in the .ptu (src/PhyloTreeUnrooted.cpp:595-603) -- and
+ * hu_db_finish completes the tables derived from them. */
+int hu_db_create_deferred(hu_db** out, const hu_hmm_params* hmm, const hu_tree_desc* tree, const hu_model_desc* model, int device);
+int hu_db_put_messages(hu_db* db, int64_t n, const int64_t* nodes, const int32_t* dirs, const double* logMsg);
+int hu_db_finish(hu_db* db);
+/* a replica of `src` on another device, copied device to device (peer path: NVLink where available) */
+int hu_db_clone(hu_db** out, hu_db* src, int device);
 /* read back device-resident pieces (tests, DB writer): n nodes starting at node0; any pointer may be NULL */
 int hu_db_get_messages(hu_db* db, int64_t node0, int64_t n, double* up, double* dn);
 int hu_db_get_seq(hu_db* db, int64_t node0, int64_t n, int8_t* seq);

@@ -124,8 +124,10 @@ def _check_read(otree, codes, start, end, ns_i, ids_i, dist_i, nk_i, est_i, pl_i
         tied |= (int(g["cNode"]), int(g["pNode"])) != (o_sorted[k].c, o_sorted[k].p)
         gp = pl_i[k]
         assert (gp["cNode"], gp["pNode"], gp["aNode"]) == (o.c, o.p, o.a)
-        np.testing.assert_allclose([gp["ratio"], gp["wnr"], gp["loglik"], gp["loglikTrue"], gp["height"]],
-                                   [o.ratio, o.wnr, o.loglik, o.loglikTrue, o.height], rtol=RTOL, atol=1e-12)
+        np.testing.assert_allclose([gp["ratio"], gp["wnr"], gp["loglik"], gp["height"]],
+                                   [o.ratio, o.wnr, o.loglik, o.height], rtol=RTOL, atol=1e-12)
+        if use_true:                                                  # the root log-likelihood is evaluated only when asked for
+            np.testing.assert_allclose(gp["loglikTrue"], o.loglikTrue, rtol=RTOL)
         assert gp["outerIters"] == o.outerIters
     o0 = rows[0]                                                       # the oracle's bestPlace
     if not use_true:                                                   # literal: all qPlace equal -> the sort artefact
@@ -154,8 +156,11 @@ def test_seed_estimate_place(small):
     for i in range(n):
         n_tied += _check_read(otree, codes[i], start[i], end[i], ns[i], ids[i], dist[i], nk[i], est[i], pl[i], best[i])
     assert n_tied < n // 4
-    # intended-loglik mode: the chosen edge is the maximum of the true root loglik
-    b.calcQValues(engine.SepParams(use_true_loglik=True))
+    # intended-loglik mode: the chosen edge is the maximum of the true root loglik (placeSeq evaluates it only on request)
+    p_true = engine.SepParams(use_true_loglik=True)
+    b.placeSeq(p_true)
+    b.calcQValues(p_true)
+    _, pl_true = b.places()
     best2 = b.best()
     for i in range(n):
         oid, odist = otree.get_seed(codes[i], start[i], end[i], 50, order=0)
@@ -163,6 +168,9 @@ def test_seed_estimate_place(small):
         top = max(r.loglikTrue for r in rows)
         mine = [r for r in rows if (r.c, r.p) == (best2[i]["cNode"], best2[i]["pNode"])][0]
         assert mine.loglikTrue >= top - 1e-9 * abs(top), i
+        by_edge = {(r.c, r.p): r for r in rows}
+        for q in pl_true[i, :nk[i]]:
+            np.testing.assert_allclose(q["loglikTrue"], by_edge[(int(q["cNode"]), int(q["pNode"]))].loglikTrue, rtol=RTOL)
     b.close()
 
 

@@ -188,3 +188,22 @@ def test_builder_on_the_device(tmp_path):
     assert float(out[1]) < 1e-9 and out[3] == "1", out
     sk = lambda f: subprocess.run([tool, "ptuskel", f], capture_output=True, text=True).stdout
     assert sk(str(tmp_path / "hand.ptu")) == sk(os.path.join(b, "hand.ptu"))
+
+
+def test_per_call_facades_write_the_references_rows(refdb_dir):
+    """SURVEY.md 8(b), "class surface to preserve": the reference's own per-read loop (src/hmmufotu.cpp:603-751) written with
+    ITS calls -- alignSeq, getSeed, estimateSeq, filterPlacements, placeSeq, calcQValues, std::sort, places[0] -- over the
+    per-call facades of host/hu_facade.cpp (BandedHMMP7::calcViterbiScores / buildViterbiTrace / buildGlobalAlign and
+    PTUnrooted::estimateSeq / placeSeq underneath), every stage on the device through the C ABI, one read at a time: the
+    rows are the reference's TSV rows, single-end and paired-end."""
+    name, d = refdb_dir
+    tool = os.path.join(ROOT, "hmmufotu_b200", "bin", "hu_host_test")
+    for tag, seed, paired in (("se0", 0, False), ("pe0", 7, True)):
+        reads = [os.path.join(GOLD, "%s_%s_%d.fasta" % (name, tag, m)) for m in (1, 2)] if paired else [os.path.join(GOLD, "%s_%s.fasta" % (name, tag))]
+        p = subprocess.run([tool, "facade", os.path.join(d, name), reads[0], str(seed)] + reads[1:], capture_output=True, text=True)
+        assert p.returncode == 0, p.stderr[-2000:]
+        got = [ln for ln in p.stdout.split("\n") if ln]
+        want = data_lines(os.path.join(GOLD, "%s_%s.tsv" % (name, tag)))[1:]
+        assert len(got) == len(want) == 64
+        bad = [i for i, (g, w) in enumerate(zip(got, want)) if g != w]
+        assert not bad, "rows differ from the reference's TSV: %s\n%s\n%s" % (bad[:5], got[bad[0]][-300:], want[bad[0]][-300:])
