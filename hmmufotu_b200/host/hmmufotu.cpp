@@ -14,6 +14,15 @@
 #include <fstream>
 #include <limits>
 #include <sstream>
+#include <algorithm>
+#include <atomic>
+#include <map>
+#include <chrono>
+#include <condition_variable>
+#include <deque>
+#include <memory>
+#include <mutex>
+#include <thread>
 
 using namespace std;
 using namespace EGriceLab::HmmUFOtu;
@@ -49,8 +58,10 @@ static void printUsage(const string& prog) {
 		 << "            --chimera-err  DBL   : max placement error used in the 'Estimate' stage of chimera SEP algorithm" << endl
 		 << "            --chimera-lod  DBL   : min log-odd required for defining a chimera read [0]" << endl
 		 << "            --chimera-out  FILE  : keep assignment output of chimera reads (bad mate orientation) in FILE" << endl
+		 << "            --chimera-info  FLAG : report detailed chimera information (segment placements, log-odd) in assignment outputs" << endl
 		 << "            -S|--seed  INT       : random seed used for CSFM-index seed searches, for debug only" << endl
-		 << "            --gpu  INT           : CUDA device to use [0]" << endl
+		 << "            --gpu  INT           : first CUDA device to use [0]" << endl
+		 << "            --gpus  INT          : number of devices (--gpu, --gpu + 1, ...): the database is loaded once, copied device to device, and the batches of reads are dealt to the devices; rows come out in file order [1]" << endl
 		 << "            --batch  INT         : reads per GPU batch [4096]" << endl
 		 << "            --align-only  FLAG   : only align the reads, do not place them" << endl
 		 << "            --check-db  FLAG     : load the database files, print a summary and exit (no GPU needed)" << endl
@@ -175,20 +186,25 @@ int main(int argc, char* argv[]) {
 	if (cmdOpts.hasOpt("-H") || cmdOpts.hasOpt("--max-height")) sp.maxHeight = atof(cmdOpts.get("-H", "--max-height", "inf").c_str());
 	sp.maxError = atof(cmdOpts.get("-e", "--err", "20").c_str());
 	sp.useTrueLoglik = cmdOpts.hasOpt("--true-loglik");
-	{ // -C|--chimera and its options, src/hmmufotu.cpp:248-260, 325-340.  The segment re-estimation compares placeSeq()
-	  // return values of the SAME window (best vs. alternative branch), and that value is the constant
-	  // W * log(sum pi e), so chimera_lod is exactly 0 and `chimera_lod > --chimera-lod (>= 0)` never
-	  // holds: with -C the reference writes the same assignment rows (checked against the reference binary,
-	  // tests/test_gpu_ref.py).  Only --chimera-info would show the segment placements; it is refused.
-		const bool checkChimera = cmdOpts.hasOpt("-C") || cmdOpts.hasOpt("--chimera");
-		if (checkChimera) {
-			const int numSeg = atoi(cmdOpts.get("--num-segment", "--num-segment", "2").c_str());
-			if (!(2 <= numSeg && numSeg <= 6)) { cerr << "--num-segment must be in range [2, 6]" << endl; return EXIT_FAILURE; }
-			if (numSeg % 2) { cerr << "--num-segment must be an even number" << endl; return EXIT_FAILURE; }
-			if (cmdOpts.hasOpt("--chimera-err") && !(atof(cmdOpts.get("--chimera-err", "--chimera-err", "0").c_str()) > 0)) { cerr << "--chimera-err must be positive" << endl; return EXIT_FAILURE; }
-			if (cmdOpts.hasOpt("--chimera-lod") && !(atof(cmdOpts.get("--chimera-lod", "--chimera-lod", "0").c_str()) >= 0)) { cerr << "--chimera-lod must be non-negative" << endl; return EXIT_FAILURE; }
-			if (cmdOpts.hasOpt("--chimera-info")) { cerr << "--chimera-info is not supported by this build (segment placements are not reported)" << endl; return EXIT_FAILURE; }
+	// -C|--chimera and its options, src/hmmufotu.cpp:248-260, 325-340.  The segment re-estimation compares placeSeq() return
+	// values of the SAME window (best vs. alternative branch), and that value is the constant W * log(sum pi e) (SURVEY.md
+	// F6), so chimera_lod is exactly 0 and `chimera_lod > --chimera-lod (>= 0)` never holds: with -C the reference writes the
+	// same assignment rows (checked against the reference binary, tests/test_gpu_ref.py).  --chimera-info adds the segment
+	// placements to every row; they are computed here as there: per segment, estimateSeq over the read's common seeds
+	// restricted to the segment's columns, filterPlacements(--chimera-err), placeSeq, then std::sort by log-likelihood.
+	const bool checkChimera = cmdOpts.hasOpt("-C") || cmdOpts.hasOpt("--chimera");
+	const bool chimeraInfo = checkChimera && cmdOpts.hasOpt("--chimera-info");
+	int numSeg = 2;
+	double maxChimeraError = 20.0 / 2; // literal: maxError / numSeg of the DEFAULTS, evaluated before the options are parsed (:147)
+	if (checkChimera) {
+		numSeg = atoi(cmdOpts.get("--num-segment", "--num-segment", "2").c_str());
+		if (!(2 <= numSeg && numSeg <= 6)) { cerr << "--num-segment must be in range [2, 6]" << endl; return EXIT_FAILURE; }
+		if (numSeg % 2) { cerr << "--num-segment must be an even number" << endl; return EXIT_FAILURE; }
+		if (cmdOpts.hasOpt("--chimera-err")) {
+			maxChimeraError = atof(cmdOpts.get("--chimera-err", "--chimera-err", "0").c_str());
+			if (!(maxChimeraError > 0)) { cerr << "--chimera-err must be positive" << endl; return EXIT_FAILURE; }
 		}
+		if (cmdOpts.hasOpt("--chimera-lod") && !(atof(cmdOpts.get("--chimera-lod", "--chimera-lod", "0").c_str()) >= 0)) { cerr << "--chimera-lod must be non-negative" << endl; return EXIT_FAILURE; }
 	}
 	{ // -m|--method, --ML, --prior: src/hmmufotu.cpp:229-246, 335-338
 		const string estMethod = cmdOpts.get("-m", "--method", "unweighted");
@@ -250,7 +266,7 @@ int main(int argc, char* argv[]) {
 	if (csfm.getCSLen() != csLen) { cerr << "Error: Unmatched CS length between CSFM-index and MSA data" << endl; return EXIT_FAILURE; }
 	if (loadProgInfo(ptuIn).bad()) return EXIT_FAILURE;
 	PTUnrooted ptu;
-	ptu.load(ptuIn);
+	ptu.load(ptuIn, false); // everything but the messages: they go from the file to the device(s) edge by edge (below)
 	if (!ptuIn || ptuIn.bad()) { cerr << "Unable to load Phylogenetic tree data '" << ptuFn << "'" << endl; return EXIT_FAILURE; }
 	if (ptu.getCSLen() != csLen || hmm.getCSLen() != csLen) { cerr << "Error: Unmatched CS length between the database files" << endl; return EXIT_FAILURE; }
 	hmm.setSequenceMode(mode);
@@ -287,16 +303,39 @@ int main(int argc, char* argv[]) {
 		return EXIT_SUCCESS;
 	}
 
-	// ---- device ----
-	hu_db* db = NULL;
+	// ---- devices: the replica is built once, on the first device, from the messages streamed out of the .ptu (never the
+	//      whole 4 x csLen x 2 (N - 1) doubles in host memory), then copied device to device (peer path) ----
+	const int nGpus = atoi(cmdOpts.get("--gpus", "--gpus", "1").c_str());
+	if (nGpus < 1) { cerr << "--gpus must be positive" << endl; return EXIT_FAILURE; }
+	vector<hu_db*> dbs(nGpus, (hu_db*) NULL);
 	{
 		const hu_hmm_params hp = hmm.params();
 		const hu_tree_desc td = ptu.treeDesc();
 		const hu_model_desc md = ptu.modelDesc();
-		HU_CHECK(hu_db_create(&db, &hp, &td, &md, device));
+		HU_CHECK(hu_db_create_deferred(&dbs[0], &hp, &td, &md, device));
+		struct Sink : PTUnrooted::MessageSink { // a few hundred MB of edges per host -> device transfer
+			hu_db* db; size_t per, cap;
+			vector<int64_t> nodes; vector<int32_t> dirs; vector<double> buf;
+			bool put(long node, int dir, const double* m) {
+				nodes.push_back(node); dirs.push_back(dir);
+				buf.insert(buf.end(), m, m + per);
+				return nodes.size() < cap || flush();
+			}
+			bool flush() {
+				if (nodes.empty()) return true;
+				const int rc = hu_db_put_messages(db, (int64_t) nodes.size(), nodes.data(), dirs.data(), buf.data());
+				nodes.clear(); dirs.clear(); buf.clear();
+				return rc == HU_OK;
+			}
+		} sink;
+		sink.db = dbs[0]; sink.per = (size_t) csLen * 4; sink.cap = max<size_t>(1, ((size_t) 256 << 20) / (sink.per * sizeof(double)));
+		sink.buf.reserve(sink.cap * sink.per);
+		if (!ptu.streamMessages(ptuIn, sink)) { cerr << "Unable to load the messages of '" << ptuFn << "': " << hu_last_error() << endl; return EXIT_FAILURE; }
+		HU_CHECK(hu_db_finish(dbs[0]));
+		for (int g = 1; g < nGpus; ++g) HU_CHECK(hu_db_clone(&dbs[g], dbs[0], device + g));
+		if (verbose) cerr << "Database on " << nGpus << " device(s)" << endl;
 	}
-	vector<double>().swap(ptu.up); // the messages now live on the device
-	vector<double>().swap(ptu.dn);
+	hu_db* db = dbs[0];
 
 	// ---- strand pre-test, :501-542: align the first nTest reads in both orientations ----
 	const bool paired = !revFn.empty();
@@ -349,7 +388,9 @@ int main(int argc, char* argv[]) {
 	if (!alnFn.empty()) { alnFile.open(alnFn.c_str()); if (!alnFile.is_open()) { cerr << "Unable to write to '" << alnFn << "' " << ::strerror(errno) << endl; return EXIT_FAILURE; } }
 	if (!chiFn.empty()) { chiFile.open(chiFn.c_str()); if (!chiFile.is_open()) { cerr << "Unable to write to '" << chiFn << "' " << ::strerror(errno) << endl; return EXIT_FAILURE; } }
 	ostream& out = outFn.empty() ? cout : outFile;
-	const string header = string("id\tdescription\t") + BandedHMMP7::HmmAlignment::TSV_HEADER + "\t" + PTUnrooted::PTPlacement::TSV_HEADER;
+	static const string CHIMERA_TSV_HEADER = "seg5_taxon_id\tseg3_taxon_id\tseg5_taxon_anno\tseg3_taxon_anno\tchimera_lod"; // :57
+	const string header = string("id\tdescription\t") + BandedHMMP7::HmmAlignment::TSV_HEADER + (chimeraInfo ? "\t" + CHIMERA_TSV_HEADER + "\t" : "\t") +
+	                      PTUnrooted::PTPlacement::TSV_HEADER; // :590-600
 	writeProgInfo(out, string(" taxonomy assignment generated by ") + argv[0]);
 	out << "# command: " << cmdOpts.cmd << endl << header << endl;
 	if (chiFile.is_open()) {
@@ -357,63 +398,196 @@ int main(int argc, char* argv[]) {
 		chiFile << "# command: " << cmdOpts.cmd << endl << header << endl;
 	}
 
-	// ---- the read loop, batched ----
-	hu_batch* batch = NULL;
-	int batchMaxLen = 0;
-	long nDone = 0;
-	while (fwdSeqI.hasNext() && (!paired || revSeqI.hasNext())) {
+	// ---- the read loop: a pipeline ----
+	// reader (this thread's helper): FASTA / FASTQ parsing and the CSFM seed search in FILE ORDER (its rand() stream is the
+	//   reference's for a given -S), -p threads inside findSeedsBatch;
+	// workers: two per device, each with its own workspace: upload, the five stages, read-back, then the TSV text of the batch
+	//   (aligned strings, placement columns) -- so the kernels of one batch overlap the host work of the next;
+	// writer (this thread): the batches' text in file order.
+	struct Job {
+		long index;
+		int n, maxLen;
 		ReadBatchHost hb;
-		int maxLen = 1;
-		const int n = readBatch(fwdSeqI, revSeqI, paired, rStrand, batchSize, hmm, csfm, seedLen, seedRegion, mode, nThreads, hb, maxLen);
-		if (!batch || maxLen > batchMaxLen) {
-			if (batch) hu_batch_destroy(batch);
-			batchMaxLen = max(maxLen + maxLen / 4, 64);
-			HU_CHECK(hu_batch_create(&batch, db, batchSize, batchMaxLen, paired ? 1 : 0));
+		string outText, chiText, alnText, errText;
+		bool failed;
+		Job() : index(0), n(0), maxLen(1), failed(false) {}
+	};
+	struct Queue {
+		mutex m; condition_variable cv;
+		deque<shared_ptr<Job> > q; bool closed; size_t cap;
+		Queue() : closed(false), cap(0) {}
+		void push(const shared_ptr<Job>& j) { unique_lock<mutex> l(m); cv.wait(l, [&] { return cap == 0 || q.size() < cap; }); q.push_back(j); cv.notify_all(); }
+		shared_ptr<Job> pop() { unique_lock<mutex> l(m); cv.wait(l, [&] { return !q.empty() || closed; }); if (q.empty()) return shared_ptr<Job>(); shared_ptr<Job> j = q.front(); q.pop_front(); cv.notify_all(); return j; }
+		void close() { unique_lock<mutex> l(m); closed = true; cv.notify_all(); }
+	};
+	const int workersPerGpu = 2, nWorkers = nGpus * workersPerGpu;
+	Queue todo, done;
+	todo.cap = (size_t) nWorkers + 2;
+	const bool wantAln = alnFile.is_open(), wantChi = chiFile.is_open();
+	auto work = [&](int wk) {
+		hu_db* wdb = dbs[wk / workersPerGpu];
+		hu_batch* batch = NULL;
+		hu_batch* segBatch = NULL; // --chimera-info: (read, segment) pairs as the rows of a second workspace
+		int batchMaxLen = 0;
+		for (;;) {
+			shared_ptr<Job> job = todo.pop();
+			if (!job) break;
+			Job& J = *job;
+			ostringstream tOut, tChi, tAln, err;
+			const int n = J.n;
+			do {
+#define HU_JOB(call) if ((call) != HU_OK) { err << "Error: " << hu_last_error() << endl; J.failed = true; break; }
+				if (!batch || J.maxLen > batchMaxLen) {
+					if (batch) hu_batch_destroy(batch);
+					batch = NULL;
+					batchMaxLen = max(J.maxLen + J.maxLen / 4, 64);
+					HU_JOB(hu_batch_create(&batch, wdb, batchSize, batchMaxLen, paired ? 1 : 0));
+				}
+				const hu_read_batch rb = {n, paired ? 1 : 0, J.hb.codes.data(), J.hb.offsets.data(), J.hb.vpaths.data(), J.hb.nPaths.data()};
+				HU_JOB(hu_batch_upload(batch, &rb));
+				if (alignOnly) { HU_JOB(hu_align_batch(batch, mode)); }
+				else { HU_JOB(hu_assign_batch(batch, mode, &sp)); }
+				const int nSeq = n * (paired ? 2 : 1);
+				vector<hu_align_row> rows(nSeq);
+				vector<int64_t> traceOff(nSeq + 1);
+				vector<char> traces((size_t) nSeq * (batchMaxLen + hmm.getProfileSize() + 8));
+				HU_JOB(hu_batch_get_align(batch, rows.data(), traces.data(), (int64_t) traces.size(), traceOff.data()));
+				vector<hu_place_row> best(n);
+				if (!alignOnly) HU_JOB(hu_batch_get_best(batch, best.data()));
+				// ---- --chimera-info (src/hmmufotu.cpp:653-691): segment placements over the common seeds ----
+				vector<PTUnrooted::PTPlacement> seg5(n), seg3(n);
+				vector<char> segDone(n, 0);
+				if (chimeraInfo && !alignOnly) {
+					vector<hu_align_row> merged(n);
+					HU_JOB(hu_batch_get_merged(batch, merged.data()));
+					vector<int8_t> codes((size_t) n * csLen);
+					HU_JOB(hu_batch_get_aligned_codes(batch, codes.data()));
+					vector<int32_t> nSeeds(n), ids((size_t) n * sp.maxNSeed);
+					HU_JOB(hu_batch_get_seeds(batch, nSeeds.data(), ids.data(), NULL));
+					const int nRows = n * numSeg;
+					if (!segBatch) HU_JOB(hu_batch_create(&segBatch, wdb, batchSize * numSeg, batchMaxLen, 0));
+					vector<int8_t> codes2((size_t) nRows * csLen);
+					vector<int32_t> st(nRows), en(nRows), nSeeds2(nRows), ids2((size_t) nRows * HU_MAX_SEED, 0);
+					for (int i = 0; i < n; ++i) {
+						const bool ok = !(merged[i].flags & (HU_ALIGN_INVALID | HU_ALIGN_CHIMERA));
+						const int segLen = (merged[i].csEnd - merged[i].csStart + 1) / numSeg;
+						for (int sg = 0; sg < numSeg; ++sg) {
+							const int q = i * numSeg + sg;
+							memcpy(&codes2[(size_t) q * csLen], &codes[(size_t) i * csLen], csLen);
+							const int segStart = merged[i].csStart + sg * segLen, segEnd = segStart + segLen - 1; // 1-based, :660-661
+							st[q] = ok && segLen > 0 ? segStart - 1 : -1; en[q] = ok && segLen > 0 ? segEnd - 1 : -1;
+							nSeeds2[q] = ok ? max(nSeeds[i], 0) : 0;
+							for (int k = 0; k < nSeeds2[q]; ++k) ids2[(size_t) q * HU_MAX_SEED + k] = ids[(size_t) i * sp.maxNSeed + k];
+						}
+					}
+					hu_sep_params sp2 = sp;
+					sp2.maxNSeed = HU_MAX_SEED; // row pitch of the setters / getters below
+					sp2.maxError = maxChimeraError;
+					HU_JOB(hu_batch_set_aligned(segBatch, nRows, codes2.data(), st.data(), en.data()));
+					HU_JOB(hu_seed_batch(segBatch, &sp2)); // sizes the seed rows of the workspace; replaced by the common seeds
+					HU_JOB(hu_batch_set_seeds(segBatch, nSeeds2.data(), ids2.data()));
+					HU_JOB(hu_estimate_batch(segBatch, &sp2));
+					HU_JOB(hu_place_batch(segBatch, &sp2));
+					vector<int32_t> nk(nRows);
+					vector<hu_place_row> rows2((size_t) nRows * HU_MAX_SEED);
+					HU_JOB(hu_batch_get_places(segBatch, nk.data(), rows2.data()));
+					for (int i = 0; i < n; ++i) {
+						vector<PTUnrooted::PTPlacement> p5, p3;
+						for (int sg = 0; sg < numSeg; ++sg)
+							for (int k = 0; k < nk[i * numSeg + sg]; ++k)
+								(sg < numSeg / 2 ? p5 : p3).push_back(ptu.toPlacement(rows2[(size_t) (i * numSeg + sg) * HU_MAX_SEED + k]));
+						if (p5.empty() || p3.empty()) continue;
+						std::sort(p5.rbegin(), p5.rend(), compareByLoglik); // :674-675
+						std::sort(p3.rbegin(), p3.rend(), compareByLoglik);
+						seg5[i] = p5[0]; seg3[i] = p3[0]; segDone[i] = 1;
+					}
+				}
+#undef HU_JOB
+				for (int i = 0; i < n; ++i) {
+					const PrimarySeq& f = J.hb.fwd[i];
+					if (rows[i].flags & HU_ALIGN_INVALID) { err << "Warning: read '" << f.getId() << "' could not be aligned, skipped" << endl; continue; }
+					BandedHMMP7::HmmAlignment al = hmm.buildGlobalAlign(f, rows[i], traces.data() + traceOff[i]);
+					bool isChimera = false;
+					if (paired) {
+						if (rows[n + i].flags & HU_ALIGN_INVALID) { err << "Warning: mate of '" << f.getId() << "' could not be aligned, skipped" << endl; continue; }
+						const BandedHMMP7::HmmAlignment revAln = hmm.buildGlobalAlign(J.hb.rev[i], rows[n + i], traces.data() + traceOff[n + i]);
+						if (!ignoreOrient && !(al.csStart <= revAln.csStart && al.csEnd <= revAln.csEnd)) {
+							err << "Warning: Bad orientation of forward/reverse read detected, treating as chimera" << endl;
+							isChimera = true;
+						} else
+							al.merge(revAln);
+					}
+					PTUnrooted::PTPlacement bestPlace;
+					bestPlace.taxonName = "NULL";
+					if (!alignOnly && !isChimera && best[i].nPlaces > 0) bestPlace = ptu.toPlacement(best[i]);
+					if (isChimera && !wantChi) continue; // chimera reads go to --chimera-out only, :693-706
+					if (!isChimera && wantAln) {
+						tAln << ">" << f.getId() << " " << f.getDesc() << ";csStart=" << al.csStart << ";csEnd=" << al.csEnd << ";" << endl;
+						for (size_t o = 0; o < al.align.length(); o += 60) // SeqIO::writeFastaSeq, DEFAULT_MAX_LINE = 60 (src/SeqIO.cpp:121-132)
+							tAln << al.align.substr(o, 60) << '\n';
+					}
+					ostream& dst = isChimera ? (ostream&) tChi : (ostream&) tOut;
+					dst << f.getId() << "\t" << f.getDesc() << "\t" << al << "\t";
+					if (chimeraInfo) {
+						// chimera_lod = (best5 - alt5) + (best3 - alt3), where alt is the SAME window placed on the other segment's
+						// branch: placeSeq returns the same constant for both, so the sum is exactly 0 (:676-689)
+						const double chimeraLod = segDone[i] ? (seg5[i].loglik - seg5[i].loglik) + (seg3[i].loglik - seg3[i].loglik) : numeric_limits<double>::quiet_NaN();
+						dst << seg5[i].getTaxonId() << "\t" << seg3[i].getTaxonId() << "\t" << (segDone[i] ? seg5[i].taxonName : string("NULL")) << "\t"
+						    << (segDone[i] ? seg3[i].taxonName : string("NULL")) << "\t" << chimeraLod << "\t";
+					}
+					dst << bestPlace << endl;
+				}
+			} while (false);
+			J.outText = tOut.str(); J.chiText = tChi.str(); J.alnText = tAln.str(); J.errText = err.str();
+			vector<PrimarySeq>().swap(J.hb.fwd); vector<PrimarySeq>().swap(J.hb.rev);
+			done.push(job);
 		}
-		const hu_read_batch rb = {n, paired ? 1 : 0, hb.codes.data(), hb.offsets.data(), hb.vpaths.data(), hb.nPaths.data()};
-		HU_CHECK(hu_batch_upload(batch, &rb));
-		if (alignOnly) HU_CHECK(hu_align_batch(batch, mode));
-		else HU_CHECK(hu_assign_batch(batch, mode, &sp));
-		const int nSeq = n * (paired ? 2 : 1);
-		vector<hu_align_row> rows(nSeq), merged(n);
-		vector<int64_t> traceOff(nSeq + 1);
-		vector<char> traces((size_t) nSeq * (batchMaxLen + hmm.getProfileSize() + 8));
-		HU_CHECK(hu_batch_get_align(batch, rows.data(), traces.data(), (int64_t) traces.size(), traceOff.data()));
-		HU_CHECK(hu_batch_get_merged(batch, merged.data()));
-		vector<hu_place_row> best(n);
-		if (!alignOnly) HU_CHECK(hu_batch_get_best(batch, best.data()));
-		for (int i = 0; i < n; ++i) {
-			const PrimarySeq& f = hb.fwd[i];
-			if (rows[i].flags & HU_ALIGN_INVALID) { cerr << "Warning: read '" << f.getId() << "' could not be aligned, skipped" << endl; continue; }
-			BandedHMMP7::HmmAlignment aln = hmm.buildGlobalAlign(f, rows[i], traces.data() + traceOff[i]);
-			bool isChimera = false;
-			if (paired) {
-				if (rows[n + i].flags & HU_ALIGN_INVALID) { cerr << "Warning: mate of '" << f.getId() << "' could not be aligned, skipped" << endl; continue; }
-				const BandedHMMP7::HmmAlignment revAln = hmm.buildGlobalAlign(hb.rev[i], rows[n + i], traces.data() + traceOff[n + i]);
-				if (!ignoreOrient && !(aln.csStart <= revAln.csStart && aln.csEnd <= revAln.csEnd)) {
-					cerr << "Warning: Bad orientation of forward/reverse read detected, treating as chimera" << endl;
-					isChimera = true;
-				} else
-					aln.merge(revAln);
-			}
-			PTUnrooted::PTPlacement bestPlace;
-			bestPlace.taxonName = "NULL";
-			if (!alignOnly && !isChimera && best[i].nPlaces > 0) bestPlace = ptu.toPlacement(best[i]);
-			ostream& dst = isChimera ? (ostream&) chiFile : out;
-			if (isChimera && !chiFile.is_open()) continue; // chimera reads go to --chimera-out only, :693-706
-			if (!isChimera && alnFile.is_open()) {
-				ostringstream d;
-				d << f.getDesc() << ";csStart=" << aln.csStart << ";csEnd=" << aln.csEnd << ";";
-				alnFile << ">" << f.getId() << " " << d.str() << endl;
-				for (size_t o = 0; o < aln.align.length(); o += 60) // SeqIO::writeFastaSeq, DEFAULT_MAX_LINE = 60 (src/SeqIO.cpp:121-132)
-					alnFile << aln.align.substr(o, 60) << '\n';
-			}
-			dst << f.getId() << "\t" << f.getDesc() << "\t" << aln << "\t" << bestPlace << endl;
+		if (batch) hu_batch_destroy(batch);
+		if (segBatch) hu_batch_destroy(segBatch);
+	};
+	vector<thread> workers;
+	for (int wk = 0; wk < nWorkers; ++wk) workers.push_back(thread(work, wk));
+	atomic<long> nJobs(-1); // set by the reader when the input is exhausted
+	thread reader([&] {
+		long k = 0;
+		while (fwdSeqI.hasNext() && (!paired || revSeqI.hasNext())) {
+			shared_ptr<Job> job(new Job());
+			job->index = k++;
+			job->n = readBatch(fwdSeqI, revSeqI, paired, rStrand, batchSize, hmm, csfm, seedLen, seedRegion, mode, nThreads, job->hb, job->maxLen);
+			todo.push(job);
 		}
-		nDone += n;
-		if (verbose) cerr << nDone << " reads processed" << endl;
+		nJobs = k;
+		todo.close();
+	});
+	bool anyFailed = false;
+	{
+		map<long, shared_ptr<Job> > parked; // batches that finished ahead of their turn
+		long next = 0, nDone = 0;
+		for (;;) {
+			const long total = nJobs.load();
+			if (total >= 0 && next >= total) break;
+			shared_ptr<Job> job;
+			{
+				unique_lock<mutex> l(done.m);
+				done.cv.wait_for(l, chrono::milliseconds(50), [&] { return !done.q.empty(); });
+				if (!done.q.empty()) { job = done.q.front(); done.q.pop_front(); }
+			}
+			if (job) parked[job->index] = job;
+			while (parked.count(next)) {
+				Job& J = *parked[next];
+				cerr << J.errText;
+				if (J.failed) anyFailed = true;
+				out << J.outText;
+				if (wantChi) chiFile << J.chiText;
+				if (wantAln) alnFile << J.alnText;
+				nDone += J.n;
+				if (verbose) cerr << nDone << " reads processed" << endl;
+				parked.erase(next++);
+			}
+		}
 	}
-	if (batch) hu_batch_destroy(batch);
-	hu_db_destroy(db);
-	return EXIT_SUCCESS;
+	reader.join();
+	for (size_t wk = 0; wk < workers.size(); ++wk) workers[wk].join();
+	for (int g = 0; g < nGpus; ++g) hu_db_destroy(dbs[g]);
+	return anyFailed ? EXIT_FAILURE : EXIT_SUCCESS;
 }

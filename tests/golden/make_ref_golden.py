@@ -127,6 +127,12 @@ def extra():
         os.remove(d + ".ptu")
     for ext in (".msa", ".csfm", ".hmm"):
         os.remove(db + ext)
+    # -C --chimera-info: the segment placements in the output (src/hmmufotu.cpp:653-691, 736-745)
+    d = "gg_70_otus_GTR"
+    with gzip.open(d + ".ptu.gz", "rb") as f, open(d + ".ptu", "wb") as o:
+        shutil.copyfileobj(f, o)
+    run(os.path.join(REF, "hmmufotu"), d, d + "_se0.fasta", "-o", d + "_se0.chimera.tsv", "-s", "1", "-S", "0", "-p", "1", "-C", "--chimera-info")
+    os.remove(d + ".ptu")
 
 
 if __name__ == "__main__":

@@ -44,10 +44,10 @@ def data_lines(path):
     return [ln.rstrip("\n") for ln in open(path) if not ln.startswith("#")]
 
 
-def run_case(name, d, tag, seed, paired, opts=(), variant=""):
+def run_case(name, d, tag, seed, paired, opts=(), variant="", batch=64):
     reads = [os.path.join(GOLD, "%s_%s_%d.fasta" % (name, tag, m)) for m in (1, 2)] if paired else [os.path.join(GOLD, "%s_%s.fasta" % (name, tag))]
     out = os.path.join(d, tag + variant + ".tsv")
-    p = subprocess.run([CLI, os.path.join(d, name)] + reads + ["-o", out, "-s", "1", "-S", str(seed), "--batch", "64"] + list(opts), capture_output=True, text=True)
+    p = subprocess.run([CLI, os.path.join(d, name)] + reads + ["-o", out, "-s", "1", "-S", str(seed), "--batch", str(batch)] + list(opts), capture_output=True, text=True)
     assert p.returncode == 0, p.stderr[-2000:]
     got, want = data_lines(out), data_lines(os.path.join(GOLD, "%s_%s%s.tsv" % (name, tag, variant)))
     assert got[0] == want[0]                      # column header
@@ -87,6 +87,40 @@ def test_chimera_check_changes_no_row(refdb_dir):
     got, want, bad = run_case(name, d, "se0", 0, False, ["-C", "--chimera-out", os.path.join(d, "chi.tsv")])
     assert not bad
     assert [ln for ln in open(os.path.join(d, "chi.tsv")) if not ln.startswith("#")][1:] == []   # header line only
+
+
+def test_chimera_info_tsv_is_the_references(refdb_dir):
+    """-C --chimera-info (src/hmmufotu.cpp:653-691, 736-745): the 5' / 3' segment placements over the read's common seeds
+    (estimateSeq on the segment's columns, filterPlacements(--chimera-err), placeSeq, std::sort by log-likelihood) and the
+    log-odds, five extra columns per row, as the reference's binary writes them"""
+    name, d = refdb_dir
+    if not os.path.exists(os.path.join(GOLD, "%s_se0.chimera.tsv" % name)):
+        pytest.skip("the --chimera-info golden exists for the GTR database only")
+    got, want, bad = run_case(name, d, "se0", 0, False, ["-C", "--chimera-info"], ".chimera")
+    assert not bad, "rows differ from the reference's TSV: %s\n%s\n%s" % (bad[:5], got[bad[0][1]][-400:], want[bad[0][1]][-400:])
+
+
+@pytest.mark.parametrize("batch", [7, 16])
+def test_pipelined_read_loop_keeps_file_order(refdb_dir, batch):
+    """the command line's read loop is a pipeline (reader -> two workspaces per device -> writer): with batches much smaller
+    than the file, several batches are in flight on different workspaces and finish out of order; the TSV must still be the
+    reference's, rows in file order, and the seed search's rand() stream the one of a one-by-one loop"""
+    name, d = refdb_dir
+    reads = os.path.join(GOLD, name + "_se0.fasta")
+    out = os.path.join(d, "se0.b%d.tsv" % batch)
+    p = subprocess.run([CLI, os.path.join(d, name), reads, "-o", out, "-s", "1", "-S", "0", "--batch", str(batch), "-p", "3"], capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr[-2000:]
+    assert data_lines(out) == data_lines(os.path.join(GOLD, name + "_se0.tsv"))
+
+
+def test_two_devices_write_the_same_tsv(refdb_dir):
+    """--gpus 2: the database is built on the first device and cloned device to device; batches are dealt to both"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two devices")
+    name, d = refdb_dir
+    got, want, bad = run_case(name, d, "pe0", 7, True, ["--gpus", "2"], batch=8)
+    assert not bad
 
 
 def test_device_tree_evaluation_matches_the_reference_builder(refdb_dir):

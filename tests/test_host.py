@@ -563,7 +563,7 @@ def test_cli_rejects_what_the_reference_rejects(exes):
         return p.stderr
     assert "even number" in err("-C", "--num-segment", "3")
     assert "--chimera-lod must be non-negative" in err("-C", "--chimera-lod", "-1")
-    assert "--chimera-info" in err("-C", "--chimera-info")
+    assert "--chimera-err must be positive" in err("-C", "--chimera-err", "0")
     assert "Unsupported prior" in err("--prior", "depth")
     assert "Unsupported branch estimating method" in err("-m", "both")
     assert "-L|--seed-len" in err("-L", "99")
