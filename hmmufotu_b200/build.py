@@ -12,15 +12,15 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libhmmufotu_b200.so")
-SOURCES = ["hu_db.cu", "hu_viterbi.cu", "hu_seed.cu", "hu_estimate.cu", "hu_place.cu", "hu_api.cu"]
-HEADERS = ["hu_internal.cuh", "hu_batch.cuh", os.path.join("..", "..", "include", "hmmufotu_b200.h")]
+SOURCES = ["hu_db.cu", "hu_viterbi.cu", "hu_seed.cu", "hu_seedmm.cu", "hu_estimate.cu", "hu_place.cu", "hu_api.cu"]
+HEADERS = ["hu_internal.cuh", "hu_batch.cuh", "hu_mm.cuh", "hu_pipe.cuh", os.path.join("..", "..", "include", "hmmufotu_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xptxas", "-v"] + (["-DHU_PROF"] if os.environ.get("HU_PROF") else [])
 # --fmad=false where results must be bit-identical to the reference's separate multiplies and adds (Viterbi
 # costs) or to the host evaluation of the same code (model matrices, tree evaluation); the SEP kernels are
 # checked to 1e-9 relative and may contract
-NO_FMAD = {"hu_viterbi.cu", "hu_db.cu", "hu_api.cu", "hu_seed.cu"}
+NO_FMAD = {"hu_viterbi.cu", "hu_db.cu", "hu_api.cu", "hu_seed.cu", "hu_seedmm.cu"}
 
 
 def _stale(target: str, deps) -> bool:

@@ -125,6 +125,8 @@ struct hu_batch {
 	int* nodeOfPosH;
 	int nCandH;
 	double heightCached;
+	int8_t* mmB;           // K2 on the tensor cores: operand images of the reads, [ceil(maxReads / 256)][mmChunks][32 KB]
+	int2* mmRange;         // chunk range per read tile
 	double* placeSlab;     // global rho slabs for windows wider than the shared-memory capacity
 	void* estSlab;         // K3: per-CTA g slabs for windows wider than its shared-memory buffer
 	int estSlabCtas;
@@ -142,6 +144,7 @@ struct hu_batch {
 namespace hu {
 int launchViterbi(hu_batch* b, int mode);
 int launchSeed(hu_batch* b, const hu_sep_params* p);
+int launchSeedMm(hu_batch* b, const SeedArgs& a, int* launches);
 int launchEstimate(hu_batch* b, const hu_sep_params* p);
 int launchFilter(hu_batch* b, const hu_sep_params* p);
 int launchPlace(hu_batch* b, const hu_sep_params* p);

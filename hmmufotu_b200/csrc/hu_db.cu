@@ -556,6 +556,33 @@ static int createImpl(hu_db* db, const hu_hmm_params* hp, const hu_tree_desc* td
 	}
 	t.planes = planes;
 	t.seqT = seqT;
+	// ---- the tensor-core form of the scan: operand images in candidate order (hu_seedmm.cu) ----
+	t.mmA = NULL; t.seqTP = NULL; t.mmKeyTab = NULL; t.mmTiles = t.mmChunks = t.posPitch = 0;
+	if (K <= HU_MM_MAX_N) {
+		t.mmTiles = (t.nCand + HU_MM_BM - 1) / HU_MM_BM;
+		t.mmChunks = (K + 31) / 32;
+		t.posPitch = t.mmTiles * HU_MM_BM;
+		std::vector<int> posNode(t.posPitch, -1);
+		for (int x = 0, pos = 0; x < n; ++x)
+			if (x != td->root) posNode[pos++] = x;
+		const int* posNodeDev;
+		HU_TRY(upload(db, &posNodeDev, posNode.data(), posNode.size()));
+		int8_t *mmA, *seqTP;
+		HU_TRY(devAlloc(db, &mmA, (size_t) t.mmTiles * t.mmChunks * HU_MM_A_BYTES));
+		HU_TRY(devAlloc(db, &seqTP, (size_t) csLen * t.posPitch));
+		HU_TRY(buildSeedMm(db, seq, K, mmA, seqTP, posNodeDev));
+		t.mmA = mmA; t.seqTP = seqTP;
+		std::vector<uint4> keyTab(HU_MM_MAX_N + 1, make_uint4(0, 0, 0, 0));
+		for (uint32_t N = 1; N <= HU_MM_MAX_N; ++N) {
+			int bits = 0;
+			while ((1u << bits) <= N) ++bits;
+			const int k = std::max(32, 24 + bits);
+			const unsigned __int128 one = 1;
+			const uint64_t m = N == 1 ? 0 : (uint64_t) (((one << k) + N - 1) / N);
+			keyTab[N] = make_uint4((uint32_t) ((1ull << 31) / N), (uint32_t) ((1ull << 31) % N), (uint32_t) m, (uint32_t) (k - 32));
+		}
+		HU_TRY(upload(db, &t.mmKeyTab, keyTab.data(), keyTab.size()));
+	}
 	return HU_OK;
 }
 
@@ -667,6 +694,7 @@ int hu_db_clone(hu_db** out, hu_db* src, int device) {
 	{
 		int rcA = hu::configViterbiKernels();
 		if (rcA == HU_OK) rcA = hu::configSeedKernels();
+		if (rcA == HU_OK) rcA = hu::configSeedMmKernels();
 		if (rcA == HU_OK) rcA = hu::configEstimateKernels();
 		if (rcA == HU_OK) rcA = hu::configPlaceKernels();
 		if (rcA != HU_OK) return rcA;
@@ -706,6 +734,7 @@ int hu_db_clone(hu_db** out, hu_db* src, int device) {
 	HU_RM(tree.up); HU_RM(tree.dn); HU_RM(tree.upS); HU_RM(tree.dnS); HU_RM(tree.upP32); HU_RM(tree.dnP32);
 	HU_RM(tree.litTab); HU_RM(tree.modelDev); HU_RM(tree.planes); HU_RM(tree.seqT); HU_RM(tree.colK);
 	HU_RM(tree.scanNode); HU_RM(tree.posOfSlot); HU_RM(tree.nodeOfPos); HU_RM(tree.inv2N);
+	HU_RM(tree.mmA); HU_RM(tree.seqTP); HU_RM(tree.mmKeyTab);
 #undef HU_RM
 	*out = db;
 	return HU_OK;
@@ -724,6 +753,7 @@ static int createDb(hu_db** out, const hu_hmm_params* hmm, const hu_tree_desc* t
 	{
 		int rcA = hu::configViterbiKernels();
 		if (rcA == HU_OK) rcA = hu::configSeedKernels();
+		if (rcA == HU_OK) rcA = hu::configSeedMmKernels();
 		if (rcA == HU_OK) rcA = hu::configEstimateKernels();
 		if (rcA == HU_OK) rcA = hu::configPlaceKernels();
 		if (rcA != HU_OK) return rcA;

@@ -7,6 +7,7 @@
 #include <vector>
 #include <algorithm>
 #include "../../include/hmmufotu_b200.h"
+#include "hu_mm.cuh"
 
 #define HU_HD __host__ __device__ __forceinline__
 
@@ -226,6 +227,12 @@ struct TreeDev {
 	int nCand;               // number of candidates (nNodes - 1)
 	int nGapSlots;           // slots [0, nGapSlots) hold nodes whose sequence has gaps (need the valid plane)
 	const double* inv2N;     // [65536]: 2^31 / N correctly rounded (seed keys without a division), inv2N[0] = 0
+	// seed scan on the tensor cores (hu_mm.cuh, hu_seedmm.cu); mmA == NULL: not built (profile longer than HU_MM_MAX_N)
+	const int8_t* mmA;       // [mmTiles][mmChunks][16 KB]: operand images, rows = candidate positions (non-root nodes in id order)
+	const uint4* mmKeyTab;   // [HU_MM_MAX_N + 1]: {Q, R, m, k - 32} per N, the integer form of the seed key (hu_seedmm.cu)
+	const int8_t* seqTP;     // [csLen][posPitch]: node codes transposed into position order (non-match columns are read)
+	int mmTiles, mmChunks;   // ceil(nCand / 128), ceil(K / 32)
+	int posPitch;            // 128 mmTiles
 };
 
 #ifdef __CUDACC__
@@ -253,6 +260,7 @@ int configViterbiKernels();
 int configSeedKernels();
 int configEstimateKernels();
 int configPlaceKernels();
+int configSeedMmKernels();
 
 } // namespace hu
 
@@ -272,3 +280,7 @@ struct hu_db {
 	std::vector<int> scanNodeHost; // slot -> node id of the seed scan order (-1: padding)
 	hu_db() : device(0), bytes(0), deferred(0), K(0), L(0) {}
 };
+
+namespace hu {
+int buildSeedMm(hu_db* db, const int8_t* seq, int K, int8_t* A, int8_t* seqTP, const int* posNode);
+}

@@ -1029,13 +1029,24 @@ int launchSeed(hu_batch* b, const hu_sep_params* p) {
 	HU_CUDA(cudaMemsetAsync(a.rWordHi, 0xff, (size_t) a.nReadsPad * sizeof(int), b->stream));
 	packReadsKernel<<<dim3((a.nReadsPad + 127) / 128, t.nPWords), 128, 0, b->stream>>>(a, t.csLen, db->hmm.K, db->hmm.p2cs);
 	sparseListKernel<<<(b->nReads + 3) / 4, 128, 0, b->stream>>>(a, t.csLen, t.colK);
-	const int groups = a.nReadsPad / HU_SCAN_READS;
-	const size_t smem = (size_t) t.nPWords * HU_SCAN_READS * sizeof(uint4);
-	if (smem > 200 * 1024) { setError("profile too long for the seed-scan read tile (%d words)", t.nPWords); return HU_ERR_ARG; }
-	const int gapTiles = t.nGapSlots / HU_SCAN_TILE, allTiles = t.scanPitch / HU_SCAN_TILE;
-	// grid.x (fast) runs over read groups so that consecutive CTAs reuse the same node tile from L2
-	if (gapTiles > 0) seedScanKernel<true><<<dim3(groups, gapTiles), 128, smem, b->stream>>>(a, t, 0);
-	if (allTiles > gapTiles) seedScanKernel<false><<<dim3(groups, allTiles - gapTiles), 128, smem, b->stream>>>(a, t, gapTiles);
+	// the scan: on the tensor cores (hu_seedmm.cu) when the key vector is the plain candidate vector; the bit-plane kernel for
+	// the compacted vector of the literal order under -H, for profiles the packed accumulator cannot hold, or on request
+	static int scanPref = -1; // HU_SEED_SCAN=popc forces the bit-plane kernel (A/B measurements, parity tests between the two)
+	{ const char* e = getenv("HU_SEED_SCAN"); scanPref = (e && !strcmp(e, "popc")) ? 1 : 0; }
+	int scanLaunches = 0;
+	if (t.mmA && b->mmB && a.posOfSlot == t.posOfSlot && scanPref == 0) {
+		int rcM = launchSeedMm(b, a, &scanLaunches);
+		if (rcM != HU_OK) return rcM;
+	} else {
+		const int groups = a.nReadsPad / HU_SCAN_READS;
+		const size_t smem = (size_t) t.nPWords * HU_SCAN_READS * sizeof(uint4);
+		if (smem > 200 * 1024) { setError("profile too long for the seed-scan read tile (%d words)", t.nPWords); return HU_ERR_ARG; }
+		const int gapTiles = t.nGapSlots / HU_SCAN_TILE, allTiles = t.scanPitch / HU_SCAN_TILE;
+		// grid.x (fast) runs over read groups so that consecutive CTAs reuse the same node tile from L2
+		if (gapTiles > 0) seedScanKernel<true><<<dim3(groups, gapTiles), 128, smem, b->stream>>>(a, t, 0);
+		if (allTiles > gapTiles) seedScanKernel<false><<<dim3(groups, allTiles - gapTiles), 128, smem, b->stream>>>(a, t, gapTiles);
+		scanLaunches = (gapTiles > 0) + (allTiles > gapTiles);
+	}
 	HU_CUDA(cudaEventRecord(b->ev[3], b->stream));
 	if (literal) {
 		int sms = 0;
@@ -1058,7 +1069,7 @@ int launchSeed(hu_batch* b, const hu_sep_params* p) {
 	} else
 		seedSelectKernel<<<b->nReads, HU_SEL_THREADS, 0, b->stream>>>(a, t.scanPitch, t.nodeOfPos);
 	HU_CUDA(cudaEventRecord(b->ev[4], b->stream));
-	b->launches += 3 + (gapTiles > 0) + (allTiles > gapTiles);
+	b->launches += 3 + scanLaunches;
 	HU_CUDA(cudaGetLastError());
 	return HU_OK;
 }
