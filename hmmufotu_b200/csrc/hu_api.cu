@@ -245,11 +245,15 @@ int hu_batch_create(hu_batch** out, hu_db* db, int32_t maxReads, int32_t maxSeqL
 	HU_TRY(balloc(b, &b->seed.sparse, (size_t) maxReads * b->seed.sparseCap));
 	HU_TRY(balloc(b, &b->seed.keys, (size_t) maxReads * t.scanPitch));
 	HU_CUDA(cudaMemset(b->seed.keys, 0xff, (size_t) maxReads * t.scanPitch * sizeof(uint32_t))); // tail positions stay excluded
-	b->mmB = NULL; b->mmRange = NULL;
+	b->mmB = NULL; b->mmRange = NULL; b->mmMode = b->mmTileExt = b->mmCols = b->mmColReads = NULL;
 	if (t.mmA) {
 		const int numNt = (maxReads + HU_MM_BN - 1) / HU_MM_BN;
-		HU_TRY(balloc(b, &b->mmB, (size_t) numNt * t.mmChunks * HU_MM_B_BYTES));
+		HU_TRY(balloc(b, &b->mmB, (size_t) numNt * (t.mmChunks + 1) * HU_MM_B_BYTES));
 		HU_TRY(balloc(b, &b->mmRange, (size_t) numNt));
+		HU_TRY(balloc(b, &b->mmMode, (size_t) nReadsPad));
+		HU_TRY(balloc(b, &b->mmTileExt, (size_t) numNt));
+		HU_TRY(balloc(b, &b->mmCols, (size_t) 3 * (t.csLen + 1)));
+		HU_TRY(balloc(b, &b->mmColReads, (size_t) maxReads * 64));
 	}
 	HU_TRY(balloc(b, &b->seed.seedIds, (size_t) maxReads * HU_MAX_SEED));
 	HU_TRY(balloc(b, &b->seed.nSeeds, (size_t) maxReads));

@@ -127,6 +127,10 @@ struct hu_batch {
 	double heightCached;
 	int8_t* mmB;           // K2 on the tensor cores: operand images of the reads, [ceil(maxReads / 256)][mmChunks][32 KB]
 	int2* mmRange;         // chunk range per read tile
+	int* mmMode;           // per read: 0 no non-match base, 1 extension chunk, 2 raw + fix-up, -1 unplaced
+	int* mmTileExt;        // per read tile: takes the extension chunk
+	int* mmCols;           // [3][csLen + 1]: per-column counts / cursors, starts of mmColReads, starts of the exception work items
+	int* mmColReads;       // reads with an entry in a column that has exceptions, grouped by column
 	double* placeSlab;     // global rho slabs for windows wider than the shared-memory capacity
 	void* estSlab;         // K3: per-CTA g slabs for windows wider than its shared-memory buffer
 	int estSlabCtas;

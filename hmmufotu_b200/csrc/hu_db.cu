@@ -557,20 +557,34 @@ static int createImpl(hu_db* db, const hu_hmm_params* hp, const hu_tree_desc* td
 	t.planes = planes;
 	t.seqT = seqT;
 	// ---- the tensor-core form of the scan: operand images in candidate order (hu_seedmm.cu) ----
-	t.mmA = NULL; t.seqTP = NULL; t.mmKeyTab = NULL; t.mmTiles = t.mmChunks = t.posPitch = 0;
-	if (K <= HU_MM_MAX_N) {
+	t.mmA = NULL; t.seqTP = NULL; t.mmKeyTab = NULL; t.mmColDefault = NULL; t.mmExcPtr = t.mmExcPos = t.mmSlotOfPos = NULL; t.mmTiles = t.mmChunks = t.posPitch = 0;
+	if (K <= HU_MM_MAX_N - 64) {
 		t.mmTiles = (t.nCand + HU_MM_BM - 1) / HU_MM_BM;
 		t.mmChunks = (K + 31) / 32;
 		t.posPitch = t.mmTiles * HU_MM_BM;
-		std::vector<int> posNode(t.posPitch, -1);
+		std::vector<int> posNode(t.posPitch, -1), slotOfPos(t.posPitch, 0);
 		for (int x = 0, pos = 0; x < n; ++x)
 			if (x != td->root) posNode[pos++] = x;
+		for (size_t sl = 0; sl < scanNode.size(); ++sl)
+			if (scanNode[sl] >= 0) {
+				int pos = scanNode[sl] - (scanNode[sl] > td->root ? 1 : 0);
+				slotOfPos[pos] = (int) sl;
+			}
+		std::vector<int8_t> posClass, colDefault;
+		std::vector<int> excPtr, excPos;
+		seedMmColumns(hs, csLen, colK.data(), posNode, t.nCand, posClass, colDefault, excPtr, excPos);
 		const int* posNodeDev;
+		const int8_t* posClassDev;
 		HU_TRY(upload(db, &posNodeDev, posNode.data(), posNode.size()));
+		HU_TRY(upload(db, &posClassDev, posClass.data(), posClass.size()));
+		HU_TRY(upload(db, &t.mmSlotOfPos, slotOfPos.data(), slotOfPos.size()));
+		HU_TRY(upload(db, &t.mmColDefault, colDefault.data(), colDefault.size()));
+		HU_TRY(upload(db, &t.mmExcPtr, excPtr.data(), excPtr.size()));
+		HU_TRY(upload(db, &t.mmExcPos, excPos.data(), excPos.size()));
 		int8_t *mmA, *seqTP;
-		HU_TRY(devAlloc(db, &mmA, (size_t) t.mmTiles * t.mmChunks * HU_MM_A_BYTES));
+		HU_TRY(devAlloc(db, &mmA, (size_t) t.mmTiles * (t.mmChunks + 1) * HU_MM_A_BYTES));
 		HU_TRY(devAlloc(db, &seqTP, (size_t) csLen * t.posPitch));
-		HU_TRY(buildSeedMm(db, seq, K, mmA, seqTP, posNodeDev));
+		HU_TRY(buildSeedMm(db, seq, K, mmA, seqTP, posNodeDev, posClassDev));
 		t.mmA = mmA; t.seqTP = seqTP;
 		std::vector<uint4> keyTab(HU_MM_MAX_N + 1, make_uint4(0, 0, 0, 0));
 		for (uint32_t N = 1; N <= HU_MM_MAX_N; ++N) {
@@ -735,6 +749,7 @@ int hu_db_clone(hu_db** out, hu_db* src, int device) {
 	HU_RM(tree.litTab); HU_RM(tree.modelDev); HU_RM(tree.planes); HU_RM(tree.seqT); HU_RM(tree.colK);
 	HU_RM(tree.scanNode); HU_RM(tree.posOfSlot); HU_RM(tree.nodeOfPos); HU_RM(tree.inv2N);
 	HU_RM(tree.mmA); HU_RM(tree.seqTP); HU_RM(tree.mmKeyTab);
+	HU_RM(tree.mmColDefault); HU_RM(tree.mmExcPtr); HU_RM(tree.mmExcPos); HU_RM(tree.mmSlotOfPos);
 #undef HU_RM
 	*out = db;
 	return HU_OK;

@@ -231,7 +231,11 @@ struct TreeDev {
 	const int8_t* mmA;       // [mmTiles][mmChunks][16 KB]: operand images, rows = candidate positions (non-root nodes in id order)
 	const uint4* mmKeyTab;   // [HU_MM_MAX_N + 1]: {Q, R, m, k - 32} per N, the integer form of the seed key (hu_seedmm.cu)
 	const int8_t* seqTP;     // [csLen][posPitch]: node codes transposed into position order (non-match columns are read)
-	int mmTiles, mmChunks;   // ceil(nCand / 128), ceil(K / 32)
+	const int8_t* mmColDefault; // [csLen]: -1 match column, 0..3 majority base of the gap-free nodes, 4: long exception list
+	const int* mmExcPtr;     // [csLen + 1], mmExcPos: positions that deviate from their class default in a non-match column
+	const int* mmExcPos;
+	const int* mmSlotOfPos;  // [posPitch]: position -> slot of the bit planes
+	int mmTiles, mmChunks;   // ceil(nCand / 128), ceil(K / 32) (+ 1 extension chunk per tile image)
 	int posPitch;            // 128 mmTiles
 };
 
@@ -282,5 +286,7 @@ struct hu_db {
 };
 
 namespace hu {
-int buildSeedMm(hu_db* db, const int8_t* seq, int K, int8_t* A, int8_t* seqTP, const int* posNode);
+int buildSeedMm(hu_db* db, const int8_t* seq, int K, int8_t* A, int8_t* seqTP, const int* posNode, const int8_t* posClass);
+void seedMmColumns(const int8_t* hs, int csLen, const int* colK, const std::vector<int>& posNode, int nCand,
+		std::vector<int8_t>& posClass, std::vector<int8_t>& colDefault, std::vector<int>& excPtr, std::vector<int>& excPos);
 }

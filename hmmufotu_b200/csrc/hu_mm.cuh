@@ -51,6 +51,8 @@ struct MmArgs {
 	const int8_t* B;   // [numNt][nChunks][HU_MM_B_BYTES]
 	const int2* range; // [numNt]: first and last chunk any read of the tile has a base in (first > last: none)
 	int numMt, numNt, nChunks;
+	const int* tileExt; // [numNt] or NULL: the tile also takes the extension chunk `extChunk` (after its range)
+	int extChunk;
 };
 
 #ifdef __CUDACC__
@@ -123,7 +125,9 @@ __global__ void __launch_bounds__(HU_MM_THREADS, 1) seedMmKernel(MmArgs g, Epi e
 			for (int item = blockIdx.x; item < nItems; item += gridDim.x) {
 				const int mt = item / g.numNt, nt = item - mt * g.numNt;
 				const int2 rg = g.range[nt];
-				for (int kc = rg.x; kc <= rg.y; ++kc) {
+				const int last = (rg.x <= rg.y && g.tileExt && g.tileExt[nt]) ? rg.y + 1 : rg.y;
+				for (int kk = rg.x; kk <= last; ++kk) {
+					const int kc = kk > rg.y ? g.extChunk : kk;
 					mbarWaitRelaxed(&empty[stage], ph ^ 1u);
 					uint8_t* st = ring + (size_t) stage * HU_MM_STAGE_BYTES;
 					mbarArriveExpectTx(&full[stage], HU_MM_STAGE_BYTES);
@@ -144,7 +148,8 @@ __global__ void __launch_bounds__(HU_MM_THREADS, 1) seedMmKernel(MmArgs g, Epi e
 				mbarWait(&accEmpty[acc], accPh ^ 1u);
 				tcFenceAfter();
 				const uint32_t d = tmem + (uint32_t) acc * HU_MM_BN;
-				for (int kc = rg.x; kc <= rg.y; ++kc) {
+				const int last = (g.tileExt && g.tileExt[nt]) ? rg.y + 1 : rg.y;
+				for (int kc = rg.x; kc <= last; ++kc) {
 					mbarWait(&full[stage], ph);
 					tcFenceAfter();
 					const uint32_t sa = smemAddr(ring + (size_t) stage * HU_MM_STAGE_BYTES);

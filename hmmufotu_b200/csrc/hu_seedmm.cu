@@ -2,14 +2,26 @@
 // as an int8 contraction on the 5th-generation tensor cores (hu_mm.cuh), with the seed key made in the epilogue.
 //
 //   database creation : node sequences -> operand A images (rows = getSeed's candidate positions, i.e. the non-root nodes in
-//                       id order; K = 4 bytes per profile match column), and a position-ordered transpose of the sequences
+//                       id order; K = 4 bytes per profile match column) + one extension chunk per tile (below)
 //   per batch         : aligned reads -> operand B images (the read's bases inside its window), chunk range per read tile
 //   seedMmKernel      : S = A . B^T per (position, read) -> d, N -> key floor(d 2^31 / N), written in candidate order:
 //                       a warp's 32 lanes hold 32 consecutive positions of one read = one 128-byte line per store
-//   seedMmFixupKernel : reads with bases in NON-match columns (insertions buildGlobalAlign could place): the epilogue leaves
-//                       (d << 16 | N) for them and this pass adds those columns from the transposed sequences, then makes the key
+//
+// Read bases in NON-match columns (insertions buildGlobalAlign could place; pDist counts them like any column).  They are
+// few per read (about one for a 250-base amplicon read) but the node side is dense there for inferred sequences, which have
+// a base in every column.  Three tiers, all exact:
+//   1. the default.  Nodes are split by class: 1 = the sequence has no gap at all (inferred, internal nodes), 0 = the others
+//      (leaves: a non-match column is a gap for nearly all of them).  Per non-match column c the class-1 nodes have a majority
+//      base g_c.  With every class-1 node at its default and every class-0 node at a gap, an entry (c, b) of a read adds
+//      class * (16384 + (b == g_c ? 3 : -1)) to S: rank one per entry, so it rides in the contraction as an extension
+//      chunk: A row = class * (-128, 1) x 64, B row = (-128, +3 | -1) per entry.  No epilogue work.
+//   2. the exceptions.  Per column the positions that deviate from their class default are listed at database creation
+//      (a fraction of a per cent).  For the reads of the batch that have an entry in a column, the (exception position, read)
+//      pairs are recomputed from the bit planes and overwrite the tile kernel's key (seedMmExceptionKernel).
+//   3. reads with an entry in a column whose exception list is long (a non-match column that many leaves occupy), or with more
+//      than 64 entries: the epilogue leaves (d << 16 | N) and seedMmFixupKernel adds the columns from the transposed sequences.
 // Keys are bit-identical to seedScanKernel's (tests/test_gpu_mm.py); that kernel remains for profiles longer than
-// HU_MM_MAX_N match columns and for the compacted candidate vector of the literal seed order under -H/--max-height.
+// HU_MM_MAX_N - 64 match columns and for the compacted candidate vector of the literal seed order under -H/--max-height.
 #include <stdlib.h>
 #include <string.h>
 #include "hu_batch.cuh"
@@ -23,25 +35,32 @@ __device__ __forceinline__ uint32_t mmMakeKey(int d, int N, bool excluded, const
 	return (excluded || N <= 0) ? 0xFFFFFFFFu : __double2uint_rd(q);
 }
 
-// ---- operand A: one thread per (position, chunk) ----
+// ---- operand A: one thread per (position, chunk); chunk `stride - 1` is the extension chunk ----
 __global__ void __launch_bounds__(HU_MM_BM) mmPackNodesKernel(const int8_t* __restrict__ seq, int csLen, int K, const int* __restrict__ p2cs,
-		const int* __restrict__ posNode, int nChunks, int8_t* __restrict__ A) {
+		const int* __restrict__ posNode, const int8_t* __restrict__ posClass, int stride, int8_t* __restrict__ A) {
 	const int mt = blockIdx.x, kc = blockIdx.y, row = threadIdx.x;
-	const int node = __ldg(posNode + mt * HU_MM_BM + row);
+	const int p = mt * HU_MM_BM + row;
+	const int node = __ldg(posNode + p);
 	uint32_t w[32];
+	if (kc == stride - 1) {
+		const uint32_t v = (node >= 0 && posClass[p]) ? 0x01800180u : 0u; // (-128, 1, -128, 1)
 #pragma unroll
-	for (int i = 0; i < 32; ++i) {
-		const int k = kc * 32 + i + 1;
-		w[i] = (node >= 0 && k <= K) ? mmBaseWord(seq[(size_t) node * csLen + __ldg(p2cs + k) - 1]) : 0u;
+		for (int i = 0; i < 32; ++i) w[i] = v;
+	} else {
+#pragma unroll
+		for (int i = 0; i < 32; ++i) {
+			const int k = kc * 32 + i + 1;
+			w[i] = (node >= 0 && k <= K) ? mmBaseWord(seq[(size_t) node * csLen + __ldg(p2cs + k) - 1]) : 0u;
+		}
 	}
-	uint8_t* img = reinterpret_cast<uint8_t*>(A) + ((size_t) mt * nChunks + kc) * HU_MM_A_BYTES;
+	uint8_t* img = reinterpret_cast<uint8_t*>(A) + ((size_t) mt * stride + kc) * HU_MM_A_BYTES;
 #pragma unroll
 	for (int c = 0; c < 8; ++c)
 		*reinterpret_cast<uint4*>(img + mmTileOffset(row, c * 16)) = make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
 }
 
 // ---- operand B: one thread per (read, chunk); rows past the batch and reads without a window are zero ----
-__global__ void __launch_bounds__(128) mmPackReadsKernel(SeedArgs a, int L, int K, const int* __restrict__ p2cs, int nChunks, int8_t* __restrict__ B) {
+__global__ void __launch_bounds__(128) mmPackReadsKernel(SeedArgs a, int L, int K, const int* __restrict__ p2cs, int stride, int8_t* __restrict__ B) {
 	const int r = blockIdx.x * 128 + threadIdx.x, kc = blockIdx.y;
 	const bool ok = r < a.nReads && a.winStart[r] >= 0;
 	const int s = ok ? a.winStart[r] : 0, e = ok ? a.winEnd[r] : -1;
@@ -58,7 +77,47 @@ __global__ void __launch_bounds__(128) mmPackReadsKernel(SeedArgs a, int L, int 
 		w[i] = v;
 	}
 	const int nt = r / HU_MM_BN, row = r - nt * HU_MM_BN;
-	uint8_t* img = reinterpret_cast<uint8_t*>(B) + ((size_t) nt * nChunks + kc) * HU_MM_B_BYTES;
+	uint8_t* img = reinterpret_cast<uint8_t*>(B) + ((size_t) nt * stride + kc) * HU_MM_B_BYTES;
+#pragma unroll
+	for (int c = 0; c < 8; ++c)
+		*reinterpret_cast<uint4*>(img + mmTileOffset(row, c * 16)) = make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
+}
+
+// ---- the extension chunk of operand B and the read's tier; one thread per read row ----
+// mode: 0 no entry, 1 entries in the extension chunk (tiers 1 + 2), 2 raw (tier 3), -1 sparse list overflow (read unplaced)
+__global__ void __launch_bounds__(128) mmPackExtKernel(SeedArgs a, TreeDev t, int stride, int8_t* __restrict__ B, int* __restrict__ mode,
+		int* __restrict__ tileExt, int* __restrict__ colCount) {
+	const int r = blockIdx.x * 128 + threadIdx.x;
+	const int nt = r / HU_MM_BN, row = r - nt * HU_MM_BN;
+	const int ns = (r < a.nReads && a.winStart[r] >= 0) ? a.nSparse[r] : 0;
+	const uint32_t* sp = a.sparse + (size_t) (r < a.nReads ? r : 0) * a.sparseCap;
+	int m = ns < 0 ? -1 : (ns == 0 ? 0 : (ns <= 64 ? 1 : 2));
+	for (int i = 0; m == 1 && i < ns; ++i)
+		if (__ldg(t.mmColDefault + (sp[i] >> 8)) > 3) m = 2; // a column with a long exception list
+	uint32_t w[32];
+#pragma unroll
+	for (int i = 0; i < 32; ++i) w[i] = 0u;
+	if (m == 1) {
+#pragma unroll
+		for (int i = 0; i < 32; ++i) { // two entries per word: (-128, +3 | -1) each
+			uint32_t v = 0u;
+#pragma unroll
+			for (int hlf = 0; hlf < 2; ++hlf) {
+				const int e = 2 * i + hlf;
+				if (e < ns) {
+					const uint32_t ent = sp[e];
+					const int col = (int) (ent >> 8), rb = (int) (ent & 0xff);
+					const uint32_t pair = 0x80u | ((rb == (int) __ldg(t.mmColDefault + col) ? 0x03u : 0xffu) << 8);
+					v |= pair << (16 * hlf);
+					if (__ldg(t.mmExcPtr + col + 1) > __ldg(t.mmExcPtr + col)) atomicAdd(colCount + col, 1);
+				}
+			}
+			w[i] = v;
+		}
+		atomicOr(tileExt + nt, 1);
+	}
+	if (r < a.nReadsPad) mode[r] = m;
+	uint8_t* img = reinterpret_cast<uint8_t*>(B) + ((size_t) nt * stride + (stride - 1)) * HU_MM_B_BYTES;
 #pragma unroll
 	for (int c = 0; c < 8; ++c)
 		*reinterpret_cast<uint4*>(img + mmTileOffset(row, c * 16)) = make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
@@ -87,7 +146,7 @@ __global__ void __launch_bounds__(HU_MM_BN) mmRangeKernel(SeedArgs a, int2* __re
 struct KeyEpi {
 	uint32_t* keys;
 	int pitch, nReads, nNodes;
-	const int* nSparse;
+	const int* mode;
 	const int* nodeOfPos;
 	const double* height;
 	const uint4* keyTab; // [HU_MM_MAX_N + 1]
@@ -109,9 +168,9 @@ struct KeyEpi {
 		const int p = mt * HU_MM_BM + row;
 		const int r0 = nt * HU_MM_BN + col0;
 		const int rl = r0 + lane;
-		const int ns = rl < nReads ? __ldg(nSparse + rl) : 0;
-		const unsigned rawMask = __ballot_sync(0xffffffffu, ns > 0);   // finished by seedMmFixupKernel
-		const unsigned badMask = __ballot_sync(0xffffffffu, ns < 0);   // sparse list overflow: the read stays unplaced
+		const int md = rl < nReads ? __ldg(mode + rl) : 0;
+		const unsigned rawMask = __ballot_sync(0xffffffffu, md == 2);  // finished by seedMmFixupKernel
+		const unsigned badMask = __ballot_sync(0xffffffffu, md < 0);   // sparse list overflow: the read stays unplaced
 		const bool plain = !__any_sync(0xffffffffu, excl || p >= pitch) && rawMask == 0u && badMask == 0u && r0 + 32 <= nReads;
 		uint32_t* out = keys + (size_t) r0 * pitch + p;
 		if (plain) { // the common case: no per-key tests
@@ -135,35 +194,117 @@ struct KeyEpi {
 	}
 };
 
-// reads with bases in non-match columns: (d << 16 | N) -> + those columns -> key; four positions per thread
-__global__ void __launch_bounds__(256) seedMmFixupKernel(SeedArgs a, TreeDev t, int pitch) {
-	const int r = blockIdx.y;
+// tier 3: (d << 16 | N) -> + the read's non-match columns -> key; one CTA per read (the others leave at once), four positions per thread
+__global__ void __launch_bounds__(256) seedMmFixupKernel(SeedArgs a, TreeDev t, int pitch, const int* __restrict__ mode) {
+	const int r = blockIdx.x;
+	if (mode[r] != 2) return;
 	const int ns = a.nSparse[r];
-	if (ns <= 0) return;
-	const int p = (blockIdx.x * 256 + threadIdx.x) * 4;
-	if (p >= t.posPitch) return; // positions past the last tile keep their 0xFFFFFFFF
-	uint4* kp = reinterpret_cast<uint4*>(a.keys + (size_t) r * pitch + p);
-	const uint4 raw = *kp;
-	int dd[4] = {(int) (raw.x >> 16), (int) (raw.y >> 16), (int) (raw.z >> 16), (int) (raw.w >> 16)};
-	int nn[4] = {(int) (raw.x & 0xffff), (int) (raw.y & 0xffff), (int) (raw.z & 0xffff), (int) (raw.w & 0xffff)};
+	const uint32_t* sp = a.sparse + (size_t) r * a.sparseCap;
+	for (int p = threadIdx.x * 4; p < t.posPitch; p += 1024) { // positions past the last tile keep their 0xFFFFFFFF
+		uint4* kp = reinterpret_cast<uint4*>(a.keys + (size_t) r * pitch + p);
+		const uint4 raw = *kp;
+		int dd[4] = {(int) (raw.x >> 16), (int) (raw.y >> 16), (int) (raw.z >> 16), (int) (raw.w >> 16)};
+		int nn[4] = {(int) (raw.x & 0xffff), (int) (raw.y & 0xffff), (int) (raw.z & 0xffff), (int) (raw.w & 0xffff)};
+		for (int i = 0; i < ns; ++i) {
+			const uint32_t e = __ldg(sp + i);
+			const int rb = (int) (e & 0xff);
+			const char4 nb = *reinterpret_cast<const char4*>(t.seqTP + (size_t) (e >> 8) * t.posPitch + p);
+			const int b4[4] = {nb.x, nb.y, nb.z, nb.w};
+#pragma unroll
+			for (int s = 0; s < 4; ++s)
+				if (b4[s] >= 0) { nn[s]++; dd[s] += b4[s] != rb; }
+		}
+		uint32_t key[4];
+#pragma unroll
+		for (int s = 0; s < 4; ++s) {
+			const int node = __ldg(t.nodeOfPos + p + s);
+			const bool excl = node < 0 || node >= t.nNodes || !(__ldg(t.height + node) <= a.maxHeight);
+			key[s] = mmMakeKey(dd[s], nn[s], excl, t.inv2N);
+		}
+		*kp = make_uint4(key[0], key[1], key[2], key[3]);
+	}
+}
+
+// ---- tier 2: column -> reads of the batch with an entry there (counting sort on the column), then the pairs ----
+// colStart: where a column's reads start in colReads; workStart: the (column, exception) work items of the columns with reads
+__global__ void __launch_bounds__(1024) mmColScanKernel(int* __restrict__ colCount, int* __restrict__ colStart, int* __restrict__ workStart,
+		const int* __restrict__ excPtr, int csLen) {
+	__shared__ int part[1024], partW[1024];
+	const int per = (csLen + 1023) / 1024, c0 = threadIdx.x * per;
+	int s = 0, sw = 0;
+	for (int c = c0; c < min(c0 + per, csLen); ++c) {
+		s += colCount[c];
+		if (colCount[c] > 0) sw += __ldg(excPtr + c + 1) - __ldg(excPtr + c);
+	}
+	part[threadIdx.x] = s; partW[threadIdx.x] = sw;
+	__syncthreads();
+	for (int o = 1; o < 1024; o <<= 1) {
+		const int v = threadIdx.x >= o ? part[threadIdx.x - o] : 0, vw = threadIdx.x >= o ? partW[threadIdx.x - o] : 0;
+		__syncthreads();
+		part[threadIdx.x] += v; partW[threadIdx.x] += vw;
+		__syncthreads();
+	}
+	int run = part[threadIdx.x] - s, runW = partW[threadIdx.x] - sw;
+	for (int c = c0; c < min(c0 + per, csLen); ++c) {
+		const int n = colCount[c];
+		colStart[c] = run; workStart[c] = runW;
+		colCount[c] = 0; // becomes the fill cursor
+		run += n;
+		if (n > 0) runW += __ldg(excPtr + c + 1) - __ldg(excPtr + c);
+	}
+	if (threadIdx.x == 1023) { colStart[csLen] = part[1023]; workStart[csLen] = partW[1023]; }
+}
+__global__ void __launch_bounds__(128) mmColFillKernel(SeedArgs a, TreeDev t, const int* __restrict__ mode, int* __restrict__ colCount,
+		const int* __restrict__ colStart, int* __restrict__ colReads) {
+	const int r = blockIdx.x * 128 + threadIdx.x;
+	if (r >= a.nReads || mode[r] != 1) return;
+	const int ns = a.nSparse[r];
 	const uint32_t* sp = a.sparse + (size_t) r * a.sparseCap;
 	for (int i = 0; i < ns; ++i) {
-		const uint32_t e = __ldg(sp + i);
-		const int rb = (int) (e & 0xff);
-		const char4 nb = *reinterpret_cast<const char4*>(t.seqTP + (size_t) (e >> 8) * t.posPitch + p);
-		const int b4[4] = {nb.x, nb.y, nb.z, nb.w};
-#pragma unroll
-		for (int s = 0; s < 4; ++s)
-			if (b4[s] >= 0) { nn[s]++; dd[s] += b4[s] != rb; }
+		const int col = (int) (sp[i] >> 8);
+		if (__ldg(t.mmExcPtr + col + 1) > __ldg(t.mmExcPtr + col)) colReads[colStart[col] + atomicAdd(colCount + col, 1)] = r;
 	}
-	uint32_t key[4];
-#pragma unroll
-	for (int s = 0; s < 4; ++s) {
-		const int node = __ldg(t.nodeOfPos + p + s);
-		const bool excl = node < 0 || node >= t.nNodes || !(__ldg(t.height + node) <= a.maxHeight);
-		key[s] = mmMakeKey(dd[s], nn[s], excl, t.inv2N);
+}
+// a warp per (column, exception position) work item, grid-stride; lane = one of the column's reads: the pair's d and N from the
+// bit planes (match columns) and the transposed sequences (all of the read's non-match entries), as seedScanKernel computes them
+__global__ void __launch_bounds__(128) seedMmExceptionKernel(SeedArgs a, TreeDev t, const int* __restrict__ colStart, const int* __restrict__ workStart,
+		const int* __restrict__ colReads) {
+	const int lane = threadIdx.x & 31;
+	const int nWarps = gridDim.x * 4;
+	const int total = workStart[t.csLen];
+	const size_t pitch = t.scanPitch;
+	for (int item = blockIdx.x * 4 + (threadIdx.x >> 5); item < total; item += nWarps) {
+		int lo = 0, hi = t.csLen; // the column of this item: the last one whose work starts at or before it
+		while (hi - lo > 1) {
+			const int mid = (lo + hi) >> 1;
+			if (workStart[mid] <= item) lo = mid; else hi = mid;
+		}
+		const int col = lo;
+		const int p = __ldg(t.mmExcPos + __ldg(t.mmExcPtr + col) + item - workStart[col]);
+		const int slot = __ldg(t.mmSlotOfPos + p);
+		const bool excl = !(__ldg(t.height + __ldg(t.nodeOfPos + p)) <= a.maxHeight);
+		const uint32_t* pl = t.planes + slot;
+		for (int i = colStart[col] + lane; i < colStart[col + 1]; i += 32) {
+			const int r = colReads[i];
+			int d = 0, n = 0;
+			const int w1 = a.rWordHi[r];
+			for (int w = a.rWordLo[r]; w <= w1; ++w) {
+				const uint32_t nh = __ldg(pl + ((size_t) w * 3 + 0) * pitch), nl = __ldg(pl + ((size_t) w * 3 + 1) * pitch), nv = __ldg(pl + ((size_t) w * 3 + 2) * pitch);
+				const uint4 q = reinterpret_cast<const uint4*>(a.rplanes)[(size_t) w * a.nReadsPad + r];
+				const uint32_t m = nv & q.z;
+				d += __popc(((nh ^ q.x) | (nl ^ q.y)) & m);
+				n += __popc(m);
+			}
+			const int ns = a.nSparse[r];
+			const uint32_t* sp = a.sparse + (size_t) r * a.sparseCap;
+			for (int k = 0; k < ns; ++k) {
+				const uint32_t ent = sp[k];
+				const int b = t.seqTP[(size_t) (ent >> 8) * t.posPitch + p];
+				if (b >= 0) { n++; d += b != (int) (ent & 0xff); }
+			}
+			a.keys[(size_t) r * pitch + p] = mmMakeKey(d, n, excl, t.inv2N);
+		}
 	}
-	*kp = make_uint4(key[0], key[1], key[2], key[3]);
 }
 
 // seq[node][col] -> seqTP[col][position] (32 x 32 tiles through shared memory); gap code for padding positions
@@ -187,34 +328,91 @@ int configSeedMmKernels() {
 	return HU_OK;
 }
 
-bool seedMmUsable(const hu_db* db) { return db->tree.mmA != NULL; }
+// host side of the database build: classes, per-column defaults and exception lists.  hs: node sequences [nNodes][csLen],
+// posNode: position -> node (-1 padding).  colDefault: -1 match column, 0..3 the class-1 majority base, 4 long exception list
+void seedMmColumns(const int8_t* hs, int csLen, const int* colK, const std::vector<int>& posNode, int nCand,
+		std::vector<int8_t>& posClass, std::vector<int8_t>& colDefault, std::vector<int>& excPtr, std::vector<int>& excPos) {
+	posClass.assign(posNode.size(), 0);
+	std::vector<int> hist((size_t) csLen * 4, 0);
+	for (int p = 0; p < nCand; ++p) {
+		const int8_t* s = hs + (size_t) posNode[p] * csLen;
+		bool full = true;
+		for (int c = 0; c < csLen && full; ++c) full = s[c] >= 0;
+		posClass[p] = full;
+		if (full)
+			for (int c = 0; c < csLen; ++c)
+				if (!colK[c]) hist[(size_t) c * 4 + (s[c] & 3)]++;
+	}
+	colDefault.assign(csLen, -1);
+	for (int c = 0; c < csLen; ++c)
+		if (!colK[c]) {
+			int g = 0;
+			for (int b = 1; b < 4; ++b)
+				if (hist[(size_t) c * 4 + b] > hist[(size_t) c * 4 + g]) g = b;
+			colDefault[c] = (int8_t) g;
+		}
+	std::vector<int> count(csLen, 0);
+	for (int pass = 0; pass < 2; ++pass) {
+		if (pass == 1) {
+			const int limit = std::max(64, nCand / 64);
+			excPtr.assign(csLen + 1, 0);
+			for (int c = 0; c < csLen; ++c) {
+				if (colDefault[c] >= 0 && count[c] > limit) { colDefault[c] = 4; count[c] = 0; }
+				excPtr[c + 1] = excPtr[c] + count[c];
+			}
+			excPos.assign(std::max(excPtr[csLen], 1), 0);
+			std::fill(count.begin(), count.end(), 0);
+		}
+		for (int p = 0; p < nCand; ++p) {
+			const int8_t* s = hs + (size_t) posNode[p] * csLen;
+			const bool full = posClass[p];
+			for (int c = 0; c < csLen; ++c) {
+				const int g = colDefault[c];
+				if (g < 0 || g > 3) continue;
+				if (full ? s[c] != g : s[c] >= 0) {
+					if (pass == 1) excPos[excPtr[c] + count[c]] = p;
+					count[c]++;
+				}
+			}
+		}
+	}
+}
 
-// database side: operand A images, position-ordered transpose.  posNode: position -> node id, -1 padding, posPitch entries
-int buildSeedMm(hu_db* db, const int8_t* seq, int K, int8_t* A, int8_t* seqTP, const int* posNode) {
+// device side of the database build: operand A images, position-ordered transpose
+int buildSeedMm(hu_db* db, const int8_t* seq, int K, int8_t* A, int8_t* seqTP, const int* posNode, const int8_t* posClass) {
 	TreeDev& t = db->tree;
-	mmPackNodesKernel<<<dim3(t.mmTiles, t.mmChunks), HU_MM_BM>>>(seq, t.csLen, K, db->hmm.p2cs, posNode, t.mmChunks, A);
+	mmPackNodesKernel<<<dim3(t.mmTiles, t.mmChunks + 1), HU_MM_BM>>>(seq, t.csLen, K, db->hmm.p2cs, posNode, posClass, t.mmChunks + 1, A);
 	mmTransposeKernel<<<dim3(t.posPitch / 32, (t.csLen + 31) / 32), dim3(32, 8)>>>(seq, t.csLen, posNode, t.posPitch, seqTP);
 	HU_CUDA(cudaGetLastError());
 	HU_CUDA(cudaDeviceSynchronize());
 	return HU_OK;
 }
 
-// the scan of one batch; a: the stage's arguments with rValid / rWordLo / rWordHi / nSparse already made
+// the scan of one batch; a: the stage's arguments with rplanes / rValid / rWordLo / rWordHi / nSparse already made
 int launchSeedMm(hu_batch* b, const SeedArgs& a, int* launches) {
 	hu_db* db = b->db;
 	const TreeDev& t = db->tree;
-	const int numNt = (a.nReads + HU_MM_BN - 1) / HU_MM_BN;
-	mmPackReadsKernel<<<dim3(numNt * (HU_MM_BN / 128), t.mmChunks), 128, 0, b->stream>>>(a, t.csLen, db->hmm.K, db->hmm.p2cs, t.mmChunks, b->mmB);
+	const int numNt = (a.nReads + HU_MM_BN - 1) / HU_MM_BN, stride = t.mmChunks + 1;
+	int* colCount = b->mmCols;
+	int* colStart = b->mmCols + t.csLen + 1;
+	int* workStart = b->mmCols + 2 * (t.csLen + 1);
+	HU_CUDA(cudaMemsetAsync(colCount, 0, (size_t) (t.csLen + 1) * sizeof(int), b->stream));
+	HU_CUDA(cudaMemsetAsync(b->mmTileExt, 0, (size_t) numNt * sizeof(int), b->stream));
+	mmPackReadsKernel<<<dim3(numNt * (HU_MM_BN / 128), t.mmChunks), 128, 0, b->stream>>>(a, t.csLen, db->hmm.K, db->hmm.p2cs, stride, b->mmB);
+	mmPackExtKernel<<<numNt * (HU_MM_BN / 128), 128, 0, b->stream>>>(a, t, stride, b->mmB, b->mmMode, b->mmTileExt, colCount);
 	mmRangeKernel<<<numNt, HU_MM_BN, 0, b->stream>>>(a, b->mmRange);
 	int sms = 0;
 	HU_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, db->device));
-	MmArgs g = {t.mmA, b->mmB, b->mmRange, t.mmTiles, numNt, t.mmChunks};
+	MmArgs g = {t.mmA, b->mmB, b->mmRange, t.mmTiles, numNt, stride, b->mmTileExt, stride - 1};
 	KeyEpi epi;
-	epi.keys = a.keys; epi.pitch = t.scanPitch; epi.nReads = a.nReads; epi.nNodes = t.nNodes; epi.nSparse = a.nSparse;
+	epi.keys = a.keys; epi.pitch = t.scanPitch; epi.nReads = a.nReads; epi.nNodes = t.nNodes; epi.mode = b->mmMode;
 	epi.nodeOfPos = t.nodeOfPos; epi.height = t.height; epi.keyTab = t.mmKeyTab; epi.maxHeight = a.maxHeight; epi.excl = false;
 	seedMmKernel<KeyEpi><<<std::min(sms, t.mmTiles * numNt), HU_MM_THREADS, HU_MM_SMEM, b->stream>>>(g, epi);
-	seedMmFixupKernel<<<dim3((t.posPitch / 4 + 255) / 256, a.nReads), 256, 0, b->stream>>>(a, t, t.scanPitch);
-	*launches = 4;
+	seedMmFixupKernel<<<a.nReads, 256, 0, b->stream>>>(a, t, t.scanPitch, b->mmMode);
+	mmColScanKernel<<<1, 1024, 0, b->stream>>>(colCount, colStart, workStart, t.mmExcPtr, t.csLen);
+	mmColFillKernel<<<(a.nReads + 127) / 128, 128, 0, b->stream>>>(a, t, b->mmMode, colCount, colStart, b->mmColReads);
+	seedMmExceptionKernel<<<sms * 8, 128, 0, b->stream>>>(a, t, colStart, workStart, b->mmColReads);
+	*launches = 8;
 	HU_CUDA(cudaGetLastError());
 	return HU_OK;
 }

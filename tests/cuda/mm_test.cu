@@ -43,7 +43,7 @@ int main(int argc, char** argv) {
 	CK(cudaMemcpy(dR, range.data(), range.size() * sizeof(int2), cudaMemcpyHostToDevice));
 	CK(cudaMemset(dO, 0x7f, (size_t) mTot * nTot * sizeof(int)));
 	CK(cudaFuncSetAttribute(seedMmKernel<RawEpi>, cudaFuncAttributeMaxDynamicSharedMemorySize, HU_MM_SMEM));
-	MmArgs g = {dA, dB, dR, numMt, numNt, nChunks};
+	MmArgs g = {dA, dB, dR, numMt, numNt, nChunks, NULL, -1};
 	RawEpi epi = {dO, mTot};
 	int sms = 0;
 	CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
