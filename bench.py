@@ -548,15 +548,21 @@ def _main(real_stdout):
             d["gcups"] = stats["cells"] / n_meas / (per[0] / 1e3) / 1e9
             # 15 ALU operations per cell update against one issue per lane and clock (fp64 add/min: SURVEY.md 8(d) K1)
             d["alu_issue_frac"] = d["gcups"] * 1e9 * 15 / (n_sm * 128 * sm_clock)
+        if i == 1 and per[1] > 0 and stats.get("seedMacs", 0) > 0:
+            # the scan runs on the tensor cores (tcgen05.mma kind::i8): multiply-accumulates of the tiles x chunks visited;
+            # nominal dense int8 peak of a B200 (no measured int8 figure in MEASURED_PEAKS.json)
+            d["int8_tops"] = 2.0 * stats["seedMacs"] / n_meas / (per[1] / 1e3) / 1e12
+            d["int8_frac_of_nominal_4500"] = d["int8_tops"] / 4500.0
+            d.pop("hbm_frac", None)   # SURVEY's byte count assumes one node byte per (read, node, column): not what bounds this kernel
         if nme in traffic:
             d["dram_bytes_per_launch"] = traffic[nme]
         stages[nme] = d
     achieved = alg.get(dom, 0.0) / (per[dom] / 1e3) / 1e9 if per[dom] > 0 else 0.0
     roofline = dict(bound="hbm", kernel=names[dom], achieved=achieved, peak=peaks["hbm_gbs"], unit="GB/s",
                     frac=achieved / peaks["hbm_gbs"], traffic=traffic.get(names[dom]), peak_source=peaks["src"],
-                    note="achieved = algorithmic bytes per step (SURVEY.md 8(d)) / CUDA-event time of the stage; the seed scan "
-                         "shares one node tile among the reads of a batch, so its algorithmic rate exceeds physical HBM "
-                         "(it is bound by POPC issue); per-stage figures under 'stages'")
+                    note="achieved = algorithmic bytes per step (SURVEY.md 8(d)) / CUDA-event time of the stage; the seed scan is an "
+                         "int8 contraction on the tensor cores (tcgen05.mma), reported as int8_tops under 'stages', where every "
+                         "stage has its own figures")
 
     # ---------------- CPU baseline + parity of the two arms on the same reads (rank 0, N = 1) ----------------
     cpu = parity = None

@@ -245,7 +245,7 @@ int hu_batch_create(hu_batch** out, hu_db* db, int32_t maxReads, int32_t maxSeqL
 	HU_TRY(balloc(b, &b->seed.sparse, (size_t) maxReads * b->seed.sparseCap));
 	HU_TRY(balloc(b, &b->seed.keys, (size_t) maxReads * t.scanPitch));
 	HU_CUDA(cudaMemset(b->seed.keys, 0xff, (size_t) maxReads * t.scanPitch * sizeof(uint32_t))); // tail positions stay excluded
-	b->mmB = NULL; b->mmRange = NULL; b->mmMode = b->mmTileExt = b->mmCols = b->mmColReads = NULL;
+	b->mmScanRan = 0; b->mmB = NULL; b->mmRange = NULL; b->mmMode = b->mmTileExt = b->mmCols = b->mmColReads = NULL;
 	if (t.mmA) {
 		const int numNt = (maxReads + HU_MM_BN - 1) / HU_MM_BN;
 		HU_TRY(balloc(b, &b->mmB, (size_t) numNt * (t.mmChunks + 1) * HU_MM_B_BYTES));
@@ -628,6 +628,16 @@ int hu_batch_get_stats(hu_batch* b, hu_batch_stats* s) {
 	int hf = 0;
 	HU_CUDA(cudaMemcpy(&hf, b->workCount + 4, sizeof(int), cudaMemcpyDeviceToHost));
 	s->seedHeapSorts = hf;
+	if (b->mmScanRan && b->mmRange) {
+		const int numNt = (b->nReads + HU_MM_BN - 1) / HU_MM_BN;
+		std::vector<int2> rg(numNt);
+		std::vector<int> ext(numNt);
+		HU_CUDA(cudaMemcpy(rg.data(), b->mmRange, rg.size() * sizeof(int2), cudaMemcpyDeviceToHost));
+		HU_CUDA(cudaMemcpy(ext.data(), b->mmTileExt, ext.size() * sizeof(int), cudaMemcpyDeviceToHost));
+		for (int i = 0; i < numNt; ++i)
+			if (rg[i].x <= rg[i].y)
+				s->seedMacs += (int64_t) (rg[i].y - rg[i].x + 1 + (ext[i] ? 1 : 0)) * HU_MM_BK * HU_MM_BN * (int64_t) b->db->tree.posPitch;
+	}
 	return HU_OK;
 }
 

@@ -131,6 +131,7 @@ struct hu_batch {
 	int* mmTileExt;        // per read tile: takes the extension chunk
 	int* mmCols;           // [3][csLen + 1]: per-column counts / cursors, starts of mmColReads, starts of the exception work items
 	int* mmColReads;       // reads with an entry in a column that has exceptions, grouped by column
+	int mmScanRan;         // the last seed stage ran the tensor-core scan
 	double* placeSlab;     // global rho slabs for windows wider than the shared-memory capacity
 	void* estSlab;         // K3: per-CTA g slabs for windows wider than its shared-memory buffer
 	int estSlabCtas;

@@ -14,6 +14,7 @@
 // (checked to 1e-9 relative against the oracle in tests/test_gpu_parity.py).
 #include "hu_batch.cuh"
 #include "hu_stdsort.cuh"
+#include <stdlib.h>
 
 namespace hu {
 
@@ -98,7 +99,8 @@ struct PlaceRed {
 template <int WPI>
 __device__ __forceinline__ void groupSync(int group) {
 	if (WPI == 1) __syncwarp();
-	else asm volatile("bar.sync %0, %1;" ::"r"(1 + group), "r"(WPI * 32) : "memory");
+	else if (WPI == 4 || group == 0) asm volatile("bar.sync 1, %0;" ::"n"(WPI * 32) : "memory");
+	else asm volatile("bar.sync 2, %0;" ::"n"(WPI * 32) : "memory");
 }
 template <int WPI>
 __device__ __forceinline__ double groupSum(double v, PlaceRed& red, int& flip, int group, int gwarp) {
@@ -106,7 +108,7 @@ __device__ __forceinline__ double groupSum(double v, PlaceRed& red, int& flip, i
 	if (WPI == 1) return v;
 	if ((threadIdx.x & 31) == 0) red.d[flip][gwarp] = v;
 	groupSync<WPI>(group);
-	const double s = (red.d[flip][0] + red.d[flip][1]) + (red.d[flip][2] + red.d[flip][3]);
+	const double s = WPI == 2 ? red.d[flip][0] + red.d[flip][1] : (red.d[flip][0] + red.d[flip][1]) + (red.d[flip][2] + red.d[flip][3]);
 	flip ^= 1;
 	return s;
 }
@@ -116,7 +118,7 @@ __device__ __forceinline__ int groupSumInt(int v, PlaceRed& red, int& flip, int 
 	if (WPI == 1) { __syncwarp(); return v; }
 	if ((threadIdx.x & 31) == 0) red.i[flip][gwarp] = v;
 	groupSync<WPI>(group);
-	const int s = (red.i[flip][0] + red.i[flip][1]) + (red.i[flip][2] + red.i[flip][3]);
+	const int s = WPI == 2 ? red.i[flip][0] + red.i[flip][1] : (red.i[flip][0] + red.i[flip][1]) + (red.i[flip][2] + red.i[flip][3]);
 	flip ^= 1;
 	return s;
 }
@@ -398,6 +400,7 @@ __global__ void finalizeKernel(int nReads, const int* __restrict__ winStart, con
 int configPlaceKernels() {
 	const size_t smem = (size_t) HU_PLACE_WARPS * (placeWarpDoubles(HU_MAX_DG) + HU_PLACE_CAPW) * sizeof(double);
 	HU_CUDA(cudaFuncSetAttribute(placeKernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+	HU_CUDA(cudaFuncSetAttribute(placeKernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
 	HU_CUDA(cudaFuncSetAttribute(placeKernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
 	return HU_OK;
 }
@@ -417,7 +420,9 @@ int launchPlace(hu_batch* b, const hu_sep_params* p) {
 	const int KKh = db->model.dgK > 0 ? db->model.dgK : 1;
 	// long reads (windows of thousands of columns): four warps per item; amplicon reads and merged pairs: one warp per item
 	const bool wideItems = b->maxSeqLen > 700;
-	const int groups = wideItems ? 1 : HU_PLACE_WARPS;
+	int wpi = wideItems ? 4 : 1;
+	{ const char* e = getenv("HU_PLACE_WPI"); if (e && (atoi(e) == 1 || atoi(e) == 2 || atoi(e) == 4)) wpi = atoi(e); } // measurements
+	const int groups = HU_PLACE_WARPS / wpi;
 	const size_t smem = (size_t) groups * (placeWarpDoubles(KKh) + HU_PLACE_CAPW) * sizeof(double);
 	// global slab for windows wider than the shared-memory capacity, one row per group of warps
 	const size_t slabBytes = (size_t) grid * HU_PLACE_WARPS * db->tree.csLen * sizeof(double);
@@ -429,7 +434,8 @@ int launchPlace(hu_batch* b, const hu_sep_params* p) {
 	}
 	a.slab = b->placeSlab;
 	HU_CUDA(cudaMemsetAsync(a.cursor, 0, sizeof(int), b->stream)); // the stage can run on its own (per-call facades), not only after hu_estimate_batch
-	if (wideItems) placeKernel<4><<<grid, HU_PLACE_THREADS, smem, b->stream>>>(a, db->tree, db->model);
+	if (wpi == 4) placeKernel<4><<<grid, HU_PLACE_THREADS, smem, b->stream>>>(a, db->tree, db->model);
+	else if (wpi == 2) placeKernel<2><<<grid, HU_PLACE_THREADS, smem, b->stream>>>(a, db->tree, db->model);
 	else placeKernel<1><<<grid, HU_PLACE_THREADS, smem, b->stream>>>(a, db->tree, db->model);
 	HU_CUDA(cudaEventRecord(b->ev[6], b->stream));
 	b->launches += 1;

@@ -1037,7 +1037,9 @@ int launchSeed(hu_batch* b, const hu_sep_params* p) {
 	if (t.mmA && b->mmB && a.posOfSlot == t.posOfSlot && scanPref == 0) {
 		int rcM = launchSeedMm(b, a, &scanLaunches);
 		if (rcM != HU_OK) return rcM;
+		b->mmScanRan = 1;
 	} else {
+		b->mmScanRan = 0;
 		const int groups = a.nReadsPad / HU_SCAN_READS;
 		const size_t smem = (size_t) t.nPWords * HU_SCAN_READS * sizeof(uint4);
 		if (smem > 200 * 1024) { setError("profile too long for the seed-scan read tile (%d words)", t.nPWords); return HU_ERR_ARG; }
