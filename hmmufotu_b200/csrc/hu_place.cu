@@ -26,6 +26,7 @@ namespace hu {
 
 struct PlaceArgs {
 	int nReads, maxNSeed, capW, useTrue;
+	int ahead, pad;    // L2 prefetch distance of the rebuild passes, in column strides
 	double maxHeight;
 	const int8_t* aligned;
 	const int* winStart;
@@ -52,10 +53,15 @@ struct ColPrefetch {
 		if (c < W) { ld4(U + (size_t) c * 4, eu); ld4(V + (size_t) c * 4, ev); b = x[c]; }
 	}
 	// hands out the buffered column and starts loading column `cn`
-	__device__ __forceinline__ int next(const double* U, const double* V, const int8_t* x, int cn, int W, double* ou, double* ov) {
+	__device__ __forceinline__ int next(const double* U, const double* V, const int8_t* x, int cn, int W, double* ou, double* ov, int ahead) {
 		for (int k = 0; k < 4; ++k) { ou[k] = eu[k]; ov[k] = ev[k]; }
 		const int ob = b;
 		if (cn < W) { ld4(U + (size_t) cn * 4, eu); ld4(V + (size_t) cn * 4, ev); b = x[cn]; }
+		// the columns after those: on their way from DRAM to the L2 (one request per 128-byte line; no register is held for them)
+		if (ahead > 0 && (threadIdx.x & 3) == 0 && cn + ahead < W) {
+			asm volatile("prefetch.global.L2 [%0];" ::"l"(U + (size_t) (cn + ahead) * 4));
+			asm volatile("prefetch.global.L2 [%0];" ::"l"(V + (size_t) (cn + ahead) * 4));
+		}
 		return ob;
 	}
 };
@@ -214,7 +220,7 @@ __global__ void __launch_bounds__(HU_PLACE_THREADS, 4) placeKernel(PlaceArgs a, 
 			pf.init(U, V, x, gtid, W);
 			for (int cI = gtid; cI < W; cI += NT) {
 				double eu[4], ev[4], ya[4], yb[4], g[4] = {0, 0, 0, 0};
-				const int b = pf.next(U, V, x, cI + NT, W, eu, ev);
+				const int b = pf.next(U, V, x, cI + NT, W, eu, ev, a.ahead * NT);
 				for (int k = 0; k < KK; ++k) {
 					matVec4(wsP + (0 * KK + (k)) * 16, eu, ya);
 					matVec4(wsP + (1 * KK + (k)) * 16, ev, yb);
@@ -246,7 +252,7 @@ __global__ void __launch_bounds__(HU_PLACE_THREADS, 4) placeKernel(PlaceArgs a, 
 			pf.init(U, V, x, gtid, W);
 			for (int cI = gtid; cI < W; cI += NT) {
 				double eu[4], ev[4], yb[4], g[4] = {0, 0, 0, 0};
-				const int b = pf.next(U, V, x, cI + NT, W, eu, ev);
+				const int b = pf.next(U, V, x, cI + NT, W, eu, ev, a.ahead * NT);
 				for (int k = 0; k < KK; ++k) {
 					matVec4(wsP + (1 * KK + (k)) * 16, ev, yb);
 					const double* np = wsNP + (k * 5 + (b >= 0 ? b : 4)) * 4;
@@ -292,7 +298,7 @@ __global__ void __launch_bounds__(HU_PLACE_THREADS, 4) placeKernel(PlaceArgs a, 
 			pf.init(U, V, x, gtid, W);
 			for (int cI = gtid; cI < W; cI += NT) {
 				double eu[4], ev[4], ya[4], yb[4], g[4] = {0, 0, 0, 0};
-				const int b = pf.next(U, V, x, cI + NT, W, eu, ev);
+				const int b = pf.next(U, V, x, cI + NT, W, eu, ev, a.ahead * NT);
 				for (int k = 0; k < KK; ++k) {
 					matVec4(wsP + (0 * KK + (k)) * 16, eu, ya);
 					matVec4(wsP + (1 * KK + (k)) * 16, ev, yb);
@@ -410,12 +416,15 @@ int launchPlace(hu_batch* b, const hu_sep_params* p) {
 	PlaceArgs a;
 	a.nReads = b->nReads; a.maxNSeed = p->maxNSeed; a.capW = HU_PLACE_CAPW; a.useTrue = p->useTrueLoglik;
 	a.maxHeight = p->maxHeight;
+	a.ahead = 2; a.pad = 0;
+	{ const char* e = getenv("HU_PLACE_AHEAD"); if (e) a.ahead = atoi(e); } // measurements
 	a.aligned = b->vit.aligned; a.winStart = b->winStart; a.winEnd = b->winEnd;
 	a.est = b->est; a.order = b->order; a.nKept = b->nKept; a.places = b->places;
 	a.cursor = b->workCount + 1;
 	int sms = 0;
 	HU_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, db->device));
-	const int ctasPerSm = 4;
+	int ctasPerSm = 4;
+	{ const char* e = getenv("HU_PLACE_CTAS"); if (e && atoi(e) >= 1 && atoi(e) <= 4) ctasPerSm = atoi(e); } // measurements
 	const int grid = sms * ctasPerSm;
 	const int KKh = db->model.dgK > 0 ? db->model.dgK : 1;
 	// long reads (windows of thousands of columns): four warps per item; amplicon reads and merged pairs: one warp per item
