@@ -19,6 +19,7 @@
 // per-CTA slab in global memory (L2-resident) and read the read's window from global memory: any width is streamed from
 // HBM once, and there is no separate wide-window kernel any more.
 #include "hu_batch.cuh"
+#include <stdlib.h>
 #include "hu_pipe.cuh"
 #include "hu_stdsort.cuh"
 
@@ -33,7 +34,7 @@ namespace hu {
 
 struct EstArgs {
 	int nReads, maxNSeed, weighted, capW; // weighted: estimateBranchLengthWeighted instead of ...Unweighted; capW: widest window whose g fits shared memory
-	int csLen, pad;
+	int csLen, ahead; // ahead: L2 prefetch distance of the producer, in ring chunks (0: none)
 	const int8_t* aligned;
 	const int* winStart;
 	const int* winEnd;
@@ -342,6 +343,14 @@ __global__ void __launch_bounds__(HU_EST_THREADS, 3) estimateStagedKernel(EstArg
 					const double* V = t.dn + ((size_t) it.u * t.csLen + it.start) * 4;
 					for (int c0 = 0; c0 < it.W; c0 += HU_EST_CH) {
 						const uint32_t nb32 = (uint32_t) min(HU_EST_CH, it.W - c0) * 32u;
+						// the chunk that will take this stage next time round is asked into the L2 now: the ring alone keeps too few
+						// bytes in flight per SM to cover the DRAM latency (ncu r2c: DRAM 61 % busy, consumers waiting)
+						const int ca = c0 + a.ahead * HU_EST_CH;
+						if (a.ahead > 0 && ca < it.W) {
+							const uint32_t na = (uint32_t) min(HU_EST_CH, it.W - ca) * 32u;
+							bulkPrefetchL2(U + (size_t) ca * 4, na);
+							bulkPrefetchL2(V + (size_t) ca * 4, na);
+						}
 						mbarWaitRelaxed(&sm.empty[st], ph ^ 1);
 						mbarArriveExpectTx(&sm.full[st], 2 * nb32);
 						bulkLoad(sm.ring[st][0], U + (size_t) c0 * 4, nb32, &sm.full[st]);
@@ -425,7 +434,8 @@ int launchEstimate(hu_batch* b, const hu_sep_params* p) {
 	// merged paired-end windows (1.5 - 2.5 k columns) get the larger g buffer (two CTAs per SM); single-end amplicon reads
 	// and reads so long that every window spills to the global slab anyway get the small one (three CTAs per SM)
 	a.capW = (b->paired || (b->maxSeqLen > 400 && b->maxSeqLen <= 700)) ? HU_EST_CAPW_BIG : HU_EST_CAPW;
-	a.csLen = db->tree.csLen; a.pad = 0;
+	a.csLen = db->tree.csLen; a.ahead = HU_EST_STAGES;
+	{ const char* e = getenv("HU_EST_AHEAD"); if (e) a.ahead = atoi(e); } // measurements
 	a.aligned = b->vit.aligned; a.winStart = b->winStart; a.winEnd = b->winEnd;
 	a.seedIds = b->seed.seedIds; a.nSeeds = b->seed.nSeeds;
 	a.est = b->est; a.items = b->estItems; a.itemsP = b->estItemsP;

@@ -42,6 +42,11 @@ __device__ __forceinline__ void bulkLoad(void* dst, const void* src, uint32_t by
 	             ::"r"(smemAddr(dst)), "l"(src), "r"(bytes), "r"(smemAddr(bar)) : "memory");
 }
 
+// asks for `bytes` (a multiple of 16) at src to be brought into the L2: no destination, no completion to wait for
+__device__ __forceinline__ void bulkPrefetchL2(const void* src, uint32_t bytes) {
+	asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+
 // barrier among the first `threads` threads of the CTA (the consumer warps), id 1; the producer warp never joins
 __device__ __forceinline__ void consumerSync(int threads) { asm volatile("bar.sync 1, %0;" ::"r"(threads) : "memory"); }
 
