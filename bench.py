@@ -564,6 +564,12 @@ def _main(real_stdout):
                          "int8 contraction on the tensor cores (tcgen05.mma), reported as int8_tops under 'stages', where every "
                          "stage has its own figures")
 
+    if dom == 0 and stages[names[0]].get("gcups"):   # long reads: the Viterbi recurrence dominates; its roofline is ALU issue
+        g = stages[names[0]]
+        roofline = dict(bound="alu", kernel=names[0], achieved=g["gcups"] * 15, peak=n_sm * 128 * sm_clock / 1e9, unit="Gop/s",
+                        frac=g["alu_issue_frac"], traffic=traffic.get(names[0]), peak_source="148 SMs x 128 lanes x measured SM clock",
+                        note="15 ALU operations per cell update (10 fp64 adds, 5 compares) against one issue per lane and clock")
+
     # ---------------- CPU baseline + parity of the two arms on the same reads (rank 0, N = 1) ----------------
     cpu = parity = None
     if rank == 0 and world == 1 and not args.no_cpu:

@@ -129,9 +129,10 @@ __global__ void __launch_bounds__(HU_MM_BN) mmRangeKernel(SeedArgs a, int2* __re
 	if (threadIdx.x == 0) { sLo = 0x7fffffff; sHi = -1; }
 	__syncthreads();
 	const int r = blockIdx.x * HU_MM_BN + threadIdx.x;
-	if (r < a.nReads && a.winStart[r] >= 0 && a.rWordHi[r] >= 0) {
-		atomicMin(&sLo, a.rWordLo[r]);
-		atomicMax(&sHi, a.rWordHi[r]);
+	if (r < a.nReads && a.winStart[r] >= 0) {
+		const bool any = a.rWordHi[r] >= 0; // a read without a base in a match column still gets its keys (chunk 0 is all zero for it)
+		atomicMin(&sLo, any ? a.rWordLo[r] : 0);
+		atomicMax(&sHi, any ? a.rWordHi[r] : 0);
 	}
 	__syncthreads();
 	if (threadIdx.x == 0) range[blockIdx.x] = make_int2(sLo, sHi);
