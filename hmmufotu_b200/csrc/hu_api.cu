@@ -187,7 +187,7 @@ int hu_batch_create(hu_batch** out, hu_db* db, int32_t maxReads, int32_t maxSeqL
 	b->db = db; b->maxReads = maxReads; b->maxSeqLen = maxSeqLen; b->paired = paired ? 1 : 0;
 	b->maxSeq = maxReads * (paired ? 2 : 1);
 	b->nReads = b->nSeq = 0; b->launches = 0;
-	b->dPtrs = NULL; b->ptrsCap = 0; b->placeSlab = NULL; b->litIds = NULL;
+	b->dPtrs = NULL; b->ptrsCap = 0; b->placeSlab = NULL; b->litIds = NULL; b->litBits = NULL;
 	b->posOfSlotH = b->nodeOfPosH = NULL; b->nCandH = 0; b->heightCached = 0;
 	b->estSlab = NULL; b->estSlabCtas = 0;
 	*out = b;

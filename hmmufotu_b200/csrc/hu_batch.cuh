@@ -62,6 +62,12 @@ struct SeedArgs {
 	const int* nodeOfPos;   // position -> node id
 	int nCand;              // number of candidates of this run
 	int* heapFallbacks;     // diagnostic counter: reads whose literal replay reached introsort's heap-sort fallback
+	// level 1 of the literal seed order, flags made by the scan's epilogue while the keys are in registers (hu_seedmm.cu):
+	uint32_t* litPv;        // [litStride] the level-1 pivot key per read (median of the keys at positions 1, n/2, n-1), computed ahead of the scan
+	int* litOk;             // [litStride] 1: litPv and the read's two bitmaps are valid
+	uint32_t* litBitA;      // [litStride][scanPitch / 32]: bit p%32 of word p/32 of a read's row = (key at position p >= pivot); NULL: not in use
+	uint32_t* litBitB;      // same layout: key <= pivot
+	int litStride;          // reads per bitmap word row (maxReads rounded up to 32)
 };
 
 // one (read, seed) of the estimate stage, resolved once so that the streaming kernel has no dependent loads
@@ -121,6 +127,7 @@ struct hu_batch {
 	hu::EstItemP* estItemsP;
 	int* workCount;
 	unsigned long long* litIds; // (key, candidate position) work rows of the literal seed order, one per resident CTA
+	uint32_t* litBits;     // level-1 bitmaps of the literal seed order written by the tensor-core scan (allocated on first use), then litPv, litOk
 	int* posOfSlotH;       // candidate map of the literal seed order under -H/--max-height (built on first use per height)
 	int* nodeOfPosH;
 	int nCandH;

@@ -605,6 +605,25 @@ __global__ void __launch_bounds__(HU_LIT_THREADS) seedSortLiteralKernel(SeedArgs
 			// can be read with aligned 128-bit loads: HU_LIT_VEC of them in flight per lane (the pass is bound by load
 			// latency).  A lane's four flags form a nibble; three exchanges assemble the words of eight lanes.
 			const int base = 0, nW = (n + 31) / 32, nCh = (n + 127) / 128;
+			// The scan's epilogue has made this pass already if it knew the pivot (hu_seedmm.cu): bit p of the read's two bitmaps =
+			// (key at p >= pivot), (key at p <= pivot) for every position.  What differs here is local: bit 0 (the pivot's slot)
+			// is clear, position mS holds what was first, and nothing exists at or beyond n.
+			const bool fromScan = a.litBitA != NULL && a.litOk[r] && a.litPv[r] == pv; // uniform over the CTA
+			if (fromScan) {
+				const uint32_t* ga = a.litBitA + (size_t) r * (size_t) (pitch >> 5);
+				const uint32_t* gb = a.litBitB + (size_t) r * (size_t) (pitch >> 5);
+				for (int wd = tid; wd < nW; wd += HU_LIT_THREADS) {
+					uint32_t xa = ga[wd], xb = gb[wd];
+					if (wd == (mS >> 5)) {
+						const uint32_t bit = 1u << (mS & 31);
+						xa = !(k0v < pv) ? (xa | bit) : (xa & ~bit);
+						xb = !(pv < k0v) ? (xb | bit) : (xb & ~bit);
+					}
+					if (wd == 0) { xa &= ~1u; xb &= ~1u; }
+					if (wd == nW - 1 && (n & 31)) { const uint32_t keep = (1u << (n & 31)) - 1u; xa &= keep; xb &= keep; }
+					faW[wd] = xa; fbW[wd] = xb;
+				}
+			} else {
 #define LIT_FLAG_CHUNK(ch, val) { \
 				const uint32_t q_[4] = {(val).x, (val).y, (val).z, (val).w}; \
 				uint32_t na_ = 0, nb_ = 0; \
@@ -637,6 +656,7 @@ __global__ void __launch_bounds__(HU_LIT_THREADS) seedSortLiteralKernel(SeedArgs
 				LIT_FLAG_CHUNK(ch0, v1)
 			}
 #undef LIT_FLAG_CHUNK
+			}
 			if (pv != 0xFFFFFFFFu) mx = max(mx, pv);
 			__syncthreads();
 			LITP_MARK(0);
@@ -1022,6 +1042,28 @@ int launchSeed(hu_batch* b, const hu_sep_params* p) {
 		}
 		a.posOfSlot = b->posOfSlotH; a.nodeOfPos = b->nodeOfPosH; a.nCand = b->nCandH;
 	}
+	// Level 1 of the literal order's flag pass rides in the tensor-core scan's epilogue (hu_seedmm.cu) when the key vector is the
+	// plain candidate vector, large enough for the direct level 1, and the largest key is not needed (no --max-diff):
+	// HU_LIT_BITS=0 keeps the pass in seedSortLiteralKernel (A/B measurements, parity tests between the two).
+	a.litPv = NULL; a.litOk = NULL; a.litBitA = a.litBitB = NULL; a.litStride = 0;
+	{
+		const char* e = getenv("HU_LIT_BITS");
+		const bool want = !(e && !strcmp(e, "0"));
+		if (want && literal && t.mmA && b->mmB && a.posOfSlot == t.posOfSlot && !(p->maxDiff < INFINITY) && a.nCand > 4 * HU_LIT_SMALL &&
+		    t.scanPitch % 32 == 0) {
+			const int stride = (b->maxReads + 31) / 32 * 32;
+			const size_t words = (size_t) (t.scanPitch / 32) * stride;
+			if (!b->litBits) {
+				void* q = NULL;
+				HU_CUDA(cudaMalloc(&q, (2 * words + 2 * (size_t) stride) * sizeof(uint32_t)));
+				b->allocs.push_back(q);
+				b->litBits = (uint32_t*) q;
+			}
+			a.litBitA = b->litBits; a.litBitB = b->litBits + words;
+			a.litPv = b->litBits + 2 * words; a.litOk = (int*) (b->litBits + 2 * words + stride);
+			a.litStride = stride;
+		}
+	}
 	b->seed = a;
 	HU_CUDA(cudaEventRecord(b->ev[2], b->stream));
 	HU_CUDA(cudaMemsetAsync(a.rValid, 0, (size_t) a.nReadsPad * sizeof(int), b->stream));
@@ -1050,6 +1092,7 @@ int launchSeed(hu_batch* b, const hu_sep_params* p) {
 		scanLaunches = (gapTiles > 0) + (allTiles > gapTiles);
 	}
 	HU_CUDA(cudaEventRecord(b->ev[3], b->stream));
+	if (getenv("HU_LIT_DRY")) a.litBitA = NULL; // measurements: the epilogue made the flags but did not store them
 	if (literal) {
 		int sms = 0;
 		HU_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, db->device));

@@ -144,6 +144,24 @@ __global__ void __launch_bounds__(HU_MM_BN) mmRangeKernel(SeedArgs a, int2* __re
 // t (m N - 2^k) < 2^k, which k = max(32, 24 + bits(N)) guarantees for t < N^2 (m < 2^32; N = 1 has R = 0 and takes m = 0).
 // One 16-byte table entry per N: {Q, R, m, k - 32}; N = 0 never reads it (S == 0 <=> N == 0 -> excluded).  The same value as
 // makeKey()'s correctly rounded floating-point form in hu_seed.cu (both are the exact floor; tests/test_gpu_mm.py).
+// 32 x 32 bit matrix across a warp: lane i holds row i, afterwards lane j holds column j (five butterfly exchanges)
+__device__ __forceinline__ uint32_t warpBitTranspose(uint32_t x, int lane) {
+#pragma unroll
+	for (int s = 16; s > 0; s >>= 1) {
+		const uint32_t m0 = s == 16 ? 0x0000FFFFu : s == 8 ? 0x00FF00FFu : s == 4 ? 0x0F0F0F0Fu : s == 2 ? 0x33333333u : 0x55555555u; // bits b with (b & s) == 0
+		const uint32_t y = __shfl_xor_sync(0xffffffffu, x, s);
+		x = (lane & s) ? ((x & ~m0) | ((y >> s) & m0)) : ((x & m0) | ((y & m0) << s));
+	}
+	return x;
+}
+
+// LIT: the epilogue also makes level 1 of the literal seed order's flag pass (hu_seed.cu, seedSortLiteralKernel) while the keys
+// are in registers: per read the two bitmaps (key >= pivot, key <= pivot) over the candidate positions, the pivot being known
+// ahead of the scan (seedLitPivotKernel).  A thread (= position) collects its flags against the 32 reads of the chunk in one
+// word per bitmap, the warp transposes the 32 x 32 bits, and lane j stores the word of read j: bit i = position 32 w + i.
+// (A ballot per key does the same without the transpose, but 2 votes + 1 shuffle per key made the epilogue the kernel's
+// bottleneck: 3.2 -> 5.4 ms.)
+template <bool LIT>
 struct KeyEpi {
 	uint32_t* keys;
 	int pitch, nReads, nNodes;
@@ -152,6 +170,10 @@ struct KeyEpi {
 	const double* height;
 	const uint4* keyTab; // [HU_MM_MAX_N + 1]
 	double maxHeight;
+	const uint32_t* litPv; // LIT: pivot per read
+	uint32_t* litBitA;     // LIT: [litStride][pitch / 32]
+	uint32_t* litBitB;
+	int litStride;
 	bool excl; // per thread: this position is not a candidate (padding, or above --max-height)
 	__device__ __forceinline__ void begin(int mt, int, int row) {
 		const int p = mt * HU_MM_BM + row;
@@ -165,6 +187,27 @@ struct KeyEpi {
 		const uint32_t q = __umulhi((uint32_t) d * e.y, e.z) >> e.w;
 		return S == 0 ? 0xFFFFFFFFu : (uint32_t) d * e.x + q;
 	}
+	// k[j]: this position's key for read r0 + j
+	__device__ __forceinline__ void flags(const uint32_t (&k)[32], int p, int r0, int lane) const {
+		if (r0 >= abs(litStride)) return; // litStride is a multiple of 32, and so is r0
+		const uint4* pvp = reinterpret_cast<const uint4*>(litPv + r0); // the same address in every lane: one broadcast per four pivots
+		uint32_t fa = 0u, fb = 0u;
+#pragma unroll
+		for (int q = 0; q < 8; ++q) {
+			const uint4 pv = __ldg(pvp + q);
+			const uint32_t pvs[4] = {pv.x, pv.y, pv.z, pv.w};
+#pragma unroll
+			for (int c = 0; c < 4; ++c) {
+				const int j = 4 * q + c;
+				if (k[j] >= pvs[c]) fa |= 1u << j; // a compare and a predicated OR each
+				if (k[j] <= pvs[c]) fb |= 1u << j;
+			}
+		}
+		fa = warpBitTranspose(fa, lane);
+		fb = warpBitTranspose(fb, lane);
+		const size_t o = (size_t) (r0 + lane) * (size_t) (pitch >> 5) + (size_t) (p >> 5); // p >> 5 is the warp's word: its lanes are 32 consecutive positions
+		if (litStride > 0) { litBitA[o] = fa; litBitB[o] = fb; } // litStride < 0: a dry run for measurements (HU_LIT_DRY)
+	}
 	__device__ __forceinline__ void operator()(int mt, int nt, int row, int col0, const uint32_t (&v)[32], int lane) const {
 		const int p = mt * HU_MM_BM + row;
 		const int r0 = nt * HU_MM_BN + col0;
@@ -174,26 +217,73 @@ struct KeyEpi {
 		const unsigned badMask = __ballot_sync(0xffffffffu, md < 0);   // sparse list overflow: the read stays unplaced
 		const bool plain = !__any_sync(0xffffffffu, excl || p >= pitch) && rawMask == 0u && badMask == 0u && r0 + 32 <= nReads;
 		uint32_t* out = keys + (size_t) r0 * pitch + p;
+		uint32_t k[32];
 		if (plain) { // the common case: no per-key tests
 #pragma unroll
-			for (int j = 0; j < 32; ++j) { *out = key((int) v[j]); out += pitch; }
-			return;
-		}
-		if (p >= pitch) return;
-		const int nr = min(32, nReads - r0);
+			for (int j = 0; j < 32; ++j) { k[j] = key((int) v[j]); *out = k[j]; out += pitch; }
+		} else {
+			if (p >= pitch) return; // whole warps: pitch is a multiple of 32
+			const int nr = min(32, nReads - r0);
 #pragma unroll
-		for (int j = 0; j < 32; ++j) {
-			const int S = (int) v[j];
-			uint32_t k;
-			if ((rawMask >> j) & 1u) {
-				const int N = (S + 4096) >> 14;
-				k = ((uint32_t) ((16387 * N - S) >> 2) << 16) | (uint32_t) N;
-			} else
-				k = (excl || ((badMask >> j) & 1u)) ? 0xFFFFFFFFu : key(S);
-			if (j < nr) out[(size_t) j * pitch] = k;
+			for (int j = 0; j < 32; ++j) {
+				const int S = (int) v[j];
+				if ((rawMask >> j) & 1u) {
+					const int N = (S + 4096) >> 14;
+					k[j] = ((uint32_t) ((16387 * N - S) >> 2) << 16) | (uint32_t) N;
+				} else
+					k[j] = (excl || ((badMask >> j) & 1u)) ? 0xFFFFFFFFu : key(S);
+				if (j < nr) out[(size_t) j * pitch] = k[j];
+			}
 		}
+		if (LIT) flags(k, p, r0, lane);
 	}
 };
+
+// the key of one (position, read) pair from the bit planes (match columns) and the transposed sequences (the read's entries in
+// non-match columns), as seedScanKernel computes it; bit-identical to the tile kernel's key for the reads of tiers 1 and 2
+__device__ __forceinline__ uint32_t mmPairKey(const SeedArgs& a, const TreeDev& t, int p, int r) {
+	const size_t pitch = t.scanPitch;
+	const uint32_t* pl = t.planes + __ldg(t.mmSlotOfPos + p);
+	const bool excl = !(__ldg(t.height + __ldg(t.nodeOfPos + p)) <= a.maxHeight);
+	int d = 0, n = 0;
+	const int w1 = a.rWordHi[r];
+	for (int w = a.rWordLo[r]; w <= w1; ++w) {
+		const uint32_t nh = __ldg(pl + ((size_t) w * 3 + 0) * pitch), nl = __ldg(pl + ((size_t) w * 3 + 1) * pitch), nv = __ldg(pl + ((size_t) w * 3 + 2) * pitch);
+		const uint4 q = reinterpret_cast<const uint4*>(a.rplanes)[(size_t) w * a.nReadsPad + r];
+		const uint32_t m = nv & q.z;
+		d += __popc(((nh ^ q.x) | (nl ^ q.y)) & m);
+		n += __popc(m);
+	}
+	const int ns = a.nSparse[r];
+	const uint32_t* sp = a.sparse + (size_t) r * a.sparseCap;
+	for (int k = 0; k < ns; ++k) {
+		const uint32_t ent = sp[k];
+		const int b = t.seqTP[(size_t) (ent >> 8) * t.posPitch + p];
+		if (b >= 0) { n++; d += b != (int) (ent & 0xff); }
+	}
+	return mmMakeKey(d, n, excl, t.inv2N);
+}
+
+// Level-1 pivot of the literal seed order per read, ahead of the scan: std::sort's first __move_median_to_first looks at the
+// keys at positions 1, n / 2 and n - 1 (bits/stl_algo.h; seedSortLiteralKernel does the same on the finished key vector and
+// only uses the bitmaps if it arrives at the same pivot).  Four lanes per read, three of them compute one key each.
+__global__ void __launch_bounds__(128) seedLitPivotKernel(SeedArgs a, TreeDev t, const int* __restrict__ mode, int n) {
+	const int tid = blockIdx.x * 128 + threadIdx.x;
+	const int r = tid >> 2, which = tid & 3;
+	const bool ok = r < a.nReads && a.winStart[r] >= 0 && (mode[r] == 0 || mode[r] == 1);
+	const int pos = which == 0 ? 1 : (which == 1 ? n / 2 : n - 1);
+	uint32_t q = 0u;
+	if (ok && which < 3) q = mmPairKey(a, t, pos, r);
+	const int l0 = threadIdx.x & 28;
+	const uint32_t qa = __shfl_sync(0xffffffffu, q, l0), qb = __shfl_sync(0xffffffffu, q, l0 + 1), qc = __shfl_sync(0xffffffffu, q, l0 + 2);
+	if (which == 0 && r < a.litStride) {
+		uint32_t pv;
+		if (qa < qb) pv = qb < qc ? qb : (qa < qc ? qc : qa);
+		else pv = qa < qc ? qa : (qb < qc ? qc : qb);
+		a.litPv[r] = pv;
+		a.litOk[r] = ok ? 1 : 0;
+	}
+}
 
 // tier 3: (d << 16 | N) -> + the read's non-match columns -> key; one CTA per read (the others leave at once), four positions per thread
 __global__ void __launch_bounds__(256) seedMmFixupKernel(SeedArgs a, TreeDev t, int pitch, const int* __restrict__ mode) {
@@ -282,28 +372,19 @@ __global__ void __launch_bounds__(128) seedMmExceptionKernel(SeedArgs a, TreeDev
 		}
 		const int col = lo;
 		const int p = __ldg(t.mmExcPos + __ldg(t.mmExcPtr + col) + item - workStart[col]);
-		const int slot = __ldg(t.mmSlotOfPos + p);
-		const bool excl = !(__ldg(t.height + __ldg(t.nodeOfPos + p)) <= a.maxHeight);
-		const uint32_t* pl = t.planes + slot;
 		for (int i = colStart[col] + lane; i < colStart[col + 1]; i += 32) {
 			const int r = colReads[i];
-			int d = 0, n = 0;
-			const int w1 = a.rWordHi[r];
-			for (int w = a.rWordLo[r]; w <= w1; ++w) {
-				const uint32_t nh = __ldg(pl + ((size_t) w * 3 + 0) * pitch), nl = __ldg(pl + ((size_t) w * 3 + 1) * pitch), nv = __ldg(pl + ((size_t) w * 3 + 2) * pitch);
-				const uint4 q = reinterpret_cast<const uint4*>(a.rplanes)[(size_t) w * a.nReadsPad + r];
-				const uint32_t m = nv & q.z;
-				d += __popc(((nh ^ q.x) | (nl ^ q.y)) & m);
-				n += __popc(m);
+			const uint32_t k = mmPairKey(a, t, p, r);
+			a.keys[(size_t) r * pitch + p] = k;
+			if (a.litBitA && a.litOk[r]) {
+				// the pair's two flags of the literal order's level 1 follow the key.  Only this pair's bit is at stake (a pair listed
+				// under two columns gets the same key twice), so the bit is read plainly and only a changed one costs an atomic.
+				const uint32_t pv = a.litPv[r], bit = 1u << (p & 31);
+				const size_t o = (size_t) r * (size_t) (t.scanPitch >> 5) + (size_t) (p >> 5);
+				const bool fa = k >= pv, fb = k <= pv;
+				if (((a.litBitA[o] & bit) != 0u) != fa) { if (fa) atomicOr(a.litBitA + o, bit); else atomicAnd(a.litBitA + o, ~bit); }
+				if (((a.litBitB[o] & bit) != 0u) != fb) { if (fb) atomicOr(a.litBitB + o, bit); else atomicAnd(a.litBitB + o, ~bit); }
 			}
-			const int ns = a.nSparse[r];
-			const uint32_t* sp = a.sparse + (size_t) r * a.sparseCap;
-			for (int k = 0; k < ns; ++k) {
-				const uint32_t ent = sp[k];
-				const int b = t.seqTP[(size_t) (ent >> 8) * t.posPitch + p];
-				if (b >= 0) { n++; d += b != (int) (ent & 0xff); }
-			}
-			a.keys[(size_t) r * pitch + p] = mmMakeKey(d, n, excl, t.inv2N);
 		}
 	}
 }
@@ -325,7 +406,8 @@ __global__ void mmTransposeKernel(const int8_t* __restrict__ seq, int csLen, con
 }
 
 int configSeedMmKernels() {
-	HU_CUDA(cudaFuncSetAttribute(seedMmKernel<KeyEpi>, cudaFuncAttributeMaxDynamicSharedMemorySize, HU_MM_SMEM));
+	HU_CUDA(cudaFuncSetAttribute(seedMmKernel<KeyEpi<false> >, cudaFuncAttributeMaxDynamicSharedMemorySize, HU_MM_SMEM));
+	HU_CUDA(cudaFuncSetAttribute(seedMmKernel<KeyEpi<true> >, cudaFuncAttributeMaxDynamicSharedMemorySize, HU_MM_SMEM));
 	return HU_OK;
 }
 
@@ -405,15 +487,25 @@ int launchSeedMm(hu_batch* b, const SeedArgs& a, int* launches) {
 	int sms = 0;
 	HU_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, db->device));
 	MmArgs g = {t.mmA, b->mmB, b->mmRange, t.mmTiles, numNt, stride, b->mmTileExt, stride - 1};
-	KeyEpi epi;
-	epi.keys = a.keys; epi.pitch = t.scanPitch; epi.nReads = a.nReads; epi.nNodes = t.nNodes; epi.mode = b->mmMode;
-	epi.nodeOfPos = t.nodeOfPos; epi.height = t.height; epi.keyTab = t.mmKeyTab; epi.maxHeight = a.maxHeight; epi.excl = false;
-	seedMmKernel<KeyEpi><<<std::min(sms, t.mmTiles * numNt), HU_MM_THREADS, HU_MM_SMEM, b->stream>>>(g, epi);
+	if (a.litBitA) { // level-1 flags of the literal seed order ride in the epilogue: the pivots first
+		seedLitPivotKernel<<<(a.nReads * 4 + 127) / 128, 128, 0, b->stream>>>(a, t, b->mmMode, a.nCand);
+		KeyEpi<true> epi;
+		epi.keys = a.keys; epi.pitch = t.scanPitch; epi.nReads = a.nReads; epi.nNodes = t.nNodes; epi.mode = b->mmMode;
+		epi.nodeOfPos = t.nodeOfPos; epi.height = t.height; epi.keyTab = t.mmKeyTab; epi.maxHeight = a.maxHeight; epi.excl = false;
+		epi.litPv = a.litPv; epi.litBitA = a.litBitA; epi.litBitB = a.litBitB; epi.litStride = getenv("HU_LIT_DRY") ? -a.litStride : a.litStride;
+		seedMmKernel<KeyEpi<true> ><<<std::min(sms, t.mmTiles * numNt), HU_MM_THREADS, HU_MM_SMEM, b->stream>>>(g, epi);
+	} else {
+		KeyEpi<false> epi;
+		epi.keys = a.keys; epi.pitch = t.scanPitch; epi.nReads = a.nReads; epi.nNodes = t.nNodes; epi.mode = b->mmMode;
+		epi.nodeOfPos = t.nodeOfPos; epi.height = t.height; epi.keyTab = t.mmKeyTab; epi.maxHeight = a.maxHeight; epi.excl = false;
+		epi.litPv = NULL; epi.litBitA = epi.litBitB = NULL; epi.litStride = 0;
+		seedMmKernel<KeyEpi<false> ><<<std::min(sms, t.mmTiles * numNt), HU_MM_THREADS, HU_MM_SMEM, b->stream>>>(g, epi);
+	}
 	seedMmFixupKernel<<<a.nReads, 256, 0, b->stream>>>(a, t, t.scanPitch, b->mmMode);
 	mmColScanKernel<<<1, 1024, 0, b->stream>>>(colCount, colStart, workStart, t.mmExcPtr, t.csLen);
 	mmColFillKernel<<<(a.nReads + 127) / 128, 128, 0, b->stream>>>(a, t, b->mmMode, colCount, colStart, b->mmColReads);
 	seedMmExceptionKernel<<<sms * 8, 128, 0, b->stream>>>(a, t, colStart, workStart, b->mmColReads);
-	*launches = 8;
+	*launches = a.litBitA ? 9 : 8;
 	HU_CUDA(cudaGetLastError());
 	return HU_OK;
 }
