@@ -252,7 +252,7 @@ int hu_batch_create(hu_batch** out, hu_db* db, int32_t maxReads, int32_t maxSeqL
 		HU_TRY(balloc(b, &b->mmRange, (size_t) numNt));
 		HU_TRY(balloc(b, &b->mmMode, (size_t) nReadsPad));
 		HU_TRY(balloc(b, &b->mmTileExt, (size_t) numNt));
-		HU_TRY(balloc(b, &b->mmCols, (size_t) 3 * (t.csLen + 1)));
+		HU_TRY(balloc(b, &b->mmCols, (size_t) 3 * (t.csLen + 1) + (size_t) (t.scanPitch + 3) / 4)); // + one byte per candidate position (mmPosExclKernel)
 		HU_TRY(balloc(b, &b->mmColReads, (size_t) maxReads * 64));
 	}
 	HU_TRY(balloc(b, &b->seed.seedIds, (size_t) maxReads * HU_MAX_SEED));

@@ -29,7 +29,9 @@
 #define HU_MM_A_BYTES (HU_MM_BM * HU_MM_BK)
 #define HU_MM_B_BYTES (HU_MM_BN * HU_MM_BK)
 #define HU_MM_STAGE_BYTES (HU_MM_A_BYTES + HU_MM_B_BYTES)
-#define HU_MM_THREADS 320
+#define HU_MM_EPI_WARPS 16 // epilogue warps: a multiple of four (TMEM lane quarter = warp id % 4), each takes HU_MM_EPI_COLS columns of the accumulator
+#define HU_MM_EPI_COLS (HU_MM_BN / (HU_MM_EPI_WARPS / 4))
+#define HU_MM_THREADS (64 + 32 * HU_MM_EPI_WARPS)
 #define HU_MM_SMEM (HU_MM_STAGES * HU_MM_STAGE_BYTES + 1024) // + slack to align the ring to the swizzle period
 #define HU_MM_MAX_N 4095 // valid columns per (node, read) for which the packed accumulator decodes exactly
 
@@ -99,17 +101,22 @@ __device__ __forceinline__ uint64_t mmSmemDesc(uint32_t saddr) {
 #define HU_MM_IDESC ((2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t) (HU_MM_BN >> 3) << 17) | ((uint32_t) (HU_MM_BM >> 4) << 24))
 
 // Epi: __device__ void operator()(int mt, int nt, int row, int col0, const uint32_t (&v)[32], int lane) -- v[j] is the
-// accumulator of (node row 128 mt + row, read 256 nt + col0 + j); begin(mt, nt, row) is called once per tile and thread
+// accumulator of (node row 128 mt + row, read 256 nt + col0 + j); begin(mt, nt, row) is called once per tile and thread, and
+// prefetch(mt, nt, row) one tile ahead of it (it may only load into registers of the functor);
+// init(smem, tid, nThreads) once per CTA by every thread, with Epi::SMEM_BYTES of shared memory of its own.
+// (Measured and dropped, profiles/r2_summary.md: the tcgen05.ld of the next chunk issued ahead of this chunk's epilogue.)
 template <class Epi>
 __global__ void __launch_bounds__(HU_MM_THREADS, 1) seedMmKernel(MmArgs g, Epi epi) {
 	extern __shared__ uint8_t mmSmem[];
 	__shared__ unsigned long long full[HU_MM_STAGES], empty[HU_MM_STAGES], accFull[2], accEmpty[2];
 	__shared__ uint32_t sTmem;
+	__shared__ __align__(16) uint8_t epiSm[Epi::SMEM_BYTES > 0 ? Epi::SMEM_BYTES : 16];
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	epi.init(epiSm, threadIdx.x, HU_MM_THREADS); // published by the barrier below
 	uint8_t* ring = mmSmem + ((1024u - (smemAddr(mmSmem) & 1023u)) & 1023u);
 	if (threadIdx.x == 0) {
 		for (int s = 0; s < HU_MM_STAGES; ++s) { mbarInit(&full[s], 1); mbarInit(&empty[s], 1); }
-		for (int s = 0; s < 2; ++s) { mbarInit(&accFull[s], 1); mbarInit(&accEmpty[s], 8); }
+		for (int s = 0; s < 2; ++s) { mbarInit(&accFull[s], 1); mbarInit(&accEmpty[s], HU_MM_EPI_WARPS); }
 		mbarInitFence();
 	}
 	if (warp == 1) tmemAlloc(&sTmem, 512);
@@ -167,28 +174,35 @@ __global__ void __launch_bounds__(HU_MM_THREADS, 1) seedMmKernel(MmArgs g, Epi e
 		}
 	} else {
 		const int q = warp & 3;         // the TMEM lane quarter this warp may read (warp id % 4)
-		const int h = (warp - 2) >> 2;  // which half of the accumulator's columns
+		const int h = (warp - 2) >> 2;  // which group of HU_MM_EPI_COLS columns of the accumulator
 		int acc = 0;
 		uint32_t accPh = 0;
-		for (int item = blockIdx.x; item < nItems; item += gridDim.x) {
+		// items whose read tile has no window are skipped (by the other two roles as well)
+		int item = blockIdx.x;
+		while (item < nItems && g.range[item % g.numNt].x > g.range[item % g.numNt].y) item += gridDim.x;
+		if (item < nItems) epi.prefetch(item / g.numNt, item % g.numNt, q * 32 + lane);
+		while (item < nItems) {
 			const int mt = item / g.numNt, nt = item - mt * g.numNt;
-			const int2 rg = g.range[nt];
-			if (rg.x > rg.y) continue;
-			epi.begin(mt, nt, q * 32 + lane);
+			epi.begin(mt, nt, q * 32 + lane); // takes what prefetch() loaded
+			item += gridDim.x;
+			while (item < nItems && g.range[item % g.numNt].x > g.range[item % g.numNt].y) item += gridDim.x;
+			// the per-tile loads of the NEXT item are issued now and land while this tile is turned into keys (begin()'s loads
+			// used to sit in front of every tile: 14 % of the kernel's stall samples)
+			if (item < nItems) epi.prefetch(item / g.numNt, item % g.numNt, q * 32 + lane);
 			mbarWait(&accFull[acc], accPh);
 			tcFenceAfter();
-			const uint32_t ta = tmem + ((uint32_t) (q * 32) << 16) + (uint32_t) (acc * HU_MM_BN + h * (HU_MM_BN / 2));
+			const uint32_t ta = tmem + ((uint32_t) (q * 32) << 16) + (uint32_t) (acc * HU_MM_BN + h * HU_MM_EPI_COLS);
 #pragma unroll 1
-			for (int c = 0; c < HU_MM_BN / 2 / 32; ++c) {
+			for (int c = 0; c < HU_MM_EPI_COLS / 32; ++c) {
 				uint32_t v[32];
 				tmemLd32(ta + (uint32_t) (c * 32), v);
 				tmemLdWait();
-				if (c == HU_MM_BN / 2 / 32 - 1) { // the accumulator is in registers: hand it back to the MMA warp
+				if (c == HU_MM_EPI_COLS / 32 - 1) { // the accumulator is in registers: hand it back to the MMA warp
 					tcFenceBefore();
 					__syncwarp();
 					if (lane == 0) mbarArrive(&accEmpty[acc]);
 				}
-				epi(mt, nt, q * 32 + lane, h * (HU_MM_BN / 2) + c * 32, v, lane);
+				epi(mt, nt, q * 32 + lane, h * HU_MM_EPI_COLS + c * 32, v, lane);
 			}
 			acc ^= 1;
 			if (acc == 0) accPh ^= 1u;

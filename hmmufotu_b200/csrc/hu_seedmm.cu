@@ -138,6 +138,16 @@ __global__ void __launch_bounds__(HU_MM_BN) mmRangeKernel(SeedArgs a, int2* __re
 	if (threadIdx.x == 0) range[blockIdx.x] = make_int2(sLo, sHi);
 }
 
+// position -> 1 if it is not a candidate of this run (padding, or the node lies above --max-height): once per launch, so that the
+// tile kernel's epilogue has one byte to load per position instead of a node id and then its height
+__global__ void mmPosExclKernel(const int* __restrict__ nodeOfPos, const double* __restrict__ height, double maxHeight, int nNodes, int pitch,
+		uint8_t* __restrict__ posExcl) {
+	const int p = blockIdx.x * blockDim.x + threadIdx.x;
+	if (p >= pitch) return;
+	const int node = __ldg(nodeOfPos + p);
+	posExcl[p] = (node < 0 || node >= nNodes || !(__ldg(height + node) <= maxHeight)) ? 1 : 0;
+}
+
 // ---- epilogue of seedMmKernel: accumulator -> seed key ----
 // Integer form of the key.  2^31 = Q N + R (Q = floor(2^31 / N), R < N), so floor(d 2^31 / N) = d Q + floor(d R / N) with
 // d R < N^2 < 2^24; the small quotient is a multiply-high: floor(t / N) = (t m) >> k for m = ceil(2^k / N) whenever
@@ -166,19 +176,53 @@ struct KeyEpi {
 	uint32_t* keys;
 	int pitch, nReads, nNodes;
 	const int* mode;
-	const int* nodeOfPos;
-	const double* height;
+	const uint8_t* posExcl; // [pitch] 1: the position is not a candidate of this run (padding, or above --max-height)
 	const uint4* keyTab; // [HU_MM_MAX_N + 1]
-	double maxHeight;
 	const uint32_t* litPv; // LIT: pivot per read
 	uint32_t* litBitA;     // LIT: [litStride][pitch / 32]
 	uint32_t* litBitB;
 	int litStride;
 	bool excl; // per thread: this position is not a candidate (padding, or above --max-height)
+	bool tilePlain; // per warp and tile: no per-key tests needed
+	static constexpr int NCH = HU_MM_EPI_COLS / 32; // 32-read chunks per warp and tile
+	static constexpr int SMEM_BYTES = LIT ? HU_MM_EPI_WARPS * HU_MM_EPI_COLS * 4 : 0;
+	uint32_t* pvSm;      // LIT: the pivots of the 128 reads this warp handles in the current tile
+	uint32_t fa[NCH], fb[NCH]; // LIT: this position's flag words against the 32-read chunks of the tile
+	__device__ __forceinline__ void init(void* sm, int tid, int) {
+		pvSm = reinterpret_cast<uint32_t*>(sm) + max((tid >> 5) - 2, 0) * HU_MM_EPI_COLS; // epilogue warps are warps 2, 3, ...
+	}
+	// the per-tile inputs of the next tile, loaded one tile ahead
+	uint32_t nxExcl;
+	int nxMode[NCH];
+	uint32_t nxPv[NCH];
+	__device__ __forceinline__ void prefetch(int mt, int nt, int row) {
+		const int p = mt * HU_MM_BM + row;
+		nxExcl = p < pitch ? (uint32_t) __ldg(posExcl + p) : 1u;
+		const int lane = threadIdx.x & 31, h = ((int) (threadIdx.x >> 5) - 2) >> 2;
+		const int rb = nt * HU_MM_BN + h * HU_MM_EPI_COLS;
+#pragma unroll
+		for (int i = 0; i < NCH; ++i) {
+			const int rr = rb + i * 32 + lane;
+			nxMode[i] = rr < nReads ? __ldg(mode + rr) : 2;
+			if (LIT) nxPv[i] = rr < abs(litStride) ? __ldg(litPv + rr) : 0u;
+		}
+	}
 	__device__ __forceinline__ void begin(int mt, int, int row) {
 		const int p = mt * HU_MM_BM + row;
-		const int node = p < pitch ? __ldg(nodeOfPos + p) : -1;
-		excl = node < 0 || node >= nNodes || !(__ldg(height + node) <= maxHeight);
+		excl = nxExcl != 0u;
+		// the common case, decided once per tile: every position of this warp is a candidate, every one of its reads exists and is
+		// in tier 1 or 2
+		bool odd = excl || p >= pitch;
+#pragma unroll
+		for (int i = 0; i < NCH; ++i) odd = odd || nxMode[i] == 2 || nxMode[i] < 0;
+		tilePlain = !__any_sync(0xffffffffu, odd);
+		if (LIT) {
+			const int lane = threadIdx.x & 31;
+			__syncwarp(); // the previous tile's flags() of this warp are done with the old pivots
+#pragma unroll
+			for (int i = 0; i < NCH; ++i) pvSm[i * 32 + lane] = nxPv[i];
+			__syncwarp();
+		}
 	}
 	__device__ __forceinline__ uint32_t key(int S) const {
 		const int N = (S + 4096) >> 14;
@@ -187,42 +231,54 @@ struct KeyEpi {
 		const uint32_t q = __umulhi((uint32_t) d * e.y, e.z) >> e.w;
 		return S == 0 ? 0xFFFFFFFFu : (uint32_t) d * e.x + q;
 	}
-	// k[j]: this position's key for read r0 + j
-	__device__ __forceinline__ void flags(const uint32_t (&k)[32], int p, int r0, int lane) const {
-		if (r0 >= abs(litStride)) return; // litStride is a multiple of 32, and so is r0
-		const uint4* pvp = reinterpret_cast<const uint4*>(litPv + r0); // the same address in every lane: one broadcast per four pivots
-		uint32_t fa = 0u, fb = 0u;
+	// k[j]: this position's key for read r0 + j.  The flag words of the tile's four chunks are transposed together after the last
+	// one: eight independent butterfly chains hide the shuffle latency that one chain per chunk left exposed (two epilogue warps
+	// per scheduler).  (Measured and dropped: the key table's first 1024 entries in shared memory.)
+	__device__ __forceinline__ void flags(const uint32_t (&k)[32], int p, int r0, int lane) {
+		const int c = (r0 & (HU_MM_EPI_COLS - 1)) >> 5;
+		const uint4* pvp = reinterpret_cast<const uint4*>(pvSm + c * 32); // the same address in every lane: one broadcast per four pivots
+		uint32_t xa = 0u, xb = 0u;
 #pragma unroll
 		for (int q = 0; q < 8; ++q) {
-			const uint4 pv = __ldg(pvp + q);
+			const uint4 pv = pvp[q];
 			const uint32_t pvs[4] = {pv.x, pv.y, pv.z, pv.w};
 #pragma unroll
-			for (int c = 0; c < 4; ++c) {
-				const int j = 4 * q + c;
-				if (k[j] >= pvs[c]) fa |= 1u << j; // a compare and a predicated OR each
-				if (k[j] <= pvs[c]) fb |= 1u << j;
+			for (int i = 0; i < 4; ++i) {
+				const int j = 4 * q + i;
+				if (k[j] >= pvs[i]) xa |= 1u << j;
+				if (k[j] <= pvs[i]) xb |= 1u << j;
 			}
 		}
-		fa = warpBitTranspose(fa, lane);
-		fb = warpBitTranspose(fb, lane);
-		const size_t o = (size_t) (r0 + lane) * (size_t) (pitch >> 5) + (size_t) (p >> 5); // p >> 5 is the warp's word: its lanes are 32 consecutive positions
-		if (litStride > 0) { litBitA[o] = fa; litBitB[o] = fb; } // litStride < 0: a dry run for measurements (HU_LIT_DRY)
+#pragma unroll
+		for (int i = 0; i < NCH; ++i)
+			if (i == c) { fa[i] = xa; fb[i] = xb; }
+		if (c != NCH - 1) return;
+#pragma unroll
+		for (int i = 0; i < NCH; ++i) { fa[i] = warpBitTranspose(fa[i], lane); fb[i] = warpBitTranspose(fb[i], lane); }
+		const int rb = r0 - 32 * (NCH - 1) + lane; // this lane's read in chunk 0
+#pragma unroll
+		for (int i = 0; i < NCH; ++i) {
+			const int rr = rb + i * 32;
+			if (rr < abs(litStride) && litStride > 0) { // litStride < 0: a dry run for measurements (HU_LIT_DRY)
+				const size_t o = (size_t) rr * (size_t) (pitch >> 5) + (size_t) (p >> 5); // p >> 5 is the warp's word: its lanes are 32 consecutive positions
+				litBitA[o] = fa[i]; litBitB[o] = fb[i];
+			}
+		}
 	}
-	__device__ __forceinline__ void operator()(int mt, int nt, int row, int col0, const uint32_t (&v)[32], int lane) const {
+	__device__ __forceinline__ void operator()(int mt, int nt, int row, int col0, const uint32_t (&v)[32], int lane) {
 		const int p = mt * HU_MM_BM + row;
 		const int r0 = nt * HU_MM_BN + col0;
-		const int rl = r0 + lane;
-		const int md = rl < nReads ? __ldg(mode + rl) : 0;
-		const unsigned rawMask = __ballot_sync(0xffffffffu, md == 2);  // finished by seedMmFixupKernel
-		const unsigned badMask = __ballot_sync(0xffffffffu, md < 0);   // sparse list overflow: the read stays unplaced
-		const bool plain = !__any_sync(0xffffffffu, excl || p >= pitch) && rawMask == 0u && badMask == 0u && r0 + 32 <= nReads;
 		uint32_t* out = keys + (size_t) r0 * pitch + p;
 		uint32_t k[32];
-		if (plain) { // the common case: no per-key tests
+		if (tilePlain) { // the common case: no per-key tests
 #pragma unroll
 			for (int j = 0; j < 32; ++j) { k[j] = key((int) v[j]); *out = k[j]; out += pitch; }
 		} else {
 			if (p >= pitch) return; // whole warps: pitch is a multiple of 32
+			const int rl = r0 + lane;
+			const int md = rl < nReads ? __ldg(mode + rl) : 0;
+			const unsigned rawMask = __ballot_sync(0xffffffffu, md == 2);  // finished by seedMmFixupKernel
+			const unsigned badMask = __ballot_sync(0xffffffffu, md < 0);   // sparse list overflow: the read stays unplaced
 			const int nr = min(32, nReads - r0);
 #pragma unroll
 			for (int j = 0; j < 32; ++j) {
@@ -487,25 +543,26 @@ int launchSeedMm(hu_batch* b, const SeedArgs& a, int* launches) {
 	int sms = 0;
 	HU_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, db->device));
 	MmArgs g = {t.mmA, b->mmB, b->mmRange, t.mmTiles, numNt, stride, b->mmTileExt, stride - 1};
-	if (a.litBitA) { // level-1 flags of the literal seed order ride in the epilogue: the pivots first
+	if (a.litBitA) // level-1 flags of the literal seed order ride in the epilogue: the pivots first
 		seedLitPivotKernel<<<(a.nReads * 4 + 127) / 128, 128, 0, b->stream>>>(a, t, b->mmMode, a.nCand);
-		KeyEpi<true> epi;
-		epi.keys = a.keys; epi.pitch = t.scanPitch; epi.nReads = a.nReads; epi.nNodes = t.nNodes; epi.mode = b->mmMode;
-		epi.nodeOfPos = t.nodeOfPos; epi.height = t.height; epi.keyTab = t.mmKeyTab; epi.maxHeight = a.maxHeight; epi.excl = false;
-		epi.litPv = a.litPv; epi.litBitA = a.litBitA; epi.litBitB = a.litBitB; epi.litStride = getenv("HU_LIT_DRY") ? -a.litStride : a.litStride;
-		seedMmKernel<KeyEpi<true> ><<<std::min(sms, t.mmTiles * numNt), HU_MM_THREADS, HU_MM_SMEM, b->stream>>>(g, epi);
-	} else {
-		KeyEpi<false> epi;
-		epi.keys = a.keys; epi.pitch = t.scanPitch; epi.nReads = a.nReads; epi.nNodes = t.nNodes; epi.mode = b->mmMode;
-		epi.nodeOfPos = t.nodeOfPos; epi.height = t.height; epi.keyTab = t.mmKeyTab; epi.maxHeight = a.maxHeight; epi.excl = false;
-		epi.litPv = NULL; epi.litBitA = epi.litBitB = NULL; epi.litStride = 0;
-		seedMmKernel<KeyEpi<false> ><<<std::min(sms, t.mmTiles * numNt), HU_MM_THREADS, HU_MM_SMEM, b->stream>>>(g, epi);
-	}
+	const int gridMm = std::min(sms, t.mmTiles * numNt);
+	uint8_t* posExcl = reinterpret_cast<uint8_t*>(b->mmCols + 3 * (t.csLen + 1)); // the tail of the per-column work arrays
+	mmPosExclKernel<<<(t.scanPitch + 255) / 256, 256, 0, b->stream>>>(t.nodeOfPos, t.height, a.maxHeight, t.nNodes, t.scanPitch, posExcl);
+#define HU_MM_LAUNCH(LIT) { \
+		KeyEpi<LIT> epi; \
+		epi.keys = a.keys; epi.pitch = t.scanPitch; epi.nReads = a.nReads; epi.nNodes = t.nNodes; epi.mode = b->mmMode; \
+		epi.posExcl = posExcl; epi.keyTab = t.mmKeyTab; \
+		epi.excl = false; epi.tilePlain = false; epi.pvSm = NULL; \
+		epi.litPv = a.litPv; epi.litBitA = a.litBitA; epi.litBitB = a.litBitB; \
+		epi.litStride = (LIT && getenv("HU_LIT_DRY")) ? -a.litStride : a.litStride; \
+		seedMmKernel<KeyEpi<LIT> ><<<gridMm, HU_MM_THREADS, HU_MM_SMEM, b->stream>>>(g, epi); }
+	if (a.litBitA) HU_MM_LAUNCH(true) else HU_MM_LAUNCH(false)
+#undef HU_MM_LAUNCH
 	seedMmFixupKernel<<<a.nReads, 256, 0, b->stream>>>(a, t, t.scanPitch, b->mmMode);
 	mmColScanKernel<<<1, 1024, 0, b->stream>>>(colCount, colStart, workStart, t.mmExcPtr, t.csLen);
 	mmColFillKernel<<<(a.nReads + 127) / 128, 128, 0, b->stream>>>(a, t, b->mmMode, colCount, colStart, b->mmColReads);
 	seedMmExceptionKernel<<<sms * 8, 128, 0, b->stream>>>(a, t, colStart, workStart, b->mmColReads);
-	*launches = a.litBitA ? 9 : 8;
+	*launches = a.litBitA ? 10 : 9;
 	HU_CUDA(cudaGetLastError());
 	return HU_OK;
 }

@@ -10,6 +10,9 @@ using namespace hu;
 
 struct RawEpi {
 	int* out; int mTot;
+	static constexpr int SMEM_BYTES = 0;
+	__device__ void init(void*, int, int) {}
+	__device__ void prefetch(int, int, int) {}
 	__device__ void begin(int, int, int) {}
 	__device__ void operator()(int mt, int nt, int row, int col0, const uint32_t (&v)[32], int) {
 #pragma unroll
