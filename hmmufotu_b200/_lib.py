@@ -60,7 +60,7 @@ class SepParams(C.Structure):
 class BatchStats(C.Structure):
     _fields_ = [("cells", C.c_int64), ("seedPairs", C.c_int64), ("seedBytes", C.c_int64), ("estItems", C.c_int64),
                 ("estBytes", C.c_int64), ("placeItems", C.c_int64), ("placeBytes", C.c_int64), ("launches", C.c_int64),
-                ("seedHeapSorts", C.c_int64), ("seedMacs", C.c_int64)]
+                ("seedHeapSorts", C.c_int64), ("seedMacs", C.c_int64), ("seedScanFlags", C.c_int64)]
 
 
 # every symbol include/hmmufotu_b200.h declares

@@ -628,6 +628,8 @@ int hu_batch_get_stats(hu_batch* b, hu_batch_stats* s) {
 	int hf = 0;
 	HU_CUDA(cudaMemcpy(&hf, b->workCount + 4, sizeof(int), cudaMemcpyDeviceToHost));
 	s->seedHeapSorts = hf;
+	HU_CUDA(cudaMemcpy(&hf, b->workCount + 5, sizeof(int), cudaMemcpyDeviceToHost));
+	s->seedScanFlags = hf;
 	if (b->mmScanRan && b->mmRange) {
 		const int numNt = (b->nReads + HU_MM_BN - 1) / HU_MM_BN;
 		std::vector<int2> rg(numNt);

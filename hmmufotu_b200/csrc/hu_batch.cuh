@@ -68,6 +68,7 @@ struct SeedArgs {
 	uint32_t* litBitA;      // [litStride][scanPitch / 32]: bit p%32 of word p/32 of a read's row = (key at position p >= pivot); NULL: not in use
 	uint32_t* litBitB;      // same layout: key <= pivot
 	int litStride;          // reads per bitmap word row (maxReads rounded up to 32)
+	int* litFromScan;       // diagnostic counter: reads whose first flag pass came from the scan
 };
 
 // one (read, seed) of the estimate stage, resolved once so that the streaming kernel has no dependent loads

@@ -610,6 +610,7 @@ __global__ void __launch_bounds__(HU_LIT_THREADS) seedSortLiteralKernel(SeedArgs
 			// is clear, position mS holds what was first, and nothing exists at or beyond n.
 			const bool fromScan = a.litBitA != NULL && a.litOk[r] && a.litPv[r] == pv; // uniform over the CTA
 			if (fromScan) {
+				if (tid == 0 && a.litFromScan) atomicAdd(a.litFromScan, 1);
 				const uint32_t* ga = a.litBitA + (size_t) r * (size_t) (pitch >> 5);
 				const uint32_t* gb = a.litBitB + (size_t) r * (size_t) (pitch >> 5);
 				for (int wd = tid; wd < nW; wd += HU_LIT_THREADS) {
@@ -1012,7 +1013,8 @@ int launchSeed(hu_batch* b, const hu_sep_params* p) {
 	a.winStart = b->winStart;
 	a.winEnd = b->winEnd;
 	a.heapFallbacks = b->workCount + 4;
-	HU_CUDA(cudaMemsetAsync(a.heapFallbacks, 0, sizeof(int), b->stream));
+	a.litFromScan = b->workCount + 5;
+	HU_CUDA(cudaMemsetAsync(a.heapFallbacks, 0, 2 * sizeof(int), b->stream));
 	// The key vector of a read is getSeed's candidate vector: the non-root nodes in id order that pass the height filter
 	// (src/HmmUFOtu_main.cpp:131-137).  The literal order replays std::sort on exactly that vector, so with -H/--max-height
 	// the candidates are compacted (positions = ranks among the passing nodes); the (dist, id) order keeps one position per
@@ -1050,7 +1052,7 @@ int launchSeed(hu_batch* b, const hu_sep_params* p) {
 		const char* e = getenv("HU_LIT_BITS");
 		const bool want = !(e && !strcmp(e, "0"));
 		if (want && literal && t.mmA && b->mmB && a.posOfSlot == t.posOfSlot && !(p->maxDiff < INFINITY) && a.nCand > 4 * HU_LIT_SMALL &&
-		    t.scanPitch % 32 == 0) {
+		    t.scanPitch % 128 == 0) {
 			const int stride = (b->maxReads + 31) / 32 * 32;
 			const size_t words = (size_t) (t.scanPitch / 32) * stride;
 			if (!b->litBits) {

@@ -185,11 +185,18 @@ struct KeyEpi {
 	bool excl; // per thread: this position is not a candidate (padding, or above --max-height)
 	bool tilePlain; // per warp and tile: no per-key tests needed
 	static constexpr int NCH = HU_MM_EPI_COLS / 32; // 32-read chunks per warp and tile
-	static constexpr int SMEM_BYTES = LIT ? HU_MM_EPI_WARPS * HU_MM_EPI_COLS * 4 : 0;
+	static constexpr int NGRP = HU_MM_EPI_WARPS / 4; // groups of four warps (the four TMEM lane quarters) that share a column group
+	static constexpr int XCH_WORDS = HU_MM_EPI_COLS * 4 * 2; // per group and buffer: [bitmap][read][lane quarter]
+	static constexpr int SMEM_BYTES = LIT ? HU_MM_EPI_WARPS * HU_MM_EPI_COLS * 4 + 2 * NGRP * XCH_WORDS * 4 : 0;
 	uint32_t* pvSm;      // LIT: the pivots of the 128 reads this warp handles in the current tile
 	uint32_t fa[NCH], fb[NCH]; // LIT: this position's flag words against the 32-read chunks of the tile
+	uint32_t* xch;       // LIT: this group's two exchange buffers (the four lane-quarter warps assemble 16-byte bitmap stores)
+	int xchFlip;
 	__device__ __forceinline__ void init(void* sm, int tid, int) {
-		pvSm = reinterpret_cast<uint32_t*>(sm) + max((tid >> 5) - 2, 0) * HU_MM_EPI_COLS; // epilogue warps are warps 2, 3, ...
+		const int ew = max((tid >> 5) - 2, 0); // epilogue warps are warps 2, 3, ...
+		pvSm = reinterpret_cast<uint32_t*>(sm) + ew * HU_MM_EPI_COLS;
+		xch = reinterpret_cast<uint32_t*>(sm) + HU_MM_EPI_WARPS * HU_MM_EPI_COLS + (ew >> 2) * 2 * XCH_WORDS;
+		xchFlip = 0;
 	}
 	// the per-tile inputs of the next tile, loaded one tile ahead
 	uint32_t nxExcl;
@@ -255,13 +262,29 @@ struct KeyEpi {
 		if (c != NCH - 1) return;
 #pragma unroll
 		for (int i = 0; i < NCH; ++i) { fa[i] = warpBitTranspose(fa[i], lane); fb[i] = warpBitTranspose(fb[i], lane); }
-		const int rb = r0 - 32 * (NCH - 1) + lane; // this lane's read in chunk 0
+		// lane j now holds, per chunk, the word of read j for this warp's 32 positions.  The four warps of the group hold the four
+		// words of the tile (128 positions) of the same reads: they meet in shared memory and each thread stores 16 bytes of one
+		// read's bitmap (4-byte stores, 32 sectors per instruction, cost the kernel 0.5 ms).  Two buffers, one barrier per tile:
+		// a buffer is written again two tiles later, after the barrier of the tile in between, which every reader has passed.
+		const int ew = (int) (threadIdx.x >> 5) - 2, q = (int) (threadIdx.x >> 5) & 3, g = ew >> 2;
+		uint32_t* xb_ = xch + xchFlip * XCH_WORDS;
+		xchFlip ^= 1;
 #pragma unroll
 		for (int i = 0; i < NCH; ++i) {
-			const int rr = rb + i * 32;
-			if (rr < abs(litStride) && litStride > 0) { // litStride < 0: a dry run for measurements (HU_LIT_DRY)
-				const size_t o = (size_t) rr * (size_t) (pitch >> 5) + (size_t) (p >> 5); // p >> 5 is the warp's word: its lanes are 32 consecutive positions
-				litBitA[o] = fa[i]; litBitB[o] = fb[i];
+			xb_[(i * 32 + lane) * 4 + q] = fa[i];
+			xb_[HU_MM_EPI_COLS * 4 + (i * 32 + lane) * 4 + q] = fb[i];
+		}
+		asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
+		// thread t of the group's 128: bitmap t / 64... (HU_MM_EPI_COLS reads per bitmap), read t % HU_MM_EPI_COLS
+		const int t = (ew & 3) * 32 + lane; // 0..127 within the group, any order
+#pragma unroll
+		for (int u = t; u < 2 * HU_MM_EPI_COLS; u += 128) {
+			const int which = u / HU_MM_EPI_COLS, rd = u - which * HU_MM_EPI_COLS;
+			const int rr = (r0 - 32 * (NCH - 1)) + rd;
+			const uint4 w4 = *reinterpret_cast<const uint4*>(xb_ + which * HU_MM_EPI_COLS * 4 + rd * 4);
+			if (rr < abs(litStride) && litStride > 0 && p < pitch) { // litStride < 0: a dry run for measurements (HU_LIT_DRY)
+				uint32_t* dst = (which ? litBitB : litBitA) + (size_t) rr * (size_t) (pitch >> 5) + (size_t) ((p >> 7) << 2); // the tile's four words
+				*reinterpret_cast<uint4*>(dst) = w4;
 			}
 		}
 	}
@@ -274,7 +297,6 @@ struct KeyEpi {
 #pragma unroll
 			for (int j = 0; j < 32; ++j) { k[j] = key((int) v[j]); *out = k[j]; out += pitch; }
 		} else {
-			if (p >= pitch) return; // whole warps: pitch is a multiple of 32
 			const int rl = r0 + lane;
 			const int md = rl < nReads ? __ldg(mode + rl) : 0;
 			const unsigned rawMask = __ballot_sync(0xffffffffu, md == 2);  // finished by seedMmFixupKernel
@@ -288,7 +310,7 @@ struct KeyEpi {
 					k[j] = ((uint32_t) ((16387 * N - S) >> 2) << 16) | (uint32_t) N;
 				} else
 					k[j] = (excl || ((badMask >> j) & 1u)) ? 0xFFFFFFFFu : key(S);
-				if (j < nr) out[(size_t) j * pitch] = k[j];
+				if (j < nr && p < pitch) out[(size_t) j * pitch] = k[j];
 			}
 		}
 		if (LIT) flags(k, p, r0, lane);
@@ -552,7 +574,7 @@ int launchSeedMm(hu_batch* b, const SeedArgs& a, int* launches) {
 		KeyEpi<LIT> epi; \
 		epi.keys = a.keys; epi.pitch = t.scanPitch; epi.nReads = a.nReads; epi.nNodes = t.nNodes; epi.mode = b->mmMode; \
 		epi.posExcl = posExcl; epi.keyTab = t.mmKeyTab; \
-		epi.excl = false; epi.tilePlain = false; epi.pvSm = NULL; \
+		epi.excl = false; epi.tilePlain = false; epi.pvSm = NULL; epi.xch = NULL; epi.xchFlip = 0; \
 		epi.litPv = a.litPv; epi.litBitA = a.litBitA; epi.litBitB = a.litBitB; \
 		epi.litStride = (LIT && getenv("HU_LIT_DRY")) ? -a.litStride : a.litStride; \
 		seedMmKernel<KeyEpi<LIT> ><<<gridMm, HU_MM_THREADS, HU_MM_SMEM, b->stream>>>(g, epi); }

@@ -264,6 +264,7 @@ typedef struct hu_batch_stats {
 	int64_t launches;     /* kernels launched since the last hu_batch_upload / set_aligned */
 	int64_t seedHeapSorts; /* reads whose literal seed order reached introsort's heap-sort fallback (replayed; diagnostic) */
 	int64_t seedMacs;     /* int8 multiply-accumulates of the tensor-core seed scan (tiles x chunks visited); 0: the bit-plane scan ran */
+	int64_t seedScanFlags; /* reads whose literal seed order took its first flag pass from the scan's epilogue (diagnostic) */
 } hu_batch_stats;
 int hu_batch_get_stats(hu_batch* b, hu_batch_stats* s);
 

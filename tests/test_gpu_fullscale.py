@@ -119,3 +119,35 @@ def test_pipeline_properties_and_determinism(full):
         assert np.allclose(q["loglik"], W, rtol=1e-9)            # literal placeSeq return: W (1 + log sum(pi))
         assert (q["outerIters"] >= 1).all() and (q["loglikTrue"] == 0).all()   # the root log-likelihood is evaluated only on request
         assert best[i]["nPlaces"] == nk[i] and best[i]["cNode"] in q["cNode"]
+
+
+def test_literal_order_flag_pass_from_the_scan_equals_the_pass_in_the_sort(full, monkeypatch):
+    """Level 1 of the literal seed order's flag pass is made by the tensor-core scan's epilogue (pivot known ahead of the scan,
+    bitmaps per read, exception pairs patch their bits): the seeds must be those of the replay that reads the key rows itself
+    (HU_LIT_BITS=0), and every read must really have taken the bitmaps.  --max-diff needs the largest key, which only the
+    replay's own pass sees: that run must fall back, with the same seeds either way."""
+    engine, gdb, rs = full["engine"], full["gdb"], full["reads"]
+
+    def seeds(env, max_diff=None):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        p = engine.SepParams() if max_diff is None else engine.SepParams(max_diff=max_diff)
+        b = engine.Batch(gdb, rs.n, 260)
+        b.upload(rs)
+        b.alignSeq()
+        b.getSeed(p)
+        ns, ids, _ = b.seeds()
+        st = b.stats()
+        b.close()
+        for k in env:
+            monkeypatch.delenv(k)
+        return ns, ids, st
+
+    ns1, ids1, st1 = seeds({})
+    ns0, ids0, st0 = seeds({"HU_LIT_BITS": "0"})
+    assert st1["seedScanFlags"] == rs.n and st0["seedScanFlags"] == 0
+    assert np.array_equal(ns1, ns0) and np.array_equal(ids1, ids0)
+    nsd1, idsd1, std1 = seeds({}, max_diff=0.05)
+    nsd0, idsd0, _ = seeds({"HU_LIT_BITS": "0"}, max_diff=0.05)
+    assert std1["seedScanFlags"] == 0
+    assert np.array_equal(nsd1, nsd0) and np.array_equal(idsd1, idsd0)
