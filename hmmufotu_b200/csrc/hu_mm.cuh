@@ -13,12 +13,14 @@
 // r of a group at 128 (r & 7), its 16-byte chunk j at chunk position j ^ (r & 7) (Swizzle<3,4,3>).  A stage of the
 // pipeline is then ONE cp.async.bulk per operand (16 KB + 32 KB), no tensor map.
 //
-// Kernel: persistent, one CTA per SM, 10 warps: warp 0 lane 0 issues the bulk copies (4-stage ring of full/empty
-// mbarriers), warp 1 lane 0 issues the MMAs (4 x K=32 per stage) and commits them to the stage's empty barrier and, after
-// the last chunk, to the accumulator's full barrier; warps 2..9 are the epilogue: each reads its quarter of the TMEM lanes
-// (nodes) and half of the columns (reads) with tcgen05.ld, turns S into the seed key and writes it -- lane = node, so a
-// warp's store of one read's keys is one full 128-byte line of the key matrix.  Two accumulators (2 x 256 columns = all
-// of TMEM) let the MMAs of the next tile run under the epilogue of this one.
+// Kernel: persistent, one CTA per SM, 2 + HU_MM_EPI_WARPS warps: warp 0 lane 0 issues the bulk copies (4-stage ring of
+// full/empty mbarriers), warp 1 lane 0 issues the MMAs (4 x K=32 per stage) and commits them to the stage's empty barrier
+// and, after the last chunk, to the accumulator's full barrier; the other warps are the epilogue: each reads its quarter of
+// the TMEM lanes (nodes) and HU_MM_EPI_COLS of the columns (reads) with tcgen05.ld, turns S into the seed key and writes it
+// -- lane = node, so a warp's store of one read's keys is one full 128-byte line of the key matrix.  Two accumulators
+// (2 x 256 columns = all of TMEM) let the MMAs of the next tile run under the epilogue of this one.  16 epilogue warps of 96
+// registers rather than 8 of 168: the epilogue's dependent chains (key table lookup, multiply-high) need the warps to hide
+// them, and it is the longer side of the kernel once it also makes the literal seed order's flags (hu_seedmm.cu).
 #pragma once
 #include "hu_pipe.cuh"
 

@@ -5,7 +5,9 @@
 //                       id order; K = 4 bytes per profile match column) + one extension chunk per tile (below)
 //   per batch         : aligned reads -> operand B images (the read's bases inside its window), chunk range per read tile
 //   seedMmKernel      : S = A . B^T per (position, read) -> d, N -> key floor(d 2^31 / N), written in candidate order:
-//                       a warp's 32 lanes hold 32 consecutive positions of one read = one 128-byte line per store
+//                       a warp's 32 lanes hold 32 consecutive positions of one read = one 128-byte line per store;
+//                       with the literal seed order (std::sort replay, hu_seed.cu) also the first flag pass of that replay:
+//                       per read the bitmaps (key >= pivot), (key <= pivot) over the candidate positions (KeyEpi<true>)
 //
 // Read bases in NON-match columns (insertions buildGlobalAlign could place; pDist counts them like any column).  They are
 // few per read (about one for a 250-base amplicon read) but the node side is dense there for inferred sequences, which have
