@@ -69,6 +69,7 @@ struct SeedArgs {
 	uint32_t* litBitB;      // same layout: key <= pivot
 	int litStride;          // reads per bitmap word row (maxReads rounded up to 32)
 	int* litFromScan;       // diagnostic counter: reads whose first flag pass came from the scan
+	int* litCursor;         // next read of the literal order's persistent CTAs (NULL: reads dealt round-robin)
 };
 
 // one (read, seed) of the estimate stage, resolved once so that the streaming kernel has no dependent loads

@@ -561,8 +561,18 @@ __global__ void __launch_bounds__(HU_LIT_THREADS) seedSortLiteralKernel(SeedArgs
 #ifdef HU_PROF
 	long long pt_ = clock64();
 #endif
-	for (int r = blockIdx.x; r < a.nReads; r += gridDim.x) {
+	// Reads are taken from a queue: the cost of a replay varies with where the pivots fall (the first left part is anything from
+	// a tenth to nine tenths of the vector), and with 28 reads per CTA dealt round-robin the slowest CTA set the stage's time.
+	__shared__ int sRead;
+	for (int it = 0;; ++it) {
 		__syncthreads();
+		int r = blockIdx.x + it * gridDim.x;
+		if (a.litCursor) {
+			if (tid == 0) sRead = atomicAdd(a.litCursor, 1);
+			__syncthreads();
+			r = sRead;
+		}
+		if (r >= a.nReads) break;
 		LITP_MARK(7);
 		LITP_COUNT(8);
 		if (a.winStart[r] < 0 || n < 1) {
@@ -1014,7 +1024,8 @@ int launchSeed(hu_batch* b, const hu_sep_params* p) {
 	a.winEnd = b->winEnd;
 	a.heapFallbacks = b->workCount + 4;
 	a.litFromScan = b->workCount + 5;
-	HU_CUDA(cudaMemsetAsync(a.heapFallbacks, 0, 2 * sizeof(int), b->stream));
+	a.litCursor = b->workCount + 6;
+	HU_CUDA(cudaMemsetAsync(a.heapFallbacks, 0, 3 * sizeof(int), b->stream));
 	// The key vector of a read is getSeed's candidate vector: the non-root nodes in id order that pass the height filter
 	// (src/HmmUFOtu_main.cpp:131-137).  The literal order replays std::sort on exactly that vector, so with -H/--max-height
 	// the candidates are compacted (positions = ranks among the passing nodes); the (dist, id) order keeps one position per
