@@ -224,6 +224,58 @@ def test_builder_on_the_device(tmp_path):
     assert sk(str(tmp_path / "hand.ptu")) == sk(os.path.join(b, "hand.ptu"))
 
 
+def _export_builder_inputs(db, tmp_path):
+    """Builder inputs of a reference-built database, derived from the database itself with this repository's hmmufotu-inspect
+    (the reference's own 70_otus input files are not part of this repository): the leaves' aligned sequences, the tree in Newick
+    form with nodes named by id, the leaves' taxonomy, the substitution model.  Rebuilding from them gives the same node ids,
+    parents, branch lengths and sequences (checked on the CPU through the --messages-from hook: messages identical)."""
+    import gzip
+    import shutil
+    d = str(tmp_path)
+    for ext in ("msa", "hmm", "csfm"):
+        shutil.copy(os.path.join(GOLD, "%s.%s" % (db, ext)), os.path.join(d, "%s.%s" % (db, ext)))
+    ref_ptu = os.path.join(d, db + ".ptu")
+    with gzip.open(os.path.join(GOLD, db + ".ptu.gz"), "rb") as f, open(ref_ptu, "wb") as o:
+        o.write(f.read())
+    bind = os.path.join(ROOT, "hmmufotu_b200", "bin")
+    tree, anno, seqs, sm = (os.path.join(d, n) for n in ("in.tree", "in.anno", "in.fasta", "in.sm"))
+    r = subprocess.run([os.path.join(bind, "hmmufotu-inspect"), os.path.join(d, db), "-t", tree, "-a", anno, "-s", seqs], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-500:]
+    leaves = {ln[1:].split()[0] for ln in open(seqs) if ln.startswith(">")}
+    lines = [ln for ln in open(anno) if ln.split("\t")[0] in leaves]
+    with open(anno, "w") as o:
+        o.writelines(lines)
+    assert subprocess.run([os.path.join(bind, "hu_host_test"), "smdump", ref_ptu, sm]).returncode == 0
+    return ref_ptu, seqs, tree, anno, sm
+
+
+@pytest.mark.parametrize("db,extra", [("gg_70_otus_GTR", []), ("gg_70_otus_HKY85_dG", ["-V", "-k", "4"])])
+def test_builder_on_the_device_at_70_otus_size(tmp_path, db, extra):
+    """hmmufotu-build of this repository as ONE program run with the all-roots evaluation on the device, on
+    inputs the size of BASELINE.json configs[0] / [1] (125 leaves, 249 nodes, 1 486 columns; derived from the reference-built
+    databases, see _export_builder_inputs): every message within 1e-9 of what the reference's builder stored in its .ptu
+    (1.4e-14 when first run), the inferred ancestral sequences equal, with -V the discrete-Gamma shape estimated from the
+    device's fixed-rate evaluation equal to the reference's digit for digit (alpha = 1.8310984095294136), and the result
+    loads as a database."""
+    from hmmufotu_b200 import build
+    build.build_host()
+    bind = os.path.join(ROOT, "hmmufotu_b200", "bin")
+    ref_ptu, seqs, tree, anno, sm = _export_builder_inputs(db, tmp_path)
+    out = tmp_path / "out"
+    out.mkdir()
+    r = subprocess.run([os.path.join(bind, "hmmufotu-build"), seqs, tree, "-a", anno, "-n", "re70", "--dm", os.path.join(HERE, "golden", "build", "test_prior.dm"),
+                        "--sm", sm] + extra, cwd=str(out), capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-800:]
+    tool = os.path.join(bind, "hu_host_test")
+    cmp_ = subprocess.run([tool, "ptucmp", str(out / "re70.ptu"), ref_ptu], capture_output=True, text=True).stdout.split()
+    assert float(cmp_[1]) < 1e-9 and cmp_[3] == "1", cmp_
+    if extra:
+        dg = lambda f: subprocess.run([tool, "dgshow", f], capture_output=True, text=True).stdout.split("\n")[0]
+        assert dg(str(out / "re70.ptu")) == dg(ref_ptu) != ""
+    chk = subprocess.run([os.path.join(bind, "hmmufotu"), str(out / "re70"), "--check-db"], capture_output=True, text=True)
+    assert chk.returncode == 0 and "Database loaded" in chk.stderr, chk.stderr[-500:]
+
+
 def test_per_call_facades_write_the_references_rows(refdb_dir):
     """SURVEY.md 8(b), "class surface to preserve": the reference's own per-read loop (src/hmmufotu.cpp:603-751) written with
     ITS calls -- alignSeq, getSeed, estimateSeq, filterPlacements, placeSeq, calcQValues, std::sort, places[0] -- over the
