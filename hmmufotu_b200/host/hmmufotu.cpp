@@ -100,11 +100,18 @@ struct ReadBatchHost { // one batch of (pairs of) reads staged for hu_batch_uplo
 };
 
 static void stage(const PrimarySeq& read, const vector<BandedHMMP7::ViterbiAlignPath>& vps, ReadBatchHost& hb) {
-	for (size_t i = 0; i < read.length(); ++i) {
-		const int8_t b = DNA::encode((char) ::toupper(read.seq[i]));
-		if (b < 0) throw invalid_argument("read '" + read.id + "' holds a character outside the nucleotide alphabet");
-		hb.codes.push_back(b);
+	static int8_t table[256];
+	static bool tableMade = false; // built by the reader thread, the only caller
+	if (!tableMade) {
+		for (int c = 0; c < 256; ++c) table[c] = DNA::encode((char) ::toupper(c));
+		tableMade = true;
 	}
+	const size_t n = read.length(), at = hb.codes.size();
+	hb.codes.resize(at + n);
+	int8_t* out = hb.codes.data() + at;
+	int8_t bad = 0;
+	for (size_t i = 0; i < n; ++i) { out[i] = table[(unsigned char) read.seq[i]]; bad |= out[i]; }
+	if (bad < 0) throw invalid_argument("read '" + read.id + "' holds a character outside the nucleotide alphabet");
 	hb.offsets.push_back((int64_t) hb.codes.size());
 	for (int i = 0; i < 2; ++i) {
 		hu_vpath v = {0, 0, 0, 0, 0, 0};

@@ -1,6 +1,7 @@
 // Host-side C++ layer: formats, alphabet, FASTA/FASTQ, the CSFM seed index and the reference's class surface
 // over the C ABI.  See hu_host.h.  Citations are relative to /root/reference/src.
 #include "hu_host.h"
+#include <atomic>
 
 #include <pthread.h>
 
@@ -276,13 +277,13 @@ int32_t CSFMIndex::occ(int b, int32_t i) const { // symbols b in BWT[0..i]: one 
 }
 
 // backward search, src/CSFMIndex.cpp:79-99 / 121-135: [start, end] in SA coordinates
-bool CSFMIndex::search(const string& pattern, int32_t& start, int32_t& end) const {
-	if (pattern.empty() || rank.empty()) return false;
+bool CSFMIndex::search(const char* pattern, size_t len, int32_t& start, int32_t& end) const {
+	if (len == 0 || rank.empty()) return false;
 	start = 0;
 	end = concatLen;
 	bool first = true;
-	for (string::const_reverse_iterator c = pattern.rbegin(); c != pattern.rend() && start <= end; ++c) {
-		const int8_t e = DNA::encode(*c);
+	for (const char* c = pattern + len; c != pattern && start <= end;) {
+		const int8_t e = DNA::encode(*--c);
 		if (e < 0) return false;
 		const int b = e + 1;
 		if (first) {
@@ -899,63 +900,133 @@ vector<BandedHMMP7::ViterbiAlignPath> findSeeds(const BandedHMMP7& hmm, const CS
 }
 
 namespace {
-struct SeedIntervals { // phase 1 of findSeedsBatch: intervals of the attempts at each end, in attempt order
-	vector<pair<int32_t, int32_t> > at5, at3; // (1, 0) = empty interval
+// Phase 1 of findSeedsBatch: the intervals of the attempts at each end of a read, in attempt order, (1, 0) = empty interval.
+// They live in ONE flat array that the calling thread owns and keeps between batches (maxAtt slots per read and end): the
+// worker threads allocate nothing and touch no fresh pages -- with a vector per read the page faults and heap growth of eight
+// threads serialised in the kernel (one address space), and eight threads were no faster than one.
+typedef pair<int32_t, int32_t> SaRange;
+struct SeedIntervals {
+	const SaRange* at5; const SaRange* at3;
+	int n5, n3;
 };
-void speculate(const CSFMIndex& csfm, const PrimarySeq& read, int seedLen, int seedRegion, BandedHMMP7::align_mode mode, SeedIntervals& si) {
+void speculate(const CSFMIndex& csfm, const PrimarySeq& read, int seedLen, int seedRegion, BandedHMMP7::align_mode mode, SaRange* at5, SaRange* at3,
+		int maxAtt, SeedIntervals& si) {
 	const int N = (int) read.length();
 	const int regionLen = seedRegion < N ? seedRegion : N;
 	int32_t s, e;
-	for (int seedFrom = 0; seedFrom + seedLen - 1 < regionLen; ++seedFrom) {
-		const bool hit = csfm.interval(read.getSeq().substr(seedFrom, seedLen), s, e);
-		si.at5.push_back(hit ? make_pair(s, e) : make_pair((int32_t) 1, (int32_t) 0));
+	si.at5 = at5; si.at3 = at3; si.n5 = si.n3 = 0;
+	for (int seedFrom = 0; seedFrom + seedLen - 1 < regionLen && si.n5 < maxAtt; ++seedFrom) {
+		const bool hit = csfm.interval(read.getSeq().data() + seedFrom, (size_t) seedLen, s, e);
+		at5[si.n5++] = hit ? make_pair(s, e) : make_pair((int32_t) 1, (int32_t) 0);
 		if (hit) break; // nearly always the seed that is kept
 	}
 	if (mode != BandedHMMP7::GLOBAL) return;
-	for (int seedTo = N - 1; seedTo - seedLen + 1 >= N - regionLen; --seedTo) {
+	for (int seedTo = N - 1; seedTo - seedLen + 1 >= N - regionLen && si.n3 < maxAtt; --seedTo) {
 		const int seedFrom = seedTo - seedLen + 1;
 		if (seedFrom < 0) break;
-		const bool hit = csfm.interval(read.getSeq().substr(seedFrom, seedLen), s, e);
-		si.at3.push_back(hit ? make_pair(s, e) : make_pair((int32_t) 1, (int32_t) 0));
+		const bool hit = csfm.interval(read.getSeq().data() + seedFrom, (size_t) seedLen, s, e);
+		at3[si.n3++] = hit ? make_pair(s, e) : make_pair((int32_t) 1, (int32_t) 0);
 		if (hit) break;
 	}
 }
 // locateOne() with the interval taken from phase 1 when it has it
-CSLoc locateCached(const CSFMIndex& csfm, const string& pattern, const vector<pair<int32_t, int32_t> >& cache, size_t attempt) {
+CSLoc locateCached(const CSFMIndex& csfm, const string& seq, int from, int len, const SaRange* cache, int nCached, size_t attempt) {
 	int32_t s, e;
-	if (attempt < cache.size()) { s = cache[attempt].first; e = cache[attempt].second; }
-	else if (!csfm.interval(pattern, s, e)) return CSLoc();
+	if (attempt < (size_t) nCached) { s = cache[attempt].first; e = cache[attempt].second; }
+	else if (!csfm.interval(seq.data() + from, (size_t) len, s, e)) return CSLoc();
 	if (s > e) return CSLoc();
-	return csfm.locateAt(pattern, s, e);
+	return csfm.locateAt(seq.substr(from, len), s, e); // the pattern as a string only for the attempt that hits
 }
 struct SpecArgs {
-	const CSFMIndex* csfm; const vector<const PrimarySeq*>* reads; vector<SeedIntervals>* out;
-	int seedLen, seedRegion; BandedHMMP7::align_mode mode; size_t begin, end;
+	const CSFMIndex* csfm; const vector<const PrimarySeq*>* reads; SeedIntervals* out; SaRange* flat;
+	int seedLen, seedRegion, maxAtt; BandedHMMP7::align_mode mode; size_t n;
+	std::atomic<size_t>* next; // reads are handed out 64 at a time: a thread that loses its core holds up 64 reads, not an eighth of the batch
 };
 void* specThread(void* p) {
-	SpecArgs* a = (SpecArgs*) p;
-	for (size_t i = a->begin; i < a->end; ++i) speculate(*a->csfm, *(*a->reads)[i], a->seedLen, a->seedRegion, a->mode, (*a->out)[i]);
+	const SpecArgs* a = (const SpecArgs*) p;
+	for (;;) {
+		const size_t b = a->next->fetch_add(64);
+		if (b >= a->n) break;
+		const size_t e = b + 64 < a->n ? b + 64 : a->n;
+		for (size_t i = b; i < e; ++i)
+			speculate(*a->csfm, *(*a->reads)[i], a->seedLen, a->seedRegion, a->mode, a->flat + 2 * i * (size_t) a->maxAtt, a->flat + (2 * i + 1) * (size_t) a->maxAtt,
+			          a->maxAtt, a->out[i]);
+	}
 	return NULL;
 }
+
+// Worker threads that live as long as the process: a batch is some tens of milliseconds of work, and threads created per batch
+// spend that long being created, scheduled and spread over the cores (measured: eight fresh threads were no faster than one).
+class SpecPool {
+public:
+	SpecPool() : job(NULL), gen(0), pending(0) { pthread_mutex_init(&mu, NULL); pthread_cond_init(&work, NULL); pthread_cond_init(&done, NULL); pthread_mutex_init(&callers, NULL); }
+	// runs specThread(&a) on nThreads threads (the caller is one of them) and returns when all are through
+	void run(const SpecArgs& a, int nThreads) {
+		pthread_mutex_lock(&callers); // one batch at a time
+		pthread_mutex_lock(&mu);
+		while ((int) th.size() < nThreads - 1) {
+			pthread_t t;
+			Start* st = new Start; st->pool = this; st->seen = gen;
+			if (pthread_create(&t, NULL, loop, st) != 0) { delete st; break; }
+			pthread_detach(t);
+			th.push_back(t);
+		}
+		const int helpers = min((int) th.size(), nThreads - 1);
+		job = &a; quota = helpers; pending = helpers; gen++;
+		pthread_cond_broadcast(&work);
+		pthread_mutex_unlock(&mu);
+		specThread((void*) &a);
+		pthread_mutex_lock(&mu);
+		while (pending > 0) pthread_cond_wait(&done, &mu);
+		job = NULL;
+		pthread_mutex_unlock(&mu);
+		pthread_mutex_unlock(&callers);
+	}
+private:
+	struct Start { SpecPool* pool; unsigned long seen; };
+	static void* loop(void* p) {
+		Start* st = (Start*) p;
+		SpecPool* self = st->pool;
+		unsigned long seen = st->seen;
+		delete st;
+		for (;;) {
+			pthread_mutex_lock(&self->mu);
+			while (self->gen == seen || self->quota <= 0) { if (self->gen != seen) seen = self->gen; pthread_cond_wait(&self->work, &self->mu); }
+			seen = self->gen;
+			self->quota--; // this thread takes one of the batch's helper slots
+			const SpecArgs* a = self->job;
+			pthread_mutex_unlock(&self->mu);
+			specThread((void*) a);
+			pthread_mutex_lock(&self->mu);
+			if (--self->pending == 0) pthread_cond_signal(&self->done);
+			pthread_mutex_unlock(&self->mu);
+		}
+		return NULL;
+	}
+	pthread_mutex_t mu, callers;
+	pthread_cond_t work, done;
+	vector<pthread_t> th;
+	const SpecArgs* job;
+	unsigned long gen;
+	int quota, pending;
+};
+SpecPool& specPool() { static SpecPool* p = new SpecPool; return *p; } // never destroyed: its threads outlive main()'s statics
 }
 
 vector<vector<BandedHMMP7::ViterbiAlignPath> > findSeedsBatch(const BandedHMMP7& hmm, const CSFMIndex& csfm,
 		const vector<const PrimarySeq*>& reads, int seedLen, int seedRegion, BandedHMMP7::align_mode mode, int nThreads) {
 	const size_t n = reads.size();
-	vector<SeedIntervals> spec(n);
+	const int maxAtt = max(1, seedRegion - seedLen + 1); // attempts per end: one per seed start inside the region
+	static thread_local vector<SaRange> flat;            // kept (and its pages with it) from batch to batch
+	static thread_local vector<SeedIntervals> spec;
+	if (flat.size() < 2 * n * (size_t) maxAtt) flat.resize(2 * n * (size_t) maxAtt);
+	if (spec.size() < n) spec.resize(n);
 	// phase 1: no random draws, any order
 	nThreads = max(1, min(nThreads, (int) ((n + 63) / 64)));
-	vector<SpecArgs> args(nThreads);
-	vector<pthread_t> th(nThreads);
-	for (int t = 0; t < nThreads; ++t) {
-		SpecArgs a = {&csfm, &reads, &spec, seedLen, seedRegion, mode, n * t / nThreads, n * (t + 1) / nThreads};
-		args[t] = a;
-	}
-	for (int t = 1; t < nThreads; ++t)
-		if (pthread_create(&th[t], NULL, specThread, &args[t]) != 0) { specThread(&args[t]); th[t] = pthread_self(); }
-	specThread(&args[0]);
-	for (int t = 1; t < nThreads; ++t)
-		if (!pthread_equal(th[t], pthread_self())) pthread_join(th[t], NULL);
+	std::atomic<size_t> next(0);
+	const SpecArgs job = {&csfm, &reads, spec.data(), flat.data(), seedLen, seedRegion, maxAtt, mode, n, &next};
+	if (nThreads > 1) specPool().run(job, nThreads);
+	else specThread((void*) &job);
 	// phase 2: findSeeds' control flow, read by read, rand() drawn as the one-by-one loop draws it
 	vector<vector<BandedHMMP7::ViterbiAlignPath> > out(n);
 	for (size_t r = 0; r < n; ++r) {
@@ -966,7 +1037,7 @@ vector<vector<BandedHMMP7::ViterbiAlignPath> > findSeedsBatch(const BandedHMMP7&
 		size_t attempt = 0;
 		for (int seedFrom = 0; seedFrom + seedLen - 1 < regionLen; ++seedFrom, ++attempt) { // 5' seed
 			const int seedTo = seedFrom + seedLen - 1;
-			const CSLoc loc = locateCached(csfm, read.getSeq().substr(seedFrom, seedLen), spec[r].at5, attempt);
+			const CSLoc loc = locateCached(csfm, read.getSeq(), seedFrom, seedLen, spec[r].at5, spec[r].n5, attempt);
 			if (loc.isValid()) {
 				const BandedHMMP7::ViterbiAlignPath vp = hmm.buildAlignPath(loc, seedFrom + 1, seedTo + 1);
 				if (vp.isValid()) { vpaths.push_back(vp); break; }
@@ -977,7 +1048,7 @@ vector<vector<BandedHMMP7::ViterbiAlignPath> > findSeedsBatch(const BandedHMMP7&
 			for (int seedTo = N - 1; seedTo - seedLen + 1 >= N - regionLen; --seedTo, ++attempt) {
 				const int seedFrom = seedTo - seedLen + 1;
 				if (seedFrom < 0) break;
-				const CSLoc loc = locateCached(csfm, read.getSeq().substr(seedFrom, seedLen), spec[r].at3, attempt);
+				const CSLoc loc = locateCached(csfm, read.getSeq(), seedFrom, seedLen, spec[r].at3, spec[r].n3, attempt);
 				if (loc.isValid()) {
 					const BandedHMMP7::ViterbiAlignPath vp = hmm.buildAlignPath(loc, seedFrom + 1, seedTo + 1);
 					if (vp.isValid()) { vpaths.push_back(vp); break; }

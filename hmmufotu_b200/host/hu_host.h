@@ -103,6 +103,7 @@ public:
 	// locateOne() in two halves, so that the backward searches of a batch of reads can run on many threads while the
 	// rand() picks stay in file order: the SA interval of a pattern (no random draw) ...
 	bool interval(const std::string& pattern, int32_t& start, int32_t& end) const { return search(pattern, start, end); }
+	bool interval(const char* pattern, size_t len, int32_t& start, int32_t& end) const { return search(pattern, len, start, end); } // no temporary string (the batch search calls this ~30 times per read)
 	// ... and the random hit inside a non-empty interval (the rand() call and what follows it in locateOne)
 	CSLoc locateAt(const std::string& pattern, int32_t start, int32_t end) const;
 	// <db>.csfm as the reference's hmmufotu loads it (src/CSFMIndex.cpp:176-230): the index in libcds' serialisation --
@@ -115,7 +116,8 @@ public:
 	std::istream& load(std::istream& in);
 	bool operator==(const CSFMIndex& o) const;
 private:
-	bool search(const std::string& pattern, int32_t& start, int32_t& end) const;
+	bool search(const std::string& pattern, int32_t& start, int32_t& end) const { return search(pattern.data(), pattern.length(), start, end); }
+	bool search(const char* pattern, size_t len, int32_t& start, int32_t& end) const;
 	int32_t occ(int b, int32_t i) const;           // # of symbol b in BWT[0..i]
 	std::string extractCS(int32_t start, const std::string& pattern) const; // src/CSFMIndex.cpp:262-273
 	int csLen;
