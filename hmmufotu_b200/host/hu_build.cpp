@@ -415,6 +415,7 @@ istream& CSFMIndex::load(istream& in) {
 		rb.mask[b] |= 1ull << (i % 64);
 		run[b]++;
 	}
+	buildQTable();
 	// the suffix array from the BWT: the lone terminator is the smallest suffix (row 0, text position N - 1); an LF step
 	// leads from the row of position p to the row of position p - 1
 	// leads from the row of position p to the row of position p - 1.  Separators and the terminator share symbol 0, for

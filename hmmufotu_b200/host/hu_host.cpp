@@ -266,6 +266,7 @@ CSFMIndex& CSFMIndex::build(const MSA& msa) {
 		run[b]++;
 	}
 	for (int32_t i = 0; i < N; ++i) sa[i] += 1; // the reference's SA holds 1-based text positions
+	buildQTable();
 	return *this;
 }
 
@@ -276,13 +277,51 @@ int32_t CSFMIndex::occ(int b, int32_t i) const { // symbols b in BWT[0..i]: one 
 	return (int32_t) (rb.cnt[b] + __builtin_popcountll(rb.mask[b] & (r == 63 ? ~0ull : ((1ull << (r + 1)) - 1ull))));
 }
 
+// The first qlen steps of every backward search, tabulated: most attempts of the seed search die within log4(text length) steps
+// (a 20-mer with one mismatch near its end matches nothing), so one table lookup settles them.  qlen = that many symbols, at
+// most 11 (33 MB).  Depth-first over the q-mers, last symbol first, with the interval carried along; empty branches stay empty.
+void CSFMIndex::fillQ(int depth, size_t idx, int32_t start, int32_t end) {
+	for (int b = 1; b <= 4; ++b) {
+		int32_t s2, e2;
+		if (depth == 0) { s2 = C[b]; e2 = C[b + 1] - 1; }
+		else { s2 = C[b] + occ(b, start - 1); e2 = C[b] + occ(b, end) - 1; }
+		if (s2 > e2) continue;
+		const size_t id2 = idx * 4 + (size_t) (b - 1);
+		if (depth + 1 == qlen) { qtab[2 * id2] = s2; qtab[2 * id2 + 1] = e2; }
+		else fillQ(depth + 1, id2, s2, e2);
+	}
+}
+void CSFMIndex::buildQTable() {
+	qlen = 0;
+	qtab.clear();
+	if (rank.empty() || concatLen < 256) return;
+	int q = 1;
+	for (long long v = 4; v < concatLen && q < 11; v *= 4) q++;
+	qlen = q;
+	qtab.assign((size_t) 2 << (2 * q), 0);
+	for (size_t i = 0; i < qtab.size(); i += 2) qtab[i] = 1; // (1, 0): no match
+	fillQ(0, 0, 0, 0);
+}
+
 // backward search, src/CSFMIndex.cpp:79-99 / 121-135: [start, end] in SA coordinates
 bool CSFMIndex::search(const char* pattern, size_t len, int32_t& start, int32_t& end) const {
 	if (len == 0 || rank.empty()) return false;
 	start = 0;
 	end = concatLen;
 	bool first = true;
-	for (const char* c = pattern + len; c != pattern && start <= end;) {
+	const char* c = pattern + len;
+	if (qlen > 0 && len >= (size_t) qlen) { // the last qlen symbols from the table
+		size_t idx = 0;
+		for (int k = 0; k < qlen; ++k) {
+			const int8_t e = DNA::encode(*--c);
+			if (e < 0) return false; // the plain loop would meet this symbol, or run out of matches before it: false either way
+			idx = idx * 4 + (size_t) e;
+		}
+		start = qtab[2 * idx];
+		end = qtab[2 * idx + 1];
+		first = false;
+	}
+	for (; c != pattern && start <= end;) {
 		const int8_t e = DNA::encode(*--c);
 		if (e < 0) return false;
 		const int b = e + 1;

@@ -92,7 +92,7 @@ struct MSA {                                       // src/MSA.{h,cpp}: only what
 // hence locateOne()'s rand() pick, are the reference's).
 class CSFMIndex {
 public:
-	CSFMIndex() : csLen(0), concatLen(0) {}
+	CSFMIndex() : csLen(0), concatLen(0), qlen(0) {}
 	CSFMIndex& build(const MSA& msa);              // src/CSFMIndex.cpp:232-368
 	int getCSLen() const { return csLen; }
 	int32_t getConcatLen() const { return concatLen; }
@@ -128,6 +128,10 @@ private:
 		uint64_t mask[5];
 	};
 	std::vector<RankBlock> rank;                   // BWT symbols 0..4 (0 = separator / terminator)
+	int qlen;                                      // the backward search of every qlen-mer, tabulated (0: no table)
+	std::vector<int32_t> qtab;                     // [4^qlen][2]: SA interval of the qlen-mer whose LAST symbol is the most significant digit; start > end: none
+	void buildQTable();                            // called when the rank blocks are made (build(), load())
+	void fillQ(int depth, size_t idx, int32_t start, int32_t end);
 	std::vector<int32_t> sa;                       // full suffix array (1-based text positions as in the reference)
 	std::vector<uint16_t> concat2CS;               // 1-based text position -> 1-based consensus column (0: separator)
 };
